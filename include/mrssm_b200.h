@@ -1,0 +1,204 @@
+/* mrssm_b200.h — C ABI of the B200-native MRSSM training hot path.
+ *
+ * The reference (EmergentSystemLabStudent/Multimodal-RSSM) has no FFI: its boundary for this path
+ * is a set of duck-typed PyTorch modules.  Each entry point below replaces the
+ * library-kernel work those modules reach through PyTorch; the reference call site is cited on
+ * every declaration (paths relative to the reference root).  The Python host side in
+ * multimodal-rssm_b200/{algos,utils} mirrors the reference modules and binds these symbols with
+ * ctypes (multimodal-rssm_b200/mrssm_b200/_lib.py); INTEGRATION.md shows the stub a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *  - All data pointers are DEVICE pointers unless the name ends in _host.  No torch types.
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *  - Every function returns 0 on success, non-zero on failure; mrssm_last_error() then returns a
+ *    thread-local human readable message.  Nothing falls back to the CPU.
+ *  - Tensors are addressed by (pointer, 4 element strides) so NCHW (reference layout) and NHWC
+ *    (internal layout) are both first class.
+ *  - dtype: MRSSM_F32 tensors are float; MRSSM_BF16 tensors are __nv_bfloat16 (tensor-core mode).
+ */
+#ifndef MRSSM_B200_H
+#define MRSSM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRSSM_ABI_VERSION 1
+
+enum { MRSSM_ACT_NONE = 0, MRSSM_ACT_RELU = 1, MRSSM_ACT_ELU = 2 };
+enum { MRSSM_F32 = 0, MRSSM_BF16 = 1 };
+#define MRSSM_MAX_HEADS 5   /* prior + prior_expert + up to 3 modality experts */
+#define MRSSM_MAX_SUBSETS 8 /* 2^3 */
+#define MRSSM_MAX_STATE 256
+
+const char* mrssm_last_error(void);
+int mrssm_abi_version(void);
+/* 1 if the loaded library carries sm_100a code and a CUDA device of capability 10.x is present */
+int mrssm_device_ok(void);
+
+/* ---- strided 4-D tensor view: element (i,h,w,c) at ptr[i*sI + h*sH + w*sW + c*sC] ---------- */
+typedef struct mrssm_t4 {
+    void* ptr;
+    int64_t sI, sH, sW, sC;
+} mrssm_t4;
+
+/* ---- convolution family --------------------------------------------------------------------
+ * One geometry describes nn.Conv2d(k, stride 2) and nn.ConvTranspose2d(k, stride 2) alike:
+ * a "large" tensor [n_img,Hl,Wl,Cl] and a "small" tensor [n_img,Hs,Ws,Cs], Hl = 2*(Hs-1)+ksz,
+ * and a weight W[cs][cl][kh][kw] at weight[cs*w_ss + cl*w_sl + kh*ksz + kw] — which is exactly
+ * Conv2d.weight [Cout=Cs,Cin=Cl,k,k] and ConvTranspose2d.weight [Cin=Cs,Cout=Cl,k,k].
+ * nn.Linear is the case Hl=Wl=Hs=Ws=ksz=1 (weight [out=Cs,in=Cl]).
+ *   down : small = act(bias + sum_{kh,kw,cl} large[2hs+kh,2ws+kw,cl] * W)   Conv2d fwd, ConvT dgrad, Linear fwd
+ *   up   : large = act(bias + sum_{kh,kw,cs} small[hs,ws,cs] * W)           ConvT fwd, Conv2d dgrad, Linear dgrad
+ *   wgrad: dW   += sum_{img,hs,ws} small * large ; dbias += colsum           all weight gradients
+ * Replaces: encoder.py:315-322 (ImageEncoder convs), :423-432 (128x128), :287-296 (SymbolicEncoder),
+ * observation_model.py:65-74,99-102 (ImageDecoder), :172-181 (128x128), :37-51 (DenseDecoder),
+ * encoder.py:136-141,172-176 (the time-parallel half of the expert heads) and their autograd.
+ */
+typedef struct mrssm_conv_args {
+    int32_t n_img, Hl, Wl, Cl, Hs, Ws, Cs, ksz;
+    int32_t dtype;        /* MRSSM_F32 | MRSSM_BF16 (activations); weights/bias are always f32 masters */
+    int32_t act;          /* epilogue activation (down/up) */
+    int32_t mask_mode;    /* epilogue multiply by act'(mask): MRSSM_ACT_*; mask has the output's strides */
+    int32_t accumulate;   /* down/up: out = mask * act(out_old + result + bias) */
+    mrssm_t4 large, small;
+    float* weight;        /* down/up: input; wgrad: output (accumulated) */
+    int64_t w_ss, w_sl;
+    float* bias;          /* down/up: input or NULL; wgrad: dbias output (accumulated) or NULL */
+    void* mask;           /* or NULL */
+} mrssm_conv_args;
+
+int mrssm_conv_down(const mrssm_conv_args* a, void* stream);
+int mrssm_conv_up(const mrssm_conv_args* a, void* stream);
+int mrssm_conv_wgrad(const mrssm_conv_args* a, void* stream);
+/* bias gradient of a ConvTranspose2d: a->bias[cl] += sum over (img,h,w) of a->large (observation_model.py:65-74 autograd) */
+int mrssm_colsum_t4(const mrssm_conv_args* a, void* stream);
+
+/* ---- the RSSM rollout ------------------------------------------------------------------------
+ * Replaces MultimodalTransitionModel.forward (utils/models/transition_model.py:200-285), its
+ * single-modal twin TransitionModel.forward (:50-114), nn.GRUCell (:160,235), the prior head and
+ * the expert heads (encoder.py:126-155,157-190,196-224), poe/get_poe_state/get_mopoe_state
+ * (encoder.py:50-124) and the rsample calls, as ONE launch for all T steps.  n_experts = 0 is the
+ * open-loop imagination mode (transition_model.py:226-245 with observations=None).
+ *
+ * Layout: every [T,B,x] tensor is time-major contiguous.  Head 0 is the transition prior
+ * (stochastic_state_model); heads 1..n_experts are the experts in dict order (prior_expert first
+ * for the multimodal model).  Weights arrive pre-transposed ([in][out]) for the forward and in
+ * PyTorch layout ([out][in]) for the backward; w1 covers only the belief columns of fc1 — the
+ * embedding columns are hoisted into emb_pre (time-parallel GEMM, bias folded in).
+ */
+typedef struct mrssm_rollout_args {
+    int32_t T, B, D, S, H, A, n_experts;
+    int32_t act, det;
+    float min_std;
+    /* inputs */
+    const float *prev_state, *prev_belief, *actions, *nonterminals, *eps_prior, *eps_post;
+    const float* emb_pre[MRSSM_MAX_HEADS];      /* [T,B,H] per head or NULL (index = head) */
+    /* weights: fwd uses *_t ([in][out]); bwd uses PyTorch layout */
+    const float *w_sa, *b_sa;                   /* [S+A][D] (fwd) / [D][S+A] (bwd) */
+    const float *w_ih, *b_ih, *w_hh, *b_hh;     /* [D][3D] (fwd) / [3D][D] (bwd) */
+    const float* w1[MRSSM_MAX_HEADS];           /* [D][H] (fwd) / [H][ld1] (bwd) */
+    int64_t ld1[MRSSM_MAX_HEADS];               /* bwd: row stride of w1 (= D or D+E_m) */
+    const float* b1[MRSSM_MAX_HEADS];           /* NULL when folded into emb_pre */
+    const float* w2[MRSSM_MAX_HEADS];           /* [H][2S] (fwd) / [2S][H] (bwd) */
+    const float* b2[MRSSM_MAX_HEADS];
+    /* fusion table (encoder.py:73-124): subset j = bitmask over experts (bit e-1 = head e) */
+    int32_t n_subsets;
+    uint32_t subset_mask[MRSSM_MAX_SUBSETS];
+    uint8_t dim_subset[MRSSM_MAX_STATE];        /* which subset supplies state dim s */
+    /* outputs [T,B,*] */
+    float *beliefs, *prior_states, *prior_means, *prior_stds;
+    float *post_states, *post_means, *post_stds;
+    float* exp_means[MRSSM_MAX_HEADS];          /* index = head (1..n_experts) */
+    float* exp_stds[MRSSM_MAX_HEADS];
+    /* stash for BPTT (all NULL for inference): x,r,z,n,ghn [T,B,D]; u[head] [T,B,H] */
+    float *st_x, *st_r, *st_z, *st_n, *st_ghn;
+    float* st_u[MRSSM_MAX_HEADS];
+} mrssm_rollout_args;
+
+int mrssm_rollout_fwd(const mrssm_rollout_args* a, void* stream);
+
+/* BPTT through the rollout (autograd of transition_model.py:226-270).  Consumes the forward's
+ * outputs/stash plus upstream gradients of every output; produces the data gradients and the
+ * per-step pre-activation gradients from which all weight gradients follow as time-parallel
+ * mrssm_conv_wgrad calls (deferred wgrad). */
+typedef struct mrssm_rollout_bwd_args {
+    mrssm_rollout_args f;                       /* same shapes/weights (PyTorch layout)/outputs/stash */
+    /* upstream grads, [T,B,*], any may be NULL (= zero) */
+    const float *g_beliefs, *g_prior_states, *g_prior_means, *g_prior_stds;
+    const float *g_post_states, *g_post_means, *g_post_stds;
+    const float* g_exp_means[MRSSM_MAX_HEADS];
+    const float* g_exp_stds[MRSSM_MAX_HEADS];
+    /* outputs */
+    float *g_prev_state, *g_prev_belief;        /* [B,S], [B,D] */
+    float* g_actions;                           /* [T,B,A] */
+    float *d_xpre;                              /* [T,B,D]  grad wrt fc_embed pre-activation */
+    float *d_gi, *d_gh;                         /* [T,B,3D] grad wrt W_ih x+b_ih and W_hh h+b_hh */
+    float* d_u[MRSSM_MAX_HEADS];                /* [T,B,H]  grad wrt fc1 pre-activation (also = grad of emb_pre) */
+    float* d_o[MRSSM_MAX_HEADS];                /* [T,B,2S] grad wrt fc2 output */
+    float* xin;                                 /* [T,B,S+A] the masked [state,action] input, recomputed */
+} mrssm_rollout_bwd_args;
+
+int mrssm_rollout_bwd(const mrssm_rollout_bwd_args* a, void* stream);
+
+/* ---- latent part of the ELBO -------------------------------------------------------------------
+ * Replaces _get_posterior_states (MRSSM_PoE/algo.py:63-68, MRSSM_MoPoE/algo.py:62-67, base/algo.py:
+ * 157-163), _calc_kl (base/algo.py:75-94), _calc_mopoe_kl (MRSSM_MoPoE/algo.py:110-137) and the
+ * global KL (base/algo.py:186-188).  rows = (T-1)*B.
+ *   kl_mode 0: balanced KL on (post_means,post_stds)   [RSSM, NN, PoE]
+ *   kl_mode 1: MoPoE subset-averaged KL on the experts [MoPoE]
+ *   refuse   : recompute the fused posterior from the experts and draw z = mu + sigma*eps_dec
+ *              (PoE/MoPoE); otherwise z/q are the rollout's own posterior tensors.
+ * out_sums[0] = kl_loss, out_sums[1] = global KL term (un-weighted), both already averaged. */
+typedef struct mrssm_latent_args {
+    int32_t rows, S, n_experts, kl_mode, refuse;
+    int32_t n_subsets;
+    uint32_t subset_mask[MRSSM_MAX_SUBSETS];
+    uint8_t dim_subset[MRSSM_MAX_STATE];
+    float free_nats, alpha;                     /* alpha < 0: no balancing */
+    const float *prior_means, *prior_stds, *post_means, *post_stds, *eps_dec;
+    const float* exp_means[MRSSM_MAX_HEADS];    /* index 1..n_experts */
+    const float* exp_stds[MRSSM_MAX_HEADS];
+    float *z_dec, *q_means, *q_stds;            /* [rows,S] outputs when refuse */
+    float* row_scratch;                         /* [2*rows] */
+    float* out_sums;                            /* [2] */
+    /* backward only */
+    const float *g_sums;                        /* [2] upstream grads of out_sums (device) */
+    const float *g_z;                           /* [rows,S] or NULL */
+    float *g_prior_means, *g_prior_stds, *g_post_means, *g_post_stds;
+    float* g_exp_means[MRSSM_MAX_HEADS];
+    float* g_exp_stds[MRSSM_MAX_HEADS];
+} mrssm_latent_args;
+
+int mrssm_latent_fwd(const mrssm_latent_args* a, void* stream);
+int mrssm_latent_bwd(const mrssm_latent_args* a, void* stream);
+
+/* ---- reconstruction loss: sum_features mean_{t,b} (y-o)^2  (observation_model.py:28-31,
+ * base/algo.py:381-383).  n = element count, rows = (T-1)*B.  fwd writes *out; bwd writes
+ * dy = (*g) * 2 (y-o) / rows. */
+int mrssm_mse_fwd(const float* y, const float* o, int64_t n, int64_t rows, float* partial, float* out, void* stream);
+int mrssm_mse_bwd(const float* y, const float* o, int64_t n, int64_t rows, const float* g, float* dy, void* stream);
+/* elementwise (y-o)^2 for the get_mse API (observation_model.py:28-31) */
+int mrssm_sqdiff(const float* y, const float* o, int64_t n, float* out, void* stream);
+
+/* ---- optimiser: clip_grad_norm_(max_norm, L2) + Adam, no host sync (base/algo.py:41-42,258-259).
+ * One flat parameter/gradient/moment buffer.  norm_out[0] receives the pre-clip total norm. */
+int mrssm_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr,
+                    float beta1, float beta2, float eps, float max_norm, float grad_scale,
+                    float* partial, float* norm_out, void* stream);
+
+/* ---- small helpers ---- */
+int mrssm_transpose(const float* src, int64_t rows, int64_t cols, int64_t src_ld, float* dst, void* stream);
+int mrssm_concat2(const float* a, int64_t ca, const float* b, int64_t cb, int64_t rows, float* out, void* stream);
+int mrssm_colsum_acc(const float* x, int64_t rows, int64_t cols, int64_t ld, float* out, void* stream);
+int mrssm_fill(float* p, int64_t n, float v, void* stream);
+/* out = g * act'(y) with the derivative expressed through the activation OUTPUT y */
+int mrssm_act_bwd(const float* g, const float* y, int64_t n, int32_t act, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRSSM_B200_H */

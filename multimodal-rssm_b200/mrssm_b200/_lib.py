@@ -1,0 +1,174 @@
+"""ctypes binding of lib/libmrssm_b200.so (include/mrssm_b200.h).
+
+There is no CPU or eager-PyTorch fallback: if the shared library is missing, or the device is not
+an sm_100 part, every op raises.  The library is built in-tree by ``__graft_entry__.build()``
+(``make -C multimodal-rssm_b200/csrc``).
+"""
+import ctypes as C
+import os
+
+import torch
+
+MAX_HEADS = 5
+MAX_SUBSETS = 8
+MAX_STATE = 256
+ACT = {None: 0, "none": 0, "relu": 1, "elu": 2}
+F32, BF16 = 0, 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmrssm_b200.so")
+
+_f32p = C.POINTER(C.c_float)
+_vp = C.c_void_p
+
+
+class T4(C.Structure):
+    _fields_ = [("ptr", _vp), ("sI", C.c_int64), ("sH", C.c_int64), ("sW", C.c_int64), ("sC", C.c_int64)]
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_img", "Hl", "Wl", "Cl", "Hs", "Ws", "Cs", "ksz", "dtype", "act",
+                                         "mask_mode", "accumulate")] + [
+        ("large", T4), ("small", T4), ("weight", _vp), ("w_ss", C.c_int64), ("w_sl", C.c_int64),
+        ("bias", _vp), ("mask", _vp)]
+
+
+class RolloutArgs(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("T", "B", "D", "S", "H", "A", "n_experts", "act", "det")] + [
+        ("min_std", C.c_float)] + [(n, _vp) for n in ("prev_state", "prev_belief", "actions", "nonterminals",
+                                                      "eps_prior", "eps_post")] + [
+        ("emb_pre", _vp * MAX_HEADS),
+        ("w_sa", _vp), ("b_sa", _vp), ("w_ih", _vp), ("b_ih", _vp), ("w_hh", _vp), ("b_hh", _vp),
+        ("w1", _vp * MAX_HEADS), ("ld1", C.c_int64 * MAX_HEADS), ("b1", _vp * MAX_HEADS),
+        ("w2", _vp * MAX_HEADS), ("b2", _vp * MAX_HEADS),
+        ("n_subsets", C.c_int32), ("subset_mask", C.c_uint32 * MAX_SUBSETS), ("dim_subset", C.c_uint8 * MAX_STATE),
+        ("beliefs", _vp), ("prior_states", _vp), ("prior_means", _vp), ("prior_stds", _vp),
+        ("post_states", _vp), ("post_means", _vp), ("post_stds", _vp),
+        ("exp_means", _vp * MAX_HEADS), ("exp_stds", _vp * MAX_HEADS),
+        ("st_x", _vp), ("st_r", _vp), ("st_z", _vp), ("st_n", _vp), ("st_ghn", _vp),
+        ("st_u", _vp * MAX_HEADS)]
+
+
+class RolloutBwdArgs(C.Structure):
+    _fields_ = [("f", RolloutArgs)] + [(n, _vp) for n in (
+        "g_beliefs", "g_prior_states", "g_prior_means", "g_prior_stds", "g_post_states", "g_post_means",
+        "g_post_stds")] + [
+        ("g_exp_means", _vp * MAX_HEADS), ("g_exp_stds", _vp * MAX_HEADS),
+        ("g_prev_state", _vp), ("g_prev_belief", _vp), ("g_actions", _vp),
+        ("d_xpre", _vp), ("d_gi", _vp), ("d_gh", _vp),
+        ("d_u", _vp * MAX_HEADS), ("d_o", _vp * MAX_HEADS), ("xin", _vp)]
+
+
+class LatentArgs(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("rows", "S", "n_experts", "kl_mode", "refuse", "n_subsets")] + [
+        ("subset_mask", C.c_uint32 * MAX_SUBSETS), ("dim_subset", C.c_uint8 * MAX_STATE),
+        ("free_nats", C.c_float), ("alpha", C.c_float)] + [(n, _vp) for n in (
+            "prior_means", "prior_stds", "post_means", "post_stds", "eps_dec")] + [
+        ("exp_means", _vp * MAX_HEADS), ("exp_stds", _vp * MAX_HEADS),
+        ("z_dec", _vp), ("q_means", _vp), ("q_stds", _vp), ("row_scratch", _vp), ("out_sums", _vp),
+        ("g_sums", _vp), ("g_z", _vp),
+        ("g_prior_means", _vp), ("g_prior_stds", _vp), ("g_post_means", _vp), ("g_post_stds", _vp),
+        ("g_exp_means", _vp * MAX_HEADS), ("g_exp_stds", _vp * MAX_HEADS)]
+
+
+# every symbol include/mrssm_b200.h declares: name -> argtypes (restype is int unless noted)
+_i64, _i32, _f = C.c_int64, C.c_int32, C.c_float
+SYMBOLS = {
+    "mrssm_last_error": None,
+    "mrssm_abi_version": [],
+    "mrssm_device_ok": [],
+    "mrssm_conv_down": [C.POINTER(ConvArgs), _vp],
+    "mrssm_conv_up": [C.POINTER(ConvArgs), _vp],
+    "mrssm_conv_wgrad": [C.POINTER(ConvArgs), _vp],
+    "mrssm_colsum_t4": [C.POINTER(ConvArgs), _vp],
+    "mrssm_rollout_fwd": [C.POINTER(RolloutArgs), _vp],
+    "mrssm_rollout_bwd": [C.POINTER(RolloutBwdArgs), _vp],
+    "mrssm_latent_fwd": [C.POINTER(LatentArgs), _vp],
+    "mrssm_latent_bwd": [C.POINTER(LatentArgs), _vp],
+    "mrssm_mse_fwd": [_vp, _vp, _i64, _i64, _vp, _vp, _vp],
+    "mrssm_mse_bwd": [_vp, _vp, _i64, _i64, _vp, _vp, _vp],
+    "mrssm_sqdiff": [_vp, _vp, _i64, _vp, _vp],
+    "mrssm_clip_adam": [_vp, _vp, _vp, _vp, _i64, _i32, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp],
+    "mrssm_transpose": [_vp, _i64, _i64, _i64, _vp, _vp],
+    "mrssm_concat2": [_vp, _i64, _vp, _i64, _i64, _vp, _vp],
+    "mrssm_colsum_acc": [_vp, _i64, _i64, _i64, _vp, _vp],
+    "mrssm_fill": [_vp, _i64, _f, _vp],
+    "mrssm_act_bwd": [_vp, _vp, _i64, _i32, _vp, _vp],
+}
+
+_lib = None
+launches = 0          # number of C-ABI compute calls issued (bench.py reports kernel launches from it)
+kernel_launches = 0   # number of CUDA kernels those calls launched
+
+
+def load():
+    """dlopen the library (no GPU needed) and declare prototypes."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, argtypes in SYMBOLS.items():
+            fn = getattr(lib, name)
+            if argtypes is None:
+                fn.restype = C.c_char_p
+                fn.argtypes = []
+            else:
+                fn.restype = C.c_int
+                fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+_dev_checked = False
+
+
+def _require_device():
+    global _dev_checked
+    if not _dev_checked:
+        lib = load()
+        if not torch.cuda.is_available() or not lib.mrssm_device_ok():
+            raise RuntimeError("mrssm_b200 needs an sm_100 (B200) CUDA device; there is no CPU fallback: "
+                               + lib.mrssm_last_error().decode())
+        _dev_checked = True
+
+
+# kernels launched per C-ABI call (for the gpu_launches claim)
+_KERNELS_PER_CALL = {"mrssm_latent_fwd": 2, "mrssm_mse_fwd": 2, "mrssm_clip_adam": 3}
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point on torch's current stream; raise RuntimeError on failure."""
+    global launches, kernel_launches
+    _require_device()
+    lib = load()
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = getattr(lib, name)(*args, stream)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib.mrssm_last_error().decode()}")
+    launches += 1
+    kernel_launches += _KERNELS_PER_CALL.get(name, 1)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  The tensor must be CUDA fp32/bf16."""
+    if t is None:
+        return None
+    assert t.is_cuda, "mrssm_b200 ops take CUDA tensors only"
+    return t.data_ptr()
+
+
+def t4(t, sI, sH, sW, sC):
+    return T4(ptr(t), sI, sH, sW, sC)
+
+
+def nhwc(t, H, W, Cc, pix_stride=None):
+    """View a contiguous [N,H,W,C] (or [N, C] when H=W=1) buffer."""
+    ps = Cc if pix_stride is None else pix_stride
+    return T4(ptr(t), H * W * ps, W * ps, ps, 1)
+
+
+def nchw(t, H, W, Cc):
+    return T4(ptr(t), Cc * H * W, W, 1, H * W)

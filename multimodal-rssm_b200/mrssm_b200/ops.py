@@ -1,0 +1,606 @@
+"""torch.autograd.Function wrappers over the C ABI (include/mrssm_b200.h).
+
+Host-side plumbing only: shapes, workspace allocation (torch caching allocator), stream and the
+autograd chaining.  All arithmetic happens in libmrssm_b200.so.
+
+Parameter gradients are written by the kernels *directly* into ``param.grad`` (accumulated, like
+autograd would), and the Functions return ``None`` for parameter inputs; ``param.grad`` is
+normally a view into the optimiser's flat gradient buffer (optim.FlatParams) so one fused
+clip+Adam launch consumes them.  Use ``loss.backward()``, not ``torch.autograd.grad`` w.r.t.
+parameters.
+"""
+import ctypes as C
+
+import torch
+from torch.autograd import Function
+
+from . import _lib as L
+
+RELU, ELU = 1, 2
+
+
+def _f32c(t):
+    assert t.dtype == torch.float32 and t.is_cuda, (t.dtype, t.device)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def grad_buf(p):
+    """Gradient accumulator of a parameter (created zeroed on first use)."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    return p.grad
+
+
+def _conv(fn, geom, large, small, weight_ptr, w_ss, w_sl, bias_ptr=None, act=0, mask_ptr=None, mask_mode=0,
+          accumulate=0, dtype=L.F32):
+    a = L.ConvArgs(*geom, dtype, act, mask_mode, accumulate, large, small, weight_ptr, w_ss, w_sl, bias_ptr, mask_ptr)
+    L.call(fn, C.byref(a))
+    if fn == "mrssm_conv_wgrad" and bias_ptr:
+        L.kernel_launches += 1
+
+
+def _row_t4(p, ld):
+    """[rows, cols] matrix with row stride ld viewed as n_img=rows, 1x1 spatial."""
+    return L.T4(p, ld, 0, 0, 1)
+
+
+def _off(t, elems):
+    return t.data_ptr() + 4 * elems
+
+
+# ---- dense helpers (nn.Linear semantics, weight [N,K] with row stride ldw) ------------------------
+def dense_fwd(x_ptr, ldx, M, K, w_ptr, ldw, N, b_ptr, act, y_ptr, ldy, accumulate=0):
+    _conv("mrssm_conv_down", (M, 1, 1, K, 1, 1, N, 1), _row_t4(x_ptr, ldx), _row_t4(y_ptr, ldy), w_ptr, ldw, 1,
+          b_ptr, act, None, 0, accumulate)
+
+
+def dense_dgrad(dy_ptr, ldy, M, N, w_ptr, ldw, K, dx_ptr, ldx, mask_ptr=None, mask_mode=0, accumulate=0):
+    _conv("mrssm_conv_up", (M, 1, 1, K, 1, 1, N, 1), _row_t4(dx_ptr, ldx), _row_t4(dy_ptr, ldy), w_ptr, ldw, 1,
+          None, 0, mask_ptr, mask_mode, accumulate)
+
+
+def dense_wgrad(dy_ptr, ldy, x_ptr, ldx, M, N, K, dw_ptr, ldw, db_ptr=None):
+    _conv("mrssm_conv_wgrad", (M, 1, 1, K, 1, 1, N, 1), _row_t4(x_ptr, ldx), _row_t4(dy_ptr, ldy), dw_ptr, ldw, 1,
+          db_ptr)
+
+
+def act_bwd(g, y, act):
+    out = torch.empty_like(y)
+    L.call("mrssm_act_bwd", L.ptr(_f32c(g)), L.ptr(y), y.numel(), act, L.ptr(out))
+    return out
+
+
+def transpose(src_ptr, rows, cols, ld, device):
+    dst = torch.empty(cols, rows, device=device, dtype=torch.float32)
+    L.call("mrssm_transpose", src_ptr, rows, cols, ld, L.ptr(dst))
+    return dst
+
+
+# ---- MLP (SymbolicEncoder / DenseDecoder / RewardModel) ----------------------------------------------
+class MlpFn(Function):
+    """y = L_n(...act(L_1([x_0, x_1, ...]))) with `act` after every layer but the last unless
+    final_act.  Inputs may be several tensors that the reference concatenates (torch.cat([h, s]))."""
+
+    @staticmethod
+    def forward(ctx, act, final_act, n_parts, *args):
+        parts = [_f32c(t) for t in args[:n_parts]]
+        params = args[n_parts:]
+        M = parts[0].shape[0]
+        dev = parts[0].device
+        n_layers = len(params) // 2
+        acts = []
+        cur = None
+        for i in range(n_layers):
+            W, b = params[2 * i], params[2 * i + 1]
+            N, K = W.shape
+            y = torch.empty(M, N, device=dev, dtype=torch.float32)
+            a = act if (i < n_layers - 1 or final_act) else 0
+            if i == 0:
+                col = 0
+                for j, p in enumerate(parts):
+                    kp = p.shape[1]
+                    lastp = j == len(parts) - 1
+                    dense_fwd(L.ptr(p), kp, M, kp, _off(W, col), K, N, L.ptr(b) if lastp else None,
+                              a if lastp else 0, L.ptr(y), N, accumulate=int(j > 0))
+                    col += kp
+                assert col == K
+            else:
+                dense_fwd(L.ptr(cur), K, M, K, L.ptr(W), K, N, L.ptr(b), a, L.ptr(y), N)
+            acts.append(y)
+            cur = y
+        ctx.act, ctx.final_act, ctx.n_parts = act, final_act, n_parts
+        ctx.parts, ctx.acts, ctx.params = parts, acts, params
+        return cur
+
+    @staticmethod
+    def backward(ctx, g):
+        act, parts, acts, params = ctx.act, ctx.parts, ctx.acts, ctx.params
+        n_layers = len(params) // 2
+        M = parts[0].shape[0]
+        g = _f32c(g)
+        if ctx.final_act and act:
+            g = act_bwd(g, acts[-1], act)
+        gparts = [None] * len(parts)
+        for i in reversed(range(n_layers)):
+            W, b = params[2 * i], params[2 * i + 1]
+            N, K = W.shape
+            gW, gb = grad_buf(W), grad_buf(b)
+            if i > 0:
+                x = acts[i - 1]
+                dense_wgrad(L.ptr(g), N, L.ptr(x), K, M, N, K, L.ptr(gW), K, L.ptr(gb))
+                gx = torch.empty_like(x)
+                dense_dgrad(L.ptr(g), N, M, N, L.ptr(W), K, K, L.ptr(gx), K, L.ptr(x) if act else None, act)
+                g = gx
+            else:
+                col = 0
+                for j, p in enumerate(parts):
+                    kp = p.shape[1]
+                    dense_wgrad(L.ptr(g), N, L.ptr(p), kp, M, N, kp, _off(gW, col), K, L.ptr(gb) if j == 0 else None)
+                    if ctx.needs_input_grad[3 + j]:
+                        gp = torch.empty_like(p)
+                        dense_dgrad(L.ptr(g), N, M, N, _off(W, col), K, kp, L.ptr(gp), kp)
+                        gparts[j] = gp
+                    col += kp
+        return (None, None, None, *gparts, *([None] * len(params)))
+
+
+# ---- image encoder: stack of Conv2d(k4,s2)+ReLU ------------------------------------------------------
+class ConvEncoderFn(Function):
+    """[N,C,H,W] fp32 NCHW -> [N, Cout*h*w] flattened in (C,H,W) order (encoder.py:344-346).
+    Intermediates are NHWC."""
+
+    @staticmethod
+    def forward(ctx, x, *params):
+        x = _f32c(x)
+        N, Cc, H, W = x.shape
+        dev = x.device
+        n_layers = len(params) // 2
+        tensors = [(x, L.nchw(x, H, W, Cc))]
+        geoms = []
+        Hl, Wl, Cl = H, W, Cc
+        for i in range(n_layers):
+            Wt, b = params[2 * i], params[2 * i + 1]
+            Cs, _, k, _ = Wt.shape
+            Hs, Ws = (Hl - k) // 2 + 1, (Wl - k) // 2 + 1
+            assert Hl == 2 * (Hs - 1) + k, "image size not compatible with the stride-2 conv stack"
+            if i == n_layers - 1:
+                y = torch.empty(N, Cs * Hs * Ws, device=dev, dtype=torch.float32)
+                yt = L.nchw(y, Hs, Ws, Cs)
+            else:
+                y = torch.empty(N, Hs, Ws, Cs, device=dev, dtype=torch.float32)
+                yt = L.nhwc(y, Hs, Ws, Cs)
+            geom = (N, Hl, Wl, Cl, Hs, Ws, Cs, k)
+            _conv("mrssm_conv_down", geom, tensors[-1][1], yt, L.ptr(Wt), Cl * k * k, k * k, L.ptr(b), RELU)
+            tensors.append((y, yt))
+            geoms.append(geom)
+            Hl, Wl, Cl = Hs, Ws, Cs
+        ctx.tensors, ctx.geoms, ctx.params = tensors, geoms, params
+        return tensors[-1][0]
+
+    @staticmethod
+    def backward(ctx, g):
+        tensors, geoms, params = ctx.tensors, ctx.geoms, ctx.params
+        n_layers = len(geoms)
+        g = act_bwd(g, tensors[-1][0], RELU)
+        gt = L.T4(L.ptr(g), *_strides(tensors[-1][1]))
+        for i in reversed(range(n_layers)):
+            Wt, b = params[2 * i], params[2 * i + 1]
+            geom = geoms[i]
+            Cl, k = geom[3], geom[7]
+            xin, xt = tensors[i]
+            _conv("mrssm_conv_wgrad", geom, xt, gt, L.ptr(grad_buf(Wt)), Cl * k * k, k * k, L.ptr(grad_buf(b)))
+            if i > 0:
+                gx = torch.empty_like(xin)
+                gxt = L.T4(L.ptr(gx), *_strides(xt))
+                _conv("mrssm_conv_up", geom, gxt, gt, L.ptr(Wt), Cl * k * k, k * k, None, 0, L.ptr(xin), RELU)
+                g, gt = gx, gxt
+        return (None, *([None] * len(params)))
+
+
+def _strides(t4):
+    return (t4.sI, t4.sH, t4.sW, t4.sC)
+
+
+# ---- image decoder: fc([h,s]) -> ConvTranspose2d stack ------------------------------------------------
+class ConvDecoderFn(Function):
+    """h [R,D], s [R,S] -> recon [R,C,H,W] NCHW fp32 (observation_model.py:91-105)."""
+
+    @staticmethod
+    def forward(ctx, h, s, *params):
+        h, s = _f32c(h), _f32c(s)
+        R, D = h.shape
+        S = s.shape[1]
+        dev = h.device
+        fcw, fcb = params[0], params[1]
+        Em = fcw.shape[0]
+        y0 = torch.empty(R, Em, device=dev, dtype=torch.float32)
+        dense_fwd(L.ptr(h), D, R, D, L.ptr(fcw), D + S, Em, None, 0, L.ptr(y0), Em)
+        dense_fwd(L.ptr(s), S, R, S, _off(fcw, D), D + S, Em, L.ptr(fcb), 0, L.ptr(y0), Em, accumulate=1)
+        convs = params[2:]
+        n_layers = len(convs) // 2
+        tensors = [(y0, L.nhwc(y0, 1, 1, Em))]
+        geoms = []
+        Hs, Ws, Cs = 1, 1, Em
+        for i in range(n_layers):
+            Wt, b = convs[2 * i], convs[2 * i + 1]
+            _, Cl, k, _ = Wt.shape
+            Hl, Wl = 2 * (Hs - 1) + k, 2 * (Ws - 1) + k
+            last = i == n_layers - 1
+            if last:
+                y = torch.empty(R, Cl, Hl, Wl, device=dev, dtype=torch.float32)
+                yt = L.nchw(y, Hl, Wl, Cl)
+            else:
+                y = torch.empty(R, Hl, Wl, Cl, device=dev, dtype=torch.float32)
+                yt = L.nhwc(y, Hl, Wl, Cl)
+            geom = (R, Hl, Wl, Cl, Hs, Ws, Cs, k)
+            _conv("mrssm_conv_up", geom, yt, tensors[-1][1], L.ptr(Wt), Cl * k * k, k * k, L.ptr(b), 0 if last else RELU)
+            tensors.append((y, yt))
+            geoms.append(geom)
+            Hs, Ws, Cs = Hl, Wl, Cl
+        ctx.h, ctx.s, ctx.tensors, ctx.geoms, ctx.params = h, s, tensors, geoms, params
+        return tensors[-1][0]
+
+    @staticmethod
+    def backward(ctx, g):
+        h, s, tensors, geoms, params = ctx.h, ctx.s, ctx.tensors, ctx.geoms, ctx.params
+        convs = params[2:]
+        n_layers = len(geoms)
+        g = _f32c(g)
+        gt = L.T4(L.ptr(g), *_strides(tensors[-1][1]))
+        for i in reversed(range(n_layers)):
+            Wt, b = convs[2 * i], convs[2 * i + 1]
+            geom = geoms[i]
+            R, Hl, Wl, Cl, Hs, Ws, Cs, k = geom
+            xin, xt = tensors[i]
+            _conv("mrssm_conv_wgrad", geom, gt, xt, L.ptr(grad_buf(Wt)), Cl * k * k, k * k, None)
+            _colsum_t4(gt, R, Hl, Wl, Cl, grad_buf(b))
+            gx = torch.empty_like(xin)
+            gxt = L.T4(L.ptr(gx), *_strides(xt))
+            _conv("mrssm_conv_down", geom, gt, gxt, L.ptr(Wt), Cl * k * k, k * k, None, 0,
+                  L.ptr(xin) if i > 0 else None, RELU if i > 0 else 0)
+            g, gt = gx, gxt
+        fcw, fcb = params[0], params[1]
+        R, D = h.shape
+        S = s.shape[1]
+        Em = fcw.shape[0]
+        gW = grad_buf(fcw)
+        dense_wgrad(L.ptr(g), Em, L.ptr(h), D, R, Em, D, L.ptr(gW), D + S, L.ptr(grad_buf(fcb)))
+        dense_wgrad(L.ptr(g), Em, L.ptr(s), S, R, Em, S, _off(gW, D), D + S, None)
+        gh = gs = None
+        if ctx.needs_input_grad[0]:
+            gh = torch.empty_like(h)
+            dense_dgrad(L.ptr(g), Em, R, Em, L.ptr(fcw), D + S, D, L.ptr(gh), D)
+        if ctx.needs_input_grad[1]:
+            gs = torch.empty_like(s)
+            dense_dgrad(L.ptr(g), Em, R, Em, _off(fcw, D), D + S, S, L.ptr(gs), S)
+        return (gh, gs, *([None] * len(params)))
+
+
+def _colsum_t4(t4, n_img, H, W, Cc, out):
+    a = L.ConvArgs(n_img, H, W, Cc, H, W, Cc, 1, L.F32, 0, 0, 0, t4, t4, None, 0, 0, L.ptr(out), None)
+    L.call("mrssm_colsum_t4", C.byref(a))
+
+
+# ---- reconstruction loss ---------------------------------------------------------------------------------
+class MseLossFn(Function):
+    """sum_features mean_{t,b} (y-o)^2 (observation_model.py:28-31 + base/algo.py:381-383)."""
+
+    @staticmethod
+    def forward(ctx, y, o, rows):
+        y, o = _f32c(y), _f32c(o)
+        assert y.numel() == o.numel()
+        partial = torch.empty(2048, device=y.device, dtype=torch.float32)
+        out = torch.empty(1, device=y.device, dtype=torch.float32)
+        L.call("mrssm_mse_fwd", L.ptr(y), L.ptr(o), y.numel(), rows, L.ptr(partial), L.ptr(out))
+        ctx.y, ctx.o, ctx.rows = y, o, rows
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        dy = torch.empty_like(ctx.y)
+        L.call("mrssm_mse_bwd", L.ptr(ctx.y), L.ptr(ctx.o), ctx.y.numel(), ctx.rows, L.ptr(_f32c(g)), L.ptr(dy))
+        return dy, None, None
+
+
+def sqdiff(y, o):
+    """Elementwise (y-o)^2, forward only (get_mse API)."""
+    y, o = _f32c(y), _f32c(o)
+    out = torch.empty_like(y)
+    L.call("mrssm_sqdiff", L.ptr(y), L.ptr(o), y.numel(), L.ptr(out))
+    return out
+
+
+# ---- the rollout -------------------------------------------------------------------------------------------
+class FusionTable:
+    """Host-side constant tables of encoder.py:73-124 (Q8).  n_subsets == 0: no fusion (single-modal)."""
+
+    def __init__(self, n_experts, state_size, fusion):
+        import itertools
+        self.n_experts = n_experts
+        if fusion == "single":
+            self.masks, self.dim_subset = [], [0] * state_size
+        elif fusion == "MoPoE":
+            K = n_experts - 1                       # expert 1 = prior_expert, 2.. = modalities
+            subs = []
+            for n in range(K + 1):
+                subs += list(itertools.combinations(range(2, K + 2), n))
+            self.masks = [1 | sum(1 << (e - 1) for e in sub) for sub in subs]
+            n_sub = len(subs)
+            step = int(torch.floor(state_size * torch.tensor(1.0 / float(n_sub), dtype=torch.float32)))
+            self.dim_subset = [min(s // step if step > 0 else n_sub - 1, n_sub - 1) for s in range(state_size)]
+        else:                                       # PoE / NN: one subset with every expert
+            self.masks, self.dim_subset = [(1 << n_experts) - 1], [0] * state_size
+        assert len(self.masks) <= L.MAX_SUBSETS and state_size <= L.MAX_STATE
+
+    def fill(self, a):
+        a.n_subsets = len(self.masks)
+        for i, m in enumerate(self.masks):
+            a.subset_mask[i] = m
+        for i, d in enumerate(self.dim_subset):
+            a.dim_subset[i] = d
+
+
+class RolloutSpec:
+    """Static description handed to RolloutFn: sizes, activation, fusion table, which experts carry
+    an embedding, and the parameter order."""
+
+    def __init__(self, D, S, H, A, act, min_std, table, expert_has_emb):
+        self.D, self.S, self.H, self.A = D, S, H, A
+        self.act, self.min_std, self.table = act, float(min_std), table
+        self.expert_has_emb = list(expert_has_emb)      # per expert 1..E
+        self.E = len(self.expert_has_emb)
+
+
+N_FIXED_PARAMS = 6   # w_sa, b_sa, w_ih, w_hh, b_ih, b_hh  then per head (fc1.w, fc1.b, fc2.w, fc2.b)
+
+
+class RolloutFn(Function):
+    """All T steps of transition_model.py:226-270 in one launch (+ hoisted expert-embedding GEMMs).
+
+    apply(spec, observe, det, prev_state, actions, prev_belief, nonterminals|None, eps_prior|None,
+          eps_post|None, *embs (one per expert with an embedding, [T,B,E_m]), *params)
+    params: fc_embed.weight, fc_embed.bias, rnn.weight_ih, rnn.weight_hh, rnn.bias_ih, rnn.bias_hh,
+            then for head 0 (prior) and each expert: fc1.weight, fc1.bias, fc2.weight, fc2.bias.
+    returns observe: (beliefs, prior_states, prior_means, prior_stds, post_states, post_means,
+            post_stds, *exp_means, *exp_stds); imagine: first four.
+    """
+
+    @staticmethod
+    def forward(ctx, spec, observe, det, prev_state, actions, prev_belief, nonterminals, eps_prior, eps_post, *rest):
+        E = spec.E if observe else 0
+        n_emb = sum(spec.expert_has_emb) if observe else 0
+        embs = [_f32c(e) for e in rest[:n_emb]]
+        params = rest[n_emb:]
+        D, S, H, A = spec.D, spec.S, spec.H, spec.A
+        T, B = actions.shape[0], actions.shape[1]
+        dev = actions.device
+        prev_state, actions, prev_belief = _f32c(prev_state), _f32c(actions), _f32c(prev_belief)
+        nonterminals = None if nonterminals is None else _f32c(nonterminals)
+        eps_prior = None if eps_prior is None else _f32c(eps_prior)
+        eps_post = None if eps_post is None else _f32c(eps_post)
+        need_grad = any(ctx.needs_input_grad)
+        w_sa, b_sa, w_ih, w_hh, b_ih, b_hh = params[:N_FIXED_PARAMS]
+        heads = [params[N_FIXED_PARAMS + 4 * i: N_FIXED_PARAMS + 4 * i + 4] for i in range(1 + E)]
+
+        a = L.RolloutArgs()
+        a.T, a.B, a.D, a.S, a.H, a.A, a.n_experts = T, B, D, S, H, A, E
+        a.act, a.det, a.min_std = spec.act, int(bool(det)), spec.min_std
+        a.prev_state, a.prev_belief, a.actions = L.ptr(prev_state), L.ptr(prev_belief), L.ptr(actions)
+        a.nonterminals, a.eps_prior, a.eps_post = L.ptr(nonterminals), L.ptr(eps_prior), L.ptr(eps_post)
+        keep = []
+        wsaT = transpose(L.ptr(w_sa), D, S + A, S + A, dev)
+        wihT = transpose(L.ptr(w_ih), 3 * D, D, D, dev)
+        whhT = transpose(L.ptr(w_hh), 3 * D, D, D, dev)
+        keep += [wsaT, wihT, whhT]
+        a.w_sa, a.b_sa, a.w_ih, a.b_ih, a.w_hh, a.b_hh = (L.ptr(wsaT), L.ptr(b_sa), L.ptr(wihT), L.ptr(b_ih),
+                                                          L.ptr(whhT), L.ptr(b_hh))
+        emb_pre = [None] * (1 + E)
+        ei = 0
+        for hd in range(1 + E):
+            w1, b1, w2, b2 = heads[hd]
+            ld = w1.shape[1]
+            w1T = transpose(L.ptr(w1), H, D, ld, dev)
+            w2T = transpose(L.ptr(w2), 2 * S, H, H, dev)
+            keep += [w1T, w2T]
+            a.w1[hd], a.w2[hd], a.b2[hd], a.ld1[hd] = L.ptr(w1T), L.ptr(w2T), L.ptr(b2), ld
+            if hd > 0 and spec.expert_has_emb[hd - 1]:
+                emb = embs[ei]
+                ei += 1
+                Em = emb.shape[-1]
+                assert ld == D + Em, (ld, D, Em)
+                pre = torch.empty(T, B, H, device=dev, dtype=torch.float32)
+                dense_fwd(L.ptr(emb), Em, T * B, Em, _off(w1, D), ld, H, L.ptr(b1), 0, L.ptr(pre), H)
+                emb_pre[hd] = pre
+                a.emb_pre[hd] = L.ptr(pre)
+                a.b1[hd] = None
+            else:
+                assert ld == D
+                a.b1[hd] = L.ptr(b1)
+        if observe:
+            spec.table.fill(a)
+        new = lambda n: torch.empty(T, B, n, device=dev, dtype=torch.float32)
+        outs = [new(D), new(S), new(S), new(S)]
+        a.beliefs, a.prior_states, a.prior_means, a.prior_stds = [L.ptr(t) for t in outs]
+        if observe:
+            post = [new(S), new(S), new(S)]
+            a.post_states, a.post_means, a.post_stds = [L.ptr(t) for t in post]
+            em = [new(S) for _ in range(E)]
+            es = [new(S) for _ in range(E)]
+            for e in range(E):
+                a.exp_means[e + 1], a.exp_stds[e + 1] = L.ptr(em[e]), L.ptr(es[e])
+            outs += post + em + es
+        stash = None
+        if need_grad:
+            stash = dict(x=new(D), r=new(D), z=new(D), n=new(D), ghn=new(D), u=[new(H) for _ in range(1 + E)])
+            a.st_x, a.st_r, a.st_z, a.st_n, a.st_ghn = [L.ptr(stash[k]) for k in ("x", "r", "z", "n", "ghn")]
+            for hd in range(1 + E):
+                a.st_u[hd] = L.ptr(stash["u"][hd])
+        L.call("mrssm_rollout_fwd", C.byref(a))
+        del keep
+        ctx.spec, ctx.observe, ctx.det, ctx.E = spec, observe, det, E
+        ctx.inputs = (prev_state, actions, prev_belief, nonterminals, eps_prior, eps_post)
+        ctx.embs, ctx.params, ctx.outs, ctx.stash = embs, params, outs, stash
+        ctx.set_materialize_grads(False)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        spec, observe, E = ctx.spec, ctx.observe, ctx.E
+        prev_state, actions, prev_belief, nonterminals, eps_prior, eps_post = ctx.inputs
+        embs, params, outs, stash = ctx.embs, ctx.params, ctx.outs, ctx.stash
+        assert stash is not None, "rollout forward ran without grad"
+        D, S, H, A = spec.D, spec.S, spec.H, spec.A
+        T, B = actions.shape[0], actions.shape[1]
+        R = T * B
+        dev = actions.device
+        w_sa, b_sa, w_ih, w_hh, b_ih, b_hh = params[:N_FIXED_PARAMS]
+        heads = [params[N_FIXED_PARAMS + 4 * i: N_FIXED_PARAMS + 4 * i + 4] for i in range(1 + E)]
+        gouts = [None if g is None else _f32c(g) for g in gouts]
+
+        g = L.RolloutBwdArgs()
+        a = g.f
+        a.T, a.B, a.D, a.S, a.H, a.A, a.n_experts = T, B, D, S, H, A, E
+        a.act, a.det, a.min_std = spec.act, int(bool(ctx.det)), spec.min_std
+        a.prev_state, a.prev_belief, a.actions = L.ptr(prev_state), L.ptr(prev_belief), L.ptr(actions)
+        a.nonterminals, a.eps_prior, a.eps_post = L.ptr(nonterminals), L.ptr(eps_prior), L.ptr(eps_post)
+        a.w_sa, a.b_sa, a.w_ih, a.b_ih, a.w_hh, a.b_hh = (L.ptr(w_sa), L.ptr(b_sa), L.ptr(w_ih), L.ptr(b_ih),
+                                                          L.ptr(w_hh), L.ptr(b_hh))
+        for hd in range(1 + E):
+            w1, b1, w2, b2 = heads[hd]
+            a.w1[hd], a.ld1[hd], a.b1[hd], a.w2[hd], a.b2[hd] = L.ptr(w1), w1.shape[1], L.ptr(b1), L.ptr(w2), L.ptr(b2)
+            a.st_u[hd] = L.ptr(stash["u"][hd])
+        if observe:
+            spec.table.fill(a)
+        a.beliefs, a.prior_states, a.prior_means, a.prior_stds = [L.ptr(t) for t in outs[:4]]
+        g.g_beliefs, g.g_prior_states, g.g_prior_means, g.g_prior_stds = [L.ptr(t) for t in gouts[:4]]
+        if observe:
+            a.post_states, a.post_means, a.post_stds = [L.ptr(t) for t in outs[4:7]]
+            g.g_post_states, g.g_post_means, g.g_post_stds = [L.ptr(t) for t in gouts[4:7]]
+            for e in range(E):
+                a.exp_means[e + 1], a.exp_stds[e + 1] = L.ptr(outs[7 + e]), L.ptr(outs[7 + E + e])
+                g.g_exp_means[e + 1], g.g_exp_stds[e + 1] = L.ptr(gouts[7 + e]), L.ptr(gouts[7 + E + e])
+        a.st_x, a.st_r, a.st_z, a.st_n, a.st_ghn = [L.ptr(stash[k]) for k in ("x", "r", "z", "n", "ghn")]
+        new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
+        g_prev_state, g_prev_belief, g_actions = new(B, S), new(B, D), new(T, B, A)
+        d_xpre, d_gi, d_gh, xin = new(T, B, D), new(T, B, 3 * D), new(T, B, 3 * D), new(T, B, S + A)
+        d_u = [new(T, B, H) for _ in range(1 + E)]
+        d_o = [new(T, B, 2 * S) for _ in range(1 + E)]
+        g.g_prev_state, g.g_prev_belief, g.g_actions = L.ptr(g_prev_state), L.ptr(g_prev_belief), L.ptr(g_actions)
+        g.d_xpre, g.d_gi, g.d_gh, g.xin = L.ptr(d_xpre), L.ptr(d_gi), L.ptr(d_gh), L.ptr(xin)
+        for hd in range(1 + E):
+            g.d_u[hd], g.d_o[hd] = L.ptr(d_u[hd]), L.ptr(d_o[hd])
+        L.call("mrssm_rollout_bwd", C.byref(g))
+
+        # deferred, time-parallel weight gradients
+        beliefs = outs[0]
+        dense_wgrad(L.ptr(d_xpre), D, L.ptr(xin), S + A, R, D, S + A, L.ptr(grad_buf(w_sa)), S + A, L.ptr(grad_buf(b_sa)))
+        dense_wgrad(L.ptr(d_gi), 3 * D, L.ptr(stash["x"]), D, R, 3 * D, D, L.ptr(grad_buf(w_ih)), D, L.ptr(grad_buf(b_ih)))
+        gwhh = grad_buf(w_hh)
+        dense_wgrad(L.ptr(d_gh), 3 * D, L.ptr(prev_belief), D, B, 3 * D, D, L.ptr(gwhh), D, L.ptr(grad_buf(b_hh)))
+        if T > 1:
+            dense_wgrad(_off(d_gh, B * 3 * D), 3 * D, L.ptr(beliefs), D, R - B, 3 * D, D, L.ptr(gwhh), D, None)
+            _colsum(_off(d_gh, B * 3 * D), R - B, 3 * D, grad_buf(b_hh))
+        g_embs = []
+        ei = 0
+        for hd in range(1 + E):
+            w1, b1, w2, b2 = heads[hd]
+            ld = w1.shape[1]
+            dense_wgrad(L.ptr(d_o[hd]), 2 * S, L.ptr(stash["u"][hd]), H, R, 2 * S, H, L.ptr(grad_buf(w2)), H, L.ptr(grad_buf(b2)))
+            gw1 = grad_buf(w1)
+            dense_wgrad(L.ptr(d_u[hd]), H, L.ptr(beliefs), D, R, H, D, L.ptr(gw1), ld, L.ptr(grad_buf(b1)))
+            if hd > 0 and spec.expert_has_emb[hd - 1]:
+                emb = embs[ei]
+                Em = emb.shape[-1]
+                dense_wgrad(L.ptr(d_u[hd]), H, L.ptr(emb), Em, R, H, Em, _off(gw1, D), ld, None)
+                ge = None
+                if ctx.needs_input_grad[9 + ei]:
+                    ge = torch.empty_like(emb)
+                    dense_dgrad(L.ptr(d_u[hd]), H, R, H, _off(w1, D), ld, Em, L.ptr(ge), Em)
+                g_embs.append(ge)
+                ei += 1
+        return (None, None, None, g_prev_state, g_actions, g_prev_belief, None, None, None, *g_embs,
+                *([None] * len(params)))
+
+
+def _colsum(x_ptr, rows, cols, out):
+    L.call("mrssm_colsum_acc", x_ptr, rows, cols, cols, L.ptr(out))
+
+
+# ---- latent half of the ELBO -----------------------------------------------------------------------------------
+class LatentSpec:
+    def __init__(self, S, table, kl_mode, refuse, free_nats, alpha):
+        self.S, self.table, self.kl_mode, self.refuse = S, table, kl_mode, refuse
+        self.free_nats = float(free_nats)
+        self.alpha = -1.0 if alpha is None else float(alpha)
+        self.E = table.n_experts
+
+
+class LatentFn(Function):
+    """apply(spec, prior_means, prior_stds, post_means, post_stds, eps_dec|None, *exp_means, *exp_stds)
+    -> refuse: (z_dec, q_means, q_stds, sums[2]); else (sums[2],)   sums = (kl_loss, global KL)."""
+
+    @staticmethod
+    def forward(ctx, spec, prior_means, prior_stds, post_means, post_stds, eps_dec, *experts):
+        E = spec.E if (spec.refuse or spec.kl_mode == 1) else 0
+        tens = [_f32c(t) for t in (prior_means, prior_stds, post_means, post_stds)]
+        eps_dec = None if eps_dec is None else _f32c(eps_dec)
+        ex = [_f32c(t) for t in experts]
+        shape = tens[0].shape
+        rows = tens[0].numel() // spec.S
+        dev = tens[0].device
+        a = LatentFn._args(spec, rows, tens, eps_dec, ex, E)
+        scratch = torch.empty(2 * rows, device=dev, dtype=torch.float32)
+        sums = torch.empty(2, device=dev, dtype=torch.float32)
+        a.row_scratch, a.out_sums = L.ptr(scratch), L.ptr(sums)
+        outs = []
+        if spec.refuse:
+            z, qm, qs = (torch.empty(shape, device=dev, dtype=torch.float32) for _ in range(3))
+            a.z_dec, a.q_means, a.q_stds = L.ptr(z), L.ptr(qm), L.ptr(qs)
+            outs = [z, qm, qs]
+        L.call("mrssm_latent_fwd", C.byref(a))
+        ctx.spec, ctx.rows, ctx.tens, ctx.eps_dec, ctx.ex, ctx.E = spec, rows, tens, eps_dec, ex, E
+        ctx.set_materialize_grads(False)
+        if spec.refuse:
+            ctx.mark_non_differentiable(qm, qs)
+        return (*outs, sums)
+
+    @staticmethod
+    def _args(spec, rows, tens, eps_dec, ex, E):
+        a = L.LatentArgs()
+        a.rows, a.S, a.n_experts, a.kl_mode, a.refuse = rows, spec.S, E, spec.kl_mode, int(spec.refuse)
+        if E:
+            spec.table.fill(a)
+        a.free_nats, a.alpha = spec.free_nats, spec.alpha
+        a.prior_means, a.prior_stds, a.post_means, a.post_stds = [L.ptr(t) for t in tens]
+        a.eps_dec = L.ptr(eps_dec)
+        for e in range(E):
+            a.exp_means[e + 1], a.exp_stds[e + 1] = L.ptr(ex[e]), L.ptr(ex[E + e])
+        return a
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        spec, rows, tens, eps_dec, ex, E = ctx.spec, ctx.rows, ctx.tens, ctx.eps_dec, ctx.ex, ctx.E
+        dev = tens[0].device
+        g_sums = gouts[-1]
+        g_z = gouts[0] if spec.refuse else None
+        if g_sums is None:
+            g_sums = torch.zeros(2, device=dev, dtype=torch.float32)
+        a = LatentFn._args(spec, rows, tens, eps_dec, ex, E)
+        a.g_sums = L.ptr(_f32c(g_sums))
+        a.g_z = None if g_z is None else L.ptr(_f32c(g_z))
+        new = lambda: torch.empty_like(tens[0])
+        gpm, gps = new(), new()
+        a.g_prior_means, a.g_prior_stds = L.ptr(gpm), L.ptr(gps)
+        gqm = gqs = None
+        if not spec.refuse:
+            gqm, gqs = new(), new()
+            a.g_post_means, a.g_post_stds = L.ptr(gqm), L.ptr(gqs)
+        gex = [new() for _ in range(2 * E)]
+        for e in range(E):
+            a.g_exp_means[e + 1], a.g_exp_stds[e + 1] = L.ptr(gex[e]), L.ptr(gex[E + e])
+        scratch = torch.empty(1, device=dev, dtype=torch.float32)
+        a.row_scratch, a.out_sums = L.ptr(scratch), L.ptr(scratch)
+        L.call("mrssm_latent_bwd", C.byref(a))
+        n_ex_in = len(ex)
+        gex_full = gex if E else [None] * n_ex_in
+        return (None, gpm, gps, gqm, gqs, None, *gex_full)

@@ -1,0 +1,167 @@
+"""Observation decoders — B200 host side.
+
+Drop-in for the reference's ``utils/models/observation_model.py`` for the modalities on the hot path:
+``DenseDecoder`` (vectors), ``ImageDecoder`` (64x64), ``ImageDecoder_128`` and the
+``MultimodalObservationModel`` container, with the same constructor arguments, ``forward`` /
+``get_mse`` / ``get_log_prob`` API, ``.modules`` lists and state-dict keys.  In addition every
+decoder offers ``mse_loss(h_t, s_t, o_t)`` = sum_features mean_{t,b} (loc - o)^2 as a scalar, which is
+what the training step uses (the reference materialises the element-wise tensor first).
+"""
+import torch
+from torch import nn
+
+from mrssm_b200 import ops
+from utils.models.encoder import act_code
+
+_LOG_SQRT_2PI = 0.9189385332046727
+
+
+class ObservationModel_base(nn.Module):
+    def get_state_dict(self):
+        return self.state_dict()
+
+    def _load_state_dict(self, state_dict):
+        self.load_state_dict(state_dict)
+
+    def get_model_params(self):
+        return list(self.parameters())
+
+    def get_mse(self, h_t, s_t, o_t):
+        """Element-wise squared error (reference observation_model.py:28-31), differentiable."""
+        loc = self.forward(h_t, s_t)["loc"]
+        return (loc - o_t) ** 2
+
+    def get_log_prob(self, h_t, s_t, o_t):
+        loc = self.forward(h_t, s_t)["loc"]
+        return -0.5 * (o_t - loc) ** 2 - _LOG_SQRT_2PI           # Normal(loc, 1).log_prob(o)
+
+    def mse_loss(self, h_t, s_t, o_t):
+        loc = self.forward(h_t, s_t)["loc"]
+        T, B = h_t.shape[:2]
+        return ops.MseLossFn.apply(loc, o_t, T * B)
+
+
+class DenseDecoder(ObservationModel_base):
+    """Linear(D+S,E)+act -> Linear(E,E)+act -> Linear(E,obs) (reference observation_model.py:33-54)."""
+
+    def __init__(self, observation_size, belief_size, state_size, embedding_size, activation_function="relu"):
+        super().__init__()
+        self.activation_function = activation_function
+        self.fc1 = nn.Linear(belief_size + state_size, embedding_size)
+        self.fc2 = nn.Linear(embedding_size, embedding_size)
+        self.fc3 = nn.Linear(embedding_size, observation_size)
+        self.modules = [self.fc1, self.fc2, self.fc3]
+
+    def forward(self, h_t, s_t):
+        T, B = h_t.shape[:2]
+        y = ops.MlpFn.apply(act_code(self.activation_function), False, 2, h_t.reshape(T * B, -1), s_t.reshape(T * B, -1),
+                            self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
+                            self.fc3.weight, self.fc3.bias)
+        return {"loc": y.reshape(T, B, -1), "scale": 1.0}
+
+
+class _ConvDecoder(ObservationModel_base):
+    __constants__ = ["embedding_size"]
+    LAYERS = ()        # (out_channels or None for image_dim, kernel)
+
+    def __init__(self, belief_size, state_size, embedding_size, activation_function="relu", image_dim=3,
+                 normalization=None):
+        super().__init__()
+        if normalization is not None:
+            raise NotImplementedError(f"normalization={normalization!r} is a 'next' row (SURVEY §8f#1)")
+        self.embedding_size = embedding_size
+        self.fc1 = nn.Linear(belief_size + state_size, embedding_size)
+        layers, cin = [], embedding_size
+        for i, (cout, k) in enumerate(self.LAYERS):
+            cout = image_dim if cout is None else cout
+            layers.append(nn.ConvTranspose2d(cin, cout, k, stride=2))
+            if i < len(self.LAYERS) - 1:
+                layers.append(nn.ReLU())
+            cin = cout
+        self.conv = nn.Sequential(*layers)               # keys conv.{0,2,4,..}.{weight,bias}
+        self.modules = [self.fc1, self.conv]
+
+    def forward(self, h_t, s_t):
+        T, B = h_t.shape[:2]
+        params = [self.fc1.weight, self.fc1.bias]
+        params += [p for m in self.conv if isinstance(m, nn.ConvTranspose2d) for p in (m.weight, m.bias)]
+        y = ops.ConvDecoderFn.apply(h_t.reshape(T * B, -1), s_t.reshape(T * B, -1), *params)
+        return {"loc": y.reshape(T, B, *y.shape[1:]), "scale": 1.0}
+
+
+class ImageDecoder(_ConvDecoder):
+    """64x64: fc -> ConvT 1024->128 k5 -> 64 k5 -> 32 k6 -> C k6, stride 2 (reference :58-105)."""
+    LAYERS = ((128, 5), (64, 5), (32, 6), (None, 6))
+
+
+class ImageDecoder_128(_ConvDecoder):
+    """128x128: fc -> ConvT 1024->256 k6 -> 128 k4 -> 64 k4 -> 32 k4 -> C k6 (reference :162-229)."""
+    LAYERS = ((256, 6), (128, 4), (64, 4), (32, 4), (None, 6))
+
+
+def build_ObservationModel(name, observation_shapes, belief_size, state_size, hidden_size, embedding_size,
+                           activation_function, normalization=None):
+    shape = observation_shapes[name]
+    if "image" in name:
+        cls = {(64, 64): ImageDecoder, (128, 128): ImageDecoder_128}.get(tuple(shape[1:]))
+        if cls is None:
+            raise NotImplementedError(f"image size {list(shape[1:])}: only 64x64 and 128x128 are on the B200 hot path")
+        return cls(belief_size, state_size, embedding_size["image"], activation_function["cnn"],
+                   image_dim=shape[0], normalization=normalization)
+    if "sound" in name or name == "draw_target":
+        raise NotImplementedError(f"decoder for '{name}' is outside the B200 hot path (SURVEY §2/§8f)")
+    return DenseDecoder(shape[0], belief_size, state_size, embedding_size["other"], activation_function["dense"])
+
+
+class MultimodalObservationModel:
+    """One decoder per name in observation_names_rec (reference observation_model.py:537-611)."""
+    __constants__ = ["embedding_size"]
+
+    def __init__(self, observation_names_rec, observation_shapes, embedding_size, belief_size, state_size,
+                 hidden_size, activation_function, normalization=None, device=torch.device("cpu")):
+        self.observation_names_rec = observation_names_rec
+        self.observation_models = {}
+        self.modules = []
+        for name in observation_names_rec:
+            m = build_ObservationModel(name, observation_shapes, belief_size, state_size, hidden_size,
+                                       embedding_size, activation_function, normalization=normalization).to(device)
+            self.observation_models[name] = m
+            self.modules += m.modules
+
+    def forward(self, h_t, s_t):
+        return {name: m(h_t, s_t) for name, m in self.observation_models.items()}
+
+    __call__ = forward
+
+    def get_log_prob(self, h_t, s_t, o_t):
+        return {n: self.observation_models[n].get_log_prob(h_t, s_t, o_t[n]) for n in self.observation_names_rec}
+
+    def get_mse(self, h_t, s_t, o_t):
+        return {n: self.observation_models[n].get_mse(h_t, s_t, o_t[n]) for n in self.observation_names_rec}
+
+    def mse_loss(self, h_t, s_t, o_t):
+        return {n: self.observation_models[n].mse_loss(h_t, s_t, o_t[n]) for n in self.observation_names_rec}
+
+    def get_pred_value(self, h_t, s_t, key):
+        return self.observation_models[key](h_t, s_t)
+
+    def get_pred_key(self, h_t, s_t, key):
+        return self.get_pred_value(h_t, s_t, key)
+
+    def get_state_dict(self):
+        return {name: m.state_dict() for name, m in self.observation_models.items()}
+
+    def _load_state_dict(self, state_dict):
+        for name in self.observation_names_rec:
+            self.observation_models[name].load_state_dict(state_dict[name])
+
+    def get_model_params(self):
+        return [p for m in self.observation_models.values() for p in m.parameters()]
+
+    def eval(self):
+        for m in self.observation_models.values():
+            m.eval()
+
+    def train(self):
+        for m in self.observation_models.values():
+            m.train()

@@ -1,0 +1,131 @@
+"""Shared harness: run the CUDA product and the CPU oracle on identical weights, data and noise."""
+import torch
+
+from oracle import mrssm_oracle as O
+
+
+def oracle_cfg(fusion, **kw):
+    if fusion == "single":
+        kw.setdefault("names_enc", ("image_horizon",))
+        kw.setdefault("names_rec", ("image_horizon",))
+    return O.OracleConfig(fusion=fusion, **kw)
+
+
+def product_cfg(oc, B, T, device):
+    from mrssm_b200.config import hot_path_config
+    return hot_path_config(fusion=oc.fusion, batch_size=B, chunk_size=T, device=device,
+                           belief_size=oc.belief_size, state_size=oc.state_size, hidden_size=oc.hidden_size,
+                           free_nats=oc.free_nats, kl_balancing_alpha=oc.kl_balancing_alpha,
+                           global_kl_beta=oc.global_kl_beta, kl_beta=oc.kl_beta, grad_clip_norm=oc.grad_clip_norm,
+                           model_learning_rate=oc.lr, adam_epsilon=oc.adam_eps)
+
+
+def unflatten(flat):
+    out = {}
+    for k, v in flat.items():
+        parts = k.split("/")
+        d = out
+        for p in parts[:-1]:
+            d = d.setdefault(p, {})
+        d[parts[-1]] = v
+    return out
+
+
+def load_params(model, P, oc):
+    if oc.multimodal:
+        model.load_state_dict(unflatten(P))
+    else:
+        torch.nn.Module.load_state_dict(model, P)
+
+
+def named_params(model, oc):
+    """flat oracle key -> nn.Parameter of the product model."""
+    if oc.multimodal:
+        sd = model.get_state_dict()
+        sd.pop("model_optimizer")
+        by_ptr = {p.data_ptr(): p for p in model.param_list}
+        return {k: by_ptr[v.data_ptr()] for k, v in O.flatten_state(sd).items()}
+    return dict(model.named_parameters())
+
+
+class FakeD:
+    """Replay-buffer stand-in with the reference's D.sample contract (memory.py:212-222)."""
+
+    def __init__(self, batch, device):
+        self.b = batch
+        self.device = device
+
+    def sample(self, n, L):
+        d = self.device
+        return ({k: v.to(d) for k, v in self.b["obs"].items()}, self.b["actions"].to(d),
+                self.b["rewards"].to(d), self.b["nonterminals"].to(d))
+
+
+def build_product(oc, B, T, device, seed=0):
+    from algos.MRSSM.MRSSM.algo import build_RSSM
+    model = build_RSSM(product_cfg(oc, B, T, device), torch.device(device))
+    P = O.make_params(oc, seed=seed)
+    load_params(model, P, oc)
+    return model, P
+
+
+def product_step(model, oc, batch, noise, device):
+    from mrssm_b200.noise import FixedNoise
+    dev = torch.device(device)
+    streams = dict(prior=noise["eps_prior"].to(dev), post=noise["eps_post"].to(dev))
+    if oc.fusion in ("PoE", "MoPoE"):
+        streams["dec"] = noise["eps_dec"].to(dev)
+    cap = {}
+    orig = model.estimate_state
+
+    def es(*a, **k):
+        cap["states"] = orig(*a, **k)
+        return cap["states"]
+
+    model.estimate_state = es
+    try:
+        with FixedNoise(**streams):
+            model.optimize(FakeD(batch, dev))
+    finally:
+        model.estimate_state = orig
+    return cap["states"]
+
+
+def assert_states_close(st, ref, rtol, atol):
+    for k, v in ref.items():
+        if isinstance(v, dict):
+            for n in v:
+                torch.testing.assert_close(st[k][n].detach().cpu(), v[n], rtol=rtol, atol=atol, msg=lambda m: f"{k}[{n}]: {m}")
+        elif v is not None:
+            torch.testing.assert_close(st[k].detach().cpu(), v, rtol=rtol, atol=atol, msg=lambda m: f"{k}: {m}")
+
+
+def run_train_parity(fusion, B, T, steps, device, rtol=1e-3, atol=2e-5, **cfg_kw):
+    """Product vs oracle: states, losses, every gradient tensor, every updated parameter."""
+    oc = oracle_cfg(fusion, **cfg_kw)
+    model, P = build_product(oc, B, T, device)
+    named = named_params(model, oc)
+    opt = {}
+    worst = {}
+    for s in range(steps):
+        batch, noise = O.synthetic_batch(oc, B, T, seed=1234 + s)
+        ref = O.train_step(P, opt, oc, batch, noise)
+        st = product_step(model, oc, batch, noise, device)
+        assert_states_close(st, {k: v for k, v in ref["states"].items()}, rtol, atol)
+        info = {k: float(v) for k, v in model.loss_info.items()}
+        for k, v in ref["loss_info"].items():
+            assert abs(info[k] - v) <= rtol * abs(v) + 1e-5, (k, info[k], v)
+        gn = float(model.model_optimizer.grad_norm)
+        assert abs(gn - ref["grad_norm"]) <= rtol * ref["grad_norm"], (gn, ref["grad_norm"])
+        gmax = max(float(g.abs().max()) for g in ref["grads"].values())
+        for k, g in ref["grads"].items():
+            mine = named[k].grad.detach().cpu()
+            scale = max(float(g.abs().max()), 1e-3 * gmax)
+            err = float((mine - g).abs().max()) / scale
+            worst[k] = max(worst.get(k, 0.0), err)
+            assert err <= 2 * rtol, f"grad {k}: max err {err:.3e} (relative to max|g|)"
+        for k in P:
+            if k not in ref["grads"]:
+                assert float(named[k].grad.abs().max()) == 0.0, f"{k} should get no gradient"
+            torch.testing.assert_close(named[k].detach().cpu(), P[k], rtol=rtol, atol=1e-5, msg=lambda m: f"param {k}: {m}")
+    return {"worst_grad_err": max(worst.values()), "model_loss": float(model.model_loss), "steps": steps}

@@ -1,0 +1,50 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle and the committed reference fixtures."""
+import os
+
+import pytest
+import torch
+
+from oracle import mrssm_oracle as O
+from tests import parity_util as U
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+RTOL = 1e-3      # BASELINE.json north_star: rtol 1e-3 in fp32 mode
+
+
+@pytest.mark.parametrize("fusion,kw", [
+    ("MoPoE", {}), ("PoE", {}), ("NN", {}), ("single", {}),
+    ("MoPoE", dict(grad_clip_norm=0.5, kl_balancing_alpha=None)),
+    ("PoE", dict(kl_balancing_alpha=None, global_kl_beta=0.0, free_nats=0.5)),
+])
+def test_train_step_matches_oracle(fusion, kw):
+    out = U.run_train_parity(fusion, B=4, T=6, steps=2, device=DEV, rtol=RTOL, **kw)
+    assert out["worst_grad_err"] < 2 * RTOL
+
+
+@pytest.mark.parametrize("name", ["mopoe", "poe", "nn", "single", "mopoe_clip", "poe_noalpha"])
+def test_train_step_matches_reference_fixture(name, golden_dir):
+    """Directly against tests/golden/train_*.pt (outputs of the unmodified reference)."""
+    rec = torch.load(os.path.join(golden_dir, f"train_{name}.pt"), weights_only=False)
+    oc = O.OracleConfig(**rec["meta"]["cfg"])
+    B, T = rec["meta"]["B"], rec["meta"]["T"]
+    model, P = U.build_product(oc, B, T, DEV)
+    named = U.named_params(model, oc)
+    for step in rec["steps"]:
+        batch, noise = O.synthetic_batch(oc, B, T, seed=step["data_seed"])
+        st = U.product_step(model, oc, batch, noise, DEV)
+        U.assert_states_close(st, step["states"], RTOL, 2e-5)
+        info = {k: float(v) for k, v in model.loss_info.items()}
+        for k, v in step["loss_info"].items():
+            assert info[k] == pytest.approx(v, rel=RTOL, abs=1e-5), k
+        assert float(model.model_optimizer.grad_norm) == pytest.approx(step["grad_norm"], rel=RTOL)
+        gmax = max(s["norm"] for s in step["grads"].values())
+        for k, s in step["grads"].items():
+            g = named[k].grad.detach().cpu().reshape(-1)
+            assert float(g.double().norm()) == pytest.approx(s["norm"], rel=2 * RTOL, abs=1e-6 * gmax), k
+            torch.testing.assert_close(g[s["idx"]], s["val"], rtol=5 * RTOL, atol=1e-5 * max(1.0, s["norm"]))
+        for k in step["grad_none"]:
+            assert float(named[k].grad.abs().max()) == 0.0
+        for k, s in step["params_after"].items():
+            p = named[k].detach().cpu().reshape(-1)
+            torch.testing.assert_close(p[s["idx"]], s["val"], rtol=RTOL, atol=1e-5)
