@@ -47,7 +47,8 @@ typedef struct mrssm_t4 {
 
 /* ---- convolution family --------------------------------------------------------------------
  * One geometry describes nn.Conv2d(k, stride 2) and nn.ConvTranspose2d(k, stride 2) alike:
- * a "large" tensor [n_img,Hl,Wl,Cl] and a "small" tensor [n_img,Hs,Ws,Cs], Hl = 2*(Hs-1)+ksz,
+ * a "large" tensor [n_img,Hl,Wl,Cl] and a "small" tensor [n_img,Hs,Ws,Cs], Hl >= 2*(Hs-1)+ksz
+ * (equality for ConvTranspose2d; Conv2d floors, leaving the last row/column of `large` unused),
  * and a weight W[cs][cl][kh][kw] at weight[cs*w_ss + cl*w_sl + kh*ksz + kw] — which is exactly
  * Conv2d.weight [Cout=Cs,Cin=Cl,k,k] and ConvTranspose2d.weight [Cin=Cs,Cout=Cl,k,k].
  * nn.Linear is the case Hl=Wl=Hs=Ws=ksz=1 (weight [out=Cs,in=Cl]).

@@ -252,8 +252,9 @@ __global__ void colsum_t4_kernel(T4 s, int n_img, int Hs, int Ws, int Cs, float*
 int fill(const mrssm_conv_args* a, ConvK& k) {
     MRSSM_CHECK(a != nullptr, "conv: null args");
     MRSSM_CHECK(a->n_img > 0 && a->Cl > 0 && a->Cs > 0 && a->ksz > 0, "conv: bad geometry");
-    MRSSM_CHECK(a->Hl == 2 * (a->Hs - 1) + a->ksz && a->Wl == 2 * (a->Ws - 1) + a->ksz,
-                "conv: Hl=%d Hs=%d ksz=%d inconsistent (need Hl = 2*(Hs-1)+ksz)", a->Hl, a->Hs, a->ksz);
+    // Conv2d floors: the last row/column of `large` may be unused (64 -> 31 -> 14), never the reverse
+    MRSSM_CHECK(a->Hl >= 2 * (a->Hs - 1) + a->ksz && a->Wl >= 2 * (a->Ws - 1) + a->ksz && a->Hs > 0 && a->Ws > 0,
+                "conv: Hl=%d Hs=%d ksz=%d inconsistent (need Hl >= 2*(Hs-1)+ksz)", a->Hl, a->Hs, a->ksz);
     MRSSM_CHECK(a->dtype == MRSSM_F32 || a->dtype == MRSSM_BF16, "conv: bad dtype %d", a->dtype);
     MRSSM_CHECK(a->large.ptr && a->small.ptr && a->weight, "conv: null tensor");
     k.n_img = a->n_img; k.Hl = a->Hl; k.Wl = a->Wl; k.Cl = a->Cl;

@@ -242,7 +242,7 @@ int check(const mrssm_latent_args* a, bool bwd) {
         MRSSM_CHECK(a->n_experts > 0 && a->n_subsets > 0 && a->n_subsets <= MRSSM_MAX_SUBSETS, "latent: fusion table missing");
         for (int e = 1; e <= a->n_experts; ++e) MRSSM_CHECK(a->exp_means[e] && a->exp_stds[e], "latent: expert %d missing", e);
     }
-    if (a->refuse) MRSSM_CHECK(a->z_dec && a->q_means && a->q_stds && a->eps_dec, "latent: refuse outputs missing");
+    if (a->refuse) MRSSM_CHECK(a->eps_dec && (bwd || (a->z_dec && a->q_means && a->q_stds)), "latent: refuse outputs missing");
     else MRSSM_CHECK(a->post_means && a->post_stds, "latent: posterior missing");
     if (bwd) {
         MRSSM_CHECK(a->g_sums && a->g_prior_means && a->g_prior_stds, "latent_bwd: null grads");
