@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""MRSSM train-step benchmark (contract: see DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+metric  : MRSSM train seq-steps/s = (world * B * T) / step time      (BASELINE.json)
+workload: full ELBO train step (encoders + T-step observe rollout + decoders + KL, fwd + bwd,
+          global-norm clip + Adam), MoPoE, image 64x64 + 3-d joint state, D=H=200, S=30,
+          B=1024 sequences x T=50 per GPU (BASELINE config 3; weak scaling), synthetic
+          COBOTTA-shaped data and seeded weights.
+value   : K timed steps with the batch resident in HBM (CUDA events, barrier + sync both sides,
+          max over ranks).
+e2e     : the same steps through the public API model.optimize(D) with D handing out PINNED HOST
+          buffers: H2D of the batch and D2H of the loss inside the timed region.
+roofline: the dominant kernel of the step (by device time, measured live with CUDA events around
+          every C-ABI call of one extra step) — algorithmic FLOPs or bytes / its mean duration,
+          against MEASURED_PEAKS.json.  `rollout_roofline` is the same for the rollout kernel.
+cpu_baseline / --impl reference: the oracle port of the reference's CPU path (oracle/), timed on
+          the host cores on a bounded sample (B=16 sequences of the same T).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "multimodal-rssm_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "mrssm_train_seq_steps_per_s"
+UNIT = "seq-steps/s (B*T per second)"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(T, fusion, sample_B=16, steps=3, warmup=1):
+    from oracle import mrssm_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    oc = O.OracleConfig(fusion=fusion)
+    P = O.make_params(oc, seed=0)
+    opt = {}
+    times = []
+    for s in range(warmup + steps):
+        batch, noise = O.synthetic_batch(oc, sample_B, T, seed=1234 + s)
+        t0 = time.perf_counter()
+        O.train_step(P, opt, oc, batch, noise)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    med = statistics.median(times)
+    return sample_B * T / med, med, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rate, med, cores = cpu_oracle_rate(args.chunk, args.fusion, sample_B=16, steps=max(1, args.steps),
+                                       warmup=max(1, min(args.warmup, 1)))
+    sample = f"B=16 of the B={args.batch} sequences, T={args.chunk}, full train step, fp32, {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"mrssm_{args.fusion.lower()}_train_step_B{args.batch}_T{args.chunk}_per_gpu",
+            "fusion": args.fusion, "per_gpu_batch": args.batch, "chunk_size": args.chunk,
+            "global_batch": args.batch * world, "belief": 200, "state": 30, "hidden": 200,
+            "modalities": "image_horizon[3,64,64]+pose_quat_v2[3]", "mode": args.mode,
+            "parallelism": f"dp{world}", "l2_policy": "inputs_exceed_l2"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+class SyntheticReplay:
+    """D.sample contract of the reference (utils/replay_buffer/memory.py:212-222): time-major fp32
+    [obs dict, actions, rewards, nonterminals] on `device`.  `resident=True` hands out tensors that
+    already live in HBM; otherwise every sample() is an H2D copy from pinned host memory."""
+
+    def __init__(self, cfg, device, seed, n_buffers=2):
+        B, T = cfg.train.batch_size, cfg.train.chunk_size
+        g = torch.Generator(device=device).manual_seed(seed)
+        self.device, self.resident, self.i = device, True, 0
+        self.dev, self.host = [], []
+        for _ in range(n_buffers):
+            obs = {}
+            for name in cfg.rssm.observation_names_enc:
+                shp = cfg.env.observation_shapes[name]
+                if "image" in name:
+                    u8 = torch.randint(0, 256, (T, B, *shp), generator=g, device=device)
+                    x = torch.floor(u8 / 8) / 32 - 0.5 + torch.rand((T, B, *shp), generator=g, device=device) / 32
+                    del u8
+                else:
+                    x = torch.randn((T, B, *shp), generator=g, device=device)
+                obs[name] = x
+            actions = torch.randn((T, B, cfg.env.action_size), generator=g, device=device)
+            rewards = torch.zeros((T, B), device=device)
+            nonterm = torch.ones((T, B, 1), device=device)
+            drop = torch.rand(B, generator=g, device=device) < 0.1
+            tpos = torch.randint(0, T, (B,), generator=g, device=device)
+            nonterm[tpos[drop], torch.nonzero(drop).flatten(), 0] = 0
+            self.dev.append((obs, actions, rewards, nonterm))
+        self.h2d_bytes = 0
+
+    def make_host_copies(self):
+        for obs, a, r, n in self.dev:
+            pin = lambda t: t.cpu().pin_memory()
+            self.host.append(({k: pin(v) for k, v in obs.items()}, pin(a), pin(r), pin(n)))
+        obs, a, r, n = self.host[0]
+        self.h2d_bytes = sum(v.numel() * 4 for v in obs.values()) + 4 * (a.numel() + r.numel() + n.numel())
+
+    def sample(self, n, L):
+        self.i += 1
+        if self.resident:
+            obs, a, r, nt = self.dev[self.i % len(self.dev)]
+            return [obs, a, r, nt]
+        obs, a, r, nt = self.host[self.i % len(self.host)]
+        d = self.device
+        return [{k: v.to(d, non_blocking=True) for k, v in obs.items()}, a.to(d, non_blocking=True),
+                r.to(d, non_blocking=True), nt.to(d, non_blocking=True)]
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, f"/tmp/mrssm_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.proc.wait()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def timed_steps(model, D, steps, sync_loss):
+    import torch.distributed as dist
+    if dist.is_initialized():
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    loss = None
+    for _ in range(steps):
+        model.optimize(D)
+        if sync_loss:
+            loss = float(model.model_loss)          # D2H read of the step's result
+    e1.record()
+    torch.cuda.synchronize()
+    if dist.is_initialized():
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if dist.is_initialized():
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    return ms, loss
+
+
+def profile_one_step(model, D):
+    """CUDA-event time of every C-ABI call of one step -> per-kernel aggregates."""
+    from mrssm_b200 import _lib as L
+    L.profile = []
+    model.optimize(D)
+    torch.cuda.synchronize()
+    rec, L.profile = L.profile, None
+    agg = {}
+    for name, tag, work, a, b in rec:
+        key = name.replace("mrssm_", "") + (f":{tag}" if tag else "")
+        d = agg.setdefault(key, dict(ms=0.0, n=0, flops=0.0, bytes=0.0))
+        d["ms"] += a.elapsed_time(b)
+        d["n"] += 1
+        if work:
+            d["flops"] += work.get("flops", 0.0)
+            d["bytes"] += work.get("bytes", 0.0)
+    return agg
+
+
+def roofline_of(key, d, pk, total_ms):
+    ms = d["ms"] / d["n"]
+    flops, byts = d["flops"] / d["n"], d["bytes"] / d["n"]
+    ridge = pk["tf_sust"] * 1e12 / (pk["hbm"] * 1e9)
+    tensor_bound = byts > 0 and flops / byts > ridge
+    if tensor_bound:
+        ach = flops / (ms * 1e-3) / 1e12
+        out = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"]}
+    else:
+        ach = byts / (ms * 1e-3) / 1e9
+        out = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
+    out.update({"traffic": None, "kernel": key, "launch_ms": ms, "launches_per_step": d["n"],
+                "share_of_step": d["ms"] / total_ms, "peak_source": pk["src"],
+                "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": byts})
+    return out
+
+
+def run_ours(args):
+    from mrssm_b200 import _lib as L
+    from mrssm_b200.config import hot_path_config
+    from mrssm_b200.dist import DataParallel, init_from_env
+    from algos.MRSSM.MRSSM.algo import build_RSSM
+
+    rank, local, world = init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU path (use --impl reference)"
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    cfg = hot_path_config(fusion=args.fusion, batch_size=args.batch, chunk_size=args.chunk, device=device)
+    cfg.train.use_amp = args.mode == "bf16"
+    torch.manual_seed(0)
+    model = build_RSSM(cfg, torch.device(device))
+    if world > 1:
+        DataParallel(model)
+    D = SyntheticReplay(cfg, device, seed=1234 + rank)
+
+    for _ in range(args.warmup):
+        model.optimize(D)
+    sampler = ClockSampler(local)
+    k0 = L.kernel_launches
+    if rank == 0:
+        sampler.start()
+    ms, _ = timed_steps(model, D, args.steps, sync_loss=False)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = (L.kernel_launches - k0)
+    ms_step = ms / args.steps
+    value = world * args.batch * args.chunk / (ms_step * 1e-3)
+
+    # end to end: pinned host buffers -> H2D -> step -> D2H of the loss, every step
+    D.make_host_copies()
+    D.resident = False
+    model.optimize(D)
+    ms_e2e, loss = timed_steps(model, D, args.steps, sync_loss=True)
+    e2e_value = world * args.batch * args.chunk / (ms_e2e / args.steps * 1e-3)
+    D.resident = True
+
+    if rank != 0:
+        return
+    pk = peaks()
+    agg = profile_one_step(model, D)
+    total_ms = sum(d["ms"] for d in agg.values())
+    dom_key = max(agg, key=lambda k: agg[k]["ms"])
+    roof = roofline_of(dom_key, agg[dom_key], pk, total_ms)
+    rk = "rollout_fwd:observe"
+    rollout_roof = roofline_of(rk, agg[rk], pk, total_ms) if rk in agg else None
+    top = sorted(((k, d["ms"], d["n"]) for k, d in agg.items()), key=lambda x: -x[1])[:12]
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, med, cores = cpu_oracle_rate(args.chunk, args.fusion, sample_B=16, steps=3, warmup=1)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"B=16 sequences x T={args.chunk}, full train step, fp32 oracle port, median of 3 steps",
+               "ms_per_step": med * 1e3}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.mode == "fp32" else "bf16", "data": "synthetic",
+        "config": workload_config(args, world),
+        "model_steps_per_s": world * args.batch * (args.chunk - 1) / (ms_step * 1e-3),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": D.h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps, "last_loss": loss},
+        "gpu_launches": launches,
+        "roofline": roof, "rollout_roofline": rollout_roof, "cpu_baseline": cpu,
+        "top_kernels_ms": [{"kernel": k, "ms_per_step": round(m, 4), "launches": n} for k, m, n in top],
+        "profiled_step_kernel_ms": total_ms,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="sequences per GPU")
+    ap.add_argument("--chunk", type=int, default=50)
+    ap.add_argument("--fusion", default="MoPoE", choices=["MoPoE", "PoE", "NN", "single"])
+    ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    import torch.distributed as dist
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

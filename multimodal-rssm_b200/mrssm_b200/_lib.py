@@ -139,15 +139,25 @@ def _require_device():
 _KERNELS_PER_CALL = {"mrssm_latent_fwd": 2, "mrssm_mse_fwd": 2, "mrssm_clip_adam": 3}
 
 
-def call(name, *args):
-    """Invoke a C-ABI entry point on torch's current stream; raise RuntimeError on failure."""
+profile = None        # set to a list to record (name, tag, work, start_event, end_event) per call
+
+
+def call(name, *args, tag=None, work=None):
+    """Invoke a C-ABI entry point on torch's current stream; raise RuntimeError on failure.
+    tag/work ({"flops":..,"bytes":..} algorithmic work) only feed the optional per-call profile."""
     global launches, kernel_launches
     _require_device()
     lib = load()
     stream = torch.cuda.current_stream().cuda_stream
+    if profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(lib, name)(*args, stream)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {lib.mrssm_last_error().decode()}")
+    if profile is not None:
+        e1.record()
+        profile.append((name, tag, work, e0, e1))
     launches += 1
     kernel_launches += _KERNELS_PER_CALL.get(name, 1)
 

@@ -34,7 +34,14 @@ def grad_buf(p):
 def _conv(fn, geom, large, small, weight_ptr, w_ss, w_sl, bias_ptr=None, act=0, mask_ptr=None, mask_mode=0,
           accumulate=0, dtype=L.F32):
     a = L.ConvArgs(*geom, dtype, act, mask_mode, accumulate, large, small, weight_ptr, w_ss, w_sl, bias_ptr, mask_ptr)
-    L.call(fn, C.byref(a))
+    tag = work = None
+    if L.profile is not None:
+        n, Hl, Wl, Cl, Hs, Ws, Cs, k = geom
+        esz = 4 if dtype == L.F32 else 2
+        tag = "%s[%dx%dx%d<->%dx%dx%d k%d]" % (fn[11:], Hl, Wl, Cl, Hs, Ws, Cs, k)
+        work = dict(flops=2.0 * n * Hs * Ws * Cs * Cl * k * k,
+                    bytes=float(n) * (Hl * Wl * Cl + Hs * Ws * Cs) * esz + 4.0 * Cs * Cl * k * k)
+    L.call(fn, C.byref(a), tag=tag, work=work)
     if fn == "mrssm_conv_wgrad" and bias_ptr:
         L.kernel_launches += 1
 
@@ -109,12 +116,14 @@ class MlpFn(Function):
             acts.append(y)
             cur = y
         ctx.act, ctx.final_act, ctx.n_parts = act, final_act, n_parts
-        ctx.parts, ctx.acts, ctx.params = parts, acts, params
+        ctx.params = params
+        ctx.save_for_backward(*parts, *acts)        # outputs must go through save_for_backward (no ref cycle)
         return cur
 
     @staticmethod
     def backward(ctx, g):
-        act, parts, acts, params = ctx.act, ctx.parts, ctx.acts, ctx.params
+        act, params = ctx.act, ctx.params
+        parts, acts = list(ctx.saved_tensors[:ctx.n_parts]), list(ctx.saved_tensors[ctx.n_parts:])
         n_layers = len(params) // 2
         M = parts[0].shape[0]
         g = _f32c(g)
@@ -173,12 +182,14 @@ class ConvEncoderFn(Function):
             tensors.append((y, yt))
             geoms.append(geom)
             Hl, Wl, Cl = Hs, Ws, Cs
-        ctx.tensors, ctx.geoms, ctx.params = tensors, geoms, params
+        ctx.views, ctx.geoms, ctx.params = [_strides(t4) for _, t4 in tensors], geoms, params
+        ctx.save_for_backward(*[t for t, _ in tensors])
         return tensors[-1][0]
 
     @staticmethod
     def backward(ctx, g):
-        tensors, geoms, params = ctx.tensors, ctx.geoms, ctx.params
+        geoms, params = ctx.geoms, ctx.params
+        tensors = [(t, L.T4(L.ptr(t), *v)) for t, v in zip(ctx.saved_tensors, ctx.views)]
         n_layers = len(geoms)
         g = act_bwd(g, tensors[-1][0], RELU)
         gt = L.T4(L.ptr(g), *_strides(tensors[-1][1]))
@@ -236,12 +247,15 @@ class ConvDecoderFn(Function):
             tensors.append((y, yt))
             geoms.append(geom)
             Hs, Ws, Cs = Hl, Wl, Cl
-        ctx.h, ctx.s, ctx.tensors, ctx.geoms, ctx.params = h, s, tensors, geoms, params
+        ctx.views, ctx.geoms, ctx.params = [_strides(t4) for _, t4 in tensors], geoms, params
+        ctx.save_for_backward(h, s, *[t for t, _ in tensors])
         return tensors[-1][0]
 
     @staticmethod
     def backward(ctx, g):
-        h, s, tensors, geoms, params = ctx.h, ctx.s, ctx.tensors, ctx.geoms, ctx.params
+        geoms, params = ctx.geoms, ctx.params
+        h, s = ctx.saved_tensors[:2]
+        tensors = [(t, L.T4(L.ptr(t), *v)) for t, v in zip(ctx.saved_tensors[2:], ctx.views)]
         convs = params[2:]
         n_layers = len(geoms)
         g = _f32c(g)
@@ -291,13 +305,15 @@ class MseLossFn(Function):
         partial = torch.empty(2048, device=y.device, dtype=torch.float32)
         out = torch.empty(1, device=y.device, dtype=torch.float32)
         L.call("mrssm_mse_fwd", L.ptr(y), L.ptr(o), y.numel(), rows, L.ptr(partial), L.ptr(out))
-        ctx.y, ctx.o, ctx.rows = y, o, rows
+        ctx.rows = rows
+        ctx.save_for_backward(y, o)
         return out.reshape(())
 
     @staticmethod
     def backward(ctx, g):
-        dy = torch.empty_like(ctx.y)
-        L.call("mrssm_mse_bwd", L.ptr(ctx.y), L.ptr(ctx.o), ctx.y.numel(), ctx.rows, L.ptr(_f32c(g)), L.ptr(dy))
+        y, o = ctx.saved_tensors
+        dy = torch.empty_like(y)
+        L.call("mrssm_mse_bwd", L.ptr(y), L.ptr(o), y.numel(), ctx.rows, L.ptr(_f32c(g)), L.ptr(dy))
         return dy, None, None
 
 
@@ -434,20 +450,39 @@ class RolloutFn(Function):
             a.st_x, a.st_r, a.st_z, a.st_n, a.st_ghn = [L.ptr(stash[k]) for k in ("x", "r", "z", "n", "ghn")]
             for hd in range(1 + E):
                 a.st_u[hd] = L.ptr(stash["u"][hd])
-        L.call("mrssm_rollout_fwd", C.byref(a))
+        work = None
+        if L.profile is not None:
+            # compulsory HBM bytes per (b,t) = 4*(sum E_m + A + 1 + 2S) read + 4*(D + 3S + 3S + 2 E S) write
+            n_w = sum(p.numel() for p in params)
+            if observe:
+                per = 4.0 * (sum(e.shape[-1] for e in embs) + A + 1 + 2 * S) + 4.0 * (D + 6 * S + 2 * E * S)
+            else:
+                per = 4.0 * (A + S) + 4.0 * (D + 3 * S)
+            macs = (S + A) * D + 6 * D * D + (1 + E) * (D * H + H * 2 * S) + sum(e.shape[-1] * H for e in embs)
+            work = dict(bytes=per * T * B + 4.0 * n_w, flops=2.0 * macs * T * B)
+        L.call("mrssm_rollout_fwd", C.byref(a), tag="observe" if observe else "imagine", work=work)
         del keep
         ctx.spec, ctx.observe, ctx.det, ctx.E = spec, observe, det, E
-        ctx.inputs = (prev_state, actions, prev_belief, nonterminals, eps_prior, eps_post)
-        ctx.embs, ctx.params, ctx.outs, ctx.stash = embs, params, outs, stash
+        ctx.params = params
+        ins = [prev_state, actions, prev_belief, nonterminals, eps_prior, eps_post]
+        ctx.in_mask = [t is not None for t in ins]
+        st = [] if stash is None else [stash[k] for k in ("x", "r", "z", "n", "ghn")] + stash["u"]
+        ctx.counts = (len(embs), len(outs), len(st))
+        ctx.save_for_backward(*[t for t in ins if t is not None], *embs, *outs, *st)
         ctx.set_materialize_grads(False)
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *gouts):
         spec, observe, E = ctx.spec, ctx.observe, ctx.E
-        prev_state, actions, prev_belief, nonterminals, eps_prior, eps_post = ctx.inputs
-        embs, params, outs, stash = ctx.embs, ctx.params, ctx.outs, ctx.stash
-        assert stash is not None, "rollout forward ran without grad"
+        saved = list(ctx.saved_tensors)
+        ins = [saved.pop(0) if m else None for m in ctx.in_mask]
+        prev_state, actions, prev_belief, nonterminals, eps_prior, eps_post = ins
+        n_emb, n_out, n_st = ctx.counts
+        embs, outs, st = saved[:n_emb], saved[n_emb:n_emb + n_out], saved[n_emb + n_out:]
+        assert n_st, "rollout forward ran without grad"
+        stash = dict(zip(("x", "r", "z", "n", "ghn"), st[:5]), u=st[5:])
+        params = ctx.params
         D, S, H, A = spec.D, spec.S, spec.H, spec.A
         T, B = actions.shape[0], actions.shape[1]
         R = T * B
@@ -557,7 +592,8 @@ class LatentFn(Function):
             a.z_dec, a.q_means, a.q_stds = L.ptr(z), L.ptr(qm), L.ptr(qs)
             outs = [z, qm, qs]
         L.call("mrssm_latent_fwd", C.byref(a))
-        ctx.spec, ctx.rows, ctx.tens, ctx.eps_dec, ctx.ex, ctx.E = spec, rows, tens, eps_dec, ex, E
+        ctx.spec, ctx.rows, ctx.E, ctx.has_eps, ctx.n_ex = spec, rows, E, eps_dec is not None, len(ex)
+        ctx.save_for_backward(*tens, *([eps_dec] if eps_dec is not None else []), *ex)
         ctx.set_materialize_grads(False)
         if spec.refuse:
             ctx.mark_non_differentiable(qm, qs)
@@ -578,7 +614,11 @@ class LatentFn(Function):
 
     @staticmethod
     def backward(ctx, *gouts):
-        spec, rows, tens, eps_dec, ex, E = ctx.spec, ctx.rows, ctx.tens, ctx.eps_dec, ctx.ex, ctx.E
+        spec, rows, E = ctx.spec, ctx.rows, ctx.E
+        saved = list(ctx.saved_tensors)
+        tens, saved = saved[:4], saved[4:]
+        eps_dec = saved.pop(0) if ctx.has_eps else None
+        ex = saved
         dev = tens[0].device
         g_sums = gouts[-1]
         g_z = gouts[0] if spec.refuse else None
