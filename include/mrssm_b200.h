@@ -78,6 +78,43 @@ int mrssm_conv_wgrad(const mrssm_conv_args* a, void* stream);
 /* bias gradient of a ConvTranspose2d: a->bias[cl] += sum over (img,h,w) of a->large (observation_model.py:65-74 autograd) */
 int mrssm_colsum_t4(const mrssm_conv_args* a, void* stream);
 
+
+/* ---- tensor-core (tcgen05) conv family: bf16 activations, fp32 accumulation --------------------------
+ * Same geometry as mrssm_conv_args.  Activations are bf16 NHWC with the channel count padded to a
+ * multiple of 8 (Cl / Cs below are the PADDED counts; padded channels hold zeros).  Weights for
+ * down/up are packed once per optimiser step by mrssm_tc_pack_weight (bf16, K-major, zero padded);
+ * wgrad accumulates fp32 straight into the PyTorch-layout master gradient.  The output of down/up
+ * is bf16 NHWC (padded channels written as zeros) or, with out_f32, fp32 with arbitrary strides. */
+typedef struct mrssm_tc_conv_args {
+    int32_t n_img, Hl, Wl, Cl, Hs, Ws, Cs, ksz;
+    int32_t act, mask_mode, out_f32;
+    int32_t n_out_pad;      /* down/up: padded output channels (multiple of 16) = rows of the packed weight */
+    int32_t n_out_valid;    /* down/up: real output channels */
+    int32_t bias_mod;       /* down/up: bias index = n % bias_mod (0 -> n_out_valid) */
+    int32_t cs_valid, cl_valid; /* wgrad: real channel counts of the master weight */
+    mrssm_t4 large, small, mask;    /* mask: bf16, indexed like the output pixel, own strides */
+    const void* wpacked;    /* down/up */
+    const float* bias;      /* down/up, or NULL */
+    float* dweight;         /* wgrad output (accumulated) */
+    int64_t w_ss, w_sl;     /* wgrad: master weight strides */
+} mrssm_tc_conv_args;
+
+int mrssm_tc_conv_down(const mrssm_tc_conv_args* a, void* stream);
+int mrssm_tc_conv_up(const mrssm_tc_conv_args* a, void* stream);
+int mrssm_tc_conv_wgrad(const mrssm_tc_conv_args* a, void* stream);
+/* mode 0: down [Npad][Kpad=(tap,cl_pad)]; mode 1: up, 4 parity classes [4][Npad][Kpad=(th,tw,cs_pad)];
+ * mode 2: ConvTranspose2d on a 1x1 input as a dense layer [Npad=(tap,cl_pad)][Kpad=cs] */
+int mrssm_tc_pack_weight(const float* w, int64_t w_ss, int64_t w_sl, int32_t Cs_valid, int32_t Cl_valid,
+                         int32_t Cs_pad, int32_t Cl_pad, int32_t ksz, int32_t mode, int32_t Npad, int32_t Kpad,
+                         void* out, void* stream);
+/* fp32 strided [n,H,W,C] -> bf16 NHWC with channels padded to Cpad (x scale), and back */
+int mrssm_tc_to_bf16(const mrssm_t4* src, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t Cpad, float scale,
+                     void* dst, void* stream);
+int mrssm_tc_from_bf16(const void* src, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t Cpad,
+                       const mrssm_t4* dst, void* stream);
+/* out[c] += sum_rows x[row][c] for bf16 x [rows][Cpad] */
+int mrssm_tc_colsum(const void* x, int64_t rows, int32_t Cpad, int32_t Cvalid, float* out, void* stream);
+
 /* ---- the RSSM rollout ------------------------------------------------------------------------
  * Replaces MultimodalTransitionModel.forward (utils/models/transition_model.py:200-285), its
  * single-modal twin TransitionModel.forward (:50-114), nn.GRUCell (:160,235), the prior head and

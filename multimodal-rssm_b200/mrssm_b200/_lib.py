@@ -33,6 +33,13 @@ class ConvArgs(C.Structure):
         ("bias", _vp), ("mask", _vp)]
 
 
+class TcConvArgs(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_img", "Hl", "Wl", "Cl", "Hs", "Ws", "Cs", "ksz", "act", "mask_mode",
+                                         "out_f32", "n_out_pad", "n_out_valid", "bias_mod", "cs_valid", "cl_valid")] + [
+        ("large", T4), ("small", T4), ("mask", T4), ("wpacked", _vp), ("bias", _vp), ("dweight", _vp),
+        ("w_ss", C.c_int64), ("w_sl", C.c_int64)]
+
+
 class RolloutArgs(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("T", "B", "D", "S", "H", "A", "n_experts", "act", "det")] + [
         ("min_std", C.c_float)] + [(n, _vp) for n in ("prev_state", "prev_belief", "actions", "nonterminals",
@@ -81,6 +88,13 @@ SYMBOLS = {
     "mrssm_conv_up": [C.POINTER(ConvArgs), _vp],
     "mrssm_conv_wgrad": [C.POINTER(ConvArgs), _vp],
     "mrssm_colsum_t4": [C.POINTER(ConvArgs), _vp],
+    "mrssm_tc_conv_down": [C.POINTER(TcConvArgs), _vp],
+    "mrssm_tc_conv_up": [C.POINTER(TcConvArgs), _vp],
+    "mrssm_tc_conv_wgrad": [C.POINTER(TcConvArgs), _vp],
+    "mrssm_tc_pack_weight": [_vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
+    "mrssm_tc_to_bf16": [C.POINTER(T4), _i32, _i32, _i32, _i32, _i32, _f, _vp, _vp],
+    "mrssm_tc_from_bf16": [_vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(T4), _vp],
+    "mrssm_tc_colsum": [_vp, _i64, _i32, _i32, _vp, _vp],
     "mrssm_rollout_fwd": [C.POINTER(RolloutArgs), _vp],
     "mrssm_rollout_bwd": [C.POINTER(RolloutBwdArgs), _vp],
     "mrssm_latent_fwd": [C.POINTER(LatentArgs), _vp],

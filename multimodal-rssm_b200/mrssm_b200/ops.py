@@ -643,3 +643,86 @@ class LatentFn(Function):
         n_ex_in = len(ex)
         gex_full = gex if E else [None] * n_ex_in
         return (None, gpm, gps, gqm, gqs, None, *gex_full)
+
+
+# ---- tensor-core (bf16) primitives --------------------------------------------------------------------------
+def pad8(c):
+    return (c + 7) // 8 * 8
+
+
+def pad16(c):
+    return (c + 15) // 16 * 16
+
+
+def pad64(c):
+    return (c + 63) // 64 * 64
+
+
+def tc_to_bf16(src_t4, n_img, H, W, Cc, device, scale=1.0, Cpad=None):
+    """fp32 strided [n,H,W,C] -> bf16 NHWC [n,H,W,pad8(C)]."""
+    Cpad = pad8(Cc) if Cpad is None else Cpad
+    dst = torch.empty(n_img, H, W, Cpad, device=device, dtype=torch.bfloat16)
+    L.call("mrssm_tc_to_bf16", C.byref(src_t4), n_img, H, W, Cc, Cpad, float(scale), L.ptr(dst))
+    return dst
+
+
+def tc_from_bf16(src, Cc, dst_t4):
+    n_img, H, W, Cpad = src.shape
+    L.call("mrssm_tc_from_bf16", L.ptr(src), n_img, H, W, Cc, Cpad, C.byref(dst_t4))
+
+
+def tc_pack_weight(w, mode, Cs_pad, Cl_pad):
+    """w: fp32 master [Cs,Cl,k,k] (or [out,in] Linear = k 1).  mode 0 down, 1 up (4 parity classes), 2 up on 1x1 input."""
+    Cs, Cl = w.shape[0], w.shape[1]
+    k = w.shape[2] if w.dim() == 4 else 1
+    nt = (k + 1) // 2
+    if mode == 0:
+        Npad, Kpad, classes = pad16(Cs), pad64(k * k * Cl_pad), 1
+    elif mode == 1:
+        Npad, Kpad, classes = pad16(Cl), pad64(nt * nt * Cs_pad), 4
+    else:
+        Npad, Kpad, classes = pad16(k * k * Cl_pad), pad64(Cs_pad), 1
+    out = torch.empty(classes, Npad, Kpad, device=w.device, dtype=torch.bfloat16)
+    L.call("mrssm_tc_pack_weight", L.ptr(w), Cl * k * k, k * k, Cs, Cl, Cs_pad, Cl_pad, k, mode, Npad, Kpad, L.ptr(out))
+    return out
+
+
+def _tc_args(geom, large, small, act=0, mask=None, mask_mode=0, out_f32=0, n_out_pad=0, n_out_valid=0, bias_mod=0,
+             cs_valid=0, cl_valid=0, wpacked=None, bias=None, dweight=None, w_ss=0, w_sl=0):
+    return L.TcConvArgs(*geom, act, mask_mode, out_f32, n_out_pad, n_out_valid, bias_mod, cs_valid, cl_valid,
+                        large, small, mask if mask is not None else L.T4(None, 0, 0, 0, 0), wpacked, bias, dweight, w_ss, w_sl)
+
+
+def _tc_work(fn, geom, n_valid_pairs):
+    if L.profile is None:
+        return None, None
+    n, Hl, Wl, Cl, Hs, Ws, Cs, k = geom
+    cs, cl = n_valid_pairs
+    tag = "%s[%dx%dx%d<->%dx%dx%d k%d]" % (fn[9:], Hl, Wl, cl, Hs, Ws, cs, k)
+    return tag, dict(flops=2.0 * n * Hs * Ws * cs * cl * k * k, bytes=2.0 * n * (Hl * Wl * Cl + Hs * Ws * Cs) + 2.0 * cs * cl * k * k)
+
+
+def tc_conv_down(geom, large, small, wpacked, bias, n_out_valid, act=0, mask=None, mask_mode=0, out_f32=0, bias_mod=0,
+                 valid=None):
+    a = _tc_args(geom, large, small, act, mask, mask_mode, out_f32, wpacked.shape[1], n_out_valid, bias_mod,
+                 wpacked=L.ptr(wpacked), bias=L.ptr(bias))
+    tag, work = _tc_work("mrssm_tc_conv_down", geom, valid or (geom[6], geom[3]))
+    L.call("mrssm_tc_conv_down", C.byref(a), tag=tag, work=work)
+
+
+def tc_conv_up(geom, large, small, wpacked, bias, n_out_valid, act=0, mask=None, mask_mode=0, out_f32=0, valid=None):
+    a = _tc_args(geom, large, small, act, mask, mask_mode, out_f32, wpacked.shape[1], n_out_valid, 0,
+                 wpacked=L.ptr(wpacked), bias=L.ptr(bias))
+    tag, work = _tc_work("mrssm_tc_conv_up", geom, valid or (geom[6], geom[3]))
+    L.call("mrssm_tc_conv_up", C.byref(a), tag=tag, work=work)
+
+
+def tc_conv_wgrad(geom, large, small, dweight_ptr, w_ss, w_sl, cs_valid, cl_valid):
+    a = _tc_args(geom, large, small, cs_valid=cs_valid, cl_valid=cl_valid, dweight=dweight_ptr, w_ss=w_ss, w_sl=w_sl)
+    tag, work = _tc_work("mrssm_tc_conv_wgrad", geom, (cs_valid, cl_valid))
+    L.call("mrssm_tc_conv_wgrad", C.byref(a), tag=tag, work=work)
+
+
+def tc_colsum(x, Cvalid, out):
+    rows = x.numel() // x.shape[-1]
+    L.call("mrssm_tc_colsum", L.ptr(x), rows, x.shape[-1], Cvalid, L.ptr(out))

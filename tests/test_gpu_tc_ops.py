@@ -1,0 +1,118 @@
+"""-m gpu: tcgen05 conv-family kernels against the exact-fp32 CUDA-core kernels (same C ABI) on
+bf16-representable inputs.  Tolerance: bf16 output rounding (rtol 1e-2) — inputs are identical."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+# (n_img, Hl, Cl, Hs, Cs, ksz): every conv / convT / dense geometry of the 64x64 and 128x128 stacks
+GEOMS = [
+    (3, 64, 3, 31, 32, 4), (3, 31, 32, 14, 64, 4), (3, 14, 64, 6, 128, 4), (5, 6, 128, 2, 256, 4),   # encoder 64
+    (3, 5, 128, 1, 1024, 5), (3, 13, 64, 5, 128, 5), (2, 30, 32, 13, 64, 6), (2, 64, 3, 30, 32, 6),   # decoder 64
+    (300, 1, 1024, 1, 200, 1), (130, 1, 128, 1, 128, 1), (70, 1, 200, 1, 1024, 1),                   # dense
+    (2, 128, 3, 63, 16, 4), (2, 14, 256, 6, 128, 4), (1, 128, 3, 62, 32, 6),                           # 128x128 stacks
+]
+
+
+def _bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _setup(g):
+    from mrssm_b200 import _lib as L, ops
+    n, Hl, Cl, Hs, Cs, k = g
+    gen = torch.Generator(device=DEV).manual_seed(hash(g) % 1000)
+    large = _bf16_round(torch.randn(n, Hl, Hl, Cl, device=DEV, generator=gen))
+    small = _bf16_round(torch.randn(n, Hs, Hs, Cs, device=DEV, generator=gen))
+    w = _bf16_round(torch.randn(Cs, Cl, k, k, device=DEV, generator=gen) / (Cl * k * k) ** 0.5)
+    geom = (n, Hl, Hl, Cl, Hs, Hs, Cs, k)
+    Clp, Csp = ops.pad8(Cl), ops.pad8(Cs)
+    lb = ops.tc_to_bf16(L.nhwc(large, Hl, Hl, Cl), n, Hl, Hl, Cl, DEV)
+    sb = ops.tc_to_bf16(L.nhwc(small, Hs, Hs, Cs), n, Hs, Hs, Cs, DEV)
+    return L, ops, geom, (large, small, w), (lb, sb), (Clp, Csp)
+
+
+@pytest.mark.parametrize("g", GEOMS)
+def test_tc_down_matches_simt(g):
+    L, ops, geom, (large, small, w), (lb, sb), (Clp, Csp) = _setup(g)
+    n, Hl, _, Cl, Hs, _, Cs, k = geom
+    bias = torch.randn(Cs, device=DEV)
+    ref = torch.empty_like(small)
+    ops._conv("mrssm_conv_down", geom, L.nhwc(large, Hl, Hl, Cl), L.nhwc(ref, Hs, Hs, Cs), L.ptr(w), Cl * k * k, k * k,
+              L.ptr(bias), ops.RELU)
+    wp = ops.tc_pack_weight(w, 0, Csp, Clp)
+    out = torch.zeros(n, Hs, Hs, ops.pad16(Cs), device=DEV, dtype=torch.bfloat16)
+    gp = (n, Hl, Hl, Clp, Hs, Hs, Csp, k)
+    ops.tc_conv_down(gp, L.nhwc(lb, Hl, Hl, Clp), L.nhwc(out, Hs, Hs, out.shape[-1]), wp, bias, Cs, act=ops.RELU)
+    torch.testing.assert_close(out[..., :Cs].float(), ref, rtol=1e-2, atol=1e-2)
+    assert float(out[..., Cs:].float().abs().max() if out.shape[-1] > Cs else 0.0) == 0.0
+    # fp32 NCHW output variant
+    out32 = torch.empty(n, Cs, Hs, Hs, device=DEV)
+    ops.tc_conv_down(gp, L.nhwc(lb, Hl, Hl, Clp), L.nchw(out32, Hs, Hs, Cs), wp, bias, Cs, act=ops.RELU, out_f32=1)
+    torch.testing.assert_close(out32.permute(0, 2, 3, 1), ref, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("g", GEOMS)
+def test_tc_up_matches_simt(g):
+    L, ops, geom, (large, small, w), (lb, sb), (Clp, Csp) = _setup(g)
+    n, Hl, _, Cl, Hs, _, Cs, k = geom
+    if Hl != 2 * (Hs - 1) + k:
+        pytest.skip("floor geometry only occurs as a Conv2d (down/dgrad) — covered by the mask test")
+    bias = torch.randn(Cl, device=DEV)
+    ref = torch.empty_like(large)
+    ops._conv("mrssm_conv_up", geom, L.nhwc(ref, Hl, Hl, Cl), L.nhwc(small, Hs, Hs, Cs), L.ptr(w), Cl * k * k, k * k,
+              L.ptr(bias), ops.RELU)
+    wp = ops.tc_pack_weight(w, 1, Csp, Clp)
+    out = torch.zeros(n, Hl, Hl, ops.pad16(Cl), device=DEV, dtype=torch.bfloat16)
+    gp = (n, Hl, Hl, Clp, Hs, Hs, Csp, k)
+    ops.tc_conv_up(gp, L.nhwc(out, Hl, Hl, out.shape[-1]), L.nhwc(sb, Hs, Hs, Csp), wp, bias, Cl, act=ops.RELU)
+    torch.testing.assert_close(out[..., :Cl].float(), ref, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("g", GEOMS)
+def test_tc_dgrad_with_mask_matches_simt(g):
+    """Conv2d dgrad = up with the ReLU mask of the layer input, including floor geometries (64->31->14)."""
+    L, ops, geom, (large, small, w), (lb, sb), (Clp, Csp) = _setup(g)
+    n, Hl, _, Cl, Hs, _, Cs, k = geom
+    ref = torch.empty_like(large)
+    ops._conv("mrssm_conv_up", geom, L.nhwc(ref, Hl, Hl, Cl), L.nhwc(small, Hs, Hs, Cs), L.ptr(w), Cl * k * k, k * k,
+              None, 0, L.ptr(large), ops.RELU)
+    wp = ops.tc_pack_weight(w, 1, Csp, Clp)
+    out = torch.zeros(n, Hl, Hl, ops.pad16(Cl), device=DEV, dtype=torch.bfloat16)
+    gp = (n, Hl, Hl, Clp, Hs, Hs, Csp, k)
+    ops.tc_conv_up(gp, L.nhwc(out, Hl, Hl, out.shape[-1]), L.nhwc(sb, Hs, Hs, Csp), wp, None, Cl,
+                   mask=L.nhwc(lb, Hl, Hl, Clp), mask_mode=ops.RELU)
+    torch.testing.assert_close(out[..., :Cl].float(), ref, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("g", GEOMS)
+def test_tc_wgrad_matches_simt(g):
+    L, ops, geom, (large, small, w), (lb, sb), (Clp, Csp) = _setup(g)
+    n, Hl, _, Cl, Hs, _, Cs, k = geom
+    ref = torch.zeros_like(w)
+    ops._conv("mrssm_conv_wgrad", geom, L.nhwc(large, Hl, Hl, Cl), L.nhwc(small, Hs, Hs, Cs), L.ptr(ref), Cl * k * k, k * k)
+    out = torch.zeros_like(w)
+    gp = (n, Hl, Hl, Clp, Hs, Hs, Csp, k)
+    ops.tc_conv_wgrad(gp, L.nhwc(lb, Hl, Hl, Clp), L.nhwc(sb, Hs, Hs, Csp), L.ptr(out), Cl * k * k, k * k, Cs, Cl)
+    scale = float(ref.abs().max())
+    assert float((out - ref).abs().max()) <= 2e-3 * scale + 1e-4
+
+
+def test_tc_up_1x1_as_dense():
+    """ConvTranspose2d on a 1x1 input (decoder layer 0) lowered to a dense tcgen05 GEMM."""
+    from mrssm_b200 import _lib as L, ops
+    n, Cs, Cl, k = 200, 1024, 128, 5
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    x = _bf16_round(torch.randn(n, Cs, device=DEV, generator=gen))
+    w = _bf16_round(torch.randn(Cs, Cl, k, k, device=DEV, generator=gen) / Cs ** 0.5)
+    bias = torch.randn(Cl, device=DEV)
+    ref = torch.empty(n, k, k, Cl, device=DEV)
+    ops._conv("mrssm_conv_up", (n, k, k, Cl, 1, 1, Cs, k), L.nhwc(ref, k, k, Cl), L.nhwc(x, 1, 1, Cs), L.ptr(w), Cl * k * k, k * k,
+              L.ptr(bias), ops.RELU)
+    wp = ops.tc_pack_weight(w, 2, Cs, Cl)
+    xb = ops.tc_to_bf16(L.nhwc(x, 1, 1, Cs), n, 1, 1, Cs, DEV)
+    out = torch.zeros(n, k * k * Cl, device=DEV, dtype=torch.bfloat16)
+    ops.tc_conv_down((n, 1, 1, Cs, 1, 1, k * k * Cl, 1), L.nhwc(xb, 1, 1, Cs), L.nhwc(out, 1, 1, k * k * Cl), wp, bias,
+                     k * k * Cl, act=ops.RELU, bias_mod=Cl)
+    torch.testing.assert_close(out.float().reshape(n, k, k, Cl), ref, rtol=1e-2, atol=1e-2)
