@@ -329,7 +329,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="sequences per GPU")
     ap.add_argument("--chunk", type=int, default=50)
     ap.add_argument("--fusion", default="MoPoE", choices=["MoPoE", "PoE", "NN", "single"])
-    ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -726,3 +726,190 @@ def tc_conv_wgrad(geom, large, small, dweight_ptr, w_ss, w_sl, cs_valid, cl_vali
 def tc_colsum(x, Cvalid, out):
     rows = x.numel() // x.shape[-1]
     L.call("mrssm_tc_colsum", L.ptr(x), rows, x.shape[-1], Cvalid, L.ptr(out))
+
+
+# ---- bf16 tensor-core mode ------------------------------------------------------------------------------------
+_STATE = {"bf16": False, "wversion": 0}
+_wcache = {}
+
+
+def set_bf16_mode(on):
+    """True: conv stacks / big GEMMs run on the tcgen05 kernels (bf16 operands, fp32 accumulate, fp32 master
+    weights); False: exact fp32 CUDA-core kernels.  Selected from cfg.train.use_amp by the algorithm layer."""
+    _STATE["bf16"] = bool(on)
+
+
+def bf16_mode():
+    return _STATE["bf16"]
+
+
+def bump_weight_version():
+    """Called after every optimiser step / checkpoint load: packed bf16 weight copies are stale."""
+    _STATE["wversion"] += 1
+
+
+def packed(w, mode, Cs_pad, Cl_pad):
+    key = (w.data_ptr(), mode, Cs_pad, Cl_pad)
+    ver = (_STATE["wversion"], w._version)
+    hit = _wcache.get(key)
+    if hit is None or hit[0] != ver:
+        w4 = w if w.dim() == 4 else w.reshape(w.shape[0], w.shape[1], 1, 1)
+        hit = (ver, tc_pack_weight(w4.detach(), mode, Cs_pad, Cl_pad))
+        _wcache[key] = hit
+    return hit[1]
+
+
+def _bf16(*shape, device):
+    return torch.empty(*shape, device=device, dtype=torch.bfloat16)
+
+
+class ConvEncoderTCFn(Function):
+    """ConvEncoderFn on the tcgen05 kernels: NCHW fp32 image -> bf16 NHWC(8) -> conv stack (bf16 NHWC
+    intermediates) -> fp32 [N, C*h*w] embedding in (C,H,W) order."""
+
+    @staticmethod
+    def forward(ctx, x, *params):
+        x = _f32c(x)
+        N, Cc, H, W = x.shape
+        dev = x.device
+        n_layers = len(params) // 2
+        acts = [tc_to_bf16(L.nchw(x, H, W, Cc), N, H, W, Cc, dev)]
+        geoms = []
+        Hl, Wl = H, W
+        y = None
+        for i in range(n_layers):
+            Wt, b = params[2 * i], params[2 * i + 1]
+            Cs, Cl, k, _ = Wt.shape
+            Clp = acts[-1].shape[-1]
+            Hs, Ws = (Hl - k) // 2 + 1, (Wl - k) // 2 + 1
+            geom = (N, Hl, Wl, Clp, Hs, Ws, pad16(Cs), k)
+            wp = packed(Wt, 0, pad16(Cs), Clp)
+            xin = L.nhwc(acts[-1], Hl, Wl, Clp)
+            if i == n_layers - 1:
+                y = torch.empty(N, Cs * Hs * Ws, device=dev, dtype=torch.float32)
+                tc_conv_down(geom, xin, L.nchw(y, Hs, Ws, Cs), wp, b, Cs, act=RELU, out_f32=1, valid=(Cs, Cl))
+            else:
+                o = _bf16(N, Hs, Ws, pad16(Cs), device=dev)
+                tc_conv_down(geom, xin, L.nhwc(o, Hs, Ws, pad16(Cs)), wp, b, Cs, act=RELU, valid=(Cs, Cl))
+                acts.append(o)
+            geoms.append((geom, Cs, Cl))
+            Hl, Wl = Hs, Ws
+        ctx.geoms, ctx.params = geoms, params
+        ctx.save_for_backward(y, *acts)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        geoms, params = ctx.geoms, ctx.params
+        y, *acts = ctx.saved_tensors
+        dev = y.device
+        n_layers = len(geoms)
+        (N, _, _, _, Hs, Ws, Csp, _), Cs, _ = geoms[-1]
+        gm = act_bwd(g, y, RELU)
+        gb = tc_to_bf16(L.nchw(gm, Hs, Ws, Cs), N, Hs, Ws, Cs, dev, Cpad=Csp)
+        for i in reversed(range(n_layers)):
+            Wt, b = params[2 * i], params[2 * i + 1]
+            geom, Cs, Cl = geoms[i]
+            N, Hl, Wl, Clp, Hs, Ws, Csp, k = geom
+            xi = acts[i]
+            tc_conv_wgrad(geom, L.nhwc(xi, Hl, Wl, Clp), L.nhwc(gb, Hs, Ws, Csp), L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl)
+            tc_colsum(gb, Cs, grad_buf(b))
+            if i > 0:
+                gx = _bf16(N, Hl, Wl, Clp, device=dev)
+                wp = packed(Wt, 1, Csp, Clp)
+                tc_conv_up(geom, L.nhwc(gx, Hl, Wl, Clp), L.nhwc(gb, Hs, Ws, Csp), wp, None, Cl,
+                           mask=L.nhwc(xi, Hl, Wl, Clp), mask_mode=RELU, valid=(Cs, Cl))
+                gb = gx
+        return (None, *([None] * len(params)))
+
+
+class ConvDecoderTCFn(Function):
+    """ConvDecoderFn on the tcgen05 kernels.  fc([h,s]) and the ConvTranspose on the 1x1 map are dense GEMMs,
+    the remaining layers are parity-class `up` implicit GEMMs; output is fp32 NCHW."""
+
+    @staticmethod
+    def forward(ctx, h, s, *params):
+        h, s = _f32c(h), _f32c(s)
+        R, D = h.shape
+        S = s.shape[1]
+        dev = h.device
+        fcw, fcb = params[0], params[1]
+        Em = fcw.shape[0]
+        hs = torch.empty(R, D + S, device=dev, dtype=torch.float32)
+        L.call("mrssm_concat2", L.ptr(h), D, L.ptr(s), S, R, L.ptr(hs))
+        Kp = pad8(D + S)
+        hsb = tc_to_bf16(L.nhwc(hs, 1, 1, D + S), R, 1, 1, D + S, dev)
+        y0 = _bf16(R, 1, 1, pad16(Em), device=dev)
+        g0 = (R, 1, 1, Kp, 1, 1, pad16(Em), 1)
+        tc_conv_down(g0, L.nhwc(hsb, 1, 1, Kp), L.nhwc(y0, 1, 1, pad16(Em)), packed(fcw, 0, pad16(Em), Kp), fcb, Em,
+                     valid=(Em, D + S))
+        convs = params[2:]
+        n_layers = len(convs) // 2
+        acts = [y0]
+        geoms = []
+        Hs, Ws = 1, 1
+        out = None
+        for i in range(n_layers):
+            Wt, b = convs[2 * i], convs[2 * i + 1]
+            Cs, Cl, k, _ = Wt.shape
+            Csp = acts[-1].shape[-1]
+            Hl, Wl = 2 * (Hs - 1) + k, 2 * (Ws - 1) + k
+            last = i == n_layers - 1
+            Clp = pad16(Cl)
+            geom = (R, Hl, Wl, Clp, Hs, Ws, Csp, k)
+            xin = L.nhwc(acts[-1], Hs, Ws, Csp)
+            if i == 0 and Hs == 1 and not last:
+                assert Clp == Cl, "dense lowering of the first ConvTranspose needs Cout % 16 == 0"
+                o = _bf16(R, Hl, Wl, Clp, device=dev)
+                wp = packed(Wt, 2, Csp, Clp)
+                tc_conv_down((R, 1, 1, Csp, 1, 1, k * k * Clp, 1), xin, L.nhwc(o, 1, 1, k * k * Clp), wp, b, k * k * Clp,
+                             act=RELU, bias_mod=Clp, valid=(k * k * Cl, Cs))
+                acts.append(o)
+            elif last:
+                out = torch.empty(R, Cl, Hl, Wl, device=dev, dtype=torch.float32)
+                tc_conv_up(geom, L.nchw(out, Hl, Wl, Cl), xin, packed(Wt, 1, Csp, Clp), b, Cl, out_f32=1, valid=(Cs, Cl))
+            else:
+                o = _bf16(R, Hl, Wl, Clp, device=dev)
+                tc_conv_up(geom, L.nhwc(o, Hl, Wl, Clp), xin, packed(Wt, 1, Csp, Clp), b, Cl, act=RELU, valid=(Cs, Cl))
+                acts.append(o)
+            geoms.append((geom, Cs, Cl))
+            Hs, Ws = Hl, Wl
+        ctx.geoms, ctx.params, ctx.dims = geoms, params, (R, D, S, Em, Kp)
+        ctx.save_for_backward(hsb, *acts)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        geoms, params = ctx.geoms, ctx.params
+        R, D, S, Em, Kp = ctx.dims
+        hsb, *acts = ctx.saved_tensors
+        dev = hsb.device
+        convs = params[2:]
+        n_layers = len(geoms)
+        g = _f32c(g)
+        (_, Hl, Wl, Clp, _, _, _, _), _, Cl = geoms[-1]
+        gb = tc_to_bf16(L.nchw(g, Hl, Wl, Cl), R, Hl, Wl, Cl, dev)
+        for i in reversed(range(n_layers)):
+            Wt, b = convs[2 * i], convs[2 * i + 1]
+            geom, Cs, Cl = geoms[i]
+            _, Hl, Wl, _, Hs, Ws, Csp, k = geom
+            Clg = gb.shape[-1]                       # channel padding of the gradient tensor as stored
+            gg = (R, Hl, Wl, Clg, Hs, Ws, Csp, k)
+            xi = acts[i]
+            tc_conv_wgrad(gg, L.nhwc(gb, Hl, Wl, Clg), L.nhwc(xi, Hs, Ws, Csp), L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl)
+            tc_colsum(gb, Cl, grad_buf(b))
+            gx = _bf16(R, Hs, Ws, Csp, device=dev)
+            tc_conv_down(gg, L.nhwc(gb, Hl, Wl, Clg), L.nhwc(gx, Hs, Ws, Csp), packed(Wt, 0, Csp, Clg), None, Cs,
+                         mask=L.nhwc(xi, Hs, Ws, Csp) if i > 0 else None, mask_mode=RELU if i > 0 else 0, valid=(Cs, Cl))
+            gb = gx
+        fcw, fcb = params[0], params[1]
+        Emp = gb.shape[-1]
+        g0 = (R, 1, 1, Kp, 1, 1, Emp, 1)
+        tc_conv_wgrad(g0, L.nhwc(hsb, 1, 1, Kp), L.nhwc(gb, 1, 1, Emp), L.ptr(grad_buf(fcw)), D + S, 1, Em, D + S)
+        tc_colsum(gb, Em, grad_buf(fcb))
+        ghs = torch.empty(R, D + S, device=dev, dtype=torch.float32)
+        tc_conv_up(g0, L.nhwc(ghs, 1, 1, D + S), L.nhwc(gb, 1, 1, Emp), packed(fcw, 1, Emp, Kp), None, D + S, out_f32=1,
+                   valid=(Em, D + S))
+        gh = ghs[:, :D].contiguous() if ctx.needs_input_grad[0] else None
+        gs = ghs[:, D:].contiguous() if ctx.needs_input_grad[1] else None
+        return (gh, gs, *([None] * len(params)))

@@ -57,6 +57,8 @@ class FusedClipAdam(torch.optim.Optimizer):
                self.flat_p.numel(), self.step_count, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
                float(g["eps"]), float(g["max_grad_norm"]), float(self.grad_scale), L.ptr(self._partial),
                L.ptr(self.grad_norm))
+        from . import ops
+        ops.bump_weight_version()                            # packed bf16 weight copies are now stale
         for st in self.state.values():
             st["step"] = torch.tensor(float(self.step_count))
 

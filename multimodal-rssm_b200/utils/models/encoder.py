@@ -254,7 +254,8 @@ class _ConvEncoder(_EncoderBase):
 
     def forward(self, observation):
         params = [p for m in self.conv if isinstance(m, nn.Conv2d) for p in (m.weight, m.bias)]
-        hidden = ops.ConvEncoderFn.apply(observation, *params)
+        fn = ops.ConvEncoderTCFn if ops.bf16_mode() else ops.ConvEncoderFn
+        hidden = fn.apply(observation, *params)
         if hidden.shape[1] != 1024:
             raise ValueError(f"conv stack produced {hidden.shape[1]} features, the reference reshapes to 1024")
         if self.embedding_size != 1024:

@@ -85,7 +85,8 @@ class _ConvDecoder(ObservationModel_base):
         T, B = h_t.shape[:2]
         params = [self.fc1.weight, self.fc1.bias]
         params += [p for m in self.conv if isinstance(m, nn.ConvTranspose2d) for p in (m.weight, m.bias)]
-        y = ops.ConvDecoderFn.apply(h_t.reshape(T * B, -1), s_t.reshape(T * B, -1), *params)
+        fn = ops.ConvDecoderTCFn if ops.bf16_mode() else ops.ConvDecoderFn
+        y = fn.apply(h_t.reshape(T * B, -1), s_t.reshape(T * B, -1), *params)
         return {"loc": y.reshape(T, B, *y.shape[1:]), "scale": 1.0}
 
 
