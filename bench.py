@@ -295,7 +295,7 @@ def run_ours(args):
     roof = roofline_of(dom_key, agg[dom_key], pk, total_ms)
     rk = "rollout_fwd:observe"
     rollout_roof = roofline_of(rk, agg[rk], pk, total_ms) if rk in agg else None
-    top = sorted(((k, d["ms"], d["n"]) for k, d in agg.items()), key=lambda x: -x[1])[:12]
+    top = sorted(((k, d["ms"], d["n"]) for k, d in agg.items()), key=lambda x: -x[1])[:60]
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
