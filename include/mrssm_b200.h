@@ -115,6 +115,24 @@ int mrssm_tc_from_bf16(const void* src, int32_t n_img, int32_t H, int32_t W, int
 /* out[c] += sum_rows x[row][c] for bf16 x [rows][Cpad] */
 int mrssm_tc_colsum(const void* x, int64_t rows, int32_t Cpad, int32_t Cvalid, float* out, void* stream);
 
+/* ---- "plane" tensor-core conv family (ksz >= 2): TMA-staged activation tile + shifted UMMA descriptors ----
+ * Same argument struct and tensor conventions as mrssm_tc_conv_*; replaces the same reference call sites
+ * (encoder.py:315-322, observation_model.py:65-74 and their autograd).  Differences:
+ *  - the gathered tensor of `up` needs channels padded to 16, of `down` to 8; bf16 outputs padded to n_out_pad;
+ *  - `up`: n_out_pad is the per-parity-class channel padding (multiple of 8) of the output tensor;
+ *  - weights are packed by mrssm_pl_pack_weight (op 0 = down, 1 = up) into [N_total][K_total] bf16 whose
+ *    shape mrssm_pl_packed_shape reports;
+ *  - mrssm_pl_describe (host only, no GPU) formats the tiling plan of a layer (op 0 down, 1 up, 2 wgrad). */
+int mrssm_pl_conv_down(const mrssm_tc_conv_args* a, void* stream);
+int mrssm_pl_conv_up(const mrssm_tc_conv_args* a, void* stream);
+int mrssm_pl_conv_wgrad(const mrssm_tc_conv_args* a, void* stream);
+int mrssm_pl_packed_shape(int32_t op, int32_t Cs_pad, int32_t Cl_pad, int32_t ksz, int32_t* N_total, int32_t* K_total);
+int mrssm_pl_pack_weight(const float* w, int64_t w_ss, int64_t w_sl, int32_t Cs_valid, int32_t Cl_valid, int32_t Cs_pad,
+                         int32_t Cl_pad, int32_t ksz, int32_t op, void* out, void* stream);
+int mrssm_pl_describe(const mrssm_tc_conv_args* a, int32_t op, char* buf, int32_t buflen);
+/* bring-up switches (descriptor-field variants); 0 = production setting */
+int mrssm_pl_set_debug(int32_t key, int32_t value);
+
 /* ---- the RSSM rollout ------------------------------------------------------------------------
  * Replaces MultimodalTransitionModel.forward (utils/models/transition_model.py:200-285), its
  * single-modal twin TransitionModel.forward (:50-114), nn.GRUCell (:160,235), the prior head and

@@ -1,0 +1,808 @@
+// "Plane" convolution kernels for sm_100a: stride-2 Conv2d / ConvTranspose2d forward, dgrad and wgrad on
+// tcgen05 tensor cores with the activation tile loaded ONCE into shared memory by TMA.
+//
+// Idea.  A stride-2 convolution over the space-to-depth (2x2 parity) view of its input is a stride-1
+// correlation, and a stride-2 transposed convolution is, per output-parity class, a stride-1 correlation
+// over the zero-padded input.  For a stride-1 correlation the im2col matrix of tap (a,b) is the activation
+// itself shifted by a*pitch+b pixels.  So the activation tile is put in shared memory as channel-chunk
+// planes  plane[chunk][pixel][8 channels]  (16 bytes per pixel, pixel index linear over the padded tile) —
+// exactly the un-swizzled UMMA operand layout (core matrix = 8 pixels x 16 bytes, SBO = 128 B, LBO = plane
+// stride) — and every tap is the SAME planes addressed through a descriptor whose start address is advanced
+// by shift*16 bytes.  im2col is never materialised, not even in shared memory; TMA does the parity split
+// (one tensor map per parity with doubled strides) and the zero padding (out-of-bounds fill).
+//
+//   fwd-type (down / up):  D[128 pixels][BN] += A(shifted planes, K-major) * W[BN][64]   (W streamed by TMA,
+//       128B-swizzled ring; accumulators for several 128-pixel blocks live in TMEM, two sets ping-pong
+//       between the MMA issuer and the 4 epilogue warps: bias, activation, act'-mask, bf16 NHWC or fp32 strided)
+//   wgrad:  D[128 cs][2*Cl] += small^T (MN-major planes) * large parity planes shifted by the tap (MN-major);
+//       one accumulator per (kh, kw/2) tap group, contraction over pixels, accumulated across all tiles of
+//       a CTA in TMEM, then fp32 atomics into the PyTorch-layout master gradient.
+#include <cuda.h>
+#include <algorithm>
+#include <string.h>
+#include "tc_common.cuh"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+enum { OP_DOWN = 0, OP_UP = 1 };
+constexpr int NTHREADS = 256;
+constexpr int SMEM_TOTAL = 227 * 1024 - 4096;   // dynamic budget: 227 KB minus the 1 KB alignment slack and the static barriers/tables
+
+int g_dbg[4] = {0, 0, 0, 0};   // [0] fwd: swap LBO/SBO of the A descriptor, [1] wgrad: swap LBO/SBO (bring-up switches)
+
+struct T4 {
+    const void* p;
+    long long sI, sH, sW, sC;
+};
+inline T4 cvt(const mrssm_t4& t) { return T4{t.ptr, t.sI, t.sH, t.sW, t.sC}; }
+
+// ---------------------------------------------------------------------------------------------------
+// TMA + descriptors
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+// un-swizzled (INTERLEAVE) operand descriptor.
+//   K-major : core matrix = 8 rows(M/N) x 16 B(K); SBO = byte stride between 8-row groups, LBO = between the two 8-element K chunks
+//   MN-major: core matrix = 8 rows(K)   x 16 B(MN); LBO = byte stride between 8-row K groups, SBO = between 8-element MN chunks
+__device__ __forceinline__ uint64_t smem_desc_plain(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// activation map: bf16 [N][Y][X][C] with byte strides, box {8, bx, by, bi}, no swizzle, zero OOB fill
+int make_act_map(CUtensorMap* m, const void* base, long long C, long long X, long long Y, long long N, long long sx, long long sy,
+                 long long sn, int bx, int by, int bi) {
+    EncodeTiledFn enc = get_encode();
+    MRSSM_CHECK(enc, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)sx, (cuuint64_t)sy, (cuuint64_t)sn};
+    cuuint32_t box[4] = {8, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bi};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    MRSSM_CHECK(X >= 1 && Y >= 1 && N >= 1 && bx <= 256 && by <= 256 && bi <= 256 && sx % 16 == 0 && sy % 16 == 0 && sn % 16 == 0 &&
+                    ((uintptr_t)base & 15) == 0,
+                "plane conv: activation tensor not TMA-addressable (dims %lld %lld %lld %lld strides %lld %lld %lld box %d %d %d)", C, X, Y,
+                N, sx, sy, sn, bx, by, bi);
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MRSSM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: %d (dims %lld %lld %lld %lld strides %lld %lld %lld box %d %d %d)",
+                (int)r, C, X, Y, N, sx, sy, sn, bx, by, bi);
+    return 0;
+}
+// weight map: bf16 [N_total][K_total] row-major, box {64, BN}, 128B swizzle
+int make_w_map(CUtensorMap* m, const void* base, long long K_total, long long N_total, int BN) {
+    EncodeTiledFn enc = get_encode();
+    MRSSM_CHECK(enc, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)K_total, (cuuint64_t)N_total};
+    cuuint64_t strides[1] = {(cuuint64_t)K_total * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MRSSM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight) failed: %d (K %lld N %lld BN %d)", (int)r, K_total, N_total, BN);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward-type kernel (down / up)
+// ---------------------------------------------------------------------------------------------------
+struct FwdP {
+    int op;
+    int n_img, n_groups, n_bands, BI, BX, BY, TH;
+    int Hv, Wv;                 // valid output extent in position space (down: Hs,Ws; up: ceil(Hl/2),ceil(Wl/2))
+    int planes, ppm;            // A planes per tile, planes per tensor map
+    int PS, plane_bytes;        // plane stride / bytes written by TMA per plane
+    int x0, y0;                 // box origin (up: -(nt-1))
+    int n_ksteps, nkb, nt, J;
+    int BN, n_ntiles;
+    int MB_total, MBs, n_passes, n_sets, set_cols;
+    int NA, NB;
+    int act, mask_mode, out_f32, n_valid, Cop, Ho, Wo;
+    int a_stage_bytes;
+    int dbg_swap;
+    T4 out, mask;
+    const float* bias;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUtensorMap mA2,
+                 const __grid_constant__ CUtensorMap mA3, const __grid_constant__ CUtensorMap mB, const FwdP P) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t a_full[2], a_empty[2], b_full[8], b_empty[8], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ uint32_t ks_off[320];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_stage = (uint32_t)P.BN * 128u;
+    const uint32_t smemA = smem0 + (uint32_t)P.NB * b_stage;
+    const int n_tiles = P.n_groups * P.n_bands;
+
+    for (int ks = tid; ks < P.n_ksteps; ks += NTHREADS) {
+        int j = ks % P.J, t = ks / P.J, b = t % P.nt, r = t / P.nt;
+        int plane, shift;
+        if (P.op == OP_DOWN) {           // r = kh
+            plane = (r & 1) * 2 * P.J + 2 * j;
+            shift = (r >> 1) * P.BX + b;
+        } else {                         // r = a
+            plane = 2 * j;
+            shift = (P.nt - 1 - r) * P.BX + (P.nt - 1 - b);
+        }
+        ks_off[ks] = (uint32_t)plane * (uint32_t)P.PS + (uint32_t)shift * 16u;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(tc::smem_u32(&a_full[s]), 1);
+            tc::mbar_init(tc::smem_u32(&a_empty[s]), 1);
+            tc::mbar_init(tc::smem_u32(&acc_full[s]), 1);
+            tc::mbar_init(tc::smem_u32(&acc_empty[s]), 4);
+        }
+        for (int s = 0; s < 8; ++s) {
+            tc::mbar_init(tc::smem_u32(&b_full[s]), 1);
+            tc::mbar_init(tc::smem_u32(&b_empty[s]), 1);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            uint32_t acnt = 0, bcnt = 0;
+            auto issue_A = [&](int tile) {
+                const int sa = acnt % P.NA;
+                tc::mbar_wait(tc::smem_u32(&a_empty[sa]), ((acnt / P.NA) & 1) ^ 1);
+                const uint32_t bar = tc::smem_u32(&a_full[sa]);
+                mbar_expect_tx(bar, (uint32_t)P.planes * (uint32_t)P.plane_bytes);
+                const int ig = tile / P.n_bands, band = tile - ig * P.n_bands;
+                const uint32_t dst = smemA + (uint32_t)sa * (uint32_t)P.a_stage_bytes;
+                for (int q = 0; q < P.planes; ++q) {
+                    const int mi = q / P.ppm, c0 = (q - mi * P.ppm) * 8;
+                    const CUtensorMap* m = mi == 0 ? &mA0 : (mi == 1 ? &mA1 : (mi == 2 ? &mA2 : &mA3));
+                    tma_load_4d(dst + (uint32_t)q * (uint32_t)P.PS, m, c0, P.x0, band * P.TH + P.y0, ig * P.BI, bar);
+                }
+                ++acnt;
+            };
+            int tile = blockIdx.x;
+            if (tile < n_tiles) issue_A(tile);
+            for (; tile < n_tiles; tile += gridDim.x) {
+                const int next = tile + gridDim.x;
+                if (P.NA > 1 && next < n_tiles) issue_A(next);
+                for (int it = 0; it < P.n_ntiles * P.n_passes; ++it) {
+                    const int nti = it / P.n_passes;
+                    for (int kb = 0; kb < P.nkb; ++kb) {
+                        const int sb = bcnt % P.NB;
+                        tc::mbar_wait(tc::smem_u32(&b_empty[sb]), ((bcnt / P.NB) & 1) ^ 1);
+                        const uint32_t bar = tc::smem_u32(&b_full[sb]);
+                        mbar_expect_tx(bar, b_stage);
+                        tma_load_2d(smem0 + (uint32_t)sb * b_stage, &mB, kb * 64, nti * P.BN, bar);
+                        ++bcnt;
+                    }
+                }
+                if (P.NA == 1 && next < n_tiles) issue_A(next);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer ------------------------------
+        if (lane == 0) {
+            const uint32_t idesc = tc::idesc_bf16(128, P.BN, 0, 0);
+            uint32_t acnt = 0, bcnt = 0, ccnt = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int sa = acnt % P.NA;
+                tc::mbar_wait(tc::smem_u32(&a_full[sa]), (acnt / P.NA) & 1);
+                tc::tc_fence_after();
+                const uint32_t sA = smemA + (uint32_t)sa * (uint32_t)P.a_stage_bytes;
+                for (int it = 0; it < P.n_ntiles * P.n_passes; ++it) {
+                    const int pass = it % P.n_passes;
+                    const int set = ccnt % P.n_sets;
+                    tc::mbar_wait(tc::smem_u32(&acc_empty[set]), ((ccnt / P.n_sets) & 1) ^ 1);
+                    tc::tc_fence_after();
+                    const int mb0 = pass * P.MBs, nmb = min(P.MBs, P.MB_total - mb0);
+                    const uint32_t tacc = tmem_base + (uint32_t)(set * P.set_cols);
+                    for (int kb = 0; kb < P.nkb; ++kb) {
+                        const int sb = bcnt % P.NB;
+                        tc::mbar_wait(tc::smem_u32(&b_full[sb]), (bcnt / P.NB) & 1);
+                        tc::tc_fence_after();
+                        const uint32_t sB = smem0 + (uint32_t)sb * b_stage;
+                        const int nk = min(4, P.n_ksteps - kb * 4);
+                        for (int mb = 0; mb < nmb; ++mb) {
+                            const uint32_t arow = sA + (uint32_t)(mb0 + mb) * 2048u;
+                            for (int j = 0; j < nk; ++j) {
+                                uint64_t ad = P.dbg_swap ? smem_desc_plain(arow + ks_off[kb * 4 + j], 128, (uint32_t)P.PS)
+                                                         : smem_desc_plain(arow + ks_off[kb * 4 + j], (uint32_t)P.PS, 128);
+                                uint64_t bd = tc::smem_desc_sw128(sB + j * 32, 16, 1024);
+                                tc::umma_bf16(tacc + (uint32_t)(mb * P.BN), ad, bd, idesc, (kb | j) != 0);
+                            }
+                        }
+                        tc::umma_commit(tc::smem_u32(&b_empty[sb]));
+                        ++bcnt;
+                    }
+                    tc::umma_commit(tc::smem_u32(&acc_full[set]));
+                    ++ccnt;
+                }
+                tc::umma_commit(tc::smem_u32(&a_empty[sa]));
+                ++acnt;
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ------------------------------ epilogue ------------------------------
+        const int q = warp - 4;
+        const int IP = P.BY * P.BX;
+        uint32_t ccnt = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int ig = tile / P.n_bands, band = tile - ig * P.n_bands;
+            for (int it = 0; it < P.n_ntiles * P.n_passes; ++it) {
+                const int nti = it / P.n_passes, pass = it % P.n_passes;
+                const int set = ccnt % P.n_sets;
+                tc::mbar_wait(tc::smem_u32(&acc_full[set]), (ccnt / P.n_sets) & 1);
+                tc::tc_fence_after();
+                const int mb0 = pass * P.MBs, nmb = min(P.MBs, P.MB_total - mb0);
+                for (int mb = 0; mb < nmb; ++mb) {
+                    const int p = (mb0 + mb) * 128 + q * 32 + lane;
+                    const int i = p / IP, r = p - i * IP, yr = r / P.BX, x = r - yr * P.BX;
+                    const int img = ig * P.BI + i, y = band * P.TH + yr;
+                    const bool row_ok = i < P.BI && img < P.n_img && yr < P.TH && y < P.Hv && x < P.Wv;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * P.set_cols + mb * P.BN);
+                    for (int c0 = 0; c0 < P.BN; c0 += 16) {
+                        float v[16];
+                        tc::tmem_ld16(taddr + c0, v);
+                        if (!row_ok) continue;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int n = nti * P.BN + c0 + 8 * h;
+                            int cl0 = n, yy = y, xx = x;
+                            if (P.op == OP_UP) {
+                                const int cls = n / P.Cop;
+                                cl0 = n - cls * P.Cop;
+                                yy = 2 * y + (cls >> 1);
+                                xx = 2 * x + (cls & 1);
+                                if (yy >= P.Ho || xx >= P.Wo) continue;
+                            }
+                            float xv[8];
+                            uint4 mk = make_uint4(0, 0, 0, 0);
+                            if (P.mask_mode) {
+                                const bf16* mp = (const bf16*)P.mask.p + img * P.mask.sI + yy * P.mask.sH + xx * P.mask.sW + cl0;
+                                mk = *reinterpret_cast<const uint4*>(mp);
+                            }
+                            const bf16* mh = reinterpret_cast<const bf16*>(&mk);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const int c = cl0 + e;
+                                float t = v[8 * h + e];
+                                if (P.bias && c < P.n_valid) t += __ldg(P.bias + c);
+                                t = act_apply(t, P.act);
+                                if (P.mask_mode) t *= act_grad_from_out(__bfloat162float(mh[e]), P.mask_mode);
+                                xv[e] = c < P.n_valid ? t : 0.f;
+                            }
+                            if (P.out_f32) {
+                                float* op = (float*)P.out.p + img * P.out.sI + yy * P.out.sH + xx * P.out.sW;
+#pragma unroll
+                                for (int e = 0; e < 8; ++e)
+                                    if (cl0 + e < P.n_valid) op[(long long)(cl0 + e) * P.out.sC] = xv[e];
+                            } else {
+                                __align__(16) bf16 hb[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) hb[e] = __float2bfloat16(xv[e]);
+                                bf16* op = (bf16*)P.out.p + img * P.out.sI + yy * P.out.sH + xx * P.out.sW + cl0;
+                                *reinterpret_cast<uint4*>(op) = *reinterpret_cast<const uint4*>(hb);
+                            }
+                        }
+                    }
+                }
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[set]));
+                ++ccnt;
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// planner for the forward-type kernel
+// ---------------------------------------------------------------------------------------------------
+int plan_fwd(const mrssm_tc_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
+    memset(&P, 0, sizeof(P));
+    const int k = a->ksz, nt = (k + 1) / 2;
+    P.op = op;
+    P.n_img = a->n_img;
+    P.nt = nt;
+    int Cp, N_total;
+    if (op == OP_DOWN) {
+        Cp = a->Cl;
+        MRSSM_CHECK(Cp % 8 == 0, "plane down: source channels %d must be padded to 8", Cp);
+        P.Hv = a->Hs; P.Wv = a->Ws;
+        P.planes = 4 * (Cp / 8); P.ppm = Cp / 8;
+        P.x0 = P.y0 = 0;
+        P.J = Cp / 8;
+        P.n_ksteps = k * nt * P.J;
+        N_total = a->n_out_pad;
+        P.Cop = N_total;
+        P.Ho = a->Hs; P.Wo = a->Ws;
+    } else {
+        Cp = a->Cs;
+        MRSSM_CHECK(Cp % 16 == 0, "plane up: source channels %d must be padded to 16", Cp);
+        P.Hv = (a->Hl + 1) / 2; P.Wv = (a->Wl + 1) / 2;
+        P.planes = Cp / 8; P.ppm = P.planes;
+        P.x0 = P.y0 = -(nt - 1);
+        P.J = Cp / 16;
+        P.n_ksteps = nt * nt * P.J;
+        MRSSM_CHECK(a->n_out_pad % 8 == 0, "plane up: n_out_pad %d must be a multiple of 8", a->n_out_pad);
+        N_total = 4 * a->n_out_pad;
+        P.Cop = a->n_out_pad;
+        P.Ho = a->Hl; P.Wo = a->Wl;
+    }
+    MRSSM_CHECK(P.n_ksteps <= 320, "plane conv: %d K-steps exceed the table", P.n_ksteps);
+    MRSSM_CHECK(N_total % 16 == 0, "plane conv: %d output columns not a multiple of 16", N_total);
+    P.nkb = (P.n_ksteps + 3) / 4;
+    P.BN = N_total <= 256 ? N_total : (N_total % 256 == 0 ? 256 : (N_total % 128 == 0 ? 128 : 64));
+    MRSSM_CHECK(N_total % P.BN == 0, "plane conv: %d output columns not tileable", N_total);
+    P.n_ntiles = N_total / P.BN;
+    P.n_sets = 2; P.set_cols = 256;
+    P.MBs = std::max(1, 256 / P.BN);
+    P.NB = P.BN >= 256 ? 3 : 4;
+    P.BX = P.Wv + nt - 1;
+    const int maxshift = (nt - 1) * P.BX + nt - 1;
+    // a single 128-row block of the smallest tile must fit next to the weight ring: shrink the ring if it does not
+    while (P.NB > 2 && (long long)P.planes * ((128 + maxshift) * 16 + 128) > SMEM_TOTAL - (long long)P.NB * P.BN * 128) --P.NB;
+    const long long bring = (long long)P.NB * P.BN * 128;
+    const long long avail = SMEM_TOTAL - bring;
+    auto stage_bytes = [&](int BI, int BY, int TH, int& MB_total, int& PS) {
+        long long Lout = ((long long)(BI - 1) * BY + (TH - 1)) * P.BX + P.Wv;
+        MB_total = (int)((Lout + 127) / 128);
+        long long ps = std::max<long long>((long long)BI * BY * P.BX * 16, ((long long)MB_total * 128 + maxshift) * 16);
+        PS = (int)((ps + 127) / 128 * 128);
+        return (long long)P.planes * PS;
+    };
+    int MBt, PS;
+    const int BYfull = P.Hv + nt - 1;
+    long long one = stage_bytes(1, BYfull, P.Hv, MBt, PS);
+    if (one <= avail) {
+        P.NA = (2 * one <= avail) ? 2 : 1;
+        const long long budget = avail / P.NA;
+        // images per tile: the smallest count whose 128-row blocks are (nearly) as full as the best feasible one
+        double max_eff = -1.0;
+        int BImax = 0;
+        for (int BI = 1; BI <= std::min(a->n_img, 256); ++BI) {
+            long long sb = stage_bytes(BI, BYfull, P.Hv, MBt, PS);
+            if (sb > budget || PS >= 262144 || MBt > 32) break;
+            BImax = BI;
+            max_eff = std::max(max_eff, (double)BI * P.Hv * P.Wv / ((double)MBt * 128));
+        }
+        int best = 1;
+        for (int BI = 1; BI <= BImax; ++BI) {
+            stage_bytes(BI, BYfull, P.Hv, MBt, PS);
+            if ((double)BI * P.Hv * P.Wv / ((double)MBt * 128) >= max_eff - 0.02) {
+                best = BI;
+                break;
+            }
+        }
+        P.BI = best; P.BY = BYfull; P.TH = P.Hv; P.n_bands = 1;
+    } else {
+        P.NA = 2;
+        const long long budget = avail / 2;
+        int TH = P.Hv;
+        while (TH > 1 && stage_bytes(1, TH + nt - 1, TH, MBt, PS) > budget) --TH;
+        MRSSM_CHECK(stage_bytes(1, TH + nt - 1, TH, MBt, PS) <= budget, "plane conv: a single row band does not fit shared memory");
+        P.n_bands = (P.Hv + TH - 1) / TH;
+        TH = (P.Hv + P.n_bands - 1) / P.n_bands;
+        P.BI = 1; P.TH = TH; P.BY = TH + nt - 1;
+    }
+    P.a_stage_bytes = (int)stage_bytes(P.BI, P.BY, P.TH, P.MB_total, P.PS);
+    MRSSM_CHECK(P.PS / 16 < 16384, "plane conv: plane stride %d too large for the descriptor", P.PS);
+    P.plane_bytes = P.BI * P.BY * P.BX * 16;
+    P.n_groups = (a->n_img + P.BI - 1) / P.BI;
+    P.n_passes = (P.MB_total + P.MBs - 1) / P.MBs;
+    smem_bytes = (size_t)bring + (size_t)P.NA * P.a_stage_bytes + 1024;
+    MRSSM_CHECK(smem_bytes <= (size_t)SMEM_TOTAL + 1024, "plane conv: shared memory plan %zu too large", smem_bytes);
+    // epilogue
+    P.act = a->act; P.mask_mode = a->mask.ptr ? a->mask_mode : 0; P.out_f32 = a->out_f32;
+    P.n_valid = a->n_out_valid;
+    const mrssm_t4& out = (op == OP_DOWN) ? a->small : a->large;
+    P.out = cvt(out); P.mask = cvt(a->mask);
+    P.bias = a->bias;
+    P.dbg_swap = g_dbg[0];
+    MRSSM_CHECK(P.out_f32 || (out.sC == 1 && out.sW % 8 == 0 && out.sH % 8 == 0 && out.sI % 8 == 0 && ((uintptr_t)out.ptr & 15) == 0),
+                "plane conv: bf16 output must be NHWC with channels padded to 8");
+    MRSSM_CHECK(!P.mask_mode || (a->mask.sC == 1 && a->mask.sW % 8 == 0 && a->mask.sH % 8 == 0 && a->mask.sI % 8 == 0),
+                "plane conv: mask must be bf16 NHWC with channels padded to 8");
+    return 0;
+}
+
+int launch_fwd(const mrssm_tc_conv_args* a, int op, cudaStream_t st) {
+    MRSSM_CHECK(a && a->large.ptr && a->small.ptr && a->wpacked, "plane conv: null tensor");
+    MRSSM_CHECK(a->ksz >= 2, "plane conv: kernel size %d (dense layers use mrssm_tc_conv_*)", a->ksz);
+    FwdP P;
+    size_t smem;
+    if (int rc = plan_fwd(a, op, P, smem)) return rc;
+    CUtensorMap mA[4], mB;
+    memset(mA, 0, sizeof(mA));
+    if (op == OP_DOWN) {
+        const mrssm_t4& s = a->large;
+        MRSSM_CHECK(s.sC == 1, "plane down: source must be channel-contiguous");
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                const char* base = (const char*)s.ptr + 2 * (py * s.sH + px * s.sW);
+                long long X = (a->Wl - px + 1) / 2, Y = (a->Hl - py + 1) / 2;
+                if (X < 1) X = 1;
+                if (Y < 1) Y = 1;
+                if (int rc = make_act_map(&mA[py * 2 + px], base, a->Cl, X, Y, a->n_img, 4 * s.sW, 4 * s.sH, 2 * s.sI, P.BX, P.BY, P.BI)) return rc;
+            }
+    } else {
+        const mrssm_t4& s = a->small;
+        MRSSM_CHECK(s.sC == 1, "plane up: source must be channel-contiguous");
+        if (int rc = make_act_map(&mA[0], s.ptr, a->Cs, a->Ws, a->Hs, a->n_img, 2 * s.sW, 2 * s.sH, 2 * s.sI, P.BX, P.BY, P.BI)) return rc;
+        mA[1] = mA[2] = mA[3] = mA[0];
+    }
+    const long long K_total = (long long)P.nkb * 64;
+    const long long N_total = (long long)P.BN * P.n_ntiles;
+    if (int rc = make_w_map(&mB, a->wpacked, K_total, N_total, P.BN)) return rc;
+    const int n_tiles = P.n_groups * P.n_bands;
+    int grid = std::min(n_tiles, 148);
+    smem = std::max<size_t>(smem, 120 * 1024);       // > half an SM: one CTA per SM (each allocates all 512 TMEM columns)
+    MRSSM_CUDA(cudaFuncSetAttribute(plane_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    plane_fwd_kernel<<<grid, NTHREADS, smem, st>>>(mA[0], mA[1], mA[2], mA[3], mB, P);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight packing for the forward-type kernel:  out[n][k], k = kstep*16 + e  (zero padded to K_total)
+// ---------------------------------------------------------------------------------------------------
+__global__ void pack_plane_kernel(const float* __restrict__ w, long long w_ss, long long w_sl, int Cs_valid, int Cl_valid, int Csp, int Clp,
+                                  int ksz, int op, int N_total, int K_total, bf16* __restrict__ out) {
+    const int nt = (ksz + 1) / 2;
+    const long long total = (long long)N_total * K_total;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(i % K_total), n = (int)(i / K_total);
+        const int ks = kk >> 4, e = kk & 15;
+        float v = 0.f;
+        if (op == OP_DOWN) {
+            const int J = Clp / 8;
+            const int j = ks % J, t = ks / J, b = t % nt, kh = t / nt;
+            const int pl = 2 * j + (e >> 3);
+            const int px = pl / J, chunk = pl - px * J;
+            const int cl = chunk * 8 + (e & 7), kw = 2 * b + px;
+            if (n < Cs_valid && cl < Cl_valid && kh < ksz && kw < ksz) v = w[n * w_ss + cl * w_sl + kh * ksz + kw];
+        } else {
+            const int J = Csp / 16;
+            const int j = ks % J, t = ks / J, b = t % nt, aa = t / nt;
+            const int cls = n / Clp, cl = n - cls * Clp;
+            const int cs = (2 * j + (e >> 3)) * 8 + (e & 7);
+            const int kh = (cls >> 1) + 2 * aa, kw = (cls & 1) + 2 * b;
+            if (aa < nt && cls < 4 && cl < Cl_valid && cs < Cs_valid && kh < ksz && kw < ksz) v = w[cs * w_ss + cl * w_sl + kh * ksz + kw];
+        }
+        out[i] = __float2bfloat16(v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// wgrad
+// ---------------------------------------------------------------------------------------------------
+struct WgP {
+    int n_img, n_groups, n_bands, BI, BX, BY, TH, SBY;
+    int nS, nL, cpl;            // small planes per m-half, large planes, chunks per large parity plane group (Clp/8)
+    int PS_s, PS_l, small_bytes, large_bytes, offL, stage_bytes;
+    int nksteps;                // K steps (16 pixels) per tile
+    int ksz, nt, Clp, Csp, N;
+    int NG, gpp, n_cpass, n_mhalf;
+    int NA, zero_bytes, dbg_swap;
+    int cs_valid, cl_valid;
+    float* dw;
+    long long w_ss, w_sl;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant__ CUtensorMap mL0, const __grid_constant__ CUtensorMap mL1,
+                   const __grid_constant__ CUtensorMap mL2, const __grid_constant__ CUtensorMap mL3, const WgP P) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t a_full[2], a_empty[2], acc_full;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem0 - tc::smem_u32(smem_raw));
+    const int n_tiles = P.n_groups * P.n_bands;
+    const int cpass = blockIdx.y % P.n_cpass, mhalf = blockIdx.y / P.n_cpass;
+    const int g0 = cpass * P.gpp, ng = min(P.gpp, P.NG - g0);
+
+    // zero the operand stages once: pixels the TMA boxes never write (row tails, M/K round-up) must read as 0
+    for (int i = tid * 16; i < P.zero_bytes; i += NTHREADS * 16) *reinterpret_cast<uint4*>(smem_al + i) = make_uint4(0, 0, 0, 0);
+    tc::fence_proxy_async();
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(tc::smem_u32(&a_full[s]), 1);
+            tc::mbar_init(tc::smem_u32(&a_empty[s]), 1);
+        }
+        tc::mbar_init(tc::smem_u32(&acc_full), 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t acnt = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int sa = acnt % P.NA;
+                tc::mbar_wait(tc::smem_u32(&a_empty[sa]), ((acnt / P.NA) & 1) ^ 1);
+                const uint32_t bar = tc::smem_u32(&a_full[sa]);
+                mbar_expect_tx(bar, (uint32_t)P.nS * (uint32_t)P.small_bytes + (uint32_t)P.nL * (uint32_t)P.large_bytes);
+                const int ig = tile / P.n_bands, band = tile - ig * P.n_bands;
+                const uint32_t dst = smem0 + (uint32_t)sa * (uint32_t)P.stage_bytes;
+                for (int q = 0; q < P.nS; ++q)
+                    tma_load_4d(dst + (uint32_t)q * (uint32_t)P.PS_s, &mS, (mhalf * 16 + q) * 8, 0, band * P.TH, ig * P.BI, bar);
+                for (int q = 0; q < P.nL; ++q) {
+                    const int mi = q / P.cpl, c0 = (q - mi * P.cpl) * 8;
+                    const CUtensorMap* m = mi == 0 ? &mL0 : (mi == 1 ? &mL1 : (mi == 2 ? &mL2 : &mL3));
+                    tma_load_4d(dst + (uint32_t)P.offL + (uint32_t)q * (uint32_t)P.PS_l, m, c0, 0, band * P.TH, ig * P.BI, bar);
+                }
+                ++acnt;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::idesc_bf16(128, P.N, 1, 1);
+            uint32_t acnt = 0;
+            bool first = true;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int sa = acnt % P.NA;
+                tc::mbar_wait(tc::smem_u32(&a_full[sa]), (acnt / P.NA) & 1);
+                tc::tc_fence_after();
+                const uint32_t sS = smem0 + (uint32_t)sa * (uint32_t)P.stage_bytes, sL = sS + (uint32_t)P.offL;
+                for (int ks = 0; ks < P.nksteps; ++ks) {
+                    const uint64_t ad = P.dbg_swap ? smem_desc_plain(sS + (uint32_t)ks * 256u, (uint32_t)P.PS_s, 128)
+                                                   : smem_desc_plain(sS + (uint32_t)ks * 256u, 128, (uint32_t)P.PS_s);
+                    for (int gi = 0; gi < ng; ++gi) {
+                        const int g = g0 + gi, kh = g / P.nt, b = g - kh * P.nt;
+                        const uint32_t boff = (uint32_t)((kh & 1) * 2 * P.cpl) * (uint32_t)P.PS_l + (uint32_t)((kh >> 1) * P.BX + b + ks * 16) * 16u;
+                        const uint64_t bd = P.dbg_swap ? smem_desc_plain(sL + boff, (uint32_t)P.PS_l, 128) : smem_desc_plain(sL + boff, 128, (uint32_t)P.PS_l);
+                        tc::umma_bf16(tmem_base + (uint32_t)(gi * P.N), ad, bd, idesc, !(first && ks == 0));
+                    }
+                }
+                tc::umma_commit(tc::smem_u32(&a_empty[sa]));
+                first = false;
+                ++acnt;
+            }
+            tc::umma_commit(tc::smem_u32(&acc_full));
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        const int q = warp - 4;
+        tc::mbar_wait(tc::smem_u32(&acc_full), 0);
+        tc::tc_fence_after();
+        const int cs = mhalf * 128 + q * 32 + lane;
+        for (int gi = 0; gi < ng; ++gi) {
+            const int g = g0 + gi, kh = g / P.nt, b = g - kh * P.nt;
+            for (int c0 = 0; c0 < P.N; c0 += 16) {
+                float v[16];
+                tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(gi * P.N + c0), v);
+                if (cs >= P.cs_valid) continue;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int c = c0 + e, px = c / P.Clp, cl = c - px * P.Clp, kw = 2 * b + px;
+                    if (cl < P.cl_valid && kw < P.ksz) atomicAdd(P.dw + cs * P.w_ss + cl * P.w_sl + kh * P.ksz + kw, v[e]);
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+int plan_wgrad(const mrssm_tc_conv_args* a, WgP& P, size_t& smem_bytes, int& splits) {
+    memset(&P, 0, sizeof(P));
+    const int k = a->ksz, nt = (k + 1) / 2;
+    P.n_img = a->n_img; P.ksz = k; P.nt = nt;
+    P.Clp = a->Cl; P.Csp = a->Cs;
+    MRSSM_CHECK(P.Clp % 8 == 0 && P.Csp % 8 == 0, "plane wgrad: channels must be padded to 8 (Cl %d Cs %d)", P.Clp, P.Csp);
+    P.N = 2 * P.Clp;
+    MRSSM_CHECK(P.N % 16 == 0 && P.N <= 256, "plane wgrad: 2*Cl = %d must be <= 256", P.N);
+    P.cpl = P.Clp / 8;
+    P.nL = 4 * P.cpl;
+    P.n_mhalf = (P.Csp + 127) / 128;
+    P.nS = std::min(16, P.Csp / 8);
+    P.NG = k * nt;
+    P.gpp = std::min(P.NG, 512 / P.N);
+    P.n_cpass = (P.NG + P.gpp - 1) / P.gpp;
+    P.gpp = (P.NG + P.n_cpass - 1) / P.n_cpass;
+    P.BX = a->Ws + nt - 1;
+    const int maxshift = (nt - 1) * P.BX + nt - 1;
+    auto plan = [&](int BI, int TH, bool banded, int NA) -> long long {
+        const int BY = TH + nt - 1;
+        const int SBY = banded ? TH : BY;
+        const long long L = banded ? (long long)TH * P.BX : (long long)BI * BY * P.BX;
+        const long long L16 = (L + 15) / 16 * 16;
+        P.BI = BI; P.TH = TH; P.BY = BY; P.SBY = SBY; P.NA = NA;
+        P.small_bytes = BI * SBY * P.BX * 16;
+        P.large_bytes = BI * BY * P.BX * 16;
+        P.PS_s = (int)((L16 * 16 + 127) / 128 * 128);
+        P.PS_l = (int)(((L16 + maxshift) * 16 + 127) / 128 * 128);
+        P.offL = P.nS * P.PS_s;
+        P.stage_bytes = P.offL + P.nL * P.PS_l;
+        P.nksteps = (int)(L16 / 16);
+        const long long span = 16LL * P.PS_s + 0;    // an M=128 descriptor walks 16 chunk planes from the stage start
+        const long long last = std::max<long long>(P.stage_bytes, span);
+        P.zero_bytes = (int)((NA - 1) * (long long)P.stage_bytes + last);
+        return P.zero_bytes;
+    };
+    const long long avail = SMEM_TOTAL;
+    const int Hs = a->Hs;
+    bool done = false;
+    // whole images, double buffered, as many images per tile as fit (capped so a tile stays a few thousand pixels)
+    if (plan(1, Hs, false, 2) <= avail) {
+        int BI = 1;
+        while (BI < std::min(a->n_img, 256) && (long long)(BI + 1) * (Hs + nt - 1) * P.BX <= 4096 && plan(BI + 1, Hs, false, 2) <= avail) ++BI;
+        plan(BI, Hs, false, 2);
+        P.n_bands = 1;
+        done = true;
+    }
+    if (!done) {
+        int TH = Hs;
+        while (TH > 1 && plan(1, TH, true, 2) > avail) --TH;
+        MRSSM_CHECK(plan(1, TH, true, 2) <= avail, "plane wgrad: a single row band does not fit shared memory");
+        P.n_bands = (Hs + TH - 1) / TH;
+        TH = (Hs + P.n_bands - 1) / P.n_bands;
+        plan(1, TH, true, 2);
+    }
+    MRSSM_CHECK(P.PS_s / 16 < 16384 && P.PS_l / 16 < 16384, "plane wgrad: plane stride too large");
+    P.n_groups = (a->n_img + P.BI - 1) / P.BI;
+    smem_bytes = (size_t)P.zero_bytes + 1024;
+    const int n_tiles = P.n_groups * P.n_bands;
+    const int ypass = P.n_cpass * P.n_mhalf;
+    splits = std::max(1, std::min(n_tiles, (148 + ypass - 1) / ypass));
+    P.cs_valid = a->cs_valid; P.cl_valid = a->cl_valid;
+    P.dw = a->dweight; P.w_ss = a->w_ss; P.w_sl = a->w_sl;
+    P.dbg_swap = g_dbg[1];
+    return 0;
+}
+
+int launch_wgrad(const mrssm_tc_conv_args* a, cudaStream_t st) {
+    MRSSM_CHECK(a && a->large.ptr && a->small.ptr && a->dweight, "plane wgrad: null tensor");
+    MRSSM_CHECK(a->ksz >= 2, "plane wgrad: kernel size %d (dense layers use mrssm_tc_conv_wgrad)", a->ksz);
+    WgP P;
+    size_t smem;
+    int splits;
+    if (int rc = plan_wgrad(a, P, smem, splits)) return rc;
+    CUtensorMap mS, mL[4];
+    const mrssm_t4& s = a->small;
+    const mrssm_t4& l = a->large;
+    MRSSM_CHECK(s.sC == 1 && l.sC == 1, "plane wgrad: tensors must be channel-contiguous");
+    if (int rc = make_act_map(&mS, s.ptr, a->Cs, a->Ws, a->Hs, a->n_img, 2 * s.sW, 2 * s.sH, 2 * s.sI, P.BX, P.SBY, P.BI)) return rc;
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            const char* base = (const char*)l.ptr + 2 * (py * l.sH + px * l.sW);
+            long long X = std::max(1, (a->Wl - px + 1) / 2), Y = std::max(1, (a->Hl - py + 1) / 2);
+            if (int rc = make_act_map(&mL[py * 2 + px], base, a->Cl, X, Y, a->n_img, 4 * l.sW, 4 * l.sH, 2 * l.sI, P.BX, P.BY, P.BI)) return rc;
+        }
+    dim3 grid((unsigned)splits, (unsigned)(P.n_cpass * P.n_mhalf));
+    smem = std::max<size_t>(smem, 120 * 1024);
+    MRSSM_CUDA(cudaFuncSetAttribute(plane_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    plane_wgrad_kernel<<<grid, NTHREADS, smem, st>>>(mS, mL[0], mL[1], mL[2], mL[3], P);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int mrssm_pl_conv_down(const mrssm_tc_conv_args* a, void* stream) { return launch_fwd(a, OP_DOWN, (cudaStream_t)stream); }
+extern "C" int mrssm_pl_conv_up(const mrssm_tc_conv_args* a, void* stream) { return launch_fwd(a, OP_UP, (cudaStream_t)stream); }
+extern "C" int mrssm_pl_conv_wgrad(const mrssm_tc_conv_args* a, void* stream) { return launch_wgrad(a, (cudaStream_t)stream); }
+
+extern "C" int mrssm_pl_packed_shape(int32_t op, int32_t Cs_pad, int32_t Cl_pad, int32_t ksz, int32_t* N_total, int32_t* K_total) {
+    const int nt = (ksz + 1) / 2;
+    MRSSM_CHECK(N_total && K_total && ksz >= 2 && (op == OP_DOWN || op == OP_UP), "pl_packed_shape: bad args");
+    int n_ksteps;
+    if (op == OP_DOWN) {
+        MRSSM_CHECK(Cl_pad % 8 == 0 && Cs_pad % 16 == 0, "pl_packed_shape(down): Cl_pad %% 8, Cs_pad %% 16");
+        n_ksteps = ksz * nt * (Cl_pad / 8);
+        *N_total = Cs_pad;
+    } else {
+        MRSSM_CHECK(Cs_pad % 16 == 0 && Cl_pad % 8 == 0, "pl_packed_shape(up): Cs_pad %% 16, Cl_pad %% 8");
+        n_ksteps = nt * nt * (Cs_pad / 16);
+        *N_total = 4 * Cl_pad;
+    }
+    *K_total = (n_ksteps + 3) / 4 * 64;
+    return 0;
+}
+
+extern "C" int mrssm_pl_pack_weight(const float* w, int64_t w_ss, int64_t w_sl, int32_t Cs_valid, int32_t Cl_valid, int32_t Cs_pad,
+                                    int32_t Cl_pad, int32_t ksz, int32_t op, void* out, void* stream) {
+    int32_t N_total, K_total;
+    if (int rc = mrssm_pl_packed_shape(op, Cs_pad, Cl_pad, ksz, &N_total, &K_total)) return rc;
+    MRSSM_CHECK(w && out, "pl_pack_weight: null pointer");
+    const long long total = (long long)N_total * K_total;
+    const int blocks = (int)std::min<long long>(148 * 8, ceil_div64(total, 256));
+    pack_plane_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, w_ss, w_sl, Cs_valid, Cl_valid, Cs_pad, Cl_pad, ksz, op, N_total, K_total,
+                                                               (bf16*)out);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mrssm_pl_set_debug(int32_t key, int32_t value) {
+    MRSSM_CHECK(key >= 0 && key < 4, "pl_set_debug: bad key");
+    g_dbg[key] = value;
+    return 0;
+}
+
+// Host-only: describe the tiling plan of a layer (no GPU needed; used by the CPU tests and for tuning).
+extern "C" int mrssm_pl_describe(const mrssm_tc_conv_args* a, int32_t op, char* buf, int32_t buflen) {
+    MRSSM_CHECK(a && buf && buflen > 0, "pl_describe: bad args");
+    if (op == 2) {
+        WgP P;
+        size_t smem;
+        int splits;
+        if (int rc = plan_wgrad(a, P, smem, splits)) return rc;
+        snprintf(buf, buflen,
+                 "wgrad BI=%d bands=%d TH=%d BX=%d BY=%d nS=%d nL=%d PS_s=%d PS_l=%d stage=%d NA=%d ksteps/tile=%d N=%d groups=%d gpp=%d cpass=%d mhalf=%d "
+                 "splits=%d smem=%zu tiles=%d",
+                 P.BI, P.n_bands, P.TH, P.BX, P.BY, P.nS, P.nL, P.PS_s, P.PS_l, P.stage_bytes, P.NA, P.nksteps, P.N, P.NG, P.gpp, P.n_cpass,
+                 P.n_mhalf, splits, smem, P.n_groups * P.n_bands);
+    } else {
+        FwdP P;
+        size_t smem;
+        if (int rc = plan_fwd(a, op, P, smem)) return rc;
+        double eff = (double)P.BI * std::min(P.TH, P.Hv) * P.Wv / ((double)P.MB_total * 128);
+        snprintf(buf, buflen,
+                 "%s BI=%d bands=%d TH=%d BX=%d BY=%d planes=%d PS=%d stage=%d NA=%d NB=%d BN=%d ntiles=%d ksteps=%d MB_total=%d MBs=%d passes=%d "
+                 "smem=%zu tiles=%d row_eff=%.2f",
+                 op == OP_DOWN ? "down" : "up", P.BI, P.n_bands, P.TH, P.BX, P.BY, P.planes, P.PS, P.a_stage_bytes, P.NA, P.NB, P.BN, P.n_ntiles,
+                 P.n_ksteps, P.MB_total, P.MBs, P.n_passes, smem, P.n_groups * P.n_bands, eff);
+    }
+    return 0;
+}

@@ -95,6 +95,13 @@ SYMBOLS = {
     "mrssm_tc_to_bf16": [C.POINTER(T4), _i32, _i32, _i32, _i32, _i32, _f, _vp, _vp],
     "mrssm_tc_from_bf16": [_vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(T4), _vp],
     "mrssm_tc_colsum": [_vp, _i64, _i32, _i32, _vp, _vp],
+    "mrssm_pl_conv_down": [C.POINTER(TcConvArgs), _vp],
+    "mrssm_pl_conv_up": [C.POINTER(TcConvArgs), _vp],
+    "mrssm_pl_conv_wgrad": [C.POINTER(TcConvArgs), _vp],
+    "mrssm_pl_packed_shape": [_i32, _i32, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32)],
+    "mrssm_pl_pack_weight": [_vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
+    "mrssm_pl_describe": [C.POINTER(TcConvArgs), _i32, C.c_char_p, _i32],
+    "mrssm_pl_set_debug": [_i32, _i32],
     "mrssm_rollout_fwd": [C.POINTER(RolloutArgs), _vp],
     "mrssm_rollout_bwd": [C.POINTER(RolloutBwdArgs), _vp],
     "mrssm_latent_fwd": [C.POINTER(LatentArgs), _vp],
@@ -174,6 +181,14 @@ def call(name, *args, tag=None, work=None):
         profile.append((name, tag, work, e0, e1))
     launches += 1
     kernel_launches += _KERNELS_PER_CALL.get(name, 1)
+
+
+def call_host(name, *args):
+    """Invoke a host-only C-ABI entry point (no stream argument, no device needed)."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib.mrssm_last_error().decode()}")
 
 
 def ptr(t):

@@ -728,6 +728,42 @@ def tc_colsum(x, Cvalid, out):
     L.call("mrssm_tc_colsum", L.ptr(x), rows, x.shape[-1], Cvalid, L.ptr(out))
 
 
+# ---- plane (TMA + shifted-descriptor) tensor-core convs, ksz >= 2 ------------------------------------------
+DOWN, UP = 0, 1
+
+
+def pl_pack_weight(w, op, Cs_pad, Cl_pad):
+    """fp32 master [Cs,Cl,k,k] -> bf16 [N_total, K_total] in the K-step order of csrc/conv_plane.cu."""
+    Cs, Cl, k, _ = w.shape
+    n, kk = C.c_int32(), C.c_int32()
+    L.call_host("mrssm_pl_packed_shape", op, Cs_pad, Cl_pad, k, C.byref(n), C.byref(kk))
+    out = torch.empty(n.value, kk.value, device=w.device, dtype=torch.bfloat16)
+    L.call("mrssm_pl_pack_weight", L.ptr(w), Cl * k * k, k * k, Cs, Cl, Cs_pad, Cl_pad, k, op, L.ptr(out))
+    return out
+
+
+def pl_conv_down(geom, large, small, wpacked, bias, n_out_valid, n_out_pad, act=0, mask=None, mask_mode=0, out_f32=0,
+                 valid=None):
+    a = _tc_args(geom, large, small, act, mask, mask_mode, out_f32, n_out_pad, n_out_valid, 0,
+                 wpacked=L.ptr(wpacked), bias=L.ptr(bias))
+    tag, work = _tc_work("mrssm_pl_conv_down", geom, valid or (geom[6], geom[3]))
+    L.call("mrssm_pl_conv_down", C.byref(a), tag=tag, work=work)
+
+
+def pl_conv_up(geom, large, small, wpacked, bias, n_out_valid, n_out_pad, act=0, mask=None, mask_mode=0, out_f32=0,
+               valid=None):
+    a = _tc_args(geom, large, small, act, mask, mask_mode, out_f32, n_out_pad, n_out_valid, 0,
+                 wpacked=L.ptr(wpacked), bias=L.ptr(bias))
+    tag, work = _tc_work("mrssm_pl_conv_up", geom, valid or (geom[6], geom[3]))
+    L.call("mrssm_pl_conv_up", C.byref(a), tag=tag, work=work)
+
+
+def pl_conv_wgrad(geom, large, small, dweight_ptr, w_ss, w_sl, cs_valid, cl_valid):
+    a = _tc_args(geom, large, small, cs_valid=cs_valid, cl_valid=cl_valid, dweight=dweight_ptr, w_ss=w_ss, w_sl=w_sl)
+    tag, work = _tc_work("mrssm_pl_conv_wgrad", geom, (cs_valid, cl_valid))
+    L.call("mrssm_pl_conv_wgrad", C.byref(a), tag=tag, work=work)
+
+
 # ---- bf16 tensor-core mode ------------------------------------------------------------------------------------
 _STATE = {"bf16": False, "wversion": 0}
 _wcache = {}

@@ -1,0 +1,181 @@
+"""CPU model of the index arithmetic of csrc/conv_plane.cu (test infrastructure, not a product path).
+
+It replays, in numpy, what the sm_100a kernels do with their shared-memory planes: the TMA box loads (parity
+split, zero out-of-bounds fill), the K-step -> (plane, pixel shift) table, the packed weight layout and the
+epilogue's position -> pixel decode, driven by the REAL tiling plan returned by the library's host-side
+planner (mrssm_pl_describe).  Garbage shared memory is modelled as NaN, so a valid output that touched
+memory the kernel never filled shows up as NaN.  Used by tests/test_plane_sim.py against torch convolutions.
+"""
+import ctypes as C
+import re
+
+import numpy as np
+
+
+def plan(L, geom, op, n_out_pad=0):
+    """geom = (n, Hl, Wl, Clp, Hs, Ws, Csp, k) with PADDED channel counts; op 0 down, 1 up, 2 wgrad."""
+    a = L.TcConvArgs(*geom, 0, 0, 0, n_out_pad, n_out_pad, 0, geom[6], geom[3],
+                     L.T4(16, 0, 0, 0, 1), L.T4(16, 0, 0, 0, 1), L.T4(None, 0, 0, 0, 0), 16, None, 16, 0, 0)
+    buf = C.create_string_buffer(1024)
+    lib = L.load()
+    rc = lib.mrssm_pl_describe(C.byref(a), op, buf, 1024)
+    if rc != 0:
+        raise RuntimeError(lib.mrssm_last_error().decode())
+    s = buf.value.decode()
+    d = {k: (float(v) if "." in v else int(v)) for k, v in re.findall(r"(\w+)=([\d.]+)", s)}
+    d["text"] = s
+    return d
+
+
+def packed_shape(L, op, Csp, Clp, k):
+    n, kk = C.c_int32(), C.c_int32()
+    lib = L.load()
+    assert lib.mrssm_pl_packed_shape(op, Csp, Clp, k, C.byref(n), C.byref(kk)) == 0, lib.mrssm_last_error()
+    return n.value, kk.value
+
+
+def pack_weight(w, op, Csp, Clp, N_total, K_total):
+    """numpy twin of pack_plane_kernel.  w: [Cs, Cl, k, k]."""
+    Cs, Cl, k, _ = w.shape
+    nt = (k + 1) // 2
+    out = np.zeros((N_total, K_total), np.float32)
+    for n in range(N_total):
+        for kk in range(K_total):
+            ks, e = kk >> 4, kk & 15
+            if op == 0:
+                J = Clp // 8
+                j, t = ks % J, ks // J
+                b, kh = t % nt, t // nt
+                pl = 2 * j + (e >> 3)
+                px, chunk = pl // J, pl % J
+                cl, kw = chunk * 8 + (e & 7), 2 * b + px
+                if n < Cs and cl < Cl and kh < k and kw < k:
+                    out[n, kk] = w[n, cl, kh, kw]
+            else:
+                J = Csp // 16
+                j, t = ks % J, ks // J
+                b, aa = t % nt, t // nt
+                cls, cl = n // Clp, n % Clp
+                cs = (2 * j + (e >> 3)) * 8 + (e & 7)
+                kh, kw = (cls >> 1) + 2 * aa, (cls & 1) + 2 * b
+                if aa < nt and cls < 4 and cl < Cl and cs < Cs and kh < k and kw < k:
+                    out[n, kk] = w[cs, cl, kh, kw]
+    return out
+
+
+def _box(src, c0, x0, y0, i0, bx, by, bi, sx=1, sy=1, ox=0, oy=0):
+    """TMA box {8, bx, by, bi} at (c0, x0, y0, i0) of src[n, H, W, C] sub-sampled (sy, oy)/(sx, ox); zeros out of bounds.
+    Returns [bi*by*bx, 8] in shared-memory order."""
+    n, H, W, Cc = src.shape
+    sub = src[:, oy::sy, ox::sx, :]
+    out = np.zeros((bi, by, bx, 8), np.float32)
+    for i in range(bi):
+        for y in range(by):
+            for x in range(bx):
+                ii, yy, xx = i0 + i, y0 + y, x0 + x
+                if 0 <= ii < sub.shape[0] and 0 <= yy < sub.shape[1] and 0 <= xx < sub.shape[2]:
+                    v = sub[ii, yy, xx, c0:c0 + 8]
+                    out[i, y, x, :len(v)] = v
+    return out.reshape(-1, 8)
+
+
+def sim_fwd(L, op, src, w, Hl, Wl, Hs, Ws, n_out_pad):
+    """src: padded-channel NHWC source (down: large, up: small); w [Cs, Cl, k, k] master.  Returns the output
+    tensor [n, Ho, Wo, n_out_pad] (NaN where the kernel would not write)."""
+    n = src.shape[0]
+    k = w.shape[2]
+    nt = (k + 1) // 2
+    if op == 0:
+        Clp, Csp = src.shape[3], n_out_pad
+    else:
+        Csp, Clp = src.shape[3], n_out_pad
+    geom = (n, Hl, Wl, Clp, Hs, Ws, Csp, k)
+    P = plan(L, geom, op, n_out_pad)
+    N_total, K_total = packed_shape(L, op, Csp, Clp, k)
+    wp = pack_weight(w, op, Csp, Clp, N_total, K_total)
+    BI, BX, BY, TH, nb = P["BI"], P["BX"], P["BY"], P["TH"], P["bands"]
+    PSpos = P["PS"] // 16
+    planes, n_ksteps = P["planes"], P["ksteps"]
+    if op == 0:
+        J = Clp // 8
+        Hv, Wv, Ho, Wo = Hs, Ws, Hs, Ws
+    else:
+        J = Csp // 16
+        Hv, Wv, Ho, Wo = (Hl + 1) // 2, (Wl + 1) // 2, Hl, Wl
+    out = np.full((n, Ho, Wo, n_out_pad), np.nan, np.float32)
+    ngroups = (n + BI - 1) // BI
+    for ig in range(ngroups):
+        for band in range(nb):
+            A = np.full((planes, PSpos, 8), np.nan, np.float32)
+            for q in range(planes):
+                if op == 0:
+                    ppm = Clp // 8
+                    mi, c0 = q // ppm, (q % ppm) * 8
+                    A[q, :BI * BY * BX] = _box(src, c0, 0, band * TH, ig * BI, BX, BY, BI, 2, 2, mi & 1, mi >> 1)
+                else:
+                    A[q, :BI * BY * BX] = _box(src, q * 8, -(nt - 1), band * TH - (nt - 1), ig * BI, BX, BY, BI)
+            MB = P["MB_total"]
+            rows = MB * 128
+            acc = np.zeros((rows, N_total), np.float32)
+            for ks in range(n_ksteps):
+                j, t = ks % J, ks // J
+                b, r = t % nt, t // nt
+                if op == 0:
+                    plane, shift = (r & 1) * 2 * J + 2 * j, (r >> 1) * BX + b
+                else:
+                    plane, shift = 2 * j, (nt - 1 - r) * BX + (nt - 1 - b)
+                a16 = np.concatenate([A[plane, shift:shift + rows], A[plane + 1, shift:shift + rows]], axis=1)
+                acc += a16 @ wp[:, ks * 16:ks * 16 + 16].T
+            IP = BY * BX
+            for p in range(rows):
+                i, r = p // IP, p % IP
+                yr, x = r // BX, r % BX
+                img, y = ig * BI + i, band * TH + yr
+                if not (i < BI and img < n and yr < TH and y < Hv and x < Wv):
+                    continue
+                if op == 0:
+                    out[img, y, x, :] = acc[p]
+                else:
+                    for cls in range(4):
+                        yy, xx = 2 * y + (cls >> 1), 2 * x + (cls & 1)
+                        if yy < Ho and xx < Wo:
+                            out[img, yy, xx, :] = acc[p, cls * Clp:(cls + 1) * Clp]
+    return out, P
+
+
+def sim_wgrad(L, small, large, k):
+    """small [n, Hs, Ws, Csp], large [n, Hl, Wl, Clp] (padded channels).  Returns dW [Csp, Clp, k, k]."""
+    n, Hs, Ws, Csp = small.shape
+    _, Hl, Wl, Clp = large.shape
+    nt = (k + 1) // 2
+    geom = (n, Hl, Wl, Clp, Hs, Ws, Csp, k)
+    P = plan(L, geom, 2)
+    BI, BX, BY, TH, nb = P["BI"], P["BX"], P["BY"], P["TH"], P["bands"]
+    banded = nb > 1
+    SBY = TH if banded else BY
+    PS_s, PS_l = P["PS_s"] // 16, P["PS_l"] // 16
+    nks = P["tile"]          # "ksteps/tile=%d" parses as key 'tile'
+    cpl = Clp // 8
+    dW = np.zeros((Csp, Clp, k, k), np.float32)
+    ngroups = (n + BI - 1) // BI
+    for ig in range(ngroups):
+        for band in range(nb):
+            S = np.zeros((Csp // 8, PS_s, 8), np.float32)
+            Lg = np.zeros((4 * cpl, PS_l, 8), np.float32)
+            for q in range(Csp // 8):
+                S[q, :BI * SBY * BX] = _box(small, q * 8, 0, band * TH, ig * BI, BX, SBY, BI)
+            for q in range(4 * cpl):
+                mi, c0 = q // cpl, (q % cpl) * 8
+                Lg[q, :BI * BY * BX] = _box(large, c0, 0, band * TH, ig * BI, BX, BY, BI, 2, 2, mi & 1, mi >> 1)
+            K = nks * 16
+            Sm = S[:, :K].transpose(1, 0, 2).reshape(K, Csp)            # [pixel][cs]
+            for g in range(k * nt):
+                kh, b = g // nt, g % nt
+                plane0, shift = (kh & 1) * 2 * cpl, (kh >> 1) * BX + b
+                Bm = Lg[plane0:plane0 + 2 * cpl, shift:shift + K].transpose(1, 0, 2).reshape(K, 2 * Clp)   # [pixel][(px, cl)]
+                D = Sm.T @ Bm
+                for px in range(2):
+                    kw = 2 * b + px
+                    if kw < k:
+                        dW[:, :, kh, kw] += D[:, px * Clp:(px + 1) * Clp]
+    return dW, P
