@@ -132,6 +132,8 @@ int mrssm_pl_pack_weight(const float* w, int64_t w_ss, int64_t w_sl, int32_t Cs_
 int mrssm_pl_describe(const mrssm_tc_conv_args* a, int32_t op, char* buf, int32_t buflen);
 /* bring-up switches (descriptor-field variants); 0 = production setting */
 int mrssm_pl_set_debug(int32_t key, int32_t value);
+/* tuning aid: device buffer of 148*16*8 int64 receiving per-tile clock64 stamps of the fwd-type kernel (NULL = off) */
+int mrssm_pl_set_profile_buffer(void* dev_buf);
 
 /* ---- the RSSM rollout ------------------------------------------------------------------------
  * Replaces MultimodalTransitionModel.forward (utils/models/transition_model.py:200-285), its

@@ -27,9 +27,10 @@ namespace {
 using bf16 = __nv_bfloat16;
 enum { OP_DOWN = 0, OP_UP = 1 };
 constexpr int NTHREADS = 256;
-constexpr int SMEM_TOTAL = 227 * 1024 - 4096;   // dynamic budget: 227 KB minus the 1 KB alignment slack and the static barriers/tables
+constexpr int SMEM_TOTAL = 227 * 1024 - 9216;   // dynamic budget: 227 KB minus the 1 KB alignment slack and the static barriers/tables
 
-int g_dbg[4] = {0, 0, 0, 0};   // [0] fwd: swap LBO/SBO of the A descriptor, [1] wgrad: swap LBO/SBO (bring-up switches)
+long long* g_prof = nullptr;    // optional device buffer for in-kernel clock64 timelines (bring-up / tuning)
+int g_dbg[4] = {0, 0, 0, 0};   // spare bring-up switches
 
 struct T4 {
     const void* p;
@@ -131,21 +132,87 @@ struct FwdP {
     int n_ksteps, nkb, nt, J;
     int BN, n_ntiles;
     int MB_total, MBs, n_passes, n_sets, set_cols;
-    int NA, NB;
+    int NA, NB, b_res;          // b_res: the whole packed weight stays resident in shared memory (NB == nkb)
     int act, mask_mode, out_f32, n_valid, Cop, Ho, Wo;
     int a_stage_bytes;
-    int dbg_swap;
+    long long* prof;            // [CTA][16 tiles][8 slots] clock64 stamps or NULL
     T4 out, mask;
     const float* bias;
 };
+#define PROF(slot) do { if (P.prof && lit < 16) P.prof[((long long)blockIdx.x * 16 + lit) * 8 + (slot)] = clock64(); } while (0)
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+constexpr int FWD_THREADS = 384;      // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue (two per TMEM lane quarter)
+
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// bias + activation + act'-mask + store of 8 consecutive output channels of one pixel
+template <bool F32>
+__device__ __forceinline__ void epi_store8(const FwdP& P, const float* v, const float* bias_s, int cl0, long long o_off, long long m_off) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cl0), b1 = *reinterpret_cast<const float4*>(bias_s + cl0 + 4);
+    float x[8] = {v[0] + b0.x, v[1] + b0.y, v[2] + b0.z, v[3] + b0.w, v[4] + b1.x, v[5] + b1.y, v[6] + b1.z, v[7] + b1.w};
+    if (P.act == MRSSM_ACT_RELU) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = fmaxf(x[e], 0.f);
+    } else if (P.act == MRSSM_ACT_ELU) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = x[e] > 0.f ? x[e] : expm1f(x[e]);
+    }
+    if (P.mask_mode) {
+        const uint4 mk = __ldg(reinterpret_cast<const uint4*>((const bf16*)P.mask.p + m_off + cl0));
+        const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mk);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 m = __bfloat1622float2(mh[e]);
+            x[2 * e] *= act_grad_from_out(m.x, P.mask_mode);
+            x[2 * e + 1] *= act_grad_from_out(m.y, P.mask_mode);
+        }
+    }
+    if (F32) {
+        float* op = (float*)P.out.p + o_off;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (cl0 + e < P.n_valid) op[(long long)(cl0 + e) * P.out.sC] = x[e];
+    } else {
+        uint4 pk;
+        __nv_bfloat162* ph = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ph[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+        *reinterpret_cast<uint4*>((bf16*)P.out.p + o_off + cl0) = pk;
+    }
+}
+
+template <int OP, bool F32>
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUtensorMap mA2,
                  const __grid_constant__ CUtensorMap mA3, const __grid_constant__ CUtensorMap mB, const FwdP P) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t a_full[2], a_empty[2], b_full[8], b_empty[8], acc_full[2], acc_empty[2];
+    __shared__ uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2];
+    __shared__ uint64_t b_full[80], b_empty[8];
     __shared__ uint32_t tmem_base_s;
-    __shared__ uint32_t ks_off[320];
+    __shared__ __align__(16) uint32_t ks_off16[320];      // (plane*PS + shift*16) >> 4 per K-step
+    __shared__ __align__(16) float bias_s[1024];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -153,29 +220,32 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     const uint32_t smemA = smem0 + (uint32_t)P.NB * b_stage;
     const int n_tiles = P.n_groups * P.n_bands;
 
-    for (int ks = tid; ks < P.n_ksteps; ks += NTHREADS) {
-        int j = ks % P.J, t = ks / P.J, b = t % P.nt, r = t / P.nt;
-        int plane, shift;
-        if (P.op == OP_DOWN) {           // r = kh
-            plane = (r & 1) * 2 * P.J + 2 * j;
-            shift = (r >> 1) * P.BX + b;
-        } else {                         // r = a
-            plane = 2 * j;
-            shift = (P.nt - 1 - r) * P.BX + (P.nt - 1 - b);
+    for (int ks = tid; ks < 320; ks += FWD_THREADS) {
+        uint32_t off = 0;
+        if (ks < P.n_ksteps) {
+            int j = ks % P.J, t = ks / P.J, b = t % P.nt, r = t / P.nt;
+            int plane, shift;
+            if (OP == OP_DOWN) {           // r = kh
+                plane = (r & 1) * 2 * P.J + 2 * j;
+                shift = (r >> 1) * P.BX + b;
+            } else {                       // r = a
+                plane = 2 * j;
+                shift = (P.nt - 1 - r) * P.BX + (P.nt - 1 - b);
+            }
+            off = ((uint32_t)plane * (uint32_t)P.PS + (uint32_t)shift * 16u) >> 4;
         }
-        ks_off[ks] = (uint32_t)plane * (uint32_t)P.PS + (uint32_t)shift * 16u;
+        ks_off16[ks] = off;
     }
+    for (int c = tid; c < 1024; c += FWD_THREADS) bias_s[c] = (P.bias && c < P.n_valid) ? P.bias[c] : 0.f;
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(tc::smem_u32(&a_full[s]), 1);
             tc::mbar_init(tc::smem_u32(&a_empty[s]), 1);
             tc::mbar_init(tc::smem_u32(&acc_full[s]), 1);
-            tc::mbar_init(tc::smem_u32(&acc_empty[s]), 4);
+            tc::mbar_init(tc::smem_u32(&acc_empty[s]), 8);
         }
-        for (int s = 0; s < 8; ++s) {
-            tc::mbar_init(tc::smem_u32(&b_full[s]), 1);
-            tc::mbar_init(tc::smem_u32(&b_empty[s]), 1);
-        }
+        for (int s = 0; s < 80; ++s) tc::mbar_init(tc::smem_u32(&b_full[s]), 1);
+        for (int s = 0; s < 8; ++s) tc::mbar_init(tc::smem_u32(&b_empty[s]), 1);
         tc::fence_barrier_init();
     }
     if (warp == 2) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), 512);
@@ -203,21 +273,35 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                 ++acnt;
             };
             int tile = blockIdx.x;
+            int lit = 0;
+            PROF(0);
+            if (P.b_res) {
+                for (int kb = 0; kb < P.nkb; ++kb) {
+                    const uint32_t bar = tc::smem_u32(&b_full[kb]);
+                    mbar_expect_tx(bar, b_stage);
+                    tma_load_2d(smem0 + (uint32_t)kb * b_stage, &mB, kb * 64, 0, bar);
+                }
+            }
             if (tile < n_tiles) issue_A(tile);
-            for (; tile < n_tiles; tile += gridDim.x) {
+            for (; tile < n_tiles; tile += gridDim.x, ++lit) {
                 const int next = tile + gridDim.x;
+                PROF(1);
                 if (P.NA > 1 && next < n_tiles) issue_A(next);
-                for (int it = 0; it < P.n_ntiles * P.n_passes; ++it) {
-                    const int nti = it / P.n_passes;
-                    for (int kb = 0; kb < P.nkb; ++kb) {
-                        const int sb = bcnt % P.NB;
-                        tc::mbar_wait(tc::smem_u32(&b_empty[sb]), ((bcnt / P.NB) & 1) ^ 1);
-                        const uint32_t bar = tc::smem_u32(&b_full[sb]);
-                        mbar_expect_tx(bar, b_stage);
-                        tma_load_2d(smem0 + (uint32_t)sb * b_stage, &mB, kb * 64, nti * P.BN, bar);
-                        ++bcnt;
+                PROF(6);
+                if (!P.b_res) {
+                    for (int it = 0; it < P.n_ntiles * P.n_passes; ++it) {
+                        const int nti = it / P.n_passes;
+                        for (int kb = 0; kb < P.nkb; ++kb) {
+                            const int sb = bcnt % P.NB;
+                            tc::mbar_wait(tc::smem_u32(&b_empty[sb]), ((bcnt / P.NB) & 1) ^ 1);
+                            const uint32_t bar = tc::smem_u32(&b_full[sb]);
+                            mbar_expect_tx(bar, b_stage);
+                            tma_load_2d(smem0 + (uint32_t)sb * b_stage, &mB, kb * 64, nti * P.BN, bar);
+                            ++bcnt;
+                        }
                     }
                 }
+                PROF(7);
                 if (P.NA == 1 && next < n_tiles) issue_A(next);
             }
         }
@@ -226,12 +310,18 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         // ------------------------------ MMA issuer ------------------------------
         if (lane == 0) {
             const uint32_t idesc = tc::idesc_bf16(128, P.BN, 0, 0);
+            const uint32_t a_hi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1, no swizzle
+            const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, 128B swizzle
+            const uint32_t a_lbo = ((uint32_t)P.PS >> 4) << 16;
+            const uint32_t BN = (uint32_t)P.BN;
             uint32_t acnt = 0, bcnt = 0, ccnt = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            int lit = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lit) {
                 const int sa = acnt % P.NA;
                 tc::mbar_wait(tc::smem_u32(&a_full[sa]), (acnt / P.NA) & 1);
                 tc::tc_fence_after();
-                const uint32_t sA = smemA + (uint32_t)sa * (uint32_t)P.a_stage_bytes;
+                PROF(2);
+                const uint32_t a_base = (((smemA + (uint32_t)sa * (uint32_t)P.a_stage_bytes) >> 4) & 0x3FFFu) | a_lbo;
                 for (int it = 0; it < P.n_ntiles * P.n_passes; ++it) {
                     const int pass = it % P.n_passes;
                     const int set = ccnt % P.n_sets;
@@ -239,93 +329,104 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                     tc::tc_fence_after();
                     const int mb0 = pass * P.MBs, nmb = min(P.MBs, P.MB_total - mb0);
                     const uint32_t tacc = tmem_base + (uint32_t)(set * P.set_cols);
+                    const uint32_t a_pass = a_base + (uint32_t)mb0 * 128u;
                     for (int kb = 0; kb < P.nkb; ++kb) {
-                        const int sb = bcnt % P.NB;
-                        tc::mbar_wait(tc::smem_u32(&b_full[sb]), (bcnt / P.NB) & 1);
-                        tc::tc_fence_after();
-                        const uint32_t sB = smem0 + (uint32_t)sb * b_stage;
-                        const int nk = min(4, P.n_ksteps - kb * 4);
-                        for (int mb = 0; mb < nmb; ++mb) {
-                            const uint32_t arow = sA + (uint32_t)(mb0 + mb) * 2048u;
-                            for (int j = 0; j < nk; ++j) {
-                                uint64_t ad = P.dbg_swap ? smem_desc_plain(arow + ks_off[kb * 4 + j], 128, (uint32_t)P.PS)
-                                                         : smem_desc_plain(arow + ks_off[kb * 4 + j], (uint32_t)P.PS, 128);
-                                uint64_t bd = tc::smem_desc_sw128(sB + j * 32, 16, 1024);
-                                tc::umma_bf16(tacc + (uint32_t)(mb * P.BN), ad, bd, idesc, (kb | j) != 0);
+                        int sb;
+                        if (P.b_res) {
+                            sb = kb;
+                            if (lit == 0 && it == 0) {
+                                tc::mbar_wait(tc::smem_u32(&b_full[sb]), 0);
+                                tc::tc_fence_after();
                             }
+                        } else {
+                            sb = bcnt % P.NB;
+                            tc::mbar_wait(tc::smem_u32(&b_full[sb]), (bcnt / P.NB) & 1);
+                            tc::tc_fence_after();
                         }
-                        tc::umma_commit(tc::smem_u32(&b_empty[sb]));
-                        ++bcnt;
+                        const uint32_t b_lo = (((smem0 + (uint32_t)sb * b_stage) >> 4) & 0x3FFFu) | (1u << 16);
+                        const uint4 ko = *reinterpret_cast<const uint4*>(&ks_off16[kb * 4]);
+                        const int nk = min(4, P.n_ksteps - kb * 4);
+                        uint32_t a_row = a_pass, d = tacc;
+                        for (int mb = 0; mb < nmb; ++mb, a_row += 128u, d += BN) {
+                            umma_bf16_lohi(d, a_row + ko.x, a_hi, b_lo, b_hi, idesc, kb != 0);
+                            if (nk > 1) umma_bf16_lohi(d, a_row + ko.y, a_hi, b_lo + 2, b_hi, idesc, 1);
+                            if (nk > 2) umma_bf16_lohi(d, a_row + ko.z, a_hi, b_lo + 4, b_hi, idesc, 1);
+                            if (nk > 3) umma_bf16_lohi(d, a_row + ko.w, a_hi, b_lo + 6, b_hi, idesc, 1);
+                        }
+                        if (!P.b_res) {
+                            tc::umma_commit(tc::smem_u32(&b_empty[sb]));
+                            ++bcnt;
+                        }
                     }
                     tc::umma_commit(tc::smem_u32(&acc_full[set]));
                     ++ccnt;
                 }
                 tc::umma_commit(tc::smem_u32(&a_empty[sa]));
+                PROF(3);
                 ++acnt;
             }
         }
         __syncwarp();
     } else if (warp >= 4) {
         // ------------------------------ epilogue ------------------------------
-        const int q = warp - 4;
+        const int e = warp - 4, q = e & 3, part = e >> 2;
+        const bool split_cols = (P.BN % 32) == 0;                // both warps of a lane quarter share every block, half the columns each
+        const int ncols = split_cols ? P.BN / 2 : P.BN;
+        const int col0 = split_cols ? part * ncols : 0;
         const int IP = P.BY * P.BX;
         uint32_t ccnt = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int lit = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lit) {
             const int ig = tile / P.n_bands, band = tile - ig * P.n_bands;
             for (int it = 0; it < P.n_ntiles * P.n_passes; ++it) {
                 const int nti = it / P.n_passes, pass = it % P.n_passes;
                 const int set = ccnt % P.n_sets;
                 tc::mbar_wait(tc::smem_u32(&acc_full[set]), (ccnt / P.n_sets) & 1);
                 tc::tc_fence_after();
+                if (it == 0 && tid == 128) PROF(4);
                 const int mb0 = pass * P.MBs, nmb = min(P.MBs, P.MB_total - mb0);
-                for (int mb = 0; mb < nmb; ++mb) {
+                const int n0 = nti * P.BN + col0;
+                for (int mb = split_cols ? 0 : part; mb < nmb; mb += split_cols ? 1 : 2) {
                     const int p = (mb0 + mb) * 128 + q * 32 + lane;
                     const int i = p / IP, r = p - i * IP, yr = r / P.BX, x = r - yr * P.BX;
                     const int img = ig * P.BI + i, y = band * P.TH + yr;
                     const bool row_ok = i < P.BI && img < P.n_img && yr < P.TH && y < P.Hv && x < P.Wv;
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * P.set_cols + mb * P.BN);
-                    for (int c0 = 0; c0 < P.BN; c0 += 16) {
-                        float v[16];
-                        tc::tmem_ld16(taddr + c0, v);
-                        if (!row_ok) continue;
+                    long long o_base, m_base = 0;
+                    if (OP == OP_DOWN) {
+                        o_base = img * P.out.sI + y * P.out.sH + x * P.out.sW;
+                        if (P.mask_mode) m_base = img * P.mask.sI + y * P.mask.sH + x * P.mask.sW;
+                    } else {
+                        o_base = img * P.out.sI + 2 * y * P.out.sH + 2 * x * P.out.sW;
+                        if (P.mask_mode) m_base = img * P.mask.sI + 2 * y * P.mask.sH + 2 * x * P.mask.sW;
+                    }
+                    int cls = 0, cl0 = n0;
+                    if (OP == OP_UP) {
+                        cls = n0 / P.Cop;
+                        cl0 = n0 - cls * P.Cop;
+                    }
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * P.set_cols + mb * P.BN + col0);
+                    for (int c0 = 0; c0 < ncols; c0 += 32) {
+                        float v[32];
+                        const bool two = c0 + 16 < ncols;
+                        tmem_ld16_nowait(taddr + c0, v);
+                        if (two) tmem_ld16_nowait(taddr + c0 + 16, v + 16);
+                        tmem_wait_ld();
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int n = nti * P.BN + c0 + 8 * h;
-                            int cl0 = n, yy = y, xx = x;
-                            if (P.op == OP_UP) {
-                                const int cls = n / P.Cop;
-                                cl0 = n - cls * P.Cop;
-                                yy = 2 * y + (cls >> 1);
-                                xx = 2 * x + (cls & 1);
-                                if (yy >= P.Ho || xx >= P.Wo) continue;
+                        for (int h = 0; h < 4; ++h) {
+                            if (h >= 2 && !two) break;
+                            bool ok = row_ok;
+                            long long o_off = o_base, m_off = m_base;
+                            if (OP == OP_UP) {
+                                const int py = cls >> 1, px = cls & 1;
+                                ok = ok && (2 * y + py < P.Ho) && (2 * x + px < P.Wo);
+                                o_off += py * P.out.sH + px * P.out.sW;
+                                if (P.mask_mode) m_off += py * P.mask.sH + px * P.mask.sW;
                             }
-                            float xv[8];
-                            uint4 mk = make_uint4(0, 0, 0, 0);
-                            if (P.mask_mode) {
-                                const bf16* mp = (const bf16*)P.mask.p + img * P.mask.sI + yy * P.mask.sH + xx * P.mask.sW + cl0;
-                                mk = *reinterpret_cast<const uint4*>(mp);
-                            }
-                            const bf16* mh = reinterpret_cast<const bf16*>(&mk);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const int c = cl0 + e;
-                                float t = v[8 * h + e];
-                                if (P.bias && c < P.n_valid) t += __ldg(P.bias + c);
-                                t = act_apply(t, P.act);
-                                if (P.mask_mode) t *= act_grad_from_out(__bfloat162float(mh[e]), P.mask_mode);
-                                xv[e] = c < P.n_valid ? t : 0.f;
-                            }
-                            if (P.out_f32) {
-                                float* op = (float*)P.out.p + img * P.out.sI + yy * P.out.sH + xx * P.out.sW;
-#pragma unroll
-                                for (int e = 0; e < 8; ++e)
-                                    if (cl0 + e < P.n_valid) op[(long long)(cl0 + e) * P.out.sC] = xv[e];
-                            } else {
-                                __align__(16) bf16 hb[8];
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) hb[e] = __float2bfloat16(xv[e]);
-                                bf16* op = (bf16*)P.out.p + img * P.out.sI + yy * P.out.sH + xx * P.out.sW + cl0;
-                                *reinterpret_cast<uint4*>(op) = *reinterpret_cast<const uint4*>(hb);
+                            if (ok) epi_store8<F32>(P, v + 8 * h, bias_s, cl0, o_off, m_off);
+                            cl0 += 8;
+                            if (OP == OP_UP && cl0 == P.Cop) {
+                                cl0 = 0;
+                                ++cls;
                             }
                         }
                     }
@@ -335,6 +436,7 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                 if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[set]));
                 ++ccnt;
             }
+            if (tid == 128) PROF(5);
         }
     }
     tc::tc_fence_before();
@@ -380,6 +482,8 @@ int plan_fwd(const mrssm_tc_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
         P.Ho = a->Hl; P.Wo = a->Wl;
     }
     MRSSM_CHECK(P.n_ksteps <= 320, "plane conv: %d K-steps exceed the table", P.n_ksteps);
+    MRSSM_CHECK(N_total <= 1024 || op == OP_UP, "plane conv: %d output channels exceed the bias table", N_total);
+    MRSSM_CHECK(P.Cop <= 1024, "plane conv: %d output channels exceed the bias table", P.Cop);
     MRSSM_CHECK(N_total % 16 == 0, "plane conv: %d output columns not a multiple of 16", N_total);
     P.nkb = (P.n_ksteps + 3) / 4;
     P.BN = N_total <= 256 ? N_total : (N_total % 256 == 0 ? 256 : (N_total % 128 == 0 ? 128 : 64));
@@ -387,11 +491,18 @@ int plan_fwd(const mrssm_tc_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
     P.n_ntiles = N_total / P.BN;
     P.n_sets = 2; P.set_cols = 256;
     P.MBs = std::max(1, 256 / P.BN);
-    P.NB = P.BN >= 256 ? 3 : 4;
     P.BX = P.Wv + nt - 1;
     const int maxshift = (nt - 1) * P.BX + nt - 1;
-    // a single 128-row block of the smallest tile must fit next to the weight ring: shrink the ring if it does not
-    while (P.NB > 2 && (long long)P.planes * ((128 + maxshift) * 16 + 128) > SMEM_TOTAL - (long long)P.NB * P.BN * 128) --P.NB;
+    const long long min_a = (long long)P.planes * ((128 + maxshift) * 16 + 128);    // one 128-row block of the smallest tile
+    // the whole packed weight stays resident when it is small; otherwise it streams through a ring of 64-wide K blocks
+    P.b_res = (P.n_ntiles == 1 && P.nkb <= 80 && (long long)P.nkb * P.BN * 128 <= 72 * 1024 &&
+               (long long)P.nkb * P.BN * 128 + min_a <= SMEM_TOTAL);
+    if (P.b_res) {
+        P.NB = P.nkb;
+    } else {
+        P.NB = std::min(8, std::max(2, (64 * 1024) / (P.BN * 128)));
+        while (P.NB > 2 && min_a > SMEM_TOTAL - (long long)P.NB * P.BN * 128) --P.NB;
+    }
     const long long bring = (long long)P.NB * P.BN * 128;
     const long long avail = SMEM_TOTAL - bring;
     auto stage_bytes = [&](int BI, int BY, int TH, int& MB_total, int& PS) {
@@ -405,26 +516,32 @@ int plan_fwd(const mrssm_tc_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
     const int BYfull = P.Hv + nt - 1;
     long long one = stage_bytes(1, BYfull, P.Hv, MBt, PS);
     if (one <= avail) {
-        P.NA = (2 * one <= avail) ? 2 : 1;
-        const long long budget = avail / P.NA;
-        // images per tile: the smallest count whose 128-row blocks are (nearly) as full as the best feasible one
-        double max_eff = -1.0;
-        int BImax = 0;
-        for (int BI = 1; BI <= std::min(a->n_img, 256); ++BI) {
-            long long sb = stage_bytes(BI, BYfull, P.Hv, MBt, PS);
-            if (sb > budget || PS >= 262144 || MBt > 32) break;
-            BImax = BI;
-            max_eff = std::max(max_eff, (double)BI * P.Hv * P.Wv / ((double)MBt * 128));
-        }
-        int best = 1;
-        for (int BI = 1; BI <= BImax; ++BI) {
-            stage_bytes(BI, BYfull, P.Hv, MBt, PS);
-            if ((double)BI * P.Hv * P.Wv / ((double)MBt * 128) >= max_eff - 0.02) {
-                best = BI;
-                break;
+        // images per tile and A stages: maximise (valid rows / MMA rows) x (accumulator-set fill when the weights stream),
+        // taking the smallest image count within 2 % of the best; single buffering must win by 50 % to be chosen
+        auto best_for = [&](int NA, int& bestBI) -> double {
+            const long long budget = avail / NA;
+            double best = -1.0;
+            bestBI = 0;
+            for (int BI = 1; BI <= std::min(a->n_img, 256); ++BI) {
+                long long sb = stage_bytes(BI, BYfull, P.Hv, MBt, PS);
+                if (sb > budget || PS >= 262144 || (MBt > 32 && BI > 1)) break;
+                double sc = (double)BI * P.Hv * P.Wv / ((double)MBt * 128);
+                if (!P.b_res) sc *= (double)MBt / (double)(((MBt + P.MBs - 1) / P.MBs) * P.MBs);
+                if (sc > best + 0.02) {
+                    best = sc;
+                    bestBI = BI;
+                }
             }
+            return best;
+        };
+        int bi2 = 0, bi1 = 0;
+        const double s2 = best_for(2, bi2), s1 = best_for(1, bi1);
+        if (bi2 > 0 && s2 * 1.5 >= s1) {
+            P.NA = 2; P.BI = bi2;
+        } else {
+            P.NA = 1; P.BI = std::max(1, bi1);
         }
-        P.BI = best; P.BY = BYfull; P.TH = P.Hv; P.n_bands = 1;
+        P.BY = BYfull; P.TH = P.Hv; P.n_bands = 1;
     } else {
         P.NA = 2;
         const long long budget = avail / 2;
@@ -448,7 +565,7 @@ int plan_fwd(const mrssm_tc_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
     const mrssm_t4& out = (op == OP_DOWN) ? a->small : a->large;
     P.out = cvt(out); P.mask = cvt(a->mask);
     P.bias = a->bias;
-    P.dbg_swap = g_dbg[0];
+    P.prof = g_prof;
     MRSSM_CHECK(P.out_f32 || (out.sC == 1 && out.sW % 8 == 0 && out.sH % 8 == 0 && out.sI % 8 == 0 && ((uintptr_t)out.ptr & 15) == 0),
                 "plane conv: bf16 output must be NHWC with channels padded to 8");
     MRSSM_CHECK(!P.mask_mode || (a->mask.sC == 1 && a->mask.sW % 8 == 0 && a->mask.sH % 8 == 0 && a->mask.sI % 8 == 0),
@@ -487,8 +604,17 @@ int launch_fwd(const mrssm_tc_conv_args* a, int op, cudaStream_t st) {
     const int n_tiles = P.n_groups * P.n_bands;
     int grid = std::min(n_tiles, 148);
     smem = std::max<size_t>(smem, 120 * 1024);       // > half an SM: one CTA per SM (each allocates all 512 TMEM columns)
-    MRSSM_CUDA(cudaFuncSetAttribute(plane_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    plane_fwd_kernel<<<grid, NTHREADS, smem, st>>>(mA[0], mA[1], mA[2], mA[3], mB, P);
+#define PL_LAUNCH(OPV, F32V)                                                                                                   \
+    do {                                                                                                                        \
+        MRSSM_CUDA(cudaFuncSetAttribute(plane_fwd_kernel<OPV, F32V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        plane_fwd_kernel<OPV, F32V><<<grid, FWD_THREADS, smem, st>>>(mA[0], mA[1], mA[2], mA[3], mB, P);                        \
+    } while (0)
+    if (op == OP_DOWN) {
+        if (P.out_f32) PL_LAUNCH(OP_DOWN, true); else PL_LAUNCH(OP_DOWN, false);
+    } else {
+        if (P.out_f32) PL_LAUNCH(OP_UP, true); else PL_LAUNCH(OP_UP, false);
+    }
+#undef PL_LAUNCH
     MRSSM_LAUNCH_CHECK();
     return 0;
 }
@@ -533,7 +659,7 @@ struct WgP {
     int nksteps;                // K steps (16 pixels) per tile
     int ksz, nt, Clp, Csp, N;
     int NG, gpp, n_cpass, n_mhalf;
-    int NA, zero_bytes, dbg_swap;
+    int NA, zero_bytes;
     int cs_valid, cl_valid;
     float* dw;
     long long w_ss, w_sl;
@@ -594,25 +720,31 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = tc::idesc_bf16(128, P.N, 1, 1);
+            // MN-major un-swizzled descriptors: LBO = 128 B between 8-pixel (K) groups, SBO = plane stride between 8-channel chunks
+            const uint32_t s_hi = ((uint32_t)P.PS_s >> 4) | (1u << 14), l_hi = ((uint32_t)P.PS_l >> 4) | (1u << 14);
+            const uint32_t lbo = (128u >> 4) << 16;
             uint32_t acnt = 0;
-            bool first = true;
+            uint32_t accum = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int sa = acnt % P.NA;
                 tc::mbar_wait(tc::smem_u32(&a_full[sa]), (acnt / P.NA) & 1);
                 tc::tc_fence_after();
                 const uint32_t sS = smem0 + (uint32_t)sa * (uint32_t)P.stage_bytes, sL = sS + (uint32_t)P.offL;
-                for (int ks = 0; ks < P.nksteps; ++ks) {
-                    const uint64_t ad = P.dbg_swap ? smem_desc_plain(sS + (uint32_t)ks * 256u, (uint32_t)P.PS_s, 128)
-                                                   : smem_desc_plain(sS + (uint32_t)ks * 256u, 128, (uint32_t)P.PS_s);
-                    for (int gi = 0; gi < ng; ++gi) {
-                        const int g = g0 + gi, kh = g / P.nt, b = g - kh * P.nt;
-                        const uint32_t boff = (uint32_t)((kh & 1) * 2 * P.cpl) * (uint32_t)P.PS_l + (uint32_t)((kh >> 1) * P.BX + b + ks * 16) * 16u;
-                        const uint64_t bd = P.dbg_swap ? smem_desc_plain(sL + boff, (uint32_t)P.PS_l, 128) : smem_desc_plain(sL + boff, 128, (uint32_t)P.PS_l);
-                        tc::umma_bf16(tmem_base + (uint32_t)(gi * P.N), ad, bd, idesc, !(first && ks == 0));
+                const uint32_t a0 = ((sS >> 4) & 0x3FFFu) | lbo;
+                for (int gi = 0; gi < ng; ++gi) {
+                    const int g = g0 + gi, kh = g / P.nt, b = g - kh * P.nt;
+                    const uint32_t boff = (uint32_t)((kh & 1) * 2 * P.cpl) * (uint32_t)P.PS_l + (uint32_t)((kh >> 1) * P.BX + b) * 16u;
+                    uint32_t a_lo = a0, b_lo = (((sL + boff) >> 4) & 0x3FFFu) | lbo;
+                    const uint32_t d = tmem_base + (uint32_t)(gi * P.N);
+                    umma_bf16_lohi(d, a_lo, s_hi, b_lo, l_hi, idesc, accum);
+                    for (int ks = 1; ks < P.nksteps; ++ks) {
+                        a_lo += 16u;            // 16 pixels = 256 B
+                        b_lo += 16u;
+                        umma_bf16_lohi(d, a_lo, s_hi, b_lo, l_hi, idesc, 1);
                     }
                 }
                 tc::umma_commit(tc::smem_u32(&a_empty[sa]));
-                first = false;
+                accum = 1;
                 ++acnt;
             }
             tc::umma_commit(tc::smem_u32(&acc_full));
@@ -708,7 +840,6 @@ int plan_wgrad(const mrssm_tc_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
     splits = std::max(1, std::min(n_tiles, (148 + ypass - 1) / ypass));
     P.cs_valid = a->cs_valid; P.cl_valid = a->cl_valid;
     P.dw = a->dweight; P.w_ss = a->w_ss; P.w_sl = a->w_sl;
-    P.dbg_swap = g_dbg[1];
     return 0;
 }
 
@@ -780,6 +911,11 @@ extern "C" int mrssm_pl_set_debug(int32_t key, int32_t value) {
     return 0;
 }
 
+extern "C" int mrssm_pl_set_profile_buffer(void* dev_buf) {
+    g_prof = (long long*)dev_buf;
+    return 0;
+}
+
 // Host-only: describe the tiling plan of a layer (no GPU needed; used by the CPU tests and for tuning).
 extern "C" int mrssm_pl_describe(const mrssm_tc_conv_args* a, int32_t op, char* buf, int32_t buflen) {
     MRSSM_CHECK(a && buf && buflen > 0, "pl_describe: bad args");
@@ -799,9 +935,9 @@ extern "C" int mrssm_pl_describe(const mrssm_tc_conv_args* a, int32_t op, char* 
         if (int rc = plan_fwd(a, op, P, smem)) return rc;
         double eff = (double)P.BI * std::min(P.TH, P.Hv) * P.Wv / ((double)P.MB_total * 128);
         snprintf(buf, buflen,
-                 "%s BI=%d bands=%d TH=%d BX=%d BY=%d planes=%d PS=%d stage=%d NA=%d NB=%d BN=%d ntiles=%d ksteps=%d MB_total=%d MBs=%d passes=%d "
+                 "%s BI=%d bands=%d TH=%d BX=%d BY=%d planes=%d PS=%d stage=%d NA=%d NB=%d bres=%d BN=%d ntiles=%d ksteps=%d MB_total=%d MBs=%d passes=%d "
                  "smem=%zu tiles=%d row_eff=%.2f",
-                 op == OP_DOWN ? "down" : "up", P.BI, P.n_bands, P.TH, P.BX, P.BY, P.planes, P.PS, P.a_stage_bytes, P.NA, P.NB, P.BN, P.n_ntiles,
+                 op == OP_DOWN ? "down" : "up", P.BI, P.n_bands, P.TH, P.BX, P.BY, P.planes, P.PS, P.a_stage_bytes, P.NA, P.NB, P.b_res, P.BN, P.n_ntiles,
                  P.n_ksteps, P.MB_total, P.MBs, P.n_passes, smem, P.n_groups * P.n_bands, eff);
     }
     return 0;

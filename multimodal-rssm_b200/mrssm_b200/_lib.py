@@ -102,6 +102,7 @@ SYMBOLS = {
     "mrssm_pl_pack_weight": [_vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
     "mrssm_pl_describe": [C.POINTER(TcConvArgs), _i32, C.c_char_p, _i32],
     "mrssm_pl_set_debug": [_i32, _i32],
+    "mrssm_pl_set_profile_buffer": [_vp],
     "mrssm_rollout_fwd": [C.POINTER(RolloutArgs), _vp],
     "mrssm_rollout_bwd": [C.POINTER(RolloutBwdArgs), _vp],
     "mrssm_latent_fwd": [C.POINTER(LatentArgs), _vp],

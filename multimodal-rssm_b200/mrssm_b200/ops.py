@@ -799,8 +799,19 @@ def _bf16(*shape, device):
     return torch.empty(*shape, device=device, dtype=torch.bfloat16)
 
 
+def packed_pl(w, op, Cs_pad, Cl_pad):
+    """Cached plane-kernel packing of a conv weight (re-packed when the master changes)."""
+    key = (w.data_ptr(), "pl", op, Cs_pad, Cl_pad)
+    ver = (_STATE["wversion"], w._version)
+    hit = _wcache.get(key)
+    if hit is None or hit[0] != ver:
+        hit = (ver, pl_pack_weight(w.detach(), op, Cs_pad, Cl_pad))
+        _wcache[key] = hit
+    return hit[1]
+
+
 class ConvEncoderTCFn(Function):
-    """ConvEncoderFn on the tcgen05 kernels: NCHW fp32 image -> bf16 NHWC(8) -> conv stack (bf16 NHWC
+    """ConvEncoderFn on tensor cores: NCHW fp32 image -> bf16 NHWC(8) -> plane conv stack (bf16 NHWC
     intermediates) -> fp32 [N, C*h*w] embedding in (C,H,W) order."""
 
     @staticmethod
@@ -816,17 +827,17 @@ class ConvEncoderTCFn(Function):
         for i in range(n_layers):
             Wt, b = params[2 * i], params[2 * i + 1]
             Cs, Cl, k, _ = Wt.shape
-            Clp = acts[-1].shape[-1]
+            Clp, Csp = acts[-1].shape[-1], pad16(Cs)
             Hs, Ws = (Hl - k) // 2 + 1, (Wl - k) // 2 + 1
-            geom = (N, Hl, Wl, Clp, Hs, Ws, pad16(Cs), k)
-            wp = packed(Wt, 0, pad16(Cs), Clp)
+            geom = (N, Hl, Wl, Clp, Hs, Ws, Csp, k)
+            wp = packed_pl(Wt, DOWN, Csp, Clp)
             xin = L.nhwc(acts[-1], Hl, Wl, Clp)
             if i == n_layers - 1:
                 y = torch.empty(N, Cs * Hs * Ws, device=dev, dtype=torch.float32)
-                tc_conv_down(geom, xin, L.nchw(y, Hs, Ws, Cs), wp, b, Cs, act=RELU, out_f32=1, valid=(Cs, Cl))
+                pl_conv_down(geom, xin, L.nchw(y, Hs, Ws, Cs), wp, b, Cs, Csp, act=RELU, out_f32=1, valid=(Cs, Cl))
             else:
-                o = _bf16(N, Hs, Ws, pad16(Cs), device=dev)
-                tc_conv_down(geom, xin, L.nhwc(o, Hs, Ws, pad16(Cs)), wp, b, Cs, act=RELU, valid=(Cs, Cl))
+                o = _bf16(N, Hs, Ws, Csp, device=dev)
+                pl_conv_down(geom, xin, L.nhwc(o, Hs, Ws, Csp), wp, b, Cs, Csp, act=RELU, valid=(Cs, Cl))
                 acts.append(o)
             geoms.append((geom, Cs, Cl))
             Hl, Wl = Hs, Ws
@@ -848,20 +859,19 @@ class ConvEncoderTCFn(Function):
             geom, Cs, Cl = geoms[i]
             N, Hl, Wl, Clp, Hs, Ws, Csp, k = geom
             xi = acts[i]
-            tc_conv_wgrad(geom, L.nhwc(xi, Hl, Wl, Clp), L.nhwc(gb, Hs, Ws, Csp), L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl)
+            pl_conv_wgrad(geom, L.nhwc(xi, Hl, Wl, Clp), L.nhwc(gb, Hs, Ws, Csp), L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl)
             tc_colsum(gb, Cs, grad_buf(b))
             if i > 0:
                 gx = _bf16(N, Hl, Wl, Clp, device=dev)
-                wp = packed(Wt, 1, Csp, Clp)
-                tc_conv_up(geom, L.nhwc(gx, Hl, Wl, Clp), L.nhwc(gb, Hs, Ws, Csp), wp, None, Cl,
+                pl_conv_up(geom, L.nhwc(gx, Hl, Wl, Clp), L.nhwc(gb, Hs, Ws, Csp), packed_pl(Wt, UP, Csp, Clp), None, Cl, Clp,
                            mask=L.nhwc(xi, Hl, Wl, Clp), mask_mode=RELU, valid=(Cs, Cl))
                 gb = gx
         return (None, *([None] * len(params)))
 
 
 class ConvDecoderTCFn(Function):
-    """ConvDecoderFn on the tcgen05 kernels.  fc([h,s]) and the ConvTranspose on the 1x1 map are dense GEMMs,
-    the remaining layers are parity-class `up` implicit GEMMs; output is fp32 NCHW."""
+    """ConvDecoderFn on tensor cores.  fc([h,s]) and the ConvTranspose on the 1x1 map are dense tcgen05 GEMMs, the
+    remaining layers are plane `up` kernels (all four output parities in one pass); output is fp32 NCHW."""
 
     @staticmethod
     def forward(ctx, h, s, *params):
@@ -891,7 +901,7 @@ class ConvDecoderTCFn(Function):
             Csp = acts[-1].shape[-1]
             Hl, Wl = 2 * (Hs - 1) + k, 2 * (Ws - 1) + k
             last = i == n_layers - 1
-            Clp = pad16(Cl)
+            Clp = pad8(Cl) if last else pad16(Cl)
             geom = (R, Hl, Wl, Clp, Hs, Ws, Csp, k)
             xin = L.nhwc(acts[-1], Hs, Ws, Csp)
             if i == 0 and Hs == 1 and not last:
@@ -903,10 +913,10 @@ class ConvDecoderTCFn(Function):
                 acts.append(o)
             elif last:
                 out = torch.empty(R, Cl, Hl, Wl, device=dev, dtype=torch.float32)
-                tc_conv_up(geom, L.nchw(out, Hl, Wl, Cl), xin, packed(Wt, 1, Csp, Clp), b, Cl, out_f32=1, valid=(Cs, Cl))
+                pl_conv_up(geom, L.nchw(out, Hl, Wl, Cl), xin, packed_pl(Wt, UP, Csp, Clp), b, Cl, Clp, out_f32=1, valid=(Cs, Cl))
             else:
                 o = _bf16(R, Hl, Wl, Clp, device=dev)
-                tc_conv_up(geom, L.nhwc(o, Hl, Wl, Clp), xin, packed(Wt, 1, Csp, Clp), b, Cl, act=RELU, valid=(Cs, Cl))
+                pl_conv_up(geom, L.nhwc(o, Hl, Wl, Clp), xin, packed_pl(Wt, UP, Csp, Clp), b, Cl, Clp, act=RELU, valid=(Cs, Cl))
                 acts.append(o)
             geoms.append((geom, Cs, Cl))
             Hs, Ws = Hl, Wl
@@ -924,7 +934,7 @@ class ConvDecoderTCFn(Function):
         n_layers = len(geoms)
         g = _f32c(g)
         (_, Hl, Wl, Clp, _, _, _, _), _, Cl = geoms[-1]
-        gb = tc_to_bf16(L.nchw(g, Hl, Wl, Cl), R, Hl, Wl, Cl, dev)
+        gb = tc_to_bf16(L.nchw(g, Hl, Wl, Cl), R, Hl, Wl, Cl, dev, Cpad=Clp)
         for i in reversed(range(n_layers)):
             Wt, b = convs[2 * i], convs[2 * i + 1]
             geom, Cs, Cl = geoms[i]
@@ -932,11 +942,17 @@ class ConvDecoderTCFn(Function):
             Clg = gb.shape[-1]                       # channel padding of the gradient tensor as stored
             gg = (R, Hl, Wl, Clg, Hs, Ws, Csp, k)
             xi = acts[i]
-            tc_conv_wgrad(gg, L.nhwc(gb, Hl, Wl, Clg), L.nhwc(xi, Hs, Ws, Csp), L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl)
-            tc_colsum(gb, Cl, grad_buf(b))
+            dense = Hs == 1 and Ws == 1              # ConvTranspose on the 1x1 map: the dense kernels
             gx = _bf16(R, Hs, Ws, Csp, device=dev)
-            tc_conv_down(gg, L.nhwc(gb, Hl, Wl, Clg), L.nhwc(gx, Hs, Ws, Csp), packed(Wt, 0, Csp, Clg), None, Cs,
-                         mask=L.nhwc(xi, Hs, Ws, Csp) if i > 0 else None, mask_mode=RELU if i > 0 else 0, valid=(Cs, Cl))
+            if dense:
+                tc_conv_wgrad(gg, L.nhwc(gb, Hl, Wl, Clg), L.nhwc(xi, Hs, Ws, Csp), L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl)
+                tc_conv_down(gg, L.nhwc(gb, Hl, Wl, Clg), L.nhwc(gx, Hs, Ws, Csp), packed(Wt, 0, Csp, Clg), None, Cs,
+                             mask=L.nhwc(xi, Hs, Ws, Csp) if i > 0 else None, mask_mode=RELU if i > 0 else 0, valid=(Cs, Cl))
+            else:
+                pl_conv_wgrad(gg, L.nhwc(gb, Hl, Wl, Clg), L.nhwc(xi, Hs, Ws, Csp), L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl)
+                pl_conv_down(gg, L.nhwc(gb, Hl, Wl, Clg), L.nhwc(gx, Hs, Ws, Csp), packed_pl(Wt, DOWN, Csp, Clg), None, Cs, Csp,
+                             mask=L.nhwc(xi, Hs, Ws, Csp) if i > 0 else None, mask_mode=RELU if i > 0 else 0, valid=(Cs, Cl))
+            tc_colsum(gb, Cl, grad_buf(b))
             gb = gx
         fcw, fcb = params[0], params[1]
         Emp = gb.shape[-1]

@@ -1,0 +1,50 @@
+"""Per-tile clock64 timeline of the plane fwd-type kernel for one layer (tuning aid)."""
+import sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "multimodal-rssm_b200"))
+import torch
+from mrssm_b200 import _lib as L, ops
+
+def main(op="down", n=4096, Hl=64, Cl=3, Hs=31, Cs=32, k=4, f32=0):
+    dev = "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(0)
+    Clp, Csp = ops.pad8(Cl), ops.pad16(Cs)
+    lb = torch.randn(n, Hl, Hl, Clp, device=dev, generator=g).to(torch.bfloat16)
+    sb = torch.randn(n, Hs, Hs, Csp, device=dev, generator=g).to(torch.bfloat16)
+    w = torch.randn(Cs, Cl, k, k, device=dev, generator=g) / (Cl * k * k) ** 0.5
+    gp = (n, Hl, Hl, Clp, Hs, Hs, Csp, k)
+    prof = torch.zeros(148 * 16 * 8, device=dev, dtype=torch.int64)
+    if op == "down":
+        wp = ops.pl_pack_weight(w, ops.DOWN, Csp, Clp)
+        bias = torch.zeros(Cs, device=dev)
+        out = torch.zeros(n, Hs, Hs, Csp, device=dev, dtype=torch.bfloat16)
+        f = lambda: ops.pl_conv_down(gp, L.nhwc(lb, Hl, Hl, Clp), L.nhwc(out, Hs, Hs, Csp), wp, bias, Cs, Csp, act=1)
+    else:
+        wp = ops.pl_pack_weight(w, ops.UP, Csp, Clp)
+        bias = torch.zeros(Cl, device=dev)
+        if f32:
+            out = torch.zeros(n, Cl, Hl, Hl, device=dev)
+            f = lambda: ops.pl_conv_up(gp, L.nchw(out, Hl, Hl, Cl), L.nhwc(sb, Hs, Hs, Csp), wp, bias, Cl, Clp, out_f32=1)
+        else:
+            out = torch.zeros(n, Hl, Hl, Clp, device=dev, dtype=torch.bfloat16)
+            f = lambda: ops.pl_conv_up(gp, L.nhwc(out, Hl, Hl, Clp), L.nhwc(sb, Hs, Hs, Csp), wp, bias, Cl, Clp, act=1)
+    for _ in range(2):
+        f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); f(); e1.record(); torch.cuda.synchronize()
+    print(f"{op} n={n} [{Hl}x{Hl}x{Cl}<->{Hs}x{Hs}x{Cs} k{k}] f32={f32}: {e0.elapsed_time(e1):.3f} ms")
+    L.call_host("mrssm_pl_set_profile_buffer", prof.data_ptr())
+    f(); torch.cuda.synchronize()
+    L.call_host("mrssm_pl_set_profile_buffer", None)
+    p = prof.cpu().reshape(148, 16, 8)
+    names = ["P:start", "P:loop", "M:afull", "M:issued", "E:accfull", "E:end", "P:Anext", "P:Bdone"]
+    for cta in (0, 77):
+        t0 = int(p[cta, 0, 0])
+        print(f"CTA {cta} (cycles since start)")
+        for it in range(6):
+            print("  tile", it, " ".join(f"{names[s]}={int(p[cta, it, s]) - t0 if p[cta, it, s] else -1:>8d}" for s in (1, 6, 7, 2, 3, 4, 5)))
+
+if __name__ == "__main__":
+    a = sys.argv[1:]
+    main(a[0], *[int(x) for x in a[1:]])

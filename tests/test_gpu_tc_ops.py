@@ -116,3 +116,81 @@ def test_tc_up_1x1_as_dense():
     ops.tc_conv_down((n, 1, 1, Cs, 1, 1, k * k * Cl, 1), L.nhwc(xb, 1, 1, Cs), L.nhwc(out, 1, 1, k * k * Cl), wp, bias,
                      k * k * Cl, act=ops.RELU, bias_mod=Cl)
     torch.testing.assert_close(out.float().reshape(n, k, k, Cl), ref, rtol=1e-2, atol=1e-2)
+
+
+# ---- plane kernels (csrc/conv_plane.cu): TMA-staged planes + shifted descriptors, every spatial geometry -------------
+# (down needs 4*Cl/8 planes of >= 128 pixels resident: Cl <= 128)
+PL_GEOMS = [g for g in GEOMS if g[5] >= 2 and g[3] > 1 and g[2] <= 128] + [(30, 6, 128, 2, 256, 4), (5, 13, 64, 5, 128, 5),
+                                                                         (37, 14, 64, 6, 128, 4), (2, 14, 128, 6, 256, 4)]
+
+
+def _pl_setup(g):
+    from mrssm_b200 import _lib as L, ops
+    n, Hl, Cl, Hs, Cs, k = g
+    gen = torch.Generator(device=DEV).manual_seed(hash(g) % 1000)
+    large = _bf16_round(torch.randn(n, Hl, Hl, Cl, device=DEV, generator=gen))
+    small = _bf16_round(torch.randn(n, Hs, Hs, Cs, device=DEV, generator=gen))
+    w = _bf16_round(torch.randn(Cs, Cl, k, k, device=DEV, generator=gen) / (Cl * k * k) ** 0.5)
+    Clp, Csp = ops.pad8(Cl), ops.pad16(Cs)
+    lb = ops.tc_to_bf16(L.nhwc(large, Hl, Hl, Cl), n, Hl, Hl, Cl, DEV, Cpad=Clp)
+    sb = ops.tc_to_bf16(L.nhwc(small, Hs, Hs, Cs), n, Hs, Hs, Cs, DEV, Cpad=Csp)
+    return L, ops, (n, Hl, Hl, Cl, Hs, Hs, Cs, k), (n, Hl, Hl, Clp, Hs, Hs, Csp, k), (large, small, w), (lb, sb)
+
+
+@pytest.mark.parametrize("g", PL_GEOMS)
+def test_plane_down_matches_simt(g):
+    L, ops, geom, gp, (large, small, w), (lb, sb) = _pl_setup(g)
+    n, Hl, _, Cl, Hs, _, Cs, k = geom
+    Clp, Csp = gp[3], gp[6]
+    bias = torch.randn(Cs, device=DEV)
+    ref = torch.empty_like(small)
+    ops._conv("mrssm_conv_down", geom, L.nhwc(large, Hl, Hl, Cl), L.nhwc(ref, Hs, Hs, Cs), L.ptr(w), Cl * k * k, k * k,
+              L.ptr(bias), ops.RELU)
+    wp = ops.pl_pack_weight(w, ops.DOWN, Csp, Clp)
+    out = torch.full((n, Hs, Hs, Csp), 7.0, device=DEV, dtype=torch.bfloat16)
+    ops.pl_conv_down(gp, L.nhwc(lb, Hl, Hl, Clp), L.nhwc(out, Hs, Hs, Csp), wp, bias, Cs, Csp, act=ops.RELU)
+    torch.testing.assert_close(out[..., :Cs].float(), ref, rtol=1e-2, atol=1e-2)
+    assert float(out[..., Cs:].float().abs().max() if Csp > Cs else 0.0) == 0.0
+    out32 = torch.empty(n, Cs, Hs, Hs, device=DEV)
+    ops.pl_conv_down(gp, L.nhwc(lb, Hl, Hl, Clp), L.nchw(out32, Hs, Hs, Cs), wp, bias, Cs, Csp, act=ops.RELU, out_f32=1)
+    torch.testing.assert_close(out32.permute(0, 2, 3, 1), ref, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("g", PL_GEOMS)
+def test_plane_up_and_dgrad_match_simt(g):
+    L, ops, geom, gp, (large, small, w), (lb, sb) = _pl_setup(g)
+    n, Hl, _, Cl, Hs, _, Cs, k = geom
+    Clp, Csp = gp[3], gp[6]
+    wp = ops.pl_pack_weight(w, ops.UP, Csp, Clp)
+    if Hl == 2 * (Hs - 1) + k:      # ConvTranspose2d forward (+bias, ReLU), bf16 NHWC and fp32 NCHW outputs
+        bias = torch.randn(Cl, device=DEV)
+        ref = torch.empty_like(large)
+        ops._conv("mrssm_conv_up", geom, L.nhwc(ref, Hl, Hl, Cl), L.nhwc(small, Hs, Hs, Cs), L.ptr(w), Cl * k * k, k * k,
+                  L.ptr(bias), ops.RELU)
+        out = torch.full((n, Hl, Hl, Clp), 7.0, device=DEV, dtype=torch.bfloat16)
+        ops.pl_conv_up(gp, L.nhwc(out, Hl, Hl, Clp), L.nhwc(sb, Hs, Hs, Csp), wp, bias, Cl, Clp, act=ops.RELU)
+        torch.testing.assert_close(out[..., :Cl].float(), ref, rtol=1e-2, atol=1e-2)
+        out32 = torch.empty(n, Cl, Hl, Hl, device=DEV)
+        ops.pl_conv_up(gp, L.nchw(out32, Hl, Hl, Cl), L.nhwc(sb, Hs, Hs, Csp), wp, bias, Cl, Clp, act=ops.RELU, out_f32=1)
+        torch.testing.assert_close(out32.permute(0, 2, 3, 1), ref, rtol=2e-3, atol=2e-3)
+    # Conv2d dgrad with the ReLU mask of the layer input (floor geometries included)
+    ref = torch.empty_like(large)
+    ops._conv("mrssm_conv_up", geom, L.nhwc(ref, Hl, Hl, Cl), L.nhwc(small, Hs, Hs, Cs), L.ptr(w), Cl * k * k, k * k,
+              None, 0, L.ptr(large), ops.RELU)
+    out = torch.full((n, Hl, Hl, Clp), 7.0, device=DEV, dtype=torch.bfloat16)
+    ops.pl_conv_up(gp, L.nhwc(out, Hl, Hl, Clp), L.nhwc(sb, Hs, Hs, Csp), wp, None, Cl, Clp,
+                   mask=L.nhwc(lb, Hl, Hl, Clp), mask_mode=ops.RELU)
+    torch.testing.assert_close(out[..., :Cl].float(), ref, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("g", PL_GEOMS)
+def test_plane_wgrad_matches_simt(g):
+    L, ops, geom, gp, (large, small, w), (lb, sb) = _pl_setup(g)
+    n, Hl, _, Cl, Hs, _, Cs, k = geom
+    Clp, Csp = gp[3], gp[6]
+    ref = torch.zeros_like(w)
+    ops._conv("mrssm_conv_wgrad", geom, L.nhwc(large, Hl, Hl, Cl), L.nhwc(small, Hs, Hs, Cs), L.ptr(ref), Cl * k * k, k * k)
+    out = torch.zeros_like(w)
+    ops.pl_conv_wgrad(gp, L.nhwc(lb, Hl, Hl, Clp), L.nhwc(sb, Hs, Hs, Csp), L.ptr(out), Cl * k * k, k * k, Cs, Cl)
+    scale = float(ref.abs().max())
+    assert float((out - ref).abs().max()) <= 2e-3 * scale + 1e-4
