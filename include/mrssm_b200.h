@@ -116,20 +116,49 @@ int mrssm_tc_from_bf16(const void* src, int32_t n_img, int32_t H, int32_t W, int
 int mrssm_tc_colsum(const void* x, int64_t rows, int32_t Cpad, int32_t Cvalid, float* out, void* stream);
 
 /* ---- "plane" tensor-core conv family (ksz >= 2): TMA-staged activation tile + shifted UMMA descriptors ----
- * Same argument struct and tensor conventions as mrssm_tc_conv_*; replaces the same reference call sites
- * (encoder.py:315-322, observation_model.py:65-74 and their autograd).  Differences:
- *  - the gathered tensor of `up` needs channels padded to 16, of `down` to 8; bf16 outputs padded to n_out_pad;
- *  - `up`: n_out_pad is the per-parity-class channel padding (multiple of 8) of the output tensor;
- *  - weights are packed by mrssm_pl_pack_weight (op 0 = down, 1 = up) into [N_total][K_total] bf16 whose
- *    shape mrssm_pl_packed_shape reports;
- *  - mrssm_pl_describe (host only, no GPU) formats the tiling plan of a layer (op 0 down, 1 up, 2 wgrad). */
-int mrssm_pl_conv_down(const mrssm_tc_conv_args* a, void* stream);
-int mrssm_pl_conv_up(const mrssm_tc_conv_args* a, void* stream);
-int mrssm_pl_conv_wgrad(const mrssm_tc_conv_args* a, void* stream);
+ * Replaces the same reference call sites as mrssm_tc_conv_* (encoder.py:315-322, observation_model.py:65-74 and their
+ * autograd).  bf16 activations are addressed through views with channels in chunks of 8 (padded channels hold zeros):
+ *   linear        : element (i,y,x,c) at ptr[i*sI + y*sH + x*sW + (c/8)*sK + c%8]   (NHWC: sW=C, sK=8; planar: sW=8, sK=H*W*8)
+ *   parity-planar : pixel (y,x) lives in plane (y&1)*2+(x&1) at row y>>1, column x>>1:
+ *                   ptr[i*sI + ((y&1)*2+(x&1))*sP + (c/8)*sK + (y>>1)*sH + (x>>1)*sW + c%8]
+ * x-contiguous views (sW == 8) load with one TMA row per run of pixels; the operand that is gathered with stride 2
+ * (`large` of down / wgrad) should be parity-planar, the others planar.  Geometry, weight layout [cs][cl][kh][kw] and the
+ * meaning of down / up / wgrad are those of mrssm_conv_args.  `up`: n_out_pad is the per-parity-class channel padding
+ * (multiple of 8) of the output; the gathered tensor of `up` needs channels padded to 16.  Weights are packed by
+ * mrssm_pl_pack_weight (op 0 = down, 1 = up) into [N_total][K_total] bf16 (shape from mrssm_pl_packed_shape). */
+typedef struct mrssm_tv {
+    void* ptr;
+    int64_t sI, sH, sW, sK, sP;
+    int32_t par, reserved;
+} mrssm_tv;
+
+typedef struct mrssm_pl_conv_args {
+    int32_t n_img, Hl, Wl, Cl, Hs, Ws, Cs, ksz;   /* Cl / Cs: PADDED channel counts of the bf16 views */
+    int32_t act, mask_mode, out_f32;
+    int32_t n_out_pad, n_out_valid;
+    int32_t cs_valid, cl_valid;                    /* wgrad: real channel counts of the master weight */
+    int32_t reserved;
+    mrssm_tv large, small, mask;                   /* mask: indexed at the output pixel */
+    mrssm_t4 out32;                                /* fp32 output of down/up when out_f32 (arbitrary strides, e.g. NCHW) */
+    const void* wpacked;
+    const float* bias;
+    float* dweight;                                /* wgrad output (accumulated), PyTorch layout */
+    int64_t w_ss, w_sl;
+} mrssm_pl_conv_args;
+
+int mrssm_pl_conv_down(const mrssm_pl_conv_args* a, void* stream);
+int mrssm_pl_conv_up(const mrssm_pl_conv_args* a, void* stream);
+int mrssm_pl_conv_wgrad(const mrssm_pl_conv_args* a, void* stream);
 int mrssm_pl_packed_shape(int32_t op, int32_t Cs_pad, int32_t Cl_pad, int32_t ksz, int32_t* N_total, int32_t* K_total);
 int mrssm_pl_pack_weight(const float* w, int64_t w_ss, int64_t w_sl, int32_t Cs_valid, int32_t Cl_valid, int32_t Cs_pad,
                          int32_t Cl_pad, int32_t ksz, int32_t op, void* out, void* stream);
-int mrssm_pl_describe(const mrssm_tc_conv_args* a, int32_t op, char* buf, int32_t buflen);
+/* fp32 strided [n,H,W,C] -> bf16 view with channels padded to Cpad (x scale); image_processing / autograd glue */
+int mrssm_pl_import(const mrssm_t4* src, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t Cpad, float scale,
+                    const mrssm_tv* dst, void* stream);
+/* out[c] += sum over (img,y,x) of the view: bias gradients (autograd of encoder.py:315-322, observation_model.py:65-74) */
+int mrssm_pl_colsum(const mrssm_tv* x, int32_t n_img, int32_t H, int32_t W, int32_t Cpad, int32_t Cvalid, float* out, void* stream);
+/* host only, no GPU: format the tiling plan of a layer (op 0 down, 1 up, 2 wgrad) */
+int mrssm_pl_describe(const mrssm_pl_conv_args* a, int32_t op, char* buf, int32_t buflen);
 /* bring-up switches (descriptor-field variants); 0 = production setting */
 int mrssm_pl_set_debug(int32_t key, int32_t value);
 /* tuning aid: device buffer of 148*16*8 int64 receiving per-tile clock64 stamps of the fwd-type kernel (NULL = off) */

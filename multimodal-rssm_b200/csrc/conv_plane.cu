@@ -38,6 +38,20 @@ struct T4 {
 };
 inline T4 cvt(const mrssm_t4& t) { return T4{t.ptr, t.sI, t.sH, t.sW, t.sC}; }
 
+// bf16 activation view with channels in chunks of 8 (mrssm_tv): linear (NHWC: sW = C, sK = 8; planar: sW = 8, sK = H*W*8)
+// or parity-planar (par): pixel (y,x) lives in plane (y&1)*2+(x&1) at row y>>1, column x>>1.
+struct TV {
+    const void* p;
+    long long sI, sH, sW, sK, sP;
+    int par;
+};
+inline TV cvt(const mrssm_tv& t) { return TV{t.ptr, t.sI, t.sH, t.sW, t.sK, t.sP, t.par}; }
+// element offset of channel 0 of pixel (y, x) of image img
+__device__ __forceinline__ long long tv_pix(const TV& t, int img, int y, int x) {
+    if (t.par) return img * t.sI + ((y & 1) * 2 + (x & 1)) * t.sP + (y >> 1) * t.sH + (x >> 1) * t.sW;
+    return img * t.sI + y * t.sH + x * t.sW;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // TMA + descriptors
 // ---------------------------------------------------------------------------------------------------
@@ -86,7 +100,7 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// activation map: bf16 [N][Y][X][C] with byte strides, box {8, bx, by, bi}, no swizzle, zero OOB fill
+// activation map, element form: bf16 [N][Y][X][C] with byte strides, box {8, bx, by, bi}, no swizzle, zero OOB fill
 int make_act_map(CUtensorMap* m, const void* base, long long C, long long X, long long Y, long long N, long long sx, long long sy,
                  long long sn, int bx, int by, int bi) {
     EncodeTiledFn enc = get_encode();
@@ -103,6 +117,62 @@ int make_act_map(CUtensorMap* m, const void* base, long long C, long long X, lon
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MRSSM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: %d (dims %lld %lld %lld %lld strides %lld %lld %lld box %d %d %d)",
                 (int)r, C, X, Y, N, sx, sy, sn, bx, by, bi);
+    return 0;
+}
+// activation map, merged form for x-contiguous planes: the 16-byte pixel-chunk is two 64-bit elements, so one box row is a
+// whole run of bx pixels (bx*16 contiguous bytes).  dims {2X, Y, chunks, N}, box {2bx, by, 1, bi}.
+int make_act_map_merged(CUtensorMap* m, const void* base, long long X, long long Y, long long chunks, long long N, long long sy,
+                        long long sk, long long sn, int bx, int by, int bi) {
+    EncodeTiledFn enc = get_encode();
+    MRSSM_CHECK(enc, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[4] = {(cuuint64_t)(2 * X), (cuuint64_t)Y, (cuuint64_t)chunks, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)sy, (cuuint64_t)sk, (cuuint64_t)sn};
+    cuuint32_t box[4] = {(cuuint32_t)(2 * bx), (cuuint32_t)by, 1, (cuuint32_t)bi};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    MRSSM_CHECK(X >= 1 && Y >= 1 && N >= 1 && chunks >= 1 && 2 * bx <= 256 && by <= 256 && bi <= 256 && sy % 16 == 0 && sk % 16 == 0 &&
+                    sn % 16 == 0 && ((uintptr_t)base & 15) == 0,
+                "plane conv: planar tensor not TMA-addressable (dims %lld %lld %lld %lld strides %lld %lld %lld box %d %d %d)", X, Y, chunks,
+                N, sy, sk, sn, bx, by, bi);
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MRSSM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(planar) failed: %d (dims %lld %lld %lld %lld strides %lld %lld %lld box %d %d %d)",
+                (int)r, X, Y, chunks, N, sy, sk, sn, bx, by, bi);
+    return 0;
+}
+// Tensor maps of a source view [N][H][W][Cp]: one map (whole tensor) or four (its 2x2 parity sub-grids).  *merged reports
+// the coordinate convention the kernel must use: merged (2*x, y, chunk, img) or element (chunk*8, x, y, img).
+int make_view_maps(CUtensorMap* maps, int* merged, const mrssm_tv& t, int H, int W, int Cp, int N, bool parity_split, int bx, int by, int bi) {
+    const char* base = (const char*)t.ptr;
+    if (!parity_split) {
+        MRSSM_CHECK(!t.par, "plane conv: this operand must be a linear (NHWC or planar) view, not parity-planar");
+        if (t.sW == 8 && 2 * bx <= 256) {
+            *merged = 1;
+            if (int rc = make_act_map_merged(&maps[0], base, W, H, Cp / 8, N, 2 * t.sH, 2 * t.sK, 2 * t.sI, bx, by, bi)) return rc;
+        } else {
+            MRSSM_CHECK(t.sK == 8, "plane conv: a pixel-strided view must keep its channels contiguous (sK == 8)");
+            *merged = 0;
+            if (int rc = make_act_map(&maps[0], base, Cp, W, H, N, 2 * t.sW, 2 * t.sH, 2 * t.sI, bx, by, bi)) return rc;
+        }
+        maps[1] = maps[2] = maps[3] = maps[0];
+        return 0;
+    }
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            const long long X = std::max(1, (W - px + 1) / 2), Y = std::max(1, (H - py + 1) / 2);
+            if (t.par) {
+                MRSSM_CHECK(t.sW == 8 && 2 * bx <= 256, "plane conv: parity-planar views must be x-contiguous (sW == 8) with boxes <= 128 pixels");
+                *merged = 1;
+                if (int rc = make_act_map_merged(&maps[py * 2 + px], base + 2 * (py * 2 + px) * t.sP, X, Y, Cp / 8, N, 2 * t.sH, 2 * t.sK, 2 * t.sI,
+                                                 bx, by, bi))
+                    return rc;
+            } else {
+                MRSSM_CHECK(t.sK == 8, "plane conv: a linear view split by parity must be NHWC (sK == 8); use a parity-planar view");
+                *merged = 0;
+                if (int rc = make_act_map(&maps[py * 2 + px], base + 2 * (py * t.sH + px * t.sW), Cp, X, Y, N, 4 * t.sW, 4 * t.sH, 2 * t.sI, bx,
+                                          by, bi))
+                    return rc;
+            }
+        }
     return 0;
 }
 // weight map: bf16 [N_total][K_total] row-major, box {64, BN}, 128B swizzle
@@ -135,8 +205,10 @@ struct FwdP {
     int NA, NB, b_res;          // b_res: the whole packed weight stays resident in shared memory (NB == nkb)
     int act, mask_mode, out_f32, n_valid, Cop, Ho, Wo;
     int a_stage_bytes;
+    int mergedA;                // TMA coordinate convention of the activation maps
     long long* prof;            // [CTA][16 tiles][8 slots] clock64 stamps or NULL
-    T4 out, mask;
+    TV out, mask;               // bf16 output / act'-mask views (indexed at the output pixel)
+    T4 out32;                   // fp32 output (F32 kernels)
     const float* bias;
 };
 #define PROF(slot) do { if (P.prof && lit < 16) P.prof[((long long)blockIdx.x * 16 + lit) * 8 + (slot)] = clock64(); } while (0)
@@ -180,7 +252,7 @@ __device__ __forceinline__ void epi_store8(const FwdP& P, const float* v, const 
         for (int e = 0; e < 8; ++e) x[e] = x[e] > 0.f ? x[e] : expm1f(x[e]);
     }
     if (P.mask_mode) {
-        const uint4 mk = __ldg(reinterpret_cast<const uint4*>((const bf16*)P.mask.p + m_off + cl0));
+        const uint4 mk = __ldg(reinterpret_cast<const uint4*>((const bf16*)P.mask.p + m_off + (cl0 >> 3) * P.mask.sK));
         const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mk);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -190,16 +262,16 @@ __device__ __forceinline__ void epi_store8(const FwdP& P, const float* v, const 
         }
     }
     if (F32) {
-        float* op = (float*)P.out.p + o_off;
+        float* op = (float*)P.out32.p + o_off;
 #pragma unroll
         for (int e = 0; e < 8; ++e)
-            if (cl0 + e < P.n_valid) op[(long long)(cl0 + e) * P.out.sC] = x[e];
+            if (cl0 + e < P.n_valid) op[(long long)(cl0 + e) * P.out32.sC] = x[e];
     } else {
         uint4 pk;
         __nv_bfloat162* ph = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
         for (int e = 0; e < 4; ++e) ph[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
-        *reinterpret_cast<uint4*>((bf16*)P.out.p + o_off + cl0) = pk;
+        *reinterpret_cast<uint4*>((bf16*)P.out.p + o_off + (cl0 >> 3) * P.out.sK) = pk;
     }
 }
 
@@ -266,9 +338,12 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                 const int ig = tile / P.n_bands, band = tile - ig * P.n_bands;
                 const uint32_t dst = smemA + (uint32_t)sa * (uint32_t)P.a_stage_bytes;
                 for (int q = 0; q < P.planes; ++q) {
-                    const int mi = q / P.ppm, c0 = (q - mi * P.ppm) * 8;
+                    const int mi = q / P.ppm, ch = q - mi * P.ppm;
                     const CUtensorMap* m = mi == 0 ? &mA0 : (mi == 1 ? &mA1 : (mi == 2 ? &mA2 : &mA3));
-                    tma_load_4d(dst + (uint32_t)q * (uint32_t)P.PS, m, c0, P.x0, band * P.TH + P.y0, ig * P.BI, bar);
+                    if (P.mergedA)
+                        tma_load_4d(dst + (uint32_t)q * (uint32_t)P.PS, m, 2 * P.x0, band * P.TH + P.y0, ch, ig * P.BI, bar);
+                    else
+                        tma_load_4d(dst + (uint32_t)q * (uint32_t)P.PS, m, ch * 8, P.x0, band * P.TH + P.y0, ig * P.BI, bar);
                 }
                 ++acnt;
             };
@@ -391,18 +466,15 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                     const int i = p / IP, r = p - i * IP, yr = r / P.BX, x = r - yr * P.BX;
                     const int img = ig * P.BI + i, y = band * P.TH + yr;
                     const bool row_ok = i < P.BI && img < P.n_img && yr < P.TH && y < P.Hv && x < P.Wv;
-                    long long o_base, m_base = 0;
-                    if (OP == OP_DOWN) {
-                        o_base = img * P.out.sI + y * P.out.sH + x * P.out.sW;
-                        if (P.mask_mode) m_base = img * P.mask.sI + y * P.mask.sH + x * P.mask.sW;
-                    } else {
-                        o_base = img * P.out.sI + 2 * y * P.out.sH + 2 * x * P.out.sW;
-                        if (P.mask_mode) m_base = img * P.mask.sI + 2 * y * P.mask.sH + 2 * x * P.mask.sW;
-                    }
                     int cls = 0, cl0 = n0;
                     if (OP == OP_UP) {
                         cls = n0 / P.Cop;
                         cl0 = n0 - cls * P.Cop;
+                    }
+                    long long o_base = 0, m_base = 0;
+                    if (OP == OP_DOWN && row_ok) {
+                        o_base = F32 ? img * P.out32.sI + y * P.out32.sH + x * P.out32.sW : tv_pix(P.out, img, y, x);
+                        if (P.mask_mode) m_base = tv_pix(P.mask, img, y, x);
                     }
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * P.set_cols + mb * P.BN + col0);
                     for (int c0 = 0; c0 < ncols; c0 += 32) {
@@ -417,10 +489,12 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                             bool ok = row_ok;
                             long long o_off = o_base, m_off = m_base;
                             if (OP == OP_UP) {
-                                const int py = cls >> 1, px = cls & 1;
-                                ok = ok && (2 * y + py < P.Ho) && (2 * x + px < P.Wo);
-                                o_off += py * P.out.sH + px * P.out.sW;
-                                if (P.mask_mode) m_off += py * P.mask.sH + px * P.mask.sW;
+                                const int yy = 2 * y + (cls >> 1), xx = 2 * x + (cls & 1);
+                                ok = ok && yy < P.Ho && xx < P.Wo;
+                                if (ok) {
+                                    o_off = F32 ? img * P.out32.sI + yy * P.out32.sH + xx * P.out32.sW : tv_pix(P.out, img, yy, xx);
+                                    if (P.mask_mode) m_off = tv_pix(P.mask, img, yy, xx);
+                                }
                             }
                             if (ok) epi_store8<F32>(P, v + 8 * h, bias_s, cl0, o_off, m_off);
                             cl0 += 8;
@@ -450,7 +524,7 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
 // ---------------------------------------------------------------------------------------------------
 // planner for the forward-type kernel
 // ---------------------------------------------------------------------------------------------------
-int plan_fwd(const mrssm_tc_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
+int plan_fwd(const mrssm_pl_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
     memset(&P, 0, sizeof(P));
     const int k = a->ksz, nt = (k + 1) / 2;
     P.op = op;
@@ -562,19 +636,20 @@ int plan_fwd(const mrssm_tc_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
     // epilogue
     P.act = a->act; P.mask_mode = a->mask.ptr ? a->mask_mode : 0; P.out_f32 = a->out_f32;
     P.n_valid = a->n_out_valid;
-    const mrssm_t4& out = (op == OP_DOWN) ? a->small : a->large;
-    P.out = cvt(out); P.mask = cvt(a->mask);
+    const mrssm_tv& out = (op == OP_DOWN) ? a->small : a->large;
+    P.out = cvt(out); P.mask = cvt(a->mask); P.out32 = cvt(a->out32);
     P.bias = a->bias;
     P.prof = g_prof;
-    MRSSM_CHECK(P.out_f32 || (out.sC == 1 && out.sW % 8 == 0 && out.sH % 8 == 0 && out.sI % 8 == 0 && ((uintptr_t)out.ptr & 15) == 0),
-                "plane conv: bf16 output must be NHWC with channels padded to 8");
-    MRSSM_CHECK(!P.mask_mode || (a->mask.sC == 1 && a->mask.sW % 8 == 0 && a->mask.sH % 8 == 0 && a->mask.sI % 8 == 0),
-                "plane conv: mask must be bf16 NHWC with channels padded to 8");
+    auto vec_ok = [](const mrssm_tv& t) {
+        return t.sW % 8 == 0 && t.sH % 8 == 0 && t.sI % 8 == 0 && t.sK % 8 == 0 && t.sP % 8 == 0 && ((uintptr_t)t.ptr & 15) == 0;
+    };
+    MRSSM_CHECK(P.out_f32 ? a->out32.ptr != nullptr : vec_ok(out), "plane conv: bf16 output view must keep 8-channel chunks 16-byte aligned");
+    MRSSM_CHECK(!P.mask_mode || vec_ok(a->mask), "plane conv: mask view must keep 8-channel chunks 16-byte aligned");
     return 0;
 }
 
-int launch_fwd(const mrssm_tc_conv_args* a, int op, cudaStream_t st) {
-    MRSSM_CHECK(a && a->large.ptr && a->small.ptr && a->wpacked, "plane conv: null tensor");
+int launch_fwd(const mrssm_pl_conv_args* a, int op, cudaStream_t st) {
+    MRSSM_CHECK(a && a->wpacked, "plane conv: null weight");
     MRSSM_CHECK(a->ksz >= 2, "plane conv: kernel size %d (dense layers use mrssm_tc_conv_*)", a->ksz);
     FwdP P;
     size_t smem;
@@ -582,21 +657,11 @@ int launch_fwd(const mrssm_tc_conv_args* a, int op, cudaStream_t st) {
     CUtensorMap mA[4], mB;
     memset(mA, 0, sizeof(mA));
     if (op == OP_DOWN) {
-        const mrssm_t4& s = a->large;
-        MRSSM_CHECK(s.sC == 1, "plane down: source must be channel-contiguous");
-        for (int py = 0; py < 2; ++py)
-            for (int px = 0; px < 2; ++px) {
-                const char* base = (const char*)s.ptr + 2 * (py * s.sH + px * s.sW);
-                long long X = (a->Wl - px + 1) / 2, Y = (a->Hl - py + 1) / 2;
-                if (X < 1) X = 1;
-                if (Y < 1) Y = 1;
-                if (int rc = make_act_map(&mA[py * 2 + px], base, a->Cl, X, Y, a->n_img, 4 * s.sW, 4 * s.sH, 2 * s.sI, P.BX, P.BY, P.BI)) return rc;
-            }
+        MRSSM_CHECK(a->large.ptr, "plane down: null source");
+        if (int rc = make_view_maps(mA, &P.mergedA, a->large, a->Hl, a->Wl, a->Cl, a->n_img, true, P.BX, P.BY, P.BI)) return rc;
     } else {
-        const mrssm_t4& s = a->small;
-        MRSSM_CHECK(s.sC == 1, "plane up: source must be channel-contiguous");
-        if (int rc = make_act_map(&mA[0], s.ptr, a->Cs, a->Ws, a->Hs, a->n_img, 2 * s.sW, 2 * s.sH, 2 * s.sI, P.BX, P.BY, P.BI)) return rc;
-        mA[1] = mA[2] = mA[3] = mA[0];
+        MRSSM_CHECK(a->small.ptr, "plane up: null source");
+        if (int rc = make_view_maps(mA, &P.mergedA, a->small, a->Hs, a->Ws, a->Cs, a->n_img, false, P.BX, P.BY, P.BI)) return rc;
     }
     const long long K_total = (long long)P.nkb * 64;
     const long long N_total = (long long)P.BN * P.n_ntiles;
@@ -659,7 +724,7 @@ struct WgP {
     int nksteps;                // K steps (16 pixels) per tile
     int ksz, nt, Clp, Csp, N;
     int NG, gpp, n_cpass, n_mhalf;
-    int NA, zero_bytes;
+    int NA, zero_bytes, mergedS, mergedL;
     int cs_valid, cl_valid;
     float* dw;
     long long w_ss, w_sl;
@@ -706,12 +771,19 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
                 mbar_expect_tx(bar, (uint32_t)P.nS * (uint32_t)P.small_bytes + (uint32_t)P.nL * (uint32_t)P.large_bytes);
                 const int ig = tile / P.n_bands, band = tile - ig * P.n_bands;
                 const uint32_t dst = smem0 + (uint32_t)sa * (uint32_t)P.stage_bytes;
-                for (int q = 0; q < P.nS; ++q)
-                    tma_load_4d(dst + (uint32_t)q * (uint32_t)P.PS_s, &mS, (mhalf * 16 + q) * 8, 0, band * P.TH, ig * P.BI, bar);
+                for (int q = 0; q < P.nS; ++q) {
+                    if (P.mergedS)
+                        tma_load_4d(dst + (uint32_t)q * (uint32_t)P.PS_s, &mS, 0, band * P.TH, mhalf * 16 + q, ig * P.BI, bar);
+                    else
+                        tma_load_4d(dst + (uint32_t)q * (uint32_t)P.PS_s, &mS, (mhalf * 16 + q) * 8, 0, band * P.TH, ig * P.BI, bar);
+                }
                 for (int q = 0; q < P.nL; ++q) {
-                    const int mi = q / P.cpl, c0 = (q - mi * P.cpl) * 8;
+                    const int mi = q / P.cpl, ch = q - mi * P.cpl;
                     const CUtensorMap* m = mi == 0 ? &mL0 : (mi == 1 ? &mL1 : (mi == 2 ? &mL2 : &mL3));
-                    tma_load_4d(dst + (uint32_t)P.offL + (uint32_t)q * (uint32_t)P.PS_l, m, c0, 0, band * P.TH, ig * P.BI, bar);
+                    if (P.mergedL)
+                        tma_load_4d(dst + (uint32_t)P.offL + (uint32_t)q * (uint32_t)P.PS_l, m, 0, band * P.TH, ch, ig * P.BI, bar);
+                    else
+                        tma_load_4d(dst + (uint32_t)P.offL + (uint32_t)q * (uint32_t)P.PS_l, m, ch * 8, 0, band * P.TH, ig * P.BI, bar);
                 }
                 ++acnt;
             }
@@ -777,7 +849,7 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
     }
 }
 
-int plan_wgrad(const mrssm_tc_conv_args* a, WgP& P, size_t& smem_bytes, int& splits) {
+int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& splits) {
     memset(&P, 0, sizeof(P));
     const int k = a->ksz, nt = (k + 1) / 2;
     P.n_img = a->n_img; P.ksz = k; P.nt = nt;
@@ -843,37 +915,29 @@ int plan_wgrad(const mrssm_tc_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
     return 0;
 }
 
-int launch_wgrad(const mrssm_tc_conv_args* a, cudaStream_t st) {
+int launch_wgrad(const mrssm_pl_conv_args* a, cudaStream_t st) {
     MRSSM_CHECK(a && a->large.ptr && a->small.ptr && a->dweight, "plane wgrad: null tensor");
     MRSSM_CHECK(a->ksz >= 2, "plane wgrad: kernel size %d (dense layers use mrssm_tc_conv_wgrad)", a->ksz);
     WgP P;
     size_t smem;
     int splits;
     if (int rc = plan_wgrad(a, P, smem, splits)) return rc;
-    CUtensorMap mS, mL[4];
-    const mrssm_t4& s = a->small;
-    const mrssm_t4& l = a->large;
-    MRSSM_CHECK(s.sC == 1 && l.sC == 1, "plane wgrad: tensors must be channel-contiguous");
-    if (int rc = make_act_map(&mS, s.ptr, a->Cs, a->Ws, a->Hs, a->n_img, 2 * s.sW, 2 * s.sH, 2 * s.sI, P.BX, P.SBY, P.BI)) return rc;
-    for (int py = 0; py < 2; ++py)
-        for (int px = 0; px < 2; ++px) {
-            const char* base = (const char*)l.ptr + 2 * (py * l.sH + px * l.sW);
-            long long X = std::max(1, (a->Wl - px + 1) / 2), Y = std::max(1, (a->Hl - py + 1) / 2);
-            if (int rc = make_act_map(&mL[py * 2 + px], base, a->Cl, X, Y, a->n_img, 4 * l.sW, 4 * l.sH, 2 * l.sI, P.BX, P.BY, P.BI)) return rc;
-        }
+    CUtensorMap mS[4], mL[4];
+    if (int rc = make_view_maps(mS, &P.mergedS, a->small, a->Hs, a->Ws, a->Cs, a->n_img, false, P.BX, P.SBY, P.BI)) return rc;
+    if (int rc = make_view_maps(mL, &P.mergedL, a->large, a->Hl, a->Wl, a->Cl, a->n_img, true, P.BX, P.BY, P.BI)) return rc;
     dim3 grid((unsigned)splits, (unsigned)(P.n_cpass * P.n_mhalf));
     smem = std::max<size_t>(smem, 120 * 1024);
     MRSSM_CUDA(cudaFuncSetAttribute(plane_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    plane_wgrad_kernel<<<grid, NTHREADS, smem, st>>>(mS, mL[0], mL[1], mL[2], mL[3], P);
+    plane_wgrad_kernel<<<grid, NTHREADS, smem, st>>>(mS[0], mL[0], mL[1], mL[2], mL[3], P);
     MRSSM_LAUNCH_CHECK();
     return 0;
 }
 
 }  // namespace
 
-extern "C" int mrssm_pl_conv_down(const mrssm_tc_conv_args* a, void* stream) { return launch_fwd(a, OP_DOWN, (cudaStream_t)stream); }
-extern "C" int mrssm_pl_conv_up(const mrssm_tc_conv_args* a, void* stream) { return launch_fwd(a, OP_UP, (cudaStream_t)stream); }
-extern "C" int mrssm_pl_conv_wgrad(const mrssm_tc_conv_args* a, void* stream) { return launch_wgrad(a, (cudaStream_t)stream); }
+extern "C" int mrssm_pl_conv_down(const mrssm_pl_conv_args* a, void* stream) { return launch_fwd(a, OP_DOWN, (cudaStream_t)stream); }
+extern "C" int mrssm_pl_conv_up(const mrssm_pl_conv_args* a, void* stream) { return launch_fwd(a, OP_UP, (cudaStream_t)stream); }
+extern "C" int mrssm_pl_conv_wgrad(const mrssm_pl_conv_args* a, void* stream) { return launch_wgrad(a, (cudaStream_t)stream); }
 
 extern "C" int mrssm_pl_packed_shape(int32_t op, int32_t Cs_pad, int32_t Cl_pad, int32_t ksz, int32_t* N_total, int32_t* K_total) {
     const int nt = (ksz + 1) / 2;
@@ -905,6 +969,88 @@ extern "C" int mrssm_pl_pack_weight(const float* w, int64_t w_ss, int64_t w_sl, 
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// layout helpers: fp32 strided -> bf16 view (import), per-channel sums over a view (bias gradients)
+// ---------------------------------------------------------------------------------------------------
+namespace {
+__global__ void import_view_kernel(T4 src, int n, int H, int W, int Cc, int nchunk, float scale, TV dst) {
+    const long long total = (long long)n * H * W * nchunk;
+    const float* sp0 = (const float*)src.p;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        long long t = i / W;
+        const int y = (int)(t % H);
+        t /= H;
+        const int ch = (int)(t % nchunk), img = (int)(t / nchunk);
+        const float* sp = sp0 + img * src.sI + y * src.sH + x * src.sW;
+        uint4 pk;
+        __nv_bfloat162* ph = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = ch * 8 + 2 * e;
+            const float a = c < Cc ? sp[(long long)c * src.sC] * scale : 0.f;
+            const float b = c + 1 < Cc ? sp[(long long)(c + 1) * src.sC] * scale : 0.f;
+            ph[e] = __floats2bfloat162_rn(a, b);
+        }
+        *reinterpret_cast<uint4*>((bf16*)dst.p + tv_pix(dst, img, y, x) + ch * dst.sK) = pk;
+    }
+}
+
+__global__ void colsum_view_kernel(TV t, int n, int H, int W, int Cvalid, float* __restrict__ out) {
+    const int ch = blockIdx.y;
+    const long long total = (long long)n * H * W;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        const long long r = i / W;
+        const int y = (int)(r % H), img = (int)(r / H);
+        const uint4 pk = __ldg(reinterpret_cast<const uint4*>((const bf16*)t.p + tv_pix(t, img, y, x) + ch * t.sK));
+        const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(ph[e]);
+            acc[2 * e] += f.x;
+            acc[2 * e + 1] += f.y;
+        }
+    }
+    __shared__ float red[8][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float s = warp_sum(acc[e]);
+        if (lane == 0) red[warp][e] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float s = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
+        const int c = ch * 8 + threadIdx.x;
+        if (c < Cvalid) atomicAdd(out + c, s);
+    }
+}
+}  // namespace
+
+extern "C" int mrssm_pl_import(const mrssm_t4* src, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t Cpad, float scale,
+                               const mrssm_tv* dst, void* stream) {
+    MRSSM_CHECK(src && src->ptr && dst && dst->ptr && Cpad % 8 == 0 && Cpad >= C, "pl_import: bad args");
+    const long long total = (long long)n_img * H * W * (Cpad / 8);
+    const int blocks = (int)std::min<long long>(148 * 16, ceil_div64(total, 256));
+    import_view_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cvt(*src), n_img, H, W, C, Cpad / 8, scale, cvt(*dst));
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mrssm_pl_colsum(const mrssm_tv* x, int32_t n_img, int32_t H, int32_t W, int32_t Cpad, int32_t Cvalid, float* out, void* stream) {
+    MRSSM_CHECK(x && x->ptr && out && Cpad % 8 == 0 && Cvalid <= Cpad, "pl_colsum: bad args");
+    const int nchunk = (Cvalid + 7) / 8;
+    const long long total = (long long)n_img * H * W;
+    const int bx = (int)std::max<long long>(1, std::min<long long>(ceil_div64(total, 256 * 8), std::max(1, 1184 / nchunk)));
+    dim3 grid((unsigned)bx, (unsigned)nchunk);
+    colsum_view_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cvt(*x), n_img, H, W, Cvalid, out);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int mrssm_pl_set_debug(int32_t key, int32_t value) {
     MRSSM_CHECK(key >= 0 && key < 4, "pl_set_debug: bad key");
     g_dbg[key] = value;
@@ -917,7 +1063,7 @@ extern "C" int mrssm_pl_set_profile_buffer(void* dev_buf) {
 }
 
 // Host-only: describe the tiling plan of a layer (no GPU needed; used by the CPU tests and for tuning).
-extern "C" int mrssm_pl_describe(const mrssm_tc_conv_args* a, int32_t op, char* buf, int32_t buflen) {
+extern "C" int mrssm_pl_describe(const mrssm_pl_conv_args* a, int32_t op, char* buf, int32_t buflen) {
     MRSSM_CHECK(a && buf && buflen > 0, "pl_describe: bad args");
     if (op == 2) {
         WgP P;

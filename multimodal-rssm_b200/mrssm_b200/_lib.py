@@ -40,6 +40,19 @@ class TcConvArgs(C.Structure):
         ("w_ss", C.c_int64), ("w_sl", C.c_int64)]
 
 
+class TV(C.Structure):
+    """bf16 activation view with channels in chunks of 8 (mrssm_tv)."""
+    _fields_ = [("ptr", _vp), ("sI", C.c_int64), ("sH", C.c_int64), ("sW", C.c_int64), ("sK", C.c_int64), ("sP", C.c_int64),
+                ("par", C.c_int32), ("reserved", C.c_int32)]
+
+
+class PlConvArgs(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_img", "Hl", "Wl", "Cl", "Hs", "Ws", "Cs", "ksz", "act", "mask_mode", "out_f32",
+                                         "n_out_pad", "n_out_valid", "cs_valid", "cl_valid", "reserved")] + [
+        ("large", TV), ("small", TV), ("mask", TV), ("out32", T4), ("wpacked", _vp), ("bias", _vp), ("dweight", _vp),
+        ("w_ss", C.c_int64), ("w_sl", C.c_int64)]
+
+
 class RolloutArgs(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("T", "B", "D", "S", "H", "A", "n_experts", "act", "det")] + [
         ("min_std", C.c_float)] + [(n, _vp) for n in ("prev_state", "prev_belief", "actions", "nonterminals",
@@ -95,12 +108,14 @@ SYMBOLS = {
     "mrssm_tc_to_bf16": [C.POINTER(T4), _i32, _i32, _i32, _i32, _i32, _f, _vp, _vp],
     "mrssm_tc_from_bf16": [_vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(T4), _vp],
     "mrssm_tc_colsum": [_vp, _i64, _i32, _i32, _vp, _vp],
-    "mrssm_pl_conv_down": [C.POINTER(TcConvArgs), _vp],
-    "mrssm_pl_conv_up": [C.POINTER(TcConvArgs), _vp],
-    "mrssm_pl_conv_wgrad": [C.POINTER(TcConvArgs), _vp],
+    "mrssm_pl_conv_down": [C.POINTER(PlConvArgs), _vp],
+    "mrssm_pl_conv_up": [C.POINTER(PlConvArgs), _vp],
+    "mrssm_pl_conv_wgrad": [C.POINTER(PlConvArgs), _vp],
+    "mrssm_pl_import": [C.POINTER(T4), _i32, _i32, _i32, _i32, _i32, _f, C.POINTER(TV), _vp],
+    "mrssm_pl_colsum": [C.POINTER(TV), _i32, _i32, _i32, _i32, _i32, _vp, _vp],
     "mrssm_pl_packed_shape": [_i32, _i32, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32)],
     "mrssm_pl_pack_weight": [_vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
-    "mrssm_pl_describe": [C.POINTER(TcConvArgs), _i32, C.c_char_p, _i32],
+    "mrssm_pl_describe": [C.POINTER(PlConvArgs), _i32, C.c_char_p, _i32],
     "mrssm_pl_set_debug": [_i32, _i32],
     "mrssm_pl_set_profile_buffer": [_vp],
     "mrssm_rollout_fwd": [C.POINTER(RolloutArgs), _vp],
@@ -212,3 +227,31 @@ def nhwc(t, H, W, Cc, pix_stride=None):
 
 def nchw(t, H, W, Cc):
     return T4(ptr(t), Cc * H * W, W, 1, H * W)
+
+
+# ---- bf16 activation views (mrssm_tv) ------------------------------------------------------------------------------
+NHWC, PLANAR, PARITY = "nhwc", "planar", "parity"
+
+
+def view_numel(layout, n, H, W, Cp):
+    if layout == PARITY:
+        return n * 4 * (Cp // 8) * ((H + 1) // 2) * ((W + 1) // 2) * 8
+    return n * H * W * Cp
+
+
+def tv(p, layout, H, W, Cp):
+    """View of a dense bf16 buffer holding [n,H,W,Cp] in the given layout (p: device pointer or tensor)."""
+    if p is not None and not isinstance(p, int):
+        p = ptr(p)
+    if layout == NHWC:
+        return TV(p, H * W * Cp, W * Cp, Cp, 8, 0, 0, 0)
+    if layout == PLANAR:
+        return TV(p, (Cp // 8) * H * W * 8, W * 8, 8, H * W * 8, 0, 0, 0)
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    sK = H2 * W2 * 8
+    sP = (Cp // 8) * sK
+    return TV(p, 4 * sP, W2 * 8, 8, sK, sP, 1, 0)
+
+
+NO_TV = TV(None, 0, 0, 0, 0, 0, 0, 0)
+NO_T4 = T4(None, 0, 0, 0, 0)

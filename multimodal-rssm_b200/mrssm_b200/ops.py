@@ -742,26 +742,51 @@ def pl_pack_weight(w, op, Cs_pad, Cl_pad):
     return out
 
 
-def pl_conv_down(geom, large, small, wpacked, bias, n_out_valid, n_out_pad, act=0, mask=None, mask_mode=0, out_f32=0,
-                 valid=None):
-    a = _tc_args(geom, large, small, act, mask, mask_mode, out_f32, n_out_pad, n_out_valid, 0,
-                 wpacked=L.ptr(wpacked), bias=L.ptr(bias))
+def _pl_args(geom, large=None, small=None, mask=None, act=0, mask_mode=0, out32=None, n_out_pad=0, n_out_valid=0,
+             cs_valid=0, cl_valid=0, wpacked=None, bias=None, dweight=None, w_ss=0, w_sl=0):
+    return L.PlConvArgs(*geom, act, mask_mode, int(out32 is not None), n_out_pad, n_out_valid, cs_valid, cl_valid, 0,
+                        large or L.NO_TV, small or L.NO_TV, mask or L.NO_TV, out32 or L.NO_T4, wpacked, bias, dweight, w_ss, w_sl)
+
+
+def pl_conv_down(geom, large, out, wpacked, bias, n_out_valid, n_out_pad, act=0, mask=None, mask_mode=0, valid=None):
+    """large: L.TV view of the gathered tensor (parity-planar preferred); out: L.TV (bf16) or L.T4 (fp32, any strides)."""
+    f32 = isinstance(out, L.T4)
+    a = _pl_args(geom, large=large, small=None if f32 else out, mask=mask, act=act, mask_mode=mask_mode,
+                 out32=out if f32 else None, n_out_pad=n_out_pad, n_out_valid=n_out_valid, wpacked=L.ptr(wpacked), bias=L.ptr(bias))
     tag, work = _tc_work("mrssm_pl_conv_down", geom, valid or (geom[6], geom[3]))
     L.call("mrssm_pl_conv_down", C.byref(a), tag=tag, work=work)
 
 
-def pl_conv_up(geom, large, small, wpacked, bias, n_out_valid, n_out_pad, act=0, mask=None, mask_mode=0, out_f32=0,
-               valid=None):
-    a = _tc_args(geom, large, small, act, mask, mask_mode, out_f32, n_out_pad, n_out_valid, 0,
-                 wpacked=L.ptr(wpacked), bias=L.ptr(bias))
+def pl_conv_up(geom, out, small, wpacked, bias, n_out_valid, n_out_pad, act=0, mask=None, mask_mode=0, valid=None):
+    """small: L.TV view of the gathered tensor (planar preferred, channels padded to 16); out: L.TV or L.T4 (fp32)."""
+    f32 = isinstance(out, L.T4)
+    a = _pl_args(geom, large=None if f32 else out, small=small, mask=mask, act=act, mask_mode=mask_mode,
+                 out32=out if f32 else None, n_out_pad=n_out_pad, n_out_valid=n_out_valid, wpacked=L.ptr(wpacked), bias=L.ptr(bias))
     tag, work = _tc_work("mrssm_pl_conv_up", geom, valid or (geom[6], geom[3]))
     L.call("mrssm_pl_conv_up", C.byref(a), tag=tag, work=work)
 
 
 def pl_conv_wgrad(geom, large, small, dweight_ptr, w_ss, w_sl, cs_valid, cl_valid):
-    a = _tc_args(geom, large, small, cs_valid=cs_valid, cl_valid=cl_valid, dweight=dweight_ptr, w_ss=w_ss, w_sl=w_sl)
+    a = _pl_args(geom, large=large, small=small, cs_valid=cs_valid, cl_valid=cl_valid, dweight=dweight_ptr, w_ss=w_ss, w_sl=w_sl)
     tag, work = _tc_work("mrssm_pl_conv_wgrad", geom, (cs_valid, cl_valid))
     L.call("mrssm_pl_conv_wgrad", C.byref(a), tag=tag, work=work)
+
+
+def new_act(n, H, W, Cp, layout, device):
+    """Uninitialised bf16 activation buffer [n,H,W,Cp] in `layout` -> (flat tensor, L.TV view)."""
+    t = torch.empty(L.view_numel(layout, n, H, W, Cp), device=device, dtype=torch.bfloat16)
+    return t, L.tv(t, layout, H, W, Cp)
+
+
+def pl_import(src_t4, n, H, W, Cc, Cp, layout, device, scale=1.0):
+    """fp32 strided [n,H,W,C] -> bf16 view in `layout` with channels zero-padded to Cp."""
+    t, v = new_act(n, H, W, Cp, layout, device)
+    L.call("mrssm_pl_import", C.byref(src_t4), n, H, W, Cc, Cp, float(scale), C.byref(v))
+    return t, v
+
+
+def pl_colsum(view, n, H, W, Cp, Cvalid, out):
+    L.call("mrssm_pl_colsum", C.byref(view), n, H, W, Cp, Cvalid, L.ptr(out))
 
 
 # ---- bf16 tensor-core mode ------------------------------------------------------------------------------------
@@ -811,8 +836,9 @@ def packed_pl(w, op, Cs_pad, Cl_pad):
 
 
 class ConvEncoderTCFn(Function):
-    """ConvEncoderFn on tensor cores: NCHW fp32 image -> bf16 NHWC(8) -> plane conv stack (bf16 NHWC
-    intermediates) -> fp32 [N, C*h*w] embedding in (C,H,W) order."""
+    """ConvEncoderFn on tensor cores: NCHW fp32 image -> bf16 parity-planar (8 ch) -> plane conv stack (parity-planar
+    bf16 intermediates, each consumed with stride 2 by the next layer) -> fp32 [N, C*h*w] embedding in (C,H,W) order.
+    Backward: gradients flow in planar bf16 (they are the stride-1 operand of dgrad / wgrad)."""
 
     @staticmethod
     def forward(ctx, x, *params):
@@ -820,29 +846,28 @@ class ConvEncoderTCFn(Function):
         N, Cc, H, W = x.shape
         dev = x.device
         n_layers = len(params) // 2
-        acts = [tc_to_bf16(L.nchw(x, H, W, Cc), N, H, W, Cc, dev)]
+        acts = [pl_import(L.nchw(x, H, W, Cc), N, H, W, Cc, pad8(Cc), L.PARITY, dev)]
         geoms = []
-        Hl, Wl = H, W
+        Hl, Wl, Clp = H, W, pad8(Cc)
         y = None
         for i in range(n_layers):
             Wt, b = params[2 * i], params[2 * i + 1]
             Cs, Cl, k, _ = Wt.shape
-            Clp, Csp = acts[-1].shape[-1], pad16(Cs)
+            Csp = pad16(Cs)
             Hs, Ws = (Hl - k) // 2 + 1, (Wl - k) // 2 + 1
             geom = (N, Hl, Wl, Clp, Hs, Ws, Csp, k)
             wp = packed_pl(Wt, DOWN, Csp, Clp)
-            xin = L.nhwc(acts[-1], Hl, Wl, Clp)
             if i == n_layers - 1:
                 y = torch.empty(N, Cs * Hs * Ws, device=dev, dtype=torch.float32)
-                pl_conv_down(geom, xin, L.nchw(y, Hs, Ws, Cs), wp, b, Cs, Csp, act=RELU, out_f32=1, valid=(Cs, Cl))
+                pl_conv_down(geom, acts[-1][1], L.nchw(y, Hs, Ws, Cs), wp, b, Cs, Csp, act=RELU, valid=(Cs, Cl))
             else:
-                o = _bf16(N, Hs, Ws, Csp, device=dev)
-                pl_conv_down(geom, xin, L.nhwc(o, Hs, Ws, Csp), wp, b, Cs, Csp, act=RELU, valid=(Cs, Cl))
+                o = new_act(N, Hs, Ws, Csp, L.PARITY, dev)
+                pl_conv_down(geom, acts[-1][1], o[1], wp, b, Cs, Csp, act=RELU, valid=(Cs, Cl))
                 acts.append(o)
             geoms.append((geom, Cs, Cl))
-            Hl, Wl = Hs, Ws
+            Hl, Wl, Clp = Hs, Ws, Csp
         ctx.geoms, ctx.params = geoms, params
-        ctx.save_for_backward(y, *acts)
+        ctx.save_for_backward(y, *[t for t, _ in acts])
         return y
 
     @staticmethod
@@ -853,25 +878,25 @@ class ConvEncoderTCFn(Function):
         n_layers = len(geoms)
         (N, _, _, _, Hs, Ws, Csp, _), Cs, _ = geoms[-1]
         gm = act_bwd(g, y, RELU)
-        gb = tc_to_bf16(L.nchw(gm, Hs, Ws, Cs), N, Hs, Ws, Cs, dev, Cpad=Csp)
+        gb = pl_import(L.nchw(gm, Hs, Ws, Cs), N, Hs, Ws, Cs, Csp, L.PLANAR, dev)
         for i in reversed(range(n_layers)):
             Wt, b = params[2 * i], params[2 * i + 1]
             geom, Cs, Cl = geoms[i]
             N, Hl, Wl, Clp, Hs, Ws, Csp, k = geom
-            xi = acts[i]
-            pl_conv_wgrad(geom, L.nhwc(xi, Hl, Wl, Clp), L.nhwc(gb, Hs, Ws, Csp), L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl)
-            tc_colsum(gb, Cs, grad_buf(b))
+            xv = L.tv(acts[i], L.PARITY, Hl, Wl, Clp)
+            pl_conv_wgrad(geom, xv, gb[1], L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl)
+            pl_colsum(gb[1], N, Hs, Ws, Csp, Cs, grad_buf(b))
             if i > 0:
-                gx = _bf16(N, Hl, Wl, Clp, device=dev)
-                pl_conv_up(geom, L.nhwc(gx, Hl, Wl, Clp), L.nhwc(gb, Hs, Ws, Csp), packed_pl(Wt, UP, Csp, Clp), None, Cl, Clp,
-                           mask=L.nhwc(xi, Hl, Wl, Clp), mask_mode=RELU, valid=(Cs, Cl))
+                gx = new_act(N, Hl, Wl, Clp, L.PLANAR, dev)
+                pl_conv_up(geom, gx[1], gb[1], packed_pl(Wt, UP, Csp, Clp), None, Cl, Clp, mask=xv, mask_mode=RELU, valid=(Cs, Cl))
                 gb = gx
         return (None, *([None] * len(params)))
 
 
 class ConvDecoderTCFn(Function):
-    """ConvDecoderFn on tensor cores.  fc([h,s]) and the ConvTranspose on the 1x1 map are dense tcgen05 GEMMs, the
-    remaining layers are plane `up` kernels (all four output parities in one pass); output is fp32 NCHW."""
+    """ConvDecoderFn on tensor cores.  fc([h,s]) and the ConvTranspose on the 1x1 map are dense tcgen05 GEMMs (NHWC), the
+    remaining layers are plane `up` kernels (all four output parities in one pass) with planar bf16 activations; output
+    is fp32 NCHW.  Backward: gradients flow in parity-planar bf16 (stride-2 operand of dgrad / wgrad)."""
 
     @staticmethod
     def forward(ctx, h, s, *params):
@@ -891,42 +916,43 @@ class ConvDecoderTCFn(Function):
                      valid=(Em, D + S))
         convs = params[2:]
         n_layers = len(convs) // 2
-        acts = [y0]
+        acts = [(y0, L.NHWC)]
         geoms = []
-        Hs, Ws = 1, 1
+        Hs, Ws, Csp = 1, 1, pad16(Em)
         out = None
         for i in range(n_layers):
             Wt, b = convs[2 * i], convs[2 * i + 1]
             Cs, Cl, k, _ = Wt.shape
-            Csp = acts[-1].shape[-1]
             Hl, Wl = 2 * (Hs - 1) + k, 2 * (Ws - 1) + k
             last = i == n_layers - 1
             Clp = pad8(Cl) if last else pad16(Cl)
             geom = (R, Hl, Wl, Clp, Hs, Ws, Csp, k)
-            xin = L.nhwc(acts[-1], Hs, Ws, Csp)
+            xt, xl = acts[-1]
             if i == 0 and Hs == 1 and not last:
                 assert Clp == Cl, "dense lowering of the first ConvTranspose needs Cout % 16 == 0"
                 o = _bf16(R, Hl, Wl, Clp, device=dev)
                 wp = packed(Wt, 2, Csp, Clp)
-                tc_conv_down((R, 1, 1, Csp, 1, 1, k * k * Clp, 1), xin, L.nhwc(o, 1, 1, k * k * Clp), wp, b, k * k * Clp,
-                             act=RELU, bias_mod=Clp, valid=(k * k * Cl, Cs))
-                acts.append(o)
+                tc_conv_down((R, 1, 1, Csp, 1, 1, k * k * Clp, 1), L.nhwc(xt, 1, 1, Csp), L.nhwc(o, 1, 1, k * k * Clp), wp, b,
+                             k * k * Clp, act=RELU, bias_mod=Clp, valid=(k * k * Cl, Cs))
+                acts.append((o, L.NHWC))
             elif last:
                 out = torch.empty(R, Cl, Hl, Wl, device=dev, dtype=torch.float32)
-                pl_conv_up(geom, L.nchw(out, Hl, Wl, Cl), xin, packed_pl(Wt, UP, Csp, Clp), b, Cl, Clp, out_f32=1, valid=(Cs, Cl))
+                pl_conv_up(geom, L.nchw(out, Hl, Wl, Cl), L.tv(xt, xl, Hs, Ws, Csp), packed_pl(Wt, UP, Csp, Clp), b, Cl, Clp,
+                           valid=(Cs, Cl))
             else:
-                o = _bf16(R, Hl, Wl, Clp, device=dev)
-                pl_conv_up(geom, L.nhwc(o, Hl, Wl, Clp), xin, packed_pl(Wt, UP, Csp, Clp), b, Cl, Clp, act=RELU, valid=(Cs, Cl))
-                acts.append(o)
+                o = new_act(R, Hl, Wl, Clp, L.PLANAR, dev)
+                pl_conv_up(geom, o[1], L.tv(xt, xl, Hs, Ws, Csp), packed_pl(Wt, UP, Csp, Clp), b, Cl, Clp, act=RELU, valid=(Cs, Cl))
+                acts.append((o[0], L.PLANAR))
             geoms.append((geom, Cs, Cl))
-            Hs, Ws = Hl, Wl
+            Hs, Ws, Csp = Hl, Wl, Clp
         ctx.geoms, ctx.params, ctx.dims = geoms, params, (R, D, S, Em, Kp)
-        ctx.save_for_backward(hsb, *acts)
+        ctx.layouts = [l for _, l in acts]
+        ctx.save_for_backward(hsb, *[t for t, _ in acts])
         return out
 
     @staticmethod
     def backward(ctx, g):
-        geoms, params = ctx.geoms, ctx.params
+        geoms, params, layouts = ctx.geoms, ctx.params, ctx.layouts
         R, D, S, Em, Kp = ctx.dims
         hsb, *acts = ctx.saved_tensors
         dev = hsb.device
@@ -934,31 +960,37 @@ class ConvDecoderTCFn(Function):
         n_layers = len(geoms)
         g = _f32c(g)
         (_, Hl, Wl, Clp, _, _, _, _), _, Cl = geoms[-1]
-        gb = tc_to_bf16(L.nchw(g, Hl, Wl, Cl), R, Hl, Wl, Cl, dev, Cpad=Clp)
+        gb, gl = pl_import(L.nchw(g, Hl, Wl, Cl), R, Hl, Wl, Cl, Clp, L.PARITY, dev)[0], L.PARITY
         for i in reversed(range(n_layers)):
             Wt, b = convs[2 * i], convs[2 * i + 1]
             geom, Cs, Cl = geoms[i]
-            _, Hl, Wl, _, Hs, Ws, Csp, k = geom
-            Clg = gb.shape[-1]                       # channel padding of the gradient tensor as stored
-            gg = (R, Hl, Wl, Clg, Hs, Ws, Csp, k)
-            xi = acts[i]
-            dense = Hs == 1 and Ws == 1              # ConvTranspose on the 1x1 map: the dense kernels
-            gx = _bf16(R, Hs, Ws, Csp, device=dev)
+            _, Hl, Wl, Clg, Hs, Ws, Csp, k = geom
+            xi, xl = acts[i], layouts[i]
+            dense = Hs == 1 and Ws == 1              # ConvTranspose on the 1x1 map: the dense kernels (NHWC)
             if dense:
-                tc_conv_wgrad(gg, L.nhwc(gb, Hl, Wl, Clg), L.nhwc(xi, Hs, Ws, Csp), L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl)
-                tc_conv_down(gg, L.nhwc(gb, Hl, Wl, Clg), L.nhwc(gx, Hs, Ws, Csp), packed(Wt, 0, Csp, Clg), None, Cs,
+                assert gl == L.NHWC
+                gx = _bf16(R, Hs, Ws, Csp, device=dev)
+                tc_conv_wgrad(geom, L.nhwc(gb, Hl, Wl, Clg), L.nhwc(xi, Hs, Ws, Csp), L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl)
+                tc_conv_down(geom, L.nhwc(gb, Hl, Wl, Clg), L.nhwc(gx, Hs, Ws, Csp), packed(Wt, 0, Csp, Clg), None, Cs,
                              mask=L.nhwc(xi, Hs, Ws, Csp) if i > 0 else None, mask_mode=RELU if i > 0 else 0, valid=(Cs, Cl))
+                tc_colsum(gb.view(-1, Clg), Cl, grad_buf(b))
+                nl = L.NHWC
             else:
-                pl_conv_wgrad(gg, L.nhwc(gb, Hl, Wl, Clg), L.nhwc(xi, Hs, Ws, Csp), L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl)
-                pl_conv_down(gg, L.nhwc(gb, Hl, Wl, Clg), L.nhwc(gx, Hs, Ws, Csp), packed_pl(Wt, DOWN, Csp, Clg), None, Cs, Csp,
-                             mask=L.nhwc(xi, Hs, Ws, Csp) if i > 0 else None, mask_mode=RELU if i > 0 else 0, valid=(Cs, Cl))
-            tc_colsum(gb, Cl, grad_buf(b))
-            gb = gx
+                gv, xv = L.tv(gb, gl, Hl, Wl, Clg), L.tv(xi, xl, Hs, Ws, Csp)
+                # the gradient w.r.t. this layer's input feeds a dense layer (NHWC) when the layer below sits on the 1x1 map
+                nl = L.NHWC if (i > 0 and geoms[i - 1][0][4] == 1) or i == 0 else L.PARITY
+                gxt, gxv = new_act(R, Hs, Ws, Csp, nl, dev)
+                pl_conv_wgrad(geom, gv, xv, L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl)
+                pl_conv_down(geom, gv, gxv, packed_pl(Wt, DOWN, Csp, Clg), None, Cs, Csp,
+                             mask=xv if i > 0 else None, mask_mode=RELU if i > 0 else 0, valid=(Cs, Cl))
+                pl_colsum(gv, R, Hl, Wl, Clg, Cl, grad_buf(b))
+                gx = gxt
+            gb, gl = gx, nl
         fcw, fcb = params[0], params[1]
-        Emp = gb.shape[-1]
+        Emp = pad16(Em)
         g0 = (R, 1, 1, Kp, 1, 1, Emp, 1)
         tc_conv_wgrad(g0, L.nhwc(hsb, 1, 1, Kp), L.nhwc(gb, 1, 1, Emp), L.ptr(grad_buf(fcw)), D + S, 1, Em, D + S)
-        tc_colsum(gb, Em, grad_buf(fcb))
+        tc_colsum(gb.view(R, Emp), Em, grad_buf(fcb))
         ghs = torch.empty(R, D + S, device=dev, dtype=torch.float32)
         tc_conv_up(g0, L.nhwc(ghs, 1, 1, D + S), L.nhwc(gb, 1, 1, Emp), packed(fcw, 1, Emp, Kp), None, D + S, out_f32=1,
                    valid=(Em, D + S))

@@ -9,25 +9,27 @@ def main(op="down", n=4096, Hl=64, Cl=3, Hs=31, Cs=32, k=4, f32=0):
     dev = "cuda:0"
     g = torch.Generator(device=dev).manual_seed(0)
     Clp, Csp = ops.pad8(Cl), ops.pad16(Cs)
-    lb = torch.randn(n, Hl, Hl, Clp, device=dev, generator=g).to(torch.bfloat16)
-    sb = torch.randn(n, Hs, Hs, Csp, device=dev, generator=g).to(torch.bfloat16)
+    lbf = torch.randn(n, Hl, Hl, Clp, device=dev, generator=g)
+    lb = ops.pl_import(L.nhwc(lbf, Hl, Hl, Clp), n, Hl, Hl, Clp, Clp, L.PARITY, dev)
+    sbf = torch.randn(n, Hs, Hs, Csp, device=dev, generator=g)
+    sb = ops.pl_import(L.nhwc(sbf, Hs, Hs, Csp), n, Hs, Hs, Csp, Csp, L.PLANAR, dev)
     w = torch.randn(Cs, Cl, k, k, device=dev, generator=g) / (Cl * k * k) ** 0.5
     gp = (n, Hl, Hl, Clp, Hs, Hs, Csp, k)
     prof = torch.zeros(148 * 16 * 8, device=dev, dtype=torch.int64)
     if op == "down":
         wp = ops.pl_pack_weight(w, ops.DOWN, Csp, Clp)
         bias = torch.zeros(Cs, device=dev)
-        out = torch.zeros(n, Hs, Hs, Csp, device=dev, dtype=torch.bfloat16)
-        f = lambda: ops.pl_conv_down(gp, L.nhwc(lb, Hl, Hl, Clp), L.nhwc(out, Hs, Hs, Csp), wp, bias, Cs, Csp, act=1)
+        out = ops.new_act(n, Hs, Hs, Csp, L.PARITY, dev)
+        f = lambda: ops.pl_conv_down(gp, lb[1], out[1], wp, bias, Cs, Csp, act=1)
     else:
         wp = ops.pl_pack_weight(w, ops.UP, Csp, Clp)
         bias = torch.zeros(Cl, device=dev)
         if f32:
             out = torch.zeros(n, Cl, Hl, Hl, device=dev)
-            f = lambda: ops.pl_conv_up(gp, L.nchw(out, Hl, Hl, Cl), L.nhwc(sb, Hs, Hs, Csp), wp, bias, Cl, Clp, out_f32=1)
+            f = lambda: ops.pl_conv_up(gp, L.nchw(out, Hl, Hl, Cl), sb[1], wp, bias, Cl, Clp)
         else:
-            out = torch.zeros(n, Hl, Hl, Clp, device=dev, dtype=torch.bfloat16)
-            f = lambda: ops.pl_conv_up(gp, L.nhwc(out, Hl, Hl, Clp), L.nhwc(sb, Hs, Hs, Csp), wp, bias, Cl, Clp, act=1)
+            out = ops.new_act(n, Hl, Hl, Clp, L.PLANAR, dev)
+            f = lambda: ops.pl_conv_up(gp, out[1], sb[1], wp, bias, Cl, Clp, act=1)
     for _ in range(2):
         f()
     torch.cuda.synchronize()

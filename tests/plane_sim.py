@@ -14,8 +14,9 @@ import numpy as np
 
 def plan(L, geom, op, n_out_pad=0):
     """geom = (n, Hl, Wl, Clp, Hs, Ws, Csp, k) with PADDED channel counts; op 0 down, 1 up, 2 wgrad."""
-    a = L.TcConvArgs(*geom, 0, 0, 0, n_out_pad, n_out_pad, 0, geom[6], geom[3],
-                     L.T4(16, 0, 0, 0, 1), L.T4(16, 0, 0, 0, 1), L.T4(None, 0, 0, 0, 0), 16, None, 16, 0, 0)
+    n, Hl, Wl, Clp, Hs, Ws, Csp, k = geom
+    a = L.PlConvArgs(*geom, 0, 0, 0, n_out_pad, n_out_pad, geom[6], geom[3], 0,
+                     L.tv(16, L.PARITY, Hl, Wl, Clp), L.tv(16, L.PLANAR, Hs, Ws, Csp), L.NO_TV, L.NO_T4, 16, None, 16, 0, 0)
     buf = C.create_string_buffer(1024)
     lib = L.load()
     rc = lib.mrssm_pl_describe(C.byref(a), op, buf, 1024)

@@ -122,9 +122,26 @@ def test_tc_up_1x1_as_dense():
 # (down needs 4*Cl/8 planes of >= 128 pixels resident: Cl <= 128)
 PL_GEOMS = [g for g in GEOMS if g[5] >= 2 and g[3] > 1 and g[2] <= 128] + [(30, 6, 128, 2, 256, 4), (5, 13, 64, 5, 128, 5),
                                                                          (37, 14, 64, 6, 128, 4), (2, 14, 128, 6, 256, 4)]
+# (layout of `large`, layout of `small`): the production pairing and the all-NHWC one (element-wise TMA maps)
+PL_LAYOUTS = [("parity", "planar"), ("nhwc", "nhwc")]
 
 
-def _pl_setup(g):
+def export_view(t, layout, n, H, W, Cp):
+    """bf16 view buffer -> fp32 [n,H,W,Cp] (test-side inverse of the layouts in mrssm_b200/_lib.py)."""
+    if layout == "nhwc":
+        return t.view(n, H, W, Cp).float()
+    if layout == "planar":
+        return t.view(n, Cp // 8, H, W, 8).permute(0, 2, 3, 1, 4).reshape(n, H, W, Cp).float()
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    v = t.view(n, 2, 2, Cp // 8, H2, W2, 8)
+    full = torch.zeros(n, 2 * H2, 2 * W2, Cp, device=t.device)
+    for py in range(2):
+        for px in range(2):
+            full[:, py::2, px::2, :] = v[:, py, px].permute(0, 2, 3, 1, 4).reshape(n, H2, W2, Cp).float()
+    return full[:, :H, :W, :]
+
+
+def _pl_setup(g, ll, sl):
     from mrssm_b200 import _lib as L, ops
     n, Hl, Cl, Hs, Cs, k = g
     gen = torch.Generator(device=DEV).manual_seed(hash(g) % 1000)
@@ -132,14 +149,23 @@ def _pl_setup(g):
     small = _bf16_round(torch.randn(n, Hs, Hs, Cs, device=DEV, generator=gen))
     w = _bf16_round(torch.randn(Cs, Cl, k, k, device=DEV, generator=gen) / (Cl * k * k) ** 0.5)
     Clp, Csp = ops.pad8(Cl), ops.pad16(Cs)
-    lb = ops.tc_to_bf16(L.nhwc(large, Hl, Hl, Cl), n, Hl, Hl, Cl, DEV, Cpad=Clp)
-    sb = ops.tc_to_bf16(L.nhwc(small, Hs, Hs, Cs), n, Hs, Hs, Cs, DEV, Cpad=Csp)
+    lb = ops.pl_import(L.nhwc(large, Hl, Hl, Cl), n, Hl, Hl, Cl, Clp, ll, DEV)
+    sb = ops.pl_import(L.nhwc(small, Hs, Hs, Cs), n, Hs, Hs, Cs, Csp, sl, DEV)
+    torch.testing.assert_close(export_view(lb[0], ll, n, Hl, Hl, Clp)[..., :Cl], large)      # import/export round trip
+    torch.testing.assert_close(export_view(sb[0], sl, n, Hs, Hs, Csp)[..., :Cs], small)
     return L, ops, (n, Hl, Hl, Cl, Hs, Hs, Cs, k), (n, Hl, Hl, Clp, Hs, Hs, Csp, k), (large, small, w), (lb, sb)
 
 
+def _filled(ops, L, n, H, W, Cp, layout):
+    t, v = ops.new_act(n, H, W, Cp, layout, DEV)
+    t.fill_(7.0)
+    return t, v
+
+
+@pytest.mark.parametrize("ll,sl", PL_LAYOUTS)
 @pytest.mark.parametrize("g", PL_GEOMS)
-def test_plane_down_matches_simt(g):
-    L, ops, geom, gp, (large, small, w), (lb, sb) = _pl_setup(g)
+def test_plane_down_matches_simt(g, ll, sl):
+    L, ops, geom, gp, (large, small, w), (lb, sb) = _pl_setup(g, ll, sl)
     n, Hl, _, Cl, Hs, _, Cs, k = geom
     Clp, Csp = gp[3], gp[6]
     bias = torch.randn(Cs, device=DEV)
@@ -147,50 +173,58 @@ def test_plane_down_matches_simt(g):
     ops._conv("mrssm_conv_down", geom, L.nhwc(large, Hl, Hl, Cl), L.nhwc(ref, Hs, Hs, Cs), L.ptr(w), Cl * k * k, k * k,
               L.ptr(bias), ops.RELU)
     wp = ops.pl_pack_weight(w, ops.DOWN, Csp, Clp)
-    out = torch.full((n, Hs, Hs, Csp), 7.0, device=DEV, dtype=torch.bfloat16)
-    ops.pl_conv_down(gp, L.nhwc(lb, Hl, Hl, Clp), L.nhwc(out, Hs, Hs, Csp), wp, bias, Cs, Csp, act=ops.RELU)
-    torch.testing.assert_close(out[..., :Cs].float(), ref, rtol=1e-2, atol=1e-2)
-    assert float(out[..., Cs:].float().abs().max() if Csp > Cs else 0.0) == 0.0
+    for ol in ("parity", "planar", "nhwc"):          # every output layout the epilogue can address
+        out = _filled(ops, L, n, Hs, Hs, Csp, ol)
+        ops.pl_conv_down(gp, lb[1], out[1], wp, bias, Cs, Csp, act=ops.RELU)
+        o = export_view(out[0], ol, n, Hs, Hs, Csp)
+        torch.testing.assert_close(o[..., :Cs], ref, rtol=1e-2, atol=1e-2)
+        assert float(o[..., Cs:].abs().max() if Csp > Cs else 0.0) == 0.0
     out32 = torch.empty(n, Cs, Hs, Hs, device=DEV)
-    ops.pl_conv_down(gp, L.nhwc(lb, Hl, Hl, Clp), L.nchw(out32, Hs, Hs, Cs), wp, bias, Cs, Csp, act=ops.RELU, out_f32=1)
+    ops.pl_conv_down(gp, lb[1], L.nchw(out32, Hs, Hs, Cs), wp, bias, Cs, Csp, act=ops.RELU)
     torch.testing.assert_close(out32.permute(0, 2, 3, 1), ref, rtol=2e-3, atol=2e-3)
 
 
+@pytest.mark.parametrize("ll,sl", PL_LAYOUTS)
 @pytest.mark.parametrize("g", PL_GEOMS)
-def test_plane_up_and_dgrad_match_simt(g):
-    L, ops, geom, gp, (large, small, w), (lb, sb) = _pl_setup(g)
+def test_plane_up_and_dgrad_match_simt(g, ll, sl):
+    L, ops, geom, gp, (large, small, w), (lb, sb) = _pl_setup(g, ll, sl)
     n, Hl, _, Cl, Hs, _, Cs, k = geom
     Clp, Csp = gp[3], gp[6]
     wp = ops.pl_pack_weight(w, ops.UP, Csp, Clp)
-    if Hl == 2 * (Hs - 1) + k:      # ConvTranspose2d forward (+bias, ReLU), bf16 NHWC and fp32 NCHW outputs
+    if Hl == 2 * (Hs - 1) + k:      # ConvTranspose2d forward (+bias, ReLU), bf16 and fp32 NCHW outputs
         bias = torch.randn(Cl, device=DEV)
         ref = torch.empty_like(large)
         ops._conv("mrssm_conv_up", geom, L.nhwc(ref, Hl, Hl, Cl), L.nhwc(small, Hs, Hs, Cs), L.ptr(w), Cl * k * k, k * k,
                   L.ptr(bias), ops.RELU)
-        out = torch.full((n, Hl, Hl, Clp), 7.0, device=DEV, dtype=torch.bfloat16)
-        ops.pl_conv_up(gp, L.nhwc(out, Hl, Hl, Clp), L.nhwc(sb, Hs, Hs, Csp), wp, bias, Cl, Clp, act=ops.RELU)
-        torch.testing.assert_close(out[..., :Cl].float(), ref, rtol=1e-2, atol=1e-2)
+        for ol in ("planar", "parity", "nhwc"):
+            out = _filled(ops, L, n, Hl, Hl, Clp, ol)
+            ops.pl_conv_up(gp, out[1], sb[1], wp, bias, Cl, Clp, act=ops.RELU)
+            torch.testing.assert_close(export_view(out[0], ol, n, Hl, Hl, Clp)[..., :Cl], ref, rtol=1e-2, atol=1e-2)
         out32 = torch.empty(n, Cl, Hl, Hl, device=DEV)
-        ops.pl_conv_up(gp, L.nchw(out32, Hl, Hl, Cl), L.nhwc(sb, Hs, Hs, Csp), wp, bias, Cl, Clp, act=ops.RELU, out_f32=1)
+        ops.pl_conv_up(gp, L.nchw(out32, Hl, Hl, Cl), sb[1], wp, bias, Cl, Clp, act=ops.RELU)
         torch.testing.assert_close(out32.permute(0, 2, 3, 1), ref, rtol=2e-3, atol=2e-3)
-    # Conv2d dgrad with the ReLU mask of the layer input (floor geometries included)
+    # Conv2d dgrad with the ReLU mask of the layer input (floor geometries included); mask in the layout of `large`
     ref = torch.empty_like(large)
     ops._conv("mrssm_conv_up", geom, L.nhwc(ref, Hl, Hl, Cl), L.nhwc(small, Hs, Hs, Cs), L.ptr(w), Cl * k * k, k * k,
               None, 0, L.ptr(large), ops.RELU)
-    out = torch.full((n, Hl, Hl, Clp), 7.0, device=DEV, dtype=torch.bfloat16)
-    ops.pl_conv_up(gp, L.nhwc(out, Hl, Hl, Clp), L.nhwc(sb, Hs, Hs, Csp), wp, None, Cl, Clp,
-                   mask=L.nhwc(lb, Hl, Hl, Clp), mask_mode=ops.RELU)
-    torch.testing.assert_close(out[..., :Cl].float(), ref, rtol=1e-2, atol=1e-2)
+    out = _filled(ops, L, n, Hl, Hl, Clp, "planar")
+    ops.pl_conv_up(gp, out[1], sb[1], wp, None, Cl, Clp, mask=lb[1], mask_mode=ops.RELU)
+    torch.testing.assert_close(export_view(out[0], "planar", n, Hl, Hl, Clp)[..., :Cl], ref, rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize("ll,sl", PL_LAYOUTS)
 @pytest.mark.parametrize("g", PL_GEOMS)
-def test_plane_wgrad_matches_simt(g):
-    L, ops, geom, gp, (large, small, w), (lb, sb) = _pl_setup(g)
+def test_plane_wgrad_and_colsum_match_simt(g, ll, sl):
+    L, ops, geom, gp, (large, small, w), (lb, sb) = _pl_setup(g, ll, sl)
     n, Hl, _, Cl, Hs, _, Cs, k = geom
     Clp, Csp = gp[3], gp[6]
     ref = torch.zeros_like(w)
     ops._conv("mrssm_conv_wgrad", geom, L.nhwc(large, Hl, Hl, Cl), L.nhwc(small, Hs, Hs, Cs), L.ptr(ref), Cl * k * k, k * k)
     out = torch.zeros_like(w)
-    ops.pl_conv_wgrad(gp, L.nhwc(lb, Hl, Hl, Clp), L.nhwc(sb, Hs, Hs, Csp), L.ptr(out), Cl * k * k, k * k, Cs, Cl)
+    ops.pl_conv_wgrad(gp, lb[1], sb[1], L.ptr(out), Cl * k * k, k * k, Cs, Cl)
     scale = float(ref.abs().max())
     assert float((out - ref).abs().max()) <= 2e-3 * scale + 1e-4
+    for (t, v, H, Cp, Cv, x) in ((lb[0], lb[1], Hl, Clp, Cl, large), (sb[0], sb[1], Hs, Csp, Cs, small)):
+        acc = torch.zeros(Cv, device=DEV)
+        ops.pl_colsum(v, n, H, H, Cp, Cv, acc)
+        torch.testing.assert_close(acc, x.sum(dim=(0, 1, 2)), rtol=1e-3, atol=1e-2)
