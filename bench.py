@@ -100,14 +100,14 @@ def workload_config(args, world):
 # ---------------------------------------------------------------------------------------------------
 class SyntheticReplay:
     """D.sample contract of the reference (utils/replay_buffer/memory.py:212-222): time-major fp32
-    [obs dict, actions, rewards, nonterminals] on `device`.  `resident=True` hands out tensors that
-    already live in HBM; otherwise every sample() is an H2D copy from pinned host memory."""
+    [obs dict, actions, rewards, nonterminals] on `device`, handing out tensors that already live in HBM
+    (the `value` measurement; the e2e measurement uses mrssm_b200.data.PinnedChunkSource)."""
 
     def __init__(self, cfg, device, seed, n_buffers=2):
         B, T = cfg.train.batch_size, cfg.train.chunk_size
         g = torch.Generator(device=device).manual_seed(seed)
-        self.device, self.resident, self.i = device, True, 0
-        self.dev, self.host = [], []
+        self.device, self.i = device, 0
+        self.dev = []
         for _ in range(n_buffers):
             obs = {}
             for name in cfg.rssm.observation_names_enc:
@@ -126,24 +126,35 @@ class SyntheticReplay:
             tpos = torch.randint(0, T, (B,), generator=g, device=device)
             nonterm[tpos[drop], torch.nonzero(drop).flatten(), 0] = 0
             self.dev.append((obs, actions, rewards, nonterm))
-        self.h2d_bytes = 0
-
-    def make_host_copies(self):
-        for obs, a, r, n in self.dev:
-            pin = lambda t: t.cpu().pin_memory()
-            self.host.append(({k: pin(v) for k, v in obs.items()}, pin(a), pin(r), pin(n)))
-        obs, a, r, n = self.host[0]
-        self.h2d_bytes = sum(v.numel() * 4 for v in obs.values()) + 4 * (a.numel() + r.numel() + n.numel())
 
     def sample(self, n, L):
         self.i += 1
-        if self.resident:
-            obs, a, r, nt = self.dev[self.i % len(self.dev)]
-            return [obs, a, r, nt]
-        obs, a, r, nt = self.host[self.i % len(self.host)]
-        d = self.device
-        return [{k: v.to(d, non_blocking=True) for k, v in obs.items()}, a.to(d, non_blocking=True),
-                r.to(d, non_blocking=True), nt.to(d, non_blocking=True)]
+        obs, a, r, nt = self.dev[self.i % len(self.dev)]
+        return [obs, a, r, nt]
+
+
+def host_chunks(cfg, seed, n_chunks=2):
+    """Pre-gathered replay chunks as the reference keeps them on the HOST (utils/replay_buffer/memory.py:160-168):
+    uint8 frames, fp32 vectors / actions / rewards / nonterminals, time-major."""
+    B, T = cfg.train.batch_size, cfg.train.chunk_size
+    g = torch.Generator().manual_seed(seed)
+    chunks = []
+    for _ in range(n_chunks):
+        obs = {}
+        for name in cfg.rssm.observation_names_enc:
+            shp = cfg.env.observation_shapes[name]
+            if "image" in name:
+                obs[name] = torch.randint(0, 256, (T, B, *shp), generator=g, dtype=torch.uint8)
+            else:
+                obs[name] = torch.randn((T, B, *shp), generator=g)
+        actions = torch.randn((T, B, cfg.env.action_size), generator=g)
+        rewards = torch.zeros((T, B))
+        nonterm = torch.ones((T, B, 1))
+        drop = torch.rand(B, generator=g) < 0.1
+        tpos = torch.randint(0, T, (B,), generator=g)
+        nonterm[tpos[drop], torch.nonzero(drop).flatten(), 0] = 0
+        chunks.append((obs, actions, rewards, nonterm))
+    return chunks
 
 
 class ClockSampler:
@@ -278,13 +289,16 @@ def run_ours(args):
     ms_step = ms / args.steps
     value = world * args.batch * args.chunk / (ms_step * 1e-3)
 
-    # end to end: pinned host buffers -> H2D -> step -> D2H of the loss, every step
-    D.make_host_copies()
-    D.resident = False
-    model.optimize(D)
-    ms_e2e, loss = timed_steps(model, D, args.steps, sync_loss=True)
+    # end to end through the public API: model.optimize(D) with D = the pinned-host chunk source.  Every step copies that
+    # step's chunk host -> device (uint8 frames + fp32 vectors, as the reference's replay buffer stores them), normalises
+    # the frames on the device, runs the step, and reads the loss back; the copy of step k+1 overlaps step k.
+    from mrssm_b200.data import PinnedChunkSource
+    Dh = PinnedChunkSource(host_chunks(cfg, seed=4321 + rank), device, bit_depth=5, seed=rank)
+    model.optimize(Dh)
+    ms_e2e, loss = timed_steps(model, Dh, args.steps, sync_loss=True)
     e2e_value = world * args.batch * args.chunk / (ms_e2e / args.steps * 1e-3)
-    D.resident = True
+    h2d_bytes = Dh.h2d_bytes
+    del Dh
 
     if rank != 0:
         return
@@ -310,8 +324,9 @@ def run_ours(args):
         "config": workload_config(args, world),
         "model_steps_per_s": world * args.batch * (args.chunk - 1) / (ms_step * 1e-3),
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": D.h2d_bytes, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps, "last_loss": loss},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps, "last_loss": loss,
+                "input": "uint8 frames + fp32 vectors from pinned host memory, normalised on device, copy of step k+1 overlapped with step k"},
         "gpu_launches": launches,
         "roofline": roof, "rollout_roofline": rollout_roof, "cpu_baseline": cpu,
         "top_kernels_ms": [{"kernel": k, "ms_per_step": round(m, 4), "launches": n} for k, m, n in top],

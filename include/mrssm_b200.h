@@ -277,6 +277,13 @@ int mrssm_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, int
                     float beta1, float beta2, float eps, float max_norm, float grad_scale,
                     float* partial, float* norm_out, void* stream);
 
+/* ---- input pipeline: replay-buffer frames are uint8 on the host (utils/replay_buffer/memory.py:160-168); sample()
+ * moves them to the device and normalises there (memory.py:197-208 -> utils/processing/image_processing.py:5-11):
+ *   dst = floor(u8 / 2^(8-bits)) / 2^bits - 0.5 + u / 2^bits,  u ~ U[0,1).
+ * `noise` supplies u (parity tests); NULL draws it from a counter-based hash of (seed, element index). */
+int mrssm_normalize_image_u8(const uint8_t* src, int64_t n, int32_t bit_depth, const float* noise, uint64_t seed,
+                             float* dst, void* stream);
+
 /* ---- small helpers ---- */
 int mrssm_transpose(const float* src, int64_t rows, int64_t cols, int64_t src_ld, float* dst, void* stream);
 int mrssm_concat2(const float* a, int64_t ca, const float* b, int64_t cb, int64_t rows, float* out, void* stream);

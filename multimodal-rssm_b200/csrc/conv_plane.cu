@@ -213,7 +213,8 @@ struct FwdP {
 };
 #define PROF(slot) do { if (P.prof && lit < 16) P.prof[((long long)blockIdx.x * 16 + lit) * 8 + (slot)] = clock64(); } while (0)
 
-constexpr int FWD_THREADS = 384;      // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue (two per TMEM lane quarter)
+constexpr int FWD_THREADS = 640;      // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..19 epilogue (four per TMEM lane quarter)
+constexpr int EPI_WARPS = 16;
 
 __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                                uint32_t accumulate) {
@@ -314,7 +315,7 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
             tc::mbar_init(tc::smem_u32(&a_full[s]), 1);
             tc::mbar_init(tc::smem_u32(&a_empty[s]), 1);
             tc::mbar_init(tc::smem_u32(&acc_full[s]), 1);
-            tc::mbar_init(tc::smem_u32(&acc_empty[s]), 8);
+            tc::mbar_init(tc::smem_u32(&acc_empty[s]), EPI_WARPS);
         }
         for (int s = 0; s < 80; ++s) tc::mbar_init(tc::smem_u32(&b_full[s]), 1);
         for (int s = 0; s < 8; ++s) tc::mbar_init(tc::smem_u32(&b_empty[s]), 1);
@@ -444,11 +445,13 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         __syncwarp();
     } else if (warp >= 4) {
         // ------------------------------ epilogue ------------------------------
+        // Four warps share each TMEM lane quarter.  A pass is cut into items (128-row block, column part); the
+        // warps of a quarter take items round-robin.
         const int e = warp - 4, q = e & 3, part = e >> 2;
-        const bool split_cols = (P.BN % 32) == 0;                // both warps of a lane quarter share every block, half the columns each
-        const int ncols = split_cols ? P.BN / 2 : P.BN;
-        const int col0 = split_cols ? part * ncols : 0;
+        const int ncp = (P.BN % 64 == 0) ? 4 : ((P.BN % 32 == 0) ? 2 : 1);      // column parts per block
+        const int ncols = P.BN / ncp;
         const int IP = P.BY * P.BX;
+        const float inv_IP = 1.f / (float)IP, inv_BX = 1.f / (float)P.BX;
         uint32_t ccnt = 0;
         int lit = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lit) {
@@ -460,10 +463,13 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                 tc::tc_fence_after();
                 if (it == 0 && tid == 128) PROF(4);
                 const int mb0 = pass * P.MBs, nmb = min(P.MBs, P.MB_total - mb0);
-                const int n0 = nti * P.BN + col0;
-                for (int mb = split_cols ? 0 : part; mb < nmb; mb += split_cols ? 1 : 2) {
+                for (int item = part; item < nmb * ncp; item += EPI_WARPS / 4) {
+                    const int mb = item / ncp, col0 = (item - mb * ncp) * ncols;
+                    const int n0 = nti * P.BN + col0;
                     const int p = (mb0 + mb) * 128 + q * 32 + lane;
-                    const int i = p / IP, r = p - i * IP, yr = r / P.BX, x = r - yr * P.BX;
+                    // p < 2^16: (p + 0.5) / d is at least 0.5/d away from an integer, so the float quotient truncates exactly
+                    const int i = __float2int_rz(((float)p + 0.5f) * inv_IP), r = p - i * IP;
+                    const int yr = __float2int_rz(((float)r + 0.5f) * inv_BX), x = r - yr * P.BX;
                     const int img = ig * P.BI + i, y = band * P.TH + yr;
                     const bool row_ok = i < P.BI && img < P.n_img && yr < P.TH && y < P.Hv && x < P.Wv;
                     int cls = 0, cl0 = n0;
@@ -909,7 +915,7 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
     smem_bytes = (size_t)P.zero_bytes + 1024;
     const int n_tiles = P.n_groups * P.n_bands;
     const int ypass = P.n_cpass * P.n_mhalf;
-    splits = std::max(1, std::min(n_tiles, (148 + ypass - 1) / ypass));
+    splits = std::max(1, std::min(n_tiles, 148 / ypass));      // the whole grid is one wave (one CTA per SM)
     P.cs_valid = a->cs_valid; P.cl_valid = a->cl_valid;
     P.dw = a->dweight; P.w_ss = a->w_ss; P.w_sl = a->w_sl;
     return 0;

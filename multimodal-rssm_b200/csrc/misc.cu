@@ -215,3 +215,49 @@ extern "C" int mrssm_act_bwd(const float* g, const float* y, int64_t n, int32_t 
     MRSSM_LAUNCH_CHECK();
     return 0;
 }
+
+// ---- input pipeline: uint8 frames -> normalised fp32 (utils/processing/image_processing.py:5-11) ------------------
+// dst = floor(u8 / 2^(8-bits)) / 2^bits - 0.5 + u / 2^bits,  u ~ U[0,1): from `noise` when given (parity tests),
+// otherwise a counter-based hash of (seed, element index) (the reference draws torch.rand_like on the device).
+namespace {
+__device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t i) {
+    uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;           // splitmix64
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);      // 24 random bits -> [0,1)
+}
+__global__ void normalize_u8_kernel(const uint8_t* __restrict__ src, long long n, int bits, const float* __restrict__ noise,
+                                    uint64_t seed, float* __restrict__ dst) {
+    const float q = 1.f / (float)(1 << (8 - bits)), s = 1.f / (float)(1 << bits);
+    const long long n4 = n >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const uchar4 u = reinterpret_cast<const uchar4*>(src)[i];
+        float4 r;
+        const float4 nz = noise ? reinterpret_cast<const float4*>(noise)[i]
+                                : make_float4(hash_uniform(seed, 4 * i), hash_uniform(seed, 4 * i + 1), hash_uniform(seed, 4 * i + 2),
+                                              hash_uniform(seed, 4 * i + 3));
+        r.x = floorf(u.x * q) * s - 0.5f + nz.x * s;
+        r.y = floorf(u.y * q) * s - 0.5f + nz.y * s;
+        r.z = floorf(u.z * q) * s - 0.5f + nz.z * s;
+        r.w = floorf(u.w * q) * s - 0.5f + nz.w * s;
+        reinterpret_cast<float4*>(dst)[i] = r;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const long long i = (n4 << 2) + threadIdx.x;
+        const float nz = noise ? noise[i] : hash_uniform(seed, i);
+        dst[i] = floorf(src[i] * q) * s - 0.5f + nz * s;
+    }
+}
+}  // namespace
+
+extern "C" int mrssm_normalize_image_u8(const uint8_t* src, int64_t n, int32_t bit_depth, const float* noise, uint64_t seed,
+                                        float* dst, void* stream) {
+    MRSSM_CHECK(src && dst && n > 0 && bit_depth >= 1 && bit_depth <= 8, "normalize_image_u8: bad args");
+    MRSSM_CHECK(((uintptr_t)src & 3) == 0 && ((uintptr_t)dst & 15) == 0 && (!noise || ((uintptr_t)noise & 15) == 0),
+                "normalize_image_u8: buffers must be 16-byte aligned");
+    const int blocks = (int)std::min<long long>(148 * 16, std::max<long long>(1, ceil_div64(n / 4, 256)));
+    normalize_u8_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, n, bit_depth, noise, seed, dst);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}

@@ -126,6 +126,7 @@ SYMBOLS = {
     "mrssm_mse_bwd": [_vp, _vp, _i64, _i64, _vp, _vp, _vp],
     "mrssm_sqdiff": [_vp, _vp, _i64, _vp, _vp],
     "mrssm_clip_adam": [_vp, _vp, _vp, _vp, _i64, _i32, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp],
+    "mrssm_normalize_image_u8": [_vp, _i64, _i32, _vp, C.c_uint64, _vp, _vp],
     "mrssm_transpose": [_vp, _i64, _i64, _i64, _vp, _vp],
     "mrssm_concat2": [_vp, _i64, _vp, _i64, _i64, _vp, _vp],
     "mrssm_colsum_acc": [_vp, _i64, _i64, _i64, _vp, _vp],
@@ -212,6 +213,12 @@ def ptr(t):
     if t is None:
         return None
     assert t.is_cuda, "mrssm_b200 ops take CUDA tensors only"
+    return t.data_ptr()
+
+
+def ptr_any(t):
+    """Device pointer of a CUDA tensor of any dtype."""
+    assert t.is_cuda
     return t.data_ptr()
 
 

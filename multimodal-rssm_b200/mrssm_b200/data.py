@@ -1,0 +1,72 @@
+"""Host -> device input pipeline for the train step (the part the hot path needs).
+
+Mirrors what ``ExperienceReplay_Multimodal.sample`` hands to ``optimize`` (utils/replay_buffer/memory.py:191-222):
+frames live on the HOST as uint8 (memory.py:160-168); ``sample`` moves the gathered chunk to the device as uint8 and
+converts / normalises there (memory.py:197-208, image_processing.py:5-11), returning time-major fp32
+``[obs dict, actions, rewards, nonterminals]``.  Here the host buffers are pinned, the copy of batch k+1 runs on a side
+stream while step k computes, and the normalisation is one kernel (``mrssm_normalize_image_u8``).  Index sampling and
+augmentation of the replay buffer are out of scope: the source is handed ready-made chunks.
+"""
+import torch
+
+from . import _lib as L
+
+
+class PinnedChunkSource:
+    """D.sample(n, L) over a ring of pre-gathered host chunks.
+
+    chunks: list of (obs dict name -> tensor [T,B,...] (uint8 for images, fp32 otherwise), actions [T,B,A],
+    rewards [T,B], nonterminals [T,B,1]) on the CPU; they are pinned here."""
+
+    def __init__(self, chunks, device, bit_depth=5, seed=0, prefetch=True):
+        self.device = torch.device(device)
+        self.bit_depth, self.seed, self.prefetch = bit_depth, seed, prefetch
+        pin = lambda t: t.contiguous().pin_memory()
+        self.host = [({k: pin(v) for k, v in obs.items()}, pin(a), pin(r), pin(n)) for obs, a, r, n in chunks]
+        obs, a, r, n = self.host[0]
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in obs.values()) + 4 * (a.numel() + r.numel() + n.numel())
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.slots = [None, None]          # device staging, double buffered
+        self.i = 0
+        self.pending = None                # (slot index, ready event) of the batch in flight
+
+    def _slot(self, k):
+        if self.slots[k] is None:
+            obs, a, r, n = self.host[0]
+            dev = self.device
+            raw = {name: torch.empty_like(v, device=dev) for name, v in obs.items()}
+            f32 = {name: (torch.empty(v.shape, device=dev, dtype=torch.float32) if v.dtype == torch.uint8 else raw[name])
+                   for name, v in obs.items()}
+            self.slots[k] = (raw, f32, torch.empty_like(a, device=dev), torch.empty_like(r, device=dev),
+                             torch.empty_like(n, device=dev))
+        return self.slots[k]
+
+    def _launch(self, k, chunk_index):
+        """Enqueue H2D + normalisation of one chunk into slot k on the copy stream."""
+        obs, a, r, n = self.host[chunk_index % len(self.host)]
+        raw, f32, da, dr, dn = self._slot(k)
+        main = torch.cuda.current_stream(self.device)
+        self.copy_stream.wait_stream(main)                 # the slot's previous consumer has been enqueued before us
+        with torch.cuda.stream(self.copy_stream):
+            for name, v in obs.items():
+                raw[name].copy_(v, non_blocking=True)
+                if v.dtype == torch.uint8:
+                    L.call("mrssm_normalize_image_u8", L.ptr_any(raw[name]), v.numel(), self.bit_depth, None,
+                           self.seed + chunk_index, L.ptr(f32[name]))
+            da.copy_(a, non_blocking=True)
+            dr.copy_(r, non_blocking=True)
+            dn.copy_(n, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return ev
+
+    def sample(self, n, L_):
+        k = self.i & 1
+        if self.pending is None or self.pending[0] != k:
+            self.pending = (k, self._launch(k, self.i))
+        _, ev = self.pending
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        raw, f32, da, dr, dn = self.slots[k]
+        self.i += 1
+        self.pending = (k ^ 1, self._launch(k ^ 1, self.i)) if self.prefetch else None
+        return [dict(f32), da, dr, dn]

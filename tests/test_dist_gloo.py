@@ -1,0 +1,94 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the data-parallel exchange step (mrssm_b200/dist.py) —
+rank-0 parameter broadcast, SUM all-reduce of the flat gradient buffer, 1/world folded into the optimiser scale.
+With equal per-rank batches the averaged rank gradients equal the global-batch gradient; that identity
+is checked here on the oracle's loss with the batch split across the two ranks."""
+import os
+import socket
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _Opt:
+    def __init__(self, n, rank):
+        g = torch.Generator().manual_seed(100 + rank)
+        self.flat_p = torch.randn(n, generator=g)
+        self.flat_g = torch.randn(n, generator=g)
+        self.grad_scale = 1.0
+
+
+class _Model:
+    def __init__(self, opt):
+        self.model_optimizer = opt
+        self.dp = None
+
+
+def _worker(rank, world, port, q):
+    for p in (ROOT, os.path.join(ROOT, "multimodal-rssm_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from mrssm_b200.dist import DataParallel, init_from_env
+    r, l, w = init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    opt = _Opt(1000, rank)
+    g_local = opt.flat_g.clone()
+    model = _Model(opt)
+    dp = DataParallel(model)
+    assert model.dp is dp and opt.grad_scale == 1.0 / world
+    p_after = opt.flat_p.clone()
+    dp.all_reduce_grads(opt)
+    q.put((rank, p_after, g_local, opt.flat_g.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_broadcast_and_sum_allreduce_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, p0, g0, s0), (_, p1, g1, s1) = out
+    torch.testing.assert_close(p0, p1)                       # rank-0 weights everywhere
+    torch.testing.assert_close(s0, g0 + g1)                  # SUM all-reduce
+    torch.testing.assert_close(s0, s1)
+
+
+def test_mean_of_rank_gradients_is_global_batch_gradient():
+    """The identity the DP design rests on, on the oracle: loss means over (t,b) with per-(t,b) clamps."""
+    for p in (ROOT, os.path.join(ROOT, "multimodal-rssm_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from oracle import mrssm_oracle as O
+    oc = O.OracleConfig(fusion="MoPoE")
+    P = O.make_params(oc, seed=0)
+    batch, noise = O.synthetic_batch(oc, 4, 5, seed=7)
+
+    def grads(sl):
+        b = {"obs": {n: t[:, sl] for n, t in batch["obs"].items()}, "actions": batch["actions"][:, sl],
+             "rewards": batch["rewards"][:, sl], "nonterminals": batch["nonterminals"][:, sl]}
+        nz = {k: v[:, sl] for k, v in noise.items()}
+        return O.train_step({k: v.clone() for k, v in P.items()}, {}, oc, b, nz)["grads"]
+
+    g_all, g_a, g_b = grads(slice(0, 4)), grads(slice(0, 2)), grads(slice(2, 4))
+    for k in g_all:
+        scale = float(g_all[k].abs().max()) + 1e-12
+        assert float((0.5 * (g_a[k] + g_b[k]) - g_all[k]).abs().max()) <= 1e-4 * scale + 1e-7, k

@@ -59,3 +59,47 @@ def test_bf16_tensor_core_mode_within_stated_tolerance(fusion):
     assert rep["loss_rel"] < 2e-2, rep
     assert rep["gnorm_rel"] < 3e-2, rep
     assert rep["grad_rel_fro"] < 5e-2, rep
+
+
+def test_normalize_image_u8_matches_reference_formula():
+    """mrssm_normalize_image_u8 against image_processing.py:5-11 restated in torch, with the noise supplied."""
+    from mrssm_b200 import _lib as L
+    g = torch.Generator(device=DEV).manual_seed(3)
+    u8 = torch.randint(0, 256, (5, 3, 64, 64), generator=g, device=DEV, dtype=torch.uint8)
+    noise = torch.rand(u8.shape, generator=g, device=DEV)
+    out = torch.empty(u8.shape, device=DEV)
+    for bits in (5, 8):
+        L.call("mrssm_normalize_image_u8", L.ptr_any(u8), u8.numel(), bits, L.ptr(noise), 0, L.ptr(out))
+        ref = u8.float().div(2 ** (8 - bits)).floor().div(2 ** bits).sub(0.5).add(noise.div(2 ** bits))
+        torch.testing.assert_close(out, ref, rtol=0, atol=1e-7)
+    # hashed noise: values stay inside the dequantisation bin and are not constant
+    L.call("mrssm_normalize_image_u8", L.ptr_any(u8), u8.numel(), 5, None, 123, L.ptr(out))
+    lo = u8.float().div(8).floor().div(32).sub(0.5)
+    assert bool(((out >= lo) & (out < lo + 1 / 32 + 1e-6)).all())
+    assert float((out - lo).std()) > 0.005
+
+
+def test_pinned_chunk_source_feeds_optimize():
+    """The e2e input path: pinned uint8/fp32 host chunks -> async H2D + on-device normalisation -> model.optimize."""
+    from mrssm_b200.data import PinnedChunkSource
+    from oracle import mrssm_oracle as O
+    oc = O.OracleConfig(fusion="MoPoE")
+    model, _ = U.build_product(oc, 3, 5, DEV)
+    g = torch.Generator().manual_seed(0)
+    chunks = []
+    for _ in range(2):
+        obs = {"image_horizon": torch.randint(0, 256, (5, 3, 3, 64, 64), generator=g, dtype=torch.uint8),
+               "pose_quat_v2": torch.randn(5, 3, 3, generator=g)}
+        chunks.append((obs, torch.randn(5, 3, 3, generator=g), torch.zeros(5, 3), torch.ones(5, 3, 1)))
+    D = PinnedChunkSource(chunks, DEV, bit_depth=5, seed=1)
+    first = D.sample(3, 5)
+    img = first[0]["image_horizon"]
+    lo = chunks[0][0]["image_horizon"].to(DEV).float().div(8).floor().div(32).sub(0.5)
+    assert bool(((img >= lo) & (img < lo + 1 / 32 + 1e-6)).all())
+    torch.testing.assert_close(first[0]["pose_quat_v2"], chunks[0][0]["pose_quat_v2"].to(DEV))
+    D2 = PinnedChunkSource(chunks, DEV, bit_depth=5, seed=1)
+    losses = []
+    for _ in range(3):
+        model.optimize(D2)
+        losses.append(float(model.model_loss))
+    assert all(l == l and abs(l) < 1e6 for l in losses), losses
