@@ -299,6 +299,13 @@ def run_ours(args):
     e2e_value = world * args.batch * args.chunk / (ms_e2e / args.steps * 1e-3)
     h2d_bytes = Dh.h2d_bytes
     del Dh
+    if world > 1:
+        # collectives are over: the per-kernel profile below runs on rank 0 alone (no gradient all-reduce)
+        import torch.distributed as dist
+        model.dp = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
 
     if rank != 0:
         return

@@ -137,7 +137,10 @@ typedef struct mrssm_pl_conv_args {
     int32_t act, mask_mode, out_f32;
     int32_t n_out_pad, n_out_valid;
     int32_t cs_valid, cl_valid;                    /* wgrad: real channel counts of the master weight */
-    int32_t reserved;
+    int32_t s2d_cq;                                /* > 0 (down / wgrad): `large` is the SPACE-TO-DEPTH form of a cq-channel
+                                                      image (cq <= 4): a linear view [n, ceil(Hl/2), ceil(Wl/2), Cl = 16] whose
+                                                      channel (py*2+px)*cq + c is channel c of pixel (2y+py, 2x+px).  Hl, Wl stay
+                                                      the image's own size.  Made by mrssm_pl_import_s2d; weights packed with op 2. */
     mrssm_tv large, small, mask;                   /* mask: indexed at the output pixel */
     mrssm_t4 out32;                                /* fp32 output of down/up when out_f32 (arbitrary strides, e.g. NCHW) */
     const void* wpacked;
@@ -151,12 +154,18 @@ int mrssm_pl_conv_up(const mrssm_pl_conv_args* a, void* stream);
 int mrssm_pl_conv_wgrad(const mrssm_pl_conv_args* a, void* stream);
 int mrssm_pl_packed_shape(int32_t op, int32_t Cs_pad, int32_t Cl_pad, int32_t ksz, int32_t* N_total, int32_t* K_total);
 int mrssm_pl_pack_weight(const float* w, int64_t w_ss, int64_t w_sl, int32_t Cs_valid, int32_t Cl_valid, int32_t Cs_pad,
-                         int32_t Cl_pad, int32_t ksz, int32_t op, void* out, void* stream);
+                         int32_t Cl_pad, int32_t ksz, int32_t op /* 0 down, 1 up, 2 down over a space-to-depth source */,
+                         int32_t s2d_cq, void* out, void* stream);
 /* fp32 strided [n,H,W,C] -> bf16 view with channels padded to Cpad (x scale); image_processing / autograd glue */
 int mrssm_pl_import(const mrssm_t4* src, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t Cpad, float scale,
                     const mrssm_tv* dst, void* stream);
 /* out[c] += sum over (img,y,x) of the view: bias gradients (autograd of encoder.py:315-322, observation_model.py:65-74) */
-int mrssm_pl_colsum(const mrssm_tv* x, int32_t n_img, int32_t H, int32_t W, int32_t Cpad, int32_t Cvalid, float* out, void* stream);
+/* fp32 strided [n,H,W,C<=4] -> the space-to-depth view described at mrssm_pl_conv_args.s2d_cq */
+int mrssm_pl_import_s2d(const mrssm_t4* src, int32_t n_img, int32_t H, int32_t W, int32_t C, float scale, const mrssm_tv* dst,
+                        void* stream);
+/* fold > 0: the view is a space-to-depth view of a fold-channel tensor (H, W = the view's own size) */
+int mrssm_pl_colsum(const mrssm_tv* x, int32_t n_img, int32_t H, int32_t W, int32_t Cpad, int32_t Cvalid, int32_t fold,
+                    float* out, void* stream);
 /* host only, no GPU: format the tiling plan of a layer (op 0 down, 1 up, 2 wgrad) */
 int mrssm_pl_describe(const mrssm_pl_conv_args* a, int32_t op, char* buf, int32_t buflen);
 /* bring-up switches (descriptor-field variants); 0 = production setting */

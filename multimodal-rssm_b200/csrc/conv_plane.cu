@@ -206,6 +206,7 @@ struct FwdP {
     int act, mask_mode, out_f32, n_valid, Cop, Ho, Wo;
     int a_stage_bytes;
     int mergedA;                // TMA coordinate convention of the activation maps
+    int s2d;                    // down: the source is the space-to-depth (16-channel) form of a <= 4-channel image
     long long* prof;            // [CTA][16 tiles][8 slots] clock64 stamps or NULL
     TV out, mask;               // bf16 output / act'-mask views (indexed at the output pixel)
     T4 out32;                   // fp32 output (F32 kernels)
@@ -298,7 +299,10 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         if (ks < P.n_ksteps) {
             int j = ks % P.J, t = ks / P.J, b = t % P.nt, r = t / P.nt;
             int plane, shift;
-            if (OP == OP_DOWN) {           // r = kh
+            if (OP == OP_DOWN && P.s2d) {  // r = a: all four input parities are channels of the same pixel
+                plane = 2 * j;
+                shift = r * P.BX + b;
+            } else if (OP == OP_DOWN) {    // r = kh
                 plane = (r & 1) * 2 * P.J + 2 * j;
                 shift = (r >> 1) * P.BX + b;
             } else {                       // r = a
@@ -539,12 +543,20 @@ int plan_fwd(const mrssm_pl_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
     int Cp, N_total;
     if (op == OP_DOWN) {
         Cp = a->Cl;
+        P.s2d = a->s2d_cq > 0;
         MRSSM_CHECK(Cp % 8 == 0, "plane down: source channels %d must be padded to 8", Cp);
+        MRSSM_CHECK(!P.s2d || (Cp % 16 == 0 && 4 * a->s2d_cq <= Cp), "plane down: a space-to-depth source needs 4*cq <= Cl, Cl %% 16 == 0");
         P.Hv = a->Hs; P.Wv = a->Ws;
-        P.planes = 4 * (Cp / 8); P.ppm = Cp / 8;
         P.x0 = P.y0 = 0;
-        P.J = Cp / 8;
-        P.n_ksteps = k * nt * P.J;
+        if (P.s2d) {
+            P.planes = Cp / 8; P.ppm = P.planes;
+            P.J = Cp / 16;
+            P.n_ksteps = nt * nt * P.J;
+        } else {
+            P.planes = 4 * (Cp / 8); P.ppm = Cp / 8;
+            P.J = Cp / 8;
+            P.n_ksteps = k * nt * P.J;
+        }
         N_total = a->n_out_pad;
         P.Cop = N_total;
         P.Ho = a->Hs; P.Wo = a->Ws;
@@ -664,7 +676,12 @@ int launch_fwd(const mrssm_pl_conv_args* a, int op, cudaStream_t st) {
     memset(mA, 0, sizeof(mA));
     if (op == OP_DOWN) {
         MRSSM_CHECK(a->large.ptr, "plane down: null source");
-        if (int rc = make_view_maps(mA, &P.mergedA, a->large, a->Hl, a->Wl, a->Cl, a->n_img, true, P.BX, P.BY, P.BI)) return rc;
+        if (P.s2d) {
+            if (int rc = make_view_maps(mA, &P.mergedA, a->large, (a->Hl + 1) / 2, (a->Wl + 1) / 2, a->Cl, a->n_img, false, P.BX, P.BY, P.BI))
+                return rc;
+        } else if (int rc = make_view_maps(mA, &P.mergedA, a->large, a->Hl, a->Wl, a->Cl, a->n_img, true, P.BX, P.BY, P.BI)) {
+            return rc;
+        }
     } else {
         MRSSM_CHECK(a->small.ptr, "plane up: null source");
         if (int rc = make_view_maps(mA, &P.mergedA, a->small, a->Hs, a->Ws, a->Cs, a->n_img, false, P.BX, P.BY, P.BI)) return rc;
@@ -694,14 +711,21 @@ int launch_fwd(const mrssm_pl_conv_args* a, int op, cudaStream_t st) {
 // weight packing for the forward-type kernel:  out[n][k], k = kstep*16 + e  (zero padded to K_total)
 // ---------------------------------------------------------------------------------------------------
 __global__ void pack_plane_kernel(const float* __restrict__ w, long long w_ss, long long w_sl, int Cs_valid, int Cl_valid, int Csp, int Clp,
-                                  int ksz, int op, int N_total, int K_total, bf16* __restrict__ out) {
+                                  int ksz, int op, int cq, int N_total, int K_total, bf16* __restrict__ out) {
     const int nt = (ksz + 1) / 2;
     const long long total = (long long)N_total * K_total;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int kk = (int)(i % K_total), n = (int)(i / K_total);
         const int ks = kk >> 4, e = kk & 15;
         float v = 0.f;
-        if (op == OP_DOWN) {
+        if (op == 2) {                   // down over a space-to-depth source: channel = parity * cq + c
+            const int J = Clp / 16;
+            const int j = ks % J, t = ks / J, b = t % nt, aa = t / nt;
+            const int ch = (2 * j + (e >> 3)) * 8 + (e & 7);
+            const int par = ch / cq, c = ch - par * cq;
+            const int kh = 2 * aa + (par >> 1), kw = 2 * b + (par & 1);
+            if (aa < nt && par < 4 && n < Cs_valid && c < Cl_valid && kh < ksz && kw < ksz) v = w[n * w_ss + c * w_sl + kh * ksz + kw];
+        } else if (op == OP_DOWN) {
             const int J = Clp / 8;
             const int j = ks % J, t = ks / J, b = t % nt, kh = t / nt;
             const int pl = 2 * j + (e >> 3);
@@ -730,7 +754,7 @@ struct WgP {
     int nksteps;                // K steps (16 pixels) per tile
     int ksz, nt, Clp, Csp, N;
     int NG, gpp, n_cpass, n_mhalf;
-    int NA, zero_bytes, mergedS, mergedL;
+    int NA, zero_bytes, mergedS, mergedL, s2d_cq;
     int cs_valid, cl_valid;
     float* dw;
     long long w_ss, w_sl;
@@ -810,8 +834,9 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
                 const uint32_t sS = smem0 + (uint32_t)sa * (uint32_t)P.stage_bytes, sL = sS + (uint32_t)P.offL;
                 const uint32_t a0 = ((sS >> 4) & 0x3FFFu) | lbo;
                 for (int gi = 0; gi < ng; ++gi) {
-                    const int g = g0 + gi, kh = g / P.nt, b = g - kh * P.nt;
-                    const uint32_t boff = (uint32_t)((kh & 1) * 2 * P.cpl) * (uint32_t)P.PS_l + (uint32_t)((kh >> 1) * P.BX + b) * 16u;
+                    const int g = g0 + gi, kh = g / P.nt, b = g - kh * P.nt;      // space-to-depth source: kh is the row tap a
+                    const uint32_t boff = P.s2d_cq ? (uint32_t)(kh * P.BX + b) * 16u
+                                                   : (uint32_t)((kh & 1) * 2 * P.cpl) * (uint32_t)P.PS_l + (uint32_t)((kh >> 1) * P.BX + b) * 16u;
                     uint32_t a_lo = a0, b_lo = (((sL + boff) >> 4) & 0x3FFFu) | lbo;
                     const uint32_t d = tmem_base + (uint32_t)(gi * P.N);
                     umma_bf16_lohi(d, a_lo, s_hi, b_lo, l_hi, idesc, accum);
@@ -841,8 +866,23 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
                 if (cs >= P.cs_valid) continue;
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    const int c = c0 + e, px = c / P.Clp, cl = c - px * P.Clp, kw = 2 * b + px;
-                    if (cl < P.cl_valid && kw < P.ksz) atomicAdd(P.dw + cs * P.w_ss + cl * P.w_sl + kh * P.ksz + kw, v[e]);
+                    const int c = c0 + e;
+                    int cl, kh2, kw;
+                    bool ok;
+                    if (P.s2d_cq) {
+                        const int par = c / P.s2d_cq;
+                        cl = c - par * P.s2d_cq;
+                        kh2 = 2 * kh + (par >> 1);
+                        kw = 2 * b + (par & 1);
+                        ok = par < 4 && kh2 < P.ksz;
+                    } else {
+                        const int px = c / P.Clp;
+                        cl = c - px * P.Clp;
+                        kh2 = kh;
+                        kw = 2 * b + px;
+                        ok = true;
+                    }
+                    if (ok && cl < P.cl_valid && kw < P.ksz) atomicAdd(P.dw + cs * P.w_ss + cl * P.w_sl + kh2 * P.ksz + kw, v[e]);
                 }
             }
         }
@@ -861,13 +901,15 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
     P.n_img = a->n_img; P.ksz = k; P.nt = nt;
     P.Clp = a->Cl; P.Csp = a->Cs;
     MRSSM_CHECK(P.Clp % 8 == 0 && P.Csp % 8 == 0, "plane wgrad: channels must be padded to 8 (Cl %d Cs %d)", P.Clp, P.Csp);
-    P.N = 2 * P.Clp;
-    MRSSM_CHECK(P.N % 16 == 0 && P.N <= 256, "plane wgrad: 2*Cl = %d must be <= 256", P.N);
+    P.s2d_cq = a->s2d_cq;
+    MRSSM_CHECK(!P.s2d_cq || (P.Clp % 16 == 0 && 4 * P.s2d_cq <= P.Clp), "plane wgrad: a space-to-depth source needs 4*cq <= Cl, Cl %% 16 == 0");
+    P.N = P.s2d_cq ? P.Clp : 2 * P.Clp;
+    MRSSM_CHECK(P.N % 16 == 0 && P.N <= 256, "plane wgrad: N = %d must be a multiple of 16, <= 256", P.N);
     P.cpl = P.Clp / 8;
-    P.nL = 4 * P.cpl;
+    P.nL = P.s2d_cq ? P.cpl : 4 * P.cpl;
     P.n_mhalf = (P.Csp + 127) / 128;
     P.nS = std::min(16, P.Csp / 8);
-    P.NG = k * nt;
+    P.NG = P.s2d_cq ? nt * nt : k * nt;
     P.gpp = std::min(P.NG, 512 / P.N);
     P.n_cpass = (P.NG + P.gpp - 1) / P.gpp;
     P.gpp = (P.NG + P.n_cpass - 1) / P.n_cpass;
@@ -930,7 +972,11 @@ int launch_wgrad(const mrssm_pl_conv_args* a, cudaStream_t st) {
     if (int rc = plan_wgrad(a, P, smem, splits)) return rc;
     CUtensorMap mS[4], mL[4];
     if (int rc = make_view_maps(mS, &P.mergedS, a->small, a->Hs, a->Ws, a->Cs, a->n_img, false, P.BX, P.SBY, P.BI)) return rc;
-    if (int rc = make_view_maps(mL, &P.mergedL, a->large, a->Hl, a->Wl, a->Cl, a->n_img, true, P.BX, P.BY, P.BI)) return rc;
+    if (P.s2d_cq) {
+        if (int rc = make_view_maps(mL, &P.mergedL, a->large, (a->Hl + 1) / 2, (a->Wl + 1) / 2, a->Cl, a->n_img, false, P.BX, P.BY, P.BI)) return rc;
+    } else if (int rc = make_view_maps(mL, &P.mergedL, a->large, a->Hl, a->Wl, a->Cl, a->n_img, true, P.BX, P.BY, P.BI)) {
+        return rc;
+    }
     dim3 grid((unsigned)splits, (unsigned)(P.n_cpass * P.n_mhalf));
     smem = std::max<size_t>(smem, 120 * 1024);
     MRSSM_CUDA(cudaFuncSetAttribute(plane_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -947,9 +993,13 @@ extern "C" int mrssm_pl_conv_wgrad(const mrssm_pl_conv_args* a, void* stream) { 
 
 extern "C" int mrssm_pl_packed_shape(int32_t op, int32_t Cs_pad, int32_t Cl_pad, int32_t ksz, int32_t* N_total, int32_t* K_total) {
     const int nt = (ksz + 1) / 2;
-    MRSSM_CHECK(N_total && K_total && ksz >= 2 && (op == OP_DOWN || op == OP_UP), "pl_packed_shape: bad args");
+    MRSSM_CHECK(N_total && K_total && ksz >= 2 && op >= 0 && op <= 2, "pl_packed_shape: bad args");
     int n_ksteps;
-    if (op == OP_DOWN) {
+    if (op == 2) {
+        MRSSM_CHECK(Cl_pad % 16 == 0 && Cs_pad % 16 == 0, "pl_packed_shape(down, space-to-depth): Cl_pad %% 16, Cs_pad %% 16");
+        n_ksteps = nt * nt * (Cl_pad / 16);
+        *N_total = Cs_pad;
+    } else if (op == OP_DOWN) {
         MRSSM_CHECK(Cl_pad % 8 == 0 && Cs_pad % 16 == 0, "pl_packed_shape(down): Cl_pad %% 8, Cs_pad %% 16");
         n_ksteps = ksz * nt * (Cl_pad / 8);
         *N_total = Cs_pad;
@@ -963,13 +1013,14 @@ extern "C" int mrssm_pl_packed_shape(int32_t op, int32_t Cs_pad, int32_t Cl_pad,
 }
 
 extern "C" int mrssm_pl_pack_weight(const float* w, int64_t w_ss, int64_t w_sl, int32_t Cs_valid, int32_t Cl_valid, int32_t Cs_pad,
-                                    int32_t Cl_pad, int32_t ksz, int32_t op, void* out, void* stream) {
+                                    int32_t Cl_pad, int32_t ksz, int32_t op, int32_t s2d_cq, void* out, void* stream) {
+    MRSSM_CHECK(op != 2 || (s2d_cq > 0 && 4 * s2d_cq <= Cl_pad), "pl_pack_weight: op 2 needs 0 < 4*s2d_cq <= Cl_pad");
     int32_t N_total, K_total;
     if (int rc = mrssm_pl_packed_shape(op, Cs_pad, Cl_pad, ksz, &N_total, &K_total)) return rc;
     MRSSM_CHECK(w && out, "pl_pack_weight: null pointer");
     const long long total = (long long)N_total * K_total;
     const int blocks = (int)std::min<long long>(148 * 8, ceil_div64(total, 256));
-    pack_plane_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, w_ss, w_sl, Cs_valid, Cl_valid, Cs_pad, Cl_pad, ksz, op, N_total, K_total,
+    pack_plane_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, w_ss, w_sl, Cs_valid, Cl_valid, Cs_pad, Cl_pad, ksz, op, s2d_cq, N_total, K_total,
                                                                (bf16*)out);
     MRSSM_LAUNCH_CHECK();
     return 0;
@@ -1002,7 +1053,35 @@ __global__ void import_view_kernel(T4 src, int n, int H, int W, int Cc, int nchu
     }
 }
 
-__global__ void colsum_view_kernel(TV t, int n, int H, int W, int Cvalid, float* __restrict__ out) {
+// fp32 strided [n,H,W,C<=4] -> space-to-depth bf16 view [n,ceil(H/2),ceil(W/2),16]: channel = (py*2+px)*C + c, rest zero
+__global__ void import_s2d_kernel(T4 src, int n, int H, int W, int Cc, float scale, TV dst) {
+    const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+    const long long total = (long long)n * H2 * W2 * 2;
+    const float* sp0 = (const float*)src.p;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x2 = (int)(i % W2);
+        long long t = i / W2;
+        const int y2 = (int)(t % H2);
+        t /= H2;
+        const int ch = (int)(t & 1), img = (int)(t >> 1);
+        const float* sp = sp0 + img * src.sI;
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int cidx = ch * 8 + e, par = cidx / Cc, c = cidx - par * Cc;
+            const int y = 2 * y2 + (par >> 1), x = 2 * x2 + (par & 1);
+            f[e] = (par < 4 && y < H && x < W) ? sp[y * src.sH + x * src.sW + (long long)c * src.sC] * scale : 0.f;
+        }
+        uint4 pk;
+        __nv_bfloat162* ph = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ph[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+        *reinterpret_cast<uint4*>((bf16*)dst.p + tv_pix(dst, img, y2, x2) + ch * dst.sK) = pk;
+    }
+}
+
+// fold > 0: channel c of the view is channel (c % fold) of the logical tensor for c < 4*fold (space-to-depth views)
+__global__ void colsum_view_kernel(TV t, int n, int H, int W, int Cvalid, int fold, float* __restrict__ out) {
     const int ch = blockIdx.y;
     const long long total = (long long)n * H * W;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -1031,7 +1110,11 @@ __global__ void colsum_view_kernel(TV t, int n, int H, int W, int Cvalid, float*
         float s = 0.f;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
         const int c = ch * 8 + threadIdx.x;
-        if (c < Cvalid) atomicAdd(out + c, s);
+        if (fold > 0) {
+            if (c < 4 * fold && c % fold < Cvalid) atomicAdd(out + c % fold, s);
+        } else if (c < Cvalid) {
+            atomicAdd(out + c, s);
+        }
     }
 }
 }  // namespace
@@ -1046,13 +1129,24 @@ extern "C" int mrssm_pl_import(const mrssm_t4* src, int32_t n_img, int32_t H, in
     return 0;
 }
 
-extern "C" int mrssm_pl_colsum(const mrssm_tv* x, int32_t n_img, int32_t H, int32_t W, int32_t Cpad, int32_t Cvalid, float* out, void* stream) {
-    MRSSM_CHECK(x && x->ptr && out && Cpad % 8 == 0 && Cvalid <= Cpad, "pl_colsum: bad args");
-    const int nchunk = (Cvalid + 7) / 8;
+extern "C" int mrssm_pl_import_s2d(const mrssm_t4* src, int32_t n_img, int32_t H, int32_t W, int32_t C, float scale, const mrssm_tv* dst,
+                                   void* stream) {
+    MRSSM_CHECK(src && src->ptr && dst && dst->ptr && C >= 1 && C <= 4, "pl_import_s2d: bad args (C must be <= 4)");
+    const long long total = (long long)n_img * ((H + 1) / 2) * ((W + 1) / 2) * 2;
+    const int blocks = (int)std::min<long long>(148 * 16, ceil_div64(total, 256));
+    import_s2d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cvt(*src), n_img, H, W, C, scale, cvt(*dst));
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mrssm_pl_colsum(const mrssm_tv* x, int32_t n_img, int32_t H, int32_t W, int32_t Cpad, int32_t Cvalid, int32_t fold,
+                               float* out, void* stream) {
+    MRSSM_CHECK(x && x->ptr && out && Cpad % 8 == 0 && Cvalid <= Cpad && (fold == 0 || 4 * fold <= Cpad), "pl_colsum: bad args");
+    const int nchunk = fold > 0 ? (4 * fold + 7) / 8 : (Cvalid + 7) / 8;
     const long long total = (long long)n_img * H * W;
     const int bx = (int)std::max<long long>(1, std::min<long long>(ceil_div64(total, 256 * 8), std::max(1, 1184 / nchunk)));
     dim3 grid((unsigned)bx, (unsigned)nchunk);
-    colsum_view_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cvt(*x), n_img, H, W, Cvalid, out);
+    colsum_view_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cvt(*x), n_img, H, W, Cvalid, fold, out);
     MRSSM_LAUNCH_CHECK();
     return 0;
 }

@@ -732,27 +732,33 @@ def tc_colsum(x, Cvalid, out):
 DOWN, UP = 0, 1
 
 
-def pl_pack_weight(w, op, Cs_pad, Cl_pad):
-    """fp32 master [Cs,Cl,k,k] -> bf16 [N_total, K_total] in the K-step order of csrc/conv_plane.cu."""
+DOWN_S2D = 2
+
+
+def pl_pack_weight(w, op, Cs_pad, Cl_pad, s2d_cq=0):
+    """fp32 master [Cs,Cl,k,k] -> bf16 [N_total, K_total] in the K-step order of csrc/conv_plane.cu.
+    op DOWN_S2D: `down` over the space-to-depth form (Cl_pad = 16 channels) of an s2d_cq-channel image."""
     Cs, Cl, k, _ = w.shape
     n, kk = C.c_int32(), C.c_int32()
     L.call_host("mrssm_pl_packed_shape", op, Cs_pad, Cl_pad, k, C.byref(n), C.byref(kk))
     out = torch.empty(n.value, kk.value, device=w.device, dtype=torch.bfloat16)
-    L.call("mrssm_pl_pack_weight", L.ptr(w), Cl * k * k, k * k, Cs, Cl, Cs_pad, Cl_pad, k, op, L.ptr(out))
+    L.call("mrssm_pl_pack_weight", L.ptr(w), Cl * k * k, k * k, Cs, Cl, Cs_pad, Cl_pad, k, op, s2d_cq, L.ptr(out))
     return out
 
 
 def _pl_args(geom, large=None, small=None, mask=None, act=0, mask_mode=0, out32=None, n_out_pad=0, n_out_valid=0,
-             cs_valid=0, cl_valid=0, wpacked=None, bias=None, dweight=None, w_ss=0, w_sl=0):
-    return L.PlConvArgs(*geom, act, mask_mode, int(out32 is not None), n_out_pad, n_out_valid, cs_valid, cl_valid, 0,
+             cs_valid=0, cl_valid=0, wpacked=None, bias=None, dweight=None, w_ss=0, w_sl=0, s2d_cq=0):
+    return L.PlConvArgs(*geom, act, mask_mode, int(out32 is not None), n_out_pad, n_out_valid, cs_valid, cl_valid, s2d_cq,
                         large or L.NO_TV, small or L.NO_TV, mask or L.NO_TV, out32 or L.NO_T4, wpacked, bias, dweight, w_ss, w_sl)
 
 
-def pl_conv_down(geom, large, out, wpacked, bias, n_out_valid, n_out_pad, act=0, mask=None, mask_mode=0, valid=None):
-    """large: L.TV view of the gathered tensor (parity-planar preferred); out: L.TV (bf16) or L.T4 (fp32, any strides)."""
+def pl_conv_down(geom, large, out, wpacked, bias, n_out_valid, n_out_pad, act=0, mask=None, mask_mode=0, valid=None, s2d_cq=0):
+    """large: L.TV view of the gathered tensor (parity-planar preferred; the space-to-depth view when s2d_cq);
+    out: L.TV (bf16) or L.T4 (fp32, any strides)."""
     f32 = isinstance(out, L.T4)
     a = _pl_args(geom, large=large, small=None if f32 else out, mask=mask, act=act, mask_mode=mask_mode,
-                 out32=out if f32 else None, n_out_pad=n_out_pad, n_out_valid=n_out_valid, wpacked=L.ptr(wpacked), bias=L.ptr(bias))
+                 out32=out if f32 else None, n_out_pad=n_out_pad, n_out_valid=n_out_valid, wpacked=L.ptr(wpacked), bias=L.ptr(bias),
+                 s2d_cq=s2d_cq)
     tag, work = _tc_work("mrssm_pl_conv_down", geom, valid or (geom[6], geom[3]))
     L.call("mrssm_pl_conv_down", C.byref(a), tag=tag, work=work)
 
@@ -766,8 +772,9 @@ def pl_conv_up(geom, out, small, wpacked, bias, n_out_valid, n_out_pad, act=0, m
     L.call("mrssm_pl_conv_up", C.byref(a), tag=tag, work=work)
 
 
-def pl_conv_wgrad(geom, large, small, dweight_ptr, w_ss, w_sl, cs_valid, cl_valid):
-    a = _pl_args(geom, large=large, small=small, cs_valid=cs_valid, cl_valid=cl_valid, dweight=dweight_ptr, w_ss=w_ss, w_sl=w_sl)
+def pl_conv_wgrad(geom, large, small, dweight_ptr, w_ss, w_sl, cs_valid, cl_valid, s2d_cq=0):
+    a = _pl_args(geom, large=large, small=small, cs_valid=cs_valid, cl_valid=cl_valid, dweight=dweight_ptr, w_ss=w_ss, w_sl=w_sl,
+                 s2d_cq=s2d_cq)
     tag, work = _tc_work("mrssm_pl_conv_wgrad", geom, (cs_valid, cl_valid))
     L.call("mrssm_pl_conv_wgrad", C.byref(a), tag=tag, work=work)
 
@@ -785,8 +792,17 @@ def pl_import(src_t4, n, H, W, Cc, Cp, layout, device, scale=1.0):
     return t, v
 
 
-def pl_colsum(view, n, H, W, Cp, Cvalid, out):
-    L.call("mrssm_pl_colsum", C.byref(view), n, H, W, Cp, Cvalid, L.ptr(out))
+def pl_colsum(view, n, H, W, Cp, Cvalid, out, fold=0):
+    """out[c] += sum over pixels.  fold: the view is the space-to-depth view (H, W its own size) of a fold-channel tensor."""
+    L.call("mrssm_pl_colsum", C.byref(view), n, H, W, Cp, Cvalid, fold, L.ptr(out))
+
+
+def pl_import_s2d(src_t4, n, H, W, Cc, device, scale=1.0):
+    """fp32 strided [n,H,W,C<=4] -> planar bf16 space-to-depth view [n,ceil(H/2),ceil(W/2),16] (channel = parity*C + c)."""
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    t, v = new_act(n, H2, W2, 16, L.PLANAR, device)
+    L.call("mrssm_pl_import_s2d", C.byref(src_t4), n, H, W, Cc, float(scale), C.byref(v))
+    return t, v
 
 
 # ---- bf16 tensor-core mode ------------------------------------------------------------------------------------
@@ -824,13 +840,13 @@ def _bf16(*shape, device):
     return torch.empty(*shape, device=device, dtype=torch.bfloat16)
 
 
-def packed_pl(w, op, Cs_pad, Cl_pad):
+def packed_pl(w, op, Cs_pad, Cl_pad, s2d_cq=0):
     """Cached plane-kernel packing of a conv weight (re-packed when the master changes)."""
-    key = (w.data_ptr(), "pl", op, Cs_pad, Cl_pad)
+    key = (w.data_ptr(), "pl", op, Cs_pad, Cl_pad, s2d_cq)
     ver = (_STATE["wversion"], w._version)
     hit = _wcache.get(key)
     if hit is None or hit[0] != ver:
-        hit = (ver, pl_pack_weight(w.detach(), op, Cs_pad, Cl_pad))
+        hit = (ver, pl_pack_weight(w.detach(), op, Cs_pad, Cl_pad, s2d_cq))
         _wcache[key] = hit
     return hit[1]
 
@@ -846,9 +862,17 @@ class ConvEncoderTCFn(Function):
         N, Cc, H, W = x.shape
         dev = x.device
         n_layers = len(params) // 2
-        acts = [pl_import(L.nchw(x, H, W, Cc), N, H, W, Cc, pad8(Cc), L.PARITY, dev)]
+        # a <= 4-channel image goes in as its space-to-depth form (16 channels = 4 parities x C): no channel padding
+        # to 8 per parity, half the K steps in the first conv and its weight gradient
+        cq0 = Cc if Cc <= 4 else 0
+        if cq0:
+            acts = [pl_import_s2d(L.nchw(x, H, W, Cc), N, H, W, Cc, dev)]
+            Clp = 16
+        else:
+            acts = [pl_import(L.nchw(x, H, W, Cc), N, H, W, Cc, pad8(Cc), L.PARITY, dev)]
+            Clp = pad8(Cc)
         geoms = []
-        Hl, Wl, Clp = H, W, pad8(Cc)
+        Hl, Wl = H, W
         y = None
         for i in range(n_layers):
             Wt, b = params[2 * i], params[2 * i + 1]
@@ -856,15 +880,16 @@ class ConvEncoderTCFn(Function):
             Csp = pad16(Cs)
             Hs, Ws = (Hl - k) // 2 + 1, (Wl - k) // 2 + 1
             geom = (N, Hl, Wl, Clp, Hs, Ws, Csp, k)
-            wp = packed_pl(Wt, DOWN, Csp, Clp)
+            cq = cq0 if i == 0 else 0
+            wp = packed_pl(Wt, DOWN_S2D if cq else DOWN, Csp, Clp, cq)
             if i == n_layers - 1:
                 y = torch.empty(N, Cs * Hs * Ws, device=dev, dtype=torch.float32)
-                pl_conv_down(geom, acts[-1][1], L.nchw(y, Hs, Ws, Cs), wp, b, Cs, Csp, act=RELU, valid=(Cs, Cl))
+                pl_conv_down(geom, acts[-1][1], L.nchw(y, Hs, Ws, Cs), wp, b, Cs, Csp, act=RELU, valid=(Cs, Cl), s2d_cq=cq)
             else:
                 o = new_act(N, Hs, Ws, Csp, L.PARITY, dev)
-                pl_conv_down(geom, acts[-1][1], o[1], wp, b, Cs, Csp, act=RELU, valid=(Cs, Cl))
+                pl_conv_down(geom, acts[-1][1], o[1], wp, b, Cs, Csp, act=RELU, valid=(Cs, Cl), s2d_cq=cq)
                 acts.append(o)
-            geoms.append((geom, Cs, Cl))
+            geoms.append((geom, Cs, Cl, cq))
             Hl, Wl, Clp = Hs, Ws, Csp
         ctx.geoms, ctx.params = geoms, params
         ctx.save_for_backward(y, *[t for t, _ in acts])
@@ -876,15 +901,15 @@ class ConvEncoderTCFn(Function):
         y, *acts = ctx.saved_tensors
         dev = y.device
         n_layers = len(geoms)
-        (N, _, _, _, Hs, Ws, Csp, _), Cs, _ = geoms[-1]
+        (N, _, _, _, Hs, Ws, Csp, _), Cs, _, _ = geoms[-1]
         gm = act_bwd(g, y, RELU)
         gb = pl_import(L.nchw(gm, Hs, Ws, Cs), N, Hs, Ws, Cs, Csp, L.PLANAR, dev)
         for i in reversed(range(n_layers)):
             Wt, b = params[2 * i], params[2 * i + 1]
-            geom, Cs, Cl = geoms[i]
+            geom, Cs, Cl, cq = geoms[i]
             N, Hl, Wl, Clp, Hs, Ws, Csp, k = geom
-            xv = L.tv(acts[i], L.PARITY, Hl, Wl, Clp)
-            pl_conv_wgrad(geom, xv, gb[1], L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl)
+            xv = L.tv(acts[i], L.PLANAR, (Hl + 1) // 2, (Wl + 1) // 2, Clp) if cq else L.tv(acts[i], L.PARITY, Hl, Wl, Clp)
+            pl_conv_wgrad(geom, xv, gb[1], L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl, s2d_cq=cq)
             pl_colsum(gb[1], N, Hs, Ws, Csp, Cs, grad_buf(b))
             if i > 0:
                 gx = new_act(N, Hl, Wl, Clp, L.PLANAR, dev)
@@ -928,6 +953,7 @@ class ConvDecoderTCFn(Function):
             Clp = pad8(Cl) if last else pad16(Cl)
             geom = (R, Hl, Wl, Clp, Hs, Ws, Csp, k)
             xt, xl = acts[-1]
+            cq = Cl if (last and Cl <= 4) else 0          # backward: the image gradient travels in space-to-depth form
             if i == 0 and Hs == 1 and not last:
                 assert Clp == Cl, "dense lowering of the first ConvTranspose needs Cout % 16 == 0"
                 o = _bf16(R, Hl, Wl, Clp, device=dev)
@@ -943,7 +969,7 @@ class ConvDecoderTCFn(Function):
                 o = new_act(R, Hl, Wl, Clp, L.PLANAR, dev)
                 pl_conv_up(geom, o[1], L.tv(xt, xl, Hs, Ws, Csp), packed_pl(Wt, UP, Csp, Clp), b, Cl, Clp, act=RELU, valid=(Cs, Cl))
                 acts.append((o[0], L.PLANAR))
-            geoms.append((geom, Cs, Cl))
+            geoms.append((geom, Cs, Cl, cq))
             Hs, Ws, Csp = Hl, Wl, Clp
         ctx.geoms, ctx.params, ctx.dims = geoms, params, (R, D, S, Em, Kp)
         ctx.layouts = [l for _, l in acts]
@@ -959,11 +985,14 @@ class ConvDecoderTCFn(Function):
         convs = params[2:]
         n_layers = len(geoms)
         g = _f32c(g)
-        (_, Hl, Wl, Clp, _, _, _, _), _, Cl = geoms[-1]
-        gb, gl = pl_import(L.nchw(g, Hl, Wl, Cl), R, Hl, Wl, Cl, Clp, L.PARITY, dev)[0], L.PARITY
+        (_, Hl, Wl, Clp, _, _, _, _), _, Cl, cq_last = geoms[-1]
+        if cq_last:
+            gb, gl = pl_import_s2d(L.nchw(g, Hl, Wl, Cl), R, Hl, Wl, Cl, dev)[0], "s2d"
+        else:
+            gb, gl = pl_import(L.nchw(g, Hl, Wl, Cl), R, Hl, Wl, Cl, Clp, L.PARITY, dev)[0], L.PARITY
         for i in reversed(range(n_layers)):
             Wt, b = convs[2 * i], convs[2 * i + 1]
-            geom, Cs, Cl = geoms[i]
+            geom, Cs, Cl, cq = geoms[i]
             _, Hl, Wl, Clg, Hs, Ws, Csp, k = geom
             xi, xl = acts[i], layouts[i]
             dense = Hs == 1 and Ws == 1              # ConvTranspose on the 1x1 map: the dense kernels (NHWC)
@@ -976,14 +1005,21 @@ class ConvDecoderTCFn(Function):
                 tc_colsum(gb.view(-1, Clg), Cl, grad_buf(b))
                 nl = L.NHWC
             else:
-                gv, xv = L.tv(gb, gl, Hl, Wl, Clg), L.tv(xi, xl, Hs, Ws, Csp)
+                s2d = gl == "s2d"
+                H2, W2 = (Hl + 1) // 2, (Wl + 1) // 2
+                gg = (R, Hl, Wl, 16, Hs, Ws, Csp, k) if s2d else geom
+                gv = L.tv(gb, L.PLANAR, H2, W2, 16) if s2d else L.tv(gb, gl, Hl, Wl, Clg)
+                xv = L.tv(xi, xl, Hs, Ws, Csp)
                 # the gradient w.r.t. this layer's input feeds a dense layer (NHWC) when the layer below sits on the 1x1 map
                 nl = L.NHWC if (i > 0 and geoms[i - 1][0][4] == 1) or i == 0 else L.PARITY
                 gxt, gxv = new_act(R, Hs, Ws, Csp, nl, dev)
-                pl_conv_wgrad(geom, gv, xv, L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl)
-                pl_conv_down(geom, gv, gxv, packed_pl(Wt, DOWN, Csp, Clg), None, Cs, Csp,
-                             mask=xv if i > 0 else None, mask_mode=RELU if i > 0 else 0, valid=(Cs, Cl))
-                pl_colsum(gv, R, Hl, Wl, Clg, Cl, grad_buf(b))
+                pl_conv_wgrad(gg, gv, xv, L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl, s2d_cq=cq if s2d else 0)
+                pl_conv_down(gg, gv, gxv, packed_pl(Wt, DOWN_S2D if s2d else DOWN, Csp, gg[3], cq if s2d else 0), None, Cs, Csp,
+                             mask=xv if i > 0 else None, mask_mode=RELU if i > 0 else 0, valid=(Cs, Cl), s2d_cq=cq if s2d else 0)
+                if s2d:
+                    pl_colsum(gv, R, H2, W2, 16, Cl, grad_buf(b), fold=cq)
+                else:
+                    pl_colsum(gv, R, Hl, Wl, Clg, Cl, grad_buf(b))
                 gx = gxt
             gb, gl = gx, nl
         fcw, fcb = params[0], params[1]

@@ -12,10 +12,10 @@ import re
 import numpy as np
 
 
-def plan(L, geom, op, n_out_pad=0):
+def plan(L, geom, op, n_out_pad=0, s2d_cq=0):
     """geom = (n, Hl, Wl, Clp, Hs, Ws, Csp, k) with PADDED channel counts; op 0 down, 1 up, 2 wgrad."""
     n, Hl, Wl, Clp, Hs, Ws, Csp, k = geom
-    a = L.PlConvArgs(*geom, 0, 0, 0, n_out_pad, n_out_pad, geom[6], geom[3], 0,
+    a = L.PlConvArgs(*geom, 0, 0, 0, n_out_pad, n_out_pad, geom[6], geom[3], s2d_cq,
                      L.tv(16, L.PARITY, Hl, Wl, Clp), L.tv(16, L.PLANAR, Hs, Ws, Csp), L.NO_TV, L.NO_T4, 16, None, 16, 0, 0)
     buf = C.create_string_buffer(1024)
     lib = L.load()
@@ -35,7 +35,7 @@ def packed_shape(L, op, Csp, Clp, k):
     return n.value, kk.value
 
 
-def pack_weight(w, op, Csp, Clp, N_total, K_total):
+def pack_weight(w, op, Csp, Clp, N_total, K_total, cq=0):
     """numpy twin of pack_plane_kernel.  w: [Cs, Cl, k, k]."""
     Cs, Cl, k, _ = w.shape
     nt = (k + 1) // 2
@@ -43,7 +43,16 @@ def pack_weight(w, op, Csp, Clp, N_total, K_total):
     for n in range(N_total):
         for kk in range(K_total):
             ks, e = kk >> 4, kk & 15
-            if op == 0:
+            if op == 2:
+                J = Clp // 16
+                j, t = ks % J, ks // J
+                b, aa = t % nt, t // nt
+                ch = (2 * j + (e >> 3)) * 8 + (e & 7)
+                par, c = ch // cq, ch % cq
+                kh, kw = 2 * aa + (par >> 1), 2 * b + (par & 1)
+                if aa < nt and par < 4 and n < Cs and c < Cl and kh < k and kw < k:
+                    out[n, kk] = w[n, c, kh, kw]
+            elif op == 0:
                 J = Clp // 8
                 j, t = ks % J, ks // J
                 b, kh = t % nt, t // nt
@@ -80,9 +89,21 @@ def _box(src, c0, x0, y0, i0, bx, by, bi, sx=1, sy=1, ox=0, oy=0):
     return out.reshape(-1, 8)
 
 
-def sim_fwd(L, op, src, w, Hl, Wl, Hs, Ws, n_out_pad):
-    """src: padded-channel NHWC source (down: large, up: small); w [Cs, Cl, k, k] master.  Returns the output
-    tensor [n, Ho, Wo, n_out_pad] (NaN where the kernel would not write)."""
+def s2d16(x, cq):
+    """[n,H,W,cq] -> space-to-depth [n,ceil(H/2),ceil(W/2),16] with channel = (py*2+px)*cq + c."""
+    n, H, W, _ = x.shape
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    out = np.zeros((n, H2, W2, 16), np.float32)
+    for py in range(2):
+        for px in range(2):
+            sub = x[:, py::2, px::2, :cq]
+            out[:, :sub.shape[1], :sub.shape[2], (py * 2 + px) * cq:(py * 2 + px + 1) * cq] = sub
+    return out
+
+
+def sim_fwd(L, op, src, w, Hl, Wl, Hs, Ws, n_out_pad, s2d_cq=0):
+    """src: padded-channel NHWC source (down: large, up: small; the space-to-depth tensor when s2d_cq); w [Cs, Cl, k, k]
+    master.  Returns the output tensor [n, Ho, Wo, n_out_pad] (NaN where the kernel would not write)."""
     n = src.shape[0]
     k = w.shape[2]
     nt = (k + 1) // 2
@@ -91,13 +112,17 @@ def sim_fwd(L, op, src, w, Hl, Wl, Hs, Ws, n_out_pad):
     else:
         Csp, Clp = src.shape[3], n_out_pad
     geom = (n, Hl, Wl, Clp, Hs, Ws, Csp, k)
-    P = plan(L, geom, op, n_out_pad)
-    N_total, K_total = packed_shape(L, op, Csp, Clp, k)
-    wp = pack_weight(w, op, Csp, Clp, N_total, K_total)
+    P = plan(L, geom, op, n_out_pad, s2d_cq)
+    pop = 2 if s2d_cq else op
+    N_total, K_total = packed_shape(L, pop, Csp, Clp, k)
+    wp = pack_weight(w, pop, Csp, Clp, N_total, K_total, s2d_cq)
     BI, BX, BY, TH, nb = P["BI"], P["BX"], P["BY"], P["TH"], P["bands"]
     PSpos = P["PS"] // 16
     planes, n_ksteps = P["planes"], P["ksteps"]
-    if op == 0:
+    if op == 0 and s2d_cq:
+        J = Clp // 16
+        Hv, Wv, Ho, Wo = Hs, Ws, Hs, Ws
+    elif op == 0:
         J = Clp // 8
         Hv, Wv, Ho, Wo = Hs, Ws, Hs, Ws
     else:
@@ -109,7 +134,9 @@ def sim_fwd(L, op, src, w, Hl, Wl, Hs, Ws, n_out_pad):
         for band in range(nb):
             A = np.full((planes, PSpos, 8), np.nan, np.float32)
             for q in range(planes):
-                if op == 0:
+                if op == 0 and s2d_cq:
+                    A[q, :BI * BY * BX] = _box(src, q * 8, 0, band * TH, ig * BI, BX, BY, BI)
+                elif op == 0:
                     ppm = Clp // 8
                     mi, c0 = q // ppm, (q % ppm) * 8
                     A[q, :BI * BY * BX] = _box(src, c0, 0, band * TH, ig * BI, BX, BY, BI, 2, 2, mi & 1, mi >> 1)
@@ -121,7 +148,9 @@ def sim_fwd(L, op, src, w, Hl, Wl, Hs, Ws, n_out_pad):
             for ks in range(n_ksteps):
                 j, t = ks % J, ks // J
                 b, r = t % nt, t // nt
-                if op == 0:
+                if op == 0 and s2d_cq:
+                    plane, shift = 2 * j, r * BX + b
+                elif op == 0:
                     plane, shift = (r & 1) * 2 * J + 2 * j, (r >> 1) * BX + b
                 else:
                     plane, shift = 2 * j, (nt - 1 - r) * BX + (nt - 1 - b)
@@ -144,32 +173,52 @@ def sim_fwd(L, op, src, w, Hl, Wl, Hs, Ws, n_out_pad):
     return out, P
 
 
-def sim_wgrad(L, small, large, k):
-    """small [n, Hs, Ws, Csp], large [n, Hl, Wl, Clp] (padded channels).  Returns dW [Csp, Clp, k, k]."""
+def sim_wgrad(L, small, large, k, s2d_cq=0, Hl=None):
+    """small [n, Hs, Ws, Csp], large [n, Hl, Wl, Clp] (padded channels; the space-to-depth tensor of an Hl x Hl image when
+    s2d_cq).  Returns dW [Csp, Clp (or s2d_cq), k, k]."""
     n, Hs, Ws, Csp = small.shape
-    _, Hl, Wl, Clp = large.shape
+    if s2d_cq:
+        Clp, Wl = large.shape[3], Hl
+    else:
+        _, Hl, Wl, Clp = large.shape
     nt = (k + 1) // 2
     geom = (n, Hl, Wl, Clp, Hs, Ws, Csp, k)
-    P = plan(L, geom, 2)
+    P = plan(L, geom, 2, 0, s2d_cq)
     BI, BX, BY, TH, nb = P["BI"], P["BX"], P["BY"], P["TH"], P["bands"]
     banded = nb > 1
     SBY = TH if banded else BY
     PS_s, PS_l = P["PS_s"] // 16, P["PS_l"] // 16
     nks = P["tile"]          # "ksteps/tile=%d" parses as key 'tile'
     cpl = Clp // 8
-    dW = np.zeros((Csp, Clp, k, k), np.float32)
+    dW = np.zeros((Csp, s2d_cq if s2d_cq else Clp, k, k), np.float32)
     ngroups = (n + BI - 1) // BI
+    nL = cpl if s2d_cq else 4 * cpl
     for ig in range(ngroups):
         for band in range(nb):
             S = np.zeros((Csp // 8, PS_s, 8), np.float32)
-            Lg = np.zeros((4 * cpl, PS_l, 8), np.float32)
+            Lg = np.zeros((nL, PS_l, 8), np.float32)
             for q in range(Csp // 8):
                 S[q, :BI * SBY * BX] = _box(small, q * 8, 0, band * TH, ig * BI, BX, SBY, BI)
-            for q in range(4 * cpl):
-                mi, c0 = q // cpl, (q % cpl) * 8
-                Lg[q, :BI * BY * BX] = _box(large, c0, 0, band * TH, ig * BI, BX, BY, BI, 2, 2, mi & 1, mi >> 1)
+            for q in range(nL):
+                if s2d_cq:
+                    Lg[q, :BI * BY * BX] = _box(large, q * 8, 0, band * TH, ig * BI, BX, BY, BI)
+                else:
+                    mi, c0 = q // cpl, (q % cpl) * 8
+                    Lg[q, :BI * BY * BX] = _box(large, c0, 0, band * TH, ig * BI, BX, BY, BI, 2, 2, mi & 1, mi >> 1)
             K = nks * 16
             Sm = S[:, :K].transpose(1, 0, 2).reshape(K, Csp)            # [pixel][cs]
+            if s2d_cq:
+                for g in range(nt * nt):
+                    a, b = g // nt, g % nt
+                    shift = a * BX + b
+                    Bm = Lg[:, shift:shift + K].transpose(1, 0, 2).reshape(K, Clp)                          # [pixel][(parity, c)]
+                    D = Sm.T @ Bm
+                    for c in range(Clp):
+                        par, cl = c // s2d_cq, c % s2d_cq
+                        kh, kw = 2 * a + (par >> 1), 2 * b + (par & 1)
+                        if par < 4 and kh < k and kw < k:
+                            dW[:, cl, kh, kw] += D[:, c]
+                continue
             for g in range(k * nt):
                 kh, b = g // nt, g % nt
                 plane0, shift = (kh & 1) * 2 * cpl, (kh >> 1) * BX + b

@@ -228,3 +228,41 @@ def test_plane_wgrad_and_colsum_match_simt(g, ll, sl):
         acc = torch.zeros(Cv, device=DEV)
         ops.pl_colsum(v, n, H, H, Cp, Cv, acc)
         torch.testing.assert_close(acc, x.sum(dim=(0, 1, 2)), rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("g", [(3, 64, 3, 31, 32, 4), (2, 64, 3, 30, 32, 6), (2, 63, 3, 30, 16, 4), (1, 128, 3, 62, 32, 6), (4, 14, 4, 6, 16, 4)])
+def test_plane_space_to_depth_source_matches_simt(g):
+    """<= 4-channel images travel as their space-to-depth form: import, down (Conv2d fwd / ConvT dgrad), wgrad, bias sums."""
+    from mrssm_b200 import _lib as L, ops
+    n, Hl, Cl, Hs, Cs, k = g
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    large = _bf16_round(torch.randn(n, Hl, Hl, Cl, device=DEV, generator=gen))
+    small = _bf16_round(torch.randn(n, Hs, Hs, Cs, device=DEV, generator=gen))
+    w = _bf16_round(torch.randn(Cs, Cl, k, k, device=DEV, generator=gen) / (Cl * k * k) ** 0.5)
+    geom = (n, Hl, Hl, Cl, Hs, Hs, Cs, k)
+    Csp = ops.pad16(Cs)
+    H2 = (Hl + 1) // 2
+    lt, lv = ops.pl_import_s2d(L.nhwc(large, Hl, Hl, Cl), n, Hl, Hl, Cl, DEV)
+    s2d = export_view(lt, "planar", n, H2, H2, 16)
+    for par in range(4):
+        sub = large[:, par >> 1::2, par & 1::2, :]
+        torch.testing.assert_close(s2d[:, :sub.shape[1], :sub.shape[2], par * Cl:(par + 1) * Cl], sub)
+    assert float(s2d[..., 4 * Cl:].abs().max() if 4 * Cl < 16 else 0.0) == 0.0
+    gp = (n, Hl, Hl, 16, Hs, Hs, Csp, k)
+    bias = torch.randn(Cs, device=DEV)
+    ref = torch.empty_like(small)
+    ops._conv("mrssm_conv_down", geom, L.nhwc(large, Hl, Hl, Cl), L.nhwc(ref, Hs, Hs, Cs), L.ptr(w), Cl * k * k, k * k,
+              L.ptr(bias), ops.RELU)
+    wp = ops.pl_pack_weight(w, ops.DOWN_S2D, Csp, 16, Cl)
+    out = _filled(ops, L, n, Hs, Hs, Csp, "parity")
+    ops.pl_conv_down(gp, lv, out[1], wp, bias, Cs, Csp, act=ops.RELU, s2d_cq=Cl)
+    torch.testing.assert_close(export_view(out[0], "parity", n, Hs, Hs, Csp)[..., :Cs], ref, rtol=1e-2, atol=1e-2)
+    sb = ops.pl_import(L.nhwc(small, Hs, Hs, Cs), n, Hs, Hs, Cs, Csp, "planar", DEV)
+    refw = torch.zeros_like(w)
+    ops._conv("mrssm_conv_wgrad", geom, L.nhwc(large, Hl, Hl, Cl), L.nhwc(small, Hs, Hs, Cs), L.ptr(refw), Cl * k * k, k * k)
+    outw = torch.zeros_like(w)
+    ops.pl_conv_wgrad(gp, lv, sb[1], L.ptr(outw), Cl * k * k, k * k, Cs, Cl, s2d_cq=Cl)
+    assert float((outw - refw).abs().max()) <= 2e-3 * float(refw.abs().max()) + 1e-4
+    acc = torch.zeros(Cl, device=DEV)
+    ops.pl_colsum(lv, n, H2, H2, 16, Cl, acc, fold=Cl)
+    torch.testing.assert_close(acc, large.sum(dim=(0, 1, 2)), rtol=1e-3, atol=1e-2)

@@ -94,3 +94,29 @@ def test_full_size_plans_fit_shared_memory():
                 continue
             P = S.plan(L, geom, op, npad)
             assert P["smem"] <= 227 * 1024, P["text"]
+
+
+S2D = [(3, 64, 3, 31, 16, 4), (2, 64, 3, 30, 16, 6), (2, 63, 3, 30, 16, 4), (1, 128, 3, 63, 16, 4), (4, 14, 4, 6, 16, 4)]
+
+
+@pytest.mark.parametrize("g", S2D)
+def test_down_and_wgrad_over_space_to_depth_source(g):
+    """<= 4-channel images enter as their space-to-depth form (16 channels): the first conv and its weight gradient."""
+    n, Hl, Cl, Hs, Cs, k = g
+    L = _lib()
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(n, Cl, Hl, Hl, generator=gen)
+    w = torch.randn(Cs, Cl, k, k, generator=gen, requires_grad=True)
+    y = F.conv2d(x, w, stride=2)
+    assert y.shape[-1] == Hs
+    gy = torch.randn(y.shape, generator=gen)
+    y.backward(gy)
+    src = S.s2d16(x.permute(0, 2, 3, 1).numpy(), Cl)
+    Csp = _pad(Cs, 16)
+    out, P = S.sim_fwd(L, 0, src, w.detach().numpy(), Hl, Hl, Hs, Hs, Csp, s2d_cq=Cl)
+    assert not np.isnan(out).any(), P["text"]
+    np.testing.assert_allclose(out[..., :Cs], y.detach().permute(0, 2, 3, 1).numpy(), rtol=1e-4, atol=1e-4)
+    small = np.zeros((n, Hs, Hs, Csp), np.float32)
+    small[..., :Cs] = gy.permute(0, 2, 3, 1).numpy()
+    dW, P = S.sim_wgrad(L, small, src, k, s2d_cq=Cl, Hl=Hl)
+    np.testing.assert_allclose(dW[:Cs, :Cl], w.grad.numpy(), rtol=1e-3, atol=1e-3)
