@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "multimodal-rssm
 import torch
 from mrssm_b200 import _lib as L, ops
 
-def main(op="down", n=4096, Hl=64, Cl=3, Hs=31, Cs=32, k=4, f32=0):
+def main(op="down", n=4096, Hl=64, Cl=3, Hs=31, Cs=32, k=4, f32=0, mask=0):
     dev = "cuda:0"
     g = torch.Generator(device=dev).manual_seed(0)
     Clp, Csp = ops.pad8(Cl), ops.pad16(Cs)
@@ -20,7 +20,9 @@ def main(op="down", n=4096, Hl=64, Cl=3, Hs=31, Cs=32, k=4, f32=0):
         wp = ops.pl_pack_weight(w, ops.DOWN, Csp, Clp)
         bias = torch.zeros(Cs, device=dev)
         out = ops.new_act(n, Hs, Hs, Csp, L.PARITY, dev)
-        f = lambda: ops.pl_conv_down(gp, lb[1], out[1], wp, bias, Cs, Csp, act=1)
+        mk = ops.new_act(n, Hs, Hs, Csp, L.PLANAR, dev)
+        mk[0].fill_(1.0)
+        f = lambda: ops.pl_conv_down(gp, lb[1], out[1], wp, bias, Cs, Csp, act=0 if mask else 1, mask=mk[1] if mask else None, mask_mode=1 if mask else 0)
     else:
         wp = ops.pl_pack_weight(w, ops.UP, Csp, Clp)
         bias = torch.zeros(Cl, device=dev)
@@ -29,7 +31,9 @@ def main(op="down", n=4096, Hl=64, Cl=3, Hs=31, Cs=32, k=4, f32=0):
             f = lambda: ops.pl_conv_up(gp, L.nchw(out, Hl, Hl, Cl), sb[1], wp, bias, Cl, Clp)
         else:
             out = ops.new_act(n, Hl, Hl, Clp, L.PLANAR, dev)
-            f = lambda: ops.pl_conv_up(gp, out[1], sb[1], wp, bias, Cl, Clp, act=1)
+            mk = ops.new_act(n, Hl, Hl, Clp, L.PARITY, dev)
+            mk[0].fill_(1.0)
+            f = lambda: ops.pl_conv_up(gp, out[1], sb[1], wp, bias, Cl, Clp, act=0 if mask else 1, mask=mk[1] if mask else None, mask_mode=1 if mask else 0)
     for _ in range(2):
         f()
     torch.cuda.synchronize()
@@ -40,12 +44,12 @@ def main(op="down", n=4096, Hl=64, Cl=3, Hs=31, Cs=32, k=4, f32=0):
     f(); torch.cuda.synchronize()
     L.call_host("mrssm_pl_set_profile_buffer", None)
     p = prof.cpu().reshape(148, 16, 8)
-    names = ["P:start", "P:loop", "M:afull", "M:issued", "E:accfull", "E:end", "P:Anext", "P:Bdone"]
-    for cta in (0, 77):
+    names = ["P:start", "P:loop", "M:afull", "M:done", "E:accfull", "E:end", "M:accfree", "M:mmas"]
+    for cta in (0,):
         t0 = int(p[cta, 0, 0])
         print(f"CTA {cta} (cycles since start)")
-        for it in range(6):
-            print("  tile", it, " ".join(f"{names[s]}={int(p[cta, it, s]) - t0 if p[cta, it, s] else -1:>8d}" for s in (1, 6, 7, 2, 3, 4, 5)))
+        for it in range(0, 4):
+            print("  tile", it, " ".join(f"{names[s]}={int(p[cta, it, s]) - t0 if p[cta, it, s] else -1:>8d}" for s in (1, 2, 6, 7, 3, 4, 5)))
 
 if __name__ == "__main__":
     a = sys.argv[1:]
