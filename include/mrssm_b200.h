@@ -236,6 +236,9 @@ typedef struct mrssm_rollout_bwd_args {
     float* d_u[MRSSM_MAX_HEADS];                /* [T,B,H]  grad wrt fc1 pre-activation (also = grad of emb_pre) */
     float* d_o[MRSSM_MAX_HEADS];                /* [T,B,2S] grad wrt fc2 output */
     float* xin;                                 /* [T,B,S+A] the masked [state,action] input, recomputed */
+    /* optional: CONTIGUOUS [H][D] copies of the belief columns of every head's fc1 (f.w1[h] with row stride D).  When all
+     * are given the weight-streaming kernel runs (weights staged through shared memory by cp.async.bulk). */
+    const float* w1_belief[MRSSM_MAX_HEADS];
 } mrssm_rollout_bwd_args;
 
 int mrssm_rollout_bwd(const mrssm_rollout_bwd_args* a, void* stream);
@@ -295,6 +298,8 @@ int mrssm_normalize_image_u8(const uint8_t* src, int64_t n, int32_t bit_depth, c
 
 /* ---- small helpers ---- */
 int mrssm_transpose(const float* src, int64_t rows, int64_t cols, int64_t src_ld, float* dst, void* stream);
+/* dst[r][c] = src[r*ld + c]: contiguous copy of a column block */
+int mrssm_copy2d(const float* src, int64_t rows, int64_t cols, int64_t ld, float* dst, void* stream);
 int mrssm_concat2(const float* a, int64_t ca, const float* b, int64_t cb, int64_t rows, float* out, void* stream);
 int mrssm_colsum_acc(const float* x, int64_t rows, int64_t cols, int64_t ld, float* out, void* stream);
 int mrssm_fill(float* p, int64_t n, float v, void* stream);

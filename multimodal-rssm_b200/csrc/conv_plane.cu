@@ -1106,8 +1106,45 @@ __global__ void import_s2d_kernel(T4 src, int n, int H, int W, int Cc, float sca
     }
 }
 
-// fold > 0: channel c of the view is channel (c % fold) of the logical tensor for c < 4*fold (space-to-depth views)
-__global__ void colsum_view_kernel(TV t, int n, int H, int W, int Cvalid, int fold, float* __restrict__ out) {
+// same, for x-contiguous sources (src.sW == 1, W even, 3 channels... any C <= 4): one thread per s2d pixel reads the 2x2
+// patch of every channel with float2 loads (a warp reads 256 contiguous bytes per row) and writes both 8-channel chunks
+__global__ void import_s2d_rows_kernel(T4 src, int n, int H, int W, int Cc, float scale, TV dst) {
+    const int H2 = (H + 1) / 2, W2 = W / 2;
+    const long long total = (long long)n * H2 * W2;
+    const float* sp0 = (const float*)src.p;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x2 = (int)(i % W2);
+        const long long t = i / W2;
+        const int y2 = (int)(t % H2), img = (int)(t / H2);
+        float f[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) f[e] = 0.f;
+        const float* sp = sp0 + img * src.sI + 2 * x2;
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+            const int y = 2 * y2 + py;
+            if (y < H) {
+                for (int c = 0; c < Cc; ++c) {
+                    const float2 v = *reinterpret_cast<const float2*>(sp + y * src.sH + (long long)c * src.sC);
+                    f[(py * 2) * Cc + c] = v.x * scale;
+                    f[(py * 2 + 1) * Cc + c] = v.y * scale;
+                }
+            }
+        }
+        bf16* dp = (bf16*)dst.p + tv_pix(dst, img, y2, x2);
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            uint4 pk;
+            __nv_bfloat162* ph = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ph[e] = __floats2bfloat162_rn(f[ch * 8 + 2 * e], f[ch * 8 + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(dp + ch * dst.sK) = pk;
+        }
+    }
+}
+
+// flat variant for tiny spatial extents (H*W < 64): one thread per (image, pixel), generic index arithmetic
+__global__ void colsum_view_flat_kernel(TV t, int n, int H, int W, int Cvalid, int fold, float* __restrict__ out) {
     const int ch = blockIdx.y;
     const long long total = (long long)n * H * W;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -1143,6 +1180,57 @@ __global__ void colsum_view_kernel(TV t, int n, int H, int W, int Cvalid, int fo
         }
     }
 }
+
+// Per-channel sums over a view.  blockIdx.y = 8-channel chunk; blocks stride over (image, parity plane) pairs and walk
+// each plane row by row (a row is a contiguous run of W*16 bytes in the planar layouts): no per-element index arithmetic.
+// fold > 0: channel c of the view is channel (c % fold) of the logical tensor for c < 4*fold (space-to-depth views)
+__global__ void colsum_view_kernel(TV t, int n, int H, int W, int Cvalid, int fold, float* __restrict__ out) {
+    const int ch = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int npar = t.par ? 4 : 1;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // one (image, parity plane) per warp at a time; lanes sweep the plane's valid pixels (rows are contiguous runs)
+    for (long long pl = (long long)blockIdx.x * nwarps + warp; pl < (long long)n * npar; pl += (long long)gridDim.x * nwarps) {
+        const int img = (int)(pl / npar), par = (int)(pl - (long long)img * npar);
+        int Hv = H, Wv = W;
+        if (t.par) {
+            Hv = (H - (par >> 1) + 1) / 2;
+            Wv = (W - (par & 1) + 1) / 2;
+        }
+        const float invW = 1.f / (float)Wv;
+        const bf16* base = (const bf16*)t.p + img * t.sI + par * t.sP + ch * t.sK;
+        const int cnt = Hv * Wv;
+#pragma unroll 4
+        for (int i = lane; i < cnt; i += 32) {
+            const int y = __float2int_rz(((float)i + 0.5f) * invW), x = i - y * Wv;
+            const uint4 pk = __ldg(reinterpret_cast<const uint4*>(base + y * t.sH + x * t.sW));
+            const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(ph[e]);
+                acc[2 * e] += f.x;
+                acc[2 * e + 1] += f.y;
+            }
+        }
+    }
+    __shared__ float red[8][8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float s = warp_sum(acc[e]);
+        if (lane == 0) red[warp][e] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float s = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
+        const int c = ch * 8 + threadIdx.x;
+        if (fold > 0) {
+            if (c < 4 * fold && c % fold < Cvalid) atomicAdd(out + c % fold, s);
+        } else if (c < Cvalid) {
+            atomicAdd(out + c, s);
+        }
+    }
+}
 }  // namespace
 
 extern "C" int mrssm_pl_import(const mrssm_t4* src, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t Cpad, float scale,
@@ -1160,7 +1248,13 @@ extern "C" int mrssm_pl_import_s2d(const mrssm_t4* src, int32_t n_img, int32_t H
     MRSSM_CHECK(src && src->ptr && dst && dst->ptr && C >= 1 && C <= 4, "pl_import_s2d: bad args (C must be <= 4)");
     const long long total = (long long)n_img * ((H + 1) / 2) * ((W + 1) / 2) * 2;
     const int blocks = (int)std::min<long long>(148 * 16, ceil_div64(total, 256));
-    import_s2d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cvt(*src), n_img, H, W, C, scale, cvt(*dst));
+    if (src->sW == 1 && W % 2 == 0 && src->sH % 2 == 0 && src->sC % 2 == 0 && src->sI % 2 == 0 && ((uintptr_t)src->ptr & 7) == 0) {
+        const long long tot2 = (long long)n_img * ((H + 1) / 2) * (W / 2);
+        const int b2 = (int)std::min<long long>(148 * 16, ceil_div64(tot2, 256));
+        import_s2d_rows_kernel<<<b2, 256, 0, (cudaStream_t)stream>>>(cvt(*src), n_img, H, W, C, scale, cvt(*dst));
+    } else {
+        import_s2d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cvt(*src), n_img, H, W, C, scale, cvt(*dst));
+    }
     MRSSM_LAUNCH_CHECK();
     return 0;
 }
@@ -1169,10 +1263,16 @@ extern "C" int mrssm_pl_colsum(const mrssm_tv* x, int32_t n_img, int32_t H, int3
                                float* out, void* stream) {
     MRSSM_CHECK(x && x->ptr && out && Cpad % 8 == 0 && Cvalid <= Cpad && (fold == 0 || 4 * fold <= Cpad), "pl_colsum: bad args");
     const int nchunk = fold > 0 ? (4 * fold + 7) / 8 : (Cvalid + 7) / 8;
-    const long long total = (long long)n_img * H * W;
-    const int bx = (int)std::max<long long>(1, std::min<long long>(ceil_div64(total, 256 * 8), std::max(1, 1184 / nchunk)));
+    const long long planes = (long long)n_img * (x->par ? 4 : 1);
+    const int bx = (int)std::max<long long>(1, std::min<long long>(ceil_div64(planes, 8), std::max(1, 1184 / nchunk)));
     dim3 grid((unsigned)bx, (unsigned)nchunk);
-    colsum_view_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cvt(*x), n_img, H, W, Cvalid, fold, out);
+    if (H * W < 64) {
+        const long long total = (long long)n_img * H * W;
+        dim3 g2((unsigned)std::max<long long>(1, std::min<long long>(ceil_div64(total, 256 * 8), std::max(1, 1184 / nchunk))), (unsigned)nchunk);
+        colsum_view_flat_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(cvt(*x), n_img, H, W, Cvalid, fold, out);
+    } else {
+        colsum_view_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cvt(*x), n_img, H, W, Cvalid, fold, out);
+    }
     MRSSM_LAUNCH_CHECK();
     return 0;
 }

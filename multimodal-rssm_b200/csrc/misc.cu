@@ -261,3 +261,21 @@ extern "C" int mrssm_normalize_image_u8(const uint8_t* src, int64_t n, int32_t b
     MRSSM_LAUNCH_CHECK();
     return 0;
 }
+
+
+namespace {
+__global__ void copy2d_kernel(const float* __restrict__ src, long long rows, long long cols, long long ld, float* __restrict__ dst) {
+    const long long total = rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cols, c = i - r * cols;
+        dst[i] = src[r * ld + c];
+    }
+}
+}  // namespace
+
+extern "C" int mrssm_copy2d(const float* src, int64_t rows, int64_t cols, int64_t ld, float* dst, void* stream) {
+    MRSSM_CHECK(src && dst && rows > 0 && cols > 0 && ld >= cols, "copy2d: bad args");
+    copy2d_kernel<<<blocks_for(rows * cols), 256, 0, (cudaStream_t)stream>>>(src, rows, cols, ld, dst);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}

@@ -487,6 +487,18 @@ int set_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
+int rollout_check(const mrssm_rollout_args* a) { return check_common(a); }
+
+int rollout_bwd_check(const mrssm_rollout_bwd_args* g) {
+    const mrssm_rollout_args* a = &g->f;
+    if (int e = check_common(a)) return e;
+    MRSSM_CHECK(a->st_x && a->st_r && a->st_z && a->st_n && a->st_ghn, "rollout_bwd: stash missing");
+    MRSSM_CHECK(g->d_xpre && g->d_gi && g->d_gh, "rollout_bwd: null grad output");
+    for (int h = 0; h <= a->n_experts; ++h)
+        MRSSM_CHECK(a->st_u[h] && g->d_u[h] && g->d_o[h] && a->ld1[h] >= a->D, "rollout_bwd: head %d buffers missing", h);
+    return 0;
+}
+
 int rollout_fwd_simt(const mrssm_rollout_args* a, cudaStream_t st) {
     if (int e = check_common(a)) return e;
     const int NH = 1 + a->n_experts;

@@ -76,7 +76,7 @@ class RolloutBwdArgs(C.Structure):
         ("g_exp_means", _vp * MAX_HEADS), ("g_exp_stds", _vp * MAX_HEADS),
         ("g_prev_state", _vp), ("g_prev_belief", _vp), ("g_actions", _vp),
         ("d_xpre", _vp), ("d_gi", _vp), ("d_gh", _vp),
-        ("d_u", _vp * MAX_HEADS), ("d_o", _vp * MAX_HEADS), ("xin", _vp)]
+        ("d_u", _vp * MAX_HEADS), ("d_o", _vp * MAX_HEADS), ("xin", _vp), ("w1_belief", _vp * MAX_HEADS)]
 
 
 class LatentArgs(C.Structure):
@@ -129,6 +129,7 @@ SYMBOLS = {
     "mrssm_clip_adam": [_vp, _vp, _vp, _vp, _i64, _i32, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp],
     "mrssm_normalize_image_u8": [_vp, _i64, _i32, _vp, C.c_uint64, _vp, _vp],
     "mrssm_transpose": [_vp, _i64, _i64, _i64, _vp, _vp],
+    "mrssm_copy2d": [_vp, _i64, _i64, _i64, _vp, _vp],
     "mrssm_concat2": [_vp, _i64, _vp, _i64, _i64, _vp, _vp],
     "mrssm_colsum_acc": [_vp, _i64, _i64, _i64, _vp, _vp],
     "mrssm_fill": [_vp, _i64, _f, _vp],

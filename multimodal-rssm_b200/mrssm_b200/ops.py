@@ -499,10 +499,18 @@ class RolloutFn(Function):
         a.nonterminals, a.eps_prior, a.eps_post = L.ptr(nonterminals), L.ptr(eps_prior), L.ptr(eps_post)
         a.w_sa, a.b_sa, a.w_ih, a.b_ih, a.w_hh, a.b_hh = (L.ptr(w_sa), L.ptr(b_sa), L.ptr(w_ih), L.ptr(b_ih),
                                                           L.ptr(w_hh), L.ptr(b_hh))
+        keep = []
         for hd in range(1 + E):
             w1, b1, w2, b2 = heads[hd]
             a.w1[hd], a.ld1[hd], a.b1[hd], a.w2[hd], a.b2[hd] = L.ptr(w1), w1.shape[1], L.ptr(b1), L.ptr(w2), L.ptr(b2)
             a.st_u[hd] = L.ptr(stash["u"][hd])
+            if w1.shape[1] == D:
+                g.w1_belief[hd] = L.ptr(w1)
+            else:                                       # contiguous copy of the belief columns for the weight streamer
+                wc = torch.empty(H, D, device=dev, dtype=torch.float32)
+                L.call("mrssm_copy2d", L.ptr(w1), H, D, w1.shape[1], L.ptr(wc))
+                keep.append(wc)
+                g.w1_belief[hd] = L.ptr(wc)
         if observe:
             spec.table.fill(a)
         a.beliefs, a.prior_states, a.prior_means, a.prior_stds = [L.ptr(t) for t in outs[:4]]
@@ -524,6 +532,7 @@ class RolloutFn(Function):
         for hd in range(1 + E):
             g.d_u[hd], g.d_o[hd] = L.ptr(d_u[hd]), L.ptr(d_o[hd])
         L.call("mrssm_rollout_bwd", C.byref(g))
+        del keep
 
         # deferred, time-parallel weight gradients
         beliefs = outs[0]
