@@ -11,7 +11,7 @@
 namespace {
 
 constexpr int NT = 256;
-constexpr int RING = 3;
+constexpr int RING_FWD = 4, RING_BWD = 3;   // ring slots (RING-1 tiles in flight): as many as shared memory allows
 constexpr int TILE_FLOATS = 9600;          // 38 400 B per ring slot
 constexpr int MAX_TILES = 96;
 constexpr int FC1_PER_THREAD = 4;          // ceil(NH*H / NT) <= 4
@@ -65,6 +65,7 @@ __device__ __forceinline__ void load_bt(float (&v)[BT], const float* p) {
 }
 
 // The weight streamer shared by both kernels.
+template <int RING>
 struct Streamer {
     Tile* tiles;
     uint64_t* full;
@@ -83,7 +84,7 @@ struct Streamer {
     }
     // every thread: returns the slot holding tile g (and keeps two more in flight)
     __device__ __forceinline__ const float* acquire() {
-        if (threadIdx.x == 0 && g + 2 < total) issue(g + 2);      // slot (g+2)%3 was released by the barrier after tile g-1
+        if (threadIdx.x == 0 && g + RING - 1 < total) issue(g + RING - 1);      // that slot was released by the barrier after tile g-1
         const int slot = (int)(g % RING);
         mbar_wait(smem_u32(&full[slot]), (uint32_t)((g / RING) & 1));
         return ring + (size_t)slot * TILE_FLOATS;
@@ -99,6 +100,7 @@ struct Streamer {
 // ------------------------------------------------------------------------------------------------------------------
 template <int BT>
 __global__ void __launch_bounds__(NT) rollout_fwd_staged_kernel(mrssm_rollout_args a, int KC2, int KC3, int KC4) {
+    constexpr int RING = RING_FWD;
     extern __shared__ __align__(128) float smem[];
     __shared__ Tile tiles[MAX_TILES];
     __shared__ uint64_t full[RING];
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(NT) rollout_fwd_staged_kernel(mrssm_rollout_ar
     float* hprev = hA;
     float* hcur = hB;
 
-    Streamer W;
+    Streamer<RING> W;
     W.tiles = tiles; W.full = full; W.ring = ring; W.g = 0;
     if (tid == 0) {
         int n = 0;
@@ -170,8 +172,7 @@ __global__ void __launch_bounds__(NT) rollout_fwd_staged_kernel(mrssm_rollout_ar
     W.ntiles = tiles[MAX_TILES - 1].nseg;
     W.total = (long long)W.ntiles * a.T;
     if (tid == 0) {
-        W.issue(0);
-        if (W.total > 1) W.issue(1);
+        for (int i = 0; i < RING - 1 && i < W.total; ++i) W.issue(i);
     }
 
     for (int t = 0; t < a.T; ++t) {
@@ -412,6 +413,7 @@ struct BwdExtra {
 
 template <int BT>
 __global__ void __launch_bounds__(NT) rollout_bwd_staged_kernel(mrssm_rollout_bwd_args g, BwdExtra X) {
+    constexpr int RING = RING_BWD;
     extern __shared__ __align__(128) float smem[];
     __shared__ Tile tiles[MAX_TILES];
     __shared__ uint64_t full[RING];
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(NT) rollout_bwd_staged_kernel(mrssm_rollout_bw
     float* dghn = dgi + 3 * D * BT;           // [D][BT]
     float* dxp = dghn + D * BT;               // [D][BT]
 
-    Streamer W;
+    Streamer<RING> W;
     W.tiles = tiles; W.full = full; W.ring = ring; W.g = 0;
     if (tid == 0) {
         int n = 0;
@@ -478,8 +480,7 @@ __global__ void __launch_bounds__(NT) rollout_bwd_staged_kernel(mrssm_rollout_bw
     W.ntiles = tiles[MAX_TILES - 1].nseg;
     W.total = (long long)W.ntiles * a.T;
     if (tid == 0) {
-        W.issue(0);
-        if (W.total > 1) W.issue(1);
+        for (int i = 0; i < RING - 1 && i < W.total; ++i) W.issue(i);
     }
 
     for (int t = a.T - 1; t >= 0; --t) {
@@ -773,7 +774,7 @@ int rollout_fwd_staged(const mrssm_rollout_args* a, cudaStream_t st) {
     bool ok = al16(a->w_sa) && al16(a->w_ih) && al16(a->w_hh);
     for (int h = 0; h < NH; ++h) ok = ok && al16(a->w1[h]) && al16(a->w2[h]);
     if (!ok) return -1;
-    const size_t bytes = sizeof(float) * ((size_t)RING * TILE_FLOATS + (size_t)BT * ((S + A) + 3 * D + NH * H + NH * 2 * S + S));
+    const size_t bytes = sizeof(float) * ((size_t)RING_FWD * TILE_FLOATS + (size_t)BT * ((S + A) + 3 * D + NH * H + NH * 2 * S + S));
     if (bytes > 220 * 1024) return -1;
     MRSSM_CUDA(cudaFuncSetAttribute(rollout_fwd_staged_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     rollout_fwd_staged_kernel<BT><<<(a->B + BT - 1) / BT, NT, bytes, st>>>(*a, KC2, KC3, KC4);
@@ -802,7 +803,7 @@ int rollout_bwd_staged(const mrssm_rollout_bwd_args* g, const float* const* w1c,
         X.w1c[h] = w1c[h];
     }
     if (!ok) return -1;
-    const size_t bytes = sizeof(float) * ((size_t)RING * TILE_FLOATS + (size_t)BT * (D + S + NH * 2 * S + NH * H + D + 3 * D + D + D));
+    const size_t bytes = sizeof(float) * ((size_t)RING_BWD * TILE_FLOATS + (size_t)BT * (D + S + NH * 2 * S + NH * H + D + 3 * D + D + D));
     if (bytes > 220 * 1024) return -1;
     MRSSM_CUDA(cudaFuncSetAttribute(rollout_bwd_staged_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     rollout_bwd_staged_kernel<BT><<<(a->B + BT - 1) / BT, NT, bytes, st>>>(*g, X);

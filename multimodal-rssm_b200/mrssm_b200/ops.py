@@ -534,33 +534,57 @@ class RolloutFn(Function):
         L.call("mrssm_rollout_bwd", C.byref(g))
         del keep
 
-        # deferred, time-parallel weight gradients
+        # deferred, time-parallel weight gradients: dW += dY^T X over all (t,b) rows.  fp32 mode: exact CUDA-core GEMMs;
+        # bf16 mode: operands rounded to bf16 once, tcgen05 GEMMs with fp32 accumulation into the fp32 master gradient.
         beliefs = outs[0]
-        dense_wgrad(L.ptr(d_xpre), D, L.ptr(xin), S + A, R, D, S + A, L.ptr(grad_buf(w_sa)), S + A, L.ptr(grad_buf(b_sa)))
-        dense_wgrad(L.ptr(d_gi), 3 * D, L.ptr(stash["x"]), D, R, 3 * D, D, L.ptr(grad_buf(w_ih)), D, L.ptr(grad_buf(b_ih)))
+        tc = bf16_mode()
+        b16 = {}
+
+        def as_bf16(t, cols):
+            key = t.data_ptr()
+            if key not in b16:
+                rows = t.numel() // cols
+                b16[key] = pl_import(L.nhwc(t, 1, 1, cols), rows, 1, 1, cols, pad8(cols), L.NHWC, dev)[0]
+            return b16[key]
+
+        def wgrad(dy, N, x, K, rows, gw_ptr, ld, gb, dy_row0=0, x_row0=0):
+            if not tc:
+                dense_wgrad(_off(dy, dy_row0 * N), N, _off(x, x_row0 * K), K, rows, N, K, gw_ptr, ld,
+                            None if gb is None else L.ptr(gb))
+                return
+            Np, Kp = pad8(N), pad8(K)
+            dyb, xb = as_bf16(dy, N), as_bf16(x, K)
+            tc_conv_wgrad((rows, 1, 1, Kp, 1, 1, Np, 1), L.T4(xb.data_ptr() + 2 * x_row0 * Kp, Kp, 0, 0, 1),
+                          L.T4(dyb.data_ptr() + 2 * dy_row0 * Np, Np, 0, 0, 1), gw_ptr, ld, 1, N, K)
+            if gb is not None:
+                _colsum(_off(dy, dy_row0 * N), rows, N, gb)
+
+        wgrad(d_xpre, D, xin, S + A, R, L.ptr(grad_buf(w_sa)), S + A, grad_buf(b_sa))
+        wgrad(d_gi, 3 * D, stash["x"], D, R, L.ptr(grad_buf(w_ih)), D, grad_buf(b_ih))
         gwhh = grad_buf(w_hh)
-        dense_wgrad(L.ptr(d_gh), 3 * D, L.ptr(prev_belief), D, B, 3 * D, D, L.ptr(gwhh), D, L.ptr(grad_buf(b_hh)))
+        wgrad(d_gh, 3 * D, prev_belief, D, B, L.ptr(gwhh), D, grad_buf(b_hh))
         if T > 1:
-            dense_wgrad(_off(d_gh, B * 3 * D), 3 * D, L.ptr(beliefs), D, R - B, 3 * D, D, L.ptr(gwhh), D, None)
+            wgrad(d_gh, 3 * D, beliefs, D, R - B, L.ptr(gwhh), D, None, dy_row0=B)
             _colsum(_off(d_gh, B * 3 * D), R - B, 3 * D, grad_buf(b_hh))
         g_embs = []
         ei = 0
         for hd in range(1 + E):
             w1, b1, w2, b2 = heads[hd]
             ld = w1.shape[1]
-            dense_wgrad(L.ptr(d_o[hd]), 2 * S, L.ptr(stash["u"][hd]), H, R, 2 * S, H, L.ptr(grad_buf(w2)), H, L.ptr(grad_buf(b2)))
+            wgrad(d_o[hd], 2 * S, stash["u"][hd], H, R, L.ptr(grad_buf(w2)), H, grad_buf(b2))
             gw1 = grad_buf(w1)
-            dense_wgrad(L.ptr(d_u[hd]), H, L.ptr(beliefs), D, R, H, D, L.ptr(gw1), ld, L.ptr(grad_buf(b1)))
+            wgrad(d_u[hd], H, beliefs, D, R, L.ptr(gw1), ld, grad_buf(b1))
             if hd > 0 and spec.expert_has_emb[hd - 1]:
                 emb = embs[ei]
                 Em = emb.shape[-1]
-                dense_wgrad(L.ptr(d_u[hd]), H, L.ptr(emb), Em, R, H, Em, _off(gw1, D), ld, None)
+                wgrad(d_u[hd], H, emb, Em, R, _off(gw1, D), ld, None)
                 ge = None
                 if ctx.needs_input_grad[9 + ei]:
                     ge = torch.empty_like(emb)
                     dense_dgrad(L.ptr(d_u[hd]), H, R, H, _off(w1, D), ld, Em, L.ptr(ge), Em)
                 g_embs.append(ge)
                 ei += 1
+        del b16
         return (None, None, None, g_prev_state, g_actions, g_prev_belief, None, None, None, *g_embs,
                 *([None] * len(params)))
 
