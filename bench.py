@@ -242,6 +242,17 @@ def profile_one_step(model, D):
     return agg
 
 
+def measured_traffic(key):
+    """DRAM bytes per launch of a kernel from the committed `ncu --set full` capture (profiles/r01_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f)
+    e = t.get("kernels", {}).get(key)
+    return None if e is None else e.get("dram_bytes_per_launch")
+
+
 def roofline_of(key, d, pk, total_ms):
     ms = d["ms"] / d["n"]
     flops, byts = d["flops"] / d["n"], d["bytes"] / d["n"]
@@ -253,7 +264,7 @@ def roofline_of(key, d, pk, total_ms):
     else:
         ach = byts / (ms * 1e-3) / 1e9
         out = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
-    out.update({"traffic": None, "kernel": key, "launch_ms": ms, "launches_per_step": d["n"],
+    out.update({"traffic": measured_traffic(key), "kernel": key, "launch_ms": ms, "launches_per_step": d["n"],
                 "share_of_step": d["ms"] / total_ms, "peak_source": pk["src"],
                 "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": byts})
     return out
@@ -314,8 +325,7 @@ def run_ours(args):
     total_ms = sum(d["ms"] for d in agg.values())
     dom_key = max(agg, key=lambda k: agg[k]["ms"])
     roof = roofline_of(dom_key, agg[dom_key], pk, total_ms)
-    rk = "rollout_fwd:observe"
-    rollout_roof = roofline_of(rk, agg[rk], pk, total_ms) if rk in agg else None
+    rollout_roof = {k: roofline_of(k, agg[k], pk, total_ms) for k in ("rollout_fwd:observe", "rollout_bwd:observe") if k in agg}
     top = sorted(((k, d["ms"], d["n"]) for k, d in agg.items()), key=lambda x: -x[1])[:60]
 
     cpu = None

@@ -531,7 +531,17 @@ class RolloutFn(Function):
         g.d_xpre, g.d_gi, g.d_gh, g.xin = L.ptr(d_xpre), L.ptr(d_gi), L.ptr(d_gh), L.ptr(xin)
         for hd in range(1 + E):
             g.d_u[hd], g.d_o[hd] = L.ptr(d_u[hd]), L.ptr(d_o[hd])
-        L.call("mrssm_rollout_bwd", C.byref(g))
+        work = None
+        if L.profile is not None:
+            # HBM bytes per (b,t) of the BPTT kernel: forward outputs and stash read back, upstream gradients read,
+            # pre-activation gradients written (the deferred weight-gradient GEMMs consume them), fp32.
+            NHh = 1 + E
+            rd = (1 + 2 + 2 * E) * S + 5 * D + NHh * H + D + (D + 6 * S + 2 * E * S) + 2 * S + A + 1
+            wr = 7 * D + NHh * H + NHh * 2 * S + (S + A) + A
+            n_w = sum(p.numel() for p in params)
+            macs = (S + A) * D + 6 * D * D + 2 * NHh * (D * H + H * 2 * S) - NHh * D * H      # dgrad GEMVs of one step
+            work = dict(bytes=4.0 * (rd + wr) * T * B + 4.0 * n_w, flops=2.0 * macs * T * B)
+        L.call("mrssm_rollout_bwd", C.byref(g), tag="observe" if observe else "imagine", work=work)
         del keep
 
         # deferred, time-parallel weight gradients: dW += dY^T X over all (t,b) rows.  fp32 mode: exact CUDA-core GEMMs;
