@@ -189,6 +189,27 @@ int make_w_map(CUtensorMap* m, const void* base, long long K_total, long long N_
     return 0;
 }
 
+}  // namespace
+
+// bf16 row-major [outer][inner] matrix, box {box_inner, box_outer}, 128B swizzle (used by dense_tc.cu as well)
+int mrssm_tma_map_2d_sw128(void* map, const void* base, long long inner, long long outer, long long row_bytes, int box_inner, int box_outer) {
+    EncodeTiledFn enc = get_encode();
+    MRSSM_CHECK(enc, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    cuuint32_t es[2] = {1, 1};
+    MRSSM_CHECK(row_bytes % 16 == 0 && ((uintptr_t)base & 15) == 0 && box_inner * 2 == 128 && box_outer <= 256,
+                "tma_map_2d: matrix not TMA-addressable (inner %lld outer %lld row bytes %lld box %d %d)", inner, outer, row_bytes, box_inner, box_outer);
+    CUresult r = enc((CUtensorMap*)map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MRSSM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d) failed: %d (inner %lld outer %lld row bytes %lld box %d %d)", (int)r, inner, outer,
+                row_bytes, box_inner, box_outer);
+    return 0;
+}
+
+namespace {
+
 // ---------------------------------------------------------------------------------------------------
 // forward-type kernel (down / up)
 // ---------------------------------------------------------------------------------------------------

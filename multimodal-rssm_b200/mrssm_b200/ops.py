@@ -424,7 +424,15 @@ class RolloutFn(Function):
                 Em = emb.shape[-1]
                 assert ld == D + Em, (ld, D, Em)
                 pre = torch.empty(T, B, H, device=dev, dtype=torch.float32)
-                dense_fwd(L.ptr(emb), Em, T * B, Em, _off(w1, D), ld, H, L.ptr(b1), 0, L.ptr(pre), H)
+                if bf16_mode() and Em >= 64:
+                    # hoisted embedding half of fc1 as a tcgen05 GEMM: bf16 operands, fp32 accumulate and output
+                    Emp, Hp = pad8(Em), pad16(H)
+                    eb = pl_import(L.nhwc(emb, 1, 1, Em), T * B, 1, 1, Em, Emp, L.NHWC, dev)[0]
+                    tc_conv_down((T * B, 1, 1, Emp, 1, 1, Hp, 1), L.T4(eb.data_ptr(), Emp, 0, 0, 1), L.nhwc(pre, 1, 1, H),
+                                 packed_cols(w1, D, Em, 0), b1, H, out_f32=1, valid=(H, Em))
+                    del eb
+                else:
+                    dense_fwd(L.ptr(emb), Em, T * B, Em, _off(w1, D), ld, H, L.ptr(b1), 0, L.ptr(pre), H)
                 emb_pre[hd] = pre
                 a.emb_pre[hd] = L.ptr(pre)
                 a.b1[hd] = None
@@ -591,7 +599,12 @@ class RolloutFn(Function):
                 ge = None
                 if ctx.needs_input_grad[9 + ei]:
                     ge = torch.empty_like(emb)
-                    dense_dgrad(L.ptr(d_u[hd]), H, R, H, _off(w1, D), ld, Em, L.ptr(ge), Em)
+                    if tc and Em >= 64:
+                        Emp, Hp = pad8(Em), pad8(H)
+                        tc_conv_up((R, 1, 1, Emp, 1, 1, Hp, 1), L.nhwc(ge, 1, 1, Em), L.T4(as_bf16(d_u[hd], H).data_ptr(), Hp, 0, 0, 1),
+                                   packed_cols(w1, D, Em, 1), None, Em, out_f32=1, valid=(H, Em))
+                    else:
+                        dense_dgrad(L.ptr(d_u[hd]), H, R, H, _off(w1, D), ld, Em, L.ptr(ge), Em)
                 g_embs.append(ge)
                 ei += 1
         del b16
@@ -875,6 +888,26 @@ def packed(w, mode, Cs_pad, Cl_pad):
     if hit is None or hit[0] != ver:
         w4 = w if w.dim() == 4 else w.reshape(w.shape[0], w.shape[1], 1, 1)
         hit = (ver, tc_pack_weight(w4.detach(), mode, Cs_pad, Cl_pad))
+        _wcache[key] = hit
+    return hit[1]
+
+
+def packed_cols(w, col0, ncols, mode):
+    """Cached tcgen05 packing of the column block w[:, col0:col0+ncols] of a Linear weight [out, in] (mode 0: y = x W^T,
+    mode 1: dx = dy W)."""
+    key = (w.data_ptr(), "cols", col0, ncols, mode)
+    ver = (_STATE["wversion"], w._version)
+    hit = _wcache.get(key)
+    if hit is None or hit[0] != ver:
+        Cs, ld = w.shape
+        Cl = ncols
+        if mode == 0:
+            Npad, Kpad, classes = pad16(Cs), pad64(pad8(Cl)), 1
+        else:
+            Npad, Kpad, classes = pad16(Cl), pad64(pad8(Cs)), 4
+        out = torch.empty(classes, Npad, Kpad, device=w.device, dtype=torch.bfloat16)
+        L.call("mrssm_tc_pack_weight", w.data_ptr() + 4 * col0, ld, 1, Cs, Cl, pad8(Cs), pad8(Cl), 1, mode, Npad, Kpad, L.ptr(out))
+        hit = (ver, out)
         _wcache[key] = hit
     return hit[1]
 
