@@ -147,6 +147,18 @@ typedef struct mrssm_pl_conv_args {
     const float* bias;
     float* dweight;                                /* wgrad output (accumulated), PyTorch layout */
     int64_t w_ss, w_sl;
+    /* Optional output scale (device scalar x host factor): down/up outputs and wgrad contributions are multiplied by
+     * (*scale_ptr) * scale_mul when scale_ptr != NULL.  Lets a loss gradient that is known only as a device scalar
+     * (autograd's grad_output of the scalar loss) be folded into the kernels that consume the un-scaled residual. */
+    const float* scale_ptr;
+    float scale_mul;
+    /* Fused reconstruction loss for `up` with out_f32 (observation_model.py:28-31 + base/algo.py:381-383 on the last
+     * ConvTranspose2d): when mse_target != NULL (fp32, addressed with out32's strides) the epilogue computes the residual
+     * r = recon - target, adds mse_scale * sum(r^2) to *mse_sum (atomic) and writes r as bf16 in space-to-depth form
+     * (n_out_valid <= 4 channels -> 16) into the view `large`; out32.ptr may then be NULL (no reconstruction written). */
+    const float* mse_target;
+    float* mse_sum;
+    float mse_scale;
 } mrssm_pl_conv_args;
 
 int mrssm_pl_conv_down(const mrssm_pl_conv_args* a, void* stream);
@@ -165,7 +177,7 @@ int mrssm_pl_import_s2d(const mrssm_t4* src, int32_t n_img, int32_t H, int32_t W
                         void* stream);
 /* fold > 0: the view is a space-to-depth view of a fold-channel tensor (H, W = the view's own size) */
 int mrssm_pl_colsum(const mrssm_tv* x, int32_t n_img, int32_t H, int32_t W, int32_t Cpad, int32_t Cvalid, int32_t fold,
-                    float* out, void* stream);
+                    const float* scale_ptr, float scale_mul, float* out, void* stream);
 /* host only, no GPU: format the tiling plan of a layer (op 0 down, 1 up, 2 wgrad) */
 int mrssm_pl_describe(const mrssm_pl_conv_args* a, int32_t op, char* buf, int32_t buflen);
 /* bring-up switches (descriptor-field variants); 0 = production setting */

@@ -232,6 +232,12 @@ struct FwdP {
     TV out, mask;               // bf16 output / act'-mask views (indexed at the output pixel)
     T4 out32;                   // fp32 output (F32 kernels)
     const float* bias;
+    const float* scale_ptr;     // optional output scale: (*scale_ptr) * scale_mul
+    float scale_mul;
+    const float* mse_target;    // fused MSE (up, F32): residual vs target -> *mse_sum and bf16 space-to-depth residual in `out`
+    float* mse_sum;
+    float mse_scale;
+    int mse_vec;                // target rows are x-contiguous and 8-byte aligned: float2 loads
 };
 #define PROF(slot) do { if (P.prof && lit < 16) P.prof[((long long)blockIdx.x * 16 + lit) * 8 + (slot)] = clock64(); } while (0)
 
@@ -265,7 +271,8 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 
 // bias + activation + act'-mask + store of 8 consecutive output channels of one pixel
 template <bool F32>
-__device__ __forceinline__ void epi_store8(const FwdP& P, const float* v, const float* bias_s, int cl0, long long o_off, long long m_off) {
+__device__ __forceinline__ void epi_store8(const FwdP& P, const float* v, const float* bias_s, int cl0, long long o_off, long long m_off,
+                                           float oscale) {
     const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cl0), b1 = *reinterpret_cast<const float4*>(bias_s + cl0 + 4);
     float x[8] = {v[0] + b0.x, v[1] + b0.y, v[2] + b0.z, v[3] + b0.w, v[4] + b1.x, v[5] + b1.y, v[6] + b1.z, v[7] + b1.w};
     if (P.act == MRSSM_ACT_RELU) {
@@ -285,6 +292,8 @@ __device__ __forceinline__ void epi_store8(const FwdP& P, const float* v, const 
             x[2 * e + 1] *= act_grad_from_out(m.y, P.mask_mode);
         }
     }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] *= oscale;
     if (F32) {
         float* op = (float*)P.out32.p + o_off;
 #pragma unroll
@@ -296,6 +305,62 @@ __device__ __forceinline__ void epi_store8(const FwdP& P, const float* v, const 
 #pragma unroll
         for (int e = 0; e < 4; ++e) ph[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
         *reinterpret_cast<uint4*>((bf16*)P.out.p + o_off + (cl0 >> 3) * P.out.sK) = pk;
+    }
+}
+
+// Fused reconstruction loss for one output row of the last ConvTranspose2d (columns = 4 parity classes x 8, NV real
+// channels): residual vs target, sum of squares, optional reconstruction store, bf16 space-to-depth residual store.
+// NV is a template parameter so that every register-array index is static.
+template <int NV>
+__device__ __forceinline__ void mse_row(const FwdP& P, const float (&v)[32], const float* bias_s, int img, int y, int x, float& mse_acc) {
+    const float* tg = P.mse_target + img * P.out32.sI;
+    float* rc = P.out32.p ? (float*)P.out32.p + img * P.out32.sI : nullptr;
+    float tv[4][NV];
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+        const int yy = 2 * y + py;
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+            tv[py * 2][c] = tv[py * 2 + 1][c] = 0.f;
+            if (yy < P.Ho) {
+                const float* tp = tg + yy * P.out32.sH + (long long)c * P.out32.sC + 2 * x * P.out32.sW;
+                if (P.mse_vec) {           // x-contiguous target, even width: one 8-byte load covers both column parities
+                    const float2 t2 = __ldg(reinterpret_cast<const float2*>(tp));
+                    tv[py * 2][c] = t2.x;
+                    tv[py * 2 + 1][c] = t2.y;
+                } else {
+                    tv[py * 2][c] = __ldg(tp);
+                    if (2 * x + 1 < P.Wo) tv[py * 2 + 1][c] = __ldg(tp + P.out32.sW);
+                }
+            }
+        }
+    }
+    float r16[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) r16[e] = 0.f;
+#pragma unroll
+    for (int cls = 0; cls < 4; ++cls) {
+        const int yy = 2 * y + (cls >> 1), xx = 2 * x + (cls & 1);
+        const bool ok = yy < P.Ho && xx < P.Wo;
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+            float val = v[cls * 8 + c] + bias_s[c];
+            if (P.act == MRSSM_ACT_RELU) val = fmaxf(val, 0.f);
+            else if (P.act == MRSSM_ACT_ELU) val = val > 0.f ? val : expm1f(val);
+            const float res = ok ? val - tv[cls][c] : 0.f;
+            if (ok && rc) rc[yy * P.out32.sH + xx * P.out32.sW + (long long)c * P.out32.sC] = val;
+            mse_acc = fmaf(res, res, mse_acc);
+            r16[cls * NV + c] = res;
+        }
+    }
+    bf16* dp = (bf16*)P.out.p + tv_pix(P.out, img, y, x);
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        uint4 pk;
+        __nv_bfloat162* ph = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ph[e] = __floats2bfloat162_rn(r16[ch * 8 + 2 * e], r16[ch * 8 + 2 * e + 1]);
+        *reinterpret_cast<uint4*>(dp + ch * P.out.sK) = pk;
     }
 }
 
@@ -499,9 +564,12 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         // Four warps share each TMEM lane quarter.  A pass is cut into items (128-row block, column part); the
         // warps of a quarter take items round-robin.
         const int e = warp - 4, q = e & 3, part = e >> 2;
-        const int ncp = (P.BN % 64 == 0) ? 4 : ((P.BN % 32 == 0) ? 2 : 1);      // column parts per block
+        const bool mse = F32 && OP == OP_UP && P.mse_target != nullptr;       // fused reconstruction loss: whole rows per warp
+        const int ncp = mse ? 1 : ((P.BN % 64 == 0) ? 4 : ((P.BN % 32 == 0) ? 2 : 1));      // column parts per block
         const int ncols = P.BN / ncp;
         const int IP = P.BY * P.BX;
+        const float oscale = P.scale_ptr ? __ldg(P.scale_ptr) * P.scale_mul : 1.f;
+        float mse_acc = 0.f;
         const float inv_IP = 1.f / (float)IP, inv_BX = 1.f / (float)P.BX;
         uint32_t ccnt = 0;
         int lit = 0;
@@ -534,6 +602,22 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                         if (P.mask_mode) m_base = tv_pix(P.mask, img, y, x);
                     }
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * P.set_cols + mb * P.BN + col0);
+                    if (mse) {
+                        // columns = (parity class, channel): exactly the space-to-depth pixel (y, x) of the residual
+                        float v[32];
+                        tmem_ld16_nowait(taddr, v);
+                        if (P.BN > 16) tmem_ld16_nowait(taddr + 16, v + 16);
+                        tmem_wait_ld();
+                        if (row_ok) {
+                            switch (P.n_valid) {
+                                case 1: mse_row<1>(P, v, bias_s, img, y, x, mse_acc); break;
+                                case 2: mse_row<2>(P, v, bias_s, img, y, x, mse_acc); break;
+                                case 3: mse_row<3>(P, v, bias_s, img, y, x, mse_acc); break;
+                                default: mse_row<4>(P, v, bias_s, img, y, x, mse_acc); break;
+                            }
+                        }
+                        continue;
+                    }
                     for (int c0 = 0; c0 < ncols; c0 += 32) {
                         float v[32];
                         const bool two = c0 + 16 < ncols;
@@ -553,7 +637,7 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                                     if (P.mask_mode) m_off = tv_pix(P.mask, img, yy, xx);
                                 }
                             }
-                            if (ok) epi_store8<F32>(P, v + 8 * h, bias_s, cl0, o_off, m_off);
+                            if (ok) epi_store8<F32>(P, v + 8 * h, bias_s, cl0, o_off, m_off, oscale);
                             cl0 += 8;
                             if (OP == OP_UP && cl0 == P.Cop) {
                                 cl0 = 0;
@@ -568,6 +652,10 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                 ++ccnt;
             }
             if (tid == 128) PROF(5);
+        }
+        if (mse) {
+            const float sacc = warp_sum(mse_acc);
+            if (lane == 0) atomicAdd(P.mse_sum, sacc * P.mse_scale);
         }
     }
     tc::tc_fence_before();
@@ -705,10 +793,20 @@ int plan_fwd(const mrssm_pl_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
     P.out = cvt(out); P.mask = cvt(a->mask); P.out32 = cvt(a->out32);
     P.bias = a->bias;
     P.prof = g_prof;
+    P.scale_ptr = a->scale_ptr; P.scale_mul = a->scale_mul;
+    P.mse_target = a->mse_target; P.mse_sum = a->mse_sum; P.mse_scale = a->mse_scale;
+    if (P.mse_target) {
+        MRSSM_CHECK(op == OP_UP && P.out_f32 && P.mse_sum && a->n_out_valid <= 4 && a->n_out_pad == 8 && a->large.ptr && !a->large.par,
+                    "plane up: fused MSE needs out_f32, <= 4 channels (n_out_pad 8), a sum buffer and a linear space-to-depth residual view");
+        P.out = cvt(a->large);
+        P.mse_vec = a->out32.sW == 1 && (P.Wo & 1) == 0 && a->out32.sH % 2 == 0 && a->out32.sC % 2 == 0 && a->out32.sI % 2 == 0 &&
+                    ((uintptr_t)a->mse_target & 7) == 0;
+    }
     auto vec_ok = [](const mrssm_tv& t) {
         return t.sW % 8 == 0 && t.sH % 8 == 0 && t.sI % 8 == 0 && t.sK % 8 == 0 && t.sP % 8 == 0 && ((uintptr_t)t.ptr & 15) == 0;
     };
-    MRSSM_CHECK(P.out_f32 ? a->out32.ptr != nullptr : vec_ok(out), "plane conv: bf16 output view must keep 8-channel chunks 16-byte aligned");
+    MRSSM_CHECK(P.out_f32 ? (a->out32.ptr != nullptr || P.mse_target != nullptr) : vec_ok(out),
+                "plane conv: bf16 output view must keep 8-channel chunks 16-byte aligned");
     MRSSM_CHECK(!P.mask_mode || vec_ok(a->mask), "plane conv: mask view must keep 8-channel chunks 16-byte aligned");
     return 0;
 }
@@ -802,6 +900,8 @@ struct WgP {
     int ksz, nt, Clp, Csp, N;
     int NG, gpp, n_cpass, n_mhalf;
     int NA, zero_bytes, mergedS, mergedL, s2d_cq;
+    const float* scale_ptr;
+    float scale_mul;
     int cs_valid, cl_valid;
     float* dw;
     long long w_ss, w_sl;
@@ -867,6 +967,7 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
         }
         __syncwarp();
     } else if (warp == 1) {
+        // (two issuing warps do not help: profiles/micro/umma_rate.cu pattern 6 — the ~46-cycle floor per MMA is not per thread)
         if (lane == 0) {
             const uint32_t idesc = tc::idesc_bf16(128, P.N, 1, 1);
             // MN-major un-swizzled descriptors: LBO = 128 B between 8-pixel (K) groups, SBO = plane stride between 8-channel chunks
@@ -905,6 +1006,7 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
         tc::mbar_wait(tc::smem_u32(&acc_full), 0);
         tc::tc_fence_after();
         const int cs = mhalf * 128 + q * 32 + lane;
+        const float oscale = P.scale_ptr ? __ldg(P.scale_ptr) * P.scale_mul : 1.f;
         for (int gi = 0; gi < ng; ++gi) {
             const int g = g0 + gi, kh = g / P.nt, b = g - kh * P.nt;
             for (int c0 = 0; c0 < P.N; c0 += 16) {
@@ -929,7 +1031,7 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
                         kw = 2 * b + px;
                         ok = true;
                     }
-                    if (ok && cl < P.cl_valid && kw < P.ksz) atomicAdd(P.dw + cs * P.w_ss + cl * P.w_sl + kh2 * P.ksz + kw, v[e]);
+                    if (ok && cl < P.cl_valid && kw < P.ksz) atomicAdd(P.dw + cs * P.w_ss + cl * P.w_sl + kh2 * P.ksz + kw, v[e] * oscale);
                 }
             }
         }
@@ -1007,6 +1109,7 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
     splits = std::max(1, std::min(n_tiles, 148 / ypass));      // the whole grid is one wave (one CTA per SM)
     P.cs_valid = a->cs_valid; P.cl_valid = a->cl_valid;
     P.dw = a->dweight; P.w_ss = a->w_ss; P.w_sl = a->w_sl;
+    P.scale_ptr = a->scale_ptr; P.scale_mul = a->scale_mul;
     return 0;
 }
 
@@ -1165,7 +1268,8 @@ __global__ void import_s2d_rows_kernel(T4 src, int n, int H, int W, int Cc, floa
 }
 
 // flat variant for tiny spatial extents (H*W < 64): one thread per (image, pixel), generic index arithmetic
-__global__ void colsum_view_flat_kernel(TV t, int n, int H, int W, int Cvalid, int fold, float* __restrict__ out) {
+__global__ void colsum_view_flat_kernel(TV t, int n, int H, int W, int Cvalid, int fold, const float* scale_ptr, float scale_mul,
+                                        float* __restrict__ out) {
     const int ch = blockIdx.y;
     const long long total = (long long)n * H * W;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -1193,6 +1297,7 @@ __global__ void colsum_view_flat_kernel(TV t, int n, int H, int W, int Cvalid, i
     if (threadIdx.x < 8) {
         float s = 0.f;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
+        if (scale_ptr) s *= __ldg(scale_ptr) * scale_mul;
         const int c = ch * 8 + threadIdx.x;
         if (fold > 0) {
             if (c < 4 * fold && c % fold < Cvalid) atomicAdd(out + c % fold, s);
@@ -1205,7 +1310,8 @@ __global__ void colsum_view_flat_kernel(TV t, int n, int H, int W, int Cvalid, i
 // Per-channel sums over a view.  blockIdx.y = 8-channel chunk; blocks stride over (image, parity plane) pairs and walk
 // each plane row by row (a row is a contiguous run of W*16 bytes in the planar layouts): no per-element index arithmetic.
 // fold > 0: channel c of the view is channel (c % fold) of the logical tensor for c < 4*fold (space-to-depth views)
-__global__ void colsum_view_kernel(TV t, int n, int H, int W, int Cvalid, int fold, float* __restrict__ out) {
+__global__ void colsum_view_kernel(TV t, int n, int H, int W, int Cvalid, int fold, const float* scale_ptr, float scale_mul,
+                                   float* __restrict__ out) {
     const int ch = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int npar = t.par ? 4 : 1;
@@ -1244,6 +1350,7 @@ __global__ void colsum_view_kernel(TV t, int n, int H, int W, int Cvalid, int fo
     if (threadIdx.x < 8) {
         float s = 0.f;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
+        if (scale_ptr) s *= __ldg(scale_ptr) * scale_mul;
         const int c = ch * 8 + threadIdx.x;
         if (fold > 0) {
             if (c < 4 * fold && c % fold < Cvalid) atomicAdd(out + c % fold, s);
@@ -1281,7 +1388,7 @@ extern "C" int mrssm_pl_import_s2d(const mrssm_t4* src, int32_t n_img, int32_t H
 }
 
 extern "C" int mrssm_pl_colsum(const mrssm_tv* x, int32_t n_img, int32_t H, int32_t W, int32_t Cpad, int32_t Cvalid, int32_t fold,
-                               float* out, void* stream) {
+                               const float* scale_ptr, float scale_mul, float* out, void* stream) {
     MRSSM_CHECK(x && x->ptr && out && Cpad % 8 == 0 && Cvalid <= Cpad && (fold == 0 || 4 * fold <= Cpad), "pl_colsum: bad args");
     const int nchunk = fold > 0 ? (4 * fold + 7) / 8 : (Cvalid + 7) / 8;
     const long long planes = (long long)n_img * (x->par ? 4 : 1);
@@ -1290,9 +1397,9 @@ extern "C" int mrssm_pl_colsum(const mrssm_tv* x, int32_t n_img, int32_t H, int3
     if (H * W < 64) {
         const long long total = (long long)n_img * H * W;
         dim3 g2((unsigned)std::max<long long>(1, std::min<long long>(ceil_div64(total, 256 * 8), std::max(1, 1184 / nchunk))), (unsigned)nchunk);
-        colsum_view_flat_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(cvt(*x), n_img, H, W, Cvalid, fold, out);
+        colsum_view_flat_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(cvt(*x), n_img, H, W, Cvalid, fold, scale_ptr, scale_mul, out);
     } else {
-        colsum_view_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cvt(*x), n_img, H, W, Cvalid, fold, out);
+        colsum_view_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cvt(*x), n_img, H, W, Cvalid, fold, scale_ptr, scale_mul, out);
     }
     MRSSM_LAUNCH_CHECK();
     return 0;

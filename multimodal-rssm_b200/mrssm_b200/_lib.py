@@ -50,7 +50,8 @@ class PlConvArgs(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_img", "Hl", "Wl", "Cl", "Hs", "Ws", "Cs", "ksz", "act", "mask_mode", "out_f32",
                                          "n_out_pad", "n_out_valid", "cs_valid", "cl_valid", "s2d_cq")] + [
         ("large", TV), ("small", TV), ("mask", TV), ("out32", T4), ("wpacked", _vp), ("bias", _vp), ("dweight", _vp),
-        ("w_ss", C.c_int64), ("w_sl", C.c_int64)]
+        ("w_ss", C.c_int64), ("w_sl", C.c_int64), ("scale_ptr", _vp), ("scale_mul", C.c_float),
+        ("mse_target", _vp), ("mse_sum", _vp), ("mse_scale", C.c_float)]
 
 
 class RolloutArgs(C.Structure):
@@ -112,7 +113,7 @@ SYMBOLS = {
     "mrssm_pl_conv_up": [C.POINTER(PlConvArgs), _vp],
     "mrssm_pl_conv_wgrad": [C.POINTER(PlConvArgs), _vp],
     "mrssm_pl_import": [C.POINTER(T4), _i32, _i32, _i32, _i32, _i32, _f, C.POINTER(TV), _vp],
-    "mrssm_pl_colsum": [C.POINTER(TV), _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
+    "mrssm_pl_colsum": [C.POINTER(TV), _i32, _i32, _i32, _i32, _i32, _i32, _vp, _f, _vp, _vp],
     "mrssm_pl_packed_shape": [_i32, _i32, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32)],
     "mrssm_pl_pack_weight": [_vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
     "mrssm_pl_import_s2d": [C.POINTER(T4), _i32, _i32, _i32, _i32, _f, C.POINTER(TV), _vp],

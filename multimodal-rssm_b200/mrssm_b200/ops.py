@@ -803,18 +803,24 @@ def pl_pack_weight(w, op, Cs_pad, Cl_pad, s2d_cq=0):
 
 
 def _pl_args(geom, large=None, small=None, mask=None, act=0, mask_mode=0, out32=None, n_out_pad=0, n_out_valid=0,
-             cs_valid=0, cl_valid=0, wpacked=None, bias=None, dweight=None, w_ss=0, w_sl=0, s2d_cq=0):
-    return L.PlConvArgs(*geom, act, mask_mode, int(out32 is not None), n_out_pad, n_out_valid, cs_valid, cl_valid, s2d_cq,
-                        large or L.NO_TV, small or L.NO_TV, mask or L.NO_TV, out32 or L.NO_T4, wpacked, bias, dweight, w_ss, w_sl)
+             cs_valid=0, cl_valid=0, wpacked=None, bias=None, dweight=None, w_ss=0, w_sl=0, s2d_cq=0, scale=None, mse=None):
+    """scale: (device float tensor, host factor) folded into the outputs; mse: (target fp32 tensor, sum buffer, factor)."""
+    sp, sm = (L.ptr(scale[0]), float(scale[1])) if scale is not None else (None, 1.0)
+    mt, ms, mf = (L.ptr(mse[0]), L.ptr(mse[1]), float(mse[2])) if mse is not None else (None, None, 0.0)
+    f32 = int(out32 is not None)
+    return L.PlConvArgs(*geom, act, mask_mode, f32, n_out_pad, n_out_valid, cs_valid, cl_valid, s2d_cq,
+                        large or L.NO_TV, small or L.NO_TV, mask or L.NO_TV, out32 or L.NO_T4, wpacked, bias, dweight, w_ss, w_sl,
+                        sp, sm, mt, ms, mf)
 
 
-def pl_conv_down(geom, large, out, wpacked, bias, n_out_valid, n_out_pad, act=0, mask=None, mask_mode=0, valid=None, s2d_cq=0):
+def pl_conv_down(geom, large, out, wpacked, bias, n_out_valid, n_out_pad, act=0, mask=None, mask_mode=0, valid=None, s2d_cq=0,
+                 scale=None):
     """large: L.TV view of the gathered tensor (parity-planar preferred; the space-to-depth view when s2d_cq);
     out: L.TV (bf16) or L.T4 (fp32, any strides)."""
     f32 = isinstance(out, L.T4)
     a = _pl_args(geom, large=large, small=None if f32 else out, mask=mask, act=act, mask_mode=mask_mode,
                  out32=out if f32 else None, n_out_pad=n_out_pad, n_out_valid=n_out_valid, wpacked=L.ptr(wpacked), bias=L.ptr(bias),
-                 s2d_cq=s2d_cq)
+                 s2d_cq=s2d_cq, scale=scale)
     tag, work = _tc_work("mrssm_pl_conv_down", geom, valid or (geom[6], geom[3]))
     L.call("mrssm_pl_conv_down", C.byref(a), tag=tag, work=work)
 
@@ -828,9 +834,20 @@ def pl_conv_up(geom, out, small, wpacked, bias, n_out_valid, n_out_pad, act=0, m
     L.call("mrssm_pl_conv_up", C.byref(a), tag=tag, work=work)
 
 
-def pl_conv_wgrad(geom, large, small, dweight_ptr, w_ss, w_sl, cs_valid, cl_valid, s2d_cq=0):
+def pl_conv_up_mse(geom, resid, small, wpacked, bias, n_out_valid, n_out_pad, target, target_t4, sum_buf, factor, recon_t4=None,
+                   valid=None):
+    """Last ConvTranspose2d + reconstruction loss in one kernel: adds factor * sum((recon - target)^2) to sum_buf[0] and writes
+    the residual as bf16 in space-to-depth form into the view `resid`; recon_t4 (fp32, target's strides) is optional."""
+    out32 = L.T4(recon_t4.ptr if recon_t4 is not None else None, target_t4.sI, target_t4.sH, target_t4.sW, target_t4.sC)
+    a = _pl_args(geom, large=resid, small=small, out32=out32, n_out_pad=n_out_pad, n_out_valid=n_out_valid, wpacked=L.ptr(wpacked),
+                 bias=L.ptr(bias), mse=(target, sum_buf, factor))
+    tag, work = _tc_work("mrssm_pl_conv_up", geom, valid or (geom[6], geom[3]))
+    L.call("mrssm_pl_conv_up", C.byref(a), tag=tag, work=work)
+
+
+def pl_conv_wgrad(geom, large, small, dweight_ptr, w_ss, w_sl, cs_valid, cl_valid, s2d_cq=0, scale=None):
     a = _pl_args(geom, large=large, small=small, cs_valid=cs_valid, cl_valid=cl_valid, dweight=dweight_ptr, w_ss=w_ss, w_sl=w_sl,
-                 s2d_cq=s2d_cq)
+                 s2d_cq=s2d_cq, scale=scale)
     tag, work = _tc_work("mrssm_pl_conv_wgrad", geom, (cs_valid, cl_valid))
     L.call("mrssm_pl_conv_wgrad", C.byref(a), tag=tag, work=work)
 
@@ -848,9 +865,10 @@ def pl_import(src_t4, n, H, W, Cc, Cp, layout, device, scale=1.0):
     return t, v
 
 
-def pl_colsum(view, n, H, W, Cp, Cvalid, out, fold=0):
+def pl_colsum(view, n, H, W, Cp, Cvalid, out, fold=0, scale=None):
     """out[c] += sum over pixels.  fold: the view is the space-to-depth view (H, W its own size) of a fold-channel tensor."""
-    L.call("mrssm_pl_colsum", C.byref(view), n, H, W, Cp, Cvalid, fold, L.ptr(out))
+    sp, sm = (L.ptr(scale[0]), float(scale[1])) if scale is not None else (None, 1.0)
+    L.call("mrssm_pl_colsum", C.byref(view), n, H, W, Cp, Cvalid, fold, sp, sm, L.ptr(out))
 
 
 def pl_import_s2d(src_t4, n, H, W, Cc, device, scale=1.0):
@@ -1001,6 +1019,12 @@ class ConvDecoderTCFn(Function):
 
     @staticmethod
     def forward(ctx, h, s, *params):
+        return ConvDecoderTCFn._forward(ctx, h, s, None, params)
+
+    @staticmethod
+    def _forward(ctx, h, s, target, params):
+        """target None: returns the fp32 NCHW reconstruction.  Otherwise (fused loss): returns sum_features mean_rows
+        (recon - target)^2 as a 0-dim tensor and keeps the bf16 residual for the backward pass."""
         h, s = _f32c(h), _f32c(s)
         R, D = h.shape
         S = s.shape[1]
@@ -1037,6 +1061,14 @@ class ConvDecoderTCFn(Function):
                 tc_conv_down((R, 1, 1, Csp, 1, 1, k * k * Clp, 1), L.nhwc(xt, 1, 1, Csp), L.nhwc(o, 1, 1, k * k * Clp), wp, b,
                              k * k * Clp, act=RELU, bias_mod=Clp, valid=(k * k * Cl, Cs))
                 acts.append((o, L.NHWC))
+            elif last and target is not None:
+                assert cq, "the fused reconstruction loss needs an image of <= 4 channels"
+                target = _f32c(target)
+                resid = new_act(R, (Hl + 1) // 2, (Wl + 1) // 2, 16, L.PLANAR, dev)
+                out = torch.zeros(1, device=dev, dtype=torch.float32)
+                pl_conv_up_mse(geom, resid[1], L.tv(xt, xl, Hs, Ws, Csp), packed_pl(Wt, UP, Csp, Clp), b, Cl, Clp, target,
+                               L.nchw(target, Hl, Wl, Cl), out, 1.0 / R, valid=(Cs, Cl))
+                acts.append((resid[0], "s2d"))
             elif last:
                 out = torch.empty(R, Cl, Hl, Wl, device=dev, dtype=torch.float32)
                 pl_conv_up(geom, L.nchw(out, Hl, Wl, Cl), L.tv(xt, xl, Hs, Ws, Csp), packed_pl(Wt, UP, Csp, Clp), b, Cl, Clp,
@@ -1049,11 +1081,16 @@ class ConvDecoderTCFn(Function):
             Hs, Ws, Csp = Hl, Wl, Clp
         ctx.geoms, ctx.params, ctx.dims = geoms, params, (R, D, S, Em, Kp)
         ctx.layouts = [l for _, l in acts]
+        ctx.fused = target is not None
         ctx.save_for_backward(hsb, *[t for t, _ in acts])
-        return out
+        return out.reshape(()) if target is not None else out
 
     @staticmethod
     def backward(ctx, g):
+        return ConvDecoderTCFn._backward(ctx, g, 2)
+
+    @staticmethod
+    def _backward(ctx, g, n_lead):
         geoms, params, layouts = ctx.geoms, ctx.params, ctx.layouts
         R, D, S, Em, Kp = ctx.dims
         hsb, *acts = ctx.saved_tensors
@@ -1062,7 +1099,13 @@ class ConvDecoderTCFn(Function):
         n_layers = len(geoms)
         g = _f32c(g)
         (_, Hl, Wl, Clp, _, _, _, _), _, Cl, cq_last = geoms[-1]
-        if cq_last:
+        scale = None
+        if ctx.fused:
+            # the saved residual r = recon - target; dLoss/drecon = g * 2 r / R, folded into the kernels that consume r
+            gb, gl = acts.pop(), "s2d"
+            layouts = layouts[:-1]
+            scale = (g.reshape(1), 2.0 / R)
+        elif cq_last:
             gb, gl = pl_import_s2d(L.nchw(g, Hl, Wl, Cl), R, Hl, Wl, Cl, dev)[0], "s2d"
         else:
             gb, gl = pl_import(L.nchw(g, Hl, Wl, Cl), R, Hl, Wl, Cl, Clp, L.PARITY, dev)[0], L.PARITY
@@ -1089,13 +1132,15 @@ class ConvDecoderTCFn(Function):
                 # the gradient w.r.t. this layer's input feeds a dense layer (NHWC) when the layer below sits on the 1x1 map
                 nl = L.NHWC if (i > 0 and geoms[i - 1][0][4] == 1) or i == 0 else L.PARITY
                 gxt, gxv = new_act(R, Hs, Ws, Csp, nl, dev)
-                pl_conv_wgrad(gg, gv, xv, L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl, s2d_cq=cq if s2d else 0)
+                sc = scale if i == n_layers - 1 else None          # only the first consumer of the raw residual applies the scale
+                pl_conv_wgrad(gg, gv, xv, L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl, s2d_cq=cq if s2d else 0, scale=sc)
                 pl_conv_down(gg, gv, gxv, packed_pl(Wt, DOWN_S2D if s2d else DOWN, Csp, gg[3], cq if s2d else 0), None, Cs, Csp,
-                             mask=xv if i > 0 else None, mask_mode=RELU if i > 0 else 0, valid=(Cs, Cl), s2d_cq=cq if s2d else 0)
+                             mask=xv if i > 0 else None, mask_mode=RELU if i > 0 else 0, valid=(Cs, Cl), s2d_cq=cq if s2d else 0,
+                             scale=sc)
                 if s2d:
-                    pl_colsum(gv, R, H2, W2, 16, Cl, grad_buf(b), fold=cq)
+                    pl_colsum(gv, R, H2, W2, 16, Cl, grad_buf(b), fold=cq, scale=sc)
                 else:
-                    pl_colsum(gv, R, Hl, Wl, Clg, Cl, grad_buf(b))
+                    pl_colsum(gv, R, Hl, Wl, Clg, Cl, grad_buf(b), scale=sc)
                 gx = gxt
             gb, gl = gx, nl
         fcw, fcb = params[0], params[1]
@@ -1108,4 +1153,19 @@ class ConvDecoderTCFn(Function):
                    valid=(Em, D + S))
         gh = ghs[:, :D].contiguous() if ctx.needs_input_grad[0] else None
         gs = ghs[:, D:].contiguous() if ctx.needs_input_grad[1] else None
-        return (gh, gs, *([None] * len(params)))
+        return (gh, gs, *([None] * (n_lead - 2)), *([None] * len(params)))
+
+
+class ConvDecoderMseTCFn(Function):
+    """Image decoder + reconstruction loss (observation_model.py:28-31 with base/algo.py:381-383) as one autograd node:
+    apply(h, s, target [R,C,H,W] fp32, *params) -> sum_features mean_rows (recon - target)^2.  The reconstruction itself is
+    never written: the last ConvTranspose2d's epilogue forms the residual, reduces the loss and stores the residual in bf16,
+    which the backward pass consumes as the image gradient (scaled by the incoming grad on the fly)."""
+
+    @staticmethod
+    def forward(ctx, h, s, target, *params):
+        return ConvDecoderTCFn._forward(ctx, h, s, target, params)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ConvDecoderTCFn._backward(ctx, g, 3)

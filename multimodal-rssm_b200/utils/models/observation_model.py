@@ -89,6 +89,17 @@ class _ConvDecoder(ObservationModel_base):
         y = fn.apply(h_t.reshape(T * B, -1), s_t.reshape(T * B, -1), *params)
         return {"loc": y.reshape(T, B, *y.shape[1:]), "scale": 1.0}
 
+    def mse_loss(self, h_t, s_t, o_t):
+        """sum_features mean_{t,b} (loc - o)^2.  bf16 mode, <= 4 image channels: decoder and loss are ONE autograd node — the
+        last ConvTranspose2d's epilogue reduces the loss and keeps the bf16 residual, the reconstruction is never written."""
+        if not (ops.bf16_mode() and o_t.shape[2] <= 4):
+            return super().mse_loss(h_t, s_t, o_t)
+        T, B = h_t.shape[:2]
+        params = [self.fc1.weight, self.fc1.bias]
+        params += [p for m in self.conv if isinstance(m, nn.ConvTranspose2d) for p in (m.weight, m.bias)]
+        return ops.ConvDecoderMseTCFn.apply(h_t.reshape(T * B, -1), s_t.reshape(T * B, -1),
+                                            o_t.reshape(T * B, *o_t.shape[2:]), *params)
+
 
 class ImageDecoder(_ConvDecoder):
     """64x64: fc -> ConvT 1024->128 k5 -> 64 k5 -> 32 k6 -> C k6, stride 2 (reference :58-105)."""

@@ -35,7 +35,7 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int amode, int bmode, int pattern, int iters, int conv, long long* out) {
+__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int amode, int bmode, int pattern, int iters, int conv, long long* out, int Mrows = 128) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_s;
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int amode, int bmod
     for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3c003c00u;
     tc::fence_proxy_async();
     if (threadIdx.x == 0) {
-        tc::mbar_init(tc::smem_u32(&bar), 1);
+        tc::mbar_init(tc::smem_u32(&bar), pattern == 6 ? 2 : 1);
         tc::fence_barrier_init();
     }
     if (threadIdx.x < 32) tc::tmem_alloc(tc::smem_u32(&tmem_s), 512);
@@ -51,13 +51,22 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int amode, int bmod
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tm = tmem_s;
+    if (pattern == 6 && threadIdx.x == 64) {   // second issuer (warp 2), accumulator 1, tight loop
+        const uint32_t idesc2 = tc::idesc_bf16(128, N, 0, 0);
+        uint64_t ad = desc_plain(smem0, 4224, 128), bd = tc::smem_desc_sw128(smem0 + 96 * 1024, 16, 1024);
+        for (int i = 0; i < iters; ++i) tc::umma_bf16(tm + 256, ad + (uint64_t)(2 * (i & 3)), bd + (uint64_t)(2 * (i & 3)), idesc2, 1);
+        tc::umma_commit(tc::smem_u32(&bar));
+    }
     if (threadIdx.x < 32 && (conv || threadIdx.x == 0)) {
         const bool leader = conv ? elect_one() : true;
-        const uint32_t idesc = tc::idesc_bf16(128, N, 0, 0);
+        const uint32_t idesc = tc::idesc_bf16(Mrows, N, 0, 0);
         const uint32_t sA = smem0, sB = smem0 + 96 * 1024;
         const uint32_t PS = 4224;      // plane stride of a typical tile (odd multiple of 128)
         long long t0 = clock64();
-        if (pattern == 5) {            // tight, converged warp, elect inside the asm
+        if (pattern == 6) {
+            uint64_t ad = desc_plain(sA, PS, 128), bd = tc::smem_desc_sw128(sB, 16, 1024);
+            for (int i = 0; i < iters; ++i) tc::umma_bf16(tm, ad + (uint64_t)(2 * (i & 3)), bd + (uint64_t)(2 * (i & 3)), idesc, 1);
+        } else if (pattern == 5) {            // tight, converged warp, elect inside the asm
             uint64_t ad = tc::smem_desc_sw128(sA, 16, 1024), bd = tc::smem_desc_sw128(sB, 16, 1024);
             if (amode == 0) ad = desc_plain(sA, PS, 128);
             for (int i = 0; i < iters; i += 8) {
@@ -109,8 +118,9 @@ int main() {
     for (int N : {32, 128, 256})
         for (int amode = 0; amode < 1; ++amode)
             for (int bmode = 1; bmode < 2; ++bmode)
-                for (int pattern = 4; pattern < 6; ++pattern) {
+                for (int pattern = 4; pattern < 7; ++pattern) {
                     if (pattern == 5 && !conv) continue;
+                    if (pattern == 6 && conv) continue;
                     rate_kernel<<<148, 128, 200 * 1024>>>(N, amode, bmode, pattern, iters, conv, d);
                     cudaError_t e = cudaDeviceSynchronize();
                     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
@@ -118,5 +128,21 @@ int main() {
                     cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
                     printf("conv=%d %3d %5d %5d %7d  %10.1f  %10.1f\n", conv, N, amode, bmode, pattern, (double)h[0] / iters, (double)h[1] / iters);
                 }
+    printf("M=64 tight loop:\n");
+    for (int N : {16, 32, 64, 128}) {
+        rate_kernel<<<148, 128, 200 * 1024>>>(N, 0, 1, 4, iters, 0, d, 64);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+        long long h[2];
+        cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        printf("M=64 N=%3d  %10.1f  %10.1f\n", N, (double)h[0] / iters, (double)h[1] / iters);
+    }
+    for (int N : {16}) {
+        rate_kernel<<<148, 128, 200 * 1024>>>(N, 0, 1, 4, iters, 0, d, 128);
+        cudaDeviceSynchronize();
+        long long h[2];
+        cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        printf("M=128 N=%3d  %10.1f  %10.1f\n", N, (double)h[0] / iters, (double)h[1] / iters);
+    }
     return 0;
 }

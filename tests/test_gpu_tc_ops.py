@@ -266,3 +266,39 @@ def test_plane_space_to_depth_source_matches_simt(g):
     acc = torch.zeros(Cl, device=DEV)
     ops.pl_colsum(lv, n, H2, H2, 16, Cl, acc, fold=Cl)
     torch.testing.assert_close(acc, large.sum(dim=(0, 1, 2)), rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("g", [(3, 64, 3, 30, 32, 6), (2, 128, 3, 62, 32, 6), (5, 14, 4, 6, 16, 4)])
+def test_plane_up_fused_mse_matches_separate_ops(g):
+    """Last ConvTranspose2d with the reconstruction loss fused in the epilogue: loss value, optional reconstruction and the
+    bf16 space-to-depth residual against the separate kernels."""
+    from mrssm_b200 import _lib as L, ops
+    n, Hl, Cl, Hs, Cs, k = g
+    gen = torch.Generator(device=DEV).manual_seed(11)
+    small = _bf16_round(torch.randn(n, Hs, Hs, Cs, device=DEV, generator=gen))
+    w = _bf16_round(torch.randn(Cs, Cl, k, k, device=DEV, generator=gen) / (Cs * k * k / 4) ** 0.5)
+    bias = torch.randn(Cl, device=DEV)
+    target = torch.randn(n, Cl, Hl, Hl, device=DEV, generator=gen)
+    Csp, Clp = ops.pad16(Cs), ops.pad8(Cl)
+    sb = ops.pl_import(L.nhwc(small, Hs, Hs, Cs), n, Hs, Hs, Cs, Csp, "planar", DEV)
+    wp = ops.pl_pack_weight(w, ops.UP, Csp, Clp)
+    gp = (n, Hl, Hl, Clp, Hs, Hs, Csp, k)
+    recon_ref = torch.empty(n, Cl, Hl, Hl, device=DEV)
+    ops.pl_conv_up(gp, L.nchw(recon_ref, Hl, Hl, Cl), sb[1], wp, bias, Cl, Clp)
+    H2 = (Hl + 1) // 2
+    for with_recon in (False, True):
+        resid = ops.new_act(n, H2, H2, 16, "planar", DEV)
+        resid[0].fill_(7.0)
+        total = torch.zeros(1, device=DEV)
+        recon = torch.zeros(n, Cl, Hl, Hl, device=DEV) if with_recon else None
+        ops.pl_conv_up_mse(gp, resid[1], sb[1], wp, bias, Cl, Clp, target, L.nchw(target, Hl, Hl, Cl), total, 1.0 / n,
+                           recon_t4=L.nchw(recon, Hl, Hl, Cl) if with_recon else None)
+        ref_loss = ((recon_ref - target) ** 2).sum() / n
+        torch.testing.assert_close(total[0], ref_loss, rtol=1e-4, atol=1e-4)
+        if with_recon:
+            torch.testing.assert_close(recon, recon_ref, rtol=0, atol=0)
+        r = export_view(resid[0], "planar", n, H2, H2, 16)
+        d = (recon_ref - target).permute(0, 2, 3, 1)
+        for par in range(4):
+            sub = d[:, par >> 1::2, par & 1::2, :]
+            torch.testing.assert_close(r[:, :sub.shape[1], :sub.shape[2], par * Cl:(par + 1) * Cl], sub, rtol=1e-2, atol=1e-2)
