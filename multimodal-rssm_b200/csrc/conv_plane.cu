@@ -618,15 +618,15 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                         }
                         continue;
                     }
-                    for (int c0 = 0; c0 < ncols; c0 += 32) {
-                        float v[32];
-                        const bool two = c0 + 16 < ncols;
+                    // 16 columns per iteration (small loop body: the 16 epilogue warps, the issuer and the producer share one
+                    // instruction cache)
+#pragma unroll 1
+                    for (int c0 = 0; c0 < ncols; c0 += 16) {
+                        float v[16];
                         tmem_ld16_nowait(taddr + c0, v);
-                        if (two) tmem_ld16_nowait(taddr + c0 + 16, v + 16);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            if (h >= 2 && !two) break;
+                        for (int h = 0; h < 2; ++h) {
                             bool ok = row_ok;
                             long long o_off = o_base, m_off = m_base;
                             if (OP == OP_UP) {
