@@ -292,8 +292,10 @@ __device__ __forceinline__ void epi_store8(const FwdP& P, const float* v, const 
             x[2 * e + 1] *= act_grad_from_out(m.y, P.mask_mode);
         }
     }
+    if (P.scale_ptr) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) x[e] *= oscale;
+        for (int e = 0; e < 8; ++e) x[e] *= oscale;
+    }
     if (F32) {
         float* op = (float*)P.out32.p + o_off;
 #pragma unroll
@@ -565,7 +567,8 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         // warps of a quarter take items round-robin.
         const int e = warp - 4, q = e & 3, part = e >> 2;
         const bool mse = F32 && OP == OP_UP && P.mse_target != nullptr;       // fused reconstruction loss: whole rows per warp
-        const int ncp = mse ? 1 : ((P.BN % 64 == 0) ? 4 : ((P.BN % 32 == 0) ? 2 : 1));      // column parts per block
+        // column parts per block: narrow outputs stay whole (the row decode is amortised over more columns)
+        const int ncp = mse ? 1 : ((P.BN % 64 == 0 && P.BN >= 128) ? 4 : ((P.BN % 32 == 0 && P.BN >= 64) ? 2 : 1));
         const int ncols = P.BN / ncp;
         const int IP = P.BY * P.BX;
         const float oscale = P.scale_ptr ? __ldg(P.scale_ptr) * P.scale_mul : 1.f;
@@ -620,6 +623,9 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                     }
                     // 16 columns per iteration (small loop body: the 16 epilogue warps, the issuer and the producer share one
                     // instruction cache)
+                    int cur_cls = -1;                 // up: pixel offsets are recomputed only when the parity class changes
+                    bool ok_c = row_ok;
+                    long long o_pix = o_base, m_pix = m_base;
 #pragma unroll 1
                     for (int c0 = 0; c0 < ncols; c0 += 16) {
                         float v[16];
@@ -627,17 +633,16 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                         tmem_wait_ld();
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            bool ok = row_ok;
-                            long long o_off = o_base, m_off = m_base;
-                            if (OP == OP_UP) {
+                            if (OP == OP_UP && cls != cur_cls) {
+                                cur_cls = cls;
                                 const int yy = 2 * y + (cls >> 1), xx = 2 * x + (cls & 1);
-                                ok = ok && yy < P.Ho && xx < P.Wo;
-                                if (ok) {
-                                    o_off = F32 ? img * P.out32.sI + yy * P.out32.sH + xx * P.out32.sW : tv_pix(P.out, img, yy, xx);
-                                    if (P.mask_mode) m_off = tv_pix(P.mask, img, yy, xx);
+                                ok_c = row_ok && yy < P.Ho && xx < P.Wo;
+                                if (ok_c) {
+                                    o_pix = F32 ? img * P.out32.sI + yy * P.out32.sH + xx * P.out32.sW : tv_pix(P.out, img, yy, xx);
+                                    if (P.mask_mode) m_pix = tv_pix(P.mask, img, yy, xx);
                                 }
                             }
-                            if (ok) epi_store8<F32>(P, v + 8 * h, bias_s, cl0, o_off, m_off, oscale);
+                            if (ok_c) epi_store8<F32>(P, v + 8 * h, bias_s, cl0, o_pix, m_pix, oscale);
                             cl0 += 8;
                             if (OP == OP_UP && cl0 == P.Cop) {
                                 cl0 = 0;
