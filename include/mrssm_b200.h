@@ -229,6 +229,21 @@ typedef struct mrssm_rollout_args {
 
 int mrssm_rollout_fwd(const mrssm_rollout_args* a, void* stream);
 
+/* ---- the same rollout (forward) on the tensor cores -------------------------------------------------
+ * tcgen05 / TMEM version of mrssm_rollout_fwd for D, H <= 208, S <= 32, S + A <= 48, <= 4 heads (the shipped
+ * configs): 64 sequences per CTA, bf16 GEMM operands, fp32 accumulation, gate math and recurrent state.  Same
+ * reference code replaced (transition_model.py:200-285, encoder.py:50-190), same argument struct, same outputs
+ * and stash.  The weights are NOT read through the struct: they are packed once per optimiser step into the bf16
+ * B-operand stream of one time step by mrssm_rollout_tc_pack (which takes them in PyTorch layout, [out][in] fp32,
+ * w1 with row stride ld1), following the per-step MMA program built by mrssm_rollout_tc_plan (host only; the
+ * caller uploads the buffer once per shape).  Only the biases, emb_pre, inputs and outputs are read from `a`. */
+int mrssm_rollout_tc_eligible(int32_t D, int32_t S, int32_t H, int32_t A, int32_t n_experts);   /* 1 / 0 */
+int mrssm_rollout_tc_plan_bytes(int32_t D, int32_t S, int32_t H, int32_t A, int32_t n_experts, int64_t* plan_bytes,
+                                int64_t* packed_bytes);
+int mrssm_rollout_tc_plan(int32_t D, int32_t S, int32_t H, int32_t A, int32_t n_experts, void* host_buf, int64_t buflen);
+int mrssm_rollout_tc_pack(const mrssm_rollout_args* a, const void* plan_dev, int32_t n_pack, void* packed_dev, void* stream);
+int mrssm_rollout_tc_fwd(const mrssm_rollout_args* a, const void* plan_dev, const void* packed_dev, void* stream);
+
 /* BPTT through the rollout (autograd of transition_model.py:226-270).  Consumes the forward's
  * outputs/stash plus upstream gradients of every output; produces the data gradients and the
  * per-step pre-activation gradients from which all weight gradients follow as time-parallel

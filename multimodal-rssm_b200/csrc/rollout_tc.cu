@@ -1,0 +1,726 @@
+// Fused RSSM rollout, forward, on the 5th-gen tensor cores (tcgen05 + TMEM), bf16 operands, fp32 accumulate and
+// fp32 recurrent state.  Replaces the same reference code as rollout_simt.cu — utils/models/transition_model.py:
+// 200-285 (+ :50-114), nn.GRUCell (:160,235), the Gaussian heads of encoder.py:126-190, poe / MoPoE fusion
+// (encoder.py:50-124) and the rsample calls — for the sizes of the shipped configs (D, H <= 208, S <= 32,
+// S + A <= 48, <= 4 heads); mrssm_rollout_tc_eligible() says whether it applies.
+//
+// One CTA owns ROWS = 64 sequences for all T steps (tcgen05 M = 64: accumulator row i lives in TMEM lane
+// 32*(i/16) + i%16, profiles/micro/tmem_layout.cu).  Per step the chain
+//   xin=[s*mask,a] -> fc_embed -> GRU gates -> (1+E) heads fc1 -> fc2 -> fusion / rsample -> next xin
+// is a fixed PROGRAM of tcgen05.mma instructions built on the host (mrssm_rollout_tc_plan): every MMA names its
+// A operand (an activation buffer in shared memory, un-swizzled K-major chunk planes [chunk][row][8]), its B operand
+// (a block of the packed bf16 weight image), its TMEM columns and its N.  The packed weight image (one contiguous
+// byte stream per step, identical for every step, ~1.1 MB) is streamed through a shared-memory ring by cp.async.bulk
+// — the producer runs ahead across phase and step boundaries.  Roles: warp 0 = weight producer, warp 1 = MMA issuer,
+// warp 2 = TMEM allocator, warps 4..19 = epilogue (tcgen05.ld.16x256b so all 32 lanes carry data: thread t holds
+// rows t/4 and t/4+8, columns 2(t%4), 2(t%4)+1 of every 8-column group).  The epilogues do the gate math, softplus,
+// PoE / MoPoE fusion and rsample in fp32, write the API outputs and the BPTT stash to HBM, and write the NEXT
+// operand (bf16) straight into the activation buffer the following MMAs read.  h is kept in fp32 in shared memory;
+// only its bf16 copy feeds the tensor cores.
+#include <algorithm>
+#include <string.h>
+#include <vector>
+#include "tc_common.cuh"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int ROWS = 64;                  // sequences per CTA = MMA M
+constexpr int CH_BYTES = ROWS * 16;       // one 8-feature chunk plane of an A operand
+constexpr int MAXC = 26;                  // chunk planes per activation buffer (D, H <= 208)
+constexpr int XIN_CH = 6;                 // S + A <= 48
+constexpr int SLOT_BYTES = 14336;         // ring slot: 4 N=112 blocks, 2 N=208 blocks, 7 N=64 blocks
+constexpr int MAX_SLOTS = 8;
+constexpr int TC_THREADS = 640;
+constexpr int EPI_WARP0 = 4, EPI_WARPS = 16;
+constexpr int ACC_STRIDE = 112;           // TMEM columns per gate accumulator / per fc1 set
+constexpr int F2_COL = 2 * ACC_STRIDE;    // fc2 accumulators: 64 columns per head
+constexpr int TC_MAX_HEADS = 4;
+constexpr int MAX_TILES = 112, MAX_OPS = 336;
+constexpr int TC_MAGIC = 0x52544331;      // "RTC1"
+
+enum { BUF_XIN = 0, BUF_XU = 1, BUF_HPREV = 2, BUF_HNEW = 3 };
+enum { EV_XIN = 0, EV_X, EV_HA, EV_HB, EV_U0, N_EV = EV_U0 + 2 * TC_MAX_HEADS };
+enum { CM_X = 0, CM_GA, CM_GB, CM_F1, CM_F2 = CM_F1 + 2 * TC_MAX_HEADS, N_CM = CM_F2 + TC_MAX_HEADS };
+enum { SRC_WSA = 0, SRC_WIH, SRC_WHH, SRC_W1, SRC_W2 = SRC_W1 + TC_MAX_HEADS, N_SRC = SRC_W2 + TC_MAX_HEADS };
+
+// dynamic shared memory map (bytes from the 1024-aligned base)
+constexpr int OFF_XIN = 0;
+constexpr int OFF_XU = OFF_XIN + XIN_CH * CH_BYTES;
+constexpr int OFF_H0 = OFF_XU + MAXC * CH_BYTES;
+constexpr int OFF_H1 = OFF_H0 + MAXC * CH_BYTES;
+constexpr int OFF_HF = OFF_H1 + MAXC * CH_BYTES;          // fp32 h: [chunk][row][8]
+constexpr int OFF_RING = OFF_HF + MAXC * ROWS * 32;
+constexpr int ZERO_BYTES = OFF_HF;                         // operand buffers zeroed at start (padding chunks stay zero)
+
+struct TcTile {
+    uint32_t src_off, bytes;              // byte range of the packed image
+    uint16_t op_begin, op_end;
+    int8_t wait_ev, commit;               // event to wait for before the first MMA / commit barrier after the last (-1: none)
+    int16_t pad;
+};
+struct TcOp {
+    uint16_t a_off16;                     // A operand: byte offset >> 4 inside its buffer
+    uint8_t a_buf, acc;
+    uint16_t b_off16, d_col;              // B block offset >> 4 inside the ring slot; TMEM column
+    uint32_t idesc;
+};
+struct TcPack {                           // how one B block [2][N][8] is gathered from an fp32 PyTorch-layout weight
+    int32_t src_id, k0, kvalid, N;
+    int32_t seg_n[2], seg_src[2], seg_cnt[2];
+    uint32_t dst_off;
+    int32_t pad;
+};
+struct TcHeader {
+    int32_t magic, D, S, H, A, NH, n_tiles, n_ops, n_pack, cA, nD8, cAH, nH8;
+    uint32_t packed_bytes, tile_off, op_off, pack_off, total_bytes;
+};
+struct PackSrc {
+    const float* p[N_SRC];
+    int32_t ld[N_SRC];
+};
+
+__host__ __device__ inline int ceil16(int v) { return (v + 15) / 16 * 16; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// host: the per-step MMA program
+// ---------------------------------------------------------------------------------------------------------------
+struct PlanBuilder {
+    std::vector<TcTile> tiles;
+    std::vector<TcOp> ops;
+    std::vector<TcPack> packs;
+    uint32_t packed = 0;
+    int cur_wait = -1;
+    bool first = true, open = false;
+
+    void unit_begin(int wait_ev) { cur_wait = wait_ev; first = true; open = false; }
+    void unit_end(int commit) { tiles.back().commit = (int8_t)commit; open = false; }
+    // one MMA: D[d_col .. d_col+N) (+)= A(buf, chunks 2k, 2k+1) * W[rows, k0 .. k0+16)^T
+    void mma(int a_buf, int k, int d_col, int N, int acc, int src_id, int kin, int seg0_n, int seg0_src, int seg0_cnt, int seg1_n = 0,
+             int seg1_src = 0, int seg1_cnt = 0) {
+        const uint32_t bytes = 32u * (uint32_t)N;
+        if (!open || tiles.back().bytes + bytes > (uint32_t)SLOT_BYTES) {
+            TcTile t;
+            t.src_off = packed; t.bytes = 0;
+            t.op_begin = t.op_end = (uint16_t)ops.size();
+            t.wait_ev = (int8_t)(first ? cur_wait : -1);
+            t.commit = -1; t.pad = 0;
+            tiles.push_back(t);
+            first = false; open = true;
+        }
+        TcOp o;
+        o.a_off16 = (uint16_t)(2 * k * CH_BYTES / 16);
+        o.a_buf = (uint8_t)a_buf; o.acc = (uint8_t)acc;
+        o.b_off16 = (uint16_t)(tiles.back().bytes / 16);
+        o.d_col = (uint16_t)d_col;
+        o.idesc = tc::idesc_bf16(ROWS, N, 0, 0);
+        ops.push_back(o);
+        TcPack p;
+        p.src_id = src_id; p.k0 = 16 * k; p.kvalid = std::max(0, std::min(16, kin - 16 * k)); p.N = N;
+        p.seg_n[0] = seg0_n; p.seg_src[0] = seg0_src; p.seg_cnt[0] = seg0_cnt;
+        p.seg_n[1] = seg1_n; p.seg_src[1] = seg1_src; p.seg_cnt[1] = seg1_cnt;
+        p.dst_off = packed; p.pad = 0;
+        packs.push_back(p);
+        packed += bytes;
+        tiles.back().bytes += bytes;
+        tiles.back().op_end = (uint16_t)ops.size();
+    }
+};
+
+bool tc_eligible(int D, int S, int H, int A, int NH) {
+    return D % 8 == 0 && H % 8 == 0 && D >= 16 && H >= 16 && D <= 8 * MAXC && H <= 8 * MAXC && S >= 1 && S <= 32 && A >= 0 &&
+           S + A <= 8 * XIN_CH && NH >= 1 && NH <= TC_MAX_HEADS;
+}
+
+void build_plan(int D, int S, int H, int A, int NH, PlanBuilder& pb, TcHeader& h) {
+    const int nD8 = D / 8, nH8 = H / 8, cA = (nD8 + 1) / 2, cAH = (nH8 + 1) / 2;
+    const int nkD = (D + 15) / 16, nkH = (H + 15) / 16, nkX = (S + A + 15) / 16;
+    // 1. fc_embed_state_action (transition_model.py:232-233)
+    pb.unit_begin(EV_XIN);
+    for (int k = 0; k < nkX; ++k) pb.mma(BUF_XIN, k, 0, ceil16(D), k != 0, SRC_WSA, S + A, 0, 0, D);
+    pb.unit_end(CM_X);
+    // 2. GRUCell gates in two column halves (r, z, i_n, h_n of the same features share TMEM)
+    for (int hf = 0; hf < 2; ++hf) {
+        const int c0 = hf ? cA : 0, nc = hf ? nD8 - cA : cA, n0 = 8 * c0, cnt = 8 * nc, N = ceil16(cnt);
+        pb.unit_begin(hf ? EV_HA : EV_X);
+        for (int g = 0; g < 2; ++g) {       // r, z: x and h contributions into one accumulator
+            for (int k = 0; k < nkD; ++k) pb.mma(BUF_XU, k, g * ACC_STRIDE, N, k != 0, SRC_WIH, D, 0, g * D + n0, cnt);
+            for (int k = 0; k < nkD; ++k) pb.mma(BUF_HPREV, k, g * ACC_STRIDE, N, 1, SRC_WHH, D, 0, g * D + n0, cnt);
+        }
+        for (int k = 0; k < nkD; ++k) pb.mma(BUF_XU, k, 2 * ACC_STRIDE, N, k != 0, SRC_WIH, D, 0, 2 * D + n0, cnt);
+        for (int k = 0; k < nkD; ++k) pb.mma(BUF_HPREV, k, 3 * ACC_STRIDE, N, k != 0, SRC_WHH, D, 0, 2 * D + n0, cnt);
+        pb.unit_end(hf ? CM_GB : CM_GA);
+    }
+    // 3./4. heads: fc1 (belief columns; the embedding columns are hoisted) in half-head units on two TMEM sets, fc2 per head
+    auto fc1 = [&](int hd, int hf, int wait_ev) {
+        const int c0 = hf ? cAH : 0, nc = hf ? nH8 - cAH : cAH, n0 = 8 * c0, cnt = 8 * nc, N = ceil16(cnt);
+        pb.unit_begin(wait_ev);
+        for (int k = 0; k < nkD; ++k) pb.mma(BUF_HNEW, k, hf * ACC_STRIDE, N, k != 0, SRC_W1 + hd, D, 0, n0, cnt);
+        pb.unit_end(CM_F1 + 2 * hd + hf);
+    };
+    auto fc2 = [&](int hd) {
+        pb.unit_begin(EV_U0 + 2 * hd + 1);
+        for (int k = 0; k < nkH; ++k) pb.mma(BUF_XU, k, F2_COL + 64 * hd, 64, k != 0, SRC_W2 + hd, H, 0, 0, S, 32, S, S);
+        pb.unit_end(CM_F2 + hd);
+    };
+    fc1(0, 0, EV_HB);
+    fc1(0, 1, -1);
+    for (int hd = 1; hd < NH; ++hd) {
+        fc1(hd, 0, EV_U0 + 2 * hd - 2);
+        fc2(hd - 1);
+        fc1(hd, 1, -1);
+    }
+    fc2(NH - 1);
+
+    memset(&h, 0, sizeof(h));
+    h.magic = TC_MAGIC; h.D = D; h.S = S; h.H = H; h.A = A; h.NH = NH;
+    h.n_tiles = (int)pb.tiles.size(); h.n_ops = (int)pb.ops.size(); h.n_pack = (int)pb.packs.size();
+    h.cA = cA; h.nD8 = nD8; h.cAH = cAH; h.nH8 = nH8;
+    h.packed_bytes = pb.packed;
+    h.tile_off = 128;
+    h.op_off = h.tile_off + (uint32_t)(pb.tiles.size() * sizeof(TcTile));
+    h.pack_off = (h.op_off + (uint32_t)(pb.ops.size() * sizeof(TcOp)) + 15u) & ~15u;
+    h.total_bytes = h.pack_off + (uint32_t)(pb.packs.size() * sizeof(TcPack));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void r_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void r_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void r_umma(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 16 TMEM lanes x 8 columns: thread t gets (row t/4, cols 2(t%4), +1) in v[0], v[1] and (row t/4 + 8, same cols) in v[2], v[3]
+__device__ __forceinline__ void ld_frag(uint32_t taddr, float (&v)[4]) {
+    uint32_t r0, r1, r2, r3;
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_shared_bf16(uint32_t addr, float v) {
+    const unsigned short u = __bfloat16_as_ushort(__float2bfloat16(v));
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(u) : "memory");
+}
+__device__ __forceinline__ float2 ld_shared_f2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_shared_f2(uint32_t addr, float a, float b) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void st_f2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+
+// the epilogue warps signal "operand written / accumulator drained": one arrival per warp
+__device__ __forceinline__ void epi_signal(uint64_t* bar, int lane) {
+    tc::tc_fence_before();
+    tc::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(tc::smem_u32(bar));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight packing: fp32 PyTorch-layout weights -> the bf16 B-operand stream of one step
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void rollout_tc_pack_kernel(const uint8_t* __restrict__ plan, PackSrc src, bf16* __restrict__ out) {
+    const TcHeader* h = reinterpret_cast<const TcHeader*>(plan);
+    const TcPack pk = reinterpret_cast<const TcPack*>(plan + h->pack_off)[blockIdx.x];
+    const float* w = src.p[pk.src_id];
+    const long long ld = src.ld[pk.src_id];
+    bf16* dst = out + pk.dst_off / 2;
+    for (int i = threadIdx.x; i < pk.N * 16; i += blockDim.x) {
+        const int ch = i / (pk.N * 8), n = (i >> 3) % pk.N, k = ch * 8 + (i & 7);
+        float v = 0.f;
+        if (k < pk.kvalid) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+                if (n >= pk.seg_n[s] && n < pk.seg_n[s] + pk.seg_cnt[s]) v = w[(long long)(pk.seg_src[s] + n - pk.seg_n[s]) * ld + pk.k0 + k];
+        }
+        dst[i] = __float2bfloat16(v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+rollout_tc_fwd_kernel(const mrssm_rollout_args a, const uint8_t* __restrict__ plan, const uint8_t* __restrict__ packed, const int NS) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full[MAX_SLOTS], empty[MAX_SLOTS], ev[N_EV], cm[N_CM];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) TcTile tiles_s[MAX_TILES];
+    __shared__ __align__(16) TcOp ops_s[MAX_OPS];
+    __shared__ float bias_x[8 * MAXC], bias_g[4][8 * MAXC], bias_1[TC_MAX_HEADS][8 * MAXC], bias_2[TC_MAX_HEADS][64];
+    __shared__ uint32_t smask_s[32];                           // fusion subset (expert bitmask) of every state dim
+    __shared__ const float* emb_pre_s[TC_MAX_HEADS];
+    __shared__ float *st_u_s[TC_MAX_HEADS], *exp_means_s[TC_MAX_HEADS], *exp_stds_s[TC_MAX_HEADS];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* const smem = smem_raw + (smem0 - tc::smem_u32(smem_raw));
+    const TcHeader* const hd_g = reinterpret_cast<const TcHeader*>(plan);
+    const int D = a.D, S = a.S, H = a.H, A = a.A, E = a.n_experts, NH = 1 + E, B = a.B, T = a.T;
+    const int n_tiles = hd_g->n_tiles, cA = hd_g->cA, nD8 = hd_g->nD8, cAH = hd_g->cAH, nH8 = hd_g->nH8;
+    const int b0 = blockIdx.x * ROWS;
+    if (hd_g->magic != TC_MAGIC || hd_g->D != D || hd_g->S != S || hd_g->H != H || hd_g->A != A || hd_g->NH != NH || n_tiles > MAX_TILES ||
+        hd_g->n_ops > MAX_OPS) {
+        if (tid == 0) printf("mrssm rollout_tc: plan does not match the call\n");
+        __trap();
+    }
+
+    // ---- prologue ---------------------------------------------------------------------------------------
+    {
+        const uint4* ts = reinterpret_cast<const uint4*>(plan + hd_g->tile_off);
+        for (int i = tid; i < n_tiles; i += TC_THREADS) reinterpret_cast<uint4*>(tiles_s)[i] = ts[i];
+        const uint32_t* os = reinterpret_cast<const uint32_t*>(plan + hd_g->op_off);
+        for (int i = tid; i < hd_g->n_ops * 3; i += TC_THREADS) reinterpret_cast<uint32_t*>(ops_s)[i] = os[i];
+        for (int j = tid; j < 8 * MAXC; j += TC_THREADS) {
+            const bool ok = j < D;
+            bias_x[j] = ok ? a.b_sa[j] : 0.f;
+            bias_g[0][j] = ok ? a.b_ih[j] + a.b_hh[j] : 0.f;
+            bias_g[1][j] = ok ? a.b_ih[D + j] + a.b_hh[D + j] : 0.f;
+            bias_g[2][j] = ok ? a.b_ih[2 * D + j] : 0.f;
+            bias_g[3][j] = ok ? a.b_hh[2 * D + j] : 0.f;
+            for (int h = 0; h < TC_MAX_HEADS; ++h) bias_1[h][j] = (h < NH && j < H && a.b1[h]) ? a.b1[h][j] : 0.f;
+        }
+        for (int j = tid; j < TC_MAX_HEADS * 64; j += TC_THREADS) {
+            const int h = j >> 6, c = j & 63, s = c & 31;
+            bias_2[h][c] = (h < NH && s < S) ? a.b2[h][(c >> 5) * S + s] : 0.f;
+        }
+        if (tid < 32) smask_s[tid] = (tid < S && a.n_subsets > 0) ? a.subset_mask[a.dim_subset[tid]] : 0u;
+        if (tid < TC_MAX_HEADS) {
+            emb_pre_s[tid] = tid < NH ? a.emb_pre[tid] : nullptr;
+            st_u_s[tid] = tid < NH ? a.st_u[tid] : nullptr;
+            exp_means_s[tid] = tid < NH ? a.exp_means[tid] : nullptr;
+            exp_stds_s[tid] = tid < NH ? a.exp_stds[tid] : nullptr;
+        }
+        for (int i = tid; i < ZERO_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < MAX_SLOTS; ++s) {
+            tc::mbar_init(tc::smem_u32(&full[s]), 1);
+            tc::mbar_init(tc::smem_u32(&empty[s]), 1);
+        }
+        for (int i = 0; i < N_EV; ++i) tc::mbar_init(tc::smem_u32(&ev[i]), EPI_WARPS);
+        for (int i = 0; i < N_CM; ++i) tc::mbar_init(tc::smem_u32(&cm[i]), 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), 512);
+    __syncthreads();
+    // h_{-1} (fp32 + bf16 operand) and xin of step 0
+    for (int i = tid; i < ROWS * D; i += TC_THREADS) {
+        const int r = i / D, j = i - r * D;
+        const float v = (b0 + r < B) ? a.prev_belief[(long long)(b0 + r) * D + j] : 0.f;
+        *reinterpret_cast<float*>(smem + OFF_HF + (j >> 3) * (ROWS * 32) + r * 32 + (j & 7) * 4) = v;
+        *reinterpret_cast<bf16*>(smem + OFF_H0 + (j >> 3) * CH_BYTES + r * 16 + (j & 7) * 2) = __float2bfloat16(v);
+    }
+    for (int i = tid; i < ROWS * (S + A); i += TC_THREADS) {
+        const int r = i / (S + A), j = i - r * (S + A);
+        float v = 0.f;
+        if (b0 + r < B) {
+            if (j < S) v = a.prev_state[(long long)(b0 + r) * S + j] * (a.nonterminals ? a.nonterminals[b0 + r] : 1.f);
+            else v = a.actions[(long long)(b0 + r) * A + (j - S)];
+        }
+        *reinterpret_cast<bf16*>(smem + OFF_XIN + (j >> 3) * CH_BYTES + r * 16 + (j & 7) * 2) = __float2bfloat16(v);
+    }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ---- weight producer ------------------------------------------------------------------------------
+        if (lane == 0) {
+            uint32_t cnt = 0;
+            for (int t = 0; t < T; ++t) {
+                for (int ti = 0; ti < n_tiles; ++ti, ++cnt) {
+                    const int s = cnt % NS;
+                    tc::mbar_wait(tc::smem_u32(&empty[s]), ((cnt / NS) & 1) ^ 1);
+                    const uint32_t bar = tc::smem_u32(&full[s]);
+                    const uint32_t bytes = tiles_s[ti].bytes;
+                    r_expect_tx(bar, bytes);
+                    r_bulk_g2s(smem0 + OFF_RING + (uint32_t)s * SLOT_BYTES, packed + tiles_s[ti].src_off, bytes, bar);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ---- MMA issuer ------------------------------------------------------------------------------------
+        if (lane == 0) {
+            const uint32_t hi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1, no swizzle
+            const uint32_t a_lbo = ((uint32_t)CH_BYTES >> 4) << 16;
+            uint32_t cnt = 0;
+            for (int t = 0; t < T; ++t) {
+                const uint32_t par = (uint32_t)(t & 1);
+                uint32_t abase[4];
+                abase[BUF_XIN] = (smem0 + OFF_XIN) >> 4;
+                abase[BUF_XU] = (smem0 + OFF_XU) >> 4;
+                abase[BUF_HPREV] = (smem0 + ((t & 1) ? OFF_H1 : OFF_H0)) >> 4;
+                abase[BUF_HNEW] = (smem0 + ((t & 1) ? OFF_H0 : OFF_H1)) >> 4;
+                for (int ti = 0; ti < n_tiles; ++ti, ++cnt) {
+                    const TcTile tl = tiles_s[ti];
+                    if (tl.wait_ev >= 0) {
+                        if (tl.wait_ev == EV_XIN) {
+                            if (t > 0) tc::mbar_wait(tc::smem_u32(&ev[EV_XIN]), (uint32_t)((t - 1) & 1));
+                        } else {
+                            tc::mbar_wait(tc::smem_u32(&ev[tl.wait_ev]), par);
+                        }
+                        tc::tc_fence_after();
+                    }
+                    const int s = cnt % NS;
+                    tc::mbar_wait(tc::smem_u32(&full[s]), (cnt / NS) & 1);
+                    tc::tc_fence_after();
+                    const uint32_t sb = (smem0 + OFF_RING + (uint32_t)s * SLOT_BYTES) >> 4;
+                    for (int oi = tl.op_begin; oi < tl.op_end; ++oi) {
+                        const TcOp o = ops_s[oi];
+                        const uint32_t n = ((o.idesc >> 17) & 63u) << 3;
+                        const uint32_t a_lo = ((abase[o.a_buf] + o.a_off16) & 0x3FFFu) | a_lbo;
+                        const uint32_t b_lo = ((sb + o.b_off16) & 0x3FFFu) | (n << 16);       // LBO = N * 16 bytes
+                        r_umma(tmem_base + o.d_col, a_lo, b_lo, hi, o.idesc, o.acc);
+                    }
+                    tc::umma_commit(tc::smem_u32(&empty[s]));
+                    if (tl.commit >= 0) tc::umma_commit(tc::smem_u32(&cm[tl.commit]));
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI_WARPS) {
+        // ---- epilogue warps ------------------------------------------------------------------------------
+        const int ew = warp - EPI_WARP0, q = ew & 3, p = ew >> 2, etid = tid - EPI_WARP0 * 32;
+        const int r0 = 16 * q + (lane >> 2), r1 = r0 + 8, cj = 2 * (lane & 3);
+        const bool ok0 = b0 + r0 < B, ok1 = b0 + r1 < B;
+        const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
+        const uint32_t opnd0 = (uint32_t)(r0 * 16 + cj * 2), opnd1 = (uint32_t)(r1 * 16 + cj * 2);      // inside a bf16 chunk plane
+        const uint32_t hf0 = smem0 + OFF_HF + (uint32_t)(r0 * 32 + cj * 4), hf1 = smem0 + OFF_HF + (uint32_t)(r1 * 32 + cj * 4);
+        const int act = a.act;
+        for (int t = 0; t < T; ++t) {
+            const uint32_t par = (uint32_t)(t & 1);
+            const long long row0 = (long long)t * B + b0 + r0, row1 = row0 + 8;
+            // ---- E1: x = act(W_sa xin + b) -> XU, stash x ------------------------------------------------
+            tc::mbar_wait(tc::smem_u32(&cm[CM_X]), par);
+            tc::tc_fence_after();
+            {
+                const int nc = ceil16(D) >> 3;
+                for (int c = p; c < nc; c += 4) {
+                    float v[4];
+                    ld_frag(tlane + (uint32_t)(8 * c), v);
+                    wait_ld();
+                    const int j = 8 * c + cj;
+                    const float bA = bias_x[j], bB = bias_x[j + 1];
+                    const float x00 = act_apply(v[0] + bA, act), x01 = act_apply(v[1] + bB, act);
+                    const float x10 = act_apply(v[2] + bA, act), x11 = act_apply(v[3] + bB, act);
+                    const uint32_t ch = smem0 + OFF_XU + (uint32_t)c * CH_BYTES;
+                    st_shared_u32(ch + opnd0, pack_bf16x2(x00, x01));
+                    st_shared_u32(ch + opnd1, pack_bf16x2(x10, x11));
+                    if (a.st_x && j < D) {
+                        if (ok0) st_f2(a.st_x + row0 * D + j, x00, x01);
+                        if (ok1) st_f2(a.st_x + row1 * D + j, x10, x11);
+                    }
+                }
+            }
+            epi_signal(&ev[EV_X], lane);
+            // ---- E2: GRU gate math per column half -> h (fp32 + bf16 operand), beliefs, stash ----------------
+            const uint32_t hnew = smem0 + ((t & 1) ? OFF_H0 : OFF_H1);
+            for (int hf = 0; hf < 2; ++hf) {
+                tc::mbar_wait(tc::smem_u32(&cm[CM_GA + hf]), par);
+                tc::tc_fence_after();
+                const int c_lo = hf ? cA : 0, c_hi = hf ? nD8 : cA;
+                for (int c = c_lo + p; c < c_hi; c += 4) {
+                    const uint32_t col = (uint32_t)(8 * (c - c_lo));
+                    float vr[4], vz[4], vi[4], vh[4];
+                    ld_frag(tlane + col, vr);
+                    ld_frag(tlane + ACC_STRIDE + col, vz);
+                    ld_frag(tlane + 2 * ACC_STRIDE + col, vi);
+                    ld_frag(tlane + 3 * ACC_STRIDE + col, vh);
+                    wait_ld();
+                    const int j = 8 * c + cj;
+                    const float2 hp0 = ld_shared_f2(hf0 + (uint32_t)c * (ROWS * 32)), hp1 = ld_shared_f2(hf1 + (uint32_t)c * (ROWS * 32));
+                    const float hp[4] = {hp0.x, hp0.y, hp1.x, hp1.y};
+                    float rr[4], zz[4], nn[4], gg[4], hn[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int jj = j + (e & 1);
+                        rr[e] = sigmoidf_(vr[e] + bias_g[0][jj]);
+                        zz[e] = sigmoidf_(vz[e] + bias_g[1][jj]);
+                        gg[e] = vh[e] + bias_g[3][jj];
+                        nn[e] = tanhf(vi[e] + bias_g[2][jj] + rr[e] * gg[e]);
+                        hn[e] = (1.f - zz[e]) * nn[e] + zz[e] * hp[e];
+                    }
+                    st_shared_f2(hf0 + (uint32_t)c * (ROWS * 32), hn[0], hn[1]);
+                    st_shared_f2(hf1 + (uint32_t)c * (ROWS * 32), hn[2], hn[3]);
+                    const uint32_t ch = hnew + (uint32_t)c * CH_BYTES;
+                    st_shared_u32(ch + opnd0, pack_bf16x2(hn[0], hn[1]));
+                    st_shared_u32(ch + opnd1, pack_bf16x2(hn[2], hn[3]));
+                    if (ok0) {
+                        const long long off = row0 * D + j;
+                        st_f2(a.beliefs + off, hn[0], hn[1]);
+                        if (a.st_r) {
+                            st_f2(a.st_r + off, rr[0], rr[1]); st_f2(a.st_z + off, zz[0], zz[1]);
+                            st_f2(a.st_n + off, nn[0], nn[1]); st_f2(a.st_ghn + off, gg[0], gg[1]);
+                        }
+                    }
+                    if (ok1) {
+                        const long long off = row1 * D + j;
+                        st_f2(a.beliefs + off, hn[2], hn[3]);
+                        if (a.st_r) {
+                            st_f2(a.st_r + off, rr[2], rr[3]); st_f2(a.st_z + off, zz[2], zz[3]);
+                            st_f2(a.st_n + off, nn[2], nn[3]); st_f2(a.st_ghn + off, gg[2], gg[3]);
+                        }
+                    }
+                }
+                epi_signal(&ev[EV_HA + hf], lane);
+            }
+            // ---- E3: heads fc1 (+ hoisted embedding half) + act -> XU (as U), stash u ------------------------
+            for (int hd = 0; hd < NH; ++hd) {
+                const float* ep = emb_pre_s[hd];
+                float* su = st_u_s[hd];
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int c_lo = hf ? cAH : 0, c_hi = hf ? nH8 : cAH;
+                    float pre[4][4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = c_lo + p + 4 * i;
+                        pre[i][0] = pre[i][1] = pre[i][2] = pre[i][3] = 0.f;
+                        if (ep && c < c_hi) {
+                            const int j = 8 * c + cj;
+                            if (ok0) { const float2 e0 = *reinterpret_cast<const float2*>(ep + row0 * H + j); pre[i][0] = e0.x; pre[i][1] = e0.y; }
+                            if (ok1) { const float2 e1 = *reinterpret_cast<const float2*>(ep + row1 * H + j); pre[i][2] = e1.x; pre[i][3] = e1.y; }
+                        }
+                    }
+                    // (hd, half 0) of hd >= 1 also needs fc2 of head hd-1 to be done reading U: that commit was issued later
+                    const int cmi = (hf == 0 && hd > 0) ? CM_F2 + hd - 1 : CM_F1 + 2 * hd + hf;
+                    tc::mbar_wait(tc::smem_u32(&cm[cmi]), par);
+                    tc::tc_fence_after();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = c_lo + p + 4 * i;
+                        if (c < c_hi) {
+                            float v[4];
+                            ld_frag(tlane + (uint32_t)(hf * ACC_STRIDE + 8 * (c - c_lo)), v);
+                            wait_ld();
+                            const int j = 8 * c + cj;
+                            const float bA = bias_1[hd][j], bB = bias_1[hd][j + 1];
+                            const float u00 = act_apply(v[0] + bA + pre[i][0], act), u01 = act_apply(v[1] + bB + pre[i][1], act);
+                            const float u10 = act_apply(v[2] + bA + pre[i][2], act), u11 = act_apply(v[3] + bB + pre[i][3], act);
+                            const uint32_t ch = smem0 + OFF_XU + (uint32_t)c * CH_BYTES;
+                            st_shared_u32(ch + opnd0, pack_bf16x2(u00, u01));
+                            st_shared_u32(ch + opnd1, pack_bf16x2(u10, u11));
+                            if (su) {
+                                if (ok0) st_f2(su + row0 * H + j, u00, u01);
+                                if (ok1) st_f2(su + row1 * H + j, u10, u11);
+                            }
+                        }
+                    }
+                    epi_signal(&ev[EV_U0 + 2 * hd + hf], lane);
+                }
+            }
+            // ---- E4: heads fc2 -> (mean, softplus + min_std), prior sample, fusion, posterior sample, next xin --
+            const bool more = t + 1 < T;
+            if (more) {                                       // action columns of xin(t+1): the buffer is idle since E1
+                for (int i = etid; i < ROWS * A; i += EPI_WARPS * 32) {
+                    const int r = i / A, k = i - r * A, col = S + k;
+                    const float v = (b0 + r < B) ? a.actions[((long long)(t + 1) * B + b0 + r) * A + k] : 0.f;
+                    st_shared_bf16(smem0 + OFF_XIN + (uint32_t)((col >> 3) * CH_BYTES + r * 16 + (col & 7) * 2), v);
+                }
+            }
+            const int s0 = 8 * p + cj;                        // this thread: state dims s0, s0+1 of rows r0, r1
+            const bool live = 8 * p < S;
+            float epr[4] = {0.f, 0.f, 0.f, 0.f}, epo[4] = {0.f, 0.f, 0.f, 0.f}, mk[2] = {1.f, 1.f};
+            if (live) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int s = s0 + (e & 1);
+                    const bool okr = (e < 2) ? ok0 : ok1;
+                    if (okr && s < S) {
+                        const long long off = ((e < 2) ? row0 : row1) * S + s;
+                        if (a.eps_prior && !a.det) epr[e] = a.eps_prior[off];
+                        if (a.eps_post && !a.det && E > 0) epo[e] = a.eps_post[off];
+                    }
+                }
+                if (more && a.nonterminals) {
+                    if (ok0) mk[0] = a.nonterminals[row0 + B];
+                    if (ok1) mk[1] = a.nonterminals[row1 + B];
+                }
+            }
+            tc::mbar_wait(tc::smem_u32(&cm[CM_F2 + NH - 1]), par);
+            tc::tc_fence_after();
+            if (live) {
+                float mu[TC_MAX_HEADS][4], sg[TC_MAX_HEADS][4];
+#pragma unroll
+                for (int h = 0; h < TC_MAX_HEADS; ++h) {
+                    if (h < NH) {
+                        ld_frag(tlane + (uint32_t)(F2_COL + 64 * h + 8 * p), mu[h]);
+                        ld_frag(tlane + (uint32_t)(F2_COL + 64 * h + 32 + 8 * p), sg[h]);
+                    }
+                }
+                wait_ld();
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int s = s0 + (e & 1);
+                    const int r = (e < 2) ? r0 : r1;
+                    const bool okr = (e < 2) ? ok0 : ok1;
+                    if (s >= S) continue;
+                    const long long off = ((e < 2) ? row0 : row1) * S + s;
+                    float om[TC_MAX_HEADS], os[TC_MAX_HEADS];
+#pragma unroll
+                    for (int h = 0; h < TC_MAX_HEADS; ++h) {
+                        if (h < NH) {
+                            om[h] = mu[h][e] + bias_2[h][s];
+                            os[h] = softplusf_(sg[h][e] + bias_2[h][32 + s]) + a.min_std;
+                        }
+                    }
+                    const float pm = om[0], ps = os[0];
+                    const float pst = a.det ? pm : fmaf(ps, epr[e], pm);
+                    float nxt = pst;
+                    if (okr) {
+                        a.prior_means[off] = pm; a.prior_stds[off] = ps; a.prior_states[off] = pst;
+                    }
+                    if (E > 0) {
+                        float qm, qs;
+                        if (a.n_subsets == 0) {
+                            qm = om[1]; qs = os[1];
+                        } else {
+                            const unsigned mask = smask_s[s];
+                            float sumT = 0.f, sumMT = 0.f;
+#pragma unroll
+                            for (int h = 1; h < TC_MAX_HEADS; ++h) {
+                                if (h < NH && (mask & (1u << (h - 1)))) {
+                                    const float tt = 1.f / os[h];
+                                    sumT += tt;
+                                    sumMT = fmaf(om[h], tt, sumMT);
+                                }
+                            }
+                            qm = sumMT / sumT;
+                            qs = 1.f / sumT;
+                        }
+                        const float qst = a.det ? qm : fmaf(qs, epo[e], qm);
+                        if (okr) {
+#pragma unroll
+                            for (int h = 1; h < TC_MAX_HEADS; ++h) {
+                                if (h < NH) { exp_means_s[h][off] = om[h]; exp_stds_s[h][off] = os[h]; }
+                            }
+                            a.post_means[off] = qm; a.post_stds[off] = qs; a.post_states[off] = qst;
+                        }
+                        nxt = qst;
+                    }
+                    if (more)
+                        st_shared_bf16(smem0 + OFF_XIN + (uint32_t)((s >> 3) * CH_BYTES + r * 16 + (s & 7) * 2), okr ? nxt * mk[e >> 1] : 0.f);
+                }
+            }
+            epi_signal(&ev[EV_XIN], lane);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int mrssm_rollout_tc_eligible(int32_t D, int32_t S, int32_t H, int32_t A, int32_t n_experts) {
+    return tc_eligible(D, S, H, A, 1 + n_experts) ? 1 : 0;
+}
+
+extern "C" int mrssm_rollout_tc_plan_bytes(int32_t D, int32_t S, int32_t H, int32_t A, int32_t n_experts, int64_t* plan_bytes,
+                                           int64_t* packed_bytes) {
+    MRSSM_CHECK(tc_eligible(D, S, H, A, 1 + n_experts), "rollout_tc: sizes not eligible (D %d S %d H %d A %d heads %d)", D, S, H, A, 1 + n_experts);
+    PlanBuilder pb;
+    TcHeader h;
+    build_plan(D, S, H, A, 1 + n_experts, pb, h);
+    MRSSM_CHECK(h.n_tiles <= MAX_TILES && h.n_ops <= MAX_OPS, "rollout_tc: program too long (%d tiles, %d MMAs)", h.n_tiles, h.n_ops);
+    if (plan_bytes) *plan_bytes = h.total_bytes;
+    if (packed_bytes) *packed_bytes = h.packed_bytes;
+    return 0;
+}
+
+extern "C" int mrssm_rollout_tc_plan(int32_t D, int32_t S, int32_t H, int32_t A, int32_t n_experts, void* host_buf, int64_t buflen) {
+    MRSSM_CHECK(host_buf && tc_eligible(D, S, H, A, 1 + n_experts), "rollout_tc_plan: bad arguments");
+    PlanBuilder pb;
+    TcHeader h;
+    build_plan(D, S, H, A, 1 + n_experts, pb, h);
+    MRSSM_CHECK(h.n_tiles <= MAX_TILES && h.n_ops <= MAX_OPS, "rollout_tc: program too long (%d tiles, %d MMAs)", h.n_tiles, h.n_ops);
+    MRSSM_CHECK(buflen >= (int64_t)h.total_bytes, "rollout_tc_plan: buffer too small (%lld < %u)", (long long)buflen, h.total_bytes);
+    uint8_t* o = (uint8_t*)host_buf;
+    memset(o, 0, h.total_bytes);
+    memcpy(o, &h, sizeof(h));
+    memcpy(o + h.tile_off, pb.tiles.data(), pb.tiles.size() * sizeof(TcTile));
+    memcpy(o + h.op_off, pb.ops.data(), pb.ops.size() * sizeof(TcOp));
+    memcpy(o + h.pack_off, pb.packs.data(), pb.packs.size() * sizeof(TcPack));
+    return 0;
+}
+
+// a: weights in PyTorch layout ([out][in] fp32; ld1[h] = row stride of w1[h]); plan_dev: device copy of the plan;
+// n_pack: the plan header's n_pack (host knows it from its own copy)
+extern "C" int mrssm_rollout_tc_pack(const mrssm_rollout_args* a, const void* plan_dev, int32_t n_pack, void* packed_dev, void* stream) {
+    MRSSM_CHECK(a && plan_dev && packed_dev && n_pack > 0, "rollout_tc_pack: bad arguments");
+    const int NH = 1 + a->n_experts;
+    MRSSM_CHECK(tc_eligible(a->D, a->S, a->H, a->A, NH), "rollout_tc_pack: sizes not eligible");
+    PackSrc src;
+    memset(&src, 0, sizeof(src));
+    src.p[SRC_WSA] = a->w_sa; src.ld[SRC_WSA] = a->S + a->A;
+    src.p[SRC_WIH] = a->w_ih; src.ld[SRC_WIH] = a->D;
+    src.p[SRC_WHH] = a->w_hh; src.ld[SRC_WHH] = a->D;
+    for (int h = 0; h < NH; ++h) {
+        MRSSM_CHECK(a->w1[h] && a->w2[h] && a->ld1[h] >= a->D, "rollout_tc_pack: head %d weights missing", h);
+        src.p[SRC_W1 + h] = a->w1[h]; src.ld[SRC_W1 + h] = (int32_t)a->ld1[h];
+        src.p[SRC_W2 + h] = a->w2[h]; src.ld[SRC_W2 + h] = a->H;
+    }
+    MRSSM_CHECK(a->w_sa && a->w_ih && a->w_hh, "rollout_tc_pack: weights missing");
+    rollout_tc_pack_kernel<<<n_pack, 128, 0, (cudaStream_t)stream>>>((const uint8_t*)plan_dev, src, (bf16*)packed_dev);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+
+int rollout_check(const mrssm_rollout_args* a);
+
+extern "C" int mrssm_rollout_tc_fwd(const mrssm_rollout_args* a, const void* plan_dev, const void* packed_dev, void* stream) {
+    MRSSM_CHECK(a && plan_dev && packed_dev, "rollout_tc_fwd: bad arguments");
+    MRSSM_CHECK(tc_eligible(a->D, a->S, a->H, a->A, 1 + a->n_experts), "rollout_tc_fwd: sizes not eligible");
+    MRSSM_CHECK(a->T > 0 && a->B > 0 && a->prev_state && a->prev_belief && a->actions && a->beliefs && a->prior_states && a->prior_means &&
+                    a->prior_stds && a->b_sa && a->b_ih && a->b_hh,
+                "rollout_tc_fwd: missing tensors");
+    for (int h = 0; h <= a->n_experts; ++h) MRSSM_CHECK(a->b2[h] && (a->b1[h] || a->emb_pre[h]), "rollout_tc_fwd: head %d bias missing", h);
+    if (a->n_experts > 0) {
+        MRSSM_CHECK(a->post_states && a->post_means && a->post_stds, "rollout_tc_fwd: posterior outputs missing");
+        for (int h = 1; h <= a->n_experts; ++h) MRSSM_CHECK(a->exp_means[h] && a->exp_stds[h], "rollout_tc_fwd: expert outputs missing");
+        MRSSM_CHECK(a->det || a->eps_post, "rollout_tc_fwd: eps_post missing");
+    }
+    MRSSM_CHECK(a->det || a->eps_prior, "rollout_tc_fwd: eps_prior missing");
+    cudaFuncAttributes fa;
+    MRSSM_CUDA(cudaFuncGetAttributes(&fa, rollout_tc_fwd_kernel));
+    const int avail = 232448 - (int)fa.sharedSizeBytes - 1024 - OFF_RING;
+    const int NS = std::min(MAX_SLOTS, avail / SLOT_BYTES);
+    MRSSM_CHECK(NS >= 2, "rollout_tc_fwd: no room for the weight ring (%d bytes left)", avail);
+    const size_t dyn = (size_t)OFF_RING + (size_t)NS * SLOT_BYTES + 1024;
+    MRSSM_CUDA(cudaFuncSetAttribute(rollout_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    rollout_tc_fwd_kernel<<<(a->B + ROWS - 1) / ROWS, TC_THREADS, dyn, (cudaStream_t)stream>>>(*a, (const uint8_t*)plan_dev, (const uint8_t*)packed_dev, NS);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}

@@ -403,21 +403,29 @@ class RolloutFn(Function):
         a.prev_state, a.prev_belief, a.actions = L.ptr(prev_state), L.ptr(prev_belief), L.ptr(actions)
         a.nonterminals, a.eps_prior, a.eps_post = L.ptr(nonterminals), L.ptr(eps_prior), L.ptr(eps_post)
         keep = []
-        wsaT = transpose(L.ptr(w_sa), D, S + A, S + A, dev)
-        wihT = transpose(L.ptr(w_ih), 3 * D, D, D, dev)
-        whhT = transpose(L.ptr(w_hh), 3 * D, D, D, dev)
-        keep += [wsaT, wihT, whhT]
-        a.w_sa, a.b_sa, a.w_ih, a.b_ih, a.w_hh, a.b_hh = (L.ptr(wsaT), L.ptr(b_sa), L.ptr(wihT), L.ptr(b_ih),
-                                                          L.ptr(whhT), L.ptr(b_hh))
+        use_tc = rollout_tc_enabled() and bool(L.load().mrssm_rollout_tc_eligible(D, S, H, A, E))
+        if use_tc:
+            # tcgen05 rollout: the kernel reads the packed bf16 weight stream, only the biases come through `a`
+            a.b_sa, a.b_ih, a.b_hh = L.ptr(b_sa), L.ptr(b_ih), L.ptr(b_hh)
+            tc_plan, tc_packed = rollout_tc_weights(spec, E, w_sa, w_ih, w_hh, heads, dev)
+        else:
+            wsaT = transpose(L.ptr(w_sa), D, S + A, S + A, dev)
+            wihT = transpose(L.ptr(w_ih), 3 * D, D, D, dev)
+            whhT = transpose(L.ptr(w_hh), 3 * D, D, D, dev)
+            keep += [wsaT, wihT, whhT]
+            a.w_sa, a.b_sa, a.w_ih, a.b_ih, a.w_hh, a.b_hh = (L.ptr(wsaT), L.ptr(b_sa), L.ptr(wihT), L.ptr(b_ih),
+                                                              L.ptr(whhT), L.ptr(b_hh))
         emb_pre = [None] * (1 + E)
         ei = 0
         for hd in range(1 + E):
             w1, b1, w2, b2 = heads[hd]
             ld = w1.shape[1]
-            w1T = transpose(L.ptr(w1), H, D, ld, dev)
-            w2T = transpose(L.ptr(w2), 2 * S, H, H, dev)
-            keep += [w1T, w2T]
-            a.w1[hd], a.w2[hd], a.b2[hd], a.ld1[hd] = L.ptr(w1T), L.ptr(w2T), L.ptr(b2), ld
+            if not use_tc:
+                w1T = transpose(L.ptr(w1), H, D, ld, dev)
+                w2T = transpose(L.ptr(w2), 2 * S, H, H, dev)
+                keep += [w1T, w2T]
+                a.w1[hd], a.w2[hd] = L.ptr(w1T), L.ptr(w2T)
+            a.b2[hd], a.ld1[hd] = L.ptr(b2), ld
             if hd > 0 and spec.expert_has_emb[hd - 1]:
                 emb = embs[ei]
                 ei += 1
@@ -468,7 +476,11 @@ class RolloutFn(Function):
                 per = 4.0 * (A + S) + 4.0 * (D + 3 * S)
             macs = (S + A) * D + 6 * D * D + (1 + E) * (D * H + H * 2 * S) + sum(e.shape[-1] * H for e in embs)
             work = dict(bytes=per * T * B + 4.0 * n_w, flops=2.0 * macs * T * B)
-        L.call("mrssm_rollout_fwd", C.byref(a), tag="observe" if observe else "imagine", work=work)
+        if use_tc:
+            L.call("mrssm_rollout_tc_fwd", C.byref(a), L.ptr_any(tc_plan), L.ptr_any(tc_packed),
+                   tag="observe" if observe else "imagine", work=work)
+        else:
+            L.call("mrssm_rollout_fwd", C.byref(a), tag="observe" if observe else "imagine", work=work)
         del keep
         ctx.spec, ctx.observe, ctx.det, ctx.E = spec, observe, det, E
         ctx.params = params
@@ -892,6 +904,54 @@ def set_bf16_mode(on):
 
 def bf16_mode():
     return _STATE["bf16"]
+
+
+def set_rollout_tc(on):
+    """bf16 mode only: run the rollout forward on the tcgen05 kernel (csrc/rollout_tc.cu) when the sizes are eligible."""
+    _STATE["rollout_tc"] = bool(on)
+
+
+def rollout_tc_enabled():
+    return _STATE["bf16"] and _STATE.get("rollout_tc", True)
+
+
+_tc_plans = {}
+
+
+def rollout_tc_plan(D, S, H, A, E, dev):
+    """The per-step MMA program of the tcgen05 rollout (host-built once per shape, kept on the device)."""
+    key = (D, S, H, A, E, str(dev))
+    hit = _tc_plans.get(key)
+    if hit is None:
+        pb, kb = C.c_int64(), C.c_int64()
+        L.call_host("mrssm_rollout_tc_plan_bytes", D, S, H, A, E, C.byref(pb), C.byref(kb))
+        host = torch.zeros(pb.value, dtype=torch.uint8)
+        L.call_host("mrssm_rollout_tc_plan", D, S, H, A, E, host.data_ptr(), pb.value)
+        n_pack = int(host[:64].view(torch.int32)[8])
+        hit = (host.to(dev), n_pack, int(kb.value))
+        _tc_plans[key] = hit
+    return hit
+
+
+def rollout_tc_weights(spec, E, w_sa, w_ih, w_hh, heads, dev):
+    """(plan, packed bf16 weight stream) of the tcgen05 rollout; the stream is re-packed when the masters change."""
+    D, S, H, A = spec.D, spec.S, spec.H, spec.A
+    plan, n_pack, packed_bytes = rollout_tc_plan(D, S, H, A, E, dev)
+    ws = [w_sa, w_ih, w_hh] + [w for hd in heads for w in (hd[0], hd[2])]
+    key = ("rollout_tc", E) + tuple(w.data_ptr() for w in ws)
+    ver = (_STATE["wversion"],) + tuple(w._version for w in ws)
+    hit = _wcache.get(key)
+    if hit is None or hit[0] != ver:
+        pa = L.RolloutArgs()
+        pa.D, pa.S, pa.H, pa.A, pa.n_experts = D, S, H, A, E
+        pa.w_sa, pa.w_ih, pa.w_hh = L.ptr(w_sa), L.ptr(w_ih), L.ptr(w_hh)
+        for i, hd in enumerate(heads):
+            pa.w1[i], pa.ld1[i], pa.w2[i] = L.ptr(hd[0]), hd[0].shape[1], L.ptr(hd[2])
+        out = hit[1] if hit is not None else torch.empty(packed_bytes, device=dev, dtype=torch.uint8)
+        L.call("mrssm_rollout_tc_pack", C.byref(pa), L.ptr_any(plan), n_pack, L.ptr_any(out))
+        hit = (ver, out)
+        _wcache[key] = hit
+    return plan, hit[1]
 
 
 def bump_weight_version():
