@@ -243,6 +243,8 @@ int mrssm_rollout_tc_plan_bytes(int32_t D, int32_t S, int32_t H, int32_t A, int3
 int mrssm_rollout_tc_plan(int32_t D, int32_t S, int32_t H, int32_t A, int32_t n_experts, void* host_buf, int64_t buflen);
 int mrssm_rollout_tc_pack(const mrssm_rollout_args* a, const void* plan_dev, int32_t n_pack, void* packed_dev, void* stream);
 int mrssm_rollout_tc_fwd(const mrssm_rollout_args* a, const void* plan_dev, const void* packed_dev, void* stream);
+/* tuning aid: device buffer of 3*512 int64 receiving clock64 stamps of one time step of CTA 0 (NULL = off) */
+int mrssm_rollout_tc_set_profile_buffer(void* dev_buf);
 
 /* BPTT through the rollout (autograd of transition_model.py:226-270).  Consumes the forward's
  * outputs/stash plus upstream gradients of every output; produces the data gradients and the

@@ -32,12 +32,12 @@ constexpr int MAXC = 26;                  // chunk planes per activation buffer 
 constexpr int XIN_CH = 6;                 // S + A <= 48
 constexpr int SLOT_BYTES = 14336;         // ring slot: 4 N=112 blocks, 2 N=208 blocks, 7 N=64 blocks
 constexpr int MAX_SLOTS = 8;
-constexpr int TC_THREADS = 640;
+constexpr int TC_THREADS = 608;
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 16;
 constexpr int ACC_STRIDE = 112;           // TMEM columns per gate accumulator / per fc1 set
 constexpr int F2_COL = 2 * ACC_STRIDE;    // fc2 accumulators: 64 columns per head
 constexpr int TC_MAX_HEADS = 4;
-constexpr int MAX_TILES = 112, MAX_OPS = 336;
+constexpr int MAX_TILES = 112, MAX_OPS = 336, MAX_RUNS = 192;
 constexpr int TC_MAGIC = 0x52544331;      // "RTC1"
 
 enum { BUF_XIN = 0, BUF_XU = 1, BUF_HPREV = 2, BUF_HNEW = 3 };
@@ -58,13 +58,20 @@ struct TcTile {
     uint32_t src_off, bytes;              // byte range of the packed image
     uint16_t op_begin, op_end;
     int8_t wait_ev, commit;               // event to wait for before the first MMA / commit barrier after the last (-1: none)
-    int16_t pad;
+    uint8_t run_begin, run_end;           // the same MMAs as runs (what the kernel issues)
 };
 struct TcOp {
     uint16_t a_off16;                     // A operand: byte offset >> 4 inside its buffer
     uint8_t a_buf, acc;
     uint16_t b_off16, d_col;              // B block offset >> 4 inside the ring slot; TMEM column
     uint32_t idesc;
+};
+struct TcRun {                            // `count` MMAs into one accumulator: A advances 2 chunk planes, B one block per MMA
+    uint16_t a_off16;
+    uint8_t a_buf, acc_first;
+    uint16_t b_off16, d_col;
+    uint32_t idesc;
+    uint32_t count;
 };
 struct TcPack {                           // how one B block [2][N][8] is gathered from an fp32 PyTorch-layout weight
     int32_t src_id, k0, kvalid, N;
@@ -75,6 +82,16 @@ struct TcPack {                           // how one B block [2][N][8] is gather
 struct TcHeader {
     int32_t magic, D, S, H, A, NH, n_tiles, n_ops, n_pack, cA, nD8, cAH, nH8;
     uint32_t packed_bytes, tile_off, op_off, pack_off, total_bytes;
+    uint32_t run_off;
+    int32_t n_runs;
+};
+// What the kernel itself reads of the plan, passed BY VALUE (kernel parameters live in the constant bank: the MMA issuer and
+// the producer index it with warp-uniform indices, so the loads and the descriptor arithmetic stay in uniform registers).
+constexpr int PROG_RUNS = 128, PROG_TILES = 96;
+struct TcProg {
+    uint4 runs[PROG_RUNS];                // {A desc lo without smem base, B desc lo slot-relative, idesc, d_col | acc<<10 | flip<<11 | count<<13}
+    uint32_t tiles[PROG_TILES];           // bytes/16 | n_runs<<10 | (wait_ev+1)<<13 | (commit+1)<<18
+    int32_t n_tiles, cA, nD8, cAH, nH8;
 };
 struct PackSrc {
     const float* p[N_SRC];
@@ -90,6 +107,7 @@ struct PlanBuilder {
     std::vector<TcTile> tiles;
     std::vector<TcOp> ops;
     std::vector<TcPack> packs;
+    std::vector<TcRun> runs;
     uint32_t packed = 0;
     int cur_wait = -1;
     bool first = true, open = false;
@@ -105,7 +123,8 @@ struct PlanBuilder {
             t.src_off = packed; t.bytes = 0;
             t.op_begin = t.op_end = (uint16_t)ops.size();
             t.wait_ev = (int8_t)(first ? cur_wait : -1);
-            t.commit = -1; t.pad = 0;
+            t.commit = -1;
+            t.run_begin = t.run_end = (uint8_t)runs.size();
             tiles.push_back(t);
             first = false; open = true;
         }
@@ -116,6 +135,23 @@ struct PlanBuilder {
         o.d_col = (uint16_t)d_col;
         o.idesc = tc::idesc_bf16(ROWS, N, 0, 0);
         ops.push_back(o);
+        {
+            TcTile& tl = tiles.back();
+            bool ext = false;
+            if (tl.run_end > tl.run_begin) {
+                TcRun& r = runs.back();
+                ext = acc && r.a_buf == o.a_buf && r.d_col == o.d_col && r.idesc == o.idesc && r.count < 7 &&
+                      o.a_off16 == r.a_off16 + r.count * (2 * CH_BYTES / 16) && o.b_off16 == r.b_off16 + r.count * 2 * (uint32_t)N;
+                if (ext) ++r.count;
+            }
+            if (!ext) {
+                TcRun r;
+                r.a_off16 = o.a_off16; r.a_buf = o.a_buf; r.acc_first = o.acc; r.b_off16 = o.b_off16; r.d_col = o.d_col;
+                r.idesc = o.idesc; r.count = 1;
+                runs.push_back(r);
+                tl.run_end = (uint8_t)runs.size();
+            }
+        }
         TcPack p;
         p.src_id = src_id; p.k0 = 16 * k; p.kvalid = std::max(0, std::min(16, kin - 16 * k)); p.N = N;
         p.seg_n[0] = seg0_n; p.seg_src[0] = seg0_src; p.seg_cnt[0] = seg0_cnt;
@@ -181,7 +217,9 @@ void build_plan(int D, int S, int H, int A, int NH, PlanBuilder& pb, TcHeader& h
     h.tile_off = 128;
     h.op_off = h.tile_off + (uint32_t)(pb.tiles.size() * sizeof(TcTile));
     h.pack_off = (h.op_off + (uint32_t)(pb.ops.size() * sizeof(TcOp)) + 15u) & ~15u;
-    h.total_bytes = h.pack_off + (uint32_t)(pb.packs.size() * sizeof(TcPack));
+    h.run_off = h.pack_off + (uint32_t)(pb.packs.size() * sizeof(TcPack));
+    h.n_runs = (int)pb.runs.size();
+    h.total_bytes = h.run_off + (uint32_t)(pb.runs.size() * sizeof(TcRun));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -263,13 +301,54 @@ __global__ void rollout_tc_pack_kernel(const uint8_t* __restrict__ plan, PackSrc
 // ---------------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------------
+// tuning aid: clock64 stamps of time step PROF_STEP of CTA 0 (role 0 producer, 1 MMA issuer, 2 first epilogue warp)
+constexpr int PROF_STEP = 3, PROF_SLOTS = 512;   // prof buffer: 4 roles x PROF_SLOTS
+#define STAMP(role) do { if (prof && blockIdx.x == 0 && t == PROF_STEP && pi < PROF_SLOTS) prof[(role) * PROF_SLOTS + pi++] = clock64(); } while (0)
+
+// bf16-mode arithmetic: MUFU-based, absolute error ~1e-7 (the GEMM operands are rounded to bf16 anyway)
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.f + ex2_approx(-1.4426950409f * x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - 2.f * rcp_approx(1.f + ex2_approx(2.8853900818f * x)); }
+__device__ __forceinline__ float softplus_fast(float x) { return x > 20.f ? x : 0.6931471806f * lg2_approx(1.f + ex2_approx(1.4426950409f * x)); }
+__device__ __forceinline__ float act_fast(float v, int act) {
+    if (act == MRSSM_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == MRSSM_ACT_ELU) return v > 0.f ? v : ex2_approx(1.4426950409f * v) - 1.f;
+    return v;
+}
+// waits of the many (epilogue) and the patient (producer): back off so the spinning warps leave the issue slots to the
+// MMA warp and to the epilogue warps that have work
+__device__ __forceinline__ void wait_backoff(uint64_t* bar, uint32_t parity) {
+    const uint32_t b = tc::smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t it = 0; !done; ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(b), "r"(parity)
+            : "memory");
+        if (!done) {
+            __nanosleep(20);
+            if (it > (1u << 22)) {
+                printf("mrssm rollout_tc: barrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+                __trap();
+            }
+        }
+    }
+}
+
+// Warp roles.  The MMA issuer is the highest warp id of its scheduler (the issue arbiter favours high warp ids).
+constexpr int PROD_WARP = 16, ALLOC_WARP = 17, MMA_WARP = 18;
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
-rollout_tc_fwd_kernel(const mrssm_rollout_args a, const uint8_t* __restrict__ plan, const uint8_t* __restrict__ packed, const int NS) {
+rollout_tc_fwd_kernel(const __grid_constant__ mrssm_rollout_args a, const __grid_constant__ TcProg prog, const uint8_t* __restrict__ packed,
+                      const int NS, const int RPG, long long* __restrict__ prof) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full[MAX_SLOTS], empty[MAX_SLOTS], ev[N_EV], cm[N_CM];
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(16) TcTile tiles_s[MAX_TILES];
-    __shared__ __align__(16) TcOp ops_s[MAX_OPS];
     __shared__ float bias_x[8 * MAXC], bias_g[4][8 * MAXC], bias_1[TC_MAX_HEADS][8 * MAXC], bias_2[TC_MAX_HEADS][64];
     __shared__ uint32_t smask_s[32];                           // fusion subset (expert bitmask) of every state dim
     __shared__ const float* emb_pre_s[TC_MAX_HEADS];
@@ -278,22 +357,14 @@ rollout_tc_fwd_kernel(const mrssm_rollout_args a, const uint8_t* __restrict__ pl
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* const smem = smem_raw + (smem0 - tc::smem_u32(smem_raw));
-    const TcHeader* const hd_g = reinterpret_cast<const TcHeader*>(plan);
     const int D = a.D, S = a.S, H = a.H, A = a.A, E = a.n_experts, NH = 1 + E, B = a.B, T = a.T;
-    const int n_tiles = hd_g->n_tiles, cA = hd_g->cA, nD8 = hd_g->nD8, cAH = hd_g->cAH, nH8 = hd_g->nH8;
-    const int b0 = blockIdx.x * ROWS;
-    if (hd_g->magic != TC_MAGIC || hd_g->D != D || hd_g->S != S || hd_g->H != H || hd_g->A != A || hd_g->NH != NH || n_tiles > MAX_TILES ||
-        hd_g->n_ops > MAX_OPS) {
-        if (tid == 0) printf("mrssm rollout_tc: plan does not match the call\n");
-        __trap();
-    }
+    const int n_tiles = prog.n_tiles, cA = prog.cA, nD8 = prog.nD8, cAH = prog.cAH, nH8 = prog.nH8;
+    // MMA row r (0..63) <-> sequence b0 + (r/16)*RPG + r%16, valid when r%16 < RPG: with RPG = 8 a CTA owns 32 sequences and
+    // every epilogue thread carries one valid row (half the elementwise work per CTA, twice the CTAs)
+    const int b0 = blockIdx.x * 4 * RPG;
 
     // ---- prologue ---------------------------------------------------------------------------------------
     {
-        const uint4* ts = reinterpret_cast<const uint4*>(plan + hd_g->tile_off);
-        for (int i = tid; i < n_tiles; i += TC_THREADS) reinterpret_cast<uint4*>(tiles_s)[i] = ts[i];
-        const uint32_t* os = reinterpret_cast<const uint32_t*>(plan + hd_g->op_off);
-        for (int i = tid; i < hd_g->n_ops * 3; i += TC_THREADS) reinterpret_cast<uint32_t*>(ops_s)[i] = os[i];
         for (int j = tid; j < 8 * MAXC; j += TC_THREADS) {
             const bool ok = j < D;
             bias_x[j] = ok ? a.b_sa[j] : 0.f;
@@ -325,21 +396,21 @@ rollout_tc_fwd_kernel(const mrssm_rollout_args a, const uint8_t* __restrict__ pl
         for (int i = 0; i < N_CM; ++i) tc::mbar_init(tc::smem_u32(&cm[i]), 1);
         tc::fence_barrier_init();
     }
-    if (warp == 2) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), 512);
+    if (warp == ALLOC_WARP) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), 512);
     __syncthreads();
     // h_{-1} (fp32 + bf16 operand) and xin of step 0
     for (int i = tid; i < ROWS * D; i += TC_THREADS) {
-        const int r = i / D, j = i - r * D;
-        const float v = (b0 + r < B) ? a.prev_belief[(long long)(b0 + r) * D + j] : 0.f;
+        const int r = i / D, j = i - r * D, seq = b0 + (r >> 4) * RPG + (r & 15);
+        const float v = ((r & 15) < RPG && seq < B) ? a.prev_belief[(long long)seq * D + j] : 0.f;
         *reinterpret_cast<float*>(smem + OFF_HF + (j >> 3) * (ROWS * 32) + r * 32 + (j & 7) * 4) = v;
         *reinterpret_cast<bf16*>(smem + OFF_H0 + (j >> 3) * CH_BYTES + r * 16 + (j & 7) * 2) = __float2bfloat16(v);
     }
     for (int i = tid; i < ROWS * (S + A); i += TC_THREADS) {
-        const int r = i / (S + A), j = i - r * (S + A);
+        const int r = i / (S + A), j = i - r * (S + A), seq = b0 + (r >> 4) * RPG + (r & 15);
         float v = 0.f;
-        if (b0 + r < B) {
-            if (j < S) v = a.prev_state[(long long)(b0 + r) * S + j] * (a.nonterminals ? a.nonterminals[b0 + r] : 1.f);
-            else v = a.actions[(long long)(b0 + r) * A + (j - S)];
+        if ((r & 15) < RPG && seq < B) {
+            if (j < S) v = a.prev_state[(long long)seq * S + j] * (a.nonterminals ? a.nonterminals[seq] : 1.f);
+            else v = a.actions[(long long)seq * A + (j - S)];
         }
         *reinterpret_cast<bf16*>(smem + OFF_XIN + (j >> 3) * CH_BYTES + r * 16 + (j & 7) * 2) = __float2bfloat16(v);
     }
@@ -349,77 +420,102 @@ rollout_tc_fwd_kernel(const mrssm_rollout_args a, const uint8_t* __restrict__ pl
     tc::tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp == 0) {
+    if (warp == PROD_WARP) {
         // ---- weight producer ------------------------------------------------------------------------------
         if (lane == 0) {
-            uint32_t cnt = 0;
+            int pi = 0;
+            uint32_t slot = 0, phase = 0;
             for (int t = 0; t < T; ++t) {
-                for (int ti = 0; ti < n_tiles; ++ti, ++cnt) {
-                    const int s = cnt % NS;
-                    tc::mbar_wait(tc::smem_u32(&empty[s]), ((cnt / NS) & 1) ^ 1);
-                    const uint32_t bar = tc::smem_u32(&full[s]);
-                    const uint32_t bytes = tiles_s[ti].bytes;
+                uint32_t src = 0;
+                for (int ti = 0; ti < n_tiles; ++ti) {
+                    wait_backoff(&empty[slot], phase ^ 1u);
+                    STAMP(0);
+                    const uint32_t bar = tc::smem_u32(&full[slot]);
+                    const uint32_t bytes = (prog.tiles[ti] & 1023u) << 4;
                     r_expect_tx(bar, bytes);
-                    r_bulk_g2s(smem0 + OFF_RING + (uint32_t)s * SLOT_BYTES, packed + tiles_s[ti].src_off, bytes, bar);
+                    r_bulk_g2s(smem0 + OFF_RING + slot * SLOT_BYTES, packed + src, bytes, bar);
+                    src += bytes;
+                    if (++slot == (uint32_t)NS) { slot = 0; phase ^= 1u; }
                 }
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
+    } else if (warp == MMA_WARP) {
         // ---- MMA issuer ------------------------------------------------------------------------------------
         if (lane == 0) {
             const uint32_t hi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1, no swizzle
-            const uint32_t a_lbo = ((uint32_t)CH_BYTES >> 4) << 16;
-            uint32_t cnt = 0;
+            const uint32_t hdelta = (uint32_t)(OFF_H1 - OFF_H0) >> 4;
+            int pi = 0;
+            uint32_t slot = 0, phase = 0;
+            const uint32_t s16 = smem0 >> 4;
             for (int t = 0; t < T; ++t) {
                 const uint32_t par = (uint32_t)(t & 1);
-                uint32_t abase[4];
-                abase[BUF_XIN] = (smem0 + OFF_XIN) >> 4;
-                abase[BUF_XU] = (smem0 + OFF_XU) >> 4;
-                abase[BUF_HPREV] = (smem0 + ((t & 1) ? OFF_H1 : OFF_H0)) >> 4;
-                abase[BUF_HNEW] = (smem0 + ((t & 1) ? OFF_H0 : OFF_H1)) >> 4;
-                for (int ti = 0; ti < n_tiles; ++ti, ++cnt) {
-                    const TcTile tl = tiles_s[ti];
-                    if (tl.wait_ev >= 0) {
-                        if (tl.wait_ev == EV_XIN) {
-                            if (t > 0) tc::mbar_wait(tc::smem_u32(&ev[EV_XIN]), (uint32_t)((t - 1) & 1));
+                const uint32_t f1 = s16 + (par ? hdelta : 0u), f2 = s16 - (par ? hdelta : 0u);
+                int ri = 0;
+                for (int ti = 0; ti < n_tiles; ++ti) {
+                    const uint32_t tw = prog.tiles[ti];
+                    const int wev = (int)((tw >> 13) & 31u) - 1, cmi = (int)((tw >> 18) & 31u) - 1;
+                    if (wev >= 0) {
+                        if (wev == EV_XIN) {
+                            if (t > 0) tc::mbar_wait(tc::smem_u32(&ev[EV_XIN]), par ^ 1u);
                         } else {
-                            tc::mbar_wait(tc::smem_u32(&ev[tl.wait_ev]), par);
+                            tc::mbar_wait(tc::smem_u32(&ev[wev]), par);
                         }
                         tc::tc_fence_after();
                     }
-                    const int s = cnt % NS;
-                    tc::mbar_wait(tc::smem_u32(&full[s]), (cnt / NS) & 1);
+                    STAMP(1);
+                    tc::mbar_wait(tc::smem_u32(&full[slot]), phase);
                     tc::tc_fence_after();
-                    const uint32_t sb = (smem0 + OFF_RING + (uint32_t)s * SLOT_BYTES) >> 4;
-                    for (int oi = tl.op_begin; oi < tl.op_end; ++oi) {
-                        const TcOp o = ops_s[oi];
-                        const uint32_t n = ((o.idesc >> 17) & 63u) << 3;
-                        const uint32_t a_lo = ((abase[o.a_buf] + o.a_off16) & 0x3FFFu) | a_lbo;
-                        const uint32_t b_lo = ((sb + o.b_off16) & 0x3FFFu) | (n << 16);       // LBO = N * 16 bytes
-                        r_umma(tmem_base + o.d_col, a_lo, b_lo, hi, o.idesc, o.acc);
+                    STAMP(1);
+                    const uint32_t sb = (smem0 + OFF_RING + slot * SLOT_BYTES) >> 4;
+                    const int rend = ri + (int)((tw >> 10) & 7u);
+                    for (; ri < rend; ++ri) {
+                        const uint4 r = prog.runs[ri];
+                        const uint32_t fl = (r.w >> 11) & 3u, n2 = ((r.z >> 17) & 63u) << 4, cntm = (r.w >> 13) & 7u;
+                        const uint32_t a_lo = r.x + (fl == 1 ? f1 : (fl == 2 ? f2 : s16)), b_lo = r.y + sb;
+                        const uint32_t d = tmem_base + (r.w & 1023u), id = r.z;
+                        r_umma(d, a_lo, b_lo, hi, id, (r.w >> 10) & 1u);
+                        if (cntm > 1) r_umma(d, a_lo + 128u, b_lo + n2, hi, id, 1);
+                        if (cntm > 2) r_umma(d, a_lo + 256u, b_lo + 2 * n2, hi, id, 1);
+                        if (cntm > 3) r_umma(d, a_lo + 384u, b_lo + 3 * n2, hi, id, 1);
+                        if (cntm > 4) r_umma(d, a_lo + 512u, b_lo + 4 * n2, hi, id, 1);
+                        if (cntm > 5) r_umma(d, a_lo + 640u, b_lo + 5 * n2, hi, id, 1);
+                        if (cntm > 6) r_umma(d, a_lo + 768u, b_lo + 6 * n2, hi, id, 1);
                     }
-                    tc::umma_commit(tc::smem_u32(&empty[s]));
-                    if (tl.commit >= 0) tc::umma_commit(tc::smem_u32(&cm[tl.commit]));
+                    tc::umma_commit(tc::smem_u32(&empty[slot]));
+                    if (cmi >= 0) tc::umma_commit(tc::smem_u32(&cm[cmi]));
+                    STAMP(1);
+                    if (++slot == (uint32_t)NS) { slot = 0; phase ^= 1u; }
                 }
             }
         }
         __syncwarp();
-    } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI_WARPS) {
+    } else if (warp < EPI_WARPS) {
         // ---- epilogue warps ------------------------------------------------------------------------------
-        const int ew = warp - EPI_WARP0, q = ew & 3, p = ew >> 2, etid = tid - EPI_WARP0 * 32;
+        const int ew = warp, q = ew & 3, p = ew >> 2, etid = tid;
         const int r0 = 16 * q + (lane >> 2), r1 = r0 + 8, cj = 2 * (lane & 3);
-        const bool ok0 = b0 + r0 < B, ok1 = b0 + r1 < B;
+        const int seq0 = b0 + q * RPG + (lane >> 2), seq1 = seq0 + 8;
+        const bool two = RPG == 16;                                       // the second fragment row (r1) carries a sequence
+        const bool ok0 = seq0 < B, ok1 = two && seq1 < B;
+        const int ne = two ? 4 : 2;
         const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
         const uint32_t opnd0 = (uint32_t)(r0 * 16 + cj * 2), opnd1 = (uint32_t)(r1 * 16 + cj * 2);      // inside a bf16 chunk plane
         const uint32_t hf0 = smem0 + OFF_HF + (uint32_t)(r0 * 32 + cj * 4), hf1 = smem0 + OFF_HF + (uint32_t)(r1 * 32 + cj * 4);
         const int act = a.act;
+        const float min_std = a.min_std;
+        const bool det = a.det != 0;
+        int pi = 0;
+#define ESTAMP() do { if (ew == 0 && lane == 0) STAMP(2); } while (0)
+        int pj = 0;
+#define DSTAMP() do { if (prof && ew == 0 && lane == 0 && blockIdx.x == 0 && t == PROF_STEP && pj < PROF_SLOTS) prof[3 * PROF_SLOTS + pj++] = clock64(); } while (0)
         for (int t = 0; t < T; ++t) {
             const uint32_t par = (uint32_t)(t & 1);
-            const long long row0 = (long long)t * B + b0 + r0, row1 = row0 + 8;
+            const long long row0 = (long long)t * B + seq0, row1 = row0 + 8;
             // ---- E1: x = act(W_sa xin + b) -> XU, stash x ------------------------------------------------
-            tc::mbar_wait(tc::smem_u32(&cm[CM_X]), par);
+            ESTAMP();
+            wait_backoff(&cm[CM_X], par);
             tc::tc_fence_after();
+            ESTAMP();
             {
                 const int nc = ceil16(D) >> 3;
                 for (int c = p; c < nc; c += 4) {
@@ -428,23 +524,25 @@ rollout_tc_fwd_kernel(const mrssm_rollout_args a, const uint8_t* __restrict__ pl
                     wait_ld();
                     const int j = 8 * c + cj;
                     const float bA = bias_x[j], bB = bias_x[j + 1];
-                    const float x00 = act_apply(v[0] + bA, act), x01 = act_apply(v[1] + bB, act);
-                    const float x10 = act_apply(v[2] + bA, act), x11 = act_apply(v[3] + bB, act);
+                    const float x00 = act_fast(v[0] + bA, act), x01 = act_fast(v[1] + bB, act);
                     const uint32_t ch = smem0 + OFF_XU + (uint32_t)c * CH_BYTES;
                     st_shared_u32(ch + opnd0, pack_bf16x2(x00, x01));
-                    st_shared_u32(ch + opnd1, pack_bf16x2(x10, x11));
-                    if (a.st_x && j < D) {
-                        if (ok0) st_f2(a.st_x + row0 * D + j, x00, x01);
-                        if (ok1) st_f2(a.st_x + row1 * D + j, x10, x11);
+                    if (a.st_x && j < D && ok0) st_f2(a.st_x + row0 * D + j, x00, x01);
+                    if (two) {
+                        const float x10 = act_fast(v[2] + bA, act), x11 = act_fast(v[3] + bB, act);
+                        st_shared_u32(ch + opnd1, pack_bf16x2(x10, x11));
+                        if (a.st_x && j < D && ok1) st_f2(a.st_x + row1 * D + j, x10, x11);
                     }
                 }
             }
             epi_signal(&ev[EV_X], lane);
+            ESTAMP();
             // ---- E2: GRU gate math per column half -> h (fp32 + bf16 operand), beliefs, stash ----------------
             const uint32_t hnew = smem0 + ((t & 1) ? OFF_H0 : OFF_H1);
             for (int hf = 0; hf < 2; ++hf) {
-                tc::mbar_wait(tc::smem_u32(&cm[CM_GA + hf]), par);
+                wait_backoff(&cm[CM_GA + hf], par);
                 tc::tc_fence_after();
+                ESTAMP();
                 const int c_lo = hf ? cA : 0, c_hi = hf ? nD8 : cA;
                 for (int c = c_lo + p; c < c_hi; c += 4) {
                     const uint32_t col = (uint32_t)(8 * (c - c_lo));
@@ -452,26 +550,32 @@ rollout_tc_fwd_kernel(const mrssm_rollout_args a, const uint8_t* __restrict__ pl
                     ld_frag(tlane + col, vr);
                     ld_frag(tlane + ACC_STRIDE + col, vz);
                     ld_frag(tlane + 2 * ACC_STRIDE + col, vi);
+                    DSTAMP();
                     ld_frag(tlane + 3 * ACC_STRIDE + col, vh);
                     wait_ld();
+                    DSTAMP();
                     const int j = 8 * c + cj;
-                    const float2 hp0 = ld_shared_f2(hf0 + (uint32_t)c * (ROWS * 32)), hp1 = ld_shared_f2(hf1 + (uint32_t)c * (ROWS * 32));
+                    const float2 hp0 = ld_shared_f2(hf0 + (uint32_t)c * (ROWS * 32));
+                    float2 hp1 = make_float2(0.f, 0.f);
+                    if (two) hp1 = ld_shared_f2(hf1 + (uint32_t)c * (ROWS * 32));
                     const float hp[4] = {hp0.x, hp0.y, hp1.x, hp1.y};
+                    const float br[2] = {bias_g[0][j], bias_g[0][j + 1]}, bz[2] = {bias_g[1][j], bias_g[1][j + 1]};
+                    const float bi[2] = {bias_g[2][j], bias_g[2][j + 1]}, bh[2] = {bias_g[3][j], bias_g[3][j + 1]};
                     float rr[4], zz[4], nn[4], gg[4], hn[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int jj = j + (e & 1);
-                        rr[e] = sigmoidf_(vr[e] + bias_g[0][jj]);
-                        zz[e] = sigmoidf_(vz[e] + bias_g[1][jj]);
-                        gg[e] = vh[e] + bias_g[3][jj];
-                        nn[e] = tanhf(vi[e] + bias_g[2][jj] + rr[e] * gg[e]);
-                        hn[e] = (1.f - zz[e]) * nn[e] + zz[e] * hp[e];
+                        if (e < ne) {
+                            rr[e] = sigmoid_fast(vr[e] + br[e & 1]);
+                            zz[e] = sigmoid_fast(vz[e] + bz[e & 1]);
+                            gg[e] = vh[e] + bh[e & 1];
+                            nn[e] = tanh_fast(vi[e] + bi[e & 1] + rr[e] * gg[e]);
+                            hn[e] = (1.f - zz[e]) * nn[e] + zz[e] * hp[e];
+                        }
                     }
-                    st_shared_f2(hf0 + (uint32_t)c * (ROWS * 32), hn[0], hn[1]);
-                    st_shared_f2(hf1 + (uint32_t)c * (ROWS * 32), hn[2], hn[3]);
                     const uint32_t ch = hnew + (uint32_t)c * CH_BYTES;
+                    DSTAMP();
+                    st_shared_f2(hf0 + (uint32_t)c * (ROWS * 32), hn[0], hn[1]);
                     st_shared_u32(ch + opnd0, pack_bf16x2(hn[0], hn[1]));
-                    st_shared_u32(ch + opnd1, pack_bf16x2(hn[2], hn[3]));
                     if (ok0) {
                         const long long off = row0 * D + j;
                         st_f2(a.beliefs + off, hn[0], hn[1]);
@@ -480,16 +584,27 @@ rollout_tc_fwd_kernel(const mrssm_rollout_args a, const uint8_t* __restrict__ pl
                             st_f2(a.st_n + off, nn[0], nn[1]); st_f2(a.st_ghn + off, gg[0], gg[1]);
                         }
                     }
-                    if (ok1) {
-                        const long long off = row1 * D + j;
-                        st_f2(a.beliefs + off, hn[2], hn[3]);
-                        if (a.st_r) {
-                            st_f2(a.st_r + off, rr[2], rr[3]); st_f2(a.st_z + off, zz[2], zz[3]);
-                            st_f2(a.st_n + off, nn[2], nn[3]); st_f2(a.st_ghn + off, gg[2], gg[3]);
+                    if (two) {
+                        st_shared_f2(hf1 + (uint32_t)c * (ROWS * 32), hn[2], hn[3]);
+                        st_shared_u32(ch + opnd1, pack_bf16x2(hn[2], hn[3]));
+                        if (ok1) {
+                            const long long off = row1 * D + j;
+                            st_f2(a.beliefs + off, hn[2], hn[3]);
+                            if (a.st_r) {
+                                st_f2(a.st_r + off, rr[2], rr[3]); st_f2(a.st_z + off, zz[2], zz[3]);
+                                st_f2(a.st_n + off, nn[2], nn[3]); st_f2(a.st_ghn + off, gg[2], gg[3]);
+                            }
                         }
                     }
                 }
-                epi_signal(&ev[EV_HA + hf], lane);
+                DSTAMP();
+                tc::tc_fence_before();
+                tc::fence_proxy_async();
+                DSTAMP();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(tc::smem_u32(&ev[EV_HA + hf]));
+                DSTAMP();
+                ESTAMP();
             }
             // ---- E3: heads fc1 (+ hoisted embedding half) + act -> XU (as U), stash u ------------------------
             for (int hd = 0; hd < NH; ++hd) {
@@ -504,14 +619,16 @@ rollout_tc_fwd_kernel(const mrssm_rollout_args a, const uint8_t* __restrict__ pl
                         pre[i][0] = pre[i][1] = pre[i][2] = pre[i][3] = 0.f;
                         if (ep && c < c_hi) {
                             const int j = 8 * c + cj;
-                            if (ok0) { const float2 e0 = *reinterpret_cast<const float2*>(ep + row0 * H + j); pre[i][0] = e0.x; pre[i][1] = e0.y; }
-                            if (ok1) { const float2 e1 = *reinterpret_cast<const float2*>(ep + row1 * H + j); pre[i][2] = e1.x; pre[i][3] = e1.y; }
+                            if (ok0) { const float2 e0 = __ldg(reinterpret_cast<const float2*>(ep + row0 * H + j)); pre[i][0] = e0.x; pre[i][1] = e0.y; }
+                            if (ok1) { const float2 e1 = __ldg(reinterpret_cast<const float2*>(ep + row1 * H + j)); pre[i][2] = e1.x; pre[i][3] = e1.y; }
                         }
                     }
                     // (hd, half 0) of hd >= 1 also needs fc2 of head hd-1 to be done reading U: that commit was issued later
                     const int cmi = (hf == 0 && hd > 0) ? CM_F2 + hd - 1 : CM_F1 + 2 * hd + hf;
-                    tc::mbar_wait(tc::smem_u32(&cm[cmi]), par);
+                    ESTAMP();
+                    wait_backoff(&cm[cmi], par);
                     tc::tc_fence_after();
+                    ESTAMP();
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int c = c_lo + p + 4 * i;
@@ -521,50 +638,54 @@ rollout_tc_fwd_kernel(const mrssm_rollout_args a, const uint8_t* __restrict__ pl
                             wait_ld();
                             const int j = 8 * c + cj;
                             const float bA = bias_1[hd][j], bB = bias_1[hd][j + 1];
-                            const float u00 = act_apply(v[0] + bA + pre[i][0], act), u01 = act_apply(v[1] + bB + pre[i][1], act);
-                            const float u10 = act_apply(v[2] + bA + pre[i][2], act), u11 = act_apply(v[3] + bB + pre[i][3], act);
+                            const float u00 = act_fast(v[0] + bA + pre[i][0], act), u01 = act_fast(v[1] + bB + pre[i][1], act);
                             const uint32_t ch = smem0 + OFF_XU + (uint32_t)c * CH_BYTES;
                             st_shared_u32(ch + opnd0, pack_bf16x2(u00, u01));
-                            st_shared_u32(ch + opnd1, pack_bf16x2(u10, u11));
-                            if (su) {
-                                if (ok0) st_f2(su + row0 * H + j, u00, u01);
-                                if (ok1) st_f2(su + row1 * H + j, u10, u11);
+                            if (su && ok0) st_f2(su + row0 * H + j, u00, u01);
+                            if (two) {
+                                const float u10 = act_fast(v[2] + bA + pre[i][2], act), u11 = act_fast(v[3] + bB + pre[i][3], act);
+                                st_shared_u32(ch + opnd1, pack_bf16x2(u10, u11));
+                                if (su && ok1) st_f2(su + row1 * H + j, u10, u11);
                             }
                         }
                     }
                     epi_signal(&ev[EV_U0 + 2 * hd + hf], lane);
+                    ESTAMP();
                 }
             }
             // ---- E4: heads fc2 -> (mean, softplus + min_std), prior sample, fusion, posterior sample, next xin --
             const bool more = t + 1 < T;
             if (more) {                                       // action columns of xin(t+1): the buffer is idle since E1
                 for (int i = etid; i < ROWS * A; i += EPI_WARPS * 32) {
-                    const int r = i / A, k = i - r * A, col = S + k;
-                    const float v = (b0 + r < B) ? a.actions[((long long)(t + 1) * B + b0 + r) * A + k] : 0.f;
+                    const int r = i / A, k = i - r * A, col = S + k, seq = b0 + (r >> 4) * RPG + (r & 15);
+                    const float v = ((r & 15) < RPG && seq < B) ? a.actions[((long long)(t + 1) * B + seq) * A + k] : 0.f;
                     st_shared_bf16(smem0 + OFF_XIN + (uint32_t)((col >> 3) * CH_BYTES + r * 16 + (col & 7) * 2), v);
                 }
             }
             const int s0 = 8 * p + cj;                        // this thread: state dims s0, s0+1 of rows r0, r1
             const bool live = 8 * p < S;
+            const bool pairok = s0 + 1 < S && (S & 1) == 0;   // float2 stores / loads of (s0, s0+1)
             float epr[4] = {0.f, 0.f, 0.f, 0.f}, epo[4] = {0.f, 0.f, 0.f, 0.f}, mk[2] = {1.f, 1.f};
             if (live) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int s = s0 + (e & 1);
                     const bool okr = (e < 2) ? ok0 : ok1;
-                    if (okr && s < S) {
+                    if (okr && s < S && !det) {
                         const long long off = ((e < 2) ? row0 : row1) * S + s;
-                        if (a.eps_prior && !a.det) epr[e] = a.eps_prior[off];
-                        if (a.eps_post && !a.det && E > 0) epo[e] = a.eps_post[off];
+                        epr[e] = __ldg(a.eps_prior + off);
+                        if (E > 0) epo[e] = __ldg(a.eps_post + off);
                     }
                 }
                 if (more && a.nonterminals) {
-                    if (ok0) mk[0] = a.nonterminals[row0 + B];
-                    if (ok1) mk[1] = a.nonterminals[row1 + B];
+                    if (ok0) mk[0] = __ldg(a.nonterminals + row0 + B);
+                    if (ok1) mk[1] = __ldg(a.nonterminals + row1 + B);
                 }
             }
-            tc::mbar_wait(tc::smem_u32(&cm[CM_F2 + NH - 1]), par);
+            ESTAMP();
+            wait_backoff(&cm[CM_F2 + NH - 1], par);
             tc::tc_fence_after();
+            ESTAMP();
             if (live) {
                 float mu[TC_MAX_HEADS][4], sg[TC_MAX_HEADS][4];
 #pragma unroll
@@ -576,64 +697,84 @@ rollout_tc_fwd_kernel(const mrssm_rollout_args a, const uint8_t* __restrict__ pl
                 }
                 wait_ld();
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int s = s0 + (e & 1);
-                    const int r = (e < 2) ? r0 : r1;
-                    const bool okr = (e < 2) ? ok0 : ok1;
-                    if (s >= S) continue;
-                    const long long off = ((e < 2) ? row0 : row1) * S + s;
-                    float om[TC_MAX_HEADS], os[TC_MAX_HEADS];
+                for (int rr = 0; rr < 2; ++rr) {                  // one fragment row at a time (register pressure)
+                    if (rr == 1 && !two) continue;
+                    const bool okr = rr ? ok1 : ok0;
+                    float o_pm[2], o_ps[2], o_pst[2], o_qm[2], o_qs[2], o_qst[2], o_em[TC_MAX_HEADS][2], o_es[TC_MAX_HEADS][2];
 #pragma unroll
-                    for (int h = 0; h < TC_MAX_HEADS; ++h) {
-                        if (h < NH) {
-                            om[h] = mu[h][e] + bias_2[h][s];
-                            os[h] = softplusf_(sg[h][e] + bias_2[h][32 + s]) + a.min_std;
+                    for (int ee = 0; ee < 2; ++ee) {
+                        const int e = 2 * rr + ee;
+                        const int s = min(s0 + ee, 31);
+#pragma unroll
+                        for (int h = 0; h < TC_MAX_HEADS; ++h) {
+                            if (h < NH) {
+                                o_em[h][ee] = mu[h][e] + bias_2[h][s];
+                                o_es[h][ee] = softplus_fast(sg[h][e] + bias_2[h][32 + s]) + min_std;
+                            }
                         }
-                    }
-                    const float pm = om[0], ps = os[0];
-                    const float pst = a.det ? pm : fmaf(ps, epr[e], pm);
-                    float nxt = pst;
-                    if (okr) {
-                        a.prior_means[off] = pm; a.prior_stds[off] = ps; a.prior_states[off] = pst;
-                    }
-                    if (E > 0) {
-                        float qm, qs;
-                        if (a.n_subsets == 0) {
-                            qm = om[1]; qs = os[1];
-                        } else {
-                            const unsigned mask = smask_s[s];
-                            float sumT = 0.f, sumMT = 0.f;
+                        o_pm[ee] = o_em[0][ee];
+                        o_ps[ee] = o_es[0][ee];
+                        o_pst[ee] = det ? o_pm[ee] : fmaf(o_ps[ee], epr[e], o_pm[ee]);
+                        float nxt = o_pst[ee];
+                        if (E > 0) {
+                            if (a.n_subsets == 0) {
+                                o_qm[ee] = o_em[1][ee];
+                                o_qs[ee] = o_es[1][ee];
+                            } else {
+                                const unsigned mask = smask_s[s];
+                                float sumT = 0.f, sumMT = 0.f;
 #pragma unroll
-                            for (int h = 1; h < TC_MAX_HEADS; ++h) {
-                                if (h < NH && (mask & (1u << (h - 1)))) {
-                                    const float tt = 1.f / os[h];
-                                    sumT += tt;
-                                    sumMT = fmaf(om[h], tt, sumMT);
+                                for (int h = 1; h < TC_MAX_HEADS; ++h) {
+                                    if (h < NH && (mask & (1u << (h - 1)))) {
+                                        const float tt = rcp_approx(o_es[h][ee]);
+                                        sumT += tt;
+                                        sumMT = fmaf(o_em[h][ee], tt, sumMT);
+                                    }
                                 }
+                                o_qs[ee] = rcp_approx(sumT);
+                                o_qm[ee] = sumMT * o_qs[ee];
                             }
-                            qm = sumMT / sumT;
-                            qs = 1.f / sumT;
+                            o_qst[ee] = det ? o_qm[ee] : fmaf(o_qs[ee], epo[e], o_qm[ee]);
+                            nxt = o_qst[ee];
                         }
-                        const float qst = a.det ? qm : fmaf(qs, epo[e], qm);
-                        if (okr) {
-#pragma unroll
-                            for (int h = 1; h < TC_MAX_HEADS; ++h) {
-                                if (h < NH) { exp_means_s[h][off] = om[h]; exp_stds_s[h][off] = os[h]; }
-                            }
-                            a.post_means[off] = qm; a.post_stds[off] = qs; a.post_states[off] = qst;
-                        }
-                        nxt = qst;
+                        if (more && s0 + ee < S)
+                            st_shared_bf16(smem0 + OFF_XIN + (uint32_t)((s >> 3) * CH_BYTES + (rr ? r1 : r0) * 16 + (s & 7) * 2),
+                                           okr ? nxt * mk[rr] : 0.f);
                     }
-                    if (more)
-                        st_shared_bf16(smem0 + OFF_XIN + (uint32_t)((s >> 3) * CH_BYTES + r * 16 + (s & 7) * 2), okr ? nxt * mk[e >> 1] : 0.f);
+                    if (!okr) continue;
+                    // outputs: (s0, s0+1) of one row are adjacent in memory
+                    const long long off = (rr ? row1 : row0) * S + s0;
+                    auto put = [&](float* base, float v0, float v1) {
+                        if (pairok) st_f2(base + off, v0, v1);
+                        else {
+                            if (s0 < S) base[off] = v0;
+                            if (s0 + 1 < S) base[off + 1] = v1;
+                        }
+                    };
+                    put(a.prior_means, o_pm[0], o_pm[1]);
+                    put(a.prior_stds, o_ps[0], o_ps[1]);
+                    put(a.prior_states, o_pst[0], o_pst[1]);
+                    if (E > 0) {
+                        put(a.post_means, o_qm[0], o_qm[1]);
+                        put(a.post_stds, o_qs[0], o_qs[1]);
+                        put(a.post_states, o_qst[0], o_qst[1]);
+#pragma unroll
+                        for (int h = 1; h < TC_MAX_HEADS; ++h) {
+                            if (h < NH) {
+                                put(exp_means_s[h], o_em[h][0], o_em[h][1]);
+                                put(exp_stds_s[h], o_es[h][0], o_es[h][1]);
+                            }
+                        }
+                    }
                 }
             }
             epi_signal(&ev[EV_XIN], lane);
+            ESTAMP();
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == ALLOC_WARP) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, 512);
     }
@@ -654,7 +795,7 @@ extern "C" int mrssm_rollout_tc_plan_bytes(int32_t D, int32_t S, int32_t H, int3
     PlanBuilder pb;
     TcHeader h;
     build_plan(D, S, H, A, 1 + n_experts, pb, h);
-    MRSSM_CHECK(h.n_tiles <= MAX_TILES && h.n_ops <= MAX_OPS, "rollout_tc: program too long (%d tiles, %d MMAs)", h.n_tiles, h.n_ops);
+    MRSSM_CHECK(h.n_tiles <= MAX_TILES && h.n_ops <= MAX_OPS && h.n_runs < MAX_RUNS, "rollout_tc: program too long (%d tiles, %d MMAs)", h.n_tiles, h.n_ops);
     if (plan_bytes) *plan_bytes = h.total_bytes;
     if (packed_bytes) *packed_bytes = h.packed_bytes;
     return 0;
@@ -665,7 +806,7 @@ extern "C" int mrssm_rollout_tc_plan(int32_t D, int32_t S, int32_t H, int32_t A,
     PlanBuilder pb;
     TcHeader h;
     build_plan(D, S, H, A, 1 + n_experts, pb, h);
-    MRSSM_CHECK(h.n_tiles <= MAX_TILES && h.n_ops <= MAX_OPS, "rollout_tc: program too long (%d tiles, %d MMAs)", h.n_tiles, h.n_ops);
+    MRSSM_CHECK(h.n_tiles <= MAX_TILES && h.n_ops <= MAX_OPS && h.n_runs < MAX_RUNS, "rollout_tc: program too long (%d tiles, %d MMAs)", h.n_tiles, h.n_ops);
     MRSSM_CHECK(buflen >= (int64_t)h.total_bytes, "rollout_tc_plan: buffer too small (%lld < %u)", (long long)buflen, h.total_bytes);
     uint8_t* o = (uint8_t*)host_buf;
     memset(o, 0, h.total_bytes);
@@ -673,6 +814,7 @@ extern "C" int mrssm_rollout_tc_plan(int32_t D, int32_t S, int32_t H, int32_t A,
     memcpy(o + h.tile_off, pb.tiles.data(), pb.tiles.size() * sizeof(TcTile));
     memcpy(o + h.op_off, pb.ops.data(), pb.ops.size() * sizeof(TcOp));
     memcpy(o + h.pack_off, pb.packs.data(), pb.packs.size() * sizeof(TcPack));
+    memcpy(o + h.run_off, pb.runs.data(), pb.runs.size() * sizeof(TcRun));
     return 0;
 }
 
@@ -698,7 +840,19 @@ extern "C" int mrssm_rollout_tc_pack(const mrssm_rollout_args* a, const void* pl
     return 0;
 }
 
-int rollout_check(const mrssm_rollout_args* a);
+static long long* g_tc_prof = nullptr;
+static int g_tc_rpg = 0;
+/* tuning aid: sequences per 16-row group of a CTA (16 -> 64 sequences per CTA, 8 -> 32; 0 = automatic) */
+extern "C" int mrssm_rollout_tc_set_rows(int32_t rows_per_group) {
+    MRSSM_CHECK(rows_per_group == 0 || rows_per_group == 8 || rows_per_group == 16, "rollout_tc_set_rows: 0, 8 or 16");
+    g_tc_rpg = rows_per_group;
+    return 0;
+}
+/* tuning aid: device buffer of 3*512 int64 receiving clock64 stamps of one time step (NULL = off) */
+extern "C" int mrssm_rollout_tc_set_profile_buffer(void* dev_buf) {
+    g_tc_prof = (long long*)dev_buf;
+    return 0;
+}
 
 extern "C" int mrssm_rollout_tc_fwd(const mrssm_rollout_args* a, const void* plan_dev, const void* packed_dev, void* stream) {
     MRSSM_CHECK(a && plan_dev && packed_dev, "rollout_tc_fwd: bad arguments");
@@ -715,12 +869,42 @@ extern "C" int mrssm_rollout_tc_fwd(const mrssm_rollout_args* a, const void* pla
     MRSSM_CHECK(a->det || a->eps_prior, "rollout_tc_fwd: eps_prior missing");
     cudaFuncAttributes fa;
     MRSSM_CUDA(cudaFuncGetAttributes(&fa, rollout_tc_fwd_kernel));
+    static thread_local TcProg prog;
+    static thread_local int prog_key[5] = {-1, -1, -1, -1, -1};
+    if (prog_key[0] != a->D || prog_key[1] != a->S || prog_key[2] != a->H || prog_key[3] != a->A || prog_key[4] != a->n_experts) {
+        PlanBuilder pb;
+        TcHeader h;
+        build_plan(a->D, a->S, a->H, a->A, 1 + a->n_experts, pb, h);
+        MRSSM_CHECK(h.n_tiles <= PROG_TILES && h.n_runs <= PROG_RUNS, "rollout_tc: program too long (%d tiles, %d runs)", h.n_tiles, h.n_runs);
+        memset(&prog, 0, sizeof(prog));
+        for (int i = 0; i < h.n_runs; ++i) {
+            const TcRun& o = pb.runs[i];
+            const uint32_t n = ((o.idesc >> 17) & 63u) << 3;
+            uint32_t boff = OFF_XIN, flip = 0;
+            if (o.a_buf == BUF_XU) boff = OFF_XU;
+            if (o.a_buf == BUF_HPREV) { boff = OFF_H0; flip = 1; }      // odd steps: + (OFF_H1 - OFF_H0)
+            if (o.a_buf == BUF_HNEW) { boff = OFF_H1; flip = 2; }       // odd steps: - (OFF_H1 - OFF_H0)
+            prog.runs[i].x = ((boff >> 4) + o.a_off16) | (((uint32_t)CH_BYTES >> 4) << 16);
+            prog.runs[i].y = (uint32_t)o.b_off16 | (n << 16);           // LBO = N * 16 bytes
+            prog.runs[i].z = o.idesc;
+            prog.runs[i].w = (uint32_t)o.d_col | ((uint32_t)o.acc_first << 10) | (flip << 11) | (o.count << 13);
+        }
+        for (int i = 0; i < h.n_tiles; ++i) {
+            const TcTile& t = pb.tiles[i];
+            prog.tiles[i] = (t.bytes >> 4) | ((uint32_t)(t.run_end - t.run_begin) << 10) | ((uint32_t)(t.wait_ev + 1) << 13) | ((uint32_t)(t.commit + 1) << 18);
+        }
+        prog.n_tiles = h.n_tiles; prog.cA = h.cA; prog.nD8 = h.nD8; prog.cAH = h.cAH; prog.nH8 = h.nH8;
+        prog_key[0] = a->D; prog_key[1] = a->S; prog_key[2] = a->H; prog_key[3] = a->A; prog_key[4] = a->n_experts;
+    }
     const int avail = 232448 - (int)fa.sharedSizeBytes - 1024 - OFF_RING;
     const int NS = std::min(MAX_SLOTS, avail / SLOT_BYTES);
     MRSSM_CHECK(NS >= 2, "rollout_tc_fwd: no room for the weight ring (%d bytes left)", avail);
     const size_t dyn = (size_t)OFF_RING + (size_t)NS * SLOT_BYTES + 1024;
     MRSSM_CUDA(cudaFuncSetAttribute(rollout_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    rollout_tc_fwd_kernel<<<(a->B + ROWS - 1) / ROWS, TC_THREADS, dyn, (cudaStream_t)stream>>>(*a, (const uint8_t*)plan_dev, (const uint8_t*)packed_dev, NS);
+    // 64 sequences per CTA when that already fills the machine's appetite, else 32 (one valid row per epilogue thread)
+    const int RPG = g_tc_rpg ? g_tc_rpg : ((a->B + 63) / 64 >= 74 ? 16 : 8);
+    rollout_tc_fwd_kernel<<<(a->B + 4 * RPG - 1) / (4 * RPG), TC_THREADS, dyn, (cudaStream_t)stream>>>(*a, prog, (const uint8_t*)packed_dev, NS, RPG,
+                                                                                                        g_tc_prof);
     MRSSM_LAUNCH_CHECK();
     return 0;
 }

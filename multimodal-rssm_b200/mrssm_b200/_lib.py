@@ -126,6 +126,7 @@ SYMBOLS = {
     "mrssm_rollout_tc_plan": [_i32, _i32, _i32, _i32, _i32, _vp, _i64],
     "mrssm_rollout_tc_pack": [C.POINTER(RolloutArgs), _vp, _i32, _vp, _vp],
     "mrssm_rollout_tc_fwd": [C.POINTER(RolloutArgs), _vp, _vp, _vp],
+    "mrssm_rollout_tc_set_profile_buffer": [_vp],
     "mrssm_rollout_bwd": [C.POINTER(RolloutBwdArgs), _vp],
     "mrssm_latent_fwd": [C.POINTER(LatentArgs), _vp],
     "mrssm_latent_bwd": [C.POINTER(LatentArgs), _vp],

@@ -35,6 +35,7 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+__device__ int g_ps_a = 4224, g_lbo_b = 0;
 __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int amode, int bmode, int pattern, int iters, int conv, long long* out, int Mrows = 128) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar;
@@ -75,7 +76,8 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int amode, int bmod
             }
         } else if (pattern == 4) {            // tight: descriptors precomputed, unrolled by 8, only adds between MMAs
             uint64_t ad = tc::smem_desc_sw128(sA, 16, 1024), bd = tc::smem_desc_sw128(sB, 16, 1024);
-            if (amode == 0) ad = desc_plain(sA, PS, 128);
+            if (amode == 0) ad = desc_plain(sA, g_ps_a, 128);
+            if (bmode == 0) bd = desc_plain(sB, g_lbo_b ? g_lbo_b : N * 16, 128);
             for (int i = 0; i < iters; i += 8) {
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -107,11 +109,44 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int amode, int bmod
     }
 }
 
-int main() {
+int main(int argc, char** argv) {
     long long* d;
     cudaMalloc(&d, 16);
     cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const int iters = 2000;
+    if (argc > 1 && argv[1][0] == 't') {   // tight loop (pattern 4), un-swizzled A with LBO = psa, B un-swizzled (LBO = lbob or N*16) or swizzled
+        printf("M   N  psA  bmode lboB  issue_cyc/mma  total_cyc/mma\n");
+        for (int M : {64, 128})
+            for (int N : {64, 112, 208})
+                for (int psa : {1024, 1152, 4224})
+                    for (int bm = 0; bm < 3; ++bm) {
+                        int lbob = bm == 1 ? (N * 16 + 128) : 0;      // bm 0: LBO = N*16; bm 1: N*16 + 128 (odd/even flip); bm 2: swizzled
+                        cudaMemcpyToSymbol(g_ps_a, &psa, 4);
+                        cudaMemcpyToSymbol(g_lbo_b, &lbob, 4);
+                        rate_kernel<<<148, 128, 200 * 1024>>>(N, 0, bm == 2 ? 1 : 0, 4, iters, 0, d, M);
+                        cudaError_t e = cudaDeviceSynchronize();
+                        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+                        long long h[2];
+                        cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+                        printf("%3d %3d %5d %5d %5d  %10.1f  %10.1f\n", M, N, psa, bm, lbob ? lbob : N * 16, (double)h[0] / iters, (double)h[1] / iters);
+                    }
+        return 0;
+    }
+    if (argc > 1) {   // sweep for csrc/rollout_tc.cu: M x N x operand layouts, one accumulator, same operands (pattern 0)
+        printf("M   N  amode bmode  issue_cyc/mma  total_cyc/mma   (mode 0 = un-swizzled K-major planes, 1 = 128B swizzle)\n");
+        for (int M : {64, 128})
+            for (int N : {64, 96, 112, 208, 256})
+                for (int amode = 0; amode < 2; ++amode)
+                    for (int bmode = 0; bmode < 2; ++bmode) {
+                        rate_kernel<<<148, 128, 200 * 1024>>>(N, amode, bmode, 0, iters, 0, d, M);
+                        cudaError_t e = cudaDeviceSynchronize();
+                        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+                        long long h[2];
+                        cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+                        printf("%3d %3d %5d %5d  %10.1f  %10.1f\n", M, N, amode, bmode, (double)h[0] / iters, (double)h[1] / iters);
+                    }
+        return 0;
+    }
     printf("N amode bmode pattern  issue_cyc/mma  total_cyc/mma   (M=128,K=16; floor N/2)\n");
     printf("(last column block: conv = 1 -> whole warp runs the loop, MMA under elect.sync)\n");
     for (int conv = 0; conv < 2; ++conv)

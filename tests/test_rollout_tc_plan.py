@@ -10,7 +10,8 @@ import pytest
 
 ROWS, CH_BYTES, SLOT_BYTES, ACC, F2 = 64, 1024, 14336, 112, 224
 TILE = np.dtype([("src_off", "<u4"), ("bytes", "<u4"), ("op_begin", "<u2"), ("op_end", "<u2"), ("wait_ev", "i1"), ("commit", "i1"),
-                 ("pad", "<i2")])
+                 ("run_begin", "u1"), ("run_end", "u1")])
+RUN = np.dtype([("a_off16", "<u2"), ("a_buf", "u1"), ("acc_first", "u1"), ("b_off16", "<u2"), ("d_col", "<u2"), ("idesc", "<u4"), ("count", "<u4")])
 OP = np.dtype([("a_off16", "<u2"), ("a_buf", "u1"), ("acc", "u1"), ("b_off16", "<u2"), ("d_col", "<u2"), ("idesc", "<u4")])
 PACK = np.dtype([("src_id", "<i4"), ("k0", "<i4"), ("kvalid", "<i4"), ("N", "<i4"), ("seg_n", "<i4", 2), ("seg_src", "<i4", 2),
                  ("seg_cnt", "<i4", 2), ("dst_off", "<u4"), ("pad", "<i4")])
@@ -26,14 +27,28 @@ def _plan(D, S, H, A, E):
     buf = ctypes.create_string_buffer(pb.value)
     L.call_host("mrssm_rollout_tc_plan", D, S, H, A, E, ctypes.cast(buf, ctypes.c_void_p), pb.value)
     raw = np.frombuffer(buf.raw, dtype=np.uint8)
-    hdr = raw[:72].view("<i4")
+    hdr = raw[:80].view("<i4")
     n_tiles, n_ops, n_pack = int(hdr[6]), int(hdr[7]), int(hdr[8])
-    hu = raw[:72].view("<u4")
-    packed_bytes, tile_off, op_off, pack_off, total = [int(v) for v in hu[13:18]]
+    hu = raw[:80].view("<u4")
+    packed_bytes, tile_off, op_off, pack_off, total, run_off, n_runs = [int(v) for v in hu[13:20]]
     assert total == pb.value and packed_bytes == kb.value
     tiles = raw[tile_off:tile_off + n_tiles * TILE.itemsize].view(TILE)
     ops = raw[op_off:op_off + n_ops * OP.itemsize].view(OP)
     packs = raw[pack_off:pack_off + n_pack * PACK.itemsize].view(PACK)
+    runs = raw[run_off:run_off + n_runs * RUN.itemsize].view(RUN)
+    # the runs the kernel issues expand to exactly the MMA list
+    for tl in tiles:
+        exp = []
+        for r in runs[int(tl["run_begin"]):int(tl["run_end"])]:
+            N = ((int(r["idesc"]) >> 17) & 63) << 3
+            assert 1 <= int(r["count"]) <= 7
+            for i in range(int(r["count"])):
+                exp.append((int(r["a_off16"]) + 128 * i, int(r["a_buf"]), int(r["acc_first"]) if i == 0 else 1,
+                            int(r["b_off16"]) + 2 * N * i, int(r["d_col"]), int(r["idesc"])))
+        got = [tuple(int(o[k]) for k in ("a_off16", "a_buf", "acc", "b_off16", "d_col", "idesc"))
+               for o in ops[int(tl["op_begin"]):int(tl["op_end"])]]
+        assert exp == got
+    assert n_runs < 192
     return dict(cA=int(hdr[9]), nD8=int(hdr[10]), cAH=int(hdr[11]), nH8=int(hdr[12])), tiles, ops, packs, packed_bytes
 
 
