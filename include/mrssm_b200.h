@@ -243,8 +243,10 @@ int mrssm_rollout_tc_plan_bytes(int32_t D, int32_t S, int32_t H, int32_t A, int3
 int mrssm_rollout_tc_plan(int32_t D, int32_t S, int32_t H, int32_t A, int32_t n_experts, void* host_buf, int64_t buflen);
 int mrssm_rollout_tc_pack(const mrssm_rollout_args* a, const void* plan_dev, int32_t n_pack, void* packed_dev, void* stream);
 int mrssm_rollout_tc_fwd(const mrssm_rollout_args* a, const void* plan_dev, const void* packed_dev, void* stream);
-/* tuning aid: device buffer of 3*512 int64 receiving clock64 stamps of one time step of CTA 0 (NULL = off) */
+/* tuning aids: device buffer of 4*512 int64 receiving clock64 stamps of one time step of CTA 0 (NULL = off); sequences per
+ * 16-row MMA group (16 -> 64 sequences per CTA, 8 -> 32, 0 = automatic) */
 int mrssm_rollout_tc_set_profile_buffer(void* dev_buf);
+int mrssm_rollout_tc_set_rows(int32_t rows_per_group);
 
 /* BPTT through the rollout (autograd of transition_model.py:226-270).  Consumes the forward's
  * outputs/stash plus upstream gradients of every output; produces the data gradients and the
@@ -271,6 +273,14 @@ typedef struct mrssm_rollout_bwd_args {
 } mrssm_rollout_bwd_args;
 
 int mrssm_rollout_bwd(const mrssm_rollout_bwd_args* a, void* stream);
+
+/* BPTT on the tensor cores (tcgen05 twin of mrssm_rollout_bwd, same eligibility as mrssm_rollout_tc_fwd, same argument struct
+ * and outputs).  The weights are read from the bf16 stream packed by mrssm_rollout_tc_pack with the plan of
+ * mrssm_rollout_tc_bwd_plan (the transposed, dgrad-type blocks of fc2, fc1[:, :D], W_ih, W_hh, W_sa), not through the struct. */
+int mrssm_rollout_tc_bwd_plan_bytes(int32_t D, int32_t S, int32_t H, int32_t A, int32_t n_experts, int64_t* plan_bytes,
+                                    int64_t* packed_bytes);
+int mrssm_rollout_tc_bwd_plan(int32_t D, int32_t S, int32_t H, int32_t A, int32_t n_experts, void* host_buf, int64_t buflen);
+int mrssm_rollout_tc_bwd(const mrssm_rollout_bwd_args* g, const void* packed_dev, void* stream);
 
 /* ---- latent part of the ELBO -------------------------------------------------------------------
  * Replaces _get_posterior_states (MRSSM_PoE/algo.py:63-68, MRSSM_MoPoE/algo.py:62-67, base/algo.py:

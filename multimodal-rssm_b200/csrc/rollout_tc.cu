@@ -39,6 +39,7 @@ constexpr int F2_COL = 2 * ACC_STRIDE;    // fc2 accumulators: 64 columns per he
 constexpr int TC_MAX_HEADS = 4;
 constexpr int MAX_TILES = 112, MAX_OPS = 336, MAX_RUNS = 192;
 constexpr int TC_MAGIC = 0x52544331;      // "RTC1"
+constexpr int PACK_TRANSPOSED = 0x100;
 
 enum { BUF_XIN = 0, BUF_XU = 1, BUF_HPREV = 2, BUF_HNEW = 3 };
 enum { EV_XIN = 0, EV_X, EV_HA, EV_HB, EV_U0, N_EV = EV_U0 + 2 * TC_MAX_HEADS };
@@ -114,9 +115,8 @@ struct PlanBuilder {
 
     void unit_begin(int wait_ev) { cur_wait = wait_ev; first = true; open = false; }
     void unit_end(int commit) { tiles.back().commit = (int8_t)commit; open = false; }
-    // one MMA: D[d_col .. d_col+N) (+)= A(buf, chunks 2k, 2k+1) * W[rows, k0 .. k0+16)^T
-    void mma(int a_buf, int k, int d_col, int N, int acc, int src_id, int kin, int seg0_n, int seg0_src, int seg0_cnt, int seg1_n = 0,
-             int seg1_src = 0, int seg1_cnt = 0) {
+    // one MMA: D[d_col .. d_col+N) (+)= A(buf, chunk planes a_chunk, a_chunk+1) * Bblock^T, Bblock [N][16] gathered as `p` says
+    void mma2(int a_buf, int a_chunk, int d_col, int N, int acc, TcPack p) {
         const uint32_t bytes = 32u * (uint32_t)N;
         if (!open || tiles.back().bytes + bytes > (uint32_t)SLOT_BYTES) {
             TcTile t;
@@ -129,7 +129,7 @@ struct PlanBuilder {
             first = false; open = true;
         }
         TcOp o;
-        o.a_off16 = (uint16_t)(2 * k * CH_BYTES / 16);
+        o.a_off16 = (uint16_t)(a_chunk * CH_BYTES / 16);
         o.a_buf = (uint8_t)a_buf; o.acc = (uint8_t)acc;
         o.b_off16 = (uint16_t)(tiles.back().bytes / 16);
         o.d_col = (uint16_t)d_col;
@@ -152,15 +152,33 @@ struct PlanBuilder {
                 tl.run_end = (uint8_t)runs.size();
             }
         }
-        TcPack p;
-        p.src_id = src_id; p.k0 = 16 * k; p.kvalid = std::max(0, std::min(16, kin - 16 * k)); p.N = N;
-        p.seg_n[0] = seg0_n; p.seg_src[0] = seg0_src; p.seg_cnt[0] = seg0_cnt;
-        p.seg_n[1] = seg1_n; p.seg_src[1] = seg1_src; p.seg_cnt[1] = seg1_cnt;
-        p.dst_off = packed; p.pad = 0;
+        p.N = N;
+        p.dst_off = packed;
         packs.push_back(p);
         packed += bytes;
         tiles.back().bytes += bytes;
         tiles.back().op_end = (uint16_t)ops.size();
+    }
+    // forward-type block: Bblock[n][k] = W[row(n)][16 k + k'], rows through up to two segments of n
+    void mma(int a_buf, int k, int d_col, int N, int acc, int src_id, int kin, int seg0_n, int seg0_src, int seg0_cnt, int seg1_n = 0,
+             int seg1_src = 0, int seg1_cnt = 0) {
+        TcPack p;
+        memset(&p, 0, sizeof(p));
+        p.src_id = src_id; p.k0 = 16 * k; p.kvalid = std::max(0, std::min(16, kin - 16 * k));
+        p.seg_n[0] = seg0_n; p.seg_src[0] = seg0_src; p.seg_cnt[0] = seg0_cnt;
+        p.seg_n[1] = seg1_n; p.seg_src[1] = seg1_src; p.seg_cnt[1] = seg1_cnt;
+        mma2(a_buf, 2 * k, d_col, N, acc, p);
+    }
+    // transposed (dgrad-type) block: Bblock[n][k'] = W[row(16 k + k')][n_off + n] for n < n_cnt, rows through up to two
+    // segments of the contraction index
+    void mma_t(int a_chunk0, int k, int d_col, int N, int acc, int src_id, int n_off, int n_cnt, int seg0_k, int seg0_src, int seg0_cnt,
+               int seg1_k = 0, int seg1_src = 0, int seg1_cnt = 0) {
+        TcPack p;
+        memset(&p, 0, sizeof(p));
+        p.src_id = src_id | PACK_TRANSPOSED; p.k0 = 16 * k; p.kvalid = n_cnt; p.pad = n_off;
+        p.seg_n[0] = seg0_k; p.seg_src[0] = seg0_src; p.seg_cnt[0] = seg0_cnt;
+        p.seg_n[1] = seg1_k; p.seg_src[1] = seg1_src; p.seg_cnt[1] = seg1_cnt;
+        mma2(0, a_chunk0 + 2 * k, d_col, N, acc, p);
     }
 };
 
@@ -283,13 +301,20 @@ __device__ __forceinline__ void epi_signal(uint64_t* bar, int lane) {
 __global__ void rollout_tc_pack_kernel(const uint8_t* __restrict__ plan, PackSrc src, bf16* __restrict__ out) {
     const TcHeader* h = reinterpret_cast<const TcHeader*>(plan);
     const TcPack pk = reinterpret_cast<const TcPack*>(plan + h->pack_off)[blockIdx.x];
-    const float* w = src.p[pk.src_id];
-    const long long ld = src.ld[pk.src_id];
+    const float* w = src.p[pk.src_id & 0xff];
+    const long long ld = src.ld[pk.src_id & 0xff];
     bf16* dst = out + pk.dst_off / 2;
     for (int i = threadIdx.x; i < pk.N * 16; i += blockDim.x) {
         const int ch = i / (pk.N * 8), n = (i >> 3) % pk.N, k = ch * 8 + (i & 7);
         float v = 0.f;
-        if (k < pk.kvalid) {
+        if (pk.src_id & PACK_TRANSPOSED) {
+            const int kk = pk.k0 + k;
+            if (n < pk.kvalid) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+                    if (kk >= pk.seg_n[s] && kk < pk.seg_n[s] + pk.seg_cnt[s]) v = w[(long long)(pk.seg_src[s] + kk - pk.seg_n[s]) * ld + pk.pad + n];
+            }
+        } else if (k < pk.kvalid) {
 #pragma unroll
             for (int s = 0; s < 2; ++s)
                 if (n >= pk.seg_n[s] && n < pk.seg_n[s] + pk.seg_cnt[s]) v = w[(long long)(pk.seg_src[s] + n - pk.seg_n[s]) * ld + pk.k0 + k];
@@ -780,6 +805,506 @@ rollout_tc_fwd_kernel(const __grid_constant__ mrssm_rollout_args a, const __grid
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward (BPTT), same machinery: per-step MMA program over the TRANSPOSED weights, activations = gradient operands.
+// Per step t (descending):  go (head-output grads, elementwise from the upstream grads and the carried state grad)
+//   -> gu_h = go_h W2_h, du_h = gu_h * act'(u_h)            (per half head, two TMEM sets)
+//   -> G = g_beliefs + carry + sum_h du_h W1_h[:, :D]        (one accumulator)
+//   -> GRU gate backward (elementwise)  -> gx = dgi W_ih, carry' = G z + dgh W_hh   (two accumulators)
+//   -> dxpre = gx * act'(x)  -> g_xin = dxpre W_sa  -> state carry (masked), action grads
+// The pre-activation gradients (d_o, d_u, d_gi, d_gh, d_xpre) and xin go to HBM for the deferred weight-gradient GEMMs.
+// ---------------------------------------------------------------------------------------------------------------
+enum { EVB_DO = 0, EVB_DU0, EVB_GRU = EVB_DU0 + 2 * TC_MAX_HEADS, EVB_DX, N_EVB };
+enum { CMB_GB0 = 0, CMB_GCH0 = CMB_GB0 + 2 * TC_MAX_HEADS, CMB_GE = CMB_GCH0 + TC_MAX_HEADS, CMB_GF, N_CMB };
+static_assert(N_EVB <= N_EV && N_CMB <= N_CM, "barrier arrays are shared with the forward kernel");
+// operand region (chunk planes of CH_BYTES): go of head h at 8h; du at 32; later dr, dz, dn, dn*r at 0, 26, 52, 78; later dxpre at 0
+constexpr int BCH_DO = 0, BCH_DU = 8 * TC_MAX_HEADS, BCH_DR = 0, BCH_DZ = MAXC, BCH_DN = 2 * MAXC, BCH_DNR = 3 * MAXC, BCH_DX = 0;
+constexpr int BOFF_CG = 4 * MAXC * CH_BYTES;                  // fp32 carried grad wrt h: [chunk][row][8]
+constexpr int BOFF_RING = BOFF_CG + MAXC * ROWS * 32;
+constexpr int BCOL_SET = ACC_STRIDE, BCOL_GH = 2 * ACC_STRIDE, BCOL_GX = 0, BCOL_GHH = 208, BCOL_XIN = 448;
+
+void build_plan_bwd(int D, int S, int H, int A, int NH, PlanBuilder& pb, TcHeader& h) {
+    const int nD8 = D / 8, nH8 = H / 8, cA = (nD8 + 1) / 2, cAH = (nH8 + 1) / 2;
+    const int nkD = (D + 15) / 16, nkH = (H + 15) / 16;
+    const int ND = ceil16(D);
+    auto gb = [&](int hd, int hf, int wait_ev) {      // gu_h[:, half] = go_h W2_h[:, half]   (K = [mean 0..S) | std 32..32+S))
+        const int c0 = hf ? cAH : 0, nc = hf ? nH8 - cAH : cAH, n0 = 8 * c0, cnt = 8 * nc, N = ceil16(cnt);
+        pb.unit_begin(wait_ev);
+        for (int k = 0; k < 4; ++k) pb.mma_t(BCH_DO + 8 * hd, k, hf * BCOL_SET, N, k != 0, SRC_W2 + hd, n0, cnt, 0, 0, S, 32, S, S);
+        pb.unit_end(CMB_GB0 + 2 * hd + hf);
+    };
+    auto gc = [&](int hd) {                           // G += du_h W1_h[:, :D]
+        pb.unit_begin(EVB_DU0 + 2 * hd + 1);
+        for (int k = 0; k < nkH; ++k) pb.mma_t(BCH_DU, k, BCOL_GH, ND, !(hd == 0 && k == 0), SRC_W1 + hd, 0, D, 0, 0, H);
+        pb.unit_end(CMB_GCH0 + hd);
+    };
+    gb(0, 0, EVB_DO);
+    gb(0, 1, -1);
+    for (int hd = 0; hd < NH; ++hd) {
+        if (hd + 1 < NH) gb(hd + 1, 0, EVB_DU0 + 2 * hd);
+        gc(hd);
+        if (hd + 1 < NH) gb(hd + 1, 1, -1);
+    }
+    // gx = [dr dz dn] W_ih ; gh = [dr dz dn*r] W_hh
+    pb.unit_begin(EVB_GRU);
+    for (int g = 0; g < 3; ++g)
+        for (int k = 0; k < nkD; ++k) pb.mma_t(g == 0 ? BCH_DR : (g == 1 ? BCH_DZ : BCH_DN), k, BCOL_GX, ND, !(g == 0 && k == 0), SRC_WIH, 0, D, 0, g * D, D);
+    for (int g = 0; g < 3; ++g)
+        for (int k = 0; k < nkD; ++k) pb.mma_t(g == 0 ? BCH_DR : (g == 1 ? BCH_DZ : BCH_DNR), k, BCOL_GHH, ND, !(g == 0 && k == 0), SRC_WHH, 0, D, 0, g * D, D);
+    pb.unit_end(CMB_GE);
+    // g_xin = dxpre W_sa
+    pb.unit_begin(EVB_DX);
+    for (int k = 0; k < nkD; ++k) pb.mma_t(BCH_DX, k, BCOL_XIN, 8 * XIN_CH, k != 0, SRC_WSA, 0, S + A, 0, 0, D);
+    pb.unit_end(CMB_GF);
+
+    memset(&h, 0, sizeof(h));
+    h.magic = TC_MAGIC + 1; h.D = D; h.S = S; h.H = H; h.A = A; h.NH = NH;
+    h.n_tiles = (int)pb.tiles.size(); h.n_ops = (int)pb.ops.size(); h.n_pack = (int)pb.packs.size();
+    h.cA = cA; h.nD8 = nD8; h.cAH = cAH; h.nH8 = nH8;
+    h.packed_bytes = pb.packed;
+    h.tile_off = 128;
+    h.op_off = h.tile_off + (uint32_t)(pb.tiles.size() * sizeof(TcTile));
+    h.pack_off = (h.op_off + (uint32_t)(pb.ops.size() * sizeof(TcOp)) + 15u) & ~15u;
+    h.run_off = h.pack_off + (uint32_t)(pb.packs.size() * sizeof(TcPack));
+    h.n_runs = (int)pb.runs.size();
+    h.total_bytes = h.run_off + (uint32_t)(pb.runs.size() * sizeof(TcRun));
+}
+
+// the weight producer and the MMA issuer of one CTA (shared by both directions); `it` counts processed time steps
+__device__ __forceinline__ void producer_role(const TcProg& prog, const uint8_t* __restrict__ packed, uint32_t ring, int NS, int n_steps,
+                                              uint64_t* full, uint64_t* empty) {
+    uint32_t slot = 0, phase = 0;
+    const int n_tiles = prog.n_tiles;
+    for (int it = 0; it < n_steps; ++it) {
+        uint32_t src = 0;
+        for (int ti = 0; ti < n_tiles; ++ti) {
+            wait_backoff(&empty[slot], phase ^ 1u);
+            const uint32_t bar = tc::smem_u32(&full[slot]);
+            const uint32_t bytes = (prog.tiles[ti] & 1023u) << 4;
+            r_expect_tx(bar, bytes);
+            r_bulk_g2s(ring + slot * SLOT_BYTES, packed + src, bytes, bar);
+            src += bytes;
+            if (++slot == (uint32_t)NS) { slot = 0; phase ^= 1u; }
+        }
+    }
+}
+__device__ __forceinline__ void mma_role(const TcProg& prog, uint32_t abase, uint32_t ring, int NS, int n_steps, uint32_t tmem_base,
+                                         uint64_t* full, uint64_t* empty, uint64_t* ev, uint64_t* cm) {
+    const uint32_t hi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1, no swizzle
+    const uint32_t s16 = abase >> 4;
+    const int n_tiles = prog.n_tiles;
+    uint32_t slot = 0, phase = 0;
+    for (int it = 0; it < n_steps; ++it) {
+        const uint32_t par = (uint32_t)(it & 1);
+        int ri = 0;
+        for (int ti = 0; ti < n_tiles; ++ti) {
+            const uint32_t tw = prog.tiles[ti];
+            const int wev = (int)((tw >> 13) & 31u) - 1, cmi = (int)((tw >> 18) & 31u) - 1;
+            if (wev >= 0) {
+                if (wev == 0) {                                   // the step's first operand comes from the previous step's last epilogue
+                    if (it > 0) tc::mbar_wait(tc::smem_u32(&ev[0]), par ^ 1u);
+                } else {
+                    tc::mbar_wait(tc::smem_u32(&ev[wev]), par);
+                }
+                tc::tc_fence_after();
+            }
+            tc::mbar_wait(tc::smem_u32(&full[slot]), phase);
+            tc::tc_fence_after();
+            const uint32_t sb = (ring + slot * SLOT_BYTES) >> 4;
+            const int rend = ri + (int)((tw >> 10) & 7u);
+            for (; ri < rend; ++ri) {
+                const uint4 r = prog.runs[ri];
+                const uint32_t n2 = ((r.z >> 17) & 63u) << 4, cntm = (r.w >> 13) & 7u;
+                const uint32_t a_lo = r.x + s16, b_lo = r.y + sb;
+                const uint32_t d = tmem_base + (r.w & 1023u), id = r.z;
+                r_umma(d, a_lo, b_lo, hi, id, (r.w >> 10) & 1u);
+                if (cntm > 1) r_umma(d, a_lo + 128u, b_lo + n2, hi, id, 1);
+                if (cntm > 2) r_umma(d, a_lo + 256u, b_lo + 2 * n2, hi, id, 1);
+                if (cntm > 3) r_umma(d, a_lo + 384u, b_lo + 3 * n2, hi, id, 1);
+                if (cntm > 4) r_umma(d, a_lo + 512u, b_lo + 4 * n2, hi, id, 1);
+                if (cntm > 5) r_umma(d, a_lo + 640u, b_lo + 5 * n2, hi, id, 1);
+                if (cntm > 6) r_umma(d, a_lo + 768u, b_lo + 6 * n2, hi, id, 1);
+            }
+            tc::umma_commit(tc::smem_u32(&empty[slot]));
+            if (cmi >= 0) tc::umma_commit(tc::smem_u32(&cm[cmi]));
+            if (++slot == (uint32_t)NS) { slot = 0; phase ^= 1u; }
+        }
+    }
+}
+
+struct BwdPtrs {          // per-head pointers the epilogue indexes dynamically (kept in shared memory)
+    const float *st_u[TC_MAX_HEADS], *exp_means[TC_MAX_HEADS], *exp_stds[TC_MAX_HEADS], *g_exp_means[TC_MAX_HEADS], *g_exp_stds[TC_MAX_HEADS];
+    float *d_u[TC_MAX_HEADS], *d_o[TC_MAX_HEADS];
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __grid_constant__ TcProg prog, const uint8_t* __restrict__ packed,
+                      const int NS, const int RPG) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full[MAX_SLOTS], empty[MAX_SLOTS], ev[N_EV], cm[N_CM];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ uint32_t smask_s[32];
+    __shared__ BwdPtrs P;
+
+    const mrssm_rollout_args& a = g.f;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* const smem = smem_raw + (smem0 - tc::smem_u32(smem_raw));
+    const int D = a.D, S = a.S, H = a.H, A = a.A, E = a.n_experts, NH = 1 + E, B = a.B, T = a.T;
+    const int nD8 = prog.nD8, cAH = prog.cAH, nH8 = prog.nH8;
+    const int b0 = blockIdx.x * 4 * RPG;
+
+    if (tid < 32) smask_s[tid] = (tid < S) ? (a.n_subsets > 0 ? a.subset_mask[a.dim_subset[tid]] : 1u) : 0u;
+    if (tid < TC_MAX_HEADS) {
+        const bool ok = tid < NH;
+        P.st_u[tid] = ok ? a.st_u[tid] : nullptr;
+        P.exp_means[tid] = ok ? a.exp_means[tid] : nullptr;
+        P.exp_stds[tid] = ok ? a.exp_stds[tid] : nullptr;
+        P.g_exp_means[tid] = ok ? g.g_exp_means[tid] : nullptr;
+        P.g_exp_stds[tid] = ok ? g.g_exp_stds[tid] : nullptr;
+        P.d_u[tid] = ok ? g.d_u[tid] : nullptr;
+        P.d_o[tid] = ok ? g.d_o[tid] : nullptr;
+    }
+    for (int i = tid; i < BOFF_RING / 16; i += TC_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        for (int s = 0; s < MAX_SLOTS; ++s) {
+            tc::mbar_init(tc::smem_u32(&full[s]), 1);
+            tc::mbar_init(tc::smem_u32(&empty[s]), 1);
+        }
+        for (int i = 0; i < N_EV; ++i) tc::mbar_init(tc::smem_u32(&ev[i]), EPI_WARPS);
+        for (int i = 0; i < N_CM; ++i) tc::mbar_init(tc::smem_u32(&cm[i]), 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == ALLOC_WARP) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), 512);
+    __syncthreads();
+
+    // epilogue-thread coordinates (all warps compute them; only warps < EPI_WARPS use them)
+    const int q = warp & 3, p = warp >> 2;
+    const int r0 = 16 * q + (lane >> 2), r1 = r0 + 8, cj = 2 * (lane & 3);
+    const int seq0 = b0 + q * RPG + (lane >> 2);
+    const bool two = RPG == 16;
+    const bool ok0 = seq0 < B, ok1 = two && seq0 + 8 < B;
+    const int act = a.act;
+    const float min_std = a.min_std;
+    const bool det = a.det != 0;
+    const int s0 = 8 * p + cj;                                   // state dims s0, s0+1 (rows r0, r1) for the fusion backward
+    const bool live = 8 * p < S;
+    const bool pairS = s0 + 1 < S && (S & 1) == 0;
+    float cgs[4] = {0.f, 0.f, 0.f, 0.f};                         // carried grad wrt the fed-back state at (r0|r1, s0|s0+1)
+
+    // go of step t from the upstream grads and the state carry -> DO operands (bf16) + d_o (HBM)
+    auto step_a = [&](int t) {
+        if (!live) return;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            if (rr == 1 && !two) continue;
+            const bool okr = rr ? ok1 : ok0;
+            const int r = rr ? r1 : r0;
+            const long long row = (long long)t * B + seq0 + 8 * rr;
+            float gm[TC_MAX_HEADS][2], gs[TC_MAX_HEADS][2];
+#pragma unroll
+            for (int ee = 0; ee < 2; ++ee) {
+                const int s = s0 + ee;
+                const bool lv = okr && s < S;
+                const long long off = lv ? row * S + s : 0;
+                const float carry = cgs[2 * rr + ee];
+                float gps = (g.g_prior_states && lv) ? __ldg(g.g_prior_states + off) : 0.f;
+                if (E == 0) gps += carry;
+                const float gpm = gps + ((g.g_prior_means && lv) ? __ldg(g.g_prior_means + off) : 0.f);
+                float gpsd = (g.g_prior_stds && lv) ? __ldg(g.g_prior_stds + off) : 0.f;
+                if (!det && lv) gpsd = fmaf(gps, __ldg(a.eps_prior + off), gpsd);
+                const float psd = lv ? __ldg(a.prior_stds + off) : 1.f;
+                gm[0][ee] = lv ? gpm : 0.f;
+                gs[0][ee] = lv ? gpsd * (1.f - ex2_approx(-1.4426950409f * (psd - min_std))) : 0.f;
+                if (E > 0) {
+                    const float gq = ((g.g_post_states && lv) ? __ldg(g.g_post_states + off) : 0.f) + carry;
+                    const float gqm = gq + ((g.g_post_means && lv) ? __ldg(g.g_post_means + off) : 0.f);
+                    float gqs = (g.g_post_stds && lv) ? __ldg(g.g_post_stds + off) : 0.f;
+                    if (!det && lv) gqs = fmaf(gq, __ldg(a.eps_post + off), gqs);
+                    const unsigned mask = smask_s[min(s, 31)];
+                    float Pp = 1.f, qm = 0.f;
+                    if (a.n_subsets && lv) {
+                        Pp = __ldg(a.post_stds + off);             // = 1 / sum of precisions
+                        qm = __ldg(a.post_means + off);
+                    }
+#pragma unroll
+                    for (int e = 1; e < TC_MAX_HEADS; ++e) {
+                        if (e < NH) {
+                            float vm = (P.g_exp_means[e] && lv) ? __ldg(P.g_exp_means[e] + off) : 0.f;
+                            float vs = (P.g_exp_stds[e] && lv) ? __ldg(P.g_exp_stds[e] + off) : 0.f;
+                            const float sd = lv ? __ldg(P.exp_stds[e] + off) : 1.f;
+                            if (lv && (mask & (1u << (e - 1)))) {
+                                if (a.n_subsets == 0) {
+                                    vm += gqm;
+                                    vs += gqs;
+                                } else {
+                                    const float te = rcp_approx(sd);
+                                    const float mu = __ldg(P.exp_means[e] + off);
+                                    vm = fmaf(gqm, te * Pp, vm);
+                                    const float gT = gqm * (mu - qm) * Pp - gqs * (Pp * Pp);
+                                    vs = fmaf(-gT, te * te, vs);
+                                }
+                            }
+                            gm[e][ee] = lv ? vm : 0.f;
+                            gs[e][ee] = lv ? vs * (1.f - ex2_approx(-1.4426950409f * (sd - min_std))) : 0.f;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < TC_MAX_HEADS; ++e) {
+                if (e < NH) {
+                    const uint32_t base = smem0 + (uint32_t)((BCH_DO + 8 * e) * CH_BYTES + r * 16 + cj * 2);
+                    st_shared_u32(base + (uint32_t)p * CH_BYTES, pack_bf16x2(gm[e][0], gm[e][1]));
+                    st_shared_u32(base + (uint32_t)(4 + p) * CH_BYTES, pack_bf16x2(gs[e][0], gs[e][1]));
+                    if (okr) {
+                        float* dm = P.d_o[e] + row * 2 * S + s0;
+                        if (pairS) { st_f2(dm, gm[e][0], gm[e][1]); st_f2(dm + S, gs[e][0], gs[e][1]); }
+                        else {
+                            if (s0 < S) { dm[0] = gm[e][0]; dm[S] = gs[e][0]; }
+                            if (s0 + 1 < S) { dm[1] = gm[e][1]; dm[S + 1] = gs[e][1]; }
+                        }
+                    }
+                }
+            }
+        }
+    };
+    if (warp < EPI_WARPS) step_a(T - 1);
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == PROD_WARP) {
+        if (lane == 0) producer_role(prog, packed, smem0 + BOFF_RING, NS, T, full, empty);
+        __syncwarp();
+    } else if (warp == MMA_WARP) {
+        if (lane == 0) mma_role(prog, smem0, smem0 + BOFF_RING, NS, T, tmem_base, full, empty, ev, cm);
+        __syncwarp();
+    } else if (warp < EPI_WARPS) {
+        const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
+        const uint32_t opnd0 = (uint32_t)(r0 * 16 + cj * 2), opnd1 = (uint32_t)(r1 * 16 + cj * 2);
+        const uint32_t cg0 = smem0 + BOFF_CG + (uint32_t)(r0 * 32 + cj * 4), cg1 = smem0 + BOFF_CG + (uint32_t)(r1 * 32 + cj * 4);
+        for (int it = 0; it < T; ++it) {
+            const int t = T - 1 - it;
+            const uint32_t par = (uint32_t)(it & 1);
+            const long long row0 = (long long)t * B + seq0, row1 = row0 + 8;
+            // ---- Eb: du_h = gu_h * act'(u_h) -> DU operand, d_u ------------------------------------------------
+            for (int hd = 0; hd < NH; ++hd) {
+                const float* su = P.st_u[hd];
+                float* du = P.d_u[hd];
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int c_lo = hf ? cAH : 0, c_hi = hf ? nH8 : cAH;
+                    float uu[4][4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = c_lo + p + 4 * i;
+                        uu[i][0] = uu[i][1] = uu[i][2] = uu[i][3] = 0.f;
+                        if (c < c_hi) {
+                            const int j = 8 * c + cj;
+                            if (ok0) { const float2 e0 = __ldg(reinterpret_cast<const float2*>(su + row0 * H + j)); uu[i][0] = e0.x; uu[i][1] = e0.y; }
+                            if (ok1) { const float2 e1 = __ldg(reinterpret_cast<const float2*>(su + row1 * H + j)); uu[i][2] = e1.x; uu[i][3] = e1.y; }
+                        }
+                    }
+                    // half 0 of head hd >= 1 overwrites DU: G += du_{hd-1} W1 must have read it (that commit was issued later)
+                    const int cmi = (hf == 0 && hd > 0) ? CMB_GCH0 + hd - 1 : CMB_GB0 + 2 * hd + hf;
+                    wait_backoff(&cm[cmi], par);
+                    tc::tc_fence_after();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = c_lo + p + 4 * i;
+                        if (c < c_hi) {
+                            float v[4];
+                            ld_frag(tlane + (uint32_t)(hf * BCOL_SET + 8 * (c - c_lo)), v);
+                            wait_ld();
+                            const int j = 8 * c + cj;
+                            const float d00 = ok0 ? v[0] * act_grad_from_out(uu[i][0], act) : 0.f, d01 = ok0 ? v[1] * act_grad_from_out(uu[i][1], act) : 0.f;
+                            const uint32_t ch = smem0 + (uint32_t)(BCH_DU + c) * CH_BYTES;
+                            st_shared_u32(ch + opnd0, pack_bf16x2(d00, d01));
+                            if (ok0) st_f2(du + row0 * H + j, d00, d01);
+                            if (two) {
+                                const float d10 = ok1 ? v[2] * act_grad_from_out(uu[i][2], act) : 0.f, d11 = ok1 ? v[3] * act_grad_from_out(uu[i][3], act) : 0.f;
+                                st_shared_u32(ch + opnd1, pack_bf16x2(d10, d11));
+                                if (ok1) st_f2(du + row1 * H + j, d10, d11);
+                            }
+                        }
+                    }
+                    epi_signal(&ev[EVB_DU0 + 2 * hd + hf], lane);
+                }
+            }
+            // ---- Ed: G = g_beliefs + carry + acc ; GRU gate backward -> dr, dz, dn, dn*r operands, d_gi, d_gh; carry = G z ------
+            {
+                // per chunk: stash (r, z, n, W_hn h), h_{t-1} and the upstream belief grad, software-pipelined one chunk ahead
+                struct GruIn { float2 r, z, n, h, p, gb; };
+                auto load_in = [&](int c, int rr) {
+                    GruIn x;
+                    x.r = x.z = x.n = x.h = x.p = x.gb = make_float2(0.f, 0.f);
+                    if (c < nD8 && (rr ? ok1 : ok0)) {
+                        const int j = 8 * c + cj;
+                        const long long off = (rr ? row1 : row0) * D + j;
+                        x.r = __ldg(reinterpret_cast<const float2*>(a.st_r + off));
+                        x.z = __ldg(reinterpret_cast<const float2*>(a.st_z + off));
+                        x.n = __ldg(reinterpret_cast<const float2*>(a.st_n + off));
+                        x.h = __ldg(reinterpret_cast<const float2*>(a.st_ghn + off));
+                        x.p = (t > 0) ? __ldg(reinterpret_cast<const float2*>(a.beliefs + off - (long long)B * D))
+                                      : __ldg(reinterpret_cast<const float2*>(a.prev_belief + (long long)(seq0 + 8 * rr) * D + j));
+                        if (g.g_beliefs) x.gb = __ldg(reinterpret_cast<const float2*>(g.g_beliefs + off));
+                    }
+                    return x;
+                };
+                GruIn nx0 = load_in(p, 0), nx1 = load_in(two ? p : nD8, 1);
+                wait_backoff(&cm[CMB_GCH0 + NH - 1], par);
+                tc::tc_fence_after();
+                for (int c = p; c < nD8; c += 4) {
+                    const GruIn in0 = nx0, in1 = nx1;
+                    nx0 = load_in(c + 4, 0);
+                    nx1 = load_in(two ? c + 4 : nD8, 1);
+                    float v[4];
+                    ld_frag(tlane + (uint32_t)(BCOL_GH + 8 * c), v);
+                    wait_ld();
+                    const int j = 8 * c + cj;
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        if (rr == 1 && !two) continue;
+                        const bool okr = rr ? ok1 : ok0;
+                        const GruIn& x = rr ? in1 : in0;
+                        const uint32_t cga = (rr ? cg1 : cg0) + (uint32_t)c * (ROWS * 32);
+                        float gr[2] = {0.f, 0.f}, gz[2] = {0.f, 0.f}, gn[2] = {0.f, 0.f}, gnr[2] = {0.f, 0.f}, dir[2] = {0.f, 0.f};
+                        if (okr) {
+                            const float2 cg = ld_shared_f2(cga);
+                            const float G[2] = {v[2 * rr] + cg.x + x.gb.x, v[2 * rr + 1] + cg.y + x.gb.y};
+                            const float r_[2] = {x.r.x, x.r.y}, z_[2] = {x.z.x, x.z.y}, n_[2] = {x.n.x, x.n.y}, h_[2] = {x.h.x, x.h.y}, p_[2] = {x.p.x, x.p.y};
+#pragma unroll
+                            for (int ee = 0; ee < 2; ++ee) {
+                                const float gnn = G[ee] * (1.f - z_[ee]), gzz = G[ee] * (p_[ee] - n_[ee]);
+                                dir[ee] = G[ee] * z_[ee];
+                                gn[ee] = gnn * (1.f - n_[ee] * n_[ee]);
+                                gr[ee] = gn[ee] * h_[ee] * r_[ee] * (1.f - r_[ee]);
+                                gz[ee] = gzz * z_[ee] * (1.f - z_[ee]);
+                                gnr[ee] = gn[ee] * r_[ee];
+                            }
+                            const long long o3 = (rr ? row1 : row0) * 3 * D + j;
+                            st_f2(g.d_gi + o3, gr[0], gr[1]); st_f2(g.d_gi + o3 + D, gz[0], gz[1]); st_f2(g.d_gi + o3 + 2 * D, gn[0], gn[1]);
+                            st_f2(g.d_gh + o3, gr[0], gr[1]); st_f2(g.d_gh + o3 + D, gz[0], gz[1]); st_f2(g.d_gh + o3 + 2 * D, gnr[0], gnr[1]);
+                        }
+                        st_shared_f2(cga, dir[0], dir[1]);
+                        const uint32_t o = (rr ? opnd1 : opnd0) + (uint32_t)c * CH_BYTES;
+                        st_shared_u32(smem0 + BCH_DR * CH_BYTES + o, pack_bf16x2(gr[0], gr[1]));
+                        st_shared_u32(smem0 + BCH_DZ * CH_BYTES + o, pack_bf16x2(gz[0], gz[1]));
+                        st_shared_u32(smem0 + BCH_DN * CH_BYTES + o, pack_bf16x2(gn[0], gn[1]));
+                        st_shared_u32(smem0 + BCH_DNR * CH_BYTES + o, pack_bf16x2(gnr[0], gnr[1]));
+                    }
+                }
+            }
+            // the padding chunk planes of the four gate operands alias go / du planes of this step: clear them
+            if ((D & 15) != 0) {
+                for (int i = tid; i < 4 * (CH_BYTES / 4); i += EPI_WARPS * 32) {
+                    const int b = i / (CH_BYTES / 4), w = i - b * (CH_BYTES / 4);
+                    st_shared_u32(smem0 + (uint32_t)((b * MAXC + nD8) * CH_BYTES + 4 * w), 0u);
+                }
+            }
+            epi_signal(&ev[EVB_GRU], lane);
+            // ---- Ee: dxpre = gx * act'(x) -> DX operand, d_xpre ; carry += gh -----------------------------------
+            float2 xn0 = make_float2(0.f, 0.f), xn1 = make_float2(0.f, 0.f);
+            if (p < nD8) {
+                if (ok0) xn0 = __ldg(reinterpret_cast<const float2*>(a.st_x + row0 * D + 8 * p + cj));
+                if (ok1) xn1 = __ldg(reinterpret_cast<const float2*>(a.st_x + row1 * D + 8 * p + cj));
+            }
+            wait_backoff(&cm[CMB_GE], par);
+            tc::tc_fence_after();
+            for (int c = p; c < nD8; c += 4) {
+                const float2 xa = xn0, xb = xn1;
+                if (c + 4 < nD8) {
+                    if (ok0) xn0 = __ldg(reinterpret_cast<const float2*>(a.st_x + row0 * D + 8 * (c + 4) + cj));
+                    if (ok1) xn1 = __ldg(reinterpret_cast<const float2*>(a.st_x + row1 * D + 8 * (c + 4) + cj));
+                }
+                float vx[4], vh[4];
+                ld_frag(tlane + (uint32_t)(BCOL_GX + 8 * c), vx);
+                ld_frag(tlane + (uint32_t)(BCOL_GHH + 8 * c), vh);
+                wait_ld();
+                const int j = 8 * c + cj;
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    if (rr == 1 && !two) continue;
+                    const bool okr = rr ? ok1 : ok0;
+                    const long long off = (rr ? row1 : row0) * D + j;
+                    const uint32_t cga = (rr ? cg1 : cg0) + (uint32_t)c * (ROWS * 32);
+                    float dx0 = 0.f, dx1 = 0.f;
+                    if (okr) {
+                        const float2 xv = rr ? xb : xa;
+                        dx0 = vx[2 * rr] * act_grad_from_out(xv.x, act);
+                        dx1 = vx[2 * rr + 1] * act_grad_from_out(xv.y, act);
+                        st_f2(g.d_xpre + off, dx0, dx1);
+                        const float2 cg = ld_shared_f2(cga);
+                        st_shared_f2(cga, cg.x + vh[2 * rr], cg.y + vh[2 * rr + 1]);
+                    }
+                    st_shared_u32(smem0 + (uint32_t)(BCH_DX + c) * CH_BYTES + (rr ? opnd1 : opnd0), pack_bf16x2(dx0, dx1));
+                }
+            }
+            if ((D & 15) != 0) {
+                for (int i = tid; i < CH_BYTES / 4; i += EPI_WARPS * 32) st_shared_u32(smem0 + (uint32_t)((BCH_DX + nD8) * CH_BYTES + 4 * i), 0u);
+            }
+            epi_signal(&ev[EVB_DX], lane);
+            // ---- Ef: g_xin -> state carry (masked), action grads, xin ; then go of step t-1 -------------------------
+            wait_backoff(&cm[CMB_GF], par);
+            tc::tc_fence_after();
+            for (int grp = p; grp * 8 < S + A; grp += 4) {
+                float v[4];
+                ld_frag(tlane + (uint32_t)(BCOL_XIN + 8 * grp), v);
+                wait_ld();
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    if (rr == 1 && !two) continue;
+                    const bool okr = rr ? ok1 : ok0;
+                    const long long row = rr ? row1 : row0;
+                    const float m = (okr && a.nonterminals) ? __ldg(a.nonterminals + row) : 1.f;
+#pragma unroll
+                    for (int ee = 0; ee < 2; ++ee) {
+                        const int i = 8 * grp + cj + ee;
+                        const float acc = v[2 * rr + ee];
+                        if (i < S) {
+                            cgs[2 * rr + ee] = okr ? acc * m : 0.f;           // grp == p here (S <= 32)
+                            if (okr && g.xin) {
+                                const float* src = (E > 0) ? a.post_states : a.prior_states;
+                                const float sp = (t > 0) ? __ldg(src + (row - B) * S + i) : __ldg(a.prev_state + (long long)(seq0 + 8 * rr) * S + i);
+                                g.xin[row * (S + A) + i] = sp * m;
+                            }
+                        } else if (i < S + A && okr) {
+                            if (g.g_actions) g.g_actions[row * A + (i - S)] = acc;
+                            if (g.xin) g.xin[row * (S + A) + i] = __ldg(a.actions + row * A + (i - S));
+                        }
+                    }
+                }
+            }
+            if (t > 0) step_a(t - 1);
+            epi_signal(&ev[EVB_DO], lane);
+        }
+        // ---- carries out -------------------------------------------------------------------------------------
+        if (g.g_prev_belief) {
+            for (int c = p; c < nD8; c += 4) {
+                const int j = 8 * c + cj;
+                if (ok0) { const float2 cg = ld_shared_f2(cg0 + (uint32_t)c * (ROWS * 32)); st_f2(g.g_prev_belief + (long long)seq0 * D + j, cg.x, cg.y); }
+                if (ok1) { const float2 cg = ld_shared_f2(cg1 + (uint32_t)c * (ROWS * 32)); st_f2(g.g_prev_belief + (long long)(seq0 + 8) * D + j, cg.x, cg.y); }
+            }
+        }
+        if (g.g_prev_state && live) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int s = s0 + (e & 1);
+                if (s < S && ((e < 2) ? ok0 : ok1)) g.g_prev_state[(long long)(seq0 + 8 * (e >> 1)) * S + s] = cgs[e];
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == ALLOC_WARP) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -905,6 +1430,94 @@ extern "C" int mrssm_rollout_tc_fwd(const mrssm_rollout_args* a, const void* pla
     const int RPG = g_tc_rpg ? g_tc_rpg : ((a->B + 63) / 64 >= 74 ? 16 : 8);
     rollout_tc_fwd_kernel<<<(a->B + 4 * RPG - 1) / (4 * RPG), TC_THREADS, dyn, (cudaStream_t)stream>>>(*a, prog, (const uint8_t*)packed_dev, NS, RPG,
                                                                                                         g_tc_prof);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- backward ----------------------------------------------------------------------------------------------------
+extern "C" int mrssm_rollout_tc_bwd_plan_bytes(int32_t D, int32_t S, int32_t H, int32_t A, int32_t n_experts, int64_t* plan_bytes,
+                                               int64_t* packed_bytes) {
+    MRSSM_CHECK(tc_eligible(D, S, H, A, 1 + n_experts), "rollout_tc: sizes not eligible (D %d S %d H %d A %d heads %d)", D, S, H, A, 1 + n_experts);
+    PlanBuilder pb;
+    TcHeader h;
+    build_plan_bwd(D, S, H, A, 1 + n_experts, pb, h);
+    MRSSM_CHECK(h.n_tiles <= PROG_TILES && h.n_runs <= PROG_RUNS, "rollout_tc_bwd: program too long (%d tiles, %d runs)", h.n_tiles, h.n_runs);
+    if (plan_bytes) *plan_bytes = h.total_bytes;
+    if (packed_bytes) *packed_bytes = h.packed_bytes;
+    return 0;
+}
+
+extern "C" int mrssm_rollout_tc_bwd_plan(int32_t D, int32_t S, int32_t H, int32_t A, int32_t n_experts, void* host_buf, int64_t buflen) {
+    MRSSM_CHECK(host_buf && tc_eligible(D, S, H, A, 1 + n_experts), "rollout_tc_bwd_plan: bad arguments");
+    PlanBuilder pb;
+    TcHeader h;
+    build_plan_bwd(D, S, H, A, 1 + n_experts, pb, h);
+    MRSSM_CHECK(h.n_tiles <= PROG_TILES && h.n_runs <= PROG_RUNS, "rollout_tc_bwd: program too long (%d tiles, %d runs)", h.n_tiles, h.n_runs);
+    MRSSM_CHECK(buflen >= (int64_t)h.total_bytes, "rollout_tc_bwd_plan: buffer too small (%lld < %u)", (long long)buflen, h.total_bytes);
+    uint8_t* o = (uint8_t*)host_buf;
+    memset(o, 0, h.total_bytes);
+    memcpy(o, &h, sizeof(h));
+    memcpy(o + h.tile_off, pb.tiles.data(), pb.tiles.size() * sizeof(TcTile));
+    memcpy(o + h.op_off, pb.ops.data(), pb.ops.size() * sizeof(TcOp));
+    memcpy(o + h.pack_off, pb.packs.data(), pb.packs.size() * sizeof(TcPack));
+    memcpy(o + h.run_off, pb.runs.data(), pb.runs.size() * sizeof(TcRun));
+    return 0;
+}
+
+static void fill_prog(const PlanBuilder& pb, const TcHeader& h, TcProg& prog) {
+    memset(&prog, 0, sizeof(prog));
+    for (int i = 0; i < h.n_runs; ++i) {
+        const TcRun& o = pb.runs[i];
+        const uint32_t n = ((o.idesc >> 17) & 63u) << 3;
+        prog.runs[i].x = (uint32_t)o.a_off16 | (((uint32_t)CH_BYTES >> 4) << 16);
+        prog.runs[i].y = (uint32_t)o.b_off16 | (n << 16);
+        prog.runs[i].z = o.idesc;
+        prog.runs[i].w = (uint32_t)o.d_col | ((uint32_t)o.acc_first << 10) | (o.count << 13);
+    }
+    for (int i = 0; i < h.n_tiles; ++i) {
+        const TcTile& t = pb.tiles[i];
+        prog.tiles[i] = (t.bytes >> 4) | ((uint32_t)(t.run_end - t.run_begin) << 10) | ((uint32_t)(t.wait_ev + 1) << 13) | ((uint32_t)(t.commit + 1) << 18);
+    }
+    prog.n_tiles = h.n_tiles; prog.cA = h.cA; prog.nD8 = h.nD8; prog.cAH = h.cAH; prog.nH8 = h.nH8;
+}
+
+int rollout_bwd_check(const mrssm_rollout_bwd_args* g);
+
+// g: as mrssm_rollout_bwd (the weights are NOT read through the struct: packed_dev is the stream packed by mrssm_rollout_tc_pack
+// from the plan of mrssm_rollout_tc_bwd_plan)
+extern "C" int mrssm_rollout_tc_bwd(const mrssm_rollout_bwd_args* g, const void* packed_dev, void* stream) {
+    MRSSM_CHECK(g && packed_dev, "rollout_tc_bwd: bad arguments");
+    const mrssm_rollout_args* a = &g->f;
+    MRSSM_CHECK(tc_eligible(a->D, a->S, a->H, a->A, 1 + a->n_experts), "rollout_tc_bwd: sizes not eligible");
+    MRSSM_CHECK(a->T > 0 && a->B > 0 && a->prev_state && a->prev_belief && a->actions && a->beliefs && a->prior_states && a->prior_stds &&
+                    a->st_x && a->st_r && a->st_z && a->st_n && a->st_ghn && g->d_xpre && g->d_gi && g->d_gh,
+                "rollout_tc_bwd: missing tensors");
+    for (int h = 0; h <= a->n_experts; ++h) MRSSM_CHECK(a->st_u[h] && g->d_u[h] && g->d_o[h], "rollout_tc_bwd: head %d buffers missing", h);
+    if (a->n_experts > 0) {
+        MRSSM_CHECK(a->post_states && a->post_means && a->post_stds, "rollout_tc_bwd: posterior tensors missing");
+        for (int h = 1; h <= a->n_experts; ++h) MRSSM_CHECK(a->exp_means[h] && a->exp_stds[h], "rollout_tc_bwd: expert tensors missing");
+        MRSSM_CHECK(a->det || a->eps_post, "rollout_tc_bwd: eps_post missing");
+    }
+    MRSSM_CHECK(a->det || a->eps_prior, "rollout_tc_bwd: eps_prior missing");
+    static thread_local TcProg prog;
+    static thread_local int key[5] = {-1, -1, -1, -1, -1};
+    if (key[0] != a->D || key[1] != a->S || key[2] != a->H || key[3] != a->A || key[4] != a->n_experts) {
+        PlanBuilder pb;
+        TcHeader h;
+        build_plan_bwd(a->D, a->S, a->H, a->A, 1 + a->n_experts, pb, h);
+        MRSSM_CHECK(h.n_tiles <= PROG_TILES && h.n_runs <= PROG_RUNS, "rollout_tc_bwd: program too long (%d tiles, %d runs)", h.n_tiles, h.n_runs);
+        fill_prog(pb, h, prog);
+        key[0] = a->D; key[1] = a->S; key[2] = a->H; key[3] = a->A; key[4] = a->n_experts;
+    }
+    cudaFuncAttributes fa;
+    MRSSM_CUDA(cudaFuncGetAttributes(&fa, rollout_tc_bwd_kernel));
+    const int avail = 232448 - (int)fa.sharedSizeBytes - 1024 - BOFF_RING;
+    const int NS = std::min(MAX_SLOTS, avail / SLOT_BYTES);
+    MRSSM_CHECK(NS >= 2, "rollout_tc_bwd: no room for the weight ring (%d bytes left)", avail);
+    const size_t dyn = (size_t)BOFF_RING + (size_t)NS * SLOT_BYTES + 1024;
+    MRSSM_CUDA(cudaFuncSetAttribute(rollout_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    const int RPG = g_tc_rpg ? g_tc_rpg : ((a->B + 63) / 64 >= 74 ? 16 : 8);
+    rollout_tc_bwd_kernel<<<(a->B + 4 * RPG - 1) / (4 * RPG), TC_THREADS, dyn, (cudaStream_t)stream>>>(*g, prog, (const uint8_t*)packed_dev, NS, RPG);
     MRSSM_LAUNCH_CHECK();
     return 0;
 }

@@ -520,10 +520,15 @@ class RolloutFn(Function):
         a.w_sa, a.b_sa, a.w_ih, a.b_ih, a.w_hh, a.b_hh = (L.ptr(w_sa), L.ptr(b_sa), L.ptr(w_ih), L.ptr(b_ih),
                                                           L.ptr(w_hh), L.ptr(b_hh))
         keep = []
+        use_tc = rollout_tc_enabled() and bool(L.load().mrssm_rollout_tc_eligible(D, S, H, A, E))
+        if use_tc:
+            tc_packed = rollout_tc_weights(spec, E, w_sa, w_ih, w_hh, heads, dev, bwd=True)[1]
         for hd in range(1 + E):
             w1, b1, w2, b2 = heads[hd]
             a.w1[hd], a.ld1[hd], a.b1[hd], a.w2[hd], a.b2[hd] = L.ptr(w1), w1.shape[1], L.ptr(b1), L.ptr(w2), L.ptr(b2)
             a.st_u[hd] = L.ptr(stash["u"][hd])
+            if use_tc:
+                continue
             if w1.shape[1] == D:
                 g.w1_belief[hd] = L.ptr(w1)
             else:                                       # contiguous copy of the belief columns for the weight streamer
@@ -561,7 +566,10 @@ class RolloutFn(Function):
             n_w = sum(p.numel() for p in params)
             macs = (S + A) * D + 6 * D * D + 2 * NHh * (D * H + H * 2 * S) - NHh * D * H      # dgrad GEMVs of one step
             work = dict(bytes=4.0 * (rd + wr) * T * B + 4.0 * n_w, flops=2.0 * macs * T * B)
-        L.call("mrssm_rollout_bwd", C.byref(g), tag="observe" if observe else "imagine", work=work)
+        if use_tc:
+            L.call("mrssm_rollout_tc_bwd", C.byref(g), L.ptr_any(tc_packed), tag="observe" if observe else "imagine", work=work)
+        else:
+            L.call("mrssm_rollout_bwd", C.byref(g), tag="observe" if observe else "imagine", work=work)
         del keep
 
         # deferred, time-parallel weight gradients: dW += dY^T X over all (t,b) rows.  fp32 mode: exact CUDA-core GEMMs;
@@ -918,27 +926,29 @@ def rollout_tc_enabled():
 _tc_plans = {}
 
 
-def rollout_tc_plan(D, S, H, A, E, dev):
-    """The per-step MMA program of the tcgen05 rollout (host-built once per shape, kept on the device)."""
-    key = (D, S, H, A, E, str(dev))
+def rollout_tc_plan(D, S, H, A, E, dev, bwd=False):
+    """The per-step MMA program of the tcgen05 rollout (host-built once per shape and direction, kept on the device)."""
+    key = (D, S, H, A, E, str(dev), bwd)
     hit = _tc_plans.get(key)
     if hit is None:
         pb, kb = C.c_int64(), C.c_int64()
-        L.call_host("mrssm_rollout_tc_plan_bytes", D, S, H, A, E, C.byref(pb), C.byref(kb))
+        stem = "mrssm_rollout_tc_bwd_plan" if bwd else "mrssm_rollout_tc_plan"
+        L.call_host(stem + "_bytes", D, S, H, A, E, C.byref(pb), C.byref(kb))
         host = torch.zeros(pb.value, dtype=torch.uint8)
-        L.call_host("mrssm_rollout_tc_plan", D, S, H, A, E, host.data_ptr(), pb.value)
+        L.call_host(stem, D, S, H, A, E, host.data_ptr(), pb.value)
         n_pack = int(host[:64].view(torch.int32)[8])
         hit = (host.to(dev), n_pack, int(kb.value))
         _tc_plans[key] = hit
     return hit
 
 
-def rollout_tc_weights(spec, E, w_sa, w_ih, w_hh, heads, dev):
-    """(plan, packed bf16 weight stream) of the tcgen05 rollout; the stream is re-packed when the masters change."""
+def rollout_tc_weights(spec, E, w_sa, w_ih, w_hh, heads, dev, bwd=False):
+    """(plan, packed bf16 weight stream) of the tcgen05 rollout (forward or BPTT); the stream is re-packed when the masters
+    change."""
     D, S, H, A = spec.D, spec.S, spec.H, spec.A
-    plan, n_pack, packed_bytes = rollout_tc_plan(D, S, H, A, E, dev)
+    plan, n_pack, packed_bytes = rollout_tc_plan(D, S, H, A, E, dev, bwd)
     ws = [w_sa, w_ih, w_hh] + [w for hd in heads for w in (hd[0], hd[2])]
-    key = ("rollout_tc", E) + tuple(w.data_ptr() for w in ws)
+    key = ("rollout_tc", E, bwd) + tuple(w.data_ptr() for w in ws)
     ver = (_STATE["wversion"],) + tuple(w._version for w in ws)
     hit = _wcache.get(key)
     if hit is None or hit[0] != ver:

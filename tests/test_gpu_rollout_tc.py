@@ -100,3 +100,58 @@ def test_rollout_tc_stash_matches_fp32():
     for i, (r, o) in enumerate(zip(*stashes)):
         err = (o - r).abs()
         assert float(err.max()) <= 3e-2 * max(1.0, float(r.abs().max())), (i, float(err.max()))
+
+
+BWD_CASES = [
+    (200, 30, 200, 3, "MoPoE", (0, 1024, 128), 6, 40, False),
+    (200, 30, 200, 3, "PoE", (0, 1024, 128), 4, 70, False),
+    (200, 30, 200, 3, "single", (1024,), 5, 33, False),
+    (200, 30, 200, 3, None, (), 7, 20, False),
+    (64, 8, 48, 2, "MoPoE", (0, 72), 5, 9, False),
+    (208, 32, 104, 6, "PoE", (0, 64, 64), 3, 65, False),
+]
+
+
+@pytest.mark.parametrize("case", BWD_CASES)
+def test_rollout_tc_bptt_matches_fp32(case):
+    """BPTT on the tensor cores (csrc/rollout_tc.cu, backward) against the exact fp32 BPTT kernel: same stash, same upstream
+    gradients.  Compared: gradients of the initial state / belief, of the actions and embeddings, and every parameter
+    gradient (the deferred weight-gradient GEMMs run on the kernels' pre-activation gradients).  Tolerance (stated): relative
+    Frobenius error <= 3e-2 per tensor (bf16 operand rounding of gradients and weights, T recurrent steps)."""
+    from mrssm_b200 import _lib as L, ops
+    D, S, H, A, fusion, emb_sizes, T, B, det = case
+    gen = torch.Generator(device=DEV).manual_seed(11 + D + B)
+    observe = fusion is not None
+    E = len(emb_sizes)
+    table = ops.FusionTable(E, S, fusion if observe else "single")
+    spec = ops.RolloutSpec(D, S, H, A, ops.RELU, 0.1, table, [e > 0 for e in emb_sizes])
+    params = [p.requires_grad_(True) for p in _params(gen, D, S, H, A, emb_sizes)]
+    rn = lambda *s: torch.randn(*s, device=DEV, generator=gen)
+    nonterm = (torch.rand(T, B, device=DEV, generator=gen) > 0.15).float()
+    ins = [rn(B, S).requires_grad_(True), rn(T, B, A).requires_grad_(True), (rn(B, D) * 0.5).requires_grad_(True), nonterm,
+           rn(T, B, S), rn(T, B, S) if observe else None]
+    embs = [rn(T, B, e).requires_grad_(True) for e in emb_sizes if e > 0]
+    n_out = 7 + 2 * E if observe else 4
+    gouts = None
+    results = []
+    for tc in (False, True):
+        for t in ins[:3] + embs + params:
+            t.grad = None
+        ops.set_bf16_mode(True)
+        ops.set_rollout_tc(False)                       # identical (fp32-kernel) forward and stash for both runs
+        try:
+            outs = ops.RolloutFn.apply(spec, observe, det, *ins, *embs, *params)
+            assert len(outs) == n_out
+            if gouts is None:
+                gouts = [rn(*o.shape) / o.shape[-1] ** 0.5 for o in outs]
+            ops.set_rollout_tc(tc)
+            torch.autograd.backward(outs, gouts)
+        finally:
+            ops.set_rollout_tc(True)
+            ops.set_bf16_mode(False)
+        results.append([t.grad.clone() for t in ins[:3] + embs + params])
+    names = ["g_prev_state", "g_actions", "g_prev_belief"] + [f"g_emb{i}" for i in range(len(embs))] + [f"g_param{i}" for i in range(len(params))]
+    for n, r, o in zip(names, *results):
+        assert torch.isfinite(o).all(), n
+        rel = float((o - r).norm() / (r.norm() + 1e-12))
+        assert rel <= 3e-2, (n, rel, float(r.norm()))
