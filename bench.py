@@ -325,7 +325,7 @@ def run_ours(args):
     total_ms = sum(d["ms"] for d in agg.values())
     dom_key = max(agg, key=lambda k: agg[k]["ms"])
     roof = roofline_of(dom_key, agg[dom_key], pk, total_ms)
-    rollout_roof = {k: roofline_of(k, agg[k], pk, total_ms) for k in ("rollout_fwd:observe", "rollout_bwd:observe") if k in agg}
+    rollout_roof = {k: roofline_of(k, agg[k], pk, total_ms) for k in ("rollout_fwd:observe", "rollout_bwd:observe", "rollout_tc_fwd:observe", "rollout_tc_bwd:observe") if k in agg}
     top = sorted(((k, d["ms"], d["n"]) for k, d in agg.items()), key=lambda x: -x[1])[:60]
 
     cpu = None

@@ -247,6 +247,8 @@ int mrssm_rollout_tc_fwd(const mrssm_rollout_args* a, const void* plan_dev, cons
  * 16-row MMA group (16 -> 64 sequences per CTA, 8 -> 32, 0 = automatic) */
 int mrssm_rollout_tc_set_profile_buffer(void* dev_buf);
 int mrssm_rollout_tc_set_rows(int32_t rows_per_group);
+/* 0: force the table-driven MMA issue even for the sizes with a statically unrolled program (D=H=200, S=30, A=3; 1, 2, 4 heads) */
+int mrssm_rollout_tc_set_static(int32_t on);
 
 /* BPTT through the rollout (autograd of transition_model.py:226-270).  Consumes the forward's
  * outputs/stash plus upstream gradients of every output; produces the data gradients and the

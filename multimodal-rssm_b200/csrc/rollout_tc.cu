@@ -365,9 +365,112 @@ __device__ __forceinline__ void wait_backoff(uint64_t* bar, uint32_t parity) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Statically unrolled MMA issue for the shipped model sizes: the same program build_plan / build_plan_bwd emit, walked at
+// compile time so every descriptor offset, TMEM column, N and tile boundary is an immediate (one thread issues ~10
+// instructions per MMA instead of ~40 through the run tables; the MMA issuer is the serial bottleneck of a step).  The
+// tile split below MUST mirror PlanBuilder::mma2 (greedy fill of SLOT_BYTES per unit) — tests/test_rollout_tc_plan.py and the
+// GPU parity tests cover both paths.
+// ---------------------------------------------------------------------------------------------------------------
+struct Issuer {
+    uint32_t slot, phase, NS, ring16, tmem, par, sb;
+    int it;
+    uint64_t *full, *empty, *ev, *cm;
+    int tile_bytes;
+    bool open;
+    __device__ __forceinline__ void unit_begin(int wev) {
+        if (wev >= 0) {
+            if (wev == 0) {
+                if (it > 0) tc::mbar_wait(tc::smem_u32(&ev[0]), par ^ 1u);
+            } else {
+                tc::mbar_wait(tc::smem_u32(&ev[wev]), par);
+            }
+            tc::tc_fence_after();
+        }
+        open = false;
+    }
+    __device__ __forceinline__ void close_tile() {
+        tc::umma_commit(tc::smem_u32(&empty[slot]));
+        if (++slot == NS) { slot = 0; phase ^= 1u; }
+    }
+    __device__ __forceinline__ void unit_end(int cmi) {
+        tc::umma_commit(tc::smem_u32(&empty[slot]));
+        tc::umma_commit(tc::smem_u32(&cm[cmi]));
+        if (++slot == NS) { slot = 0; phase ^= 1u; }
+        open = false;
+    }
+    __device__ __forceinline__ void emit(uint32_t a16, int d_col, int N, int acc) {
+        const int bytes = 32 * N;
+        if (!open || tile_bytes + bytes > SLOT_BYTES) {
+            if (open) close_tile();
+            tc::mbar_wait(tc::smem_u32(&full[slot]), phase);
+            tc::tc_fence_after();
+            sb = ring16 + slot * (uint32_t)(SLOT_BYTES >> 4);
+            tile_bytes = 0;
+            open = true;
+        }
+        const uint32_t hi = (128u >> 4) | (1u << 14);
+        r_umma(tmem + (uint32_t)d_col, a16 | (((uint32_t)CH_BYTES >> 4) << 16), (sb + (uint32_t)(tile_bytes >> 4)) | ((uint32_t)N << 16), hi,
+               tc::idesc_bf16(ROWS, N, 0, 0), (uint32_t)acc);
+        tile_bytes += bytes;
+    }
+};
+constexpr uint32_t CH16 = CH_BYTES >> 4;
+
+template <int D, int S, int H, int A, int NH>
+__device__ __forceinline__ void static_step_fwd(Issuer& I, uint32_t xin16, uint32_t xu16, uint32_t hprev16, uint32_t hnew16) {
+    constexpr int nD8 = D / 8, nH8 = H / 8, cA = (nD8 + 1) / 2, cAH = (nH8 + 1) / 2;
+    constexpr int nkD = (D + 15) / 16, nkH = (H + 15) / 16, nkX = (S + A + 15) / 16, ND = (D + 15) / 16 * 16;
+    I.unit_begin(EV_XIN);
+#pragma unroll
+    for (int k = 0; k < nkX; ++k) I.emit(xin16 + 2 * k * CH16, 0, ND, k != 0);
+    I.unit_end(CM_X);
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+        const int nc = hf ? nD8 - cA : cA, N = (8 * nc + 15) / 16 * 16;
+        I.unit_begin(hf ? EV_HA : EV_X);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+#pragma unroll
+            for (int k = 0; k < nkD; ++k) I.emit(xu16 + 2 * k * CH16, g * ACC_STRIDE, N, k != 0);
+#pragma unroll
+            for (int k = 0; k < nkD; ++k) I.emit(hprev16 + 2 * k * CH16, g * ACC_STRIDE, N, 1);
+        }
+#pragma unroll
+        for (int k = 0; k < nkD; ++k) I.emit(xu16 + 2 * k * CH16, 2 * ACC_STRIDE, N, k != 0);
+#pragma unroll
+        for (int k = 0; k < nkD; ++k) I.emit(hprev16 + 2 * k * CH16, 3 * ACC_STRIDE, N, k != 0);
+        I.unit_end(hf ? CM_GB : CM_GA);
+    }
+    auto fc1 = [&](int hd, int hf, int wev) {
+        const int nc = hf ? nH8 - cAH : cAH, N = (8 * nc + 15) / 16 * 16;
+        I.unit_begin(wev);
+#pragma unroll
+        for (int k = 0; k < nkD; ++k) I.emit(hnew16 + 2 * k * CH16, hf * ACC_STRIDE, N, k != 0);
+        I.unit_end(CM_F1 + 2 * hd + hf);
+    };
+    auto fc2 = [&](int hd) {
+        I.unit_begin(EV_U0 + 2 * hd + 1);
+#pragma unroll
+        for (int k = 0; k < nkH; ++k) I.emit(xu16 + 2 * k * CH16, F2_COL + 64 * hd, 64, k != 0);
+        I.unit_end(CM_F2 + hd);
+    };
+    fc1(0, 0, EV_HB);
+    fc1(0, 1, -1);
+#pragma unroll
+    for (int hd = 1; hd < NH; ++hd) {
+        fc1(hd, 0, EV_U0 + 2 * hd - 2);
+        fc2(hd - 1);
+        fc1(hd, 1, -1);
+    }
+    fc2(NH - 1);
+}
+
 // Warp roles.  The MMA issuer is the highest warp id of its scheduler (the issue arbiter favours high warp ids).
 constexpr int PROD_WARP = 16, ALLOC_WARP = 17, MMA_WARP = 18;
 
+template <int NHS>      // 0: table-driven MMA issue (any eligible size); > 0: statically unrolled issue for D=H=200, S=30, A=3, NHS heads
 __global__ void __launch_bounds__(TC_THREADS, 1)
 rollout_tc_fwd_kernel(const __grid_constant__ mrssm_rollout_args a, const __grid_constant__ TcProg prog, const uint8_t* __restrict__ packed,
                       const int NS, const int RPG, long long* __restrict__ prof) {
@@ -467,7 +570,18 @@ rollout_tc_fwd_kernel(const __grid_constant__ mrssm_rollout_args a, const __grid
         __syncwarp();
     } else if (warp == MMA_WARP) {
         // ---- MMA issuer ------------------------------------------------------------------------------------
-        if (lane == 0) {
+        if (NHS > 0) {
+            if (lane == 0) {
+                Issuer I;
+                I.slot = 0; I.phase = 0; I.NS = (uint32_t)NS; I.ring16 = (smem0 + OFF_RING) >> 4; I.tmem = tmem_base;
+                I.full = full; I.empty = empty; I.ev = ev; I.cm = cm; I.tile_bytes = 0; I.open = false; I.sb = 0;
+                for (int t = 0; t < T; ++t) {
+                    I.it = t; I.par = (uint32_t)(t & 1);
+                    static_step_fwd<200, 30, 200, 3, (NHS > 0 ? NHS : 1)>(I, (smem0 + OFF_XIN) >> 4, (smem0 + OFF_XU) >> 4,
+                                                                        (smem0 + ((t & 1) ? OFF_H1 : OFF_H0)) >> 4, (smem0 + ((t & 1) ? OFF_H0 : OFF_H1)) >> 4);
+                }
+            }
+        } else if (lane == 0) {
             const uint32_t hi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1, no swizzle
             const uint32_t hdelta = (uint32_t)(OFF_H1 - OFF_H0) >> 4;
             int pi = 0;
@@ -933,11 +1047,56 @@ __device__ __forceinline__ void mma_role(const TcProg& prog, uint32_t abase, uin
     }
 }
 
+
+template <int D, int S, int H, int A, int NH>
+__device__ __forceinline__ void static_step_bwd(Issuer& I, uint32_t base16) {
+    constexpr int nH8 = H / 8, cAH = (nH8 + 1) / 2;
+    constexpr int nkD = (D + 15) / 16, nkH = (H + 15) / 16, ND = (D + 15) / 16 * 16;
+    auto gb = [&](int hd, int hf, int wev) {
+        const int nc = hf ? nH8 - cAH : cAH, N = (8 * nc + 15) / 16 * 16;
+        I.unit_begin(wev);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) I.emit(base16 + (BCH_DO + 8 * hd + 2 * k) * CH16, hf * BCOL_SET, N, k != 0);
+        I.unit_end(CMB_GB0 + 2 * hd + hf);
+    };
+    auto gc = [&](int hd) {
+        I.unit_begin(EVB_DU0 + 2 * hd + 1);
+#pragma unroll
+        for (int k = 0; k < nkH; ++k) I.emit(base16 + (BCH_DU + 2 * k) * CH16, BCOL_GH, ND, !(hd == 0 && k == 0));
+        I.unit_end(CMB_GCH0 + hd);
+    };
+    gb(0, 0, EVB_DO);
+    gb(0, 1, -1);
+#pragma unroll
+    for (int hd = 0; hd < NH; ++hd) {
+        if (hd + 1 < NH) gb(hd + 1, 0, EVB_DU0 + 2 * hd);
+        gc(hd);
+        if (hd + 1 < NH) gb(hd + 1, 1, -1);
+    }
+    I.unit_begin(EVB_GRU);
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+#pragma unroll
+        for (int k = 0; k < nkD; ++k) I.emit(base16 + ((g == 0 ? BCH_DR : (g == 1 ? BCH_DZ : BCH_DN)) + 2 * k) * CH16, BCOL_GX, ND, !(g == 0 && k == 0));
+    }
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+#pragma unroll
+        for (int k = 0; k < nkD; ++k) I.emit(base16 + ((g == 0 ? BCH_DR : (g == 1 ? BCH_DZ : BCH_DNR)) + 2 * k) * CH16, BCOL_GHH, ND, !(g == 0 && k == 0));
+    }
+    I.unit_end(CMB_GE);
+    I.unit_begin(EVB_DX);
+#pragma unroll
+    for (int k = 0; k < nkD; ++k) I.emit(base16 + (BCH_DX + 2 * k) * CH16, BCOL_XIN, 8 * XIN_CH, k != 0);
+    I.unit_end(CMB_GF);
+}
+
 struct BwdPtrs {          // per-head pointers the epilogue indexes dynamically (kept in shared memory)
     const float *st_u[TC_MAX_HEADS], *exp_means[TC_MAX_HEADS], *exp_stds[TC_MAX_HEADS], *g_exp_means[TC_MAX_HEADS], *g_exp_stds[TC_MAX_HEADS];
     float *d_u[TC_MAX_HEADS], *d_o[TC_MAX_HEADS];
 };
 
+template <int NHS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __grid_constant__ TcProg prog, const uint8_t* __restrict__ packed,
                       const int NS, const int RPG) {
@@ -1081,7 +1240,19 @@ rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __
         if (lane == 0) producer_role(prog, packed, smem0 + BOFF_RING, NS, T, full, empty);
         __syncwarp();
     } else if (warp == MMA_WARP) {
-        if (lane == 0) mma_role(prog, smem0, smem0 + BOFF_RING, NS, T, tmem_base, full, empty, ev, cm);
+        if (NHS > 0) {
+            if (lane == 0) {
+                Issuer I;
+                I.slot = 0; I.phase = 0; I.NS = (uint32_t)NS; I.ring16 = (smem0 + BOFF_RING) >> 4; I.tmem = tmem_base;
+                I.full = full; I.empty = empty; I.ev = ev; I.cm = cm; I.tile_bytes = 0; I.open = false; I.sb = 0;
+                for (int it = 0; it < T; ++it) {
+                    I.it = it; I.par = (uint32_t)(it & 1);
+                    static_step_bwd<200, 30, 200, 3, (NHS > 0 ? NHS : 1)>(I, smem0 >> 4);
+                }
+            }
+        } else if (lane == 0) {
+            mma_role(prog, smem0, smem0 + BOFF_RING, NS, T, tmem_base, full, empty, ev, cm);
+        }
         __syncwarp();
     } else if (warp < EPI_WARPS) {
         const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
@@ -1367,6 +1538,12 @@ extern "C" int mrssm_rollout_tc_pack(const mrssm_rollout_args* a, const void* pl
 
 static long long* g_tc_prof = nullptr;
 static int g_tc_rpg = 0;
+static int g_tc_static = 1;
+/* tuning / test aid: 0 forces the table-driven MMA issue even for the sizes that have a statically unrolled program */
+extern "C" int mrssm_rollout_tc_set_static(int32_t on) {
+    g_tc_static = on ? 1 : 0;
+    return 0;
+}
 /* tuning aid: sequences per 16-row group of a CTA (16 -> 64 sequences per CTA, 8 -> 32; 0 = automatic) */
 extern "C" int mrssm_rollout_tc_set_rows(int32_t rows_per_group) {
     MRSSM_CHECK(rows_per_group == 0 || rows_per_group == 8 || rows_per_group == 16, "rollout_tc_set_rows: 0, 8 or 16");
@@ -1392,8 +1569,11 @@ extern "C" int mrssm_rollout_tc_fwd(const mrssm_rollout_args* a, const void* pla
         MRSSM_CHECK(a->det || a->eps_post, "rollout_tc_fwd: eps_post missing");
     }
     MRSSM_CHECK(a->det || a->eps_prior, "rollout_tc_fwd: eps_prior missing");
+    const int NH = 1 + a->n_experts;
+    const bool stat = g_tc_static && a->D == 200 && a->S == 30 && a->H == 200 && a->A == 3 && (NH == 1 || NH == 2 || NH == 4);
+    auto kern = !stat ? rollout_tc_fwd_kernel<0> : (NH == 1 ? rollout_tc_fwd_kernel<1> : (NH == 2 ? rollout_tc_fwd_kernel<2> : rollout_tc_fwd_kernel<4>));
     cudaFuncAttributes fa;
-    MRSSM_CUDA(cudaFuncGetAttributes(&fa, rollout_tc_fwd_kernel));
+    MRSSM_CUDA(cudaFuncGetAttributes(&fa, kern));
     static thread_local TcProg prog;
     static thread_local int prog_key[5] = {-1, -1, -1, -1, -1};
     if (prog_key[0] != a->D || prog_key[1] != a->S || prog_key[2] != a->H || prog_key[3] != a->A || prog_key[4] != a->n_experts) {
@@ -1425,10 +1605,10 @@ extern "C" int mrssm_rollout_tc_fwd(const mrssm_rollout_args* a, const void* pla
     const int NS = std::min(MAX_SLOTS, avail / SLOT_BYTES);
     MRSSM_CHECK(NS >= 2, "rollout_tc_fwd: no room for the weight ring (%d bytes left)", avail);
     const size_t dyn = (size_t)OFF_RING + (size_t)NS * SLOT_BYTES + 1024;
-    MRSSM_CUDA(cudaFuncSetAttribute(rollout_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    MRSSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     // 64 sequences per CTA when that already fills the machine's appetite, else 32 (one valid row per epilogue thread)
     const int RPG = g_tc_rpg ? g_tc_rpg : ((a->B + 63) / 64 >= 74 ? 16 : 8);
-    rollout_tc_fwd_kernel<<<(a->B + 4 * RPG - 1) / (4 * RPG), TC_THREADS, dyn, (cudaStream_t)stream>>>(*a, prog, (const uint8_t*)packed_dev, NS, RPG,
+    kern<<<(a->B + 4 * RPG - 1) / (4 * RPG), TC_THREADS, dyn, (cudaStream_t)stream>>>(*a, prog, (const uint8_t*)packed_dev, NS, RPG,
                                                                                                         g_tc_prof);
     MRSSM_LAUNCH_CHECK();
     return 0;
@@ -1509,15 +1689,18 @@ extern "C" int mrssm_rollout_tc_bwd(const mrssm_rollout_bwd_args* g, const void*
         fill_prog(pb, h, prog);
         key[0] = a->D; key[1] = a->S; key[2] = a->H; key[3] = a->A; key[4] = a->n_experts;
     }
+    const int NH = 1 + a->n_experts;
+    const bool stat = g_tc_static && a->D == 200 && a->S == 30 && a->H == 200 && a->A == 3 && (NH == 1 || NH == 2 || NH == 4);
+    auto kern = !stat ? rollout_tc_bwd_kernel<0> : (NH == 1 ? rollout_tc_bwd_kernel<1> : (NH == 2 ? rollout_tc_bwd_kernel<2> : rollout_tc_bwd_kernel<4>));
     cudaFuncAttributes fa;
-    MRSSM_CUDA(cudaFuncGetAttributes(&fa, rollout_tc_bwd_kernel));
+    MRSSM_CUDA(cudaFuncGetAttributes(&fa, kern));
     const int avail = 232448 - (int)fa.sharedSizeBytes - 1024 - BOFF_RING;
     const int NS = std::min(MAX_SLOTS, avail / SLOT_BYTES);
     MRSSM_CHECK(NS >= 2, "rollout_tc_bwd: no room for the weight ring (%d bytes left)", avail);
     const size_t dyn = (size_t)BOFF_RING + (size_t)NS * SLOT_BYTES + 1024;
-    MRSSM_CUDA(cudaFuncSetAttribute(rollout_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    MRSSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     const int RPG = g_tc_rpg ? g_tc_rpg : ((a->B + 63) / 64 >= 74 ? 16 : 8);
-    rollout_tc_bwd_kernel<<<(a->B + 4 * RPG - 1) / (4 * RPG), TC_THREADS, dyn, (cudaStream_t)stream>>>(*g, prog, (const uint8_t*)packed_dev, NS, RPG);
+    kern<<<(a->B + 4 * RPG - 1) / (4 * RPG), TC_THREADS, dyn, (cudaStream_t)stream>>>(*g, prog, (const uint8_t*)packed_dev, NS, RPG);
     MRSSM_LAUNCH_CHECK();
     return 0;
 }

@@ -128,6 +128,7 @@ SYMBOLS = {
     "mrssm_rollout_tc_fwd": [C.POINTER(RolloutArgs), _vp, _vp, _vp],
     "mrssm_rollout_tc_set_profile_buffer": [_vp],
     "mrssm_rollout_tc_set_rows": [_i32],
+    "mrssm_rollout_tc_set_static": [_i32],
     "mrssm_rollout_tc_bwd_plan_bytes": [_i32, _i32, _i32, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64)],
     "mrssm_rollout_tc_bwd_plan": [_i32, _i32, _i32, _i32, _i32, _vp, _i64],
     "mrssm_rollout_tc_bwd": [C.POINTER(RolloutBwdArgs), _vp, _vp],
