@@ -1099,7 +1099,7 @@ struct BwdPtrs {          // per-head pointers the epilogue indexes dynamically 
 template <int NHS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __grid_constant__ TcProg prog, const uint8_t* __restrict__ packed,
-                      const int NS, const int RPG) {
+                      const int NS, const int RPG, long long* __restrict__ prof) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full[MAX_SLOTS], empty[MAX_SLOTS], ev[N_EV], cm[N_CM];
     __shared__ uint32_t tmem_base_s;
@@ -1258,10 +1258,13 @@ rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __
         const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
         const uint32_t opnd0 = (uint32_t)(r0 * 16 + cj * 2), opnd1 = (uint32_t)(r1 * 16 + cj * 2);
         const uint32_t cg0 = smem0 + BOFF_CG + (uint32_t)(r0 * 32 + cj * 4), cg1 = smem0 + BOFF_CG + (uint32_t)(r1 * 32 + cj * 4);
+        int pi = 0;
+#define BSTAMP() do { if (prof && warp == 0 && lane == 0 && blockIdx.x == 0 && it == PROF_STEP && pi < PROF_SLOTS) prof[2 * PROF_SLOTS + pi++] = clock64(); } while (0)
         for (int it = 0; it < T; ++it) {
             const int t = T - 1 - it;
             const uint32_t par = (uint32_t)(it & 1);
             const long long row0 = (long long)t * B + seq0, row1 = row0 + 8;
+            BSTAMP();
             // ---- Eb: du_h = gu_h * act'(u_h) -> DU operand, d_u ------------------------------------------------
             for (int hd = 0; hd < NH; ++hd) {
                 const float* su = P.st_u[hd];
@@ -1283,6 +1286,7 @@ rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __
                     const int cmi = (hf == 0 && hd > 0) ? CMB_GCH0 + hd - 1 : CMB_GB0 + 2 * hd + hf;
                     wait_backoff(&cm[cmi], par);
                     tc::tc_fence_after();
+                    BSTAMP();
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int c = c_lo + p + 4 * i;
@@ -1303,6 +1307,7 @@ rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __
                         }
                     }
                     epi_signal(&ev[EVB_DU0 + 2 * hd + hf], lane);
+                    BSTAMP();
                 }
             }
             // ---- Ed: G = g_beliefs + carry + acc ; GRU gate backward -> dr, dz, dn, dn*r operands, d_gi, d_gh; carry = G z ------
@@ -1328,6 +1333,7 @@ rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __
                 GruIn nx0 = load_in(p, 0), nx1 = load_in(two ? p : nD8, 1);
                 wait_backoff(&cm[CMB_GCH0 + NH - 1], par);
                 tc::tc_fence_after();
+                BSTAMP();
                 for (int c = p; c < nD8; c += 4) {
                     const GruIn in0 = nx0, in1 = nx1;
                     nx0 = load_in(c + 4, 0);
@@ -1377,6 +1383,7 @@ rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __
                 }
             }
             epi_signal(&ev[EVB_GRU], lane);
+            BSTAMP();
             // ---- Ee: dxpre = gx * act'(x) -> DX operand, d_xpre ; carry += gh -----------------------------------
             float2 xn0 = make_float2(0.f, 0.f), xn1 = make_float2(0.f, 0.f);
             if (p < nD8) {
@@ -1385,6 +1392,7 @@ rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __
             }
             wait_backoff(&cm[CMB_GE], par);
             tc::tc_fence_after();
+            BSTAMP();
             for (int c = p; c < nD8; c += 4) {
                 const float2 xa = xn0, xb = xn1;
                 if (c + 4 < nD8) {
@@ -1418,9 +1426,11 @@ rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __
                 for (int i = tid; i < CH_BYTES / 4; i += EPI_WARPS * 32) st_shared_u32(smem0 + (uint32_t)((BCH_DX + nD8) * CH_BYTES + 4 * i), 0u);
             }
             epi_signal(&ev[EVB_DX], lane);
+            BSTAMP();
             // ---- Ef: g_xin -> state carry (masked), action grads, xin ; then go of step t-1 -------------------------
             wait_backoff(&cm[CMB_GF], par);
             tc::tc_fence_after();
+            BSTAMP();
             for (int grp = p; grp * 8 < S + A; grp += 4) {
                 float v[4];
                 ld_frag(tlane + (uint32_t)(BCOL_XIN + 8 * grp), v);
@@ -1449,8 +1459,10 @@ rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __
                     }
                 }
             }
+            BSTAMP();
             if (t > 0) step_a(t - 1);
             epi_signal(&ev[EVB_DO], lane);
+            BSTAMP();
         }
         // ---- carries out -------------------------------------------------------------------------------------
         if (g.g_prev_belief) {
@@ -1700,7 +1712,7 @@ extern "C" int mrssm_rollout_tc_bwd(const mrssm_rollout_bwd_args* g, const void*
     const size_t dyn = (size_t)BOFF_RING + (size_t)NS * SLOT_BYTES + 1024;
     MRSSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     const int RPG = g_tc_rpg ? g_tc_rpg : ((a->B + 63) / 64 >= 74 ? 16 : 8);
-    kern<<<(a->B + 4 * RPG - 1) / (4 * RPG), TC_THREADS, dyn, (cudaStream_t)stream>>>(*g, prog, (const uint8_t*)packed_dev, NS, RPG);
+    kern<<<(a->B + 4 * RPG - 1) / (4 * RPG), TC_THREADS, dyn, (cudaStream_t)stream>>>(*g, prog, (const uint8_t*)packed_dev, NS, RPG, g_tc_prof);
     MRSSM_LAUNCH_CHECK();
     return 0;
 }
