@@ -172,6 +172,8 @@ int mrssm_pl_pack_weight(const float* w, int64_t w_ss, int64_t w_sl, int32_t Cs_
 int mrssm_pl_import(const mrssm_t4* src, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t Cpad, float scale,
                     const mrssm_tv* dst, void* stream);
 /* out[c] += sum over (img,y,x) of the view: bias gradients (autograd of encoder.py:315-322, observation_model.py:65-74) */
+/* bf16 view -> bf16 view copy of the same logical [n,H,W,Cpad] tensor (layout change, e.g. parity-planar -> NHWC) */
+int mrssm_pl_copy(const mrssm_tv* src, int32_t n_img, int32_t H, int32_t W, int32_t Cpad, const mrssm_tv* dst, void* stream);
 /* fp32 strided [n,H,W,C<=4] -> the space-to-depth view described at mrssm_pl_conv_args.s2d_cq */
 int mrssm_pl_import_s2d(const mrssm_t4* src, int32_t n_img, int32_t H, int32_t W, int32_t C, float scale, const mrssm_tv* dst,
                         void* stream);

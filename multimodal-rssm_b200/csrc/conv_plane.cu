@@ -1208,6 +1208,20 @@ __global__ void import_view_kernel(T4 src, int n, int H, int W, int Cc, int nchu
     }
 }
 
+// bf16 view -> bf16 view (same logical [n,H,W,C] tensor, different layout): 16 bytes per (pixel, chunk)
+__global__ void copy_view_kernel(TV src, int n, int H, int W, int nchunk, TV dst) {
+    const long long total = (long long)n * H * W * nchunk;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % nchunk);
+        long long t = i / nchunk;
+        const int x = (int)(t % W);
+        t /= W;
+        const int y = (int)(t % H), img = (int)(t / H);
+        const uint4 pk = __ldg(reinterpret_cast<const uint4*>((const bf16*)src.p + tv_pix(src, img, y, x) + ch * src.sK));
+        *reinterpret_cast<uint4*>((bf16*)dst.p + tv_pix(dst, img, y, x) + ch * dst.sK) = pk;
+    }
+}
+
 // fp32 strided [n,H,W,C<=4] -> space-to-depth bf16 view [n,ceil(H/2),ceil(W/2),16]: channel = (py*2+px)*C + c, rest zero
 __global__ void import_s2d_kernel(T4 src, int n, int H, int W, int Cc, float scale, TV dst) {
     const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
@@ -1372,6 +1386,15 @@ extern "C" int mrssm_pl_import(const mrssm_t4* src, int32_t n_img, int32_t H, in
     const long long total = (long long)n_img * H * W * (Cpad / 8);
     const int blocks = (int)std::min<long long>(148 * 16, ceil_div64(total, 256));
     import_view_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cvt(*src), n_img, H, W, C, Cpad / 8, scale, cvt(*dst));
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mrssm_pl_copy(const mrssm_tv* src, int32_t n_img, int32_t H, int32_t W, int32_t Cpad, const mrssm_tv* dst, void* stream) {
+    MRSSM_CHECK(src && src->ptr && dst && dst->ptr && Cpad % 8 == 0 && Cpad > 0, "pl_copy: bad args");
+    const long long total = (long long)n_img * H * W * (Cpad / 8);
+    const int blocks = (int)std::min<long long>(148 * 16, ceil_div64(total, 256));
+    copy_view_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cvt(*src), n_img, H, W, Cpad / 8, cvt(*dst));
     MRSSM_LAUNCH_CHECK();
     return 0;
 }

@@ -113,6 +113,7 @@ SYMBOLS = {
     "mrssm_pl_conv_up": [C.POINTER(PlConvArgs), _vp],
     "mrssm_pl_conv_wgrad": [C.POINTER(PlConvArgs), _vp],
     "mrssm_pl_import": [C.POINTER(T4), _i32, _i32, _i32, _i32, _i32, _f, C.POINTER(TV), _vp],
+    "mrssm_pl_copy": [C.POINTER(TV), _i32, _i32, _i32, _i32, C.POINTER(TV), _vp],
     "mrssm_pl_colsum": [C.POINTER(TV), _i32, _i32, _i32, _i32, _i32, _i32, _vp, _f, _vp, _vp],
     "mrssm_pl_packed_shape": [_i32, _i32, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32)],
     "mrssm_pl_pack_weight": [_vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp],

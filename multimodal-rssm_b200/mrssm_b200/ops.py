@@ -885,6 +885,13 @@ def pl_import(src_t4, n, H, W, Cc, Cp, layout, device, scale=1.0):
     return t, v
 
 
+def pl_copy(src_view, n, H, W, Cp, layout, device):
+    """bf16 view -> new bf16 buffer of the same logical tensor in `layout`."""
+    t, v = new_act(n, H, W, Cp, layout, device)
+    L.call("mrssm_pl_copy", C.byref(src_view), n, H, W, Cp, C.byref(v))
+    return t, v
+
+
 def pl_colsum(view, n, H, W, Cp, Cvalid, out, fold=0, scale=None):
     """out[c] += sum over pixels.  fold: the view is the space-to-depth view (H, W its own size) of a fold-channel tensor."""
     sp, sm = (L.ptr(scale[0]), float(scale[1])) if scale is not None else (None, 1.0)
@@ -1073,7 +1080,15 @@ class ConvEncoderTCFn(Function):
             geom, Cs, Cl, cq = geoms[i]
             N, Hl, Wl, Clp, Hs, Ws, Csp, k = geom
             xv = L.tv(acts[i], L.PLANAR, (Hl + 1) // 2, (Wl + 1) // 2, Clp) if cq else L.tv(acts[i], L.PARITY, Hl, Wl, Clp)
-            pl_conv_wgrad(geom, xv, gb[1], L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl, s2d_cq=cq)
+            if i == n_layers - 1 and Hs * Ws <= 4 and not cq:
+                # tiny maps: the plane kernel's TMA boxes are a few pixels wide (3.1 ms at cfg 3); the NHWC implicit-GEMM
+                # weight-gradient kernel gathers whole channel runs instead (1.2 ms + two small layout copies)
+                xn = pl_copy(xv, N, Hl, Wl, Clp, L.NHWC, dev)[0]
+                gn = pl_import(L.nchw(gm, Hs, Ws, Cs), N, Hs, Ws, Cs, Csp, L.NHWC, dev)[0]
+                tc_conv_wgrad(geom, L.nhwc(xn, Hl, Wl, Clp), L.nhwc(gn, Hs, Ws, Csp), L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl)
+                del xn, gn
+            else:
+                pl_conv_wgrad(geom, xv, gb[1], L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl, s2d_cq=cq)
             pl_colsum(gb[1], N, Hs, Ws, Csp, Cs, grad_buf(b))
             if i > 0:
                 gx = new_act(N, Hl, Wl, Clp, L.PLANAR, dev)
