@@ -905,6 +905,9 @@ struct WgP {
     int ksz, nt, Clp, Csp, N;
     int NG, gpp, n_cpass, n_mhalf;
     int NA, zero_bytes, mergedS, mergedL, s2d_cq;
+    int rep, Ntot;              // rep: the large tile is loaded once per COLUMN tap b with the box origin shifted by b pixels (plane
+                                // group = b), so one MMA of N = Ntot = nt * N covers the nt column taps of a row tap a; row taps stay
+                                // descriptor shifts of a * BX pixels (space-to-depth sources: N = 16 per tap otherwise)
     const float* scale_ptr;
     float scale_mul;
     int cs_valid, cl_valid;
@@ -961,6 +964,13 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
                 }
                 for (int q = 0; q < P.nL; ++q) {
                     const int mi = q / P.cpl, ch = q - mi * P.cpl;
+                    if (P.rep) {            // plane group mi = column tap b: the same box, origin shifted by b pixels
+                        if (P.mergedL)
+                            tma_load_4d(dst + (uint32_t)P.offL + (uint32_t)q * (uint32_t)P.PS_l, &mL0, 2 * mi, band * P.TH, ch, ig * P.BI, bar);
+                        else
+                            tma_load_4d(dst + (uint32_t)P.offL + (uint32_t)q * (uint32_t)P.PS_l, &mL0, ch * 8, mi, band * P.TH, ig * P.BI, bar);
+                        continue;
+                    }
                     const CUtensorMap* m = mi == 0 ? &mL0 : (mi == 1 ? &mL1 : (mi == 2 ? &mL2 : &mL3));
                     if (P.mergedL)
                         tma_load_4d(dst + (uint32_t)P.offL + (uint32_t)q * (uint32_t)P.PS_l, m, 0, band * P.TH, ch, ig * P.BI, bar);
@@ -986,6 +996,23 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
                 tc::tc_fence_after();
                 const uint32_t sS = smem0 + (uint32_t)sa * (uint32_t)P.stage_bytes, sL = sS + (uint32_t)P.offL;
                 const uint32_t a0 = ((sS >> 4) & 0x3FFFu) | lbo;
+                if (P.rep) {                // the nt column taps of row tap a in one MMA: B walks the nt * cpl x-shifted plane copies
+                    const uint32_t idesc_all = tc::idesc_bf16(128, P.Ntot, 1, 1);
+                    for (int ta = 0; ta < P.nt; ++ta) {
+                        uint32_t a_lo = a0, b_lo = (((sL + (uint32_t)(ta * P.BX) * 16u) >> 4) & 0x3FFFu) | lbo;
+                        const uint32_t d = tmem_base + (uint32_t)(ta * P.Ntot);
+                        umma_bf16_lohi(d, a_lo, s_hi, b_lo, l_hi, idesc_all, accum);
+                        for (int ks = 1; ks < P.nksteps; ++ks) {
+                            a_lo += 16u;
+                            b_lo += 16u;
+                            umma_bf16_lohi(d, a_lo, s_hi, b_lo, l_hi, idesc_all, 1);
+                        }
+                    }
+                    tc::umma_commit(tc::smem_u32(&a_empty[sa]));
+                    accum = 1;
+                    ++acnt;
+                    continue;
+                }
                 for (int gi = 0; gi < ng; ++gi) {
                     const int g = g0 + gi, kh = g / P.nt, b = g - kh * P.nt;      // space-to-depth source: kh is the row tap a
                     const uint32_t boff = P.s2d_cq ? (uint32_t)(kh * P.BX + b) * 16u
@@ -1064,6 +1091,9 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
     P.n_mhalf = (P.Csp + 127) / 128;
     P.nS = std::min(16, P.Csp / 8);
     P.NG = P.s2d_cq ? nt * nt : k * nt;
+    P.rep = (P.s2d_cq && nt * P.N <= 256 && nt * nt * P.N <= 512 && !g_dbg[3]) ? 1 : 0;
+    P.Ntot = nt * P.N;
+    if (P.rep) P.nL = nt * P.cpl;
     P.gpp = std::min(P.NG, 512 / P.N);
     P.n_cpass = (P.NG + P.gpp - 1) / P.gpp;
     P.gpp = (P.NG + P.n_cpass - 1) / P.n_cpass;
@@ -1454,9 +1484,9 @@ extern "C" int mrssm_pl_describe(const mrssm_pl_conv_args* a, int32_t op, char* 
         if (int rc = plan_wgrad(a, P, smem, splits)) return rc;
         snprintf(buf, buflen,
                  "wgrad BI=%d bands=%d TH=%d BX=%d BY=%d nS=%d nL=%d PS_s=%d PS_l=%d stage=%d NA=%d ksteps/tile=%d N=%d groups=%d gpp=%d cpass=%d mhalf=%d "
-                 "splits=%d smem=%zu tiles=%d",
+                 "splits=%d smem=%zu tiles=%d rep=%d",
                  P.BI, P.n_bands, P.TH, P.BX, P.BY, P.nS, P.nL, P.PS_s, P.PS_l, P.stage_bytes, P.NA, P.nksteps, P.N, P.NG, P.gpp, P.n_cpass,
-                 P.n_mhalf, splits, smem, P.n_groups * P.n_bands);
+                 P.n_mhalf, splits, smem, P.n_groups * P.n_bands, P.rep);
     } else {
         FwdP P;
         size_t smem;
