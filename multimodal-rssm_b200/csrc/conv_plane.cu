@@ -230,6 +230,7 @@ struct FwdP {
     int s2d;                    // down: the source is the space-to-depth (16-channel) form of a <= 4-channel image
     long long* prof;            // [CTA][16 tiles][8 slots] clock64 stamps or NULL
     TV out, mask;               // bf16 output / act'-mask views (indexed at the output pixel)
+    long long mask_img_bytes;   // > 0: the mask view stores every image as one dense block of this many bytes (L2 prefetch per tile)
     T4 out32;                   // fp32 output (F32 kernels)
     const float* bias;
     const float* scale_ptr;     // optional output scale: (*scale_ptr) * scale_mul
@@ -431,6 +432,19 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                 mbar_expect_tx(bar, (uint32_t)P.planes * (uint32_t)P.plane_bytes);
                 const int ig = tile / P.n_bands, band = tile - ig * P.n_bands;
                 const uint32_t dst = smemA + (uint32_t)sa * (uint32_t)P.a_stage_bytes;
+                if (P.mask_img_bytes > 0 && band == 0) {
+                    // the epilogue of this tile multiplies by act'(forward activation) read straight from HBM, 16 bytes per lane with
+                    // the miss latency exposed: pull the tile's images of the mask into L2 now, a tile ahead of their use
+                    const int i0 = ig * P.BI, ni = min(P.BI, P.n_img - i0);
+                    const char* mp = (const char*)P.mask.p + (long long)i0 * P.mask_img_bytes;
+                    long long left = (long long)ni * P.mask_img_bytes;
+                    while (left > 0) {
+                        const uint32_t sz = (uint32_t)(left < 65536 ? left : 65536);
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(mp), "r"(sz) : "memory");
+                        mp += sz;
+                        left -= sz;
+                    }
+                }
                 for (int q = 0; q < P.planes; ++q) {
                     const int mi = q / P.ppm, ch = q - mi * P.ppm;
                     const CUtensorMap* m = mi == 0 ? &mA0 : (mi == 1 ? &mA1 : (mi == 2 ? &mA2 : &mA3));
@@ -796,6 +810,13 @@ int plan_fwd(const mrssm_pl_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
     P.n_valid = a->n_out_valid;
     const mrssm_tv& out = (op == OP_DOWN) ? a->small : a->large;
     P.out = cvt(out); P.mask = cvt(a->mask); P.out32 = cvt(a->out32);
+    P.mask_img_bytes = 0;
+    if (P.mask_mode && !g_dbg[2]) {
+        // dense per-image blocks: parity-planar = 4 parity planes of (Cp/8) chunk planes; planar = (Cp/8) chunk planes; NHWC = H*W*Cp
+        const mrssm_tv& mv = a->mask;
+        const long long img_bytes = 2 * mv.sI;
+        if (img_bytes > 0 && img_bytes % 16 == 0 && ((uintptr_t)mv.ptr & 15) == 0 && img_bytes <= (1 << 20)) P.mask_img_bytes = img_bytes;
+    }
     P.bias = a->bias;
     P.prof = g_prof;
     P.scale_ptr = a->scale_ptr; P.scale_mul = a->scale_mul;
