@@ -345,7 +345,7 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / args.steps, "last_loss": loss,
                 "input": "uint8 frames + fp32 vectors from pinned host memory, normalised on device, copy of step k+1 overlapped with step k"},
         "gpu_launches": launches,
-        "roofline": roof, "rollout_roofline": rollout_roof, "cpu_baseline": cpu,
+        "roofline": roof, "rollout_roofline": rollout_roof, "cpu_baseline": cpu, "kernel_order": list(agg.keys()),
         "top_kernels_ms": [{"kernel": k, "ms_per_step": round(m, 4), "launches": n} for k, m, n in top],
         "profiled_step_kernel_ms": total_ms,
     }
