@@ -272,7 +272,7 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 
 // bias + activation + act'-mask + store of 8 consecutive output channels of one pixel
 template <bool F32>
-__device__ __forceinline__ void epi_store8(const FwdP& P, const float* v, const float* bias_s, int cl0, long long o_off, long long m_off,
+__device__ __forceinline__ void epi_store8(const FwdP& P, const float* v, const float* bias_s, int cl0, long long o_off, const uint4 mk,
                                            float oscale) {
     const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cl0), b1 = *reinterpret_cast<const float4*>(bias_s + cl0 + 4);
     float x[8] = {v[0] + b0.x, v[1] + b0.y, v[2] + b0.z, v[3] + b0.w, v[4] + b1.x, v[5] + b1.y, v[6] + b1.z, v[7] + b1.w};
@@ -284,7 +284,6 @@ __device__ __forceinline__ void epi_store8(const FwdP& P, const float* v, const 
         for (int e = 0; e < 8; ++e) x[e] = x[e] > 0.f ? x[e] : expm1f(x[e]);
     }
     if (P.mask_mode) {
-        const uint4 mk = __ldg(reinterpret_cast<const uint4*>((const bf16*)P.mask.p + m_off + (cl0 >> 3) * P.mask.sK));
         const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mk);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -640,10 +639,34 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                     int cur_cls = -1;                 // up: pixel offsets are recomputed only when the parity class changes
                     bool ok_c = row_ok;
                     long long o_pix = o_base, m_pix = m_base;
+                    // act'-mask vectors: when the item stays inside one parity class (always, for the masked layers) they are loaded
+                    // one 16-column iteration ahead of their use (an L2 hit is still ~400 cycles)
+                    const bool m_ahead = P.mask_mode && (OP == OP_DOWN || cl0 + ncols <= P.Cop);
+                    const bf16* m_ptr = nullptr;
+                    uint4 mk0 = make_uint4(0u, 0u, 0u, 0u), mk1 = mk0;
+                    if (m_ahead) {
+                        bool ok_m = row_ok;
+                        long long mp = m_base;
+                        if (OP == OP_UP) {
+                            const int yy = 2 * y + (cls >> 1), xx = 2 * x + (cls & 1);
+                            ok_m = row_ok && yy < P.Ho && xx < P.Wo;
+                            if (ok_m) mp = tv_pix(P.mask, img, yy, xx);
+                        }
+                        if (ok_m) {
+                            m_ptr = (const bf16*)P.mask.p + mp + (cl0 >> 3) * P.mask.sK;
+                            mk0 = __ldg(reinterpret_cast<const uint4*>(m_ptr));
+                            if (ncols > 8) mk1 = __ldg(reinterpret_cast<const uint4*>(m_ptr + P.mask.sK));
+                        }
+                    }
 #pragma unroll 1
                     for (int c0 = 0; c0 < ncols; c0 += 16) {
                         float v[16];
                         tmem_ld16_nowait(taddr + c0, v);
+                        uint4 mc[2] = {mk0, mk1};
+                        if (m_ahead && m_ptr && c0 + 16 < ncols) {
+                            mk0 = __ldg(reinterpret_cast<const uint4*>(m_ptr + (long long)((c0 + 16) >> 3) * P.mask.sK));
+                            mk1 = __ldg(reinterpret_cast<const uint4*>(m_ptr + (long long)((c0 + 24) >> 3) * P.mask.sK));
+                        }
                         tmem_wait_ld();
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
@@ -653,10 +676,13 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                                 ok_c = row_ok && yy < P.Ho && xx < P.Wo;
                                 if (ok_c) {
                                     o_pix = F32 ? img * P.out32.sI + yy * P.out32.sH + xx * P.out32.sW : tv_pix(P.out, img, yy, xx);
-                                    if (P.mask_mode) m_pix = tv_pix(P.mask, img, yy, xx);
+                                    if (P.mask_mode && !m_ahead) m_pix = tv_pix(P.mask, img, yy, xx);
                                 }
                             }
-                            if (ok_c) epi_store8<F32>(P, v + 8 * h, bias_s, cl0, o_pix, m_pix, oscale);
+                            if (ok_c) {
+                                if (P.mask_mode && !m_ahead) mc[h] = __ldg(reinterpret_cast<const uint4*>((const bf16*)P.mask.p + m_pix + (cl0 >> 3) * P.mask.sK));
+                                epi_store8<F32>(P, v + 8 * h, bias_s, cl0, o_pix, mc[h], oscale);
+                            }
                             cl0 += 8;
                             if (OP == OP_UP && cl0 == P.Cop) {
                                 cl0 = 0;
