@@ -11,7 +11,11 @@
 //       both operands MN-major (a smem row is one pixel = one contraction index), split-K over pixel
 //       ranges, fp32 atomics straight into the PyTorch-layout gradient.
 #include <algorithm>
+#include <cuda.h>
+#include <string.h>
 #include "tc_common.cuh"
+
+int mrssm_tma_map_2d_sw128(void* map, const void* base, long long inner, long long outer, long long row_bytes, int box_inner, int box_outer);
 
 namespace {
 
@@ -236,9 +240,21 @@ struct WgK {
     T4 small, large;
     float* dw;
     long long w_ss, w_sl;
+    int tma;                    // dense case (1x1 small map, taps contiguous in the large row): both operands arrive by TMA (128B swizzle)
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1) conv_tc_wgrad_kernel(WgK a) {
+__device__ __forceinline__ void wg_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void wg_tma_2d(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant__ CUtensorMap mL, const WgK a) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[4], bar_empty[4], bar_accum;
     __shared__ uint32_t tmem_base_s;
@@ -256,7 +272,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_wgrad_kernel(WgK a) {
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            tc::mbar_init(tc::smem_u32(&bar_full[s]), NLOAD);
+            tc::mbar_init(tc::smem_u32(&bar_full[s]), a.tma ? 1 : NLOAD);
             tc::mbar_init(tc::smem_u32(&bar_empty[s]), 1);
         }
         tc::mbar_init(tc::smem_u32(&bar_accum), 1);
@@ -274,6 +290,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_wgrad_kernel(WgK a) {
         // thread -> (pixel row r of the 64-pixel block, quarter q): r = tid & 63, q = tid >> 6 (0..3)
         const int r = tid & 63, q = tid >> 6;
         const int nslabB = a.BN / 64;
+        if (a.tma) {
+            // dense layers: a K block is 64 whole rows of both matrices; one thread issues 2 + BN/64 TMA boxes of [64 rows][128 B]
+            // (rows past the end and feature columns past the padded width are zero-filled by the TMA unit)
+            if (tid == 0) {
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int s = kb % S;
+                    if (kb >= S) tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ((kb / S) - 1) & 1);
+                    const uint32_t sA = smem0 + s * stage_bytes, sB = sA + a_bytes;
+                    const uint32_t bar = tc::smem_u32(&bar_full[s]);
+                    const int row = (int)(p_begin + (long long)kb * BK);
+                    wg_expect_tx(bar, stage_bytes);
+                    wg_tma_2d(sA, &mS, m0, row, bar);
+                    wg_tma_2d(sA + 8192, &mS, m0 + 64, row, bar);
+                    for (int i = 0; i < nslabB; ++i) wg_tma_2d(sB + i * 8192, &mL, n0 + 64 * i, row, bar);
+                }
+            }
+        } else
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % S;
             if (kb >= S) tc::mbar_wait(tc::smem_u32(&bar_empty[s]), ((kb / S) - 1) & 1);
@@ -311,14 +344,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_wgrad_kernel(WgK a) {
                 tc::mbar_arrive(tc::smem_u32(&bar_full[(kb - LAG) % S]));
             }
         }
-        if (nkb >= 2) {
-            tc::cp_async_wait<1>();
+        if (!a.tma) {
+            if (nkb >= 2) {
+                tc::cp_async_wait<1>();
+                tc::fence_proxy_async();
+                tc::mbar_arrive(tc::smem_u32(&bar_full[(nkb - 2) % S]));
+            }
+            tc::cp_async_wait<0>();
             tc::fence_proxy_async();
-            tc::mbar_arrive(tc::smem_u32(&bar_full[(nkb - 2) % S]));
+            tc::mbar_arrive(tc::smem_u32(&bar_full[(nkb - 1) % S]));
         }
-        tc::cp_async_wait<0>();
-        tc::fence_proxy_async();
-        tc::mbar_arrive(tc::smem_u32(&bar_full[(nkb - 1) % S]));
 
         if (warp < 4) {
             tc::mbar_wait(tc::smem_u32(&bar_accum), 0);
@@ -576,8 +611,21 @@ extern "C" int mrssm_tc_conv_wgrad(const mrssm_tc_conv_args* a, void* stream) {
     k.tmem_cols = pow2_cols(k.BN);
     size_t smem = (size_t)k.stages * stage + 1024;
     dim3 grid((unsigned)ceil_div64(k.Cs, BM), (unsigned)ceil_div64(k.Ncols, k.BN), (unsigned)splits);
+    CUtensorMap mS, mL;
+    memset(&mS, 0, sizeof(mS));
+    memset(&mL, 0, sizeof(mL));
+    k.tma = 0;
+    const bool dense = a->Hs == 1 && a->Ws == 1 && a->Hl == a->ksz && a->Wl == a->ksz &&
+                       (a->ksz == 1 || (a->large.sW == k.Cl && a->large.sH == (long long)a->ksz * k.Cl)) && a->small.sI % 8 == 0 &&
+                       a->large.sI % 8 == 0 && ((uintptr_t)a->small.ptr & 15) == 0 && ((uintptr_t)a->large.ptr & 15) == 0 &&
+                       a->small.sI >= k.Cs && a->large.sI >= k.Ncols && a->n_img >= 64;
+    if (dense) {
+        if (int rc = mrssm_tma_map_2d_sw128(&mS, a->small.ptr, k.Cs, a->n_img, a->small.sI * 2, 64, 64)) return rc;
+        if (int rc = mrssm_tma_map_2d_sw128(&mL, a->large.ptr, k.Ncols, a->n_img, a->large.sI * 2, 64, 64)) return rc;
+        k.tma = 1;
+    }
     MRSSM_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_tc_wgrad_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(k);
+    conv_tc_wgrad_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(mS, mL, k);
     MRSSM_LAUNCH_CHECK();
     return 0;
 }
