@@ -231,6 +231,7 @@ struct FwdP {
     long long* prof;            // [CTA][16 tiles][8 slots] clock64 stamps or NULL
     TV out, mask;               // bf16 output / act'-mask views (indexed at the output pixel)
     long long mask_img_bytes;   // > 0: the mask view stores every image as one dense block of this many bytes (L2 prefetch per tile)
+    long long tgt_img_bytes;    // > 0: same for the fp32 target images of the fused reconstruction loss
     T4 out32;                   // fp32 output (F32 kernels)
     const float* bias;
     const float* scale_ptr;     // optional output scale: (*scale_ptr) * scale_mul
@@ -431,12 +432,13 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                 mbar_expect_tx(bar, (uint32_t)P.planes * (uint32_t)P.plane_bytes);
                 const int ig = tile / P.n_bands, band = tile - ig * P.n_bands;
                 const uint32_t dst = smemA + (uint32_t)sa * (uint32_t)P.a_stage_bytes;
-                if (P.mask_img_bytes > 0 && band == 0) {
-                    // the epilogue of this tile multiplies by act'(forward activation) read straight from HBM, 16 bytes per lane with
-                    // the miss latency exposed: pull the tile's images of the mask into L2 now, a tile ahead of their use
+                if ((P.mask_img_bytes > 0 || P.tgt_img_bytes > 0) && band == 0) {
+                    // the epilogue of this tile reads the act'-mask (forward activation) / the loss target straight from HBM, a few
+                    // bytes per lane with the miss latency exposed: pull the tile's images into L2 now, a tile ahead of their use
                     const int i0 = ig * P.BI, ni = min(P.BI, P.n_img - i0);
-                    const char* mp = (const char*)P.mask.p + (long long)i0 * P.mask_img_bytes;
-                    long long left = (long long)ni * P.mask_img_bytes;
+                    const long long ib = P.mask_img_bytes > 0 ? P.mask_img_bytes : P.tgt_img_bytes;
+                    const char* mp = (P.mask_img_bytes > 0 ? (const char*)P.mask.p : (const char*)P.mse_target) + (long long)i0 * ib;
+                    long long left = (long long)ni * ib;
                     while (left > 0) {
                         const uint32_t sz = (uint32_t)(left < 65536 ? left : 65536);
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(mp), "r"(sz) : "memory");
@@ -853,6 +855,8 @@ int plan_fwd(const mrssm_pl_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
         P.out = cvt(a->large);
         P.mse_vec = a->out32.sW == 1 && (P.Wo & 1) == 0 && a->out32.sH % 2 == 0 && a->out32.sC % 2 == 0 && a->out32.sI % 2 == 0 &&
                     ((uintptr_t)a->mse_target & 7) == 0;
+        const long long tb = 4 * a->out32.sI;
+        P.tgt_img_bytes = (!g_dbg[2] && tb > 0 && tb % 16 == 0 && ((uintptr_t)a->mse_target & 15) == 0 && tb <= (1 << 20)) ? tb : 0;
     }
     auto vec_ok = [](const mrssm_tv& t) {
         return t.sW % 8 == 0 && t.sH % 8 == 0 && t.sI % 8 == 0 && t.sK % 8 == 0 && t.sP % 8 == 0 && ((uintptr_t)t.ptr & 15) == 0;
