@@ -232,6 +232,7 @@ struct FwdP {
     TV out, mask;               // bf16 output / act'-mask views (indexed at the output pixel)
     long long mask_img_bytes;   // > 0: the mask view stores every image as one dense block of this many bytes (L2 prefetch per tile)
     long long tgt_img_bytes;    // > 0: same for the fp32 target images of the fused reconstruction loss
+    uint32_t ks_off16[320];     // (plane*PS + shift*16) >> 4 per K-step: read by the MMA issuer from the constant bank (uniform regs)
     T4 out32;                   // fp32 output (F32 kernels)
     const float* bias;
     const float* scale_ptr;     // optional output scale: (*scale_ptr) * scale_mul
@@ -370,12 +371,11 @@ __device__ __forceinline__ void mse_row(const FwdP& P, const float (&v)[32], con
 template <int OP, bool F32>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUtensorMap mA2,
-                 const __grid_constant__ CUtensorMap mA3, const __grid_constant__ CUtensorMap mB, const FwdP P) {
+                 const __grid_constant__ CUtensorMap mA3, const __grid_constant__ CUtensorMap mB, const __grid_constant__ FwdP P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2];
     __shared__ uint64_t b_full[80], b_empty[8];
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(16) uint32_t ks_off16[320];      // (plane*PS + shift*16) >> 4 per K-step
     __shared__ __align__(16) float bias_s[1024];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -384,25 +384,6 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     const uint32_t smemA = smem0 + (uint32_t)P.NB * b_stage;
     const int n_tiles = P.n_groups * P.n_bands;
 
-    for (int ks = tid; ks < 320; ks += FWD_THREADS) {
-        uint32_t off = 0;
-        if (ks < P.n_ksteps) {
-            int j = ks % P.J, t = ks / P.J, b = t % P.nt, r = t / P.nt;
-            int plane, shift;
-            if (OP == OP_DOWN && P.s2d) {  // r = a: all four input parities are channels of the same pixel
-                plane = 2 * j;
-                shift = r * P.BX + b;
-            } else if (OP == OP_DOWN) {    // r = kh
-                plane = (r & 1) * 2 * P.J + 2 * j;
-                shift = (r >> 1) * P.BX + b;
-            } else {                       // r = a
-                plane = 2 * j;
-                shift = (P.nt - 1 - r) * P.BX + (P.nt - 1 - b);
-            }
-            off = ((uint32_t)plane * (uint32_t)P.PS + (uint32_t)shift * 16u) >> 4;
-        }
-        ks_off16[ks] = off;
-    }
     for (int c = tid; c < 1024; c += FWD_THREADS) bias_s[c] = (P.bias && c < P.n_valid) ? P.bias[c] : 0.f;
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -526,14 +507,14 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                         for (int mb = 0; mb < nmb; ++mb, a_row += 128u, d += BN) {
                             uint32_t b_lo = b_base;
                             for (int kb = 0; kb < nfull; ++kb, b_lo += b_step) {
-                                const uint4 ko = *reinterpret_cast<const uint4*>(&ks_off16[kb * 4]);
+                                const uint4 ko = make_uint4(P.ks_off16[kb * 4], P.ks_off16[kb * 4 + 1], P.ks_off16[kb * 4 + 2], P.ks_off16[kb * 4 + 3]);
                                 umma_bf16_lohi(d, a_row + ko.x, a_hi, b_lo, b_hi, idesc, kb != 0);
                                 umma_bf16_lohi(d, a_row + ko.y, a_hi, b_lo + 2, b_hi, idesc, 1);
                                 umma_bf16_lohi(d, a_row + ko.z, a_hi, b_lo + 4, b_hi, idesc, 1);
                                 umma_bf16_lohi(d, a_row + ko.w, a_hi, b_lo + 6, b_hi, idesc, 1);
                             }
                             if (ntail) {
-                                const uint4 ko = *reinterpret_cast<const uint4*>(&ks_off16[nfull * 4]);
+                                const uint4 ko = make_uint4(P.ks_off16[nfull * 4], P.ks_off16[nfull * 4 + 1], P.ks_off16[nfull * 4 + 2], P.ks_off16[nfull * 4 + 3]);
                                 umma_bf16_lohi(d, a_row + ko.x, a_hi, b_lo, b_hi, idesc, nfull != 0);
                                 if (ntail > 1) umma_bf16_lohi(d, a_row + ko.y, a_hi, b_lo + 2, b_hi, idesc, 1);
                                 if (ntail > 2) umma_bf16_lohi(d, a_row + ko.z, a_hi, b_lo + 4, b_hi, idesc, 1);
@@ -545,7 +526,7 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                             tc::mbar_wait(tc::smem_u32(&b_full[sb]), (bcnt / P.NB) & 1);
                             tc::tc_fence_after();
                             const uint32_t b_lo = (((smem0 + (uint32_t)sb * b_stage) >> 4) & 0x3FFFu) | (1u << 16);
-                            const uint4 ko = *reinterpret_cast<const uint4*>(&ks_off16[kb * 4]);
+                            const uint4 ko = make_uint4(P.ks_off16[kb * 4], P.ks_off16[kb * 4 + 1], P.ks_off16[kb * 4 + 2], P.ks_off16[kb * 4 + 3]);
                             const int nk = min(4, P.n_ksteps - kb * 4);
                             uint32_t a_row = a_pass, d = tacc;
                             if (nk == 4) {
@@ -890,6 +871,26 @@ int launch_fwd(const mrssm_pl_conv_args* a, int op, cudaStream_t st) {
     const long long K_total = (long long)P.nkb * 64;
     const long long N_total = (long long)P.BN * P.n_ntiles;
     if (int rc = make_w_map(&mB, a->wpacked, K_total, N_total, P.BN)) return rc;
+    // K-step table: which chunk plane and which pixel shift every K step (tap, 16-channel slab) reads
+    for (int ks = 0; ks < 320; ++ks) {
+        uint32_t off = 0;
+        if (ks < P.n_ksteps) {
+            const int j = ks % P.J, t = ks / P.J, b = t % P.nt, r = t / P.nt;
+            int plane, shift;
+            if (op == OP_DOWN && P.s2d) {   // r = a: all four input parities are channels of the same pixel
+                plane = 2 * j;
+                shift = r * P.BX + b;
+            } else if (op == OP_DOWN) {     // r = kh
+                plane = (r & 1) * 2 * P.J + 2 * j;
+                shift = (r >> 1) * P.BX + b;
+            } else {                        // r = a
+                plane = 2 * j;
+                shift = (P.nt - 1 - r) * P.BX + (P.nt - 1 - b);
+            }
+            off = ((uint32_t)plane * (uint32_t)P.PS + (uint32_t)shift * 16u) >> 4;
+        }
+        P.ks_off16[ks] = off;
+    }
     const int n_tiles = P.n_groups * P.n_bands;
     int grid = std::min(n_tiles, 148);
     smem = std::max<size_t>(smem, 120 * 1024);       // > half an SM: one CTA per SM (each allocates all 512 TMEM columns)
