@@ -812,6 +812,8 @@ int plan_fwd(const mrssm_pl_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
     P.plane_bytes = P.BI * P.BY * P.BX * 16;
     P.n_groups = (a->n_img + P.BI - 1) / P.BI;
     P.n_passes = (P.MB_total + P.MBs - 1) / P.MBs;
+    // equal passes: the two TMEM sets ping-pong between passes, so an 8 + 1 split would serialise the big pass's MMAs with its own epilogue
+    P.MBs = (P.MB_total + P.n_passes - 1) / P.n_passes;
     smem_bytes = (size_t)bring + (size_t)P.NA * P.a_stage_bytes + 1024;
     MRSSM_CHECK(smem_bytes <= (size_t)SMEM_TOTAL + 1024, "plane conv: shared memory plan %zu too large", smem_bytes);
     // epilogue
