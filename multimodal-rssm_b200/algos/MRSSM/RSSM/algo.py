@@ -45,6 +45,8 @@ class RSSM(RSSM_base):
         init_belief = torch.zeros(batch_size, r.belief_size, device=self.cfg.main.device)
         init_state = torch.zeros(batch_size, r.state_size, device=self.cfg.main.device)
         obs_emb = bottle_tupele(self.encoder, observations)
+        if self.dp is not None:
+            self.dp.watch("transition", [obs_emb])
         out = self.transition_model(init_state, actions, init_belief, obs_emb, nonterminals, det=det)
         keys = ("beliefs", "prior_states", "prior_means", "prior_std_devs", "posterior_states", "posterior_means",
                 "posterior_std_devs", "expert_means", "expert_std_devs")

@@ -132,6 +132,8 @@ class RSSM_base(nn.Module):
 
     def _calc_loss(self, observations_target, actions, rewards, nonterminals, states):
         z, _, _, kl_loss, kl_global = self._latent_terms(states)
+        if self.dp is not None:        # decoder gradients are complete once the gradient of the decoders' input latent exists
+            self.dp.watch("decoder", [z, states["beliefs"]])
         observations_loss = self._calc_observations_loss(observations_target, states["beliefs"], z)
         kl_loss_sum = kl_loss
         if self.cfg.rssm.global_kl_beta != 0:
@@ -245,6 +247,8 @@ class MRSSM_base(RSSM_base):
         init_belief = torch.zeros(batch_size, r.belief_size, device=self.cfg.main.device)
         init_state = torch.zeros(batch_size, r.state_size, device=self.cfg.main.device)
         obs_emb = bottle_tupele_multimodal(self.encoder, observations)
+        if self.dp is not None:        # transition gradients are complete once the gradient of the embeddings exists
+            self.dp.watch("transition", list(obs_emb.values()))
         out = self.transition_model(init_state, actions, init_belief, obs_emb, nonterminals, det=det)
         keys = ("beliefs", "prior_states", "prior_means", "prior_std_devs", "posterior_states", "posterior_means",
                 "posterior_std_devs", "expert_means", "expert_std_devs")

@@ -1,6 +1,7 @@
 """Data parallelism over sequence batches: one process per GPU, torch.distributed
 (NCCL over NVLink) for the single exchange step of the path — a SUM all-reduce of the flat gradient
-buffer; the 1/world average is folded into the fused clip+Adam kernel (``grad_scale``).
+buffer, issued bucket by bucket under backward; the 1/world average is folded into the fused clip+Adam kernel
+(``grad_scale``).
 
 Every (b) is independent through encoders, rollout, decoders and the per-(t,b) free-nats clamp, so with
 equal per-rank batches mean(rank gradients) == global-batch gradient exactly.  The reference has no
@@ -13,7 +14,17 @@ import torch.distributed as dist
 
 
 class DataParallel:
-    def __init__(self, model, bucket_bytes=None):
+    """Gradient exchange of the data-parallel train step, overlapped with backward.
+
+    The flat gradient buffer is cut into buckets that follow the order in which backward completes them — decoders first,
+    then the transition model (the rollout's BPTT and its deferred weight-gradient GEMMs), then the encoders and whatever is
+    left (reward head, alignment padding).  ``watch(bucket, tensors)`` hangs an autograd hook on a tensor whose gradient is
+    produced right after the bucket's last weight-gradient kernel was enqueued (the decoders' input latent, the encoders'
+    output embedding); the hook issues an asynchronous SUM all-reduce of that slice (NCCL orders it after the kernels already
+    on the compute stream and runs it on its own stream, under the rest of backward).  ``all_reduce_grads`` launches what is
+    left and makes the compute stream wait for all of it before the fused clip + Adam step."""
+
+    def __init__(self, model, overlap=True):
         assert dist.is_initialized()
         self.world = dist.get_world_size()
         self.model = model
@@ -21,11 +32,73 @@ class DataParallel:
         opt.grad_scale = 1.0 / self.world
         # identical weights everywhere: broadcast rank 0's flat parameter buffer once
         dist.broadcast(opt.flat_p, src=0)
+        self._buckets = self._plan_buckets(model, opt) if overlap else None
+        self._pending, self._launched = [], []
         model.dp = self
 
+    @staticmethod
+    def _plan_buckets(model, opt):
+        """{name: (lo, hi)} element ranges of flat_g, or None when the model does not expose the reference's module objects."""
+        total = opt.flat_g.numel()
+        base = opt.flat_g.data_ptr()
+        getters = (("decoder", lambda: model.observation_model.get_model_params()),
+                   ("transition", lambda: model.transition_model.get_model_params()),
+                   ("encoder", lambda: model.encoder.get_model_params()))
+        ranges = {}
+        try:
+            for name, get in getters:
+                ps = [p for p in get() if p.grad is not None]
+                if not ps:
+                    return None
+                lo = min((p.grad.data_ptr() - base) // 4 for p in ps)
+                hi = max((p.grad.data_ptr() - base) // 4 + p.numel() for p in ps)
+                if lo < 0 or hi > total:
+                    return None
+                ranges[name] = (int(lo), int(hi))
+        except AttributeError:
+            return None
+        spans = sorted(ranges.values())
+        if any(a[1] > b[0] for a, b in zip(spans, spans[1:])):
+            return None                                   # interleaved modules: one all-reduce at the end
+        return ranges
+
+    def watch(self, name, tensors):
+        """Launch bucket ``name`` as soon as the gradient of (the first differentiable one of) ``tensors`` is computed."""
+        if self.world == 1 or self._buckets is None or name not in self._buckets:
+            return
+        for t in tensors:
+            if isinstance(t, torch.Tensor) and t.requires_grad:
+                def hook(grad, name=name):
+                    self._launch(name)
+                    return None
+                t.register_hook(hook)
+                return
+
+    def _launch(self, name):
+        if name in self._launched:
+            return
+        lo, hi = self._buckets[name]
+        self._launched.append(name)
+        self._pending.append(dist.all_reduce(self.model.model_optimizer.flat_g[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+
     def all_reduce_grads(self, opt):
-        if self.world > 1:
+        if self.world == 1:
+            return
+        if self._buckets is None:
             dist.all_reduce(opt.flat_g, op=dist.ReduceOp.SUM)
+            return
+        for name in self._buckets:
+            self._launch(name)
+        # the gaps between the buckets (reward head, padding)
+        pos = 0
+        for lo, hi in sorted(self._buckets.values()) + [(opt.flat_g.numel(), opt.flat_g.numel())]:
+            if lo > pos:
+                self._pending.append(dist.all_reduce(opt.flat_g[pos:lo], op=dist.ReduceOp.SUM, async_op=True))
+            pos = max(pos, hi)
+        for w in self._pending:
+            w.wait()
+        self.last_order = list(self._launched)          # for tests / logging
+        self._pending, self._launched = [], []
 
 
 def init_from_env(backend=None):

@@ -92,3 +92,99 @@ def test_mean_of_rank_gradients_is_global_batch_gradient():
     for k in g_all:
         scale = float(g_all[k].abs().max()) + 1e-12
         assert float((0.5 * (g_a[k] + g_b[k]) - g_all[k]).abs().max()) <= 1e-4 * scale + 1e-7, k
+
+
+class _Mod:
+    def __init__(self, params):
+        self._p = params
+
+    def get_model_params(self):
+        return self._p
+
+
+def _bucket_worker(rank, world, port, q):
+    for p in (ROOT, os.path.join(ROOT, "multimodal-rssm_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from mrssm_b200.dist import DataParallel, init_from_env
+    init_from_env(backend="gloo")
+    # a flat gradient buffer laid out like FusedClipAdam's: transition | decoder | reward (no bucket) | encoder, with padding
+    sizes = dict(transition=37, decoder=53, reward=11, encoder=29)
+    total = sum((n + 3) // 4 * 4 for n in sizes.values())
+    opt = _Opt(total, rank)
+    opt.flat_g.zero_()
+    params, off = {}, 0
+    g = torch.Generator().manual_seed(5)                                    # same weights on every rank
+    for name, n in sizes.items():
+        p = torch.nn.Parameter(torch.randn(n, generator=g))
+        p.grad = opt.flat_g[off:off + n]
+        params[name] = p
+        off += (n + 3) // 4 * 4
+    model = _Model(opt)
+    model.observation_model = _Mod([params["decoder"]])
+    model.transition_model = _Mod([params["transition"]])
+    model.encoder = _Mod([params["encoder"]])
+    dp = DataParallel(model)
+    assert dp._buckets is not None and set(dp._buckets) == {"decoder", "transition", "encoder"}
+    # forward: x -> encoder -> emb -> transition -> z -> decoder -> loss (rank-dependent data); reward head gets a gradient too.
+    # Like the product's autograd Functions, a layer writes its weight gradient into p.grad INSIDE backward and returns None for
+    # the parameter, so the gradient exists before the hook of the layer's input fires.
+    class Lin(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, p, n_out):
+            ctx.save_for_backward(x)
+            ctx.p = p
+            return (x * p.detach()).sum() * torch.ones(n_out)
+
+        @staticmethod
+        def backward(ctx, g):
+            (x,) = ctx.saved_tensors
+            ctx.p.grad += g.sum() * x
+            return g.sum() * ctx.p.detach(), None, None
+
+    def run(dp_):
+        opt.flat_g.zero_()
+        x = torch.full((29,), float(rank + 1), requires_grad=True)
+        emb = Lin.apply(x, params["encoder"], 37)
+        if dp_ is not None:
+            dp_.watch("transition", [emb])
+        z = Lin.apply(emb, params["transition"], 53)
+        if dp_ is not None:
+            dp_.watch("decoder", [z])
+        loss = Lin.apply(z, params["decoder"], 1).sum()
+        loss.backward()
+        params["reward"].grad += float(rank + 1)
+
+    run(None)
+    local = opt.flat_g.clone()                          # this rank's gradient, no exchange
+    order = []
+    orig = dp._launch
+    dp._launch = lambda name: (order.append(name), orig(name))[1]
+    run(dp)
+    launched_in_backward = list(order)
+    dp.all_reduce_grads(opt)
+    q.put((rank, local, opt.flat_g.clone(), launched_in_backward, dp.last_order))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_launches_under_backward_gloo():
+    """Buckets are exchanged in the order backward completes them (decoder, transition from hooks; encoder and the
+    un-bucketed remainder at the end) and the result equals one SUM all-reduce of the whole buffer."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, l0, s0, in_bwd0, ord0), (_, l1, s1, in_bwd1, ord1) = out
+    assert in_bwd0 == in_bwd1 == ["decoder", "transition"]          # launched by the hooks, before backward returned
+    assert ord0 == ["decoder", "transition", "encoder"]
+    # note: the hook of a bucket fires after that bucket's gradients were written, so the early launch sums final values
+    torch.testing.assert_close(s0, s1)
+    torch.testing.assert_close(s0, l0 + l1)
