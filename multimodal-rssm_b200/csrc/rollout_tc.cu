@@ -986,11 +986,22 @@ void build_plan_bwd(int D, int S, int H, int A, int NH, PlanBuilder& pb, TcHeade
 }
 
 // the weight producer and the MMA issuer of one CTA (shared by both directions); `it` counts processed time steps
+// rows x width fp32 block of a time-major [T, B, width] tensor -> L2 (one bulk prefetch; skipped when not 16-byte addressable)
+__device__ __forceinline__ void prefetch_rows(const float* p, long long row0, int rows, int width) {
+    if (!p || rows <= 0) return;
+    const char* a = (const char*)(p + row0 * width);
+    const uint32_t bytes = (uint32_t)rows * (uint32_t)width * 4u;
+    if ((((uintptr_t)a) | bytes) & 15u) return;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(bytes) : "memory");
+}
+
+template <class OnStep>
 __device__ __forceinline__ void producer_role(const TcProg& prog, const uint8_t* __restrict__ packed, uint32_t ring, int NS, int n_steps,
-                                              uint64_t* full, uint64_t* empty) {
+                                              uint64_t* full, uint64_t* empty, OnStep on_step) {
     uint32_t slot = 0, phase = 0;
     const int n_tiles = prog.n_tiles;
     for (int it = 0; it < n_steps; ++it) {
+        on_step(it);
         uint32_t src = 0;
         for (int ti = 0; ti < n_tiles; ++ti) {
             wait_backoff(&empty[slot], phase ^ 1u);
@@ -1237,7 +1248,41 @@ rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp == PROD_WARP) {
-        if (lane == 0) producer_role(prog, packed, smem0 + BOFF_RING, NS, T, full, empty);
+        if (lane == 0) {
+            // The stash, the outputs and the upstream gradients were written a whole decoder pass ago (DRAM): while step `it`
+            // streams its weights, pull the blocks the epilogues of the NEXT step read (rows of this CTA are contiguous in every
+            // time-major tensor) into L2 with a few bulk prefetches.
+            const int rows = min(4 * RPG, B - b0);
+            auto prefetch_step = [&](int t, bool wide, bool narrow) {
+                if (t < 0) return;
+                const long long r0 = (long long)t * B + b0;
+                if (wide) {
+                    prefetch_rows(a.st_r, r0, rows, D); prefetch_rows(a.st_z, r0, rows, D); prefetch_rows(a.st_n, r0, rows, D);
+                    prefetch_rows(a.st_ghn, r0, rows, D); prefetch_rows(a.st_x, r0, rows, D); prefetch_rows(g.g_beliefs, r0, rows, D);
+                    if (t > 0) prefetch_rows(a.beliefs, r0 - B, rows, D);
+                    for (int h = 0; h < NH; ++h) prefetch_rows(P.st_u[h], r0, rows, H);
+                }
+                if (narrow) {
+                    prefetch_rows(g.g_prior_states, r0, rows, S); prefetch_rows(g.g_prior_means, r0, rows, S);
+                    prefetch_rows(g.g_prior_stds, r0, rows, S); prefetch_rows(a.prior_stds, r0, rows, S);
+                    prefetch_rows(a.eps_prior, r0, rows, S);
+                    if (E > 0) {
+                        prefetch_rows(g.g_post_states, r0, rows, S); prefetch_rows(g.g_post_means, r0, rows, S);
+                        prefetch_rows(g.g_post_stds, r0, rows, S); prefetch_rows(a.eps_post, r0, rows, S);
+                        prefetch_rows(a.post_stds, r0, rows, S); prefetch_rows(a.post_means, r0, rows, S);
+                        for (int e = 1; e < NH; ++e) {
+                            prefetch_rows(P.g_exp_means[e], r0, rows, S); prefetch_rows(P.g_exp_stds[e], r0, rows, S);
+                            prefetch_rows(P.exp_stds[e], r0, rows, S); prefetch_rows(P.exp_means[e], r0, rows, S);
+                        }
+                    }
+                }
+            };
+            producer_role(prog, packed, smem0 + BOFF_RING, NS, T, full, empty, [&](int it) {
+                const int t = T - 1 - it;
+                if (it == 0) prefetch_step(t, true, false);
+                prefetch_step(t - 1, true, true);
+            });
+        }
         __syncwarp();
     } else if (warp == MMA_WARP) {
         if (NHS > 0) {
