@@ -287,6 +287,15 @@ __device__ __forceinline__ void st_shared_f2(uint32_t addr, float a, float b) {
 }
 __device__ __forceinline__ void st_f2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 
+// rows x width fp32 block of a time-major [T, B, width] tensor -> L2 (one bulk prefetch; skipped when not 16-byte addressable)
+__device__ __forceinline__ void prefetch_rows(const float* p, long long row0, int rows, int width) {
+    if (!p || rows <= 0) return;
+    const char* a = (const char*)(p + row0 * width);
+    const uint32_t bytes = (uint32_t)rows * (uint32_t)width * 4u;
+    if ((((uintptr_t)a) | bytes) & 15u) return;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(bytes) : "memory");
+}
+
 // the epilogue warps signal "operand written / accumulator drained": one arrival per warp
 __device__ __forceinline__ void epi_signal(uint64_t* bar, int lane) {
     tc::tc_fence_before();
@@ -553,7 +562,17 @@ rollout_tc_fwd_kernel(const __grid_constant__ mrssm_rollout_args a, const __grid
         if (lane == 0) {
             int pi = 0;
             uint32_t slot = 0, phase = 0;
+            const int prows = min(4 * RPG, B - b0);
             for (int t = 0; t < T; ++t) {
+                // the next step's inputs of this CTA (hoisted embedding rows, noise) -> L2 while this step streams its weights
+                for (int tt = (t == 0 ? 0 : t + 1); tt <= t + 1 && tt < T; ++tt) {
+                    const long long r0 = (long long)tt * B + b0;
+                    for (int h = 0; h < NH; ++h) prefetch_rows(emb_pre_s[h], r0, prows, H);
+                    if (!a.det) {
+                        prefetch_rows(a.eps_prior, r0, prows, S);
+                        if (E > 0) prefetch_rows(a.eps_post, r0, prows, S);
+                    }
+                }
                 uint32_t src = 0;
                 for (int ti = 0; ti < n_tiles; ++ti) {
                     wait_backoff(&empty[slot], phase ^ 1u);
@@ -986,15 +1005,6 @@ void build_plan_bwd(int D, int S, int H, int A, int NH, PlanBuilder& pb, TcHeade
 }
 
 // the weight producer and the MMA issuer of one CTA (shared by both directions); `it` counts processed time steps
-// rows x width fp32 block of a time-major [T, B, width] tensor -> L2 (one bulk prefetch; skipped when not 16-byte addressable)
-__device__ __forceinline__ void prefetch_rows(const float* p, long long row0, int rows, int width) {
-    if (!p || rows <= 0) return;
-    const char* a = (const char*)(p + row0 * width);
-    const uint32_t bytes = (uint32_t)rows * (uint32_t)width * 4u;
-    if ((((uintptr_t)a) | bytes) & 15u) return;
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(bytes) : "memory");
-}
-
 template <class OnStep>
 __device__ __forceinline__ void producer_role(const TcProg& prog, const uint8_t* __restrict__ packed, uint32_t ring, int NS, int n_steps,
                                               uint64_t* full, uint64_t* empty, OnStep on_step) {
