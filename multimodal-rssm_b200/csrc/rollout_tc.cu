@@ -426,6 +426,12 @@ struct Issuer {
     }
 };
 constexpr uint32_t CH16 = CH_BYTES >> 4;
+// opaque identity: keeps the compiler from hoisting every (buffer base + chunk offset) sum of the unrolled program into
+// registers for the whole step (hundreds of bytes of spills in the issuing thread); the add is redone next to its MMA
+__device__ __forceinline__ uint32_t opaque(uint32_t v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
 
 template <int D, int S, int H, int A, int NH>
 __device__ __forceinline__ void static_step_fwd(Issuer& I, uint32_t xin16, uint32_t xu16, uint32_t hprev16, uint32_t hnew16) {
@@ -433,7 +439,7 @@ __device__ __forceinline__ void static_step_fwd(Issuer& I, uint32_t xin16, uint3
     constexpr int nkD = (D + 15) / 16, nkH = (H + 15) / 16, nkX = (S + A + 15) / 16, ND = (D + 15) / 16 * 16;
     I.unit_begin(EV_XIN);
 #pragma unroll
-    for (int k = 0; k < nkX; ++k) I.emit(xin16 + 2 * k * CH16, 0, ND, k != 0);
+    for (int k = 0; k < nkX; ++k) I.emit(opaque(xin16) + 2 * k * CH16, 0, ND, k != 0);
     I.unit_end(CM_X);
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
@@ -442,27 +448,27 @@ __device__ __forceinline__ void static_step_fwd(Issuer& I, uint32_t xin16, uint3
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
 #pragma unroll
-            for (int k = 0; k < nkD; ++k) I.emit(xu16 + 2 * k * CH16, g * ACC_STRIDE, N, k != 0);
+            for (int k = 0; k < nkD; ++k) I.emit(opaque(xu16) + 2 * k * CH16, g * ACC_STRIDE, N, k != 0);
 #pragma unroll
-            for (int k = 0; k < nkD; ++k) I.emit(hprev16 + 2 * k * CH16, g * ACC_STRIDE, N, 1);
+            for (int k = 0; k < nkD; ++k) I.emit(opaque(hprev16) + 2 * k * CH16, g * ACC_STRIDE, N, 1);
         }
 #pragma unroll
-        for (int k = 0; k < nkD; ++k) I.emit(xu16 + 2 * k * CH16, 2 * ACC_STRIDE, N, k != 0);
+        for (int k = 0; k < nkD; ++k) I.emit(opaque(xu16) + 2 * k * CH16, 2 * ACC_STRIDE, N, k != 0);
 #pragma unroll
-        for (int k = 0; k < nkD; ++k) I.emit(hprev16 + 2 * k * CH16, 3 * ACC_STRIDE, N, k != 0);
+        for (int k = 0; k < nkD; ++k) I.emit(opaque(hprev16) + 2 * k * CH16, 3 * ACC_STRIDE, N, k != 0);
         I.unit_end(hf ? CM_GB : CM_GA);
     }
     auto fc1 = [&](int hd, int hf, int wev) {
         const int nc = hf ? nH8 - cAH : cAH, N = (8 * nc + 15) / 16 * 16;
         I.unit_begin(wev);
 #pragma unroll
-        for (int k = 0; k < nkD; ++k) I.emit(hnew16 + 2 * k * CH16, hf * ACC_STRIDE, N, k != 0);
+        for (int k = 0; k < nkD; ++k) I.emit(opaque(hnew16) + 2 * k * CH16, hf * ACC_STRIDE, N, k != 0);
         I.unit_end(CM_F1 + 2 * hd + hf);
     };
     auto fc2 = [&](int hd) {
         I.unit_begin(EV_U0 + 2 * hd + 1);
 #pragma unroll
-        for (int k = 0; k < nkH; ++k) I.emit(xu16 + 2 * k * CH16, F2_COL + 64 * hd, 64, k != 0);
+        for (int k = 0; k < nkH; ++k) I.emit(opaque(xu16) + 2 * k * CH16, F2_COL + 64 * hd, 64, k != 0);
         I.unit_end(CM_F2 + hd);
     };
     fc1(0, 0, EV_HB);
@@ -479,10 +485,14 @@ __device__ __forceinline__ void static_step_fwd(Issuer& I, uint32_t xin16, uint3
 // Warp roles.  The MMA issuer is the highest warp id of its scheduler (the issue arbiter favours high warp ids).
 constexpr int PROD_WARP = 16, ALLOC_WARP = 17, MMA_WARP = 18;
 
-template <int NHS>      // 0: table-driven MMA issue (any eligible size); > 0: statically unrolled issue for D=H=200, S=30, A=3, NHS heads
+// NHS 0: table-driven MMA issue (any eligible size); > 0: statically unrolled issue for D=H=200, S=30, A=3, NHS heads.
+// TWO: 64 sequences per CTA (both rows of every 16x256b fragment carry a sequence) instead of 32 (row t/4 only) — a template
+// parameter so that the second row's registers and arithmetic do not exist in the 32-sequence kernels.
+template <int NHS, bool TWO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 rollout_tc_fwd_kernel(const __grid_constant__ mrssm_rollout_args a, const __grid_constant__ TcProg prog, const uint8_t* __restrict__ packed,
-                      const int NS, const int RPG, long long* __restrict__ prof) {
+                      const int NS, long long* __restrict__ prof) {
+    constexpr int RPG = TWO ? 16 : 8;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full[MAX_SLOTS], empty[MAX_SLOTS], ev[N_EV], cm[N_CM];
     __shared__ uint32_t tmem_base_s;
@@ -653,9 +663,9 @@ rollout_tc_fwd_kernel(const __grid_constant__ mrssm_rollout_args a, const __grid
         const int ew = warp, q = ew & 3, p = ew >> 2, etid = tid;
         const int r0 = 16 * q + (lane >> 2), r1 = r0 + 8, cj = 2 * (lane & 3);
         const int seq0 = b0 + q * RPG + (lane >> 2), seq1 = seq0 + 8;
-        const bool two = RPG == 16;                                       // the second fragment row (r1) carries a sequence
+        constexpr bool two = TWO;                                         // the second fragment row (r1) carries a sequence
         const bool ok0 = seq0 < B, ok1 = two && seq1 < B;
-        const int ne = two ? 4 : 2;
+        constexpr int ne = two ? 4 : 2;
         const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
         const uint32_t opnd0 = (uint32_t)(r0 * 16 + cj * 2), opnd1 = (uint32_t)(r1 * 16 + cj * 2);      // inside a bf16 chunk plane
         const uint32_t hf0 = smem0 + OFF_HF + (uint32_t)(r0 * 32 + cj * 4), hf1 = smem0 + OFF_HF + (uint32_t)(r1 * 32 + cj * 4);
@@ -1077,13 +1087,13 @@ __device__ __forceinline__ void static_step_bwd(Issuer& I, uint32_t base16) {
         const int nc = hf ? nH8 - cAH : cAH, N = (8 * nc + 15) / 16 * 16;
         I.unit_begin(wev);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) I.emit(base16 + (BCH_DO + 8 * hd + 2 * k) * CH16, hf * BCOL_SET, N, k != 0);
+        for (int k = 0; k < 4; ++k) I.emit(opaque(base16) + (BCH_DO + 8 * hd + 2 * k) * CH16, hf * BCOL_SET, N, k != 0);
         I.unit_end(CMB_GB0 + 2 * hd + hf);
     };
     auto gc = [&](int hd) {
         I.unit_begin(EVB_DU0 + 2 * hd + 1);
 #pragma unroll
-        for (int k = 0; k < nkH; ++k) I.emit(base16 + (BCH_DU + 2 * k) * CH16, BCOL_GH, ND, !(hd == 0 && k == 0));
+        for (int k = 0; k < nkH; ++k) I.emit(opaque(base16) + (BCH_DU + 2 * k) * CH16, BCOL_GH, ND, !(hd == 0 && k == 0));
         I.unit_end(CMB_GCH0 + hd);
     };
     gb(0, 0, EVB_DO);
@@ -1098,17 +1108,17 @@ __device__ __forceinline__ void static_step_bwd(Issuer& I, uint32_t base16) {
 #pragma unroll
     for (int g = 0; g < 3; ++g) {
 #pragma unroll
-        for (int k = 0; k < nkD; ++k) I.emit(base16 + ((g == 0 ? BCH_DR : (g == 1 ? BCH_DZ : BCH_DN)) + 2 * k) * CH16, BCOL_GX, ND, !(g == 0 && k == 0));
+        for (int k = 0; k < nkD; ++k) I.emit(opaque(base16) + ((g == 0 ? BCH_DR : (g == 1 ? BCH_DZ : BCH_DN)) + 2 * k) * CH16, BCOL_GX, ND, !(g == 0 && k == 0));
     }
 #pragma unroll
     for (int g = 0; g < 3; ++g) {
 #pragma unroll
-        for (int k = 0; k < nkD; ++k) I.emit(base16 + ((g == 0 ? BCH_DR : (g == 1 ? BCH_DZ : BCH_DNR)) + 2 * k) * CH16, BCOL_GHH, ND, !(g == 0 && k == 0));
+        for (int k = 0; k < nkD; ++k) I.emit(opaque(base16) + ((g == 0 ? BCH_DR : (g == 1 ? BCH_DZ : BCH_DNR)) + 2 * k) * CH16, BCOL_GHH, ND, !(g == 0 && k == 0));
     }
     I.unit_end(CMB_GE);
     I.unit_begin(EVB_DX);
 #pragma unroll
-    for (int k = 0; k < nkD; ++k) I.emit(base16 + (BCH_DX + 2 * k) * CH16, BCOL_XIN, 8 * XIN_CH, k != 0);
+    for (int k = 0; k < nkD; ++k) I.emit(opaque(base16) + (BCH_DX + 2 * k) * CH16, BCOL_XIN, 8 * XIN_CH, k != 0);
     I.unit_end(CMB_GF);
 }
 
@@ -1117,10 +1127,11 @@ struct BwdPtrs {          // per-head pointers the epilogue indexes dynamically 
     float *d_u[TC_MAX_HEADS], *d_o[TC_MAX_HEADS];
 };
 
-template <int NHS>
+template <int NHS, bool TWO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __grid_constant__ TcProg prog, const uint8_t* __restrict__ packed,
-                      const int NS, const int RPG, long long* __restrict__ prof) {
+                      const int NS, long long* __restrict__ prof) {
+    constexpr int RPG = TWO ? 16 : 8;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full[MAX_SLOTS], empty[MAX_SLOTS], ev[N_EV], cm[N_CM];
     __shared__ uint32_t tmem_base_s;
@@ -1163,7 +1174,7 @@ rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __
     const int q = warp & 3, p = warp >> 2;
     const int r0 = 16 * q + (lane >> 2), r1 = r0 + 8, cj = 2 * (lane & 3);
     const int seq0 = b0 + q * RPG + (lane >> 2);
-    const bool two = RPG == 16;
+    constexpr bool two = TWO;
     const bool ok0 = seq0 < B, ok1 = two && seq0 + 8 < B;
     const int act = a.act;
     const float min_std = a.min_std;
@@ -1315,6 +1326,8 @@ rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __
         const uint32_t cg0 = smem0 + BOFF_CG + (uint32_t)(r0 * 32 + cj * 4), cg1 = smem0 + BOFF_CG + (uint32_t)(r1 * 32 + cj * 4);
         int pi = 0;
 #define BSTAMP() do { if (prof && warp == 0 && lane == 0 && blockIdx.x == 0 && it == PROF_STEP && pi < PROF_SLOTS) prof[2 * PROF_SLOTS + pi++] = clock64(); } while (0)
+        int pj = 0;
+#define BDSTAMP() do { if (prof && warp == 0 && lane == 0 && blockIdx.x == 0 && it == PROF_STEP && pj < PROF_SLOTS) prof[3 * PROF_SLOTS + pj++] = clock64(); } while (0)
         for (int it = 0; it < T; ++it) {
             const int t = T - 1 - it;
             const uint32_t par = (uint32_t)(it & 1);
@@ -1390,12 +1403,14 @@ rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __
                 tc::tc_fence_after();
                 BSTAMP();
                 for (int c = p; c < nD8; c += 4) {
+                    BDSTAMP();
                     const GruIn in0 = nx0, in1 = nx1;
                     nx0 = load_in(c + 4, 0);
                     nx1 = load_in(two ? c + 4 : nD8, 1);
                     float v[4];
                     ld_frag(tlane + (uint32_t)(BCOL_GH + 8 * c), v);
                     wait_ld();
+                    BDSTAMP();
                     const int j = 8 * c + cj;
 #pragma unroll
                     for (int rr = 0; rr < 2; ++rr) {
@@ -1417,10 +1432,12 @@ rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __
                                 gz[ee] = gzz * z_[ee] * (1.f - z_[ee]);
                                 gnr[ee] = gn[ee] * r_[ee];
                             }
+                            if (rr == 0) BDSTAMP();
                             const long long o3 = (rr ? row1 : row0) * 3 * D + j;
                             st_f2(g.d_gi + o3, gr[0], gr[1]); st_f2(g.d_gi + o3 + D, gz[0], gz[1]); st_f2(g.d_gi + o3 + 2 * D, gn[0], gn[1]);
                             st_f2(g.d_gh + o3, gr[0], gr[1]); st_f2(g.d_gh + o3 + D, gz[0], gz[1]); st_f2(g.d_gh + o3 + 2 * D, gnr[0], gnr[1]);
                         }
+                        if (rr == 0) BDSTAMP();
                         st_shared_f2(cga, dir[0], dir[1]);
                         const uint32_t o = (rr ? opnd1 : opnd0) + (uint32_t)c * CH_BYTES;
                         st_shared_u32(smem0 + BCH_DR * CH_BYTES + o, pack_bf16x2(gr[0], gr[1]));
@@ -1638,7 +1655,11 @@ extern "C" int mrssm_rollout_tc_fwd(const mrssm_rollout_args* a, const void* pla
     MRSSM_CHECK(a->det || a->eps_prior, "rollout_tc_fwd: eps_prior missing");
     const int NH = 1 + a->n_experts;
     const bool stat = g_tc_static && a->D == 200 && a->S == 30 && a->H == 200 && a->A == 3 && (NH == 1 || NH == 2 || NH == 4);
-    auto kern = !stat ? rollout_tc_fwd_kernel<0> : (NH == 1 ? rollout_tc_fwd_kernel<1> : (NH == 2 ? rollout_tc_fwd_kernel<2> : rollout_tc_fwd_kernel<4>));
+    // 64 sequences per CTA when that already fills the machine, else 32 (one valid row per epilogue thread)
+    const int RPG = g_tc_rpg ? g_tc_rpg : ((a->B + 63) / 64 >= 74 ? 16 : 8);
+    auto kern = rollout_tc_fwd_kernel<0, false>;
+    if (RPG == 16) kern = (stat && NH == 4) ? rollout_tc_fwd_kernel<4, true> : rollout_tc_fwd_kernel<0, true>;
+    else if (stat) kern = NH == 1 ? rollout_tc_fwd_kernel<1, false> : (NH == 2 ? rollout_tc_fwd_kernel<2, false> : rollout_tc_fwd_kernel<4, false>);
     cudaFuncAttributes fa;
     MRSSM_CUDA(cudaFuncGetAttributes(&fa, kern));
     static thread_local TcProg prog;
@@ -1673,10 +1694,7 @@ extern "C" int mrssm_rollout_tc_fwd(const mrssm_rollout_args* a, const void* pla
     MRSSM_CHECK(NS >= 2, "rollout_tc_fwd: no room for the weight ring (%d bytes left)", avail);
     const size_t dyn = (size_t)OFF_RING + (size_t)NS * SLOT_BYTES + 1024;
     MRSSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    // 64 sequences per CTA when that already fills the machine's appetite, else 32 (one valid row per epilogue thread)
-    const int RPG = g_tc_rpg ? g_tc_rpg : ((a->B + 63) / 64 >= 74 ? 16 : 8);
-    kern<<<(a->B + 4 * RPG - 1) / (4 * RPG), TC_THREADS, dyn, (cudaStream_t)stream>>>(*a, prog, (const uint8_t*)packed_dev, NS, RPG,
-                                                                                                        g_tc_prof);
+    kern<<<(a->B + 4 * RPG - 1) / (4 * RPG), TC_THREADS, dyn, (cudaStream_t)stream>>>(*a, prog, (const uint8_t*)packed_dev, NS, g_tc_prof);
     MRSSM_LAUNCH_CHECK();
     return 0;
 }
@@ -1758,7 +1776,10 @@ extern "C" int mrssm_rollout_tc_bwd(const mrssm_rollout_bwd_args* g, const void*
     }
     const int NH = 1 + a->n_experts;
     const bool stat = g_tc_static && a->D == 200 && a->S == 30 && a->H == 200 && a->A == 3 && (NH == 1 || NH == 2 || NH == 4);
-    auto kern = !stat ? rollout_tc_bwd_kernel<0> : (NH == 1 ? rollout_tc_bwd_kernel<1> : (NH == 2 ? rollout_tc_bwd_kernel<2> : rollout_tc_bwd_kernel<4>));
+    const int RPG = g_tc_rpg ? g_tc_rpg : ((a->B + 63) / 64 >= 74 ? 16 : 8);
+    auto kern = rollout_tc_bwd_kernel<0, false>;
+    if (RPG == 16) kern = (stat && NH == 4) ? rollout_tc_bwd_kernel<4, true> : rollout_tc_bwd_kernel<0, true>;
+    else if (stat) kern = NH == 1 ? rollout_tc_bwd_kernel<1, false> : (NH == 2 ? rollout_tc_bwd_kernel<2, false> : rollout_tc_bwd_kernel<4, false>);
     cudaFuncAttributes fa;
     MRSSM_CUDA(cudaFuncGetAttributes(&fa, kern));
     const int avail = 232448 - (int)fa.sharedSizeBytes - 1024 - BOFF_RING;
@@ -1766,8 +1787,7 @@ extern "C" int mrssm_rollout_tc_bwd(const mrssm_rollout_bwd_args* g, const void*
     MRSSM_CHECK(NS >= 2, "rollout_tc_bwd: no room for the weight ring (%d bytes left)", avail);
     const size_t dyn = (size_t)BOFF_RING + (size_t)NS * SLOT_BYTES + 1024;
     MRSSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    const int RPG = g_tc_rpg ? g_tc_rpg : ((a->B + 63) / 64 >= 74 ? 16 : 8);
-    kern<<<(a->B + 4 * RPG - 1) / (4 * RPG), TC_THREADS, dyn, (cudaStream_t)stream>>>(*g, prog, (const uint8_t*)packed_dev, NS, RPG, g_tc_prof);
+    kern<<<(a->B + 4 * RPG - 1) / (4 * RPG), TC_THREADS, dyn, (cudaStream_t)stream>>>(*g, prog, (const uint8_t*)packed_dev, NS, g_tc_prof);
     MRSSM_LAUNCH_CHECK();
     return 0;
 }

@@ -57,6 +57,9 @@ v = [int(x) for x in prof2.cpu().view(4, 512)[2] if int(x) > 0]
 print("--- BWD epilogue warp 0: step start; per half-head (after wait, after signal) x 2NH; Ed (after wait, after signal); Ee (after wait, after signal); Ef (after wait, before step_a, after signal)")
 print(" ".join(str(x - v[0]) for x in v))
 print("deltas:", " ".join(str(b - a) for a, b in zip(v, v[1:])))
+w = [int(x) for x in prof2.cpu().view(4, 512)[3] if int(x) > 0]
+print("--- BWD gate backward (Ed), per chunk: loop top, after TMEM load, after math (before global stores), after global stores")
+print("deltas:", " ".join(str(b - a) for a, b in zip(w, w[1:])))
 t0 = int(p[p > 0].min())
 for role, name in enumerate(("producer (stamp after empty-wait, per tile)", "mma (before full-wait, after full-wait, after issue+commit; per tile)",
                              "epilogue warp 0 (before wait / after wait / after signal per unit)",

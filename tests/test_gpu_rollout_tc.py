@@ -155,3 +155,18 @@ def test_rollout_tc_bptt_matches_fp32(case):
         assert torch.isfinite(o).all(), n
         rel = float((o - r).norm() / (r.norm() + 1e-12))
         assert rel <= 3e-2, (n, rel, float(r.norm()))
+
+
+@pytest.mark.parametrize("rows", [16, 8])
+def test_rollout_tc_both_cta_shapes(rows):
+    """64 sequences per CTA (both rows of every TMEM fragment carry a sequence; chosen automatically for B >= 4700) and 32
+    per CTA give the same results: forward outputs and BPTT gradients against the fp32 kernels, with the shape forced."""
+    from mrssm_b200 import _lib as L
+    L.call_host("mrssm_rollout_tc_set_rows", rows)
+    try:
+        test_rollout_tc_matches_fp32(CASES[0])
+        test_rollout_tc_matches_fp32(CASES[2])
+        test_rollout_tc_bptt_matches_fp32(BWD_CASES[0])
+        test_rollout_tc_bptt_matches_fp32(BWD_CASES[3])
+    finally:
+        L.call_host("mrssm_rollout_tc_set_rows", 0)
