@@ -1398,15 +1398,21 @@ rollout_tc_bwd_kernel(const __grid_constant__ mrssm_rollout_bwd_args g, const __
                     }
                     return x;
                 };
-                GruIn nx0 = load_in(p, 0), nx1 = load_in(two ? p : nD8, 1);
+                // two chunks ahead when only one fragment row is live (the loads are L2 hits at ~600 cycles, an iteration is shorter)
+                GruIn nx0 = load_in(p, 0), nx1 = load_in(two ? p : nD8, 1), nxx = load_in(two ? nD8 : p + 4, 0);
                 wait_backoff(&cm[CMB_GCH0 + NH - 1], par);
                 tc::tc_fence_after();
                 BSTAMP();
                 for (int c = p; c < nD8; c += 4) {
                     BDSTAMP();
                     const GruIn in0 = nx0, in1 = nx1;
-                    nx0 = load_in(c + 4, 0);
-                    nx1 = load_in(two ? c + 4 : nD8, 1);
+                    if (two) {
+                        nx0 = load_in(c + 4, 0);
+                        nx1 = load_in(c + 4, 1);
+                    } else {
+                        nx0 = nxx;
+                        nxx = load_in(c + 8, 0);
+                    }
                     float v[4];
                     ld_frag(tlane + (uint32_t)(BCOL_GH + 8 * c), v);
                     wait_ld();
