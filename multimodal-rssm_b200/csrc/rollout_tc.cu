@@ -198,10 +198,10 @@ void build_plan(int D, int S, int H, int A, int NH, PlanBuilder& pb, TcHeader& h
     for (int hf = 0; hf < 2; ++hf) {
         const int c0 = hf ? cA : 0, nc = hf ? nD8 - cA : cA, n0 = 8 * c0, cnt = 8 * nc, N = ceil16(cnt);
         pb.unit_begin(hf ? EV_HA : EV_X);
-        for (int g = 0; g < 2; ++g) {       // r, z: x and h contributions into one accumulator
-            for (int k = 0; k < nkD; ++k) pb.mma(BUF_XU, k, g * ACC_STRIDE, N, k != 0, SRC_WIH, D, 0, g * D + n0, cnt);
-            for (int k = 0; k < nkD; ++k) pb.mma(BUF_HPREV, k, g * ACC_STRIDE, N, 1, SRC_WHH, D, 0, g * D + n0, cnt);
-        }
+        // r and z in ONE MMA of N = ACC_STRIDE + N (their accumulators are adjacent TMEM columns; the B block stacks the r rows
+        // and the z rows): x and h contributions into the same accumulators
+        for (int k = 0; k < nkD; ++k) pb.mma(BUF_XU, k, 0, ACC_STRIDE + N, k != 0, SRC_WIH, D, 0, n0, cnt, ACC_STRIDE, D + n0, cnt);
+        for (int k = 0; k < nkD; ++k) pb.mma(BUF_HPREV, k, 0, ACC_STRIDE + N, 1, SRC_WHH, D, 0, n0, cnt, ACC_STRIDE, D + n0, cnt);
         for (int k = 0; k < nkD; ++k) pb.mma(BUF_XU, k, 2 * ACC_STRIDE, N, k != 0, SRC_WIH, D, 0, 2 * D + n0, cnt);
         for (int k = 0; k < nkD; ++k) pb.mma(BUF_HPREV, k, 3 * ACC_STRIDE, N, k != 0, SRC_WHH, D, 0, 2 * D + n0, cnt);
         pb.unit_end(hf ? CM_GB : CM_GA);
@@ -446,12 +446,9 @@ __device__ __forceinline__ void static_step_fwd(Issuer& I, uint32_t xin16, uint3
         const int nc = hf ? nD8 - cA : cA, N = (8 * nc + 15) / 16 * 16;
         I.unit_begin(hf ? EV_HA : EV_X);
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
+        for (int k = 0; k < nkD; ++k) I.emit(opaque(xu16) + 2 * k * CH16, 0, ACC_STRIDE + N, k != 0);
 #pragma unroll
-            for (int k = 0; k < nkD; ++k) I.emit(opaque(xu16) + 2 * k * CH16, g * ACC_STRIDE, N, k != 0);
-#pragma unroll
-            for (int k = 0; k < nkD; ++k) I.emit(opaque(hprev16) + 2 * k * CH16, g * ACC_STRIDE, N, 1);
-        }
+        for (int k = 0; k < nkD; ++k) I.emit(opaque(hprev16) + 2 * k * CH16, 0, ACC_STRIDE + N, 1);
 #pragma unroll
         for (int k = 0; k < nkD; ++k) I.emit(opaque(xu16) + 2 * k * CH16, 2 * ACC_STRIDE, N, k != 0);
 #pragma unroll
