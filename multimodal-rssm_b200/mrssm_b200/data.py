@@ -7,9 +7,47 @@ converts / normalises there (memory.py:197-208, image_processing.py:5-11), retur
 stream while step k computes, and the normalisation is one kernel (``mrssm_normalize_image_u8``).  Index sampling and
 augmentation of the replay buffer are out of scope: the source is handed ready-made chunks.
 """
+import contextlib
+import os
+
 import torch
 
 from . import _lib as L
+
+
+def _device_local_cpus(device):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None when that cannot be determined."""
+    try:
+        p = torch.cuda.get_device_properties(device)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        return cpus if cpus and cpus != allowed else None
+    except Exception:
+        return None
+
+
+@contextlib.contextmanager
+def near_device(device):
+    """Run the body on the CPUs of the GPU's NUMA node: pinned buffers allocated (first touched) inside land in the memory
+    the GPU's PCIe root complex reaches without crossing the socket interconnect.  No-op when the topology is unknown."""
+    cpus = _device_local_cpus(device)
+    if cpus is None:
+        yield
+        return
+    old = os.sched_getaffinity(0)
+    try:
+        os.sched_setaffinity(0, cpus)
+        yield
+    finally:
+        os.sched_setaffinity(0, old)
 
 
 class PinnedChunkSource:
@@ -22,7 +60,8 @@ class PinnedChunkSource:
         self.device = torch.device(device)
         self.bit_depth, self.seed, self.prefetch = bit_depth, seed, prefetch
         pin = lambda t: t.contiguous().pin_memory()
-        self.host = [({k: pin(v) for k, v in obs.items()}, pin(a), pin(r), pin(n)) for obs, a, r, n in chunks]
+        with near_device(self.device):       # pinned staging memory NUMA-local to the GPU
+            self.host = [({k: pin(v) for k, v in obs.items()}, pin(a), pin(r), pin(n)) for obs, a, r, n in chunks]
         obs, a, r, n = self.host[0]
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in obs.values()) + 4 * (a.numel() + r.numel() + n.numel())
         self.copy_stream = torch.cuda.Stream(device=self.device)
