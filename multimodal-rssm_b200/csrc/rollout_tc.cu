@@ -426,8 +426,8 @@ struct Issuer {
     }
 };
 constexpr uint32_t CH16 = CH_BYTES >> 4;
-// opaque identity: keeps the compiler from hoisting every (buffer base + chunk offset) sum of the unrolled program into
-// registers for the whole step (hundreds of bytes of spills in the issuing thread); the add is redone next to its MMA
+// opaque identity: keeps the compiler from hoisting every (buffer base + chunk offset) sum of the unrolled program out of the
+// step loop; the add is redone next to its MMA (one uniform add) instead of living in a register across the whole step
 __device__ __forceinline__ uint32_t opaque(uint32_t v) {
     asm volatile("" : "+r"(v));
     return v;
