@@ -42,8 +42,6 @@ class RSSM_base(nn.Module):
         self.observation_name = cfg.rssm.observation_names_enc[0]
         if cfg.rssm.overshooting_kl_beta != 0:
             raise NotImplementedError("latent overshooting is a 'next' row (SURVEY §8f#3)")
-        if cfg.rssm.predict_reward:
-            raise NotImplementedError("predict_reward=True is a 'next' row (SURVEY §8f#3)")
         self._init_models(device)
         self._init_param_list()
         self._init_optimizer()
@@ -138,7 +136,13 @@ class RSSM_base(nn.Module):
         kl_loss_sum = kl_loss
         if self.cfg.rssm.global_kl_beta != 0:
             kl_loss_sum = kl_loss + self.cfg.rssm.global_kl_beta * kl_global
-        reward_loss = torch.zeros((), device=kl_loss.device)    # predict_reward False (reference :200-201)
+        if self.cfg.rssm.predict_reward:                        # reference _calc_reward_loss :96-109, :175
+            r = self.reward_model(h_t=states["beliefs"], s_t=z)["loc"]
+            rows = r.numel()
+            mse = ops.MseLossFn.apply(r.reshape(rows, 1), rewards[:-1].reshape(rows, 1).contiguous(), rows)
+            reward_loss = self._obs_loss_from_mse(mse, 1)       # MSE, or -log N(r; loc, 1) with worldmodel_LogProbLoss
+        else:                                                   # the reference zeroes it (:200-201): forward skipped
+            reward_loss = torch.zeros((), device=kl_loss.device)
         return observations_loss, reward_loss, kl_loss_sum, kl_loss
 
     def _get_model_loss(self, observations_target, actions, rewards, nonterminals, states):
@@ -149,7 +153,7 @@ class RSSM_base(nn.Module):
         info = {"observations_loss_sum": observations_loss_sum.detach()}
         for name, v in observations_loss.items():
             info["observation_{}_loss".format(name)] = v.detach()
-        info["reward_loss"] = reward_loss
+        info["reward_loss"] = reward_loss.detach()
         info["kl_loss_sum"] = kl_loss_sum.detach()
         info["kl_loss"] = kl_loss.detach()
         return model_loss, info

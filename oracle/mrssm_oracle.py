@@ -56,6 +56,7 @@ class OracleConfig:
     lr: float = 1e-3
     adam_eps: float = 1e-7
     grad_clip_norm: float = 100.0
+    predict_reward: bool = False     # base/algo.py:200-201: False zeroes the reward loss (shipped default)
 
     @property
     def multimodal(self) -> bool:
@@ -504,10 +505,12 @@ def decoder_latent(cfg: OracleConfig, st: dict, eps_dec: Optional[Tensor]):
     return st["posterior_states"], st["posterior_means"], st["posterior_std_devs"]
 
 
-def elbo(P, cfg: OracleConfig, st: dict, obs_target: Dict[str, Tensor], eps_dec: Optional[Tensor]):
-    """_calc_loss + _get_model_loss (base/algo.py:165-232) with the shipped defaults
-    (overshooting off, predict_reward False -> reward loss zeroed, MSE observation loss
-    mean over (t,b) then sum over features, base/algo.py:381-383)."""
+def elbo(P, cfg: OracleConfig, st: dict, obs_target: Dict[str, Tensor], eps_dec: Optional[Tensor],
+         rewards: Optional[Tensor] = None):
+    """_calc_loss + _get_model_loss (base/algo.py:165-232): overshooting off, MSE observation loss
+    mean over (t,b) then sum over features (base/algo.py:381-383); the reward loss (_calc_reward_loss
+    base/algo.py:96-109: MSE of the reward head on [h, z] against rewards[:-1], mean over (t,b)) is
+    zeroed unless predict_reward (base/algo.py:200-201)."""
     z, qm, qs = decoder_latent(cfg, st, eps_dec)
     rec = decode(P, cfg, st["beliefs"], z)
     obs_loss = {n: F.mse_loss(rec[n], obs_target[n], reduction="none").mean((0, 1)).sum()
@@ -518,8 +521,12 @@ def elbo(P, cfg: OracleConfig, st: dict, obs_target: Dict[str, Tensor], eps_dec:
         kl_sum = kl_sum + cfg.global_kl_beta * kl_normal(
             qm, qs, torch.zeros_like(qm), torch.ones_like(qs)).sum(2).mean((0, 1))
     obs_sum = sum(obs_loss.values())
-    model_loss = obs_sum + cfg.kl_beta * kl_sum                                    # :221 (reward = 0)
-    info = {"observations_loss_sum": obs_sum, "reward_loss": torch.zeros(()),
+    reward_loss = torch.zeros(())
+    if cfg.predict_reward:                                                          # :96-109, :175
+        r = reward_model(P, cfg, st["beliefs"], z)
+        reward_loss = F.mse_loss(r, rewards[:-1], reduction="none").mean((0, 1))
+    model_loss = obs_sum + reward_loss + cfg.kl_beta * kl_sum                      # :221
+    info = {"observations_loss_sum": obs_sum, "reward_loss": reward_loss,
             "kl_loss_sum": kl_sum, "kl_loss": kl}
     for n in cfg.names_rec:
         info[f"observation_{n}_loss"] = obs_loss[n]
@@ -566,7 +573,7 @@ def train_step(P: Dict[str, Tensor], opt: dict, cfg: OracleConfig, batch: dict, 
     tgt = {n: o[1:] for n, o in batch["obs"].items()}                               # base:241
     st = estimate_state(leaves, cfg, {n: tgt[n] for n in cfg.names_enc}, batch["actions"][:-1],
                         batch["nonterminals"][:-1], noise["eps_prior"], noise["eps_post"])
-    loss, info = elbo(leaves, cfg, st, tgt, noise.get("eps_dec"))
+    loss, info = elbo(leaves, cfg, st, tgt, noise.get("eps_dec"), batch.get("rewards"))
     loss.backward()
     keys = [k for k in leaves if leaves[k].grad is not None]     # reward model: grad None (a24)
     grads = {k: leaves[k].grad for k in keys}
@@ -608,6 +615,8 @@ def synthetic_batch(cfg: OracleConfig, B: int, T: int, seed: int = 1234, dtype=t
     S = cfg.state_size
     noise = {k: torch.randn((T - 1, B, S), generator=g).to(dtype)
              for k in ("eps_prior", "eps_post", "eps_dec")}
-    batch = {"obs": obs, "actions": actions, "rewards": torch.zeros(T, B, dtype=dtype),
-             "nonterminals": nonterm}
+    rewards = torch.zeros(T, B, dtype=dtype)
+    if cfg.predict_reward:           # own generator: the other tensors of a seed do not change with this switch
+        rewards = torch.randn((T, B), generator=torch.Generator().manual_seed(seed + 77)).to(dtype)
+    batch = {"obs": obs, "actions": actions, "rewards": rewards, "nonterminals": nonterm}
     return batch, noise

@@ -49,7 +49,7 @@ def ref_cfg(oc: O.OracleConfig, B, T):
         train=dict(batch_size=B, chunk_size=T, use_amp=False),
         rssm=dict(
             observation_names_enc=list(oc.names_enc), observation_names_rec=list(oc.names_rec),
-            predict_reward=False, multimodal=oc.multimodal,
+            predict_reward=oc.predict_reward, multimodal=oc.multimodal,
             multimodal_params=dict(fusion_method=oc.fusion, expert_dist="q(st|ht,ot)"),
             activation_function=dict(cnn="relu", dense=oc.act_dense, fusion="relu"),
             embedding_size=dict(oc.embedding_size), hidden_size=oc.hidden_size,
@@ -237,5 +237,6 @@ if __name__ == "__main__":
     gen_train("single", O.OracleConfig(fusion="single", names_enc=("image_horizon",), names_rec=("image_horizon",)))
     gen_train("mopoe_clip", O.OracleConfig(fusion="MoPoE", grad_clip_norm=0.5, kl_balancing_alpha=None))
     gen_train("poe_noalpha", O.OracleConfig(fusion="PoE", kl_balancing_alpha=None, global_kl_beta=0.0, free_nats=0.5))
+    gen_train("mopoe_reward", O.OracleConfig(fusion="MoPoE", predict_reward=True))
     gen_infer("mopoe", O.OracleConfig(fusion="MoPoE"))
     gen_infer("single", O.OracleConfig(fusion="single", names_enc=("image_horizon",), names_rec=("image_horizon",)))

@@ -24,7 +24,7 @@ def _product_cfg(oc, B, T, device):
                            belief_size=oc.belief_size, state_size=oc.state_size, hidden_size=oc.hidden_size,
                            free_nats=oc.free_nats, kl_balancing_alpha=oc.kl_balancing_alpha,
                            global_kl_beta=oc.global_kl_beta, kl_beta=oc.kl_beta, grad_clip_norm=oc.grad_clip_norm,
-                           model_learning_rate=oc.lr, adam_epsilon=oc.adam_eps)
+                           model_learning_rate=oc.lr, adam_epsilon=oc.adam_eps, predict_reward=oc.predict_reward)
 
 
 def unflatten(flat):

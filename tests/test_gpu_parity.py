@@ -16,13 +16,14 @@ RTOL = 1e-3      # BASELINE.json north_star: rtol 1e-3 in fp32 mode
     ("MoPoE", {}), ("PoE", {}), ("NN", {}), ("single", {}),
     ("MoPoE", dict(grad_clip_norm=0.5, kl_balancing_alpha=None)),
     ("PoE", dict(kl_balancing_alpha=None, global_kl_beta=0.0, free_nats=0.5)),
+    ("MoPoE", dict(predict_reward=True)),
 ])
 def test_train_step_matches_oracle(fusion, kw):
     out = U.run_train_parity(fusion, B=4, T=6, steps=2, device=DEV, rtol=RTOL, **kw)
     assert out["worst_grad_err"] < 2 * RTOL
 
 
-@pytest.mark.parametrize("name", ["mopoe", "poe", "nn", "single", "mopoe_clip", "poe_noalpha"])
+@pytest.mark.parametrize("name", ["mopoe", "poe", "nn", "single", "mopoe_clip", "poe_noalpha", "mopoe_reward"])
 def test_train_step_matches_reference_fixture(name, golden_dir):
     """Directly against tests/golden/train_*.pt (outputs of the unmodified reference)."""
     rec = torch.load(os.path.join(golden_dir, f"train_{name}.pt"), weights_only=False)

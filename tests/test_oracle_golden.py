@@ -7,7 +7,7 @@ import torch
 
 from oracle import mrssm_oracle as O
 
-TRAIN = ["mopoe", "poe", "nn", "single", "mopoe_clip", "poe_noalpha"]
+TRAIN = ["mopoe", "poe", "nn", "single", "mopoe_clip", "poe_noalpha", "mopoe_reward"]
 
 
 def _cfg(meta):
