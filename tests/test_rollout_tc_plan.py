@@ -145,3 +145,144 @@ def test_program_computes_the_step_gemms(dims):
     expect.append(CM_F2 + NH - 1)
     assert seen_commits == expect
     assert waits[:4] == [EV_XIN, EV_X, EV_HA, EV_HB]
+
+
+# ---- BPTT program ---------------------------------------------------------------------------------------------------
+EVB_DO, EVB_DU0, EVB_GRU, EVB_DX = 0, 1, 9, 10
+CMB_GB0, CMB_GCH0, CMB_GE, CMB_GF = 0, 8, 12, 13
+BCH_DU, BCOL_SET, BCOL_GH, BCOL_GX, BCOL_GHH, BCOL_XIN = 32, 112, 224, 0, 208, 448
+MAXC = 26
+
+
+def _plan_bwd(D, S, H, A, E):
+    from mrssm_b200 import _lib as L
+    L.load()
+    pb, kb = ctypes.c_int64(), ctypes.c_int64()
+    L.call_host("mrssm_rollout_tc_bwd_plan_bytes", D, S, H, A, E, ctypes.byref(pb), ctypes.byref(kb))
+    buf = ctypes.create_string_buffer(pb.value)
+    L.call_host("mrssm_rollout_tc_bwd_plan", D, S, H, A, E, ctypes.cast(buf, ctypes.c_void_p), pb.value)
+    raw = np.frombuffer(buf.raw, dtype=np.uint8)
+    hdr, hu = raw[:80].view("<i4"), raw[:80].view("<u4")
+    n_tiles, n_ops, n_pack = int(hdr[6]), int(hdr[7]), int(hdr[8])
+    packed_bytes, tile_off, op_off, pack_off = [int(v) for v in hu[13:17]]
+    tiles = raw[tile_off:tile_off + n_tiles * TILE.itemsize].view(TILE)
+    ops = raw[op_off:op_off + n_ops * OP.itemsize].view(OP)
+    packs = raw[pack_off:pack_off + n_pack * PACK.itemsize].view(PACK)
+    return dict(cAH=int(hdr[11]), nH8=int(hdr[12])), tiles, ops, packs, packed_bytes
+
+
+def _pack_any(packs, srcs, packed_bytes):
+    """numpy twin of rollout_tc_pack_kernel including the transposed (dgrad-type) blocks."""
+    out = np.zeros(packed_bytes // 2, dtype=np.float32)
+    for pk in packs:
+        sid, N = int(pk["src_id"]), int(pk["N"])
+        w = srcs[sid & 0xff]
+        blk = np.zeros((2, N, 8), dtype=np.float32)
+        if sid & 0x100:           # Bblock[n][k'] = W[row(k0 + k')][n_off + n], n < n_cnt
+            n_cnt, n_off = int(pk["kvalid"]), int(pk["pad"])
+            for k in range(16):
+                kk = int(pk["k0"]) + k
+                for s in range(2):
+                    k0s, r0, cnt = int(pk["seg_n"][s]), int(pk["seg_src"][s]), int(pk["seg_cnt"][s])
+                    if k0s <= kk < k0s + cnt:
+                        blk[k // 8, :n_cnt, k % 8] = w[r0 + kk - k0s, n_off:n_off + n_cnt]
+        else:
+            for s in range(2):
+                n0, r0, cnt = int(pk["seg_n"][s]), int(pk["seg_src"][s]), int(pk["seg_cnt"][s])
+                for k in range(int(pk["kvalid"])):
+                    blk[k // 8, n0:n0 + cnt, k % 8] = w[r0:r0 + cnt, int(pk["k0"]) + k]
+        out[int(pk["dst_off"]) // 2: int(pk["dst_off"]) // 2 + 16 * N] = blk.reshape(-1)
+    return out
+
+
+@pytest.mark.parametrize("dims", [(200, 30, 200, 3, 3), (200, 30, 200, 3, 0), (64, 8, 48, 2, 2), (208, 32, 104, 6, 1)])
+def test_bptt_program_computes_the_step_gemms(dims):
+    """Same replay for the backward program: go W2, du W1[:, :D] summed over heads, [dr dz dn] W_ih, [dr dz dn*r] W_hh,
+    dxpre W_sa, with the operand region re-used exactly as the kernel re-uses it."""
+    D, S, H, A, E = dims
+    NH = 1 + E
+    hd, tiles, ops, packs, packed_bytes = _plan_bwd(D, S, H, A, E)
+    rng = np.random.default_rng(1)
+    w_sa = rng.standard_normal((D, S + A)).astype(np.float32)
+    w_ih = rng.standard_normal((3 * D, D)).astype(np.float32)
+    w_hh = rng.standard_normal((3 * D, D)).astype(np.float32)
+    ld1 = [D, D, D + 24, D + 8][:NH]
+    w1 = [rng.standard_normal((H, ld)).astype(np.float32) for ld in ld1]
+    w2 = [rng.standard_normal((2 * S, H)).astype(np.float32) for _ in range(NH)]
+    srcs = {0: w_sa, 1: w_ih, 2: w_hh}
+    for h in range(NH):
+        srcs[3 + h], srcs[7 + h] = w1[h], w2[h]
+    image = _pack_any(packs, srcs, packed_bytes)
+
+    go = [rng.standard_normal((ROWS, 2 * S)).astype(np.float32) for _ in range(NH)]
+    du = [rng.standard_normal((ROWS, H)).astype(np.float32) for _ in range(NH)]
+    dr, dz, dn, dnr, dx = (rng.standard_normal((ROWS, D)).astype(np.float32) for _ in range(5))
+    region = np.zeros((4 * MAXC, ROWS, 8), dtype=np.float32)
+
+    def put(chunk0, mat):
+        nch = (mat.shape[1] + 7) // 8
+        region[chunk0:chunk0 + nch] = 0.0
+        for c in range(nch):
+            w = min(8, mat.shape[1] - 8 * c)
+            region[chunk0 + c, :, :w] = mat[:, 8 * c:8 * c + w]
+
+    def put_go(h):                  # means at K 0..S-1, raw stds at K 32..32+S-1
+        m = np.zeros((ROWS, 64), dtype=np.float32)
+        m[:, :S], m[:, 32:32 + S] = go[h][:, :S], go[h][:, S:]
+        put(8 * h, m)
+
+    for h in range(NH):
+        put_go(h)
+    tmem = np.full((ROWS, 512), np.nan, dtype=np.float32)
+    cAH, nH8 = hd["cAH"], hd["nH8"]
+    gh_ref = np.zeros((ROWS, D), dtype=np.float32)
+    seen, off = [], 0
+    for tl in tiles:
+        assert int(tl["src_off"]) == off and 0 < int(tl["bytes"]) <= SLOT_BYTES
+        off += int(tl["bytes"])
+        ev = int(tl["wait_ev"])
+        if ev >= EVB_DU0 and ev < EVB_GRU and (ev - EVB_DU0) % 2 == 1:
+            put(BCH_DU, du[(ev - EVB_DU0) // 2])                       # the du buffer is rewritten per head
+        elif ev == EVB_GRU:
+            put(0, dr), put(MAXC, dz), put(2 * MAXC, dn), put(3 * MAXC, dnr)
+        elif ev == EVB_DX:
+            put(0, dx)
+        for o in ops[int(tl["op_begin"]):int(tl["op_end"])]:
+            N = ((int(o["idesc"]) >> 17) & 63) << 3
+            a_ch = int(o["a_off16"]) * 16 // CH_BYTES
+            Amat = np.concatenate([region[a_ch], region[a_ch + 1]], axis=1)
+            b0 = (int(tl["src_off"]) + int(o["b_off16"]) * 16) // 2
+            blk = image[b0:b0 + 16 * N].reshape(2, N, 8)
+            prod = Amat @ np.concatenate([blk[0], blk[1]], axis=1).T
+            c0 = int(o["d_col"])
+            assert c0 + N <= 512
+            tmem[:, c0:c0 + N] = prod + (tmem[:, c0:c0 + N] if o["acc"] else 0.0)
+        cm = int(tl["commit"])
+        if cm < 0:
+            continue
+        seen.append(cm)
+        tol = dict(rtol=1e-4, atol=2e-3)
+        if CMB_GB0 <= cm < CMB_GCH0:
+            h, hf = (cm - CMB_GB0) // 2, (cm - CMB_GB0) % 2
+            n0, cnt = (0, 8 * cAH) if hf == 0 else (8 * cAH, 8 * (nH8 - cAH))
+            np.testing.assert_allclose(tmem[:, hf * BCOL_SET:hf * BCOL_SET + cnt], go[h] @ w2[h][:, n0:n0 + cnt], **tol)
+        elif CMB_GCH0 <= cm < CMB_GE:
+            h = cm - CMB_GCH0
+            gh_ref = gh_ref + du[h] @ w1[h][:, :D]
+            np.testing.assert_allclose(tmem[:, BCOL_GH:BCOL_GH + D], gh_ref, **tol)
+        elif cm == CMB_GE:
+            np.testing.assert_allclose(tmem[:, BCOL_GX:BCOL_GX + D], np.concatenate([dr, dz, dn], 1) @ w_ih, **tol)
+            np.testing.assert_allclose(tmem[:, BCOL_GHH:BCOL_GHH + D], np.concatenate([dr, dz, dnr], 1) @ w_hh, **tol)
+        else:
+            assert cm == CMB_GF
+            np.testing.assert_allclose(tmem[:, BCOL_XIN:BCOL_XIN + S + A], dx @ w_sa, **tol)
+    assert off == packed_bytes
+    expect = [CMB_GB0, CMB_GB0 + 1]
+    for h in range(NH):
+        if h + 1 < NH:
+            expect.append(CMB_GB0 + 2 * (h + 1))
+        expect.append(CMB_GCH0 + h)
+        if h + 1 < NH:
+            expect.append(CMB_GB0 + 2 * (h + 1) + 1)
+    expect += [CMB_GE, CMB_GF]
+    assert seen == expect
