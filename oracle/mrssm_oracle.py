@@ -57,6 +57,9 @@ class OracleConfig:
     adam_eps: float = 1e-7
     grad_clip_norm: float = 100.0
     predict_reward: bool = False     # base/algo.py:200-201: False zeroes the reward loss (shipped default)
+    overshooting_distance: int = 0   # latent overshooting (base/algo.py:111-148, MoPoE/algo.py:69-108); kl_beta 0 = off
+    overshooting_kl_beta: float = 0.0
+    overshooting_reward_scale: float = 0.0
 
     @property
     def multimodal(self) -> bool:
@@ -505,8 +508,63 @@ def decoder_latent(cfg: OracleConfig, st: dict, eps_dec: Optional[Tensor]):
     return st["posterior_states"], st["posterior_means"], st["posterior_std_devs"]
 
 
+def latent_overshooting(P, cfg: OracleConfig, st: dict, actions: Tensor, rewards: Tensor, nonterminals: Tensor,
+                        eps_over: List[Tensor]):
+    """RSSM_base._latent_overshooting (base/algo.py:111-148) and the MoPoE override (MRSSM_MoPoE/algo.py:69-108).
+    actions [T,B,A], rewards [T,B], nonterminals [T,B,1] are the FULL chunk; st holds the T-1 model steps.
+    For every start t = 1..T-2 an open-loop (imagination) rollout of up to `overshooting_distance` steps from
+    (beliefs[t-1], prior_states[t-1]) is run — all starts concatenated along the batch, shorter runs zero-padded — and
+    its priors are pulled towards the DETACHED posteriors of the same steps: max((KL * seq_mask).sum(S), free_nats)
+    .mean((0,1)) * overshooting_kl_beta.  MoPoE: one such term (one rollout, fresh noise) per modality subset, averaged.
+    eps_over: one [OD, (T-2)*B, S] noise tensor per rollout.  Returns (kl term, reward term)."""
+    T, B = actions.shape[0], actions.shape[1]
+    OD, S = cfg.overshooting_distance, cfg.state_size
+    beliefs, prior_states = st["beliefs"], st["prior_states"]
+    if cfg.fusion == "MoPoE":
+        names = list(st["expert_means"].keys())
+        tm, ts = subsets_poe([st["expert_means"][n] for n in names], [st["expert_std_devs"][n] for n in names])
+        targets = list(zip(tm, ts))
+    elif cfg.fusion == "PoE":        # _get_posterior_states of MRSSM_PoE re-fuses the experts (same values as the rollout's)
+        names = list(st["expert_means"].keys())
+        targets = [fuse([st["expert_means"][n] for n in names], [st["expert_std_devs"][n] for n in names], "PoE")]
+    else:
+        targets = [(st["posterior_means"], st["posterior_std_devs"])]
+    free = torch.full((1,), cfg.free_nats, dtype=beliefs.dtype)
+    kl_sum = torch.zeros((), dtype=beliefs.dtype)
+    reward = torch.zeros((), dtype=beliefs.dtype)
+    last = None
+    for (qm_all, qs_all), eps in zip(targets, eps_over):
+        acts, nts, rws, h0, s0, qm, qs, msk = [], [], [], [], [], [], [], []
+        for t in range(1, T - 1):
+            d = min(t + OD, T - 1)
+            t_, d_ = t - 1, d - 1
+            pad = t - d + OD                                                  # base:124
+            padt = lambda x, v=0.0: F.pad(x, (0, 0) * (x.dim() - 1) + (0, pad), value=v)
+            acts.append(padt(actions[t:d]))
+            nts.append(padt(nonterminals[t:d]))
+            rws.append(padt(rewards[t:d]))
+            h0.append(beliefs[t_])
+            s0.append(prior_states[t_])
+            qm.append(padt(qm_all[t_ + 1:d_ + 1].detach()))
+            qs.append(padt(qs_all[t_ + 1:d_ + 1].detach(), 1.0))              # std padded with 1 (no infinite KL)
+            msk.append(padt(torch.ones(d - t, B, S, dtype=beliefs.dtype)))
+        out = rollout(P, cfg, torch.cat(s0, 0), torch.cat(acts, 1), torch.cat(h0, 0), None, torch.cat(nts, 1), eps, None)
+        seq_mask = torch.cat(msk, 1)
+        div = kl_normal(torch.cat(qm, 1), torch.cat(qs, 1), out["prior_means"], out["prior_std_devs"])
+        kl_sum = kl_sum + cfg.overshooting_kl_beta * torch.max((div * seq_mask).sum(2), free).mean((0, 1))
+        last = (out, seq_mask, torch.cat(rws, 1))
+    kl_sum = kl_sum / len(targets)                                             # MoPoE:101 (a single term otherwise)
+    if cfg.overshooting_reward_scale != 0:                                     # base:143-146 (MoPoE: the LAST subset's rollout)
+        out, seq_mask, rw = last
+        r = reward_model(P, cfg, out["beliefs"], out["prior_states"])
+        reward = (1.0 / OD) * cfg.overshooting_reward_scale * \
+            F.mse_loss(r * seq_mask[:, :, 0], rw, reduction="none").mean((0, 1)) * (T - 1)
+    return kl_sum, reward
+
+
 def elbo(P, cfg: OracleConfig, st: dict, obs_target: Dict[str, Tensor], eps_dec: Optional[Tensor],
-         rewards: Optional[Tensor] = None):
+         rewards: Optional[Tensor] = None, actions: Optional[Tensor] = None, nonterminals: Optional[Tensor] = None,
+         eps_over: Optional[List[Tensor]] = None):
     """_calc_loss + _get_model_loss (base/algo.py:165-232): overshooting off, MSE observation loss
     mean over (t,b) then sum over features (base/algo.py:381-383); the reward loss (_calc_reward_loss
     base/algo.py:96-109: MSE of the reward head on [h, z] against rewards[:-1], mean over (t,b)) is
@@ -522,9 +580,16 @@ def elbo(P, cfg: OracleConfig, st: dict, obs_target: Dict[str, Tensor], eps_dec:
             qm, qs, torch.zeros_like(qm), torch.ones_like(qs)).sum(2).mean((0, 1))
     obs_sum = sum(obs_loss.values())
     reward_loss = torch.zeros(())
-    if cfg.predict_reward:                                                          # :96-109, :175
+    need_reward = cfg.predict_reward
+    if need_reward:                                                                 # :96-109, :175
         r = reward_model(P, cfg, st["beliefs"], z)
         reward_loss = F.mse_loss(r, rewards[:-1], reduction="none").mean((0, 1))
+    if cfg.overshooting_kl_beta != 0:                                               # :190-193
+        kl_o, r_o = latent_overshooting(P, cfg, st, actions, rewards, nonterminals, eps_over)
+        kl_sum = kl_sum + kl_o
+        reward_loss = reward_loss + r_o
+    if not cfg.predict_reward:                                                      # :200-201
+        reward_loss = torch.zeros(())
     model_loss = obs_sum + reward_loss + cfg.kl_beta * kl_sum                      # :221
     info = {"observations_loss_sum": obs_sum, "reward_loss": reward_loss,
             "kl_loss_sum": kl_sum, "kl_loss": kl}
@@ -573,7 +638,8 @@ def train_step(P: Dict[str, Tensor], opt: dict, cfg: OracleConfig, batch: dict, 
     tgt = {n: o[1:] for n, o in batch["obs"].items()}                               # base:241
     st = estimate_state(leaves, cfg, {n: tgt[n] for n in cfg.names_enc}, batch["actions"][:-1],
                         batch["nonterminals"][:-1], noise["eps_prior"], noise["eps_post"])
-    loss, info = elbo(leaves, cfg, st, tgt, noise.get("eps_dec"), batch.get("rewards"))
+    loss, info = elbo(leaves, cfg, st, tgt, noise.get("eps_dec"), batch.get("rewards"), batch["actions"],
+                      batch["nonterminals"], noise.get("eps_over"))
     loss.backward()
     keys = [k for k in leaves if leaves[k].grad is not None]     # reward model: grad None (a24)
     grads = {k: leaves[k].grad for k in keys}
@@ -615,6 +681,12 @@ def synthetic_batch(cfg: OracleConfig, B: int, T: int, seed: int = 1234, dtype=t
     S = cfg.state_size
     noise = {k: torch.randn((T - 1, B, S), generator=g).to(dtype)
              for k in ("eps_prior", "eps_post", "eps_dec")}
+    if cfg.overshooting_kl_beta != 0:     # own generator again: one [OD, (T-2)B, S] tensor per imagination rollout
+        go = torch.Generator().manual_seed(seed + 177)
+        n_roll = 2 ** (len(cfg.names_enc)) if cfg.fusion == "MoPoE" else 1
+        noise["eps_over"] = [torch.randn((cfg.overshooting_distance, (T - 2) * B, S), generator=go).to(dtype) for _ in range(n_roll)]
+        if cfg.fusion == "PoE":               # the base _latent_overshooting calls _get_posterior_states once more: one unused draw
+            noise["eps_dec2"] = torch.randn((T - 1, B, S), generator=go).to(dtype)
     rewards = torch.zeros(T, B, dtype=dtype)
     if cfg.predict_reward:           # own generator: the other tensors of a seed do not change with this switch
         rewards = torch.randn((T, B), generator=torch.Generator().manual_seed(seed + 77)).to(dtype)

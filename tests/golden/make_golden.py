@@ -54,8 +54,9 @@ def ref_cfg(oc: O.OracleConfig, B, T):
             activation_function=dict(cnn="relu", dense=oc.act_dense, fusion="relu"),
             embedding_size=dict(oc.embedding_size), hidden_size=oc.hidden_size,
             belief_size=oc.belief_size, state_size=oc.state_size, normalization=None,
-            worldmodel_LogProbLoss=False, overshooting_distance=0, overshooting_kl_beta=0,
-            overshooting_reward_scale=0, global_kl_beta=oc.global_kl_beta, free_nats=oc.free_nats,
+            worldmodel_LogProbLoss=False, overshooting_distance=oc.overshooting_distance,
+            overshooting_kl_beta=oc.overshooting_kl_beta,
+            overshooting_reward_scale=oc.overshooting_reward_scale, global_kl_beta=oc.global_kl_beta, free_nats=oc.free_nats,
             kl_beta=oc.kl_beta, kl_balancing_alpha=oc.kl_balancing_alpha, learning_rate_schedule=0,
             adam_epsilon=oc.adam_eps, grad_clip_norm=oc.grad_clip_norm, model_learning_rate=oc.lr)))
 
@@ -100,6 +101,12 @@ def queue_train_noise(fifo, noise, fusion):
         fifo.push(noise["eps_post"][t])
     if fusion in ("PoE", "MoPoE"):
         fifo.push(noise["eps_dec"])
+    if "eps_over" in noise:                  # latent overshooting: (PoE: one more decoder-latent draw, unused) then, per
+        if "eps_dec2" in noise:              # imagination rollout, one (N,S) draw per step
+            fifo.push(noise["eps_dec2"])
+        for eps in noise["eps_over"]:
+            for t in range(eps.shape[0]):
+                fifo.push(eps[t])
 
 
 def summarize(t, n=24):
@@ -238,5 +245,10 @@ if __name__ == "__main__":
     gen_train("mopoe_clip", O.OracleConfig(fusion="MoPoE", grad_clip_norm=0.5, kl_balancing_alpha=None))
     gen_train("poe_noalpha", O.OracleConfig(fusion="PoE", kl_balancing_alpha=None, global_kl_beta=0.0, free_nats=0.5))
     gen_train("mopoe_reward", O.OracleConfig(fusion="MoPoE", predict_reward=True))
+    gen_train("mopoe_over", O.OracleConfig(fusion="MoPoE", overshooting_distance=3, overshooting_kl_beta=0.5))
+    gen_train("poe_over", O.OracleConfig(fusion="PoE", overshooting_distance=2, overshooting_kl_beta=1.0, predict_reward=True,
+                                         overshooting_reward_scale=0.5))
+    gen_train("single_over", O.OracleConfig(fusion="single", names_enc=("image_horizon",), names_rec=("image_horizon",),
+                                            overshooting_distance=4, overshooting_kl_beta=0.25))
     gen_infer("mopoe", O.OracleConfig(fusion="MoPoE"))
     gen_infer("single", O.OracleConfig(fusion="single", names_enc=("image_horizon",), names_rec=("image_horizon",)))

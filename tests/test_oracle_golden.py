@@ -7,7 +7,7 @@ import torch
 
 from oracle import mrssm_oracle as O
 
-TRAIN = ["mopoe", "poe", "nn", "single", "mopoe_clip", "poe_noalpha", "mopoe_reward"]
+TRAIN = ["mopoe", "poe", "nn", "single", "mopoe_clip", "poe_noalpha", "mopoe_reward", "mopoe_over", "poe_over", "single_over"]
 
 
 def _cfg(meta):
