@@ -318,6 +318,37 @@ typedef struct mrssm_latent_args {
 int mrssm_latent_fwd(const mrssm_latent_args* a, void* stream);
 int mrssm_latent_bwd(const mrssm_latent_args* a, void* stream);
 
+/* ---- latent overshooting ---------------------------------------------------------------------------
+ * Replaces _latent_overshooting (base/algo.py:111-148; MoPoE override MRSSM_MoPoE/algo.py:69-108).  One open-loop run of
+ * up to OD steps per start step t = 1..T-2, all runs side by side: N = (T-2)*B columns, column n = (t-1)*B + b, row
+ * (k, n) of every [OD, N, .] tensor belongs to source time t+k and is padding when t+k >= T-1.
+ *   gather : actions_o / nonterminals_o / rewards_o / mask_o  <- the zero-padded slices the reference builds with
+ *            F.pad + torch.cat (base/algo.py:124-130); rewards_o and mask_o are optional.
+ *   kl_fwd : out[0] = scale * mean_rows max(sum_S KL(q || prior) * mask, free_nats)   (base/algo.py:138-141), q = the
+ *            DETACHED posterior of step t+k: post_means/post_stds [T-1,B,S] when n_experts == 0, else the product of the
+ *            experts `subset_mask` selects (bit e-1 = expert e; encoder.py:50-71).  row_scratch keeps the clamped row values.
+ *   kl_bwd : g_prior_means / g_prior_stds [OD,N,S] from g_out[0] and the forward's row_scratch. */
+typedef struct mrssm_overshoot_args {
+    int32_t T, B, S, A, OD;                     /* T = chunk length (T-1 model steps) */
+    int32_t n_experts;
+    uint32_t subset_mask;
+    float free_nats, scale;
+    const float *prior_means, *prior_stds;      /* [OD, N, S] */
+    const float *post_means, *post_stds;        /* [T-1, B, S] */
+    const float* exp_means[MRSSM_MAX_HEADS];    /* [T-1, B, S], index 1..n_experts */
+    const float* exp_stds[MRSSM_MAX_HEADS];
+    float* row_scratch;                         /* [OD*N] */
+    float* out;                                 /* [1] */
+    const float* g_out;                         /* [1] (device) */
+    float *g_prior_means, *g_prior_stds;        /* [OD, N, S] */
+    const float *actions, *nonterminals, *rewards;              /* [T,B,A], [T,B], [T,B] (rewards may be NULL) */
+    float *actions_o, *nonterminals_o, *rewards_o, *mask_o;     /* [OD,N,A], [OD,N] x3 */
+} mrssm_overshoot_args;
+
+int mrssm_overshoot_gather(const mrssm_overshoot_args* a, void* stream);
+int mrssm_overshoot_kl_fwd(const mrssm_overshoot_args* a, void* stream);
+int mrssm_overshoot_kl_bwd(const mrssm_overshoot_args* a, void* stream);
+
 /* ---- reconstruction loss: sum_features mean_{t,b} (y-o)^2  (observation_model.py:28-31,
  * base/algo.py:381-383).  n = element count, rows = (T-1)*B.  fwd writes *out; bwd writes
  * dy = (*g) * 2 (y-o) / rows. */

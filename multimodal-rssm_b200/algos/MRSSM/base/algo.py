@@ -40,8 +40,6 @@ class RSSM_base(nn.Module):
         self.cfg = cfg
         self.device = device
         self.observation_name = cfg.rssm.observation_names_enc[0]
-        if cfg.rssm.overshooting_kl_beta != 0:
-            raise NotImplementedError("latent overshooting is a 'next' row (SURVEY §8f#3)")
         self._init_models(device)
         self._init_param_list()
         self._init_optimizer()
@@ -120,6 +118,46 @@ class RSSM_base(nn.Module):
     def _calc_kl(self, states):
         return self._latent_terms(states)[3]
 
+    def _overshooting_targets(self, states):
+        """-> list of (n_experts, expert mask, target tensors): one open-loop run per entry.  RSSM / NN: the rollout's
+        posterior (reference base/algo.py:118); PoE: the product of all experts (MRSSM_PoE _get_posterior_states);
+        MoPoE: one run per modality subset (MRSSM_MoPoE/algo.py:78-80)."""
+        if self._refuse or self._kl_mode == 1:
+            table = self.transition_model._spec().table
+            names = list(states["expert_means"].keys())
+            experts = [states["expert_means"][n] for n in names] + [states["expert_std_devs"][n] for n in names]
+            masks = table.masks if self._kl_mode == 1 else [(1 << table.n_experts) - 1]
+            return [(table.n_experts, m, experts) for m in masks]
+        return [(0, 0, [states["posterior_means"], states["posterior_std_devs"]])]
+
+    def _latent_overshooting(self, actions, rewards, nonterminals, states):
+        """Reference base/algo.py:111-148 (MoPoE: MRSSM_MoPoE/algo.py:69-108).  actions / rewards / nonterminals are the
+        full chunk.  Every start step's open-loop run is one column block of a single imagination rollout."""
+        r = self.cfg.rssm
+        T, B, OD = actions.shape[0], actions.shape[1], r.overshooting_distance
+        beliefs, prior_states = states["beliefs"], states["prior_states"]
+        targets = self._overshooting_targets(states)
+        want_reward = r.overshooting_reward_scale != 0 and r.predict_reward    # zeroed otherwise (reference :200-201)
+        gspec = ops.OvershootSpec(T, B, r.state_size, actions.shape[2], OD, r.free_nats)
+        act_o, nt_o, rw_o, mask_o = ops.overshoot_gather(gspec, actions, nonterminals, rewards if want_reward else None,
+                                                         want_mask=want_reward)
+        h0 = beliefs[:T - 2].reshape(gspec.N, -1)            # beliefs[t-1] of every start t = 1..T-2, side by side
+        s0 = prior_states[:T - 2].reshape(gspec.N, -1)
+        kl_sum = None
+        for n_experts, mask, tg in targets:
+            o_beliefs, o_states, o_means, o_stds = self.transition_model(s0, act_o, h0, None, nt_o)[:4]
+            spec = ops.OvershootSpec(T, B, r.state_size, actions.shape[2], OD, r.free_nats,
+                                     scale=r.overshooting_kl_beta / len(targets), n_experts=n_experts, mask=mask)
+            kl = ops.OvershootKlFn.apply(spec, o_means, o_stds, *tg)
+            kl_sum = kl if kl_sum is None else kl_sum + kl
+        reward_loss = torch.zeros((), device=kl_sum.device)
+        if want_reward:                                       # on the last run, as the reference does
+            pred = self.reward_model(h_t=o_beliefs, s_t=o_states)["loc"] * mask_o
+            rows = pred.numel()
+            mse = ops.MseLossFn.apply(pred.reshape(rows, 1), rw_o.reshape(rows, 1), rows)
+            reward_loss = mse * ((1.0 / OD) * r.overshooting_reward_scale * (T - 1))
+        return kl_sum, reward_loss
+
     def _calc_observations_loss(self, observations_target, beliefs, posterior_states):
         raise NotImplementedError
 
@@ -143,6 +181,10 @@ class RSSM_base(nn.Module):
             reward_loss = self._obs_loss_from_mse(mse, 1)       # MSE, or -log N(r; loc, 1) with worldmodel_LogProbLoss
         else:                                                   # the reference zeroes it (:200-201): forward skipped
             reward_loss = torch.zeros((), device=kl_loss.device)
+        if self.cfg.rssm.overshooting_kl_beta != 0:             # reference :190-193
+            kl_over, reward_over = self._latent_overshooting(actions, rewards, nonterminals, states)
+            kl_loss_sum = kl_loss_sum + kl_over
+            reward_loss = reward_loss + reward_over
         return observations_loss, reward_loss, kl_loss_sum, kl_loss
 
     def _get_model_loss(self, observations_target, actions, rewards, nonterminals, states):

@@ -92,6 +92,15 @@ class LatentArgs(C.Structure):
         ("g_exp_means", _vp * MAX_HEADS), ("g_exp_stds", _vp * MAX_HEADS)]
 
 
+class OvershootArgs(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("T", "B", "S", "A", "OD", "n_experts")] + [
+        ("subset_mask", C.c_uint32), ("free_nats", C.c_float), ("scale", C.c_float)] + [(n, _vp) for n in (
+            "prior_means", "prior_stds", "post_means", "post_stds")] + [
+        ("exp_means", _vp * MAX_HEADS), ("exp_stds", _vp * MAX_HEADS)] + [(n, _vp) for n in (
+            "row_scratch", "out", "g_out", "g_prior_means", "g_prior_stds", "actions", "nonterminals", "rewards",
+            "actions_o", "nonterminals_o", "rewards_o", "mask_o")]
+
+
 # every symbol include/mrssm_b200.h declares: name -> argtypes (restype is int unless noted)
 _i64, _i32, _f = C.c_int64, C.c_int32, C.c_float
 SYMBOLS = {
@@ -136,6 +145,9 @@ SYMBOLS = {
     "mrssm_rollout_bwd": [C.POINTER(RolloutBwdArgs), _vp],
     "mrssm_latent_fwd": [C.POINTER(LatentArgs), _vp],
     "mrssm_latent_bwd": [C.POINTER(LatentArgs), _vp],
+    "mrssm_overshoot_gather": [C.POINTER(OvershootArgs), _vp],
+    "mrssm_overshoot_kl_fwd": [C.POINTER(OvershootArgs), _vp],
+    "mrssm_overshoot_kl_bwd": [C.POINTER(OvershootArgs), _vp],
     "mrssm_mse_fwd": [_vp, _vp, _i64, _i64, _vp, _vp, _vp],
     "mrssm_mse_bwd": [_vp, _vp, _i64, _i64, _vp, _vp, _vp],
     "mrssm_sqdiff": [_vp, _vp, _i64, _vp, _vp],
@@ -189,7 +201,7 @@ def _require_device():
 
 
 # kernels launched per C-ABI call (for the gpu_launches claim)
-_KERNELS_PER_CALL = {"mrssm_latent_fwd": 2, "mrssm_mse_fwd": 2, "mrssm_clip_adam": 3}
+_KERNELS_PER_CALL = {"mrssm_latent_fwd": 2, "mrssm_overshoot_kl_fwd": 2, "mrssm_mse_fwd": 2, "mrssm_clip_adam": 3}
 
 
 profile = None        # set to a list to record (name, tag, work, start_event, end_event) per call

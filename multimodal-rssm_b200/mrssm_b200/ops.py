@@ -721,6 +721,86 @@ class LatentFn(Function):
         return (None, gpm, gps, gqm, gqs, None, *gex_full)
 
 
+# ---- latent overshooting -----------------------------------------------------------------------------------------
+class OvershootSpec:
+    """T = chunk length (T-1 model steps), OD = overshooting distance; `mask` selects the experts whose product is the
+    target posterior (0: the rollout's own posterior tensors); out = scale * mean_rows max(masked KL, free_nats)."""
+
+    def __init__(self, T, B, S, A, OD, free_nats, scale=1.0, n_experts=0, mask=0):
+        self.T, self.B, self.S, self.A, self.OD = T, B, S, A, OD
+        self.free_nats, self.scale, self.n_experts, self.mask = float(free_nats), float(scale), n_experts, mask
+        self.N = (T - 2) * B
+
+    def args(self):
+        a = L.OvershootArgs()
+        a.T, a.B, a.S, a.A, a.OD = self.T, self.B, self.S, self.A, self.OD
+        a.n_experts, a.subset_mask, a.free_nats, a.scale = self.n_experts, self.mask, self.free_nats, self.scale
+        return a
+
+
+def overshoot_gather(spec, actions, nonterminals, rewards=None, want_mask=False):
+    """The padded, batch-concatenated open-loop inputs of base/algo.py:124-130 in one launch:
+    -> actions [OD,N,A], nonterminals [OD,N,1], rewards [OD,N]|None, seq mask [OD,N]|None."""
+    dev = actions.device
+    actions, nonterminals = _f32c(actions), _f32c(nonterminals)
+    assert actions.shape == (spec.T, spec.B, spec.A) and nonterminals.numel() == spec.T * spec.B
+    new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
+    a = spec.args()
+    act_o, nt_o = new(spec.OD, spec.N, spec.A), new(spec.OD, spec.N, 1)
+    rw_o = new(spec.OD, spec.N) if rewards is not None else None
+    mk_o = new(spec.OD, spec.N) if want_mask else None
+    rewards = None if rewards is None else _f32c(rewards)
+    a.actions, a.nonterminals, a.rewards = L.ptr(actions), L.ptr(nonterminals), L.ptr(rewards)
+    a.actions_o, a.nonterminals_o, a.rewards_o, a.mask_o = L.ptr(act_o), L.ptr(nt_o), L.ptr(rw_o), L.ptr(mk_o)
+    L.call("mrssm_overshoot_gather", C.byref(a))
+    return act_o, nt_o, rw_o, mk_o
+
+
+class OvershootKlFn(Function):
+    """apply(spec, prior_means, prior_stds [OD,N,S], *targets) -> scalar.  targets: (post_means, post_stds) when
+    spec.n_experts == 0, else (*exp_means, *exp_stds), each [T-1,B,S]; the targets are constants (detached in the
+    reference, base/algo.py:129)."""
+
+    @staticmethod
+    def forward(ctx, spec, prior_means, prior_stds, *targets):
+        pm, ps = _f32c(prior_means), _f32c(prior_stds)
+        tg = [_f32c(t.detach()) for t in targets]
+        assert pm.shape == (spec.OD, spec.N, spec.S) and all(t.shape == (spec.T - 1, spec.B, spec.S) for t in tg)
+        dev = pm.device
+        scratch = torch.empty(spec.OD * spec.N, device=dev, dtype=torch.float32)
+        out = torch.empty((), device=dev, dtype=torch.float32)
+        a = OvershootKlFn._args(spec, pm, ps, tg, scratch)
+        a.out = L.ptr(out)
+        L.call("mrssm_overshoot_kl_fwd", C.byref(a))
+        ctx.spec = spec
+        ctx.save_for_backward(pm, ps, scratch, *tg)
+        return out
+
+    @staticmethod
+    def _args(spec, pm, ps, tg, scratch):
+        a = spec.args()
+        a.prior_means, a.prior_stds, a.row_scratch = L.ptr(pm), L.ptr(ps), L.ptr(scratch)
+        if spec.n_experts:
+            E = spec.n_experts
+            assert len(tg) == 2 * E
+            for e in range(E):
+                a.exp_means[e + 1], a.exp_stds[e + 1] = L.ptr(tg[e]), L.ptr(tg[E + e])
+        else:
+            a.post_means, a.post_stds = L.ptr(tg[0]), L.ptr(tg[1])
+        return a
+
+    @staticmethod
+    def backward(ctx, g):
+        spec = ctx.spec
+        pm, ps, scratch, *tg = ctx.saved_tensors
+        a = OvershootKlFn._args(spec, pm, ps, tg, scratch)
+        g = _f32c(g)
+        gpm, gps = torch.empty_like(pm), torch.empty_like(ps)
+        a.g_out, a.g_prior_means, a.g_prior_stds = L.ptr(g), L.ptr(gpm), L.ptr(gps)
+        L.call("mrssm_overshoot_kl_bwd", C.byref(a))
+        return (None, gpm, gps, *([None] * len(tg)))
+
+
 # ---- tensor-core (bf16) primitives --------------------------------------------------------------------------
 def pad8(c):
     return (c + 7) // 8 * 8

@@ -24,7 +24,9 @@ def _product_cfg(oc, B, T, device):
                            belief_size=oc.belief_size, state_size=oc.state_size, hidden_size=oc.hidden_size,
                            free_nats=oc.free_nats, kl_balancing_alpha=oc.kl_balancing_alpha,
                            global_kl_beta=oc.global_kl_beta, kl_beta=oc.kl_beta, grad_clip_norm=oc.grad_clip_norm,
-                           model_learning_rate=oc.lr, adam_epsilon=oc.adam_eps, predict_reward=oc.predict_reward)
+                           model_learning_rate=oc.lr, adam_epsilon=oc.adam_eps, predict_reward=oc.predict_reward,
+                           overshooting_distance=oc.overshooting_distance, overshooting_kl_beta=oc.overshooting_kl_beta,
+                           overshooting_reward_scale=oc.overshooting_reward_scale)
 
 
 def unflatten(flat):
@@ -79,7 +81,8 @@ def build_product(oc, B, T, device, seed=0, bf16=False):
 def product_step(model, oc, batch, noise, device):
     from mrssm_b200.noise import FixedNoise
     dev = torch.device(device)
-    streams = dict(prior=noise["eps_prior"].to(dev), post=noise["eps_post"].to(dev))
+    streams = dict(prior=[noise["eps_prior"].to(dev)] + [e.to(dev) for e in noise.get("eps_over", [])],   # one per open-loop run
+                   post=noise["eps_post"].to(dev))
     if oc.fusion in ("PoE", "MoPoE"):
         streams["dec"] = noise["eps_dec"].to(dev)
     cap = {}

@@ -23,7 +23,8 @@ def test_train_step_matches_oracle(fusion, kw):
     assert out["worst_grad_err"] < 2 * RTOL
 
 
-@pytest.mark.parametrize("name", ["mopoe", "poe", "nn", "single", "mopoe_clip", "poe_noalpha", "mopoe_reward"])
+@pytest.mark.parametrize("name", ["mopoe", "poe", "nn", "single", "mopoe_clip", "poe_noalpha", "mopoe_reward",
+                                  "mopoe_over", "poe_over", "single_over"])
 def test_train_step_matches_reference_fixture(name, golden_dir):
     """Directly against tests/golden/train_*.pt (outputs of the unmodified reference)."""
     rec = torch.load(os.path.join(golden_dir, f"train_{name}.pt"), weights_only=False)
