@@ -363,6 +363,33 @@ int mrssm_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, int
                     float beta1, float beta2, float eps, float max_norm, float grad_scale,
                     float* partial, float* norm_out, void* stream);
 
+/* ---- replay-buffer sampling on the device -------------------------------------------------------------
+ * Replaces ExperienceReplay_Multimodal._retrieve_batch for image observations (utils/replay_buffer/memory.py:191-208):
+ * gather by index -> crop (data_augment.py:158-174) -> + PCA colour shift + Gaussian noise, clip to [0,255]
+ * (data_augment.py:178-210) -> quantise / dequantise (utils/processing/image_processing.py:5-11), one pass:
+ *   x   = frames[idx[row], c, y+dh, x+dw]
+ *   x   = clip(x + delta[c] + gauss * gauss_scale * 255, 0, 255)        (only when delta / gauss / gauss_scale > 0 is given)
+ *   out = floor(x / 2^(8-bits)) / 2^bits - 0.5 + u / 2^bits
+ * gauss ~ N(0,1) and u ~ U[0,1) come from the caller's tensors when given (parity tests), else from a counter-based hash of
+ * (seed, element index).  idx holds rows = L*n frame slots in the reference's order (row = l*n + b).  bit_depth 0 skips
+ * the last line (binary mask images are only gathered and cropped, memory.py:199-201). */
+typedef struct mrssm_replay_gather_args {
+    const uint8_t* frames;                      /* [size, C, Hs, Ws] device */
+    const int64_t* idx;                         /* [rows] device */
+    int64_t rows;
+    int32_t C, Hs, Ws, H, W, dh, dw, bit_depth; /* output [rows, C, H, W], crop origin (dh, dw) */
+    const float* delta;                         /* [C] device or NULL */
+    const float* gauss;                         /* [rows, C, H, W] or NULL */
+    float gauss_scale;
+    const float* uniform;                       /* [rows, C, H, W] or NULL */
+    uint64_t seed;
+    float* out;
+} mrssm_replay_gather_args;
+
+int mrssm_replay_gather_u8(const mrssm_replay_gather_args* a, void* stream);
+/* fp32 rows (vector observations, actions, rewards, nonterminals; memory.py:193-196,210-212): out[r,:] = src[idx[r],:] */
+int mrssm_gather_rows(const float* src, const int64_t* idx, int64_t rows, int32_t K, float* out, void* stream);
+
 /* ---- input pipeline: replay-buffer frames are uint8 on the host (utils/replay_buffer/memory.py:160-168); sample()
  * moves them to the device and normalises there (memory.py:197-208 -> utils/processing/image_processing.py:5-11):
  *   dst = floor(u8 / 2^(8-bits)) / 2^bits - 0.5 + u / 2^bits,  u ~ U[0,1).

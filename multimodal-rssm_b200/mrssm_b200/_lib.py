@@ -101,6 +101,12 @@ class OvershootArgs(C.Structure):
             "actions_o", "nonterminals_o", "rewards_o", "mask_o")]
 
 
+class ReplayGatherArgs(C.Structure):
+    _fields_ = [("frames", _vp), ("idx", _vp), ("rows", C.c_int64)] + [(n, C.c_int32) for n in (
+        "C", "Hs", "Ws", "H", "W", "dh", "dw", "bit_depth")] + [
+        ("delta", _vp), ("gauss", _vp), ("gauss_scale", C.c_float), ("uniform", _vp), ("seed", C.c_uint64), ("out", _vp)]
+
+
 # every symbol include/mrssm_b200.h declares: name -> argtypes (restype is int unless noted)
 _i64, _i32, _f = C.c_int64, C.c_int32, C.c_float
 SYMBOLS = {
@@ -152,6 +158,8 @@ SYMBOLS = {
     "mrssm_mse_bwd": [_vp, _vp, _i64, _i64, _vp, _vp, _vp],
     "mrssm_sqdiff": [_vp, _vp, _i64, _vp, _vp],
     "mrssm_clip_adam": [_vp, _vp, _vp, _vp, _i64, _i32, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp],
+    "mrssm_replay_gather_u8": [C.POINTER(ReplayGatherArgs), _vp],
+    "mrssm_gather_rows": [_vp, _vp, _i64, _i32, _vp, _vp],
     "mrssm_normalize_image_u8": [_vp, _i64, _i32, _vp, C.c_uint64, _vp, _vp],
     "mrssm_transpose": [_vp, _i64, _i64, _i64, _vp, _vp],
     "mrssm_copy2d": [_vp, _i64, _i64, _i64, _vp, _vp],

@@ -1,0 +1,135 @@
+"""CPU: the replay buffer's host logic and oracle/replay_oracle.py against tests/golden/replay_*.pt (outputs of the
+unmodified reference buffer, tests/golden/make_replay_golden.py).
+
+* episode files -> stores: the product's loader fills a (host) store bit-identical to the reference's;
+* chunk starts and augmentation choices: the product's `_sample_idx` / `_plan_batch` consume numpy's RNG exactly as the
+  reference does (same slots, and the RNG ends in the same state);
+* the batch math: the oracle fed with those choices and torch's RNG stream in the reference's order reproduces the
+  reference batches bit for bit.
+The device half (`sample` itself) is covered by tests/test_gpu_replay.py; on a host-only store it must fail loudly."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import replay_oracle as RO
+from tests import replay_util as R
+
+
+def _buffer(cfg, files, device="cpu"):
+    from utils.replay_buffer.memory import ExperienceReplay_Multimodal
+    D = ExperienceReplay_Multimodal(**R.buffer_kwargs(cfg, torch.device(device)))
+    D.file_names += files
+    for f in files:
+        D._set_data_to_buffer(f)
+    if D.pca_scales is not None:
+        D._set_color_aug_params()
+    return D
+
+
+def _load(name, golden_dir, tmp_path, device="cpu"):
+    rec = torch.load(os.path.join(golden_dir, f"replay_{name}.pt"), weights_only=False)
+    cfg = R.CONFIGS[name]
+    files = R.write_dataset(str(tmp_path), cfg)
+    assert [os.path.basename(f) for f in files] == rec["files"]
+    return rec, cfg, _buffer(cfg, files, device)
+
+
+def oracle_batch(D, cfg, vec_idxs, plan, n, L):
+    """The oracle on the buffer's stores with the planned choices; noise from torch's global RNG in the reference's order
+    (per image modality: randn for the Gaussian noise when its scale is > 0, then rand for the dequantisation)."""
+    obs = {}
+    for name in D.observation_names:
+        store = D.observations[name].cpu()
+        if name not in plan:
+            obs[name] = RO.gather_rows(store, vec_idxs, n, L)
+            continue
+        p = plan[name]
+        C = store.shape[1]
+        hw = (p["side"], p["side"]) if p["crop"] is not None else tuple(store.shape[-2:])
+        shape = (L, n, C, *hw)
+        gauss = torch.randn(*shape) if p["gauss_scale"] > 0 else None
+        uniform = None if p["plain"] else torch.rand(shape)
+        obs[name] = RO.gather_image(store, vec_idxs, n, L, crop=p["crop"], side=p["side"], delta=p["delta"], gauss=gauss,
+                                    gauss_scale=p["gauss_scale"], uniform=uniform, bit_depth=D.bit_depth, normalise=not p["plain"])
+    return (obs, RO.gather_rows(D.actions.cpu(), vec_idxs, n, L), RO.gather_rows(D.rewards.cpu(), vec_idxs, n, L),
+            RO.gather_rows(D.nonterminals.cpu(), vec_idxs, n, L))
+
+
+@pytest.mark.parametrize("name", ["default", "augment"])
+def test_loader_fills_the_store_like_the_reference(name, golden_dir, tmp_path):
+    rec, cfg, D = _load(name, golden_dir, tmp_path)
+    assert (D.idx, D.full, D.steps, D.episodes) == (rec["idx"], rec["full"], rec["steps"], rec["episodes"])
+    for k, d in rec["stores"].items():
+        assert D.observations[k].dtype == (torch.uint8 if "image" in k else torch.float32)
+        R.assert_digest(D.observations[k][:D.idx].float(), d)
+    assert torch.equal(D.actions[:D.idx], rec["actions"])
+    assert torch.equal(D.rewards[:D.idx], rec["rewards"])
+    assert torch.equal(D.nonterminals[:D.idx], rec["nonterminals"])
+    for k, (lam, vec) in rec["pca"].items():
+        torch.testing.assert_close(D.lambd_eigen_values[k].cpu(), lam, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(D.p_eigen_vectors[k].cpu(), vec, rtol=1e-5, atol=1e-6)
+
+
+def test_spiral_crop_table_matches_reference(golden_dir):
+    from utils.replay_buffer.data_augment import spiral_offset
+    rec = torch.load(os.path.join(golden_dir, "replay_augment.pt"), weights_only=False)
+    assert [spiral_offset(i) for i in range(len(rec["spiral"]))] == [tuple(x) for x in rec["spiral"]]
+
+
+@pytest.mark.parametrize("name", ["default", "augment"])
+def test_host_plan_and_oracle_reproduce_reference_batches(name, golden_dir, tmp_path):
+    rec, cfg, D = _load(name, golden_dir, tmp_path)
+    for s in rec["samples"]:
+        np.random.seed(s["seed"])
+        torch.manual_seed(s["seed"])
+        idxs = np.asarray([D._sample_idx(R.L) for _ in range(R.N)])
+        assert np.array_equal(idxs, s["idxs"])
+        vec_idxs, plan = D._plan_batch(idxs)
+        obs, actions, rewards, nonterminals = oracle_batch(D, cfg, vec_idxs, plan, R.N, R.L)
+        for k, d in s["obs"].items():
+            R.assert_digest(obs[k], d)
+        assert torch.equal(actions, s["actions"]) and torch.equal(rewards, s["rewards"])
+        assert torch.equal(nonterminals, s["nonterminals"])
+        assert float(np.random.rand()) == s["np_next"]          # both RNG streams were consumed exactly as the reference does
+        assert float(torch.rand(())) == s["torch_next"]
+
+
+def test_sample_idx_never_crosses_the_write_position():
+    from utils.replay_buffer.memory import ExperienceReplay_Multimodal
+    D = ExperienceReplay_Multimodal(size=20, observation_names=["v"], observation_shapes={"v": [2]}, action_size=1)
+    np.random.seed(0)
+    D.idx, D.full = 7, True                    # wrapped buffer: chunks may wrap around the end but not run over slot 7
+    for _ in range(300):
+        idxs = D._sample_idx(6)
+        assert len(idxs) == 6 and D.idx not in idxs[1:]
+        assert np.array_equal(idxs, np.arange(idxs[0], idxs[0] + 6) % 20)
+    D.idx, D.full = 13, False                  # partly filled: only slots [0, idx) hold data
+    for _ in range(300):
+        idxs = D._sample_idx(5)
+        assert idxs[0] >= 0 and idxs[-1] < 13
+
+
+def test_append_and_episode_overflow():
+    from utils.replay_buffer.memory import ExperienceReplay_Multimodal
+    D = ExperienceReplay_Multimodal(size=3, observation_names=["image", "v"], observation_shapes={"image": [3, 64, 64], "v": [2]},
+                                    action_size=2)
+    frame = np.random.RandomState(0).rand(3, 64, 64).astype(np.float32) - 0.5
+    for i in range(4):
+        D.append({"image": frame, "v": np.array([i, -i], dtype=np.float32)}, np.array([1.0, 2.0]), 0.5 * i, i == 2)
+    assert (D.idx, D.full, D.steps, D.episodes) == (1, True, 4, 1)
+    expect = np.clip(np.floor((frame + 0.5) * 32) * 8, 0, 255).astype(np.uint8)     # image_processing.py:15-16
+    assert np.array_equal(D.observations["image"][0].numpy(), expect)
+    assert D.observations["v"][0].tolist() == [3.0, -3.0] and float(D.rewards[0]) == 1.5
+    assert D.nonterminals[:, 0].tolist() == [1.0, 1.0, 0.0]
+
+
+def test_sample_fails_loudly_without_a_device(golden_dir, tmp_path):
+    """No CPU fallback: the gather kernels are the only implementation of `sample`."""
+    if torch.cuda.is_available():
+        pytest.skip("host-only check")
+    _, _, D = _load("default", golden_dir, tmp_path)
+    np.random.seed(0)
+    with pytest.raises((RuntimeError, AssertionError)):
+        D.sample(R.N, R.L)
