@@ -4,8 +4,9 @@ Mirrors what ``ExperienceReplay_Multimodal.sample`` hands to ``optimize`` (utils
 frames live on the HOST as uint8 (memory.py:160-168); ``sample`` moves the gathered chunk to the device as uint8 and
 converts / normalises there (memory.py:197-208, image_processing.py:5-11), returning time-major fp32
 ``[obs dict, actions, rewards, nonterminals]``.  Here the host buffers are pinned, the copy of batch k+1 runs on a side
-stream while step k computes, and the normalisation is one kernel (``mrssm_normalize_image_u8``).  Index sampling and
-augmentation of the replay buffer are out of scope: the source is handed ready-made chunks.
+stream while step k computes, and the normalisation is one kernel (``mrssm_normalize_image_u8``).  This source is handed
+ready-made chunks (bench.py's e2e leg); the full replay buffer — chunk sampling, augmentation, device-resident uint8 frame
+store — is ``utils/replay_buffer/memory.py``.
 """
 import contextlib
 import os
