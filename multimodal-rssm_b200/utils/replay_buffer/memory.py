@@ -188,13 +188,16 @@ class ExperienceReplay_Multimodal:
         L.call("mrssm_gather_rows", L.ptr(store), L.ptr_any(slots), rows, K, L.ptr(out))
         return out
 
-    def _plan_batch(self, idxs):
+    def _plan_batch(self, idxs, crop_idx=None, pca_rand=None):
         """Host half of _retrieve_batch: the slot list (row = l * n + b) and, per image modality, the augmentation choices,
         drawn from numpy's global RNG in the reference's order (memory.py:191-208, data_augment.py:178-208).
+        A given crop_idx / pca_rand (three coefficients) replaces the corresponding draw, as in the reference's
+        augment_image_data (used by utils/evaluation/estimate_states.py).
         -> (vec_idxs int64 [L*n], {name: dict(crop=(dh, dw)|None, side, delta=[C] cpu tensor|None, gauss_scale, plain)})"""
         vec_idxs = np.ascontiguousarray(idxs.transpose().reshape(-1)).astype(np.int64)
         assert vec_idxs.min() >= 0 and vec_idxs.max() < self.size
-        pca_rand = None
+        if pca_rand is not None:
+            pca_rand = np.asarray(torch.as_tensor(pca_rand).cpu(), dtype=np.float64)
         plan = {}
         for name in self.observation_names:
             if "image" not in name:
@@ -203,8 +206,8 @@ class ExperienceReplay_Multimodal:
             side = crop_size_of(name)
             crop = None
             if self.n_crop is not None:
-                crop_idx = np.random.randint(0, self.n_crop)
-                crop = crop_origin(crop_idx, store.shape[-2:], (side, side), self.dh_base, self.dw_base)
+                pos = np.random.randint(0, self.n_crop) if crop_idx is None else crop_idx
+                crop = crop_origin(pos, store.shape[-2:], (side, side), self.dh_base, self.dw_base)
             plain = "bin" in name                   # binary masks: cropped only, neither augmented nor normalised
             gauss_scale, delta = 0.0, None
             if not plain:
@@ -219,8 +222,8 @@ class ExperienceReplay_Multimodal:
             plan[name] = dict(crop=crop, side=side, delta=delta, gauss_scale=gauss_scale, plain=plain)
         return vec_idxs, plan
 
-    def _retrieve_batch(self, idxs, n, L_):
-        vec_idxs, plan = self._plan_batch(idxs)
+    def _retrieve_batch(self, idxs, n, L_, crop_idx=None, pca_rand=None):
+        vec_idxs, plan = self._plan_batch(idxs, crop_idx, pca_rand)
         rows = n * L_
         slots = torch.from_numpy(vec_idxs).to(self.device, non_blocking=True)
         observations = {}

@@ -126,7 +126,8 @@ def test_in_kernel_noise(golden_dir, tmp_path):
     p = plan[R.IMAGE]
     ref = RO.gather_image(D.observations[R.IMAGE].cpu(), vec_idxs, R.N, R.L, crop=p["crop"], side=p["side"], delta=p["delta"],
                           uniform=torch.zeros(R.L, R.N, 3, 64, 64), bit_depth=5)
-    assert torch.equal(torch.floor((c.cpu() + 0.5) * 32), torch.floor((ref + 0.5) * 32 + 0.5 / 32))
+    noise = (c.cpu() + 0.5) * 32 - (ref + 0.5) * 32             # ref carries zero noise: the level itself
+    assert float(noise.min()) >= 0.0 and float(noise.max()) <= 1.0      # 1.0 only when fp32 rounds level + u up (u -> 1)
     # binary masks come back raw (0 / 255), cropped
     m = batches[0][R.BIN]
     assert m.shape == (R.L, R.N, 1, 64, 64) and set(m.unique().tolist()) <= {0.0, 255.0}

@@ -1,0 +1,119 @@
+"""-m gpu: the callers either side of the hot path, end to end on the device —
+`algos/MRSSM/MRSSM/train.py` (episode directories -> device-resident replay buffers -> optimize / validation / checkpoint,
+reference train.py:9-58) and `utils/evaluation/estimate_states.py` (B = 1, T = episode length `estimate_state` over every
+stored episode, reference estimate_states.py:60-91), plus B = 1 parity of that path against the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mrssm_oracle as O
+from tests import parity_util as U
+from tests import replay_util as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _cfg(use_amp):
+    from mrssm_b200.config import hot_path_config, to_attr
+    cfg = hot_path_config(fusion="MoPoE", batch_size=3, chunk_size=4, device=DEV)
+    cfg.train.use_amp = use_amp
+    cfg.train.experience_size = R.SIZE
+    cfg.train.augmentation = to_attr(dict(n_crop=1, dh_base=1, dw_base=1, noise_scales=[0.0], pca_scales=[0.0]))
+    cfg.train.train_data_path, cfg.train.validation_data_path = "train", "val"
+    cfg.train.train_iteration, cfg.train.validation_interval, cfg.train.checkpoint_interval = 4, 2, 4
+    cfg.train.model_path = None
+    return cfg
+
+
+@pytest.mark.parametrize("use_amp", [False, True])
+def test_train_driver_then_estimate_states(tmp_path, use_amp):
+    from algos.MRSSM.MRSSM.algo import build_RSSM
+    from algos.MRSSM.MRSSM.train import train
+    from utils.evaluation import estimate_states as ES
+    cfg = _cfg(use_amp)
+    R.write_dataset(str(tmp_path / "train"), R.CONFIGS["default"], seed=5)
+    R.write_dataset(str(tmp_path / "val"), R.CONFIGS["default"], seed=6)
+    results = tmp_path / "results"
+    os.makedirs(results)
+    np.random.seed(0)
+    model = train(cfg, str(tmp_path), str(results), torch.device(DEV))
+    ckpt = str(results / "models_4.pth")
+    assert os.path.exists(ckpt)
+    assert model.itr_optim == 4 and torch.isfinite(model.model_loss).item()
+    assert all(np.isfinite(float(v)) for v in model.validation_info.values())
+
+    states = ES.run(cfg, str(tmp_path), torch.device(DEV), build_RSSM, ckpt)
+    assert os.path.exists(str(results / "states_models_4.npy"))
+    assert len(states) == len(R.EPISODES)
+    lengths = sorted(st["beliefs"].shape[0] + 1 for st in states.values())
+    assert lengths == sorted(R.EPISODES)
+    for name, st in states.items():
+        T1 = st["beliefs"].shape[0]
+        assert name.endswith(".npy") and st["beliefs"].shape == (T1, 1, 200) and st["posterior_means"].shape == (T1, 1, 30)
+        assert all(np.isfinite(v).all() for k, v in st.items() if isinstance(v, np.ndarray))
+        assert set(st["expert_means"].keys()) == {"prior_expert", R.IMAGE, R.VEC}
+
+
+def test_episode_data_is_the_stored_episode(tmp_path):
+    from algos.MRSSM.MRSSM.train import get_dataset_loader
+    from utils.evaluation import estimate_states as ES
+    cfg = _cfg(False)
+    R.write_dataset(str(tmp_path / "train"), R.CONFIGS["default"], seed=5)
+    D = get_dataset_loader(cfg, str(tmp_path), torch.device(DEV), "train")
+    bounds = ES.episode_bounds(D)
+    assert bounds[0] == 0 and bounds[-1] == D.idx == sum(R.EPISODES) and len(bounds) == len(R.EPISODES) + 1
+    for e in range(len(R.EPISODES)):
+        obs, actions, rewards, nonterminals = ES.get_episode_data(D, e, crop_idx=0)
+        s, t = int(bounds[e]), int(bounds[e + 1])
+        T = t - s
+        assert obs[R.IMAGE].shape == (T, 1, 3, 64, 64) and actions.shape == (T, 1, 3)
+        assert rewards.shape == (T, 1) and nonterminals.shape == (T, 1, 1)
+        # 5-bit quantisation level of every stored pixel + dequantisation noise in [0, 1] levels (1 only when fp32 rounds
+        # level + u, u -> 1, up — the reference's normalize_image has the same property)
+        noise = (obs[R.IMAGE][:, 0] + 0.5) * 32 - torch.floor(D.observations[R.IMAGE][s:t].float() / 8)
+        assert float(noise.min()) >= 0.0 and float(noise.max()) <= 1.0 and 0.45 < float(noise.mean()) < 0.55
+        assert torch.equal(obs[R.VEC][:, 0], D.observations[R.VEC][s:t])
+        assert torch.equal(actions[:, 0], D.actions[s:t]) and torch.equal(rewards[:, 0], D.rewards[s:t])
+        assert float(nonterminals[-1]) == 0.0 and float(nonterminals[:-1].min()) == 1.0
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_single_sequence_estimate_state_matches_oracle(tmp_path, bf16):
+    """B = 1: one stored episode through encoders + observe rollout against the oracle with shared noise.  fp32 mode: rtol
+    1e-3; bf16 mode: the stated bf16 tolerance of test_gpu_rollout_configs.py (mean abs error <= 1e-2, max <= 0.25)."""
+    from algos.MRSSM.MRSSM.train import get_dataset_loader
+    from mrssm_b200 import ops
+    from mrssm_b200.noise import FixedNoise
+    from utils.evaluation import estimate_states as ES
+    R.write_dataset(str(tmp_path / "train"), R.CONFIGS["default"], seed=5)
+    D = get_dataset_loader(_cfg(False), str(tmp_path), torch.device(DEV), "train")
+    oc = U.oracle_cfg("MoPoE")
+    obs, actions, rewards, nonterminals = ES.get_episode_data(D, 0, crop_idx=0)
+    T = actions.shape[0]
+    model, P = U.build_product(oc, 1, T, DEV, bf16=bf16)
+    tgt = model._clip_obs(obs, idx_start=1)
+    g = torch.Generator().manual_seed(4)
+    eps_prior, eps_post = torch.randn(T - 1, 1, oc.state_size, generator=g), torch.randn(T - 1, 1, oc.state_size, generator=g)
+    with torch.no_grad():
+        ref = O.estimate_state(P, oc, {k: v.cpu() for k, v in tgt.items()}, actions[:-1].cpu(), nonterminals[:-1].cpu(),
+                               eps_prior, eps_post, det=False)
+        ops.set_bf16_mode(bf16)
+        try:
+            with FixedNoise(prior=eps_prior.to(DEV), post=eps_post.to(DEV)):
+                st = model.estimate_state(tgt, actions[:-1], rewards, nonterminals[:-1])
+        finally:
+            ops.set_bf16_mode(False)
+    if not bf16:
+        U.assert_states_close(st, ref, 1e-3, 2e-5)
+        return
+    for k, v in ref.items():
+        items = v.items() if isinstance(v, dict) else [(None, v)]
+        for n, t in items:
+            if t is None:
+                continue
+            mine = (st[k][n] if n is not None else st[k]).cpu()
+            err = (mine - t).abs()
+            assert torch.isfinite(mine).all() and float(err.mean()) <= 1e-2 and float(err.max()) <= 0.25, (k, n, float(err.max()))
