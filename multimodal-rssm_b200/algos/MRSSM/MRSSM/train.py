@@ -1,53 +1,66 @@
-"""Training driver (reference algos/MRSSM/MRSSM/train.py): replay buffers from episode directories, then
-optimize / validation / checkpoint on the reference's schedule.  The experiment logger (hydra / wandb set-up,
-utils/logger.py) is control plane and not part of this package: `run` takes the three values it would produce."""
+"""Training driver over device-resident replay buffers.
+
+Interface of the reference's algos/MRSSM/MRSSM/train.py (`get_dataset_loader`, `train`, `run`; :9-66): two buffers are filled
+from episode directories, then `optimize` runs `train_iteration` times with `validation` every `validation_interval` and a
+checkpoint every `checkpoint_interval` iterations.  The experiment logger (hydra / wandb, utils/logger.py) is control plane
+and not part of this package, so `run` takes the three values it would hand over.  One process drives one GPU; under
+torchrun pass `dp=mrssm_b200.dist.DataParallel` and every rank samples its own chunks."""
 import os
 
 import torch
 
+from algos.MRSSM.MRSSM.algo import build_RSSM
 from utils.replay_buffer.memory import ExperienceReplay_Multimodal, load_dataset
 
-from algos.MRSSM.MRSSM.algo import build_RSSM
+
+def _buffer_options(cfg):
+    """Constructor arguments of the replay buffer, gathered from the three config groups that hold them."""
+    aug, env, rssm = cfg.train.augmentation, cfg.env, cfg.rssm
+    wanted = dict.fromkeys(list(rssm.observation_names_enc) + list(rssm.observation_names_rec))     # union, first-seen order
+    opts = {key: aug[key] for key in ("n_crop", "dh_base", "dw_base", "noise_scales", "pca_scales")}
+    opts.update(size=cfg.train.experience_size, observation_names=list(wanted), observation_shapes=env.observation_shapes,
+                action_name=env.action_name, action_size=env.action_size, bit_depth=env.bit_depth)
+    return opts
 
 
 def get_dataset_loader(cfg, cwd, device, dataset_path):
-    observation_names = list(set(list(cfg.rssm.observation_names_enc) + list(cfg.rssm.observation_names_rec)))
-    aug = cfg.train.augmentation
-    D = ExperienceReplay_Multimodal(size=cfg.train.experience_size, observation_names=observation_names,
-                                    observation_shapes=cfg.env.observation_shapes, n_crop=aug.n_crop, dh_base=aug.dh_base,
-                                    dw_base=aug.dw_base, noise_scales=aug.noise_scales, pca_scales=aug.pca_scales,
-                                    action_name=cfg.env.action_name, action_size=cfg.env.action_size,
-                                    bit_depth=cfg.env.bit_depth, device=device)
-    load_dataset(cfg, cwd, D, dataset_path)
-    return D
+    """A buffer on `device` holding every episode found under dataset_path (one directory or a list of them)."""
+    buffer = ExperienceReplay_Multimodal(device=device, **_buffer_options(cfg))
+    load_dataset(cfg, cwd, buffer, dataset_path)
+    return buffer
+
+
+def _restore(model, cfg, cwd):
+    if cfg.train.model_path is None:
+        return
+    path = os.path.join(cwd, cfg.train.model_path)
+    if not os.path.exists(path):
+        raise NotImplementedError("{} is not exist".format(path))
+    model.load_model(path)
+
+
+def _due(itr, every):
+    return bool(every) and itr % every == 0
 
 
 def train(cfg, cwd, results_dir, device, dp=None):
-    """dp: optional mrssm_b200.dist.DataParallel factory applied to the model (one process per GPU)."""
-    print("Initialize training environment and experience replay memory")
-    D = get_dataset_loader(cfg, cwd, device, cfg.train.train_data_path)
-    D_val = get_dataset_loader(cfg, cwd, device, cfg.train.validation_data_path)
-    print("Initialise model parameters randomly")
+    buffers = {split: get_dataset_loader(cfg, cwd, device, cfg.train[split + "_data_path"]) for split in ("train", "validation")}
     model = build_RSSM(cfg, device)
-    if cfg.train.model_path is not None:
-        model_path = os.path.join(cwd, cfg.train.model_path)
-        if not os.path.exists(model_path):
-            raise NotImplementedError("{} is not exist".format(model_path))
-        model.load_model(model_path)
+    _restore(model, cfg, cwd)
     if dp is not None:
         dp(model)
-    for itr in range(1, cfg.train.train_iteration + 1):
-        model.optimize(D)
-        if itr % cfg.train.validation_interval == 0:
-            model.validation(D_val)
-        if itr % cfg.train.checkpoint_interval == 0:
+    last = cfg.train.train_iteration
+    for itr in range(1, last + 1):
+        model.optimize(buffers["train"])
+        if _due(itr, cfg.train.validation_interval):
+            model.validation(buffers["validation"])
+        if _due(itr, cfg.train.checkpoint_interval):
             model.save_model(results_dir, itr)
     return model
 
 
 def run(cfg, cwd=None, results_dir=None, device=None):
-    cwd = os.getcwd() if cwd is None else cwd
-    results_dir = cwd if results_dir is None else results_dir
-    device = torch.device(cfg.main.device) if device is None else device
+    cwd = cwd or os.getcwd()
+    results_dir = results_dir or cwd
     os.makedirs(results_dir, exist_ok=True)
-    return train(cfg, cwd, results_dir, device)
+    return train(cfg, cwd, results_dir, device or torch.device(cfg.main.device))
