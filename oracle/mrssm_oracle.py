@@ -57,6 +57,7 @@ class OracleConfig:
     adam_eps: float = 1e-7
     grad_clip_norm: float = 100.0
     predict_reward: bool = False     # base/algo.py:200-201: False zeroes the reward loss (shipped default)
+    normalization: Optional[str] = None   # None | "BatchNorm" (64x64 image encoder / decoder, encoder.py:324-337, observation_model.py:75-86)
     overshooting_distance: int = 0   # latent overshooting (base/algo.py:111-148, MoPoE/algo.py:69-108); kl_beta 0 = off
     overshooting_kl_beta: float = 0.0
     overshooting_reward_scale: float = 0.0
@@ -113,9 +114,21 @@ def param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
         lin(prefix + "fc1", H, n_in)
         lin(prefix + "fc2", 2 * S, H)
 
+    def batch_norm(prefix, c):                      # affine parameters; the running statistics are buffers (make_buffers)
+        sh[prefix + ".weight"] = (c,)
+        sh[prefix + ".bias"] = (c,)
+
     def image_encoder(prefix, shape):
         c = shape[0]
         chans = [c, 32, 64, 128, 256] if shape[1] == 64 else [c, 16, 32, 64, 128, 256]
+        if cfg.normalization == "BatchNorm":        # Conv2d(bias=False), BatchNorm2d, ReLU triples (encoder.py:324-337)
+            assert shape[1] == 64, "BatchNorm oracle: 64x64 images only"
+            for i in range(len(chans) - 1):
+                sh[f"{prefix}conv.{3 * i}.weight"] = (chans[i + 1], chans[i], 4, 4)
+                batch_norm(f"{prefix}conv.{3 * i + 1}", chans[i + 1])
+            if cfg.embedding_size["image"] != 1024:
+                lin(prefix + "fc", cfg.embedding_size["image"], 1024)
+            return
         for i in range(len(chans) - 1):
             sh[f"{prefix}conv.{2 * i}.weight"] = (chans[i + 1], chans[i], 4, 4)
             sh[f"{prefix}conv.{2 * i}.bias"] = (chans[i + 1],)
@@ -129,6 +142,15 @@ def param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
             spec = [(E, 128, 5), (128, 64, 5), (64, 32, 6), (32, c, 6)]
         else:
             spec = [(E, 256, 6), (256, 128, 4), (128, 64, 4), (64, 32, 4), (32, c, 6)]
+        if cfg.normalization == "BatchNorm":        # ConvT(bias=False), BatchNorm2d, ReLU triples, last ConvT with bias
+            assert shape[1] == 64, "BatchNorm oracle: 64x64 images only"
+            for i, (ci, co, k) in enumerate(spec):
+                sh[f"{prefix}conv.{3 * i}.weight"] = (ci, co, k, k)
+                if i < len(spec) - 1:
+                    batch_norm(f"{prefix}conv.{3 * i + 1}", co)
+                else:
+                    sh[f"{prefix}conv.{3 * i}.bias"] = (co,)
+            return
         for i, (ci, co, k) in enumerate(spec):
             sh[f"{prefix}conv.{2 * i}.weight"] = (ci, co, k, k)
             sh[f"{prefix}conv.{2 * i}.bias"] = (co,)
@@ -196,6 +218,9 @@ def make_params(cfg: OracleConfig, seed: int = 0, dtype=torch.float32) -> Dict[s
     shapes = param_shapes(cfg)
     for k in sorted(shapes):
         shp = shapes[k]
+        if len(shp) == 1 and k.endswith(".weight"):             # BatchNorm scale: U(0.5, 1.5)
+            out[k] = (torch.rand(shp, generator=g, dtype=torch.float64) + 0.5).to(dtype)
+            continue
         if k.endswith("weight") or "weight_" in k:
             if "observation_model" in k and "conv." in k:      # ConvTranspose: [Ci,Co,k,k]
                 fan_in = shp[1] * shp[2] * shp[3]
@@ -205,7 +230,48 @@ def make_params(cfg: OracleConfig, seed: int = 0, dtype=torch.float32) -> Dict[s
             fan_in = max(shp[0], 16)
         b = 1.0 / math.sqrt(fan_in)
         out[k] = ((torch.rand(shp, generator=g, dtype=torch.float64) * 2 - 1) * b).to(dtype)
+    if cfg.normalization == "BatchNorm":
+        out.update(make_buffers(cfg, dtype))
     return out
+
+
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1          # nn.BatchNorm2d defaults, as constructed by the reference
+
+
+def is_buffer(key: str) -> bool:
+    return key.endswith(("running_mean", "running_var", "num_batches_tracked"))
+
+
+def make_buffers(cfg: OracleConfig, dtype=torch.float32) -> Dict[str, Tensor]:
+    """Freshly constructed BatchNorm buffers (zeros / ones / 0), keyed like the checkpoint.  They travel in the same flat
+    dict as the parameters; train_step leaves them out of the optimiser and lets batch_norm() update them."""
+    out = {}
+    for k, shp in param_shapes(cfg).items():
+        if len(shp) == 1 and k.endswith(".weight"):
+            base = k[:-len("weight")]
+            out[base + "running_mean"] = torch.zeros(shp, dtype=dtype)
+            out[base + "running_var"] = torch.ones(shp, dtype=dtype)
+            out[base + "num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+    return out
+
+
+def batch_norm(p: "_P", x: Tensor, train: bool) -> Tensor:
+    """nn.BatchNorm2d(affine=True, track_running_stats=True): train mode normalises with the batch statistics over
+    (N, H, W) (biased variance) and moves the running statistics by momentum 0.1 (unbiased variance); eval mode normalises
+    with the running statistics."""
+    mean, var = p["running_mean"], p["running_var"]
+    if not train:
+        xh = (x - mean[None, :, None, None]) / torch.sqrt(var[None, :, None, None] + BN_EPS)
+        return xh * p["weight"][None, :, None, None] + p["bias"][None, :, None, None]
+    m = x.mean(dim=(0, 2, 3))
+    v = x.var(dim=(0, 2, 3), unbiased=False)
+    n = x.numel() // x.shape[1]
+    with torch.no_grad():
+        mean.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * m)
+        var.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * v * n / (n - 1))
+        p["num_batches_tracked"].add_(1)
+    xh = (x - m[None, :, None, None]) / torch.sqrt(v[None, :, None, None] + BN_EPS)
+    return xh * p["weight"][None, :, None, None] + p["bias"][None, :, None, None]
 
 
 class _P:
@@ -241,10 +307,19 @@ def _groups(P: Dict[str, Tensor], cfg: OracleConfig):
 # --------------------------------------------------------------------------------------------
 # encoders  (utils/models/encoder.py)
 # --------------------------------------------------------------------------------------------
-def image_encoder(p: _P, x: Tensor, emb: int, act_cnn: str = "relu") -> Tensor:
+def image_encoder(p: _P, x: Tensor, emb: int, act_cnn: str = "relu", train: bool = True) -> Tensor:
     """ImageEncoder (64x64) encoder.py:307-351 / ImageEncoder_128 :415-500, normalization=None:
-    n x (Conv2d k4 s2 + ReLU) then reshape(-1,1024) (flatten order C,H,W)."""
+    n x (Conv2d k4 s2 + ReLU) then reshape(-1,1024) (flatten order C,H,W).
+    normalization="BatchNorm" (encoder.py:324-337): n x (Conv2d k4 s2 without bias + BatchNorm2d + ReLU)."""
     i = 0
+    if (p.prefix + "conv.1.running_mean") in p.p:
+        while (p.prefix + f"conv.{3 * i}.weight") in p.p:
+            x = F.relu(batch_norm(p.sub(f"conv.{3 * i + 1}."), F.conv2d(x, p[f"conv.{3 * i}.weight"], None, stride=2), train))
+            i += 1
+        x = x.reshape(-1, 1024)
+        if emb != 1024:
+            x = _act(act_cnn)(F.linear(x, p["fc.weight"], p["fc.bias"]))
+        return x
     while (p.prefix + f"conv.{2 * i}.weight") in p.p:
         x = F.relu(F.conv2d(x, p[f"conv.{2 * i}.weight"], p[f"conv.{2 * i}.bias"], stride=2))
         i += 1
@@ -262,7 +337,7 @@ def symbolic_encoder(p: _P, x: Tensor, act: str) -> Tensor:
     return a(F.linear(x, p["fc3.weight"], p["fc3.bias"]))
 
 
-def encode(P, cfg: OracleConfig, obs: Dict[str, Tensor]) -> Dict[str, Tensor]:
+def encode(P, cfg: OracleConfig, obs: Dict[str, Tensor], train: bool = True) -> Dict[str, Tensor]:
     """bottle_tupele_multimodal + MultimodalEncoder.forward (encoder.py:25-48, 778-783):
     fold [T',B,...] -> [T'*B,...], encode every modality, unfold."""
     g = _groups(P, cfg)
@@ -272,7 +347,7 @@ def encode(P, cfg: OracleConfig, obs: Dict[str, Tensor]) -> Dict[str, Tensor]:
         Tn, B = x.shape[:2]
         flat = x.reshape(Tn * B, *x.shape[2:])
         if "image" in n:
-            e = image_encoder(g["enc"][n], flat, cfg.embedding_size["image"])
+            e = image_encoder(g["enc"][n], flat, cfg.embedding_size["image"], train=train)
         else:
             e = symbolic_encoder(g["enc"][n], flat, cfg.act_dense)
         out[n] = e.reshape(Tn, B, -1)
@@ -416,13 +491,23 @@ def rollout(P, cfg: OracleConfig, prev_state: Tensor, actions: Tensor, prev_beli
 # --------------------------------------------------------------------------------------------
 # decoders  (utils/models/observation_model.py), reward model
 # --------------------------------------------------------------------------------------------
-def image_decoder(p: _P, h: Tensor, s: Tensor) -> Tensor:
+def image_decoder(p: _P, h: Tensor, s: Tensor, train: bool = True) -> Tensor:
     """ImageDecoder.forward observation_model.py:91-105 (64x64) / ImageDecoder_128 :215-229:
     fc1([h,s]) (no activation) -> [N,E,1,1] -> ConvTranspose2d stack with ReLU between."""
     Tn, B = h.shape[:2]
     x = F.linear(torch.cat([h.reshape(Tn * B, -1), s.reshape(Tn * B, -1)], 1),
                  p["fc1.weight"], p["fc1.bias"])
     x = x.reshape(Tn * B, -1, 1, 1)
+    if (p.prefix + "conv.1.running_mean") in p.p:           # observation_model.py:75-86
+        n = 0
+        while (p.prefix + f"conv.{3 * n}.weight") in p.p:
+            n += 1
+        for i in range(n):
+            last = i == n - 1
+            x = F.conv_transpose2d(x, p[f"conv.{3 * i}.weight"], p[f"conv.{3 * i}.bias"] if last else None, stride=2)
+            if not last:
+                x = F.relu(batch_norm(p.sub(f"conv.{3 * i + 1}."), x, train))
+        return x.reshape(Tn, B, *x.shape[1:])
     n = 0
     while (p.prefix + f"conv.{2 * n}.weight") in p.p:
         n += 1
@@ -447,12 +532,12 @@ def dense_decoder(p: _P, h: Tensor, s: Tensor, act: str) -> Tensor:
     return y.reshape(Tn, B, -1)
 
 
-def decode(P, cfg: OracleConfig, h: Tensor, s: Tensor) -> Dict[str, Tensor]:
+def decode(P, cfg: OracleConfig, h: Tensor, s: Tensor, train: bool = True) -> Dict[str, Tensor]:
     """MultimodalObservationModel.forward observation_model.py:560-566 ('loc' only)."""
     g = _groups(P, cfg)
     out = {}
     for n in cfg.names_rec:
-        out[n] = image_decoder(g["dec"][n], h, s) if "image" in n else \
+        out[n] = image_decoder(g["dec"][n], h, s, train) if "image" in n else \
             dense_decoder(g["dec"][n], h, s, cfg.act_dense)
     return out
 
@@ -564,13 +649,13 @@ def latent_overshooting(P, cfg: OracleConfig, st: dict, actions: Tensor, rewards
 
 def elbo(P, cfg: OracleConfig, st: dict, obs_target: Dict[str, Tensor], eps_dec: Optional[Tensor],
          rewards: Optional[Tensor] = None, actions: Optional[Tensor] = None, nonterminals: Optional[Tensor] = None,
-         eps_over: Optional[List[Tensor]] = None):
+         eps_over: Optional[List[Tensor]] = None, train: bool = True):
     """_calc_loss + _get_model_loss (base/algo.py:165-232): overshooting off, MSE observation loss
     mean over (t,b) then sum over features (base/algo.py:381-383); the reward loss (_calc_reward_loss
     base/algo.py:96-109: MSE of the reward head on [h, z] against rewards[:-1], mean over (t,b)) is
     zeroed unless predict_reward (base/algo.py:200-201)."""
     z, qm, qs = decoder_latent(cfg, st, eps_dec)
-    rec = decode(P, cfg, st["beliefs"], z)
+    rec = decode(P, cfg, st["beliefs"], z, train)
     obs_loss = {n: F.mse_loss(rec[n], obs_target[n], reduction="none").mean((0, 1)).sum()
                 for n in cfg.names_rec}
     kl = kl_loss(cfg, st)
@@ -599,11 +684,12 @@ def elbo(P, cfg: OracleConfig, st: dict, obs_target: Dict[str, Tensor], eps_dec:
 
 
 def estimate_state(P, cfg: OracleConfig, obs_target, actions, nonterminals, eps_prior, eps_post,
-                   det=False) -> dict:
-    """MRSSM_base.estimate_state base/algo.py:337-366 (zeros init, encode, rollout)."""
+                   det=False, train: bool = True) -> dict:
+    """MRSSM_base.estimate_state base/algo.py:337-366 (zeros init, encode, rollout).  train: BatchNorm mode of the encoders
+    (model.train() / model.eval())."""
     B = actions.shape[1]
     dt = actions.dtype
-    emb = encode(P, cfg, obs_target)
+    emb = encode(P, cfg, obs_target, train)
     if not cfg.multimodal:
         emb = {cfg.names_enc[0]: emb[cfg.names_enc[0]]}
     return rollout(P, cfg, torch.zeros(B, cfg.state_size, dtype=dt), actions,
@@ -634,7 +720,7 @@ def train_step(P: Dict[str, Tensor], opt: dict, cfg: OracleConfig, batch: dict, 
     batch: obs {name:[T,B,...]}, actions [T,B,A], nonterminals [T,B,1]; noise: eps_prior/eps_post/
     eps_dec [T-1,B,S].  Mutates P and opt (keys 'm','v','step').  Returns loss_info, grads,
     grad_norm."""
-    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
+    leaves = {k: (v if is_buffer(k) else v.detach().clone().requires_grad_(True)) for k, v in P.items()}   # BatchNorm buffers: shared, updated in place
     tgt = {n: o[1:] for n, o in batch["obs"].items()}                               # base:241
     st = estimate_state(leaves, cfg, {n: tgt[n] for n in cfg.names_enc}, batch["actions"][:-1],
                         batch["nonterminals"][:-1], noise["eps_prior"], noise["eps_post"])

@@ -53,7 +53,7 @@ def ref_cfg(oc: O.OracleConfig, B, T):
             multimodal_params=dict(fusion_method=oc.fusion, expert_dist="q(st|ht,ot)"),
             activation_function=dict(cnn="relu", dense=oc.act_dense, fusion="relu"),
             embedding_size=dict(oc.embedding_size), hidden_size=oc.hidden_size,
-            belief_size=oc.belief_size, state_size=oc.state_size, normalization=None,
+            belief_size=oc.belief_size, state_size=oc.state_size, normalization=oc.normalization,
             worldmodel_LogProbLoss=False, overshooting_distance=oc.overshooting_distance,
             overshooting_kl_beta=oc.overshooting_kl_beta,
             overshooting_reward_scale=oc.overshooting_reward_scale, global_kl_beta=oc.global_kl_beta, free_nats=oc.free_nats,
@@ -130,8 +130,15 @@ def named_ref_params(model, oc):
         sd.pop("model_optimizer")
         # state_dict tensors alias the parameters; map by data_ptr to find .grad
         by_ptr = {p.data_ptr(): p for p in model.param_list}
-        return {k: by_ptr[v.data_ptr()] for k, v in O.flatten_state(sd).items()}
+        return {k: by_ptr[v.data_ptr()] for k, v in O.flatten_state(sd).items() if not O.is_buffer(k)}
     return dict(model.named_parameters())
+
+
+def ref_buffers(model, oc):
+    """BatchNorm running statistics of the reference model, keyed like the oracle's flat dict."""
+    sd = model.get_state_dict()
+    sd.pop("model_optimizer", None)
+    return {k: v.detach().clone() for k, v in O.flatten_state(sd).items() if O.is_buffer(k)}
 
 
 class FakeD:
@@ -161,7 +168,7 @@ def gen_train(name, oc, B=4, T=6, steps=2):
     model._init_optimizer()
     named = named_ref_params(model, oc)
     rec = dict(meta=dict(name=name, B=B, T=T, cfg=oc.__dict__.copy(), param_seed=0),
-               param_checksum=float(sum(v.double().abs().sum() for v in P.values())), steps=[])
+               param_checksum=float(sum(v.double().abs().sum() for k, v in P.items() if not O.is_buffer(k))), steps=[])
     cap = {}
     orig_es = model.estimate_state
     orig_ml = model._get_model_loss
@@ -201,6 +208,19 @@ def gen_train(name, oc, B=4, T=6, steps=2):
                 grad_norm=cap["grad_norm"], grad_none=cap["grad_none"],
                 grads={k: summarize(g) for k, g in cap["grads"].items()},
                 params_after={k: summarize(p) for k, p in named.items()}))
+            if oc.normalization is not None:
+                rec["steps"][-1]["buffers_after"] = ref_buffers(model, oc)
+        if oc.normalization is not None:        # eval mode (running statistics) after the training steps: validation's forward
+            model.estimate_state = orig_es
+            model.eval()
+            batch, _ = O.synthetic_batch(oc, B, T, seed=77)
+            tgt = {n: batch["obs"][n][1:] for n in oc.names_enc}
+            with torch.no_grad():
+                st = model.estimate_state(tgt, batch["actions"][:-1], None, batch["nonterminals"][:-1], det=True)
+                out = model.observation_model(h_t=st["beliefs"], s_t=st["posterior_states"])
+                rec["eval"] = dict(data_seed=77, states=states_to_plain(st),
+                                   recon={n: summarize((out[n] if oc.multimodal else out)["loc"], n=64) for n in oc.names_rec})
+            model.train()
     finally:
         torch.nn.utils.clip_grad_norm_ = orig_clip
     torch.save(rec, os.path.join(HERE, f"train_{name}.pt"))
@@ -250,5 +270,11 @@ if __name__ == "__main__":
                                          overshooting_reward_scale=0.5))
     gen_train("single_over", O.OracleConfig(fusion="single", names_enc=("image_horizon",), names_rec=("image_horizon",),
                                             overshooting_distance=4, overshooting_kl_beta=0.25))
+    # BatchNorm over 20 samples amplifies parameter differences a few hundred times per layer (1/sqrt(var + 1e-5) on nearly
+    # constant channels); a small learning rate keeps Adam's sign-like first update from turning fp32 summation-order
+    # noise into visible step-2 differences
+    gen_train("mopoe_bn", O.OracleConfig(fusion="MoPoE", normalization="BatchNorm", lr=1e-5))
+    gen_train("single_bn", O.OracleConfig(fusion="single", names_enc=("image_horizon",), names_rec=("image_horizon",),
+                                          normalization="BatchNorm", lr=1e-5))
     gen_infer("mopoe", O.OracleConfig(fusion="MoPoE"))
     gen_infer("single", O.OracleConfig(fusion="single", names_enc=("image_horizon",), names_rec=("image_horizon",)))
