@@ -155,6 +155,27 @@ def param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
             sh[f"{prefix}conv.{2 * i}.weight"] = (ci, co, k, k)
             sh[f"{prefix}conv.{2 * i}.bias"] = (co,)
 
+    def instance_norm(prefix, c):                   # affine parameters (running statistics: make_buffers)
+        sh[prefix + ".weight"] = (c,)
+        sh[prefix + ".bias"] = (c,)
+
+    def sound_encoder(prefix):                      # SoundEncoder_v2 encoder.py:661-721, channels_base = 128
+        cb, emb = 128, cfg.embedding_size["sound"]
+        sh[prefix + "down_sample_1.0.weight"] = (cb, 1, 3, 9)
+        for i, (ci, co, k) in enumerate([(cb // 2, cb * 2, (4, 8)), (cb, cb * 4, (4, 8)), (cb * 2, cb * 4, (3, 4))]):
+            sh[f"{prefix}down_sample_{i + 2}.0.weight"] = (co, ci, *k)
+            instance_norm(f"{prefix}down_sample_{i + 2}.1", co)
+        sh[prefix + "down_conversion.0.weight"] = (emb // 2, cb * 64, 1)
+        instance_norm(prefix + "down_conversion.1", emb // 2)       # InstanceNorm1d(affine=True): no running statistics
+
+    def sound_decoder(prefix):                      # SoundDecoder_v2 observation_model.py:420-472
+        cb = 128
+        sh[prefix + "up_conversion.weight"] = (cb * 2 * 32 * 4, S + D, 1)
+        for i, (ci, co, k) in enumerate([(cb * 2, cb * 4, (3, 4)), (cb * 2, cb * 2, (4, 4)), (cb, cb, (4, 4))]):
+            sh[f"{prefix}up_sample_{i}.0.weight"] = (ci, co, *k)    # ConvTranspose2d: [in, out, kh, kw]
+            instance_norm(f"{prefix}up_sample_{i}.1", co)
+        sh[prefix + "out.weight"] = (1, cb // 2, 7, 7)
+
     def mlp3(prefix, n_in, n_hid, n_out):
         lin(prefix + "fc1", n_hid, n_in)
         lin(prefix + "fc2", n_hid, n_hid)
@@ -174,6 +195,8 @@ def param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
         for n in cfg.names_rec:
             if "image" in n:
                 image_decoder(f"observation_model/{n}/", cfg.observation_shapes[n])
+            elif "sound" in n:
+                sound_decoder(f"observation_model/{n}/")
             else:
                 mlp3(f"observation_model/{n}/", D + S, cfg.embedding_size["other"],
                      cfg.observation_shapes[n][0])
@@ -181,6 +204,8 @@ def param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
         for n in cfg.names_enc:
             if "image" in n:
                 image_encoder(f"encoder/{n}/", cfg.observation_shapes[n])
+            elif "sound" in n:
+                sound_encoder(f"encoder/{n}/")
             else:
                 e = cfg.embedding_size["other"]
                 mlp3(f"encoder/{n}/", cfg.observation_shapes[n][0], e, e)
@@ -230,7 +255,7 @@ def make_params(cfg: OracleConfig, seed: int = 0, dtype=torch.float32) -> Dict[s
             fan_in = max(shp[0], 16)
         b = 1.0 / math.sqrt(fan_in)
         out[k] = ((torch.rand(shp, generator=g, dtype=torch.float64) * 2 - 1) * b).to(dtype)
-    if cfg.normalization == "BatchNorm":
+    if cfg.normalization == "BatchNorm" or any("sound" in n for n in (*cfg.names_enc, *cfg.names_rec)):
         out.update(make_buffers(cfg, dtype))
     return out
 
@@ -247,7 +272,7 @@ def make_buffers(cfg: OracleConfig, dtype=torch.float32) -> Dict[str, Tensor]:
     dict as the parameters; train_step leaves them out of the optimiser and lets batch_norm() update them."""
     out = {}
     for k, shp in param_shapes(cfg).items():
-        if len(shp) == 1 and k.endswith(".weight"):
+        if len(shp) == 1 and k.endswith(".weight") and "down_conversion" not in k:
             base = k[:-len("weight")]
             out[base + "running_mean"] = torch.zeros(shp, dtype=dtype)
             out[base + "running_var"] = torch.ones(shp, dtype=dtype)
@@ -329,6 +354,55 @@ def image_encoder(p: _P, x: Tensor, emb: int, act_cnn: str = "relu", train: bool
     return x
 
 
+def instance_norm(p: _P, x: Tensor, train: bool) -> Tensor:
+    """nn.InstanceNorm2d(affine=True, track_running_stats=True) / nn.InstanceNorm1d(affine=True): train mode (and the 1d
+    layer, which tracks nothing, always) normalises every (sample, channel) plane with its own biased variance; the tracked
+    layers move their running statistics by momentum 0.1 towards the batch means of the per-plane mean / unbiased variance
+    and, in eval mode, normalise with them."""
+    dims = tuple(range(2, x.dim()))
+    shape = (1, -1) + (1,) * (x.dim() - 2)
+    tracked = (p.prefix + "running_mean") in p.p
+    if tracked and not train:
+        xh = (x - p["running_mean"].reshape(shape)) / torch.sqrt(p["running_var"].reshape(shape) + BN_EPS)
+    else:
+        m = x.mean(dim=dims, keepdim=True)
+        v = x.var(dim=dims, unbiased=False, keepdim=True)
+        if tracked:
+            n = x[0, 0].numel()
+            with torch.no_grad():
+                p["running_mean"].mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * m.mean(0).reshape(-1))
+                p["running_var"].mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * (v * n / (n - 1)).mean(0).reshape(-1))
+                # (torch's instance norm leaves num_batches_tracked at 0)
+        xh = (x - m) / torch.sqrt(v + BN_EPS)
+    return xh * p["weight"].reshape(shape) + p["bias"].reshape(shape)
+
+
+def sound_encoder(p: _P, x: Tensor, train: bool = True) -> Tensor:
+    """SoundEncoder_v2.forward encoder.py:703-714: [N,128,20] spectrogram -> 4 x (Conv2d without bias [+ InstanceNorm2d] +
+    GLU over channels) -> view(N, 8192, 4) -> Conv1d k1 + InstanceNorm1d + GLU -> [N, embedding]."""
+    x = F.glu(F.conv2d(x.unsqueeze(1), p["down_sample_1.0.weight"], None, padding=(1, 4)), dim=1)
+    for i, (stride, pad) in enumerate([((2, 2), (1, 3)), ((2, 2), (1, 3)), ((1, 1), (1, 1))]):
+        q = p.sub(f"down_sample_{i + 2}.")
+        x = F.glu(instance_norm(q.sub("1."), F.conv2d(x, q["0.weight"], None, stride=stride, padding=pad), train), dim=1)
+    x = x.contiguous().view(-1, p["down_conversion.0.weight"].shape[1], 4)
+    x = F.glu(instance_norm(p.sub("down_conversion.1."), F.conv1d(x, p["down_conversion.0.weight"]), train), dim=1)
+    return x.contiguous().view(x.shape[0], -1)
+
+
+def sound_decoder(p: _P, h: Tensor, s: Tensor, train: bool = True) -> Tensor:
+    """SoundDecoder_v2.forward observation_model.py:456-472.  Its signature is (s_t, h_t) but every caller passes
+    (beliefs, states) positionally, so the concat order is [state, belief] — reproduced here: h = beliefs,
+    s = states, input = cat([s, h])."""
+    Tn, B = h.shape[:2]
+    x = torch.cat([s.reshape(Tn * B, -1, 1), h.reshape(Tn * B, -1, 1)], dim=1)
+    x = F.conv1d(x, p["up_conversion.weight"]).view(Tn * B, -1, 32, 4)
+    for i, (stride, pad) in enumerate([((1, 1), (1, 1)), ((2, 2), (1, 1)), ((2, 2), (1, 1))]):
+        q = p.sub(f"up_sample_{i}.")
+        x = F.glu(instance_norm(q.sub("1."), F.conv_transpose2d(x, q["0.weight"], None, stride=stride, padding=pad), train), dim=1)
+    x = F.conv2d(x, p["out.weight"], None, padding=3).squeeze(1)
+    return x.reshape(Tn, B, *x.shape[1:])
+
+
 def symbolic_encoder(p: _P, x: Tensor, act: str) -> Tensor:
     """SymbolicEncoder encoder.py:282-296: three Linear+act."""
     a = _act(act)
@@ -348,6 +422,8 @@ def encode(P, cfg: OracleConfig, obs: Dict[str, Tensor], train: bool = True) -> 
         flat = x.reshape(Tn * B, *x.shape[2:])
         if "image" in n:
             e = image_encoder(g["enc"][n], flat, cfg.embedding_size["image"], train=train)
+        elif "sound" in n:
+            e = sound_encoder(g["enc"][n], flat, train)
         else:
             e = symbolic_encoder(g["enc"][n], flat, cfg.act_dense)
         out[n] = e.reshape(Tn, B, -1)
@@ -537,8 +613,12 @@ def decode(P, cfg: OracleConfig, h: Tensor, s: Tensor, train: bool = True) -> Di
     g = _groups(P, cfg)
     out = {}
     for n in cfg.names_rec:
-        out[n] = image_decoder(g["dec"][n], h, s, train) if "image" in n else \
-            dense_decoder(g["dec"][n], h, s, cfg.act_dense)
+        if "image" in n:
+            out[n] = image_decoder(g["dec"][n], h, s, train)
+        elif "sound" in n:
+            out[n] = sound_decoder(g["dec"][n], h, s, train)
+        else:
+            out[n] = dense_decoder(g["dec"][n], h, s, cfg.act_dense)
     return out
 
 

@@ -170,6 +170,7 @@ def gen_train(name, oc, B=4, T=6, steps=2):
     rec = dict(meta=dict(name=name, B=B, T=T, cfg=oc.__dict__.copy(), param_seed=0),
                param_checksum=float(sum(v.double().abs().sum() for k, v in P.items() if not O.is_buffer(k))), steps=[])
     cap = {}
+    has_buffers = any(O.is_buffer(k) for k in P)
     orig_es = model.estimate_state
     orig_ml = model._get_model_loss
 
@@ -208,9 +209,9 @@ def gen_train(name, oc, B=4, T=6, steps=2):
                 grad_norm=cap["grad_norm"], grad_none=cap["grad_none"],
                 grads={k: summarize(g) for k, g in cap["grads"].items()},
                 params_after={k: summarize(p) for k, p in named.items()}))
-            if oc.normalization is not None:
+            if has_buffers:
                 rec["steps"][-1]["buffers_after"] = ref_buffers(model, oc)
-        if oc.normalization is not None:        # eval mode (running statistics) after the training steps: validation's forward
+        if has_buffers:                         # eval mode (running statistics) after the training steps: validation's forward
             model.estimate_state = orig_es
             model.eval()
             batch, _ = O.synthetic_batch(oc, B, T, seed=77)
@@ -276,5 +277,10 @@ if __name__ == "__main__":
     gen_train("mopoe_bn", O.OracleConfig(fusion="MoPoE", normalization="BatchNorm", lr=1e-5))
     gen_train("single_bn", O.OracleConfig(fusion="single", names_enc=("image_horizon",), names_rec=("image_horizon",),
                                           normalization="BatchNorm", lr=1e-5))
+    sound_shapes = {"image_horizon": [3, 64, 64], "sound": [128, 20]}
+    gen_train("mopoe_sound", O.OracleConfig(fusion="MoPoE", names_enc=("image_horizon", "sound"), names_rec=("image_horizon", "sound"),
+                                            observation_shapes=sound_shapes, lr=1e-5), B=2, T=4)
+    gen_train("mopoe_sound_bn", O.OracleConfig(fusion="MoPoE", names_enc=("image_horizon", "sound"), names_rec=("image_horizon", "sound"),
+                                               observation_shapes=sound_shapes, normalization="BatchNorm", lr=1e-5), B=2, T=4)
     gen_infer("mopoe", O.OracleConfig(fusion="MoPoE"))
     gen_infer("single", O.OracleConfig(fusion="single", names_enc=("image_horizon",), names_rec=("image_horizon",)))
