@@ -3,6 +3,7 @@ configurations the replay fixtures were generated with."""
 import os
 
 import numpy as np
+import torch
 
 IMAGE, BIN, VEC, ACTION = "image_horizon", "image_bin", "pose_quat_v2", "d_pose_quat_v2"
 
@@ -82,3 +83,22 @@ def assert_digest(t, d, exact=True):
         assert abs(float(flat.double().abs().sum()) - d["abs_sum"]) <= 1e-9 * max(1.0, d["abs_sum"])
     else:
         torch.testing.assert_close(flat[::37], d["sample"], rtol=1e-5, atol=1e-6)
+
+
+def make_buffer(cfg, files, device="cpu"):
+    from utils.replay_buffer.memory import ExperienceReplay_Multimodal
+    D = ExperienceReplay_Multimodal(**buffer_kwargs(cfg, torch.device(device)))
+    D.file_names += files
+    for f in files:
+        D._set_data_to_buffer(f)
+    if D.pca_scales is not None:
+        D._set_color_aug_params()
+    return D
+
+
+def load_fixture_buffer(name, golden_dir, tmp_path, device="cpu"):
+    rec = torch.load(os.path.join(golden_dir, f"replay_{name}.pt"), weights_only=False)
+    cfg = CONFIGS[name]
+    files = write_dataset(str(tmp_path), cfg)
+    assert [os.path.basename(f) for f in files] == rec["files"]
+    return rec, cfg, make_buffer(cfg, files, device)

@@ -16,7 +16,7 @@ import torch
 
 from oracle import replay_oracle as RO
 from tests import replay_util as R
-from tests.test_replay_oracle import _load
+from tests.replay_util import load_fixture_buffer as _load
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"

@@ -17,23 +17,7 @@ from oracle import replay_oracle as RO
 from tests import replay_util as R
 
 
-def _buffer(cfg, files, device="cpu"):
-    from utils.replay_buffer.memory import ExperienceReplay_Multimodal
-    D = ExperienceReplay_Multimodal(**R.buffer_kwargs(cfg, torch.device(device)))
-    D.file_names += files
-    for f in files:
-        D._set_data_to_buffer(f)
-    if D.pca_scales is not None:
-        D._set_color_aug_params()
-    return D
-
-
-def _load(name, golden_dir, tmp_path, device="cpu"):
-    rec = torch.load(os.path.join(golden_dir, f"replay_{name}.pt"), weights_only=False)
-    cfg = R.CONFIGS[name]
-    files = R.write_dataset(str(tmp_path), cfg)
-    assert [os.path.basename(f) for f in files] == rec["files"]
-    return rec, cfg, _buffer(cfg, files, device)
+from tests.replay_util import load_fixture_buffer as _load  # noqa: E402
 
 
 def oracle_batch(D, cfg, vec_idxs, plan, n, L):
