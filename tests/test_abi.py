@@ -58,3 +58,34 @@ def test_rollout_tc_plan_is_host_only():
         assert kb.value % 512 == 0 and kb.value > 0
     assert lib.mrssm_rollout_tc_eligible(1024, 64, 1024, 3, 3) == 0      # BASELINE config 5: CUDA-core rollout
     assert lib.mrssm_rollout_tc_eligible(200, 30, 200, 3, 4) == 0
+
+
+STRUCTS = {"mrssm_t4": "T4", "mrssm_conv_args": "ConvArgs", "mrssm_tc_conv_args": "TcConvArgs", "mrssm_tv": "TV",
+           "mrssm_pl_conv_args": "PlConvArgs", "mrssm_rollout_args": "RolloutArgs", "mrssm_rollout_bwd_args": "RolloutBwdArgs",
+           "mrssm_latent_args": "LatentArgs", "mrssm_overshoot_args": "OvershootArgs",
+           "mrssm_replay_gather_args": "ReplayGatherArgs"}
+
+
+def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 (no C++ / torch types), every struct it defines has a ctypes
+    mirror, and size plus the offset of every field agree between gcc and ctypes (a reordered or mistyped field in either
+    place would silently shift every pointer behind it)."""
+    from mrssm_b200 import _lib as L
+    src = open(HEADER).read()
+    assert sorted(re.findall(r"^} (mrssm_[a-z0-9_]+);", src, flags=re.M)) == sorted(STRUCTS)
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "%s"' % HEADER, 'int main(void) {']
+    for cname, pyname in STRUCTS.items():
+        cls = getattr(L, pyname)
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for field in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, field[0], cname, field[0]))
+    lines += ['return 0; }']
+    c_file, exe = tmp_path / "layout.c", tmp_path / "layout"
+    c_file.write_text("\n".join(lines))
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-o", str(exe), str(c_file)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)]).decode().splitlines())
+    for cname, pyname in STRUCTS.items():
+        cls = getattr(L, pyname)
+        assert int(got[cname]) == ctypes.sizeof(cls), (cname, got[cname], ctypes.sizeof(cls))
+        for field in cls._fields_:
+            assert int(got[f"{cname}.{field[0]}"]) == getattr(cls, field[0]).offset, (cname, field[0])
