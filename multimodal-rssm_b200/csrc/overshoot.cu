@@ -121,7 +121,7 @@ __global__ void overshoot_gather_kernel(mrssm_overshoot_args a, int rows) {
 
 int check(const mrssm_overshoot_args* a) {
     MRSSM_CHECK(a && a->T >= 3 && a->B > 0 && a->OD > 0, "overshoot: needs T >= 3, B > 0, distance > 0");
-    MRSSM_CHECK((long long)a->OD * (a->T - 2) * a->B < (1ll << 31), "overshoot: too many rows");
+    MRSSM_CHECK((long long)a->OD * (a->T - 2) * a->B < (1ll << 26), "overshoot: too many rows");     /* 32 threads per row, 32-bit thread index */
     return 0;
 }
 
