@@ -4,7 +4,8 @@ Interface of the reference's algos/MRSSM/MRSSM/train.py (`get_dataset_loader`, `
 from episode directories, then `optimize` runs `train_iteration` times with `validation` every `validation_interval` and a
 checkpoint every `checkpoint_interval` iterations.  The experiment logger (hydra / wandb, utils/logger.py) is control plane
 and not part of this package, so `run` takes the three values it would hand over.  One process drives one GPU; under
-torchrun pass `dp=mrssm_b200.dist.DataParallel` and every rank samples its own chunks."""
+torchrun pass `dp=mrssm_b200.dist.DataParallel`; every rank samples its own chunks from numpy's global RNG, so seed it
+per rank (`np.random.seed(seed + RANK)`) or all ranks draw the same batch."""
 import os
 
 import torch

@@ -117,3 +117,18 @@ def test_sample_fails_loudly_without_a_device(golden_dir, tmp_path):
     np.random.seed(0)
     with pytest.raises((RuntimeError, AssertionError)):
         D.sample(R.N, R.L)
+
+
+def test_visualize_helpers():
+    from utils.evaluation import visualize_utils as V
+    rng = np.random.RandomState(0)
+    frame = rng.rand(3, 8, 8).astype(np.float32) - 0.5
+    img = V.reverse_image_observation(torch.as_tensor(frame))
+    assert img.shape == (8, 8, 3) and img.dtype == np.uint8
+    assert np.array_equal(img, np.clip(np.floor((frame + 0.5) * 32) * 8, 0, 255).astype(np.uint8).transpose(1, 2, 0))
+    feat = rng.randn(5, 2, 6).astype(np.float32)
+    x, y, z = V.get_xyz(feat)
+    assert x.shape == (10,) and np.array_equal(z, feat.reshape(-1, 6)[:, 2])
+    pca = V.get_pca_model(torch.as_tensor(feat), n_components=3)
+    assert pca.transform(V.flat(feat)).shape == (10, 3)
+    assert torch.equal(V.np2tensor(feat), torch.as_tensor(feat)) and isinstance(V.tensor2np(torch.ones(2)), np.ndarray)
