@@ -145,16 +145,26 @@ class ExperienceReplay_Multimodal:
         self.nonterminals = torch.empty((size, 1), dtype=torch.float32, device=dev)
 
     # ---- sampling (reference :175-222) ---------------------------------------------------------------------------
-    def _sample_idx(self, L_, idx_max=None):
-        """Slots of one chunk of L consecutive steps that does not run over the write position."""
+    def _sample_start(self, L_, idx_max=None):
+        """First slot of one chunk of L consecutive steps that does not run over the write position: one
+        np.random.randint per attempt, exactly like the reference's rejection loop (:177-189)."""
         upper = self.size if self.full else self.idx - L_
         if idx_max is not None:
             upper = np.min([idx_max, upper])
         while True:
             start = np.random.randint(0, upper)
-            idxs = np.arange(start, start + L_) % self.size
-            if self.idx not in idxs[1:]:
-                return idxs
+            # slots start+1 .. start+L-1 (mod size) must not contain the write position
+            if (self.idx - start - 1) % self.size >= L_ - 1:
+                return start
+
+    def _sample_chunks(self, n, L_):
+        """Slots [n, L] of n chunks: the draws stay sequential (RNG parity), the slot table is built in one step."""
+        starts = np.asarray([self._sample_start(L_) for _ in range(n)])
+        return (starts[:, None] + np.arange(L_)[None, :]) % self.size
+
+    def _sample_idx(self, L_, idx_max=None):
+        """Slots of one chunk (the reference's helper, kept for callers that use it directly)."""
+        return (self._sample_start(L_, idx_max) + np.arange(L_)) % self.size
 
     def _noise(self, kind, name, shape):
         if self.noise_source is None:
@@ -244,8 +254,7 @@ class ExperienceReplay_Multimodal:
     def sample(self, n, L_):
         """n chunks of L consecutive steps, time-major: [obs dict [L,n,...], actions [L,n,A], rewards [L,n],
         nonterminals [L,n,1]] on `device`."""
-        idxs = np.asarray([self._sample_idx(L_) for _ in range(n)])
-        return list(self._retrieve_batch(idxs, n, L_))
+        return list(self._retrieve_batch(self._sample_chunks(n, L_), n, L_))
 
     # ---- filling (reference :224-268) ------------------------------------------------------------------------------
     def append(self, observation, action, reward, done):

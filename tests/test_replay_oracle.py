@@ -70,6 +70,8 @@ def test_host_plan_and_oracle_reproduce_reference_batches(name, golden_dir, tmp_
         torch.manual_seed(s["seed"])
         idxs = np.asarray([D._sample_idx(R.L) for _ in range(R.N)])
         assert np.array_equal(idxs, s["idxs"])
+        np.random.seed(s["seed"])                                # the batched form `sample` uses draws the same chunks
+        assert np.array_equal(D._sample_chunks(R.N, R.L), s["idxs"])
         vec_idxs, plan = D._plan_batch(idxs)
         obs, actions, rewards, nonterminals = oracle_batch(D, cfg, vec_idxs, plan, R.N, R.L)
         for k, d in s["obs"].items():
