@@ -134,3 +134,25 @@ def test_visualize_helpers():
     pca = V.get_pca_model(torch.as_tensor(feat), n_components=3)
     assert pca.transform(V.flat(feat)).shape == (10, 3)
     assert torch.equal(V.np2tensor(feat), torch.as_tensor(feat)) and isinstance(V.tensor2np(torch.ones(2)), np.ndarray)
+
+
+def test_episode_preprocessing_edge_cases():
+    """preprocess_data (reference memory.py:47-65): shortest stream wins, 'seed' is dropped, HWC -> CHW, normalised floats ->
+    uint8, a plain 'image' key of another size is renamed, nonterminals = 1 - done; calc_image_shape keeps the crop margin."""
+    from utils.replay_buffer.memory import calc_image_shape, clip_episode, preprocess_data
+    rng = np.random.RandomState(1)
+    hwc = rng.randint(0, 256, size=(5, 32, 32, 3)).astype(np.uint8)
+    data = {"image": hwc.copy(), "v": rng.randn(7, 2).astype(np.float32), "done": np.array([0, 0, 0, 0, 1, 0], dtype=np.float32),
+            "reward": np.zeros(5, dtype=np.float32), "seed": np.arange(9)}
+    clipped, n = clip_episode(dict(data))
+    assert n == 5 and "seed" not in clipped and all(len(v) == 5 for v in clipped.values())
+    out, n = preprocess_data(dict(data))
+    assert n == 5 and "image" not in out and out["image_32"].shape == (5, 3, 32, 32)
+    assert np.array_equal(out["image_32"], hwc.transpose(0, 3, 1, 2))
+    assert out["nonterminals"].shape == (5, 1) and out["nonterminals"][:, 0].tolist() == [1, 1, 1, 1, 0]
+    as_float = (np.floor(hwc / 8.0) / 32.0 - 0.5).astype(np.float32)            # what normalize_image produces, noise-free
+    out2, _ = preprocess_data({"image_horizon": as_float, "done": np.zeros(5, dtype=np.float32)})
+    assert out2["image_horizon"].dtype == np.uint8
+    assert np.array_equal(out2["image_horizon"], (hwc // 8 * 8).transpose(0, 3, 1, 2))
+    assert calc_image_shape([3, 64, 64]) == [3, 64, 64]
+    assert calc_image_shape([3, 64, 64], n_crop=9, dw_base=2, dh_base=3) == [3, 70, 68]      # k = 2: +k*dh rows, +k*dw columns
