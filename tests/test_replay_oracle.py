@@ -156,3 +156,35 @@ def test_episode_preprocessing_edge_cases():
     assert np.array_equal(out2["image_horizon"], (hwc // 8 * 8).transpose(0, 3, 1, 2))
     assert calc_image_shape([3, 64, 64]) == [3, 64, 64]
     assert calc_image_shape([3, 64, 64], n_crop=9, dw_base=2, dh_base=3) == [3, 70, 68]      # k = 2: +k*dh rows, +k*dw columns
+
+
+@pytest.mark.parametrize("name", ["default", "augment"])
+def test_sample_plumbing_reproduces_reference_batches(name, golden_dir, tmp_path):
+    """`sample` end to end on the host with the two kernel calls swapped for the oracle's gathers (test-only stand-ins; the
+    product itself has no host path): chunk draws, slot order, per-modality plans, noise order and output shapes must give
+    the reference batches bit for bit.  The kernels themselves are checked against the same fixtures in test_gpu_replay.py."""
+    from utils.replay_buffer.data_augment import crop_size_of
+    rec, cfg, D = _load(name, golden_dir, tmp_path)
+
+    def gather_image(mod, slots, rows, crop, delta, gauss_scale, normalise):
+        store = D.observations[mod]
+        side = crop_size_of(mod)
+        hw = (side, side) if crop is not None else tuple(store.shape[-2:])
+        shape = (R.L, R.N, store.shape[1], *hw)
+        gauss = torch.randn(*shape) if gauss_scale > 0 else None          # the reference's order: Gaussian noise, then dequantisation
+        uniform = torch.rand(shape) if normalise else None
+        out = RO.gather_image(store, slots.numpy(), R.N, R.L, crop=crop, side=side, delta=delta, gauss=gauss,
+                              gauss_scale=gauss_scale, uniform=uniform, bit_depth=D.bit_depth, normalise=normalise)
+        return out.reshape(rows, *out.shape[2:])
+
+    D._gather_image = gather_image
+    D._gather_rows = lambda store, slots, rows: store[slots].reshape(rows, -1)
+    for s in rec["samples"]:
+        np.random.seed(s["seed"])
+        torch.manual_seed(s["seed"])
+        obs, actions, rewards, nonterminals = D.sample(R.N, R.L)
+        for k, d in s["obs"].items():
+            R.assert_digest(obs[k], d)
+        assert torch.equal(actions, s["actions"]) and torch.equal(rewards, s["rewards"])
+        assert torch.equal(nonterminals, s["nonterminals"])
+        assert float(np.random.rand()) == s["np_next"] and float(torch.rand(())) == s["torch_next"]
