@@ -27,6 +27,7 @@ def _buffer_options(cfg):
 def get_dataset_loader(cfg, cwd, device, dataset_path):
     """A buffer on `device` holding every episode found under dataset_path (one directory or a list of them)."""
     buffer = ExperienceReplay_Multimodal(device=device, **_buffer_options(cfg))
+    buffer.seed = int(os.environ.get("RANK", 0))        # in-kernel dequantisation / Gaussian noise streams differ per rank
     load_dataset(cfg, cwd, buffer, dataset_path)
     return buffer
 
