@@ -57,6 +57,7 @@ class OracleConfig:
     adam_eps: float = 1e-7
     grad_clip_norm: float = 100.0
     predict_reward: bool = False     # base/algo.py:200-201: False zeroes the reward loss (shipped default)
+    worldmodel_LogProbLoss: bool = False   # -log N(o; loc, 1) instead of the squared error (base/algo.py:101-103, :375-378)
     normalization: Optional[str] = None   # None | "BatchNorm" (64x64 image encoder / decoder, encoder.py:324-337, observation_model.py:75-86)
     overshooting_distance: int = 0   # latent overshooting (base/algo.py:111-148, MoPoE/algo.py:69-108); kl_beta 0 = off
     overshooting_kl_beta: float = 0.0
@@ -736,8 +737,14 @@ def elbo(P, cfg: OracleConfig, st: dict, obs_target: Dict[str, Tensor], eps_dec:
     zeroed unless predict_reward (base/algo.py:200-201)."""
     z, qm, qs = decoder_latent(cfg, st, eps_dec)
     rec = decode(P, cfg, st["beliefs"], z, train)
-    obs_loss = {n: F.mse_loss(rec[n], obs_target[n], reduction="none").mean((0, 1)).sum()
-                for n in cfg.names_rec}
+    def point_loss(pred, target):
+        """Per-element loss: squared error, or -log N(target; pred, 1) = (target - pred)^2 / 2 + log sqrt(2 pi) with
+        worldmodel_LogProbLoss (torch.distributions.Normal.log_prob, scale 1.0)."""
+        if cfg.worldmodel_LogProbLoss:
+            return 0.5 * (target - pred) ** 2 + 0.5 * math.log(2 * math.pi)
+        return F.mse_loss(pred, target, reduction="none")
+
+    obs_loss = {n: point_loss(rec[n], obs_target[n]).mean((0, 1)).sum() for n in cfg.names_rec}
     kl = kl_loss(cfg, st)
     kl_sum = kl.clone()
     if cfg.global_kl_beta != 0:                                                    # :186-188
@@ -748,7 +755,7 @@ def elbo(P, cfg: OracleConfig, st: dict, obs_target: Dict[str, Tensor], eps_dec:
     need_reward = cfg.predict_reward
     if need_reward:                                                                 # :96-109, :175
         r = reward_model(P, cfg, st["beliefs"], z)
-        reward_loss = F.mse_loss(r, rewards[:-1], reduction="none").mean((0, 1))
+        reward_loss = point_loss(r, rewards[:-1]).mean((0, 1))
     if cfg.overshooting_kl_beta != 0:                                               # :190-193
         kl_o, r_o = latent_overshooting(P, cfg, st, actions, rewards, nonterminals, eps_over)
         kl_sum = kl_sum + kl_o

@@ -54,7 +54,7 @@ def ref_cfg(oc: O.OracleConfig, B, T):
             activation_function=dict(cnn="relu", dense=oc.act_dense, fusion="relu"),
             embedding_size=dict(oc.embedding_size), hidden_size=oc.hidden_size,
             belief_size=oc.belief_size, state_size=oc.state_size, normalization=oc.normalization,
-            worldmodel_LogProbLoss=False, overshooting_distance=oc.overshooting_distance,
+            worldmodel_LogProbLoss=oc.worldmodel_LogProbLoss, overshooting_distance=oc.overshooting_distance,
             overshooting_kl_beta=oc.overshooting_kl_beta,
             overshooting_reward_scale=oc.overshooting_reward_scale, global_kl_beta=oc.global_kl_beta, free_nats=oc.free_nats,
             kl_beta=oc.kl_beta, kl_balancing_alpha=oc.kl_balancing_alpha, learning_rate_schedule=0,
@@ -282,5 +282,8 @@ if __name__ == "__main__":
                                             observation_shapes=sound_shapes, lr=1e-5), B=2, T=4)
     gen_train("mopoe_sound_bn", O.OracleConfig(fusion="MoPoE", names_enc=("image_horizon", "sound"), names_rec=("image_horizon", "sound"),
                                                observation_shapes=sound_shapes, normalization="BatchNorm", lr=1e-5), B=2, T=4)
+    gen_train("mopoe_logprob", O.OracleConfig(fusion="MoPoE", worldmodel_LogProbLoss=True, predict_reward=True))
+    gen_train("single_logprob", O.OracleConfig(fusion="single", names_enc=("image_horizon",), names_rec=("image_horizon",),
+                                               worldmodel_LogProbLoss=True))
     gen_infer("mopoe", O.OracleConfig(fusion="MoPoE"))
     gen_infer("single", O.OracleConfig(fusion="single", names_enc=("image_horizon",), names_rec=("image_horizon",)))
