@@ -247,6 +247,7 @@ class RSSM_base(nn.Module):
             observations_target, actions, rewards, nonterminals = self._sample_data(D)
             states = self.estimate_state(observations_target, actions[:-1], rewards, nonterminals[:-1])
             _, info = self._get_model_loss(observations_target, actions, rewards, nonterminals, states)
+        self._ramp_lr()        # the reference advances its LR ramp inside _calc_loss (base/algo.py:195-198), validation included
         self.validation_info = info
         self._log(info, "validation", self.itr_optim)
         self.train()

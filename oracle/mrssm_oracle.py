@@ -57,6 +57,7 @@ class OracleConfig:
     adam_eps: float = 1e-7
     grad_clip_norm: float = 100.0
     predict_reward: bool = False     # base/algo.py:200-201: False zeroes the reward loss (shipped default)
+    learning_rate_schedule: int = 0        # > 0: Adam starts at lr 0 and gains lr/schedule per loss evaluation up to lr (base/algo.py:40-41,195-198)
     worldmodel_LogProbLoss: bool = False   # -log N(o; loc, 1) instead of the squared error (base/algo.py:101-103, :375-378)
     normalization: Optional[str] = None   # None | "BatchNorm" (64x64 image encoder / decoder, encoder.py:324-337, observation_model.py:75-86)
     overshooting_distance: int = 0   # latent overshooting (base/algo.py:111-148, MoPoE/algo.py:69-108); kl_beta 0 = off
@@ -818,11 +819,14 @@ def train_step(P: Dict[str, Tensor], opt: dict, cfg: OracleConfig, batch: dict, 
     grads = {k: leaves[k].grad for k in keys}
     total, coef = clip_coef(list(grads.values()), cfg.grad_clip_norm)
     opt["step"] = opt.get("step", 0) + 1
+    lr = cfg.lr
+    if cfg.learning_rate_schedule != 0:        # the ramp advances inside _calc_loss, i.e. before this step's update
+        lr = opt["lr"] = min(opt.get("lr", 0.0) + cfg.lr / cfg.learning_rate_schedule, cfg.lr)
     for k in keys:
         if k not in opt.setdefault("m", {}):
             opt["m"][k] = torch.zeros_like(P[k])
             opt.setdefault("v", {})[k] = torch.zeros_like(P[k])
-        adam_update(P[k], grads[k] * coef, opt["m"][k], opt["v"][k], opt["step"], cfg.lr, cfg.adam_eps)
+        adam_update(P[k], grads[k] * coef, opt["m"][k], opt["v"][k], opt["step"], lr, cfg.adam_eps)
     return {"loss_info": {k: float(v) for k, v in info.items()}, "model_loss": float(loss),
             "grads": grads, "grad_norm": float(total), "states": st}
 

@@ -57,7 +57,7 @@ def ref_cfg(oc: O.OracleConfig, B, T):
             worldmodel_LogProbLoss=oc.worldmodel_LogProbLoss, overshooting_distance=oc.overshooting_distance,
             overshooting_kl_beta=oc.overshooting_kl_beta,
             overshooting_reward_scale=oc.overshooting_reward_scale, global_kl_beta=oc.global_kl_beta, free_nats=oc.free_nats,
-            kl_beta=oc.kl_beta, kl_balancing_alpha=oc.kl_balancing_alpha, learning_rate_schedule=0,
+            kl_beta=oc.kl_beta, kl_balancing_alpha=oc.kl_balancing_alpha, learning_rate_schedule=oc.learning_rate_schedule,
             adam_epsilon=oc.adam_eps, grad_clip_norm=oc.grad_clip_norm, model_learning_rate=oc.lr)))
 
 
@@ -285,5 +285,6 @@ if __name__ == "__main__":
     gen_train("mopoe_logprob", O.OracleConfig(fusion="MoPoE", worldmodel_LogProbLoss=True, predict_reward=True))
     gen_train("single_logprob", O.OracleConfig(fusion="single", names_enc=("image_horizon",), names_rec=("image_horizon",),
                                                worldmodel_LogProbLoss=True))
+    gen_train("mopoe_lrramp", O.OracleConfig(fusion="MoPoE", learning_rate_schedule=3), steps=3)
     gen_infer("mopoe", O.OracleConfig(fusion="MoPoE"))
     gen_infer("single", O.OracleConfig(fusion="single", names_enc=("image_horizon",), names_rec=("image_horizon",)))
