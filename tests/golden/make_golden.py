@@ -285,6 +285,10 @@ if __name__ == "__main__":
     gen_train("mopoe_logprob", O.OracleConfig(fusion="MoPoE", worldmodel_LogProbLoss=True, predict_reward=True))
     gen_train("single_logprob", O.OracleConfig(fusion="single", names_enc=("image_horizon",), names_rec=("image_horizon",),
                                                worldmodel_LogProbLoss=True))
+    gen_train("mopoe_emb512", O.OracleConfig(fusion="MoPoE", embedding_size={"fusion": 1024, "image": 512, "sound": 256, "other": 64}))
+    gen_train("mopoe_img128", O.OracleConfig(fusion="MoPoE", names_enc=("image_horizon_128", "pose_quat_v2"),
+                                             names_rec=("image_horizon_128", "pose_quat_v2"),
+                                             observation_shapes={"image_horizon_128": [3, 128, 128], "pose_quat_v2": [3]}), B=2, T=4)
     gen_train("mopoe_lrramp", O.OracleConfig(fusion="MoPoE", learning_rate_schedule=3), steps=3)
     gen_infer("mopoe", O.OracleConfig(fusion="MoPoE"))
     gen_infer("single", O.OracleConfig(fusion="single", names_enc=("image_horizon",), names_rec=("image_horizon",)))

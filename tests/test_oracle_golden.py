@@ -8,7 +8,8 @@ import torch
 from oracle import mrssm_oracle as O
 
 TRAIN = ["mopoe", "poe", "nn", "single", "mopoe_clip", "poe_noalpha", "mopoe_reward", "mopoe_over", "poe_over", "single_over",
-         "mopoe_bn", "single_bn", "mopoe_sound", "mopoe_sound_bn", "mopoe_logprob", "single_logprob", "mopoe_lrramp"]
+         "mopoe_bn", "single_bn", "mopoe_sound", "mopoe_sound_bn", "mopoe_logprob", "single_logprob", "mopoe_lrramp",
+         "mopoe_emb512", "mopoe_img128"]
 
 
 def _cfg(meta):
