@@ -26,7 +26,9 @@ def _product_cfg(oc, B, T, device):
                            global_kl_beta=oc.global_kl_beta, kl_beta=oc.kl_beta, grad_clip_norm=oc.grad_clip_norm,
                            model_learning_rate=oc.lr, adam_epsilon=oc.adam_eps, predict_reward=oc.predict_reward,
                            overshooting_distance=oc.overshooting_distance, overshooting_kl_beta=oc.overshooting_kl_beta,
-                           overshooting_reward_scale=oc.overshooting_reward_scale)
+                           overshooting_reward_scale=oc.overshooting_reward_scale,
+                           worldmodel_LogProbLoss=oc.worldmodel_LogProbLoss, learning_rate_schedule=oc.learning_rate_schedule,
+                           embedding_size=dict(oc.embedding_size))
 
 
 def unflatten(flat):
