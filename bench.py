@@ -16,8 +16,11 @@ e2e     : the same steps through the public API model.optimize(D) with D handing
 roofline: the dominant kernel of the step (by device time, measured live with CUDA events around
           every C-ABI call of one extra step) — algorithmic FLOPs or bytes / its mean duration,
           against MEASURED_PEAKS.json.  `rollout_roofline` is the same for the rollout kernel.
-cpu_baseline / --impl reference: the oracle port of the reference's CPU path (oracle/), timed on
-          the host cores on a bounded sample (B=16 sequences of the same T).
+cpu_baseline / --impl reference: the UNMODIFIED reference's model.optimize(D) (oracle/_ref, staged by
+          __graft_entry__.build(); kind "reference") — or, when it is not staged, the oracle port of it (kind "port") —
+          timed on the host cores on a bounded sample (B=16 sequences of the same T).
+same_box_rollout: BASELINE configs 2 and 4 (rollout only) of this build next to the reference modules on the same
+          B200 under stock PyTorch.  strong_scaling (N > 1): the same global batch split over the ranks.
 """
 import argparse
 import json
@@ -69,19 +72,54 @@ def cpu_oracle_rate(T, fusion, sample_B=16, steps=3, warmup=1):
     return sample_B * T / med, med, torch.get_num_threads()
 
 
+def reference_rate(T, fusion, sample_B=16, steps=3, warmup=1, in_process=False):
+    """The UNMODIFIED reference (oracle/_ref, staged by __graft_entry__.build) on the host cores: model.optimize(D) at
+    B = sample_B.  Runs in its own process unless in_process (the product mirrors the names `algos` / `utils`).
+    -> (rate, seconds per step, cores, kind); falls back to the oracle port when the reference is not staged."""
+    from oracle import ref_arm
+    if ref_arm.available():
+        try:
+            if in_process:
+                r = ref_arm.time_train(sample_B, T, fusion, steps, warmup, "cpu")
+            else:
+                out = subprocess.run([sys.executable, "-m", "oracle.ref_arm", "train", "--batch", str(sample_B), "--chunk", str(T),
+                                      "--steps", str(steps), "--warmup", str(warmup), "--fusion", fusion], cwd=ROOT,
+                                     capture_output=True, text=True, timeout=900)
+                r = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+            return r["seq_steps_per_s"], r["ms_per_step"] * 1e-3, r["cores"], "reference"
+        except Exception as e:                                   # pragma: no cover
+            print(f"bench: reference arm failed ({e!r}); timing the oracle port instead", file=sys.stderr)
+    rate, med, cores = cpu_oracle_rate(T, fusion, sample_B=sample_B, steps=steps, warmup=warmup)
+    return rate, med, cores, "port"
+
+
+def same_box_reference():
+    """the reference transition model on this B200 under stock PyTorch, configs 2 and 4 (own process)."""
+    from oracle import ref_arm
+    if not ref_arm.available():
+        return None
+    try:
+        out = subprocess.run([sys.executable, "-m", "oracle.ref_arm", "samebox"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+        return json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    except Exception as e:                                       # pragma: no cover
+        print(f"bench: same-box reference arm failed ({e!r})", file=sys.stderr)
+        return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rate, med, cores = cpu_oracle_rate(args.chunk, args.fusion, sample_B=16, steps=max(1, args.steps),
-                                       warmup=max(1, min(args.warmup, 1)))
-    sample = f"B=16 of the B={args.batch} sequences, T={args.chunk}, full train step, fp32, {cores} threads"
+    rate, med, cores, kind = reference_rate(args.chunk, args.fusion, sample_B=16, steps=max(1, min(args.steps, 5)),
+                                            warmup=max(1, min(args.warmup, 1)), in_process=True)
+    what = "unmodified reference model.optimize(D)" if kind == "reference" else "fp32 oracle port of the reference step"
+    sample = f"B=16 of the B={args.batch} sequences, T={args.chunk}, full train step, {what}, fp32, {cores} threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -270,6 +308,62 @@ def roofline_of(key, d, pk, total_ms):
     return out
 
 
+def rollout_configs(model, device):
+    """BASELINE configs 2 and 4 (rollout only) through MultimodalTransitionModel.__call__, CUDA events, next to the reference
+    modules run on the same GPU under stock PyTorch (SURVEY §8d 'same box' comparator)."""
+    from mrssm_b200 import ops
+    tm = model.transition_model
+    g = torch.Generator(device=device).manual_seed(5)
+    rn = lambda *s: torch.randn(*s, device=device, generator=g)
+
+    def timed(fn, reps=5):
+        fn()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    B, T, Bi, H = 256, 49, 4096, 100
+    emb = {"image_horizon": rn(T, B, 1024), "pose_quat_v2": rn(T, B, 128)}
+    a2, nt2 = rn(T, B, 3), torch.ones(T, B, 1, device=device)
+    s0, h0 = torch.zeros(B, 30, device=device), torch.zeros(B, 200, device=device)
+    a4, s4, h4 = rn(H, Bi, 3), rn(Bi, 30), rn(Bi, 200)
+    ours = {}
+    was = ops.bf16_mode()
+    try:
+        for mode in ("bf16", "fp32"):
+            ops.set_bf16_mode(mode == "bf16")
+
+            def fwd():
+                with torch.no_grad():
+                    tm(s0, a2, h0, emb, nt2)
+
+            def fwd_bwd():
+                e = {k: v.detach().requires_grad_(True) for k, v in emb.items()}
+                out = tm(s0, a2, h0, e, nt2)
+                torch.autograd.backward(list(out[:7]), [torch.ones_like(t) for t in out[:7]])
+
+            def imagine():
+                with torch.no_grad():
+                    tm(s4, a4, h4)
+
+            for key, fn, units in (("cfg2_observe_fwd", fwd, 256 * 50), ("cfg2_observe_fwd_bwd", fwd_bwd, 256 * 50),
+                                   ("cfg4_imagine", imagine, Bi * H)):
+                ms = timed(fn)
+                ours.setdefault(key, {})[mode] = dict(ms=ms, seq_steps_per_s=units / (ms * 1e-3))
+    finally:
+        ops.set_bf16_mode(was)
+        model.model_optimizer.zero_grad()
+    return {"ours": ours, "reference_cuda_stock_pytorch": same_box_reference(),
+            "what": "config 2: observe rollout B=256 T=50 (49 steps); config 4: imagination B=4096 H=100; fp32 = exact CUDA-core "
+                    "kernels, bf16 = tcgen05 rollout; CUDA events, median of 5"}
+
+
 def run_ours(args):
     from mrssm_b200 import _lib as L
     from mrssm_b200.config import hot_path_config
@@ -310,6 +404,21 @@ def run_ours(args):
     e2e_value = world * args.batch * args.chunk / (ms_e2e / args.steps * 1e-3)
     h2d_bytes = Dh.h2d_bytes
     del Dh
+    strong = None
+    if world > 1 and args.batch % world == 0:
+        # secondary: strong scaling — the same GLOBAL batch (args.batch sequences) split over the ranks
+        cfg_s = hot_path_config(fusion=args.fusion, batch_size=args.batch // world, chunk_size=args.chunk, device=device)
+        cfg_s.train.use_amp = args.mode == "bf16"
+        torch.manual_seed(0)
+        model_s = build_RSSM(cfg_s, torch.device(device))
+        DataParallel(model_s)
+        Ds = SyntheticReplay(cfg_s, device, seed=99 + rank)
+        for _ in range(3):
+            model_s.optimize(Ds)
+        ms_s, _ = timed_steps(model_s, Ds, args.steps, sync_loss=False)
+        strong = {"global_batch": args.batch, "per_gpu_batch": args.batch // world, "ms_per_step": ms_s / args.steps,
+                  "value": args.batch * args.chunk / (ms_s / args.steps * 1e-3), "unit": UNIT}
+        del model_s, Ds
     if world > 1:
         # collectives are over: the per-kernel profile below runs on rank 0 alone (no gradient all-reduce)
         import torch.distributed as dist
@@ -328,12 +437,14 @@ def run_ours(args):
     rollout_roof = {k: roofline_of(k, agg[k], pk, total_ms) for k in ("rollout_fwd:observe", "rollout_bwd:observe", "rollout_tc_fwd:observe", "rollout_tc_bwd:observe") if k in agg}
     top = sorted(((k, d["ms"], d["n"]) for k, d in agg.items()), key=lambda x: -x[1])[:60]
 
-    cpu = None
+    cpu = same_box = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, med, cores = cpu_oracle_rate(args.chunk, args.fusion, sample_B=16, steps=3, warmup=1)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"B=16 sequences x T={args.chunk}, full train step, fp32 oracle port, median of 3 steps",
+        rate, med, cores, kind = reference_rate(args.chunk, args.fusion, sample_B=16, steps=3, warmup=1)
+        what = "unmodified reference model.optimize(D)" if kind == "reference" else "fp32 oracle port"
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"B=16 sequences x T={args.chunk}, full train step, {what}, median of 3 steps",
                "ms_per_step": med * 1e3}
+        same_box = rollout_configs(model, device)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -345,7 +456,8 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / args.steps, "last_loss": loss,
                 "input": "uint8 frames + fp32 vectors from pinned host memory, normalised on device, copy of step k+1 overlapped with step k"},
         "gpu_launches": launches,
-        "roofline": roof, "rollout_roofline": rollout_roof, "cpu_baseline": cpu, "kernel_order": list(agg.keys()),
+        "roofline": roof, "rollout_roofline": rollout_roof, "cpu_baseline": cpu, "same_box_rollout": same_box,
+        "strong_scaling": strong, "kernel_order": list(agg.keys()),
         "top_kernels_ms": [{"kernel": k, "ms_per_step": round(m, 4), "launches": n} for k, m, n in top],
         "profiled_step_kernel_ms": total_ms,
     }

@@ -4,10 +4,12 @@ Interface of the reference's algos/MRSSM/MRSSM/train.py (`get_dataset_loader`, `
 from episode directories, then `optimize` runs `train_iteration` times with `validation` every `validation_interval` and a
 checkpoint every `checkpoint_interval` iterations.  The experiment logger (hydra / wandb, utils/logger.py) is control plane
 and not part of this package, so `run` takes the three values it would hand over.  One process drives one GPU; under
-torchrun pass `dp=mrssm_b200.dist.DataParallel`; every rank samples its own chunks from numpy's global RNG, so seed it
-per rank (`np.random.seed(seed + RANK)`) or all ranks draw the same batch."""
+torchrun pass `dp=mrssm_b200.dist.DataParallel` to `run` / `train`: numpy's global RNG (chunk starts, augmentation choices)
+is then re-seeded per rank (`cfg.main.seed + RANK`) so the ranks draw different batches, and only rank 0 writes checkpoints
+(`save_model`)."""
 import os
 
+import numpy as np
 import torch
 
 from algos.MRSSM.MRSSM.algo import build_RSSM
@@ -51,6 +53,8 @@ def train(cfg, cwd, results_dir, device, dp=None):
     _restore(model, cfg, cwd)
     if dp is not None:
         dp(model)
+        rank = int(os.environ.get("RANK", 0))
+        np.random.seed(int(cfg.main.get("seed", 0) or 0) + rank)       # identical seeds would make N ranks compute one rank's gradient
     last = cfg.train.train_iteration
     for itr in range(1, last + 1):
         model.optimize(buffers["train"])
@@ -61,8 +65,14 @@ def train(cfg, cwd, results_dir, device, dp=None):
     return model
 
 
-def run(cfg, cwd=None, results_dir=None, device=None):
+def run(cfg, cwd=None, results_dir=None, device=None, dp=None):
+    """Reference run(cfg) (train.py:58-66) minus the hydra / wandb logger set-up: seeds as utils/logger.py:93-100 does."""
     cwd = cwd or os.getcwd()
     results_dir = results_dir or cwd
     os.makedirs(results_dir, exist_ok=True)
-    return train(cfg, cwd, results_dir, device or torch.device(cfg.main.device))
+    seed = int(cfg.main.get("seed", 0) or 0)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed(seed)
+    return train(cfg, cwd, results_dir, device or torch.device(cfg.main.device), dp=dp)

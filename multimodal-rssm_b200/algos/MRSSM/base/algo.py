@@ -61,6 +61,8 @@ class RSSM_base(nn.Module):
         r = self.cfg.rssm
         lr0 = 0 if r.learning_rate_schedule != 0 else r.model_learning_rate
         self.model_optimizer = FusedClipAdam(self.param_list, lr=lr0, eps=r.adam_epsilon, max_grad_norm=r.grad_clip_norm)
+        if getattr(self, "dp", None) is not None:     # rebuilt after load_model under data parallelism: re-bind the exchange
+            self.dp.attach(self.model_optimizer)
 
     def get_state_dict(self):
         raise NotImplementedError
@@ -75,7 +77,13 @@ class RSSM_base(nn.Module):
         self._init_optimizer()         # the reference rebuilds Adam after loading, dropping the moments
 
     def save_model(self, results_dir, itr):
-        torch.save(self.get_state_dict(), os.path.join(results_dir, "models_%d.pth" % itr))
+        """Every rank holds the same weights under data parallelism: rank 0 writes, everyone waits for the file."""
+        import torch.distributed as dist
+        multi = self.dp is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if not multi or dist.get_rank() == 0:
+            torch.save(self.get_state_dict(), os.path.join(results_dir, "models_%d.pth" % itr))
+        if multi:
+            dist.barrier()
 
     def _clip_obs(self, observations, idx_start=0, idx_end=None):
         return {k: v[idx_start:idx_end] for k, v in observations.items()}

@@ -4,8 +4,12 @@ YAML tree the reference composes with hydra (config/config.yaml -> main/ env/ rs
 needed by the hot path (SURVEY §8b 'Config keys actually read')."""
 import copy
 import os
+import re
 
 import yaml
+
+# PyYAML (YAML 1.1) reads `1e-7` as a string; omegaconf — which the reference's hydra entry uses — reads it as a float
+_FLOAT = re.compile(r"^[+-]?(\d+\.?\d*|\.\d+)[eE][+-]?\d+$")
 
 
 class AttrDict(dict):
@@ -27,6 +31,8 @@ def to_attr(d):
         return AttrDict({k: to_attr(v) for k, v in d.items()})
     if isinstance(d, list):
         return [to_attr(v) for v in d]
+    if isinstance(d, str) and _FLOAT.match(d):
+        return float(d)
     return d
 
 

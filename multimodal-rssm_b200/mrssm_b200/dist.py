@@ -28,13 +28,20 @@ class DataParallel:
         assert dist.is_initialized()
         self.world = dist.get_world_size()
         self.model = model
-        opt = model.model_optimizer
-        opt.grad_scale = 1.0 / self.world
-        # identical weights everywhere: broadcast rank 0's flat parameter buffer once
-        dist.broadcast(opt.flat_p, src=0)
-        self._buckets = self._plan_buckets(model, opt) if overlap else None
+        self.overlap = overlap
         self._pending, self._launched = [], []
         model.dp = self
+        self.attach(model.model_optimizer)
+
+    def attach(self, opt):
+        """(Re-)bind to the model's optimiser: called at construction and whenever the model rebuilds it (load_model ->
+        _init_optimizer): the fresh optimiser has new flat buffers, so the weights are broadcast again (rank 0's checkpoint
+        wins), the buckets are re-planned over the new gradient buffer and the 1/world scale is set."""
+        opt.grad_scale = 1.0 / self.world
+        dist.broadcast(opt.flat_p, src=0)                 # identical weights everywhere
+        self._buckets = self._plan_buckets(self.model, opt) if self.overlap else None
+        self._pending, self._launched = [], []
+        self._opt = opt
 
     @staticmethod
     def _plan_buckets(model, opt):
@@ -82,6 +89,9 @@ class DataParallel:
         self._pending.append(dist.all_reduce(self.model.model_optimizer.flat_g[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
 
     def all_reduce_grads(self, opt):
+        if opt is not getattr(self, "_opt", None):        # optimiser replaced behind our back: re-bind before exchanging
+            self.attach(opt)
+        opt.grad_scale = 1.0 / self.world                 # read at step time: the SUM below is turned into the mean by clip+Adam
         if self.world == 1:
             return
         if self._buckets is None:

@@ -52,6 +52,11 @@ class FusedClipAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         g = self.param_groups[0]
+        base, end = self.flat_g.data_ptr(), self.flat_g.data_ptr() + 4 * self.flat_g.numel()
+        for p in g["params"]:       # the kernels accumulate into p.grad; it must still be the view of the flat buffer
+            if p.grad is None or not (base <= p.grad.data_ptr() < end):
+                raise RuntimeError("FusedClipAdam: a parameter's .grad no longer aliases the flat gradient buffer "
+                                   "(zero_grad(set_to_none=True) or an external optimiser replaced it)")
         self.step_count += 1
         L.call("mrssm_clip_adam", L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.flat_m), L.ptr(self.flat_v),
                self.flat_p.numel(), self.step_count, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),

@@ -107,6 +107,8 @@ def get_data(file_name, n_crop=1, dh_base=1, dw_base=1, encoding="ASCII"):
 
 # ---- the buffer ---------------------------------------------------------------------------------------------------
 class ExperienceReplay_Multimodal:
+    _instances = 0
+
     def __init__(self, size, observation_names=["image"], observation_shapes=dict(image=[3, 64, 64]), n_crop=None,
                  dh_base=None, dw_base=None, noise_scales=None, pca_scales=None, action_name="action", action_size=None,
                  bit_depth=5, device=torch.device("cpu")):
@@ -129,6 +131,8 @@ class ExperienceReplay_Multimodal:
         self.noise_source = None            # tests: fn(kind, name, shape) -> tensor for kind in {"uniform", "gauss"}
         self._draws = 0                     # counter mixed into the kernels' hash seed
         self.seed = 0
+        ExperienceReplay_Multimodal._instances += 1
+        self._salt = ExperienceReplay_Multimodal._instances      # train / validation buffers with one seed still draw different noise
         self._init_buffer(size)
 
     def _init_buffer(self, size):
@@ -172,7 +176,15 @@ class ExperienceReplay_Multimodal:
         t = self.noise_source(kind, name, tuple(shape))
         return None if t is None else t.to(device=self.device, dtype=torch.float32).contiguous()
 
+    def _require_cuda(self):
+        if self.device.type != "cuda":
+            # the constructor keeps the reference's host default so that loading / filling can be exercised anywhere, but
+            # sampling is a CUDA gather kernel and the product has no CPU path (oracle/replay_oracle.py is test infrastructure)
+            raise RuntimeError(f"ExperienceReplay_Multimodal.sample: the store is on {self.device}; construct the buffer with "
+                               "device=torch.device('cuda:<n>') — the B200 replay buffer samples on the GPU only")
+
     def _gather_image(self, name, slots, rows, crop, delta, gauss_scale, normalise):
+        self._require_cuda()
         store = self.observations[name]
         C, Hs, Ws = store.shape[1:]
         side = crop_size_of(name) if crop is not None else None
@@ -188,14 +200,17 @@ class ExperienceReplay_Multimodal:
         a.delta, a.out = L.ptr(delta), L.ptr(out)
         a.gauss, a.gauss_scale, a.uniform = L.ptr(gauss), float(gauss_scale), L.ptr(uniform)
         self._draws += 1
-        a.seed = (int(self.seed) * 0x9E3779B1 + self._draws) & 0xFFFFFFFFFFFFFFFF
-        L.call("mrssm_replay_gather_u8", ctypes.byref(a))
+        a.seed = ((int(self.seed) * 0x9E3779B1 + self._salt) * 0x85EBCA6B + self._draws) & 0xFFFFFFFFFFFFFFFF
+        with torch.cuda.device(self.device):          # launch on the buffer's device, whichever device is current
+            L.call("mrssm_replay_gather_u8", ctypes.byref(a))
         return out
 
     def _gather_rows(self, store, slots, rows):
+        self._require_cuda()
         K = store.numel() // store.shape[0]
         out = torch.empty((rows, K), device=self.device, dtype=torch.float32)
-        L.call("mrssm_gather_rows", L.ptr(store), L.ptr_any(slots), rows, K, L.ptr(out))
+        with torch.cuda.device(self.device):
+            L.call("mrssm_gather_rows", L.ptr(store), L.ptr_any(slots), rows, K, L.ptr(out))
         return out
 
     def _plan_batch(self, idxs, crop_idx=None, pca_rand=None):

@@ -4,6 +4,11 @@ import torch
 from oracle import mrssm_oracle as O
 
 
+def to_attr(d):
+    from mrssm_b200.config import to_attr as f
+    return f(d)
+
+
 def oracle_cfg(fusion, **kw):
     if fusion == "single":
         kw.setdefault("names_enc", ("image_horizon",))
@@ -19,6 +24,17 @@ def product_cfg(oc, B, T, device, bf16=False):
 
 
 def _product_cfg(oc, B, T, device):
+    from mrssm_b200.config import hot_path_config
+    cfg = _hot_cfg(oc, B, T, device)
+    # modality set and shapes exactly as the oracle configuration names them (128x128 images, other vector names)
+    cfg.rssm.observation_names_enc = list(oc.names_enc)
+    cfg.rssm.observation_names_rec = list(oc.names_rec)
+    cfg.env.observation_shapes = to_attr({k: list(v) for k, v in oc.observation_shapes.items()})
+    cfg.env.action_size = oc.action_size
+    return cfg
+
+
+def _hot_cfg(oc, B, T, device):
     from mrssm_b200.config import hot_path_config
     return hot_path_config(fusion=oc.fusion, batch_size=B, chunk_size=T, device=device,
                            belief_size=oc.belief_size, state_size=oc.state_size, hidden_size=oc.hidden_size,

@@ -188,3 +188,53 @@ def test_bucketed_allreduce_launches_under_backward_gloo():
     # note: the hook of a bucket fires after that bucket's gradients were written, so the early launch sums final values
     torch.testing.assert_close(s0, s1)
     torch.testing.assert_close(s0, l0 + l1)
+
+
+def _reattach_worker(rank, world, port, q):
+    for p in (ROOT, os.path.join(ROOT, "multimodal-rssm_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from mrssm_b200.dist import DataParallel, init_from_env
+    init_from_env(backend="gloo")
+    model = _Model(_Opt(64, rank))
+    dp = DataParallel(model)
+    # load_model() rebuilds the optimiser (base/algo.py: _init_optimizer): fresh flat buffers, grad_scale back to 1.0,
+    # rank-dependent weights (each rank read its own file / rank 0 only has the checkpoint)
+    new = _Opt(64, 10 + rank)
+    model.model_optimizer = new
+    assert new.grad_scale == 1.0
+    g_local = new.flat_g.clone()
+    dp.all_reduce_grads(new)                     # notices the replaced optimiser: re-binds, re-broadcasts, sets the scale
+    q.put((rank, new.flat_p.clone(), g_local, new.flat_g.clone(), new.grad_scale))
+    # and the explicit path the algorithm layer takes
+    newer = _Opt(64, 20 + rank)
+    model.model_optimizer = newer
+    dp.attach(newer)
+    q.put((rank, newer.flat_p.clone(), None, None, newer.grad_scale))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_optimizer_rebuilt_after_attach_is_rebound_gloo():
+    """load_model after DataParallel was attached must not apply world x the mean gradient nor leave the ranks
+    with different weights."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_reattach_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in range(4)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    first = sorted([o for o in out if o[2] is not None], key=lambda t: t[0])
+    second = sorted([o for o in out if o[2] is None], key=lambda t: t[0])
+    (_, p0, g0, s0, sc0), (_, p1, g1, s1, sc1) = first
+    assert sc0 == sc1 == 0.5
+    torch.testing.assert_close(p0, p1)
+    torch.testing.assert_close(s0, g0 + g1)
+    torch.testing.assert_close(s0, s1)
+    torch.testing.assert_close(second[0][1], second[1][1])
+    assert second[0][4] == second[1][4] == 0.5

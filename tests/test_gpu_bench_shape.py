@@ -1,0 +1,302 @@
+"""-m gpu: the BENCHMARKED regime — bf16 tensor-core mode at BASELINE config 3's own shape (B = 1024 sequences x T = 50,
+n = 50 176 frames per conv launch: persistent 148-CTA loops, TMEM ping-pong, grid.y-split weight-gradient passes).
+
+(a) every plane conv / ConvT / weight-gradient geometry of the 64x64 stacks at n = 50 176, production layouts, against
+    torch.nn.functional.conv2d / conv_transpose2d / torch.nn.grad.conv2d_weight in fp32 (slices for the forward-type
+    kernels, all frames for the weight gradients) AND against the exact fp32 CUDA-core kernels of this library;
+(b) one full bf16 train step at B = 1024, T = 50 with fixed noise against the CPU oracle: rollout outputs of 16 of the 1 024
+    sequences (sequences are independent), and the losses, the gradient norm and the whole gradient against the oracle
+    accumulated over the 64 sub-batches of 16 sequences (every loss term is a mean over (t, b));
+(c) a 200-step loss-curve A/B of bf16 mode against fp32 mode on the same data, weights and noise.
+
+Stated bf16 tolerances (measured values are printed and recorded in DESIGN.md §4): see the asserts.
+"""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import mrssm_oracle as O
+from tests import parity_util as U
+from tests.test_gpu_tc_ops import _bf16_round, export_view
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+N_FRAMES = 1024 * 49          # BASELINE config 3: (T - 1) * B frames per launch
+
+# (Hl, Cl, Hs, Cs, k) of every plane layer of the 64x64 encoder / decoder
+LAYERS = {"E1": (64, 3, 31, 32, 4), "E2": (31, 32, 14, 64, 4), "E3": (14, 64, 6, 128, 4), "E4": (6, 128, 2, 256, 4),
+          "D2": (13, 64, 5, 128, 5), "D3": (30, 32, 13, 64, 6), "D4": (64, 3, 30, 32, 6)}
+
+
+def _slices(n):
+    return [slice(0, 96), slice(n // 2 - 37, n // 2 + 59), slice(n - 96, n)]
+
+
+def _inputs(name, n):
+    from mrssm_b200 import _lib as L, ops
+    Hl, Cl, Hs, Cs, k = LAYERS[name]
+    gen = torch.Generator(device=DEV).manual_seed(sum(map(ord, name)))
+    large = _bf16_round(torch.randn(n, Hl, Hl, Cl, device=DEV, generator=gen))
+    small = _bf16_round(torch.randn(n, Hs, Hs, Cs, device=DEV, generator=gen))
+    w = _bf16_round(torch.randn(Cs, Cl, k, k, device=DEV, generator=gen) / (Cl * k * k) ** 0.5)
+    return L, ops, large, small, w
+
+
+def _ref_down(large, w, bias, relu=True):
+    y = F.conv2d(large.permute(0, 3, 1, 2), w, bias, stride=2)
+    return (F.relu(y) if relu else y).permute(0, 2, 3, 1)
+
+
+def _ref_up(small, w, bias, Hl, relu=False, mask=None):
+    k = w.shape[-1]
+    Hs = small.shape[1]
+    y = F.conv_transpose2d(small.permute(0, 3, 1, 2), w, bias, stride=2, output_padding=Hl - (2 * (Hs - 1) + k))
+    y = F.relu(y) if relu else y
+    y = y.permute(0, 2, 3, 1)
+    return y if mask is None else y * (mask > 0)
+
+
+def _ref_wgrad(large, small, wshape, chunk=3136):
+    acc = torch.zeros(wshape, device=large.device, dtype=torch.float64)
+    for i in range(0, large.shape[0], chunk):
+        acc += torch.nn.grad.conv2d_weight(large[i:i + chunk].permute(0, 3, 1, 2), wshape, small[i:i + chunk].permute(0, 3, 1, 2),
+                                           stride=2).double()
+    return acc.float()
+
+
+def _simt(ops, L, fn, geom, large_t4, small_t4, w, bias=None, act=0, mask=None, mask_mode=0):
+    k, Cl = geom[7], geom[3]
+    ops._conv(fn, geom, large_t4, small_t4, L.ptr(w), Cl * k * k, k * k, None if bias is None else L.ptr(bias), act,
+              None if mask is None else L.ptr(mask), mask_mode)
+
+
+@pytest.mark.parametrize("name", ["E2", "E3", "E4", "D2", "D3"])
+def test_plane_layers_at_bench_frame_count(name):
+    """8+-channel layers, production layouts: `large` parity-planar, `small` planar."""
+    n = N_FRAMES
+    L, ops, large, small, w = _inputs(name, n)
+    Hl, Cl, Hs, Cs, k = LAYERS[name]
+    Clp, Csp = ops.pad8(Cl), ops.pad16(Cs)
+    gp = (n, Hl, Hl, Clp, Hs, Hs, Csp, k)
+    lb = ops.pl_import(L.nhwc(large, Hl, Hl, Cl), n, Hl, Hl, Cl, Clp, "parity", DEV)
+    sb = ops.pl_import(L.nhwc(small, Hs, Hs, Cs), n, Hs, Hs, Cs, Csp, "planar", DEV)
+    bias_s, bias_l = torch.randn(Cs, device=DEV), torch.randn(Cl, device=DEV)
+    # down: Conv2d forward (+bias, ReLU) == ConvTranspose2d dgrad
+    out = ops.new_act(n, Hs, Hs, Csp, "parity", DEV)
+    ops.pl_conv_down(gp, lb[1], out[1], ops.pl_pack_weight(w, ops.DOWN, Csp, Clp), bias_s, Cs, Csp, act=ops.RELU)
+    o = export_view(out[0], "parity", n, Hs, Hs, Csp)[..., :Cs]
+    for sl in _slices(n):
+        torch.testing.assert_close(o[sl], _ref_down(large[sl], w, bias_s), rtol=1e-2, atol=1e-2)
+        m = sl.stop - sl.start
+        ref = torch.empty(m, Hs, Hs, Cs, device=DEV)
+        _simt(ops, L, "mrssm_conv_down", (m, Hl, Hl, Cl, Hs, Hs, Cs, k), L.nhwc(large[sl], Hl, Hl, Cl), L.nhwc(ref, Hs, Hs, Cs), w, bias_s, ops.RELU)
+        torch.testing.assert_close(o[sl], ref, rtol=1e-2, atol=1e-2)
+    del out, o
+    # up with the ReLU mask of `large`: Conv2d dgrad (floor geometries included) == ConvTranspose2d forward when exact
+    out = ops.new_act(n, Hl, Hl, Clp, "planar", DEV)
+    ops.pl_conv_up(gp, out[1], sb[1], ops.pl_pack_weight(w, ops.UP, Csp, Clp), None, Cl, Clp, mask=lb[1], mask_mode=ops.RELU)
+    o = export_view(out[0], "planar", n, Hl, Hl, Clp)[..., :Cl]
+    for sl in _slices(n):
+        torch.testing.assert_close(o[sl], _ref_up(small[sl], w, None, Hl, mask=large[sl]), rtol=1e-2, atol=1e-2)
+        m = sl.stop - sl.start
+        ref = torch.empty(m, Hl, Hl, Cl, device=DEV)
+        _simt(ops, L, "mrssm_conv_up", (m, Hl, Hl, Cl, Hs, Hs, Cs, k), L.nhwc(ref, Hl, Hl, Cl), L.nhwc(small[sl], Hs, Hs, Cs), w, None, 0,
+              large[sl].contiguous(), ops.RELU)
+        torch.testing.assert_close(o[sl], ref, rtol=1e-2, atol=1e-2)
+    if Hl == 2 * (Hs - 1) + k:
+        ops.pl_conv_up(gp, out[1], sb[1], ops.pl_pack_weight(w, ops.UP, Csp, Clp), bias_l, Cl, Clp, act=ops.RELU)
+        o = export_view(out[0], "planar", n, Hl, Hl, Clp)[..., :Cl]
+        for sl in _slices(n):
+            torch.testing.assert_close(o[sl], _ref_up(small[sl], w, bias_l, Hl, relu=True), rtol=1e-2, atol=1e-2)
+    del out, o
+    # weight gradient over ALL frames (E4 runs on the NHWC implicit-GEMM kernel in the product: both routes are checked)
+    ref = _ref_wgrad(large, small, w.shape)
+    scale = float(ref.abs().max())
+    dw = torch.zeros_like(w)
+    ops.pl_conv_wgrad(gp, lb[1], sb[1], L.ptr(dw), Cl * k * k, k * k, Cs, Cl)
+    err = float((dw - ref).abs().max()) / scale
+    print(f"[bench-shape] {name} wgrad (plane) max err / max|ref| = {err:.2e}")
+    assert err <= 2e-3
+    if name == "E4":
+        xn = ops.pl_copy(lb[1], n, Hl, Hl, Clp, "nhwc", DEV)[0]
+        gn = ops.pl_import(L.nhwc(small, Hs, Hs, Cs), n, Hs, Hs, Cs, Csp, "nhwc", DEV)[0]
+        dw2 = torch.zeros_like(w)
+        ops.tc_conv_wgrad(gp, L.nhwc(xn, Hl, Hl, Clp), L.nhwc(gn, Hs, Hs, Csp), L.ptr(dw2), Cl * k * k, k * k, Cs, Cl)
+        err = float((dw2 - ref).abs().max()) / scale
+        print(f"[bench-shape] E4 wgrad (NHWC implicit GEMM) max err / max|ref| = {err:.2e}")
+        assert err <= 2e-3
+    # bias gradient (column sums) over all frames
+    acc = torch.zeros(Cs, device=DEV)
+    ops.pl_colsum(sb[1], n, Hs, Hs, Csp, Cs, acc)
+    torch.testing.assert_close(acc, small.sum(dim=(0, 1, 2), dtype=torch.float64).float(), rtol=1e-3, atol=1e-2 + 1e-4 * (n * Hs * Hs) ** 0.5)
+
+
+@pytest.mark.parametrize("name", ["E1", "D4"])
+def test_three_channel_layers_at_bench_frame_count(name):
+    """The image layers (space-to-depth sources): first Conv2d forward / last ConvTranspose2d dgrad, their weight gradients,
+    and the last ConvTranspose2d forward with the fused reconstruction loss."""
+    n = N_FRAMES
+    L, ops, large, small, w = _inputs(name, n)
+    Hl, Cl, Hs, Cs, k = LAYERS[name]
+    Csp, H2 = ops.pad16(Cs), (Hl + 1) // 2
+    gp = (n, Hl, Hl, 16, Hs, Hs, Csp, k)
+    lt, lv = ops.pl_import_s2d(L.nhwc(large, Hl, Hl, Cl), n, Hl, Hl, Cl, DEV)
+    bias = torch.randn(Cs, device=DEV)
+    out = ops.new_act(n, Hs, Hs, Csp, "parity", DEV)
+    ops.pl_conv_down(gp, lv, out[1], ops.pl_pack_weight(w, ops.DOWN_S2D, Csp, 16, Cl), bias, Cs, Csp, act=ops.RELU, s2d_cq=Cl)
+    o = export_view(out[0], "parity", n, Hs, Hs, Csp)[..., :Cs]
+    for sl in _slices(n):
+        torch.testing.assert_close(o[sl], _ref_down(large[sl], w, bias), rtol=1e-2, atol=1e-2)
+    del out, o
+    sb = ops.pl_import(L.nhwc(small, Hs, Hs, Cs), n, Hs, Hs, Cs, Csp, "planar", DEV)
+    ref = _ref_wgrad(large, small, w.shape)
+    dw = torch.zeros_like(w)
+    ops.pl_conv_wgrad(gp, lv, sb[1], L.ptr(dw), Cl * k * k, k * k, Cs, Cl, s2d_cq=Cl)
+    err = float((dw - ref).abs().max()) / float(ref.abs().max())
+    print(f"[bench-shape] {name} wgrad (space-to-depth) max err / max|ref| = {err:.2e}")
+    assert err <= 2e-3
+    if name != "D4":
+        return
+    # last ConvTranspose2d + fused MSE: loss value over all frames, residual on slices
+    Clp = ops.pad8(Cl)
+    gpu = (n, Hl, Hl, Clp, Hs, Hs, Csp, k)
+    w_up = _bf16_round(w / 3.0)
+    bias_l = torch.randn(Cl, device=DEV) * 0.1
+    target = torch.rand(n, Cl, Hl, Hl, device=DEV) - 0.5
+    resid = ops.new_act(n, H2, H2, 16, "planar", DEV)
+    total = torch.zeros(1, device=DEV)
+    ops.pl_conv_up_mse(gpu, resid[1], sb[1], ops.pl_pack_weight(w_up, ops.UP, Csp, Clp), bias_l, Cl, Clp, target,
+                       L.nchw(target, Hl, Hl, Cl), total, 1.0 / n)
+    loss_ref = 0.0
+    for i in range(0, n, 3136):
+        rec = _ref_up(small[i:i + 3136], w_up, bias_l, Hl)
+        loss_ref += float(((rec - target[i:i + 3136].permute(0, 2, 3, 1)) ** 2).sum(dtype=torch.float64))
+    loss_ref /= n
+    rel = abs(float(total[0]) - loss_ref) / loss_ref
+    print(f"[bench-shape] D4 fused reconstruction loss: kernel {float(total[0]):.4f} torch {loss_ref:.4f} rel {rel:.2e}")
+    assert rel <= 1e-4
+    r = export_view(resid[0], "planar", n, H2, H2, 16)
+    for sl in _slices(n):
+        d = _ref_up(small[sl], w_up, bias_l, Hl) - target[sl].permute(0, 2, 3, 1)
+        for par in range(4):
+            sub = d[:, par >> 1::2, par & 1::2, :]
+            torch.testing.assert_close(r[sl][:, :sub.shape[1], :sub.shape[2], par * Cl:(par + 1) * Cl], sub, rtol=1e-2, atol=1e-2)
+
+
+def _oracle_loss_and_grads(P, oc, batch, noise):
+    """Loss terms and gradients of one batch, no optimiser update (oracle/mrssm_oracle.train_step minus Adam)."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
+    tgt = {n: o[1:] for n, o in batch["obs"].items()}
+    st = O.estimate_state(leaves, oc, {n: tgt[n] for n in oc.names_enc}, batch["actions"][:-1], batch["nonterminals"][:-1],
+                          noise["eps_prior"], noise["eps_post"])
+    loss, info = O.elbo(leaves, oc, st, tgt, noise.get("eps_dec"), batch.get("rewards"), batch["actions"], batch["nonterminals"],
+                        noise.get("eps_over"))
+    loss.backward()
+    grads = {k: v.grad for k, v in leaves.items() if v.grad is not None}
+    return {k: float(v) for k, v in info.items()}, grads, {k: (v.detach() if torch.is_tensor(v) else v) for k, v in st.items()}
+
+
+def _sub_batch(batch, noise, idx):
+    b = {"obs": {k: v[:, idx] for k, v in batch["obs"].items()}, "actions": batch["actions"][:, idx],
+         "rewards": batch["rewards"][:, idx], "nonterminals": batch["nonterminals"][:, idx]}
+    return b, {k: v[:, idx] for k, v in noise.items()}
+
+
+def test_bench_shape_train_step_matches_oracle():
+    """One bf16 step at B = 1024, T = 50 (the bench.py workload) against the fp32 CPU oracle."""
+    B, T, CH = 1024, 50, 16
+    torch.set_num_threads(os.cpu_count())
+    oc = U.oracle_cfg("MoPoE")
+    model, P = U.build_product(oc, B, T, DEV, bf16=True)
+    named = U.named_params(model, oc)
+    batch, noise = O.synthetic_batch(oc, B, T, seed=1234)
+    st = U.product_step(model, oc, batch, noise, DEV)
+    info = {k: float(v) for k, v in model.loss_info.items()}
+    gn = float(model.model_optimizer.grad_norm)
+    mine = {k: named[k].grad.detach().cpu().clone() for k in P}
+
+    # (i) rollout outputs of 16 sequences spread over the CTAs of the rollout kernel (32 sequences per CTA)
+    pick = torch.tensor([(37 + 61 * i) % B for i in range(CH)])
+    sb, sn = _sub_batch(batch, noise, pick)
+    _, _, ref_st = _oracle_loss_and_grads(P, oc, sb, sn)
+    state_err = 0.0
+    for k, v in ref_st.items():
+        items = v.items() if isinstance(v, dict) else [(None, v)]
+        for nme, t in items:
+            if t is None:
+                continue
+            got = (st[k][nme] if nme is not None else st[k]).detach().cpu()[:, pick]
+            state_err = max(state_err, float((got - t).abs().max() / (t.abs().max() + 1e-6)))
+    # (ii) losses and gradients: every term is a mean over (t, b), so the batch result is the mean over sub-batches
+    acc_info, acc_g = {}, {}
+    for c in range(B // CH):
+        idx = torch.arange(c * CH, (c + 1) * CH)
+        cb, cn = _sub_batch(batch, noise, idx)
+        ci, cg, _ = _oracle_loss_and_grads(P, oc, cb, cn)
+        for k, v in ci.items():
+            acc_info[k] = acc_info.get(k, 0.0) + v * CH / B
+        for k, g in cg.items():
+            acc_g[k] = acc_g.get(k, 0) + g.double() * (CH / B)
+    loss_rel = max(abs(info[k] - v) / abs(v) for k, v in acc_info.items() if abs(v) > 1e-6)
+    ref_gn = sum(float((g ** 2).sum()) for g in acc_g.values()) ** 0.5
+    num = sum(float(((mine[k].double() - g) ** 2).sum()) for k, g in acc_g.items())
+    fro = (num / ref_gn ** 2) ** 0.5
+    worst = max(((float(((mine[k].double() - g) ** 2).sum()) / max(float((g ** 2).sum()), 1e-30)) ** 0.5, k) for k, g in acc_g.items()
+                if float((g ** 2).sum()) ** 0.5 > 1e-3 * ref_gn)
+    rep = dict(state_err=state_err, loss_rel=loss_rel, gnorm_rel=abs(gn - ref_gn) / ref_gn, grad_rel_fro=fro,
+               worst_tensor=worst, losses=info, oracle_losses=acc_info, grad_norm=gn, oracle_grad_norm=ref_gn)
+    print("[bench-shape] B=1024 T=50 bf16 step vs oracle:", rep)
+    assert state_err < 2e-2, rep
+    assert loss_rel < 5e-3, rep
+    assert rep["gnorm_rel"] < 2e-2, rep
+    assert fro < 5e-2, rep
+    for k in P:
+        if k not in acc_g:
+            assert float(mine[k].abs().max()) == 0.0, f"{k} should get no gradient"
+
+
+def test_bf16_and_fp32_modes_loss_curves_agree():
+    """200 optimisation steps from the same weights on the same data and noise: bf16 tensor-core mode against the exact fp32
+    mode.  Stated gap: every step's model loss within 2 % of the fp32 curve, the mean over the last 50 steps within 1 %."""
+    from algos.MRSSM.MRSSM.algo import build_RSSM
+    from mrssm_b200.config import hot_path_config
+    B, T, STEPS = 64, 50, 200
+    g = torch.Generator(device=DEV).manual_seed(99)
+    data = []
+    for _ in range(4):
+        u8 = torch.randint(0, 256, (T, B, 3, 64, 64), generator=g, device=DEV)
+        img = torch.floor(u8 / 8) / 32 - 0.5 + torch.rand((T, B, 3, 64, 64), generator=g, device=DEV) / 32
+        nt = torch.ones(T, B, 1, device=DEV)
+        nt[T // 3, ::7, 0] = 0
+        data.append(({"image_horizon": img, "pose_quat_v2": torch.randn(T, B, 3, generator=g, device=DEV)},
+                     torch.randn(T, B, 3, generator=g, device=DEV), torch.zeros(T, B, device=DEV), nt))
+
+    class D:
+        def __init__(self):
+            self.i = 0
+
+        def sample(self, n, L):
+            self.i += 1
+            return list(data[self.i % len(data)])
+
+    curves = {}
+    for mode in ("fp32", "bf16"):
+        cfg = hot_path_config(fusion="MoPoE", batch_size=B, chunk_size=T, device=DEV)
+        cfg.train.use_amp = mode == "bf16"
+        torch.manual_seed(0)
+        model = build_RSSM(cfg, torch.device(DEV))
+        src, losses = D(), []
+        for s in range(STEPS):
+            torch.manual_seed(1000 + s)          # identical reparameterisation noise in both modes
+            model.optimize(src)
+            losses.append(model.model_loss)
+        curves[mode] = torch.stack(losses).cpu()
+    a, b = curves["fp32"], curves["bf16"]
+    rel = ((b - a).abs() / a.abs())
+    tail = abs(float(b[-50:].mean() - a[-50:].mean())) / float(a[-50:].mean())
+    print(f"[bench-shape] loss curves: fp32 {float(a[0]):.2f} -> {float(a[-1]):.2f}, bf16 {float(b[0]):.2f} -> {float(b[-1]):.2f}; "
+          f"max step gap {float(rel.max()):.3e}, mean gap {float(rel.mean()):.3e}, last-50 mean gap {tail:.3e}")
+    assert float(a[-1]) < 0.7 * float(a[0]), "the fp32 run should be learning"
+    assert float(rel.max()) < 2e-2 and tail < 1e-2

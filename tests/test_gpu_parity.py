@@ -24,7 +24,10 @@ def test_train_step_matches_oracle(fusion, kw):
 
 
 @pytest.mark.parametrize("name", ["mopoe", "poe", "nn", "single", "mopoe_clip", "poe_noalpha", "mopoe_reward",
-                                  "mopoe_over", "poe_over", "single_over"])
+                                  "mopoe_over", "poe_over", "single_over",
+                                  # LogProb loss (base/algo.py:164-167), LR ramp (:208-212), fc branch of the conv encoder
+                                  # (encoder.py:261-262), 128x128 stacks (encoder.py:415-509, observation_model.py:162-229)
+                                  "mopoe_logprob", "single_logprob", "mopoe_lrramp", "mopoe_emb512", "mopoe_img128"])
 def test_train_step_matches_reference_fixture(name, golden_dir):
     """Directly against tests/golden/train_*.pt (outputs of the unmodified reference)."""
     rec = torch.load(os.path.join(golden_dir, f"train_{name}.pt"), weights_only=False)
