@@ -159,6 +159,19 @@ typedef struct mrssm_pl_conv_args {
     const float* mse_target;
     float* mse_sum;
     float mse_scale;
+    /* wgrad: bias gradient of the same layer from the operand tile that is already in shared memory (autograd of the `+ bias`
+     * of nn.Conv2d encoder.py:315-322 / nn.ConvTranspose2d observation_model.py:65-74).  dbias[c] += scale * sum over every
+     * pixel of channel c of `small` (dbias_from = 1: Conv2d, the gradient is the small tensor, cs_valid channels) or of
+     * `large` (dbias_from = 2: ConvTranspose2d, cl_valid channels; with s2d_cq the four parity copies fold onto channel c).
+     * Replaces a separate pass over the gradient tensor (mrssm_pl_colsum). */
+    float* dbias;
+    int32_t dbias_from;
+    /* ReLU sign bits, one bit per element, byte (pixel, 8-channel chunk) at [img][y][x][C/8] of the OUTPUT tensor:
+     * relu_bits_out (down / up with act = ReLU): written by the epilogue, bit = output > 0;
+     * relu_bits_in  (down / up, mask_mode = ReLU, instead of `mask`): the act'-mask of a dgrad, 1/16 of the bytes of the
+     * bf16 activation it stands for. */
+    uint8_t* relu_bits_out;
+    const uint8_t* relu_bits_in;
 } mrssm_pl_conv_args;
 
 int mrssm_pl_conv_down(const mrssm_pl_conv_args* a, void* stream);
@@ -184,6 +197,9 @@ int mrssm_pl_colsum(const mrssm_tv* x, int32_t n_img, int32_t H, int32_t W, int3
 int mrssm_pl_describe(const mrssm_pl_conv_args* a, int32_t op, char* buf, int32_t buflen);
 /* bring-up switches (descriptor-field variants); 0 = production setting */
 int mrssm_pl_set_debug(int32_t key, int32_t value);
+/* tuning aid: force the forward-type planner's tiling (images per tile, rows per band, activation stages, resident weights
+ * 0/1, weight-ring slots); 0 / -1 = planner's choice.  Production plans come from the built-in measured table. */
+int mrssm_pl_set_plan_override(int32_t BI, int32_t TH, int32_t NA, int32_t bres, int32_t NB);
 /* tuning aid: device buffer of 148*16*8 int64 receiving per-tile clock64 stamps of the fwd-type kernel (NULL = off) */
 int mrssm_pl_set_profile_buffer(void* dev_buf);
 

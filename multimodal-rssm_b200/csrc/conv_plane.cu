@@ -30,6 +30,11 @@ constexpr int NTHREADS = 256;
 constexpr int SMEM_TOTAL = 227 * 1024 - 9216;   // dynamic budget: 227 KB minus the 1 KB alignment slack and the static barriers/tables
 
 long long* g_prof = nullptr;    // optional device buffer for in-kernel clock64 timelines (bring-up / tuning)
+// tuning aid (mrssm_pl_set_plan_override): force the tiling of the forward-type planner.  0 / -1 = let the planner choose.
+struct PlanOvr {
+    int BI, TH, NA, bres, NB;
+};
+PlanOvr g_ovr = {0, 0, 0, -1, 0};
 int g_dbg[4] = {0, 0, 0, 0};   // spare bring-up switches
 
 struct T4 {
@@ -241,6 +246,11 @@ struct FwdP {
     float* mse_sum;
     float mse_scale;
     int mse_vec;                // target rows are x-contiguous and 8-byte aligned: float2 loads
+    // fast epilogue (bf16 output, act none / ReLU, every item inside one parity class): nc columns per item (16, 32 or 64)
+    int fast, ncp, nc;
+    uint8_t* bits_out;          // ReLU sign bits of the output, byte (pixel, 8-channel chunk) at [img][y][x][Cop/8]
+    const uint8_t* bits_in;     // act'-mask of a dgrad in the same form (instead of the bf16 `mask` view)
+    long long bits_img_bytes;   // bytes of one image of bits_in (L2 prefetch per tile)
 };
 #define PROF(slot) do { if (P.prof && lit < 16) P.prof[((long long)blockIdx.x * 16 + lit) * 8 + (slot)] = clock64(); } while (0)
 
@@ -368,7 +378,127 @@ __device__ __forceinline__ void mse_row(const FwdP& P, const float (&v)[32], con
     }
 }
 
-template <int OP, bool F32>
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+        "%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// prmt with sign replication: every byte of the result is 0xFF / 0x00 from the msb of the selected source byte
+__device__ __forceinline__ uint32_t half_masks_from_flags(uint32_t w) {      // bit 15 -> low half, bit 31 -> high half
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(d) : "r"(w));
+    return d;
+}
+__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m) { return (a & m) | (b & ~m); }
+
+// ReLU sign byte of 8 channels held as four packed bf16x2 words (values >= +0): bit (3 - j) = channel 2j > 0, bit (7 - j) =
+// channel 2j + 1 > 0.  (x + 0x7FFF per half sets the half's msb iff the half is non-zero.)
+__device__ __forceinline__ uint32_t relu_byte(const uint32_t (&p)[4]) {
+    uint32_t r = p[0] + 0x7FFF7FFFu;
+    r = bitsel(r, (p[1] + 0x7FFF7FFFu) >> 1, 0x80008000u);
+    r = bitsel(r, (p[2] + 0x7FFF7FFFu) >> 2, 0xC000C000u);
+    r = bitsel(r, (p[3] + 0x7FFF7FFFu) >> 3, 0xE000E000u);
+    return ((r >> 12) & 0xFu) | ((r >> 24) & 0xF0u);
+}
+// keep the halves of the four packed words whose flag bit is set in the sign byte b
+__device__ __forceinline__ void apply_relu_byte(uint32_t (&p)[4], uint32_t b) {
+    const uint32_t e = (b & 0xFu) | ((b & 0xF0u) << 12);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] &= half_masks_from_flags(e << (12 + j));
+}
+// the same from a bf16 activation (act'-mask given as the forward output itself): half > 0
+__device__ __forceinline__ void apply_relu_bf16(uint32_t (&p)[4], const uint4 m) {
+    const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t nz = (mw[j] & 0x7FFF7FFFu) + 0x7FFF7FFFu;          // msb of a half = magnitude non-zero
+        p[j] &= half_masks_from_flags(nz & ~mw[j]);                      // and not negative
+    }
+}
+
+// One epilogue item of the fast path: 32 rows (this warp's TMEM lanes) x NC accumulator columns that lie inside one
+// parity class -> bias, ReLU, act'-mask, scale, bf16 pack, one 16-byte store per 8 channels, optional sign bytes out.
+template <int OP, int NC>
+__device__ __forceinline__ void epi_fast_item(const FwdP& P, const float* bias_s, uint32_t taddr, bool row_ok, int img, int y, int x, int n0,
+                                              float oscale) {
+    int cls = 0, cl0 = n0;
+    if (OP == OP_UP) {
+        cls = n0 / P.Cop;
+        cl0 = n0 - cls * P.Cop;
+    }
+    const int yy = OP == OP_UP ? 2 * y + (cls >> 1) : y, xx = OP == OP_UP ? 2 * x + (cls & 1) : x;
+    const bool ok = row_ok && yy < P.Ho && xx < P.Wo;
+    bf16* o_ptr = nullptr;
+    const bf16* m_ptr = nullptr;
+    long long boff = 0;
+    if (ok) {
+        o_ptr = (bf16*)P.out.p + tv_pix(P.out, img, yy, xx) + (cl0 >> 3) * P.out.sK;
+        boff = ((long long)(img * P.Ho + yy) * P.Wo + xx) * (P.Cop >> 3) + (cl0 >> 3);
+        if (!P.bits_in && P.mask_mode) m_ptr = (const bf16*)P.mask.p + tv_pix(P.mask, img, yy, xx) + (cl0 >> 3) * P.mask.sK;
+    }
+    constexpr int W = NC >= 32 ? 32 : 16;          // columns per tcgen05.ld (one sign word of W / 8 bytes each)
+#pragma unroll
+    for (int c0 = 0; c0 < NC; c0 += W) {
+        float v[W];
+        if (W == 32) tmem_ld32_nowait(taddr + c0, v);
+        else tmem_ld16_nowait(taddr + c0, v);
+        uint32_t mb = 0xFFFFFFFFu, ob = 0;
+        uint4 mk[W / 8];
+        if (ok && P.bits_in) {
+            if (W == 32) mb = __ldg(reinterpret_cast<const unsigned int*>(P.bits_in + boff + (c0 >> 3)));
+            else mb = __ldg(reinterpret_cast<const unsigned short*>(P.bits_in + boff + (c0 >> 3)));
+        }
+        if (m_ptr) {
+#pragma unroll
+            for (int j = 0; j < W / 8; ++j) mk[j] = __ldg(reinterpret_cast<const uint4*>(m_ptr + (long long)((c0 >> 3) + j) * P.mask.sK));
+        }
+        tmem_wait_ld();
+        if (ok) {
+#pragma unroll
+            for (int j = 0; j < W / 8; ++j) {
+                const float* vv = v + 8 * j;
+                const int cl = cl0 + c0 + 8 * j;
+                const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cl), b1 = *reinterpret_cast<const float4*>(bias_s + cl + 4);
+                float t[8] = {vv[0] + b0.x, vv[1] + b0.y, vv[2] + b0.z, vv[3] + b0.w, vv[4] + b1.x, vv[5] + b1.y, vv[6] + b1.z, vv[7] + b1.w};
+                if (P.act == MRSSM_ACT_RELU) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) t[e] = fmaxf(t[e], 0.f);
+                }
+                if (P.scale_ptr) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) t[e] *= oscale;
+                }
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(t[2 * e], t[2 * e + 1]);
+                    pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                if (P.bits_in) apply_relu_byte(pk, (mb >> (8 * j)) & 0xFFu);
+                else if (m_ptr) apply_relu_bf16(pk, mk[j]);
+                if (P.bits_out) ob |= relu_byte(pk) << (8 * j);
+                *reinterpret_cast<uint4*>(o_ptr + (long long)((c0 >> 3) + j) * P.out.sK) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            if (P.bits_out) {
+                if (W == 32) *reinterpret_cast<unsigned int*>(P.bits_out + boff + (c0 >> 3)) = ob;
+                else *reinterpret_cast<unsigned short*>(P.bits_out + boff + (c0 >> 3)) = (unsigned short)ob;
+            }
+        }
+    }
+}
+
+// NC = 0: generic epilogue (fp32 outputs, fused loss, ELU, odd widths); NC = 16 / 32 / 64: the fast bf16 epilogue with NC
+// accumulator columns per item (a kernel of its own, so neither path pays for the other's registers)
+template <int OP, bool F32, int NC>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUtensorMap mA2,
                  const __grid_constant__ CUtensorMap mA3, const __grid_constant__ CUtensorMap mB, const __grid_constant__ FwdP P) {
@@ -413,6 +543,20 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                 mbar_expect_tx(bar, (uint32_t)P.planes * (uint32_t)P.plane_bytes);
                 const int ig = tile / P.n_bands, band = tile - ig * P.n_bands;
                 const uint32_t dst = smemA + (uint32_t)sa * (uint32_t)P.a_stage_bytes;
+                if (P.bits_img_bytes > 0 && band == 0) {
+                    // the sign bytes of this tile's images: pull them into L2 a tile ahead of the epilogue's loads (16-byte granules)
+                    const int i0 = ig * P.BI, ni = min(P.BI, P.n_img - i0);
+                    const uintptr_t lo = ((uintptr_t)P.bits_in + (uintptr_t)((long long)i0 * P.bits_img_bytes)) & ~(uintptr_t)15;
+                    const uintptr_t hi = ((uintptr_t)P.bits_in + (uintptr_t)((long long)(i0 + ni) * P.bits_img_bytes) + 15) & ~(uintptr_t)15;
+                    const char* mp = (const char*)lo;
+                    long long left = (long long)(hi - lo);
+                    while (left > 0) {
+                        const uint32_t sz = (uint32_t)(left < 65536 ? left : 65536);
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(mp), "r"(sz) : "memory");
+                        mp += sz;
+                        left -= sz;
+                    }
+                }
                 if ((P.mask_img_bytes > 0 || P.tgt_img_bytes > 0) && band == 0) {
                     // the epilogue of this tile reads the act'-mask (forward activation) / the loss target straight from HBM, a few
                     // bytes per lane with the miss latency exposed: pull the tile's images into L2 now, a tile ahead of their use
@@ -562,9 +706,9 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         // Four warps share each TMEM lane quarter.  A pass is cut into items (128-row block, column part); the
         // warps of a quarter take items round-robin.
         const int e = warp - 4, q = e & 3, part = e >> 2;
-        const bool mse = F32 && OP == OP_UP && P.mse_target != nullptr;       // fused reconstruction loss: whole rows per warp
+        const bool mse = NC == 0 && F32 && OP == OP_UP && P.mse_target != nullptr;       // fused reconstruction loss: whole rows per warp
         // column parts per block: narrow outputs stay whole (the row decode is amortised over more columns)
-        const int ncp = mse ? 1 : ((P.BN % 64 == 0 && P.BN >= 128) ? 4 : ((P.BN % 32 == 0 && P.BN >= 64) ? 2 : 1));
+        const int ncp = P.ncp;
         const int ncols = P.BN / ncp;
         const int IP = P.BY * P.BX;
         const float oscale = P.scale_ptr ? __ldg(P.scale_ptr) * P.scale_mul : 1.f;
@@ -601,6 +745,10 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                         if (P.mask_mode) m_base = tv_pix(P.mask, img, y, x);
                     }
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * P.set_cols + mb * P.BN + col0);
+                    if (NC > 0) {
+                        epi_fast_item<OP, NC == 0 ? 16 : NC>(P, bias_s, taddr, row_ok, img, y, x, n0, oscale);
+                        continue;
+                    }
                     if (mse) {
                         // columns = (parity class, channel): exactly the space-to-depth pixel (y, x) of the residual
                         float v[32];
@@ -697,6 +845,24 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
 // ---------------------------------------------------------------------------------------------------
 // planner for the forward-type kernel
 // ---------------------------------------------------------------------------------------------------
+// Tilings measured on B200 for the layer geometries of the shipped 64x64 stacks at large frame counts (profiles/sweep_plans.py);
+// anything else takes the planner's heuristic.  Key: op, space-to-depth source, (Hl, Cl, Hs, Cs, k) with padded channels.
+struct TunedPlan {
+    int op, s2d, Hl, Cl, Hs, Cs, k;
+    int BI, TH, NA, bres, NB;
+};
+const TunedPlan kTuned[] = {
+    {-1, 0, 0, 0, 0, 0, 0, 0, 0, 0, -1, 0},
+};
+const TunedPlan* find_tuned(const mrssm_pl_conv_args* a, int op) {
+    if (a->n_img < 1024) return nullptr;             // small launches: the heuristic (few tiles, fill matters more than overlap)
+    for (const TunedPlan& t : kTuned)
+        if (t.op == op && t.s2d == (a->s2d_cq > 0) && t.Hl == a->Hl && t.Cl == a->Cl && t.Hs == a->Hs && t.Cs == a->Cs && t.k == a->ksz &&
+            a->Hl == a->Wl && a->Hs == a->Ws)
+            return &t;
+    return nullptr;
+}
+
 int plan_fwd(const mrssm_pl_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
     memset(&P, 0, sizeof(P));
     const int k = a->ksz, nt = (k + 1) / 2;
@@ -750,12 +916,19 @@ int plan_fwd(const mrssm_pl_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
     const int maxshift = (nt - 1) * P.BX + nt - 1;
     const long long min_a = (long long)P.planes * ((128 + maxshift) * 16 + 128);    // one 128-row block of the smallest tile
     // the whole packed weight stays resident when it is small; otherwise it streams through a ring of 64-wide K blocks
-    P.b_res = (P.n_ntiles == 1 && P.nkb <= 80 && (long long)P.nkb * P.BN * 128 <= 152 * 1024 &&
-               (long long)P.nkb * P.BN * 128 + std::max<long long>(min_a, 36 * 1024) <= SMEM_TOTAL);
+    const bool res_fits = P.n_ntiles == 1 && P.nkb <= 80 && (long long)P.nkb * P.BN * 128 + std::max<long long>(min_a, 36 * 1024) <= SMEM_TOTAL;
+    P.b_res = res_fits && (long long)P.nkb * P.BN * 128 <= 152 * 1024;
+    const TunedPlan* tuned = find_tuned(a, op);
+    PlanOvr ovr = g_ovr;
+    if (tuned && !ovr.BI && !ovr.TH && !ovr.NA && ovr.bres < 0) ovr = PlanOvr{tuned->BI, tuned->TH, tuned->NA, tuned->bres, tuned->NB};
+    if (ovr.bres >= 0) {
+        MRSSM_CHECK(!ovr.bres || res_fits, "plane conv: plan override asks for resident weights that do not fit");
+        P.b_res = ovr.bres;
+    }
     if (P.b_res) {
         P.NB = P.nkb;
     } else {
-        P.NB = std::min(8, std::max(2, (64 * 1024) / (P.BN * 128)));
+        P.NB = ovr.NB > 0 ? ovr.NB : std::min(8, std::max(2, (64 * 1024) / (P.BN * 128)));
         while (P.NB > 2 && min_a > SMEM_TOTAL - (long long)P.NB * P.BN * 128) --P.NB;
     }
     const long long bring = (long long)P.NB * P.BN * 128;
@@ -770,7 +943,18 @@ int plan_fwd(const mrssm_pl_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
     int MBt, PS;
     const int BYfull = P.Hv + nt - 1;
     long long one = stage_bytes(1, BYfull, P.Hv, MBt, PS);
-    if (one <= avail) {
+    if (ovr.BI > 0 || ovr.TH > 0 || ovr.NA > 0) {
+        // forced tiling (tuned table / tuning sweep): whole images (TH == Hv, BI images per tile) or row bands of one image
+        const int TH = ovr.TH > 0 ? std::min(ovr.TH, P.Hv) : P.Hv;
+        P.n_bands = (P.Hv + TH - 1) / TH;
+        P.BI = P.n_bands > 1 ? 1 : std::max(1, std::min(ovr.BI, a->n_img));
+        P.TH = TH;
+        P.BY = TH + nt - 1;
+        P.NA = ovr.NA > 0 ? std::min(ovr.NA, 2) : 2;
+        const long long sb = stage_bytes(P.BI, P.BY, P.TH, MBt, PS);
+        MRSSM_CHECK(sb * P.NA <= avail && PS < 262144, "plane conv: forced plan (BI %d TH %d NA %d) needs %lld bytes of %lld", P.BI, P.TH, P.NA,
+                    sb * P.NA, avail);
+    } else if (one <= avail) {
         // images per tile and A stages: maximise (valid rows / MMA rows) x (accumulator-set fill when the weights stream),
         // taking the smallest image count within 2 % of the best; single buffering must win by 50 % to be chosen
         auto best_for = [&](int NA, int& bestBI) -> double {
@@ -841,6 +1025,38 @@ int plan_fwd(const mrssm_pl_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
         const long long tb = 4 * a->out32.sI;
         P.tgt_img_bytes = (!g_dbg[2] && tb > 0 && tb % 16 == 0 && ((uintptr_t)a->mse_target & 15) == 0 && tb <= (1 << 20)) ? tb : 0;
     }
+    // epilogue shape: columns per item.  Fast path: bf16 output, act none / ReLU, ReLU (or no) act'-mask, and items that stay
+    // inside one parity class; otherwise the generic epilogue (fp32 outputs, fused loss, ELU, odd widths).
+    P.bits_out = a->relu_bits_out; P.bits_in = a->relu_bits_in;
+    {
+        const bool mse_k = P.mse_target != nullptr;
+        int nc = 0;
+        for (int c : {64, 32, 16}) {
+            if (P.BN % c == 0 && (op == OP_DOWN || P.Cop % c == 0) && (c == 16 || P.BN / c <= 16)) {
+                nc = c;
+                break;
+            }
+        }
+        // narrow tiles: keep >= 4 items per 128-row block per lane quarter busy only when it costs nothing
+        if (nc == 64 && P.BN < 256) nc = 32;
+        const bool act_ok = P.act == 0 || P.act == MRSSM_ACT_RELU;
+        const bool mask_ok = P.mask_mode == 0 || P.mask_mode == MRSSM_ACT_RELU;
+        P.fast = (!P.out_f32 && !mse_k && nc > 0 && act_ok && mask_ok && !g_dbg[1]) ? 1 : 0;
+        if (P.bits_in) {
+            MRSSM_CHECK(a->mask_mode == MRSSM_ACT_RELU && !a->mask.ptr, "plane conv: relu_bits_in replaces the mask view (mask_mode must be ReLU)");
+            P.mask_mode = MRSSM_ACT_RELU;
+        }
+        MRSSM_CHECK(!(P.bits_in || P.bits_out) || P.fast, "plane conv: ReLU sign bits need the bf16 fast epilogue (bf16 output, ReLU, %d columns)", P.BN);
+        MRSSM_CHECK(!P.bits_out || P.act == MRSSM_ACT_RELU, "plane conv: relu_bits_out needs act = ReLU");
+        if (P.fast) {
+            P.nc = nc; P.ncp = P.BN / nc;
+        } else {
+            P.ncp = mse_k ? 1 : ((P.BN % 64 == 0 && P.BN >= 128) ? 4 : ((P.BN % 32 == 0 && P.BN >= 64) ? 2 : 1));
+            P.nc = P.BN / P.ncp;
+        }
+        P.bits_img_bytes = (P.bits_in && !g_dbg[2]) ? (long long)P.Ho * P.Wo * (P.Cop >> 3) : 0;
+        if (P.bits_in) P.mask_img_bytes = 0;
+    }
     auto vec_ok = [](const mrssm_tv& t) {
         return t.sW % 8 == 0 && t.sH % 8 == 0 && t.sI % 8 == 0 && t.sK % 8 == 0 && t.sP % 8 == 0 && ((uintptr_t)t.ptr & 15) == 0;
     };
@@ -896,16 +1112,21 @@ int launch_fwd(const mrssm_pl_conv_args* a, int op, cudaStream_t st) {
     const int n_tiles = P.n_groups * P.n_bands;
     int grid = std::min(n_tiles, 148);
     smem = std::max<size_t>(smem, 120 * 1024);       // > half an SM: one CTA per SM (each allocates all 512 TMEM columns)
-#define PL_LAUNCH(OPV, F32V)                                                                                                   \
-    do {                                                                                                                        \
-        MRSSM_CUDA(cudaFuncSetAttribute(plane_fwd_kernel<OPV, F32V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-        plane_fwd_kernel<OPV, F32V><<<grid, FWD_THREADS, smem, st>>>(mA[0], mA[1], mA[2], mA[3], mB, P);                        \
+#define PL_LAUNCH(OPV, F32V, NCV)                                                                                                   \
+    do {                                                                                                                             \
+        MRSSM_CUDA(cudaFuncSetAttribute(plane_fwd_kernel<OPV, F32V, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        plane_fwd_kernel<OPV, F32V, NCV><<<grid, FWD_THREADS, smem, st>>>(mA[0], mA[1], mA[2], mA[3], mB, P);                        \
     } while (0)
-    if (op == OP_DOWN) {
-        if (P.out_f32) PL_LAUNCH(OP_DOWN, true); else PL_LAUNCH(OP_DOWN, false);
-    } else {
-        if (P.out_f32) PL_LAUNCH(OP_UP, true); else PL_LAUNCH(OP_UP, false);
-    }
+#define PL_LAUNCH_OP(OPV)                                        \
+    do {                                                         \
+        if (P.out_f32) PL_LAUNCH(OPV, true, 0);                  \
+        else if (!P.fast) PL_LAUNCH(OPV, false, 0);              \
+        else if (P.nc == 64) PL_LAUNCH(OPV, false, 64);          \
+        else if (P.nc == 32) PL_LAUNCH(OPV, false, 32);          \
+        else PL_LAUNCH(OPV, false, 16);                          \
+    } while (0)
+    if (op == OP_DOWN) PL_LAUNCH_OP(OP_DOWN); else PL_LAUNCH_OP(OP_UP);
+#undef PL_LAUNCH_OP
 #undef PL_LAUNCH
     MRSSM_LAUNCH_CHECK();
     return 0;
@@ -967,7 +1188,13 @@ struct WgP {
     int cs_valid, cl_valid;
     float* dw;
     long long w_ss, w_sl;
+    // bias gradient from the resident operand tile (warps 4..7 while the MMAs run): db_from 1 = small planes, 2 = large planes
+    float* db;
+    int db_from, db_nch, db_npar;     // 8-channel chunks to sum, plane groups per chunk (large, parity split: 4)
+    int db_valid, db_fold;            // real channels; fold > 0: channel c of the tile is channel c % fold for c < 4 * fold
 };
+
+constexpr int WG_SUM_WARPS = 4;       // warps 4..7
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant__ CUtensorMap mL0, const __grid_constant__ CUtensorMap mL1,
@@ -987,9 +1214,11 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
     for (int i = tid * 16; i < P.zero_bytes; i += NTHREADS * 16) *reinterpret_cast<uint4*>(smem_al + i) = make_uint4(0, 0, 0, 0);
     tc::fence_proxy_async();
     if (tid == 0) {
+        // a stage is released by the MMA commit and, when this CTA also sums the bias gradient, by the summing warps
+        const bool do_sum = P.db_from != 0 && cpass == 0 && (P.db_from == 1 || mhalf == 0);
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(tc::smem_u32(&a_full[s]), 1);
-            tc::mbar_init(tc::smem_u32(&a_empty[s]), 1);
+            tc::mbar_init(tc::smem_u32(&a_empty[s]), do_sum ? 1 + WG_SUM_WARPS : 1);
         }
         tc::mbar_init(tc::smem_u32(&acc_full), 1);
         tc::fence_barrier_init();
@@ -1089,6 +1318,80 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
         __syncwarp();
     } else if (warp >= 4) {
         const int q = warp - 4;
+        if (P.db_from != 0 && cpass == 0 && (P.db_from == 1 || mhalf == 0)) {      // `large` is shared by the Cs halves: one of them sums it
+            // ---- bias gradient: per-channel sums over the pixels of the gradient operand, read from the tile the TMA already
+            // put in shared memory for the MMAs (planes [chunk][pixel][8 ch]: a warp sweeps one plane with 16-byte loads).
+            // Chunk c of this CTA is summed by warp (c % 4) [nch >= 4] or by warps {c, c + nch, ..} [nch < 4].
+            const int nch = P.db_nch;
+            const int cpw = nch >= WG_SUM_WARPS ? nch / WG_SUM_WARPS : 1;        // chunks per warp (1, 2 or 4)
+            const int wpc = nch >= WG_SUM_WARPS ? 1 : WG_SUM_WARPS / nch;        // warps per chunk
+            const int sub = nch >= WG_SUM_WARPS ? 0 : q / nch;                   // which share of the pixels (wpc > 1)
+            const int c_first = nch >= WG_SUM_WARPS ? q : q % nch;
+            const bool active = nch >= WG_SUM_WARPS || q < nch * wpc;
+            float acc[4][8];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
+            const uint32_t ps = P.db_from == 1 ? (uint32_t)P.PS_s : (uint32_t)P.PS_l;
+            const uint32_t off0 = P.db_from == 1 ? 0u : (uint32_t)P.offL;
+            const int grp_stride = P.cpl;                                        // large: plane index = group * cpl + chunk
+            uint32_t acnt = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int sa = acnt % P.NA;
+                tc::mbar_wait(tc::smem_u32(&a_full[sa]), (acnt / P.NA) & 1);
+                const int band = tile % P.n_bands;
+                // entries to count: the whole plane, or — row bands share their halo rows — the first TH rows (all of them in the last band)
+                int cnt;
+                if (P.db_from == 1) cnt = P.BI * P.SBY * P.BX;
+                else cnt = (P.n_bands > 1 && band < P.n_bands - 1) ? P.TH * P.BX : P.BI * P.BY * P.BX;
+                if (active) {
+                    const uint8_t* stage = smem_al + (size_t)sa * P.stage_bytes + off0;
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        if (a < cpw) {
+                            const int c = c_first + a * WG_SUM_WARPS;
+                            for (int g = 0; g < P.db_npar; ++g) {
+                                const uint8_t* pl = stage + (size_t)(g * grp_stride + c) * ps;
+                                for (int e = sub * 32 + lane; e < cnt; e += 32 * wpc) {
+                                    const uint4 pk = *reinterpret_cast<const uint4*>(pl + (size_t)e * 16);
+                                    const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+                                    for (int h = 0; h < 4; ++h) {
+                                        const float2 f = __bfloat1622float2(ph[h]);
+                                        acc[a][2 * h] += f.x;
+                                        acc[a][2 * h + 1] += f.y;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(tc::smem_u32(&a_empty[sa]));
+                ++acnt;
+            }
+            if (active) {
+                const float sc = P.scale_ptr ? __ldg(P.scale_ptr) * P.scale_mul : 1.f;
+                const int ch0 = P.db_from == 1 ? mhalf * 16 : 0;                  // small: this CTA holds chunks [16 mhalf, 16 mhalf + nS)
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    if (a < cpw) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float sum = warp_sum(acc[a][e]);
+                            int c = (ch0 + c_first + a * WG_SUM_WARPS) * 8 + e;
+                            bool ok = true;
+                            if (P.db_fold > 0) {
+                                ok = c < 4 * P.db_fold;
+                                c = c % P.db_fold;
+                            }
+                            if (lane == 0 && ok && c < P.db_valid) atomicAdd(P.db + c, sum * sc);
+                        }
+                    }
+                }
+            }
+        }
         tc::mbar_wait(tc::smem_u32(&acc_full), 0);
         tc::tc_fence_after();
         const int cs = mhalf * 128 + q * 32 + lane;
@@ -1199,6 +1502,18 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
     P.cs_valid = a->cs_valid; P.cl_valid = a->cl_valid;
     P.dw = a->dweight; P.w_ss = a->w_ss; P.w_sl = a->w_sl;
     P.scale_ptr = a->scale_ptr; P.scale_mul = a->scale_mul;
+    P.db = a->dbias; P.db_from = a->dbias ? a->dbias_from : 0;
+    if (P.db_from) {
+        MRSSM_CHECK(P.db_from == 1 || P.db_from == 2, "plane wgrad: dbias_from %d (1 = small, 2 = large)", P.db_from);
+        if (P.db_from == 1) {
+            P.db_nch = P.nS; P.db_npar = 1; P.db_valid = a->cs_valid; P.db_fold = 0;
+        } else {
+            P.db_nch = P.cpl; P.db_npar = (P.s2d_cq || P.rep) ? 1 : 4; P.db_valid = a->cl_valid; P.db_fold = P.s2d_cq;
+        }
+        MRSSM_CHECK(P.db_nch == 1 || P.db_nch == 2 || P.db_nch == 4 || P.db_nch == 8 || P.db_nch == 16,
+                    "plane wgrad: bias-gradient sums need 1, 2, 4, 8 or 16 channel chunks (got %d)", P.db_nch);
+        MRSSM_CHECK(P.n_bands == 1 || P.BI == 1, "plane wgrad: banded tiles hold one image");
+    }
     return 0;
 }
 
@@ -1520,6 +1835,11 @@ extern "C" int mrssm_pl_colsum(const mrssm_tv* x, int32_t n_img, int32_t H, int3
 extern "C" int mrssm_pl_set_debug(int32_t key, int32_t value) {
     MRSSM_CHECK(key >= 0 && key < 4, "pl_set_debug: bad key");
     g_dbg[key] = value;
+    return 0;
+}
+
+extern "C" int mrssm_pl_set_plan_override(int32_t BI, int32_t TH, int32_t NA, int32_t bres, int32_t NB) {
+    g_ovr = PlanOvr{BI, TH, NA, bres, NB};
     return 0;
 }
 

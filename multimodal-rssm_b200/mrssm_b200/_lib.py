@@ -51,7 +51,8 @@ class PlConvArgs(C.Structure):
                                          "n_out_pad", "n_out_valid", "cs_valid", "cl_valid", "s2d_cq")] + [
         ("large", TV), ("small", TV), ("mask", TV), ("out32", T4), ("wpacked", _vp), ("bias", _vp), ("dweight", _vp),
         ("w_ss", C.c_int64), ("w_sl", C.c_int64), ("scale_ptr", _vp), ("scale_mul", C.c_float),
-        ("mse_target", _vp), ("mse_sum", _vp), ("mse_scale", C.c_float)]
+        ("mse_target", _vp), ("mse_sum", _vp), ("mse_scale", C.c_float),
+        ("dbias", _vp), ("dbias_from", C.c_int32), ("relu_bits_out", _vp), ("relu_bits_in", _vp)]
 
 
 class RolloutArgs(C.Structure):
@@ -134,6 +135,7 @@ SYMBOLS = {
     "mrssm_pl_pack_weight": [_vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
     "mrssm_pl_import_s2d": [C.POINTER(T4), _i32, _i32, _i32, _i32, _f, C.POINTER(TV), _vp],
     "mrssm_pl_describe": [C.POINTER(PlConvArgs), _i32, C.c_char_p, _i32],
+    "mrssm_pl_set_plan_override": [_i32, _i32, _i32, _i32, _i32],
     "mrssm_pl_set_debug": [_i32, _i32],
     "mrssm_pl_set_profile_buffer": [_vp],
     "mrssm_rollout_fwd": [C.POINTER(RolloutArgs), _vp],

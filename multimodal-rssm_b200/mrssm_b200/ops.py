@@ -913,23 +913,40 @@ def _pl_args(geom, large=None, small=None, mask=None, act=0, mask_mode=0, out32=
                         sp, sm, mt, ms, mf)
 
 
+def new_relu_bits(n, H, W, Cp, device):
+    """ReLU sign bits of an [n,H,W,Cp] activation: one byte per (pixel, 8-channel chunk), [n][H][W][Cp/8] (+ 16 bytes of slack
+    for the 16-byte L2 prefetch granules).  Written by a forward epilogue, read by the matching dgrad epilogue."""
+    return torch.empty(n * H * W * (Cp // 8) + 16, device=device, dtype=torch.uint8)
+
+
+def _set_bits(a, bits_out, bits_in):
+    if bits_out is not None:
+        a.relu_bits_out = L.ptr_any(bits_out)
+    if bits_in is not None:
+        a.relu_bits_in, a.mask_mode = L.ptr_any(bits_in), RELU
+
+
 def pl_conv_down(geom, large, out, wpacked, bias, n_out_valid, n_out_pad, act=0, mask=None, mask_mode=0, valid=None, s2d_cq=0,
-                 scale=None):
+                 scale=None, bits_out=None, bits_in=None):
     """large: L.TV view of the gathered tensor (parity-planar preferred; the space-to-depth view when s2d_cq);
-    out: L.TV (bf16) or L.T4 (fp32, any strides)."""
+    out: L.TV (bf16) or L.T4 (fp32, any strides).  bits_out: buffer of new_relu_bits for the sign bits of the (ReLU) output;
+    bits_in: the sign bits standing in for the ReLU act'-mask (instead of `mask`)."""
     f32 = isinstance(out, L.T4)
     a = _pl_args(geom, large=large, small=None if f32 else out, mask=mask, act=act, mask_mode=mask_mode,
                  out32=out if f32 else None, n_out_pad=n_out_pad, n_out_valid=n_out_valid, wpacked=L.ptr(wpacked), bias=L.ptr(bias),
                  s2d_cq=s2d_cq, scale=scale)
+    _set_bits(a, bits_out, bits_in)
     tag, work = _tc_work("mrssm_pl_conv_down", geom, valid or (geom[6], geom[3]))
     L.call("mrssm_pl_conv_down", C.byref(a), tag=tag, work=work)
 
 
-def pl_conv_up(geom, out, small, wpacked, bias, n_out_valid, n_out_pad, act=0, mask=None, mask_mode=0, valid=None):
+def pl_conv_up(geom, out, small, wpacked, bias, n_out_valid, n_out_pad, act=0, mask=None, mask_mode=0, valid=None, bits_out=None,
+               bits_in=None):
     """small: L.TV view of the gathered tensor (planar preferred, channels padded to 16); out: L.TV or L.T4 (fp32)."""
     f32 = isinstance(out, L.T4)
     a = _pl_args(geom, large=None if f32 else out, small=small, mask=mask, act=act, mask_mode=mask_mode,
                  out32=out if f32 else None, n_out_pad=n_out_pad, n_out_valid=n_out_valid, wpacked=L.ptr(wpacked), bias=L.ptr(bias))
+    _set_bits(a, bits_out, bits_in)
     tag, work = _tc_work("mrssm_pl_conv_up", geom, valid or (geom[6], geom[3]))
     L.call("mrssm_pl_conv_up", C.byref(a), tag=tag, work=work)
 
@@ -945,9 +962,13 @@ def pl_conv_up_mse(geom, resid, small, wpacked, bias, n_out_valid, n_out_pad, ta
     L.call("mrssm_pl_conv_up", C.byref(a), tag=tag, work=work)
 
 
-def pl_conv_wgrad(geom, large, small, dweight_ptr, w_ss, w_sl, cs_valid, cl_valid, s2d_cq=0, scale=None):
+def pl_conv_wgrad(geom, large, small, dweight_ptr, w_ss, w_sl, cs_valid, cl_valid, s2d_cq=0, scale=None, dbias=None, dbias_from=0):
+    """dbias (fp32 [channels], accumulated) + dbias_from (1: per-channel sums of `small`, the gradient of a Conv2d; 2: of `large`,
+    the gradient of a ConvTranspose2d): the layer's bias gradient from the tile the kernel already holds in shared memory."""
     a = _pl_args(geom, large=large, small=small, cs_valid=cs_valid, cl_valid=cl_valid, dweight=dweight_ptr, w_ss=w_ss, w_sl=w_sl,
                  s2d_cq=s2d_cq, scale=scale)
+    if dbias is not None:
+        a.dbias, a.dbias_from = L.ptr(dbias), dbias_from
     tag, work = _tc_work("mrssm_pl_conv_wgrad", geom, (cs_valid, cl_valid))
     L.call("mrssm_pl_conv_wgrad", C.byref(a), tag=tag, work=work)
 
@@ -1123,6 +1144,7 @@ class ConvEncoderTCFn(Function):
             acts = [pl_import(L.nchw(x, H, W, Cc), N, H, W, Cc, pad8(Cc), L.PARITY, dev)]
             Clp = pad8(Cc)
         geoms = []
+        bits = []
         Hl, Wl = H, W
         y = None
         for i in range(n_layers):
@@ -1138,20 +1160,22 @@ class ConvEncoderTCFn(Function):
                 pl_conv_down(geom, acts[-1][1], L.nchw(y, Hs, Ws, Cs), wp, b, Cs, Csp, act=RELU, valid=(Cs, Cl), s2d_cq=cq)
             else:
                 o = new_act(N, Hs, Ws, Csp, L.PARITY, dev)
-                pl_conv_down(geom, acts[-1][1], o[1], wp, b, Cs, Csp, act=RELU, valid=(Cs, Cl), s2d_cq=cq)
+                bits.append(new_relu_bits(N, Hs, Ws, Csp, dev))       # 1 bit per element: the dgrad's act'-mask
+                pl_conv_down(geom, acts[-1][1], o[1], wp, b, Cs, Csp, act=RELU, valid=(Cs, Cl), s2d_cq=cq, bits_out=bits[-1])
                 acts.append(o)
             geoms.append((geom, Cs, Cl, cq))
             Hl, Wl, Clp = Hs, Ws, Csp
         ctx.geoms, ctx.params = geoms, params
-        ctx.save_for_backward(y, *[t for t, _ in acts])
+        ctx.save_for_backward(y, *[t for t, _ in acts], *bits)
         return y
 
     @staticmethod
     def backward(ctx, g):
         geoms, params = ctx.geoms, ctx.params
-        y, *acts = ctx.saved_tensors
-        dev = y.device
         n_layers = len(geoms)
+        y, *rest = ctx.saved_tensors
+        acts, bits = rest[:n_layers], rest[n_layers:]        # bits[i - 1]: sign bits of acts[i] (the output of layer i - 1)
+        dev = y.device
         (N, _, _, _, Hs, Ws, Csp, _), Cs, _, _ = geoms[-1]
         gm = act_bwd(g, y, RELU)
         gb = pl_import(L.nchw(gm, Hs, Ws, Cs), N, Hs, Ws, Cs, Csp, L.PLANAR, dev)
@@ -1167,12 +1191,12 @@ class ConvEncoderTCFn(Function):
                 gn = pl_import(L.nchw(gm, Hs, Ws, Cs), N, Hs, Ws, Cs, Csp, L.NHWC, dev)[0]
                 tc_conv_wgrad(geom, L.nhwc(xn, Hl, Wl, Clp), L.nhwc(gn, Hs, Ws, Csp), L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl)
                 del xn, gn
-            else:
-                pl_conv_wgrad(geom, xv, gb[1], L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl, s2d_cq=cq)
-            pl_colsum(gb[1], N, Hs, Ws, Csp, Cs, grad_buf(b))
+                pl_colsum(gb[1], N, Hs, Ws, Csp, Cs, grad_buf(b))
+            else:       # weight and bias gradient in one kernel (the bias sums read the gradient tile from shared memory)
+                pl_conv_wgrad(geom, xv, gb[1], L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl, s2d_cq=cq, dbias=grad_buf(b), dbias_from=1)
             if i > 0:
                 gx = new_act(N, Hl, Wl, Clp, L.PLANAR, dev)
-                pl_conv_up(geom, gx[1], gb[1], packed_pl(Wt, UP, Csp, Clp), None, Cl, Clp, mask=xv, mask_mode=RELU, valid=(Cs, Cl))
+                pl_conv_up(geom, gx[1], gb[1], packed_pl(Wt, UP, Csp, Clp), None, Cl, Clp, bits_in=bits[i - 1], valid=(Cs, Cl))
                 gb = gx
         return (None, *([None] * len(params)))
 
@@ -1207,6 +1231,7 @@ class ConvDecoderTCFn(Function):
         convs = params[2:]
         n_layers = len(convs) // 2
         acts = [(y0, L.NHWC)]
+        bits = {}                                    # index into acts -> ReLU sign bits of that activation (plane layers)
         geoms = []
         Hs, Ws, Csp = 1, 1, pad16(Em)
         out = None
@@ -1240,14 +1265,17 @@ class ConvDecoderTCFn(Function):
                            valid=(Cs, Cl))
             else:
                 o = new_act(R, Hl, Wl, Clp, L.PLANAR, dev)
-                pl_conv_up(geom, o[1], L.tv(xt, xl, Hs, Ws, Csp), packed_pl(Wt, UP, Csp, Clp), b, Cl, Clp, act=RELU, valid=(Cs, Cl))
+                bits[len(acts)] = new_relu_bits(R, Hl, Wl, Clp, dev)
+                pl_conv_up(geom, o[1], L.tv(xt, xl, Hs, Ws, Csp), packed_pl(Wt, UP, Csp, Clp), b, Cl, Clp, act=RELU, valid=(Cs, Cl),
+                           bits_out=bits[len(acts)])
                 acts.append((o[0], L.PLANAR))
             geoms.append((geom, Cs, Cl, cq))
             Hs, Ws, Csp = Hl, Wl, Clp
         ctx.geoms, ctx.params, ctx.dims = geoms, params, (R, D, S, Em, Kp)
         ctx.layouts = [l for _, l in acts]
         ctx.fused = target is not None
-        ctx.save_for_backward(hsb, *[t for t, _ in acts])
+        ctx.bit_slots = sorted(bits)
+        ctx.save_for_backward(hsb, *[t for t, _ in acts], *[bits[i] for i in ctx.bit_slots])
         return out.reshape(()) if target is not None else out
 
     @staticmethod
@@ -1259,6 +1287,9 @@ class ConvDecoderTCFn(Function):
         geoms, params, layouts = ctx.geoms, ctx.params, ctx.layouts
         R, D, S, Em, Kp = ctx.dims
         hsb, *acts = ctx.saved_tensors
+        nb = len(ctx.bit_slots)
+        bits = dict(zip(ctx.bit_slots, acts[len(acts) - nb:])) if nb else {}
+        acts = acts[:len(acts) - nb]
         dev = hsb.device
         convs = params[2:]
         n_layers = len(geoms)
@@ -1298,14 +1329,12 @@ class ConvDecoderTCFn(Function):
                 nl = L.NHWC if (i > 0 and geoms[i - 1][0][4] == 1) or i == 0 else L.PARITY
                 gxt, gxv = new_act(R, Hs, Ws, Csp, nl, dev)
                 sc = scale if i == n_layers - 1 else None          # only the first consumer of the raw residual applies the scale
-                pl_conv_wgrad(gg, gv, xv, L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl, s2d_cq=cq if s2d else 0, scale=sc)
+                pl_conv_wgrad(gg, gv, xv, L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl, s2d_cq=cq if s2d else 0, scale=sc,
+                              dbias=grad_buf(b), dbias_from=2)
+                xbits = bits.get(i)                    # sign bits of this layer's input (written by the plane layer below)
                 pl_conv_down(gg, gv, gxv, packed_pl(Wt, DOWN_S2D if s2d else DOWN, Csp, gg[3], cq if s2d else 0), None, Cs, Csp,
-                             mask=xv if i > 0 else None, mask_mode=RELU if i > 0 else 0, valid=(Cs, Cl), s2d_cq=cq if s2d else 0,
-                             scale=sc)
-                if s2d:
-                    pl_colsum(gv, R, H2, W2, 16, Cl, grad_buf(b), fold=cq, scale=sc)
-                else:
-                    pl_colsum(gv, R, Hl, Wl, Clg, Cl, grad_buf(b), scale=sc)
+                             mask=xv if (i > 0 and xbits is None) else None, mask_mode=RELU if i > 0 else 0, valid=(Cs, Cl),
+                             s2d_cq=cq if s2d else 0, scale=sc, bits_in=xbits)
                 gx = gxt
             gb, gl = gx, nl
         fcw, fcb = params[0], params[1]

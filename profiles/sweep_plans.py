@@ -1,0 +1,112 @@
+"""Tiling sweep of the plane forward-type kernels (tuning aid): for every production layer of the 64x64 stacks at n frames,
+time the planner's own choice and a grid of forced tilings (mrssm_pl_set_plan_override), print the best few.  The winners go
+into kTuned (csrc/conv_plane.cu).
+
+    python profiles/sweep_plans.py [n_frames] [layer ...]
+"""
+import itertools
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "multimodal-rssm_b200"))
+import torch
+from mrssm_b200 import _lib as L, ops
+
+DEV = "cuda:0"
+# name: (op, Hl, Cl, Hs, Cs, k, mode)   mode: fwd (bias + ReLU + sign bits out) | dgrad (sign bits in) | s2d variants
+LAYERS = {
+    "E1_fwd": ("down_s2d", 64, 3, 31, 32, 4, "fwd"), "E2_fwd": ("down", 31, 32, 14, 64, 4, "fwd"), "E3_fwd": ("down", 14, 64, 6, 128, 4, "fwd"),
+    "E4_dgrad": ("up", 6, 128, 2, 256, 4, "dgrad"), "E3_dgrad": ("up", 14, 64, 6, 128, 4, "dgrad"), "E2_dgrad": ("up", 31, 32, 14, 64, 4, "dgrad"),
+    "D2_fwd": ("up", 13, 64, 5, 128, 5, "fwd"), "D3_fwd": ("up", 30, 32, 13, 64, 6, "fwd"),
+    "D4_dgrad": ("down_s2d", 64, 3, 30, 32, 6, "dgrad"), "D3_dgrad": ("down", 30, 32, 13, 64, 6, "dgrad"), "D2_dgrad": ("down", 13, 64, 5, 128, 5, "dgrad_bf16mask"),
+}
+
+
+def build(name, n):
+    op, Hl, Cl, Hs, Cs, k, mode = LAYERS[name]
+    g = torch.Generator(device=DEV).manual_seed(0)
+    s2d = op == "down_s2d"
+    Clp, Csp = (16 if s2d else ops.pad8(Cl)), ops.pad16(Cs)
+    w = torch.randn(Cs, Cl, k, k, device=DEV, generator=g) / (Cl * k * k) ** 0.5
+    gp = (n, Hl, Hl, Clp, Hs, Hs, Csp, k)
+    if op.startswith("down"):
+        if s2d:
+            src = ops.new_act(n, (Hl + 1) // 2, (Hl + 1) // 2, 16, L.PLANAR, DEV)
+        else:
+            src = ops.new_act(n, Hl, Hl, Clp, L.PARITY, DEV)
+        src[0].normal_()
+        wp = ops.pl_pack_weight(w, ops.DOWN_S2D if s2d else ops.DOWN, Csp, Clp, Cl if s2d else 0)
+        bias = torch.zeros(Cs, device=DEV)
+        bits = ops.new_relu_bits(n, Hs, Hs, Csp, DEV)
+        bits.fill_(0x5A)
+        if mode == "fwd":
+            out = ops.new_act(n, Hs, Hs, Csp, L.PARITY, DEV)
+            return lambda: ops.pl_conv_down(gp, src[1], out[1], wp, bias, Cs, Csp, act=ops.RELU, s2d_cq=Cl if s2d else 0, bits_out=bits)
+        out = ops.new_act(n, Hs, Hs, Csp, L.PARITY if Hs > 5 else L.NHWC, DEV)
+        if mode == "dgrad_bf16mask":
+            mk = ops.new_act(n, Hs, Hs, Csp, L.NHWC, DEV)
+            mk[0].fill_(1.0)
+            return lambda: ops.pl_conv_down(gp, src[1], out[1], wp, None, Cs, Csp, mask=mk[1], mask_mode=ops.RELU)
+        return lambda: ops.pl_conv_down(gp, src[1], out[1], wp, None, Cs, Csp, s2d_cq=Cl if s2d else 0, bits_in=bits)
+    src = ops.new_act(n, Hs, Hs, Csp, L.PLANAR if Hs > 2 else L.PLANAR, DEV)
+    src[0].normal_()
+    wp = ops.pl_pack_weight(w, ops.UP, Csp, Clp)
+    bias = torch.zeros(Cl, device=DEV)
+    bits = ops.new_relu_bits(n, Hl, Hl, Clp, DEV)
+    bits.fill_(0x5A)
+    out = ops.new_act(n, Hl, Hl, Clp, L.PLANAR, DEV)
+    if mode == "fwd":
+        return lambda: ops.pl_conv_up(gp, out[1], src[1], wp, bias, Cl, Clp, act=ops.RELU, bits_out=bits)
+    return lambda: ops.pl_conv_up(gp, out[1], src[1], wp, None, Cl, Clp, bits_in=bits)
+
+
+def timed(f, reps=3):
+    f()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        f()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 50176
+    names = sys.argv[2:] or list(LAYERS)
+    results = {}
+    for name in names:
+        op, Hl, Cl, Hs, Cs, k, mode = LAYERS[name]
+        f = build(name, n)
+        L.call_host("mrssm_pl_set_plan_override", 0, 0, 0, -1, 0)
+        base = timed(f)
+        Hv = Hs if op.startswith("down") else (Hl + 1) // 2
+        ths = sorted({Hv, (Hv + 1) // 2, (Hv + 2) // 3, (Hv + 3) // 4, (Hv + 4) // 5, (Hv + 5) // 6, (Hv + 7) // 8} - {0})
+        rows = []
+        for bres, NA in itertools.product((0, 1), (1, 2)):
+            cands = [(1, th) for th in ths if th < Hv] + [(bi, Hv) for bi in (1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32)]
+            for BI, TH in cands:
+                for NB in ((0,) if bres else (0, 2, 3, 4, 6)):
+                    L.call_host("mrssm_pl_set_plan_override", BI, TH, NA, bres, NB)
+                    try:
+                        ms = timed(f, reps=2)
+                    except RuntimeError:
+                        continue
+                    rows.append((ms, BI, TH, NA, bres, NB))
+        L.call_host("mrssm_pl_set_plan_override", 0, 0, 0, -1, 0)
+        rows.sort()
+        results[name] = dict(planner_ms=base, best=rows[:6])
+        print(f"{name:10s} planner {base:.3f} ms | best " + "  ".join(f"{ms:.3f}(BI{bi} TH{th} NA{na} res{br} NB{nb})" for ms, bi, th, na, br, nb in rows[:6]), flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "sweep_plans.json"), "w") as fjs:
+        json.dump(results, fjs, indent=1)
+
+
+if __name__ == "__main__":
+    main()

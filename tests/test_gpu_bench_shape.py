@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 from oracle import mrssm_oracle as O
 from tests import parity_util as U
-from tests.test_gpu_tc_ops import _bf16_round, export_view
+from tests.test_gpu_tc_ops import _bf16_round, decode_relu_bits, export_view
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -28,6 +28,17 @@ N_FRAMES = 1024 * 49          # BASELINE config 3: (T - 1) * B frames per launch
 # (Hl, Cl, Hs, Cs, k) of every plane layer of the 64x64 encoder / decoder
 LAYERS = {"E1": (64, 3, 31, 32, 4), "E2": (31, 32, 14, 64, 4), "E3": (14, 64, 6, 128, 4), "E4": (6, 128, 2, 256, 4),
           "D2": (13, 64, 5, 128, 5), "D3": (30, 32, 13, 64, 6), "D4": (64, 3, 30, 32, 6)}
+
+
+def pack_relu_bits(flags):
+    """bool [n,H,W,Cp] -> sign bytes in the kernels' layout (inverse of decode_relu_bits), + 16 bytes of slack."""
+    n, H, W, Cp = flags.shape
+    f = flags.view(n, H, W, Cp // 8, 8).to(torch.int32)
+    b = torch.zeros(n, H, W, Cp // 8, dtype=torch.int32, device=flags.device)
+    for j in range(4):
+        b |= f[..., 2 * j] << (3 - j)
+        b |= f[..., 2 * j + 1] << (7 - j)
+    return torch.cat([b.to(torch.uint8).reshape(-1), torch.zeros(16, dtype=torch.uint8, device=flags.device)])
 
 
 def _slices(n):
@@ -85,10 +96,13 @@ def test_plane_layers_at_bench_frame_count(name):
     bias_s, bias_l = torch.randn(Cs, device=DEV), torch.randn(Cl, device=DEV)
     # down: Conv2d forward (+bias, ReLU) == ConvTranspose2d dgrad
     out = ops.new_act(n, Hs, Hs, Csp, "parity", DEV)
-    ops.pl_conv_down(gp, lb[1], out[1], ops.pl_pack_weight(w, ops.DOWN, Csp, Clp), bias_s, Cs, Csp, act=ops.RELU)
+    bits_s = ops.new_relu_bits(n, Hs, Hs, Csp, DEV)
+    ops.pl_conv_down(gp, lb[1], out[1], ops.pl_pack_weight(w, ops.DOWN, Csp, Clp), bias_s, Cs, Csp, act=ops.RELU, bits_out=bits_s)
     o = export_view(out[0], "parity", n, Hs, Hs, Csp)[..., :Cs]
     for sl in _slices(n):
         torch.testing.assert_close(o[sl], _ref_down(large[sl], w, bias_s), rtol=1e-2, atol=1e-2)
+        m = sl.stop - sl.start
+        assert torch.equal(decode_relu_bits(bits_s[sl.start * Hs * Hs * (Csp // 8):], m, Hs, Hs, Csp)[..., :Cs], o[sl] > 0)
         m = sl.stop - sl.start
         ref = torch.empty(m, Hs, Hs, Cs, device=DEV)
         _simt(ops, L, "mrssm_conv_down", (m, Hl, Hl, Cl, Hs, Hs, Cs, k), L.nhwc(large[sl], Hl, Hl, Cl), L.nhwc(ref, Hs, Hs, Cs), w, bias_s, ops.RELU)
@@ -96,7 +110,9 @@ def test_plane_layers_at_bench_frame_count(name):
     del out, o
     # up with the ReLU mask of `large`: Conv2d dgrad (floor geometries included) == ConvTranspose2d forward when exact
     out = ops.new_act(n, Hl, Hl, Clp, "planar", DEV)
-    ops.pl_conv_up(gp, out[1], sb[1], ops.pl_pack_weight(w, ops.UP, Csp, Clp), None, Cl, Clp, mask=lb[1], mask_mode=ops.RELU)
+    # production form of the act'-mask: 1 bit per element (here packed on the host from `large` > 0)
+    bits_l = pack_relu_bits(torch.nn.functional.pad(large, (0, Clp - Cl)) > 0)
+    ops.pl_conv_up(gp, out[1], sb[1], ops.pl_pack_weight(w, ops.UP, Csp, Clp), None, Cl, Clp, bits_in=bits_l)
     o = export_view(out[0], "planar", n, Hl, Hl, Clp)[..., :Cl]
     for sl in _slices(n):
         torch.testing.assert_close(o[sl], _ref_up(small[sl], w, None, Hl, mask=large[sl]), rtol=1e-2, atol=1e-2)
@@ -115,10 +131,15 @@ def test_plane_layers_at_bench_frame_count(name):
     ref = _ref_wgrad(large, small, w.shape)
     scale = float(ref.abs().max())
     dw = torch.zeros_like(w)
-    ops.pl_conv_wgrad(gp, lb[1], sb[1], L.ptr(dw), Cl * k * k, k * k, Cs, Cl)
+    frm, gx, Cv = (2, large, Cl) if name.startswith("D") else (1, small, Cs)     # decoder: the gradient is `large`
+    db = torch.zeros(Cv, device=DEV)
+    ops.pl_conv_wgrad(gp, lb[1], sb[1], L.ptr(dw), Cl * k * k, k * k, Cs, Cl, dbias=db, dbias_from=frm)
     err = float((dw - ref).abs().max()) / scale
     print(f"[bench-shape] {name} wgrad (plane) max err / max|ref| = {err:.2e}")
     assert err <= 2e-3
+    db_ref = gx.sum(dim=(0, 1, 2), dtype=torch.float64).float()
+    print(f"[bench-shape] {name} fused bias gradient max abs err = {float((db - db_ref).abs().max()):.3e} (|ref| max {float(db_ref.abs().max()):.1f})")
+    torch.testing.assert_close(db, db_ref, rtol=1e-3, atol=1e-2 + 1e-4 * gx[..., 0].numel() ** 0.5)
     if name == "E4":
         xn = ops.pl_copy(lb[1], n, Hl, Hl, Clp, "nhwc", DEV)[0]
         gn = ops.pl_import(L.nhwc(small, Hs, Hs, Cs), n, Hs, Hs, Cs, Csp, "nhwc", DEV)[0]
@@ -153,10 +174,14 @@ def test_three_channel_layers_at_bench_frame_count(name):
     sb = ops.pl_import(L.nhwc(small, Hs, Hs, Cs), n, Hs, Hs, Cs, Csp, "planar", DEV)
     ref = _ref_wgrad(large, small, w.shape)
     dw = torch.zeros_like(w)
-    ops.pl_conv_wgrad(gp, lv, sb[1], L.ptr(dw), Cl * k * k, k * k, Cs, Cl, s2d_cq=Cl)
+    frm, gx, Cv = (2, large, Cl) if name == "D4" else (1, small, Cs)
+    db = torch.zeros(Cv, device=DEV)
+    ops.pl_conv_wgrad(gp, lv, sb[1], L.ptr(dw), Cl * k * k, k * k, Cs, Cl, s2d_cq=Cl, dbias=db, dbias_from=frm)
     err = float((dw - ref).abs().max()) / float(ref.abs().max())
     print(f"[bench-shape] {name} wgrad (space-to-depth) max err / max|ref| = {err:.2e}")
     assert err <= 2e-3
+    db_ref = gx.sum(dim=(0, 1, 2), dtype=torch.float64).float()
+    torch.testing.assert_close(db, db_ref, rtol=1e-3, atol=1e-2 + 1e-4 * gx[..., 0].numel() ** 0.5)
     if name != "D4":
         return
     # last ConvTranspose2d + fused MSE: loss value over all frames, residual on slices
@@ -248,10 +273,13 @@ def test_bench_shape_train_step_matches_oracle():
     rep = dict(state_err=state_err, loss_rel=loss_rel, gnorm_rel=abs(gn - ref_gn) / ref_gn, grad_rel_fro=fro,
                worst_tensor=worst, losses=info, oracle_losses=acc_info, grad_norm=gn, oracle_grad_norm=ref_gn)
     print("[bench-shape] B=1024 T=50 bf16 step vs oracle:", rep)
-    assert state_err < 2e-2, rep
-    assert loss_rel < 5e-3, rep
-    assert rep["gnorm_rel"] < 2e-2, rep
-    assert fro < 5e-2, rep
+    # measured on B200 (round 2): state 3.1e-3, loss 6.1e-5, gradient norm 7.7e-4, whole-gradient Frobenius 1.4e-3, worst
+    # single tensor 4.0e-3 (decoder conv.0.bias); the stated tolerances leave ~3x head-room for the fp32-atomic summation order
+    assert state_err < 1e-2, rep
+    assert loss_rel < 5e-4, rep
+    assert rep["gnorm_rel"] < 3e-3, rep
+    assert fro < 5e-3, rep
+    assert worst[0] < 1.5e-2, rep
     for k in P:
         if k not in acc_g:
             assert float(mine[k].abs().max()) == 0.0, f"{k} should get no gradient"
@@ -259,7 +287,8 @@ def test_bench_shape_train_step_matches_oracle():
 
 def test_bf16_and_fp32_modes_loss_curves_agree():
     """200 optimisation steps from the same weights on the same data and noise: bf16 tensor-core mode against the exact fp32
-    mode.  Stated gap: every step's model loss within 2 % of the fp32 curve, the mean over the last 50 steps within 1 %."""
+    mode.  Stated gap (measured on B200: max step gap 1.2e-4, last-50 mean gap 3.3e-6): every step's model loss within 0.1 % of
+    the fp32 curve, the mean over the last 50 steps within 0.02 %."""
     from algos.MRSSM.MRSSM.algo import build_RSSM
     from mrssm_b200.config import hot_path_config
     B, T, STEPS = 64, 50, 200
@@ -298,5 +327,5 @@ def test_bf16_and_fp32_modes_loss_curves_agree():
     tail = abs(float(b[-50:].mean() - a[-50:].mean())) / float(a[-50:].mean())
     print(f"[bench-shape] loss curves: fp32 {float(a[0]):.2f} -> {float(a[-1]):.2f}, bf16 {float(b[0]):.2f} -> {float(b[-1]):.2f}; "
           f"max step gap {float(rel.max()):.3e}, mean gap {float(rel.mean()):.3e}, last-50 mean gap {tail:.3e}")
-    assert float(a[-1]) < 0.7 * float(a[0]), "the fp32 run should be learning"
-    assert float(rel.max()) < 2e-2 and tail < 1e-2
+    assert float(a[-50:].mean()) < float(a[:10].mean()), "the fp32 run should be learning"
+    assert float(rel.max()) < 1e-3 and tail < 2e-4

@@ -224,6 +224,15 @@ def test_plane_wgrad_and_colsum_match_simt(g, ll, sl):
     ops.pl_conv_wgrad(gp, lb[1], sb[1], L.ptr(out), Cl * k * k, k * k, Cs, Cl)
     scale = float(ref.abs().max())
     assert float((out - ref).abs().max()) <= 2e-3 * scale + 1e-4
+    # the same kernel with the bias gradient fused: per-channel sums of `small` (Conv2d) / of `large` (ConvTranspose2d, exact
+    # geometries: every pixel of `large` is inside the tile) from the operand tile in shared memory
+    for frm, x, Cv in ((1, small, Cs), (2, large, Cl)):
+        if frm == 2 and Hl != 2 * (Hs - 1) + k:
+            continue
+        out2, db = torch.zeros_like(w), torch.full((Cv,), 0.5, device=DEV)
+        ops.pl_conv_wgrad(gp, lb[1], sb[1], L.ptr(out2), Cl * k * k, k * k, Cs, Cl, dbias=db, dbias_from=frm)
+        assert float((out2 - ref).abs().max()) <= 2e-3 * scale + 1e-4
+        torch.testing.assert_close(db, 0.5 + x.sum(dim=(0, 1, 2)), rtol=1e-3, atol=1e-2)
     for (t, v, H, Cp, Cv, x) in ((lb[0], lb[1], Hl, Clp, Cl, large), (sb[0], sb[1], Hs, Csp, Cs, small)):
         acc = torch.zeros(Cv, device=DEV)
         ops.pl_colsum(v, n, H, H, Cp, Cv, acc)
@@ -263,6 +272,14 @@ def test_plane_space_to_depth_source_matches_simt(g):
     outw = torch.zeros_like(w)
     ops.pl_conv_wgrad(gp, lv, sb[1], L.ptr(outw), Cl * k * k, k * k, Cs, Cl, s2d_cq=Cl)
     assert float((outw - refw).abs().max()) <= 2e-3 * float(refw.abs().max()) + 1e-4
+    for frm, x, Cv in ((1, small, Cs), (2, large, Cl)):       # fused bias gradient; from the space-to-depth tile the parities fold
+        if frm == 2 and Hl != 2 * (Hs - 1) + k:
+            continue
+        outw2, db = torch.zeros_like(w), torch.zeros(Cv, device=DEV)
+        sc = torch.full((1,), 0.5, device=DEV)
+        ops.pl_conv_wgrad(gp, lv, sb[1], L.ptr(outw2), Cl * k * k, k * k, Cs, Cl, s2d_cq=Cl, dbias=db, dbias_from=frm, scale=(sc, 3.0))
+        assert float((outw2 - 1.5 * refw).abs().max()) <= 3e-3 * float(refw.abs().max()) + 1e-4
+        torch.testing.assert_close(db, 1.5 * x.sum(dim=(0, 1, 2)), rtol=1e-3, atol=2e-2)
     acc = torch.zeros(Cl, device=DEV)
     ops.pl_colsum(lv, n, H2, H2, 16, Cl, acc, fold=Cl)
     torch.testing.assert_close(acc, large.sum(dim=(0, 1, 2)), rtol=1e-3, atol=1e-2)
@@ -302,3 +319,62 @@ def test_plane_up_fused_mse_matches_separate_ops(g):
         for par in range(4):
             sub = d[:, par >> 1::2, par & 1::2, :]
             torch.testing.assert_close(r[:, :sub.shape[1], :sub.shape[2], par * Cl:(par + 1) * Cl], sub, rtol=1e-2, atol=1e-2)
+
+
+def decode_relu_bits(bits, n, H, W, Cp):
+    """[n*H*W*Cp/8] sign bytes (include/mrssm_b200.h: relu_bits_out) -> bool [n,H,W,Cp]: within a byte, bit (3 - j) is channel
+    2j and bit (7 - j) channel 2j + 1 of the 8-channel chunk."""
+    b = bits[: n * H * W * (Cp // 8)].view(n, H, W, Cp // 8).to(torch.int32)
+    out = torch.zeros(n, H, W, Cp // 8, 8, dtype=torch.bool, device=bits.device)
+    for j in range(4):
+        out[..., 2 * j] = ((b >> (3 - j)) & 1).bool()
+        out[..., 2 * j + 1] = ((b >> (7 - j)) & 1).bool()
+    return out.reshape(n, H, W, Cp)
+
+
+@pytest.mark.parametrize("g", PL_GEOMS)
+def test_plane_relu_sign_bits_round_trip(g):
+    """Forward epilogues emit 1 bit per element (output > 0); the dgrad epilogues that take those bits instead of the bf16
+    activation must give bit-identical gradients.  Both directions: Conv2d (down fwd -> up dgrad) and ConvTranspose2d
+    (up fwd -> down dgrad)."""
+    L, ops, geom, gp, (large, small, w), (lb, sb) = _pl_setup(g, "parity", "planar")
+    n, Hl, _, Cl, Hs, _, Cs, k = geom
+    Clp, Csp = gp[3], gp[6]
+    # Conv2d forward: y = relu(conv(large) + b) with sign bits; then "dgrad of the layer above" masked by y
+    bias = torch.randn(Cs, device=DEV)
+    out = _filled(ops, L, n, Hs, Hs, Csp, "parity")
+    bits = ops.new_relu_bits(n, Hs, Hs, Csp, DEV)
+    bits.fill_(0xAA)
+    ops.pl_conv_down(gp, lb[1], out[1], ops.pl_pack_weight(w, ops.DOWN, Csp, Clp), bias, Cs, Csp, act=ops.RELU, bits_out=bits)
+    y = export_view(out[0], "parity", n, Hs, Hs, Csp)
+    assert torch.equal(decode_relu_bits(bits, n, Hs, Hs, Csp), y > 0)
+    # a masked op writing an [n,Hs,Hs,Csp] tensor: ConvTranspose2d dgrad == `down` with the mask of its own output's ReLU
+    wpd = ops.pl_pack_weight(w, ops.DOWN, Csp, Clp)
+    ref = _filled(ops, L, n, Hs, Hs, Csp, "nhwc")
+    ops.pl_conv_down(gp, lb[1], ref[1], wpd, None, Cs, Csp, mask=out[1], mask_mode=ops.RELU)
+    got = _filled(ops, L, n, Hs, Hs, Csp, "nhwc")
+    ops.pl_conv_down(gp, lb[1], got[1], wpd, None, Cs, Csp, bits_in=bits)
+    assert torch.equal(ref[0], got[0])
+    torch.testing.assert_close(export_view(got[0], "nhwc", n, Hs, Hs, Csp)[..., :Cs],
+                               _ref_masked_down(large, w, y[..., :Cs]), rtol=1e-2, atol=1e-2)
+    if Hl != 2 * (Hs - 1) + k or Clp < 16:       # (3-channel outputs take the generic epilogue: no sign bits)
+        return
+    # ConvTranspose2d forward with sign bits, then Conv2d dgrad (`up`) masked by them
+    bias_l = torch.randn(Cl, device=DEV)
+    wpu = ops.pl_pack_weight(w, ops.UP, Csp, Clp)
+    outl = _filled(ops, L, n, Hl, Hl, Clp, "planar")
+    bits_l = ops.new_relu_bits(n, Hl, Hl, Clp, DEV)
+    ops.pl_conv_up(gp, outl[1], sb[1], wpu, bias_l, Cl, Clp, act=ops.RELU, bits_out=bits_l)
+    yl = export_view(outl[0], "planar", n, Hl, Hl, Clp)
+    assert torch.equal(decode_relu_bits(bits_l, n, Hl, Hl, Clp), yl > 0)
+    ref = _filled(ops, L, n, Hl, Hl, Clp, "planar")
+    ops.pl_conv_up(gp, ref[1], sb[1], wpu, None, Cl, Clp, mask=outl[1], mask_mode=ops.RELU)
+    got = _filled(ops, L, n, Hl, Hl, Clp, "planar")
+    ops.pl_conv_up(gp, got[1], sb[1], wpu, None, Cl, Clp, bits_in=bits_l)
+    assert torch.equal(ref[0], got[0])
+
+
+def _ref_masked_down(large, w, y):
+    import torch.nn.functional as F
+    d = F.conv2d(large.permute(0, 3, 1, 2), w, None, stride=2).permute(0, 2, 3, 1)
+    return d * (y > 0)
