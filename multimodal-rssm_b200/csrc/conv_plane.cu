@@ -75,6 +75,49 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
         ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// ---- converged-warp issue: the producer and the MMA warps run their loops with all 32 lanes (so every operand lives in the
+// uniform datapath and a TMA / MMA is ONE warp-level instruction, not an ELECT retry loop per instruction); the asynchronous
+// instruction itself is guarded by the predicate of the lane chosen once by elect.sync.
+__device__ __forceinline__ uint32_t elect_one_lane() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void mbar_expect_tx_if(uint32_t bar, uint32_t bytes, uint32_t lead) {
+    asm volatile("{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %2, 0;\n\t@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes),
+                 "r"(lead)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_if(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, int c3, uint32_t bar, uint32_t lead) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %7, 0;\n\t"
+        "@e cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n\t}"
+        ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar), "r"(lead)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_if(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t bar, uint32_t lead) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %5, 0;\n\t"
+        "@e cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n\t}"
+        ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(bar), "r"(lead)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d_if(const CUtensorMap* m, int c0, int c1, int c2, int c3, uint32_t lead) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %5, 0;\n\t"
+        "@e cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];\n\t}"
+        ::"l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(lead)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_if(const void* p, uint32_t bytes, uint32_t lead) {
+    asm volatile("{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %2, 0;\n\t@e cp.async.bulk.prefetch.L2.global [%0], %1;\n\t}" ::"l"(p), "r"(bytes), "r"(lead)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit_if(uint32_t bar, uint32_t lead) {
+    asm volatile("{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %1, 0;\n\t@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar),
+                 "r"(lead)
+                 : "memory");
+}
 // un-swizzled (INTERLEAVE) operand descriptor.
 //   K-major : core matrix = 8 rows(M/N) x 16 B(K); SBO = byte stride between 8-row groups, LBO = between the two 8-element K chunks
 //   MN-major: core matrix = 8 rows(K)   x 16 B(MN); LBO = byte stride between 8-row K groups, SBO = between 8-element MN chunks
@@ -252,7 +295,7 @@ struct FwdP {
     const uint8_t* bits_in;     // act'-mask of a dgrad in the same form (instead of the bf16 `mask` view)
     long long bits_img_bytes;   // bytes of one image of bits_in (L2 prefetch per tile)
 };
-#define PROF(slot) do { if (P.prof && lit < 16) P.prof[((long long)blockIdx.x * 16 + lit) * 8 + (slot)] = clock64(); } while (0)
+#define PROF(slot) do { if (P.prof && lit < 16 && (threadIdx.x & 31) == 0) P.prof[((long long)blockIdx.x * 16 + lit) * 8 + (slot)] = clock64(); } while (0)
 
 constexpr int FWD_THREADS = 704;      // warp 0 TMA, 2 TMEM alloc, 4..19 epilogue (four per TMEM lane quarter), 21 MMA issuer
 constexpr int MMA_WARP = 21;          // the highest warp id of its scheduler: the issue arbiter favours high warp ids
@@ -267,6 +310,18 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, u
         "setp.ne.b32 p, %6, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
         ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_lohi_if(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                  uint32_t accumulate, uint32_t lead) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 e, %7, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(lead)
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
@@ -533,53 +588,64 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp == 0) {
-        // ------------------------------ TMA producer ------------------------------
-        if (lane == 0) {
+        // ------------------------------ TMA producer (converged warp, elected lane issues) ------------------------------
+        {
+            const uint32_t lead = elect_one_lane();
             uint32_t acnt = 0, bcnt = 0;
+            auto plane_coords = [&](int tile, int q, const CUtensorMap*& m, int& c0, int& c1, int& c2, int& c3) {
+                const int ig = tile / P.n_bands, band = tile - ig * P.n_bands;
+                const int mi = q / P.ppm, ch = q - mi * P.ppm;
+                m = mi == 0 ? &mA0 : (mi == 1 ? &mA1 : (mi == 2 ? &mA2 : &mA3));
+                if (P.mergedA) {
+                    c0 = 2 * P.x0; c1 = band * P.TH + P.y0; c2 = ch; c3 = ig * P.BI;
+                } else {
+                    c0 = ch * 8; c1 = P.x0; c2 = band * P.TH + P.y0; c3 = ig * P.BI;
+                }
+            };
+            auto prefetch_range = [&](const char* base, long long lo_b, long long hi_b) {     // 16-byte granules, 64 KB pieces
+                const uintptr_t lo = ((uintptr_t)base + (uintptr_t)lo_b) & ~(uintptr_t)15;
+                const uintptr_t hi = ((uintptr_t)base + (uintptr_t)hi_b + 15) & ~(uintptr_t)15;
+                const char* mp = (const char*)lo;
+                long long left = (long long)(hi - lo);
+                while (left > 0) {
+                    const uint32_t sz = (uint32_t)(left < 65536 ? left : 65536);
+                    prefetch_l2_if(mp, sz, lead);
+                    mp += sz;
+                    left -= sz;
+                }
+            };
             auto issue_A = [&](int tile) {
                 const int sa = acnt % P.NA;
                 tc::mbar_wait(tc::smem_u32(&a_empty[sa]), ((acnt / P.NA) & 1) ^ 1);
                 const uint32_t bar = tc::smem_u32(&a_full[sa]);
-                mbar_expect_tx(bar, (uint32_t)P.planes * (uint32_t)P.plane_bytes);
+                mbar_expect_tx_if(bar, (uint32_t)P.planes * (uint32_t)P.plane_bytes, lead);
                 const int ig = tile / P.n_bands, band = tile - ig * P.n_bands;
                 const uint32_t dst = smemA + (uint32_t)sa * (uint32_t)P.a_stage_bytes;
-                if (P.bits_img_bytes > 0 && band == 0) {
-                    // the sign bytes of this tile's images: pull them into L2 a tile ahead of the epilogue's loads (16-byte granules)
-                    const int i0 = ig * P.BI, ni = min(P.BI, P.n_img - i0);
-                    const uintptr_t lo = ((uintptr_t)P.bits_in + (uintptr_t)((long long)i0 * P.bits_img_bytes)) & ~(uintptr_t)15;
-                    const uintptr_t hi = ((uintptr_t)P.bits_in + (uintptr_t)((long long)(i0 + ni) * P.bits_img_bytes) + 15) & ~(uintptr_t)15;
-                    const char* mp = (const char*)lo;
-                    long long left = (long long)(hi - lo);
-                    while (left > 0) {
-                        const uint32_t sz = (uint32_t)(left < 65536 ? left : 65536);
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(mp), "r"(sz) : "memory");
-                        mp += sz;
-                        left -= sz;
-                    }
-                }
-                if ((P.mask_img_bytes > 0 || P.tgt_img_bytes > 0) && band == 0) {
-                    // the epilogue of this tile reads the act'-mask (forward activation) / the loss target straight from HBM, a few
-                    // bytes per lane with the miss latency exposed: pull the tile's images into L2 now, a tile ahead of their use
-                    const int i0 = ig * P.BI, ni = min(P.BI, P.n_img - i0);
-                    const long long ib = P.mask_img_bytes > 0 ? P.mask_img_bytes : P.tgt_img_bytes;
-                    const char* mp = (P.mask_img_bytes > 0 ? (const char*)P.mask.p : (const char*)P.mse_target) + (long long)i0 * ib;
-                    long long left = (long long)ni * ib;
-                    while (left > 0) {
-                        const uint32_t sz = (uint32_t)(left < 65536 ? left : 65536);
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(mp), "r"(sz) : "memory");
-                        mp += sz;
-                        left -= sz;
-                    }
-                }
                 for (int q = 0; q < P.planes; ++q) {
-                    const int mi = q / P.ppm, ch = q - mi * P.ppm;
-                    const CUtensorMap* m = mi == 0 ? &mA0 : (mi == 1 ? &mA1 : (mi == 2 ? &mA2 : &mA3));
-                    if (P.mergedA)
-                        tma_load_4d(dst + (uint32_t)q * (uint32_t)P.PS, m, 2 * P.x0, band * P.TH + P.y0, ch, ig * P.BI, bar);
-                    else
-                        tma_load_4d(dst + (uint32_t)q * (uint32_t)P.PS, m, ch * 8, P.x0, band * P.TH + P.y0, ig * P.BI, bar);
+                    const CUtensorMap* m;
+                    int c0, c1, c2, c3;
+                    plane_coords(tile, q, m, c0, c1, c2, c3);
+                    tma_load_4d_if(dst + (uint32_t)q * (uint32_t)P.PS, m, c0, c1, c2, c3, bar, lead);
+                }
+                if (band == 0) {
+                    // what the epilogue of this tile reads straight from global memory (sign bytes, act'-mask, loss target): pull
+                    // the tile's images into L2 now, a tile ahead of their use
+                    const int i0 = ig * P.BI, ni = min(P.BI, P.n_img - i0);
+                    if (P.bits_img_bytes > 0) prefetch_range((const char*)P.bits_in, (long long)i0 * P.bits_img_bytes, (long long)(i0 + ni) * P.bits_img_bytes);
+                    if (P.mask_img_bytes > 0) prefetch_range((const char*)P.mask.p, (long long)i0 * P.mask_img_bytes, (long long)(i0 + ni) * P.mask_img_bytes);
+                    if (P.tgt_img_bytes > 0) prefetch_range((const char*)P.mse_target, (long long)i0 * P.tgt_img_bytes, (long long)(i0 + ni) * P.tgt_img_bytes);
                 }
                 ++acnt;
+            };
+            // single-buffered activation stage: the load of the next tile can only start when this tile's MMAs are done, so its
+            // planes are pulled into L2 meanwhile (the TMA load then hits L2 instead of HBM)
+            auto prefetch_A = [&](int tile) {
+                for (int q = 0; q < P.planes; ++q) {
+                    const CUtensorMap* m;
+                    int c0, c1, c2, c3;
+                    plane_coords(tile, q, m, c0, c1, c2, c3);
+                    tma_prefetch_4d_if(m, c0, c1, c2, c3, lead);
+                }
             };
             int tile = blockIdx.x;
             int lit = 0;
@@ -587,8 +653,8 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
             if (P.b_res) {
                 for (int kb = 0; kb < P.nkb; ++kb) {
                     const uint32_t bar = tc::smem_u32(&b_full[kb]);
-                    mbar_expect_tx(bar, b_stage);
-                    tma_load_2d(smem0 + (uint32_t)kb * b_stage, &mB, kb * 64, 0, bar);
+                    mbar_expect_tx_if(bar, b_stage, lead);
+                    tma_load_2d_if(smem0 + (uint32_t)kb * b_stage, &mB, kb * 64, 0, bar, lead);
                 }
             }
             if (tile < n_tiles) issue_A(tile);
@@ -596,6 +662,7 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                 const int next = tile + gridDim.x;
                 PROF(1);
                 if (P.NA > 1 && next < n_tiles) issue_A(next);
+                if (P.NA == 1 && next < n_tiles) prefetch_A(next);
                 if (!P.b_res) {
                     for (int it = 0; it < P.n_ntiles * P.n_passes; ++it) {
                         const int nti = it / P.n_passes;
@@ -603,8 +670,8 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                             const int sb = bcnt % P.NB;
                             tc::mbar_wait(tc::smem_u32(&b_empty[sb]), ((bcnt / P.NB) & 1) ^ 1);
                             const uint32_t bar = tc::smem_u32(&b_full[sb]);
-                            mbar_expect_tx(bar, b_stage);
-                            tma_load_2d(smem0 + (uint32_t)sb * b_stage, &mB, kb * 64, nti * P.BN, bar);
+                            mbar_expect_tx_if(bar, b_stage, lead);
+                            tma_load_2d_if(smem0 + (uint32_t)sb * b_stage, &mB, kb * 64, nti * P.BN, bar, lead);
                             ++bcnt;
                         }
                     }
@@ -614,8 +681,9 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         }
         __syncwarp();
     } else if (warp == MMA_WARP) {
-        // ------------------------------ MMA issuer ------------------------------
-        if (lane == 0) {
+        // ------------------------------ MMA issuer (converged warp, elected lane issues) ------------------------------
+        {
+            const uint32_t lead = elect_one_lane();
             const uint32_t idesc = tc::idesc_bf16(128, P.BN, 0, 0);
             const uint32_t a_hi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1, no swizzle
             const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, 128B swizzle
@@ -652,16 +720,16 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                             uint32_t b_lo = b_base;
                             for (int kb = 0; kb < nfull; ++kb, b_lo += b_step) {
                                 const uint4 ko = make_uint4(P.ks_off16[kb * 4], P.ks_off16[kb * 4 + 1], P.ks_off16[kb * 4 + 2], P.ks_off16[kb * 4 + 3]);
-                                umma_bf16_lohi(d, a_row + ko.x, a_hi, b_lo, b_hi, idesc, kb != 0);
-                                umma_bf16_lohi(d, a_row + ko.y, a_hi, b_lo + 2, b_hi, idesc, 1);
-                                umma_bf16_lohi(d, a_row + ko.z, a_hi, b_lo + 4, b_hi, idesc, 1);
-                                umma_bf16_lohi(d, a_row + ko.w, a_hi, b_lo + 6, b_hi, idesc, 1);
+                                umma_bf16_lohi_if(d, a_row + ko.x, a_hi, b_lo, b_hi, idesc, kb != 0, lead);
+                                umma_bf16_lohi_if(d, a_row + ko.y, a_hi, b_lo + 2, b_hi, idesc, 1, lead);
+                                umma_bf16_lohi_if(d, a_row + ko.z, a_hi, b_lo + 4, b_hi, idesc, 1, lead);
+                                umma_bf16_lohi_if(d, a_row + ko.w, a_hi, b_lo + 6, b_hi, idesc, 1, lead);
                             }
                             if (ntail) {
                                 const uint4 ko = make_uint4(P.ks_off16[nfull * 4], P.ks_off16[nfull * 4 + 1], P.ks_off16[nfull * 4 + 2], P.ks_off16[nfull * 4 + 3]);
-                                umma_bf16_lohi(d, a_row + ko.x, a_hi, b_lo, b_hi, idesc, nfull != 0);
-                                if (ntail > 1) umma_bf16_lohi(d, a_row + ko.y, a_hi, b_lo + 2, b_hi, idesc, 1);
-                                if (ntail > 2) umma_bf16_lohi(d, a_row + ko.z, a_hi, b_lo + 4, b_hi, idesc, 1);
+                                umma_bf16_lohi_if(d, a_row + ko.x, a_hi, b_lo, b_hi, idesc, nfull != 0, lead);
+                                if (ntail > 1) umma_bf16_lohi_if(d, a_row + ko.y, a_hi, b_lo + 2, b_hi, idesc, 1, lead);
+                                if (ntail > 2) umma_bf16_lohi_if(d, a_row + ko.z, a_hi, b_lo + 4, b_hi, idesc, 1, lead);
                             }
                         }
                     } else {
@@ -675,27 +743,27 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                             uint32_t a_row = a_pass, d = tacc;
                             if (nk == 4) {
                                 for (int mb = 0; mb < nmb; ++mb, a_row += 128u, d += BN) {
-                                    umma_bf16_lohi(d, a_row + ko.x, a_hi, b_lo, b_hi, idesc, kb != 0);
-                                    umma_bf16_lohi(d, a_row + ko.y, a_hi, b_lo + 2, b_hi, idesc, 1);
-                                    umma_bf16_lohi(d, a_row + ko.z, a_hi, b_lo + 4, b_hi, idesc, 1);
-                                    umma_bf16_lohi(d, a_row + ko.w, a_hi, b_lo + 6, b_hi, idesc, 1);
+                                    umma_bf16_lohi_if(d, a_row + ko.x, a_hi, b_lo, b_hi, idesc, kb != 0, lead);
+                                    umma_bf16_lohi_if(d, a_row + ko.y, a_hi, b_lo + 2, b_hi, idesc, 1, lead);
+                                    umma_bf16_lohi_if(d, a_row + ko.z, a_hi, b_lo + 4, b_hi, idesc, 1, lead);
+                                    umma_bf16_lohi_if(d, a_row + ko.w, a_hi, b_lo + 6, b_hi, idesc, 1, lead);
                                 }
                             } else {
                                 for (int mb = 0; mb < nmb; ++mb, a_row += 128u, d += BN) {
-                                    umma_bf16_lohi(d, a_row + ko.x, a_hi, b_lo, b_hi, idesc, kb != 0);
-                                    if (nk > 1) umma_bf16_lohi(d, a_row + ko.y, a_hi, b_lo + 2, b_hi, idesc, 1);
-                                    if (nk > 2) umma_bf16_lohi(d, a_row + ko.z, a_hi, b_lo + 4, b_hi, idesc, 1);
+                                    umma_bf16_lohi_if(d, a_row + ko.x, a_hi, b_lo, b_hi, idesc, kb != 0, lead);
+                                    if (nk > 1) umma_bf16_lohi_if(d, a_row + ko.y, a_hi, b_lo + 2, b_hi, idesc, 1, lead);
+                                    if (nk > 2) umma_bf16_lohi_if(d, a_row + ko.z, a_hi, b_lo + 4, b_hi, idesc, 1, lead);
                                 }
                             }
-                            tc::umma_commit(tc::smem_u32(&b_empty[sb]));
+                            umma_commit_if(tc::smem_u32(&b_empty[sb]), lead);
                             ++bcnt;
                         }
                     }
                     if (it == 0) PROF(7);
-                    tc::umma_commit(tc::smem_u32(&acc_full[set]));
+                    umma_commit_if(tc::smem_u32(&acc_full[set]), lead);
                     ++ccnt;
                 }
-                tc::umma_commit(tc::smem_u32(&a_empty[sa]));
+                umma_commit_if(tc::smem_u32(&a_empty[sa]), lead);
                 PROF(3);
                 ++acnt;
             }
@@ -852,7 +920,12 @@ struct TunedPlan {
     int BI, TH, NA, bres, NB;
 };
 const TunedPlan kTuned[] = {
-    {-1, 0, 0, 0, 0, 0, 0, 0, 0, 0, -1, 0},
+    // op s2d  Hl  Cl  Hs   Cs  k   BI  TH NA res NB     measured at n = 50 176 (planner's own choice -> tuned), round 2
+    {OP_DOWN, 1, 64, 16, 31, 32, 4, 4, 31, 1, 0, 0},     // E1 forward           1.228 -> 1.147 ms
+    {OP_UP, 0, 14, 64, 6, 128, 4, 4, 7, 1, 0, 4},        // E3 dgrad             1.108 -> 0.930 ms
+    {OP_UP, 0, 31, 32, 14, 64, 4, 4, 16, 1, 1, 0},       // E2 dgrad             1.795 -> 1.363 ms
+    {OP_UP, 0, 13, 64, 5, 128, 5, 3, 7, 1, 0, 3},        // D2 forward           2.050 -> 1.874 ms
+    {OP_DOWN, 1, 64, 16, 30, 32, 6, 3, 30, 2, 1, 0},     // D4 dgrad             1.329 -> 1.261 ms
 };
 const TunedPlan* find_tuned(const mrssm_pl_conv_args* a, int op) {
     if (a->n_img < 1024) return nullptr;             // small launches: the heuristic (few tiles, fill matters more than overlap)
@@ -1230,35 +1303,36 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {       // converged warp, elected lane issues (see the forward-type kernel)
+            const uint32_t lead = elect_one_lane();
             uint32_t acnt = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int sa = acnt % P.NA;
                 tc::mbar_wait(tc::smem_u32(&a_empty[sa]), ((acnt / P.NA) & 1) ^ 1);
                 const uint32_t bar = tc::smem_u32(&a_full[sa]);
-                mbar_expect_tx(bar, (uint32_t)P.nS * (uint32_t)P.small_bytes + (uint32_t)P.nL * (uint32_t)P.large_bytes);
+                mbar_expect_tx_if(bar, (uint32_t)P.nS * (uint32_t)P.small_bytes + (uint32_t)P.nL * (uint32_t)P.large_bytes, lead);
                 const int ig = tile / P.n_bands, band = tile - ig * P.n_bands;
                 const uint32_t dst = smem0 + (uint32_t)sa * (uint32_t)P.stage_bytes;
                 for (int q = 0; q < P.nS; ++q) {
                     if (P.mergedS)
-                        tma_load_4d(dst + (uint32_t)q * (uint32_t)P.PS_s, &mS, 0, band * P.TH, mhalf * 16 + q, ig * P.BI, bar);
+                        tma_load_4d_if(dst + (uint32_t)q * (uint32_t)P.PS_s, &mS, 0, band * P.TH, mhalf * 16 + q, ig * P.BI, bar, lead);
                     else
-                        tma_load_4d(dst + (uint32_t)q * (uint32_t)P.PS_s, &mS, (mhalf * 16 + q) * 8, 0, band * P.TH, ig * P.BI, bar);
+                        tma_load_4d_if(dst + (uint32_t)q * (uint32_t)P.PS_s, &mS, (mhalf * 16 + q) * 8, 0, band * P.TH, ig * P.BI, bar, lead);
                 }
                 for (int q = 0; q < P.nL; ++q) {
                     const int mi = q / P.cpl, ch = q - mi * P.cpl;
                     if (P.rep) {            // plane group mi = column tap b: the same box, origin shifted by b pixels
                         if (P.mergedL)
-                            tma_load_4d(dst + (uint32_t)P.offL + (uint32_t)q * (uint32_t)P.PS_l, &mL0, 2 * mi, band * P.TH, ch, ig * P.BI, bar);
+                            tma_load_4d_if(dst + (uint32_t)P.offL + (uint32_t)q * (uint32_t)P.PS_l, &mL0, 2 * mi, band * P.TH, ch, ig * P.BI, bar, lead);
                         else
-                            tma_load_4d(dst + (uint32_t)P.offL + (uint32_t)q * (uint32_t)P.PS_l, &mL0, ch * 8, mi, band * P.TH, ig * P.BI, bar);
+                            tma_load_4d_if(dst + (uint32_t)P.offL + (uint32_t)q * (uint32_t)P.PS_l, &mL0, ch * 8, mi, band * P.TH, ig * P.BI, bar, lead);
                         continue;
                     }
                     const CUtensorMap* m = mi == 0 ? &mL0 : (mi == 1 ? &mL1 : (mi == 2 ? &mL2 : &mL3));
                     if (P.mergedL)
-                        tma_load_4d(dst + (uint32_t)P.offL + (uint32_t)q * (uint32_t)P.PS_l, m, 0, band * P.TH, ch, ig * P.BI, bar);
+                        tma_load_4d_if(dst + (uint32_t)P.offL + (uint32_t)q * (uint32_t)P.PS_l, m, 0, band * P.TH, ch, ig * P.BI, bar, lead);
                     else
-                        tma_load_4d(dst + (uint32_t)P.offL + (uint32_t)q * (uint32_t)P.PS_l, m, ch * 8, 0, band * P.TH, ig * P.BI, bar);
+                        tma_load_4d_if(dst + (uint32_t)P.offL + (uint32_t)q * (uint32_t)P.PS_l, m, ch * 8, 0, band * P.TH, ig * P.BI, bar, lead);
                 }
                 ++acnt;
             }
@@ -1266,7 +1340,8 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
         __syncwarp();
     } else if (warp == 1) {
         // (two issuing warps do not help: profiles/micro/umma_rate.cu pattern 6 — the ~46-cycle floor per MMA is not per thread)
-        if (lane == 0) {
+        {
+            const uint32_t lead = elect_one_lane();
             const uint32_t idesc = tc::idesc_bf16(128, P.N, 1, 1);
             // MN-major un-swizzled descriptors: LBO = 128 B between 8-pixel (K) groups, SBO = plane stride between 8-channel chunks
             const uint32_t s_hi = ((uint32_t)P.PS_s >> 4) | (1u << 14), l_hi = ((uint32_t)P.PS_l >> 4) | (1u << 14);
@@ -1284,14 +1359,14 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
                     for (int ta = 0; ta < P.nt; ++ta) {
                         uint32_t a_lo = a0, b_lo = (((sL + (uint32_t)(ta * P.BX) * 16u) >> 4) & 0x3FFFu) | lbo;
                         const uint32_t d = tmem_base + (uint32_t)(ta * P.Ntot);
-                        umma_bf16_lohi(d, a_lo, s_hi, b_lo, l_hi, idesc_all, accum);
+                        umma_bf16_lohi_if(d, a_lo, s_hi, b_lo, l_hi, idesc_all, accum, lead);
                         for (int ks = 1; ks < P.nksteps; ++ks) {
                             a_lo += 16u;
                             b_lo += 16u;
-                            umma_bf16_lohi(d, a_lo, s_hi, b_lo, l_hi, idesc_all, 1);
+                            umma_bf16_lohi_if(d, a_lo, s_hi, b_lo, l_hi, idesc_all, 1, lead);
                         }
                     }
-                    tc::umma_commit(tc::smem_u32(&a_empty[sa]));
+                    umma_commit_if(tc::smem_u32(&a_empty[sa]), lead);
                     accum = 1;
                     ++acnt;
                     continue;
@@ -1302,18 +1377,18 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
                                                    : (uint32_t)((kh & 1) * 2 * P.cpl) * (uint32_t)P.PS_l + (uint32_t)((kh >> 1) * P.BX + b) * 16u;
                     uint32_t a_lo = a0, b_lo = (((sL + boff) >> 4) & 0x3FFFu) | lbo;
                     const uint32_t d = tmem_base + (uint32_t)(gi * P.N);
-                    umma_bf16_lohi(d, a_lo, s_hi, b_lo, l_hi, idesc, accum);
+                    umma_bf16_lohi_if(d, a_lo, s_hi, b_lo, l_hi, idesc, accum, lead);
                     for (int ks = 1; ks < P.nksteps; ++ks) {
                         a_lo += 16u;            // 16 pixels = 256 B
                         b_lo += 16u;
-                        umma_bf16_lohi(d, a_lo, s_hi, b_lo, l_hi, idesc, 1);
+                        umma_bf16_lohi_if(d, a_lo, s_hi, b_lo, l_hi, idesc, 1, lead);
                     }
                 }
-                tc::umma_commit(tc::smem_u32(&a_empty[sa]));
+                umma_commit_if(tc::smem_u32(&a_empty[sa]), lead);
                 accum = 1;
                 ++acnt;
             }
-            tc::umma_commit(tc::smem_u32(&acc_full));
+            umma_commit_if(tc::smem_u32(&acc_full), lead);
         }
         __syncwarp();
     } else if (warp >= 4) {
