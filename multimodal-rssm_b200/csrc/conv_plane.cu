@@ -35,7 +35,8 @@ struct PlanOvr {
     int BI, TH, NA, bres, NB;
 };
 PlanOvr g_ovr = {0, 0, 0, -1, 0};
-int g_dbg[4] = {0, 0, 0, 0};   // spare bring-up switches
+int g_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // bring-up switches: 0 barrier polling, 1 no fast epilogue, 2 no L2 prefetch, 3 no column-tap
+                                            // replication (wgrad), 4 no grouped TMA boxes
 
 struct T4 {
     const void* p;
@@ -78,6 +79,32 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
 // ---- converged-warp issue: the producer and the MMA warps run their loops with all 32 lanes (so every operand lives in the
 // uniform datapath and a TMA / MMA is ONE warp-level instruction, not an ELECT retry loop per instruction); the asynchronous
 // instruction itself is guarded by the predicate of the lane chosen once by elect.sync.
+// Barrier wait of a converged warp.  mode 0: every lane polls; mode 1: only the elected lane polls and the result is spread with
+// a vote (warp-uniform by construction, so the code behind it stays in the uniform datapath) — 32 pollers per warp load the
+// barrier unit that also has to deliver the TMA / MMA completions.
+__device__ __forceinline__ void mbar_wait_conv(uint32_t bar, uint32_t parity, uint32_t lead, int mode) {
+    if (mode == 0) {
+        tc::mbar_wait(bar, parity);
+        return;
+    }
+    for (uint32_t it = 0;; ++it) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p, e;\n\t"
+            "setp.ne.b32 e, %3, 0;\n\t"
+            "setp.ne.b32 p, 0, 0;\n\t"
+            "@e mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(lead)
+            : "memory");
+        if (__any_sync(0xffffffffu, done != 0)) return;
+        if (it > (1u << 24)) {
+            if (lead) printf("mrssm plane: mbarrier wait timeout (block %d,%d warp %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x >> 5, bar, parity);
+            __trap();
+        }
+    }
+}
 __device__ __forceinline__ uint32_t elect_one_lane() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -187,10 +214,54 @@ int make_act_map_merged(CUtensorMap* m, const void* base, long long X, long long
                 (int)r, X, Y, chunks, N, sy, sk, sn, bx, by, bi);
     return 0;
 }
+// grouped form for x-contiguous planes: ONE box covers every chunk plane of the map.  dims {2X, Y, N, chunks} — the image dimension
+// before the chunk dimension, whatever their strides — box {2bx, by, bi, chunks}: the box lands in shared memory as
+// [chunk][img][y][x], i.e. the chunk planes the MMA descriptors walk, back to back (plane stride = bi*by*bx*16 bytes).  A TMA box
+// costs the TMA unit ~200 cycles whatever its size (profiles/micro/tma_rate.cu), so 4-64 plane boxes per tile were the
+// bottleneck of most layers.
+int make_act_map_grouped(CUtensorMap* m, const void* base, long long X, long long Y, long long chunks, long long N, long long sy,
+                         long long sk, long long sn, int bx, int by, int bi, int bch) {
+    EncodeTiledFn enc = get_encode();
+    MRSSM_CHECK(enc, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[4] = {(cuuint64_t)(2 * X), (cuuint64_t)Y, (cuuint64_t)N, (cuuint64_t)chunks};
+    cuuint64_t strides[3] = {(cuuint64_t)sy, (cuuint64_t)sn, (cuuint64_t)sk};
+    cuuint32_t box[4] = {(cuuint32_t)(2 * bx), (cuuint32_t)by, (cuuint32_t)bi, (cuuint32_t)bch};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    MRSSM_CHECK(X >= 1 && Y >= 1 && N >= 1 && chunks >= 1 && 2 * bx <= 256 && by <= 256 && bi <= 256 && bch <= 256 && sy % 16 == 0 && sk % 16 == 0 &&
+                    sn % 16 == 0 && ((uintptr_t)base & 15) == 0,
+                "plane conv: planar tensor not TMA-addressable (grouped; dims %lld %lld %lld %lld strides %lld %lld %lld box %d %d %d %d)", X, Y, N,
+                chunks, sy, sn, sk, bx, by, bi, bch);
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MRSSM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(grouped planar) failed: %d (dims %lld %lld %lld %lld strides %lld %lld %lld box %d %d %d %d)",
+                (int)r, X, Y, N, chunks, sy, sn, sk, bx, by, bi, bch);
+    return 0;
+}
+// can the view be loaded with grouped boxes?  (x-contiguous planes: planar or parity-planar)
+inline bool view_groupable(const mrssm_tv& t, bool parity_split) { return t.sW == 8 && (parity_split ? t.par != 0 : t.par == 0); }
+
 // Tensor maps of a source view [N][H][W][Cp]: one map (whole tensor) or four (its 2x2 parity sub-grids).  *merged reports
 // the coordinate convention the kernel must use: merged (2*x, y, chunk, img) or element (chunk*8, x, y, img).
-int make_view_maps(CUtensorMap* maps, int* merged, const mrssm_tv& t, int H, int W, int Cp, int N, bool parity_split, int bx, int by, int bi) {
+int make_view_maps(CUtensorMap* maps, int* merged, const mrssm_tv& t, int H, int W, int Cp, int N, bool parity_split, int bx, int by, int bi,
+                   int group_chunks = 0) {
     const char* base = (const char*)t.ptr;
+    if (group_chunks > 0) {                 // *merged = 2: coordinates (2*x, y, img, first chunk)
+        MRSSM_CHECK(view_groupable(t, parity_split), "plane conv: grouped boxes need x-contiguous planes");
+        *merged = 2;
+        if (!parity_split) {
+            if (int rc = make_act_map_grouped(&maps[0], base, W, H, Cp / 8, N, 2 * t.sH, 2 * t.sK, 2 * t.sI, bx, by, bi, group_chunks)) return rc;
+            maps[1] = maps[2] = maps[3] = maps[0];
+            return 0;
+        }
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                const long long X = std::max(1, (W - px + 1) / 2), Y = std::max(1, (H - py + 1) / 2);
+                if (int rc = make_act_map_grouped(&maps[py * 2 + px], base + 2 * (py * 2 + px) * t.sP, X, Y, Cp / 8, N, 2 * t.sH, 2 * t.sK, 2 * t.sI,
+                                                  bx, by, bi, group_chunks))
+                    return rc;
+            }
+        return 0;
+    }
     if (!parity_split) {
         MRSSM_CHECK(!t.par, "plane conv: this operand must be a linear (NHWC or planar) view, not parity-planar");
         if (t.sW == 8 && 2 * bx <= 256) {
@@ -274,7 +345,8 @@ struct FwdP {
     int NA, NB, b_res;          // b_res: the whole packed weight stays resident in shared memory (NB == nkb)
     int act, mask_mode, out_f32, n_valid, Cop, Ho, Wo;
     int a_stage_bytes;
-    int mergedA;                // TMA coordinate convention of the activation maps
+    int mergedA;                // TMA coordinate convention of the activation maps (2: grouped boxes, one per map)
+    int group;                  // one box per tensor map: every chunk plane of the map (planes are dense, PS = plane_bytes)
     int s2d;                    // down: the source is the space-to-depth (16-channel) form of a <= 4-channel image
     long long* prof;            // [CTA][16 tiles][8 slots] clock64 stamps or NULL
     TV out, mask;               // bf16 output / act'-mask views (indexed at the output pixel)
@@ -291,6 +363,7 @@ struct FwdP {
     int mse_vec;                // target rows are x-contiguous and 8-byte aligned: float2 loads
     // fast epilogue (bf16 output, act none / ReLU, every item inside one parity class): nc columns per item (16, 32 or 64)
     int fast, ncp, nc;
+    int poll;                   // barrier polling of the converged warps (mbar_wait_conv)
     uint8_t* bits_out;          // ReLU sign bits of the output, byte (pixel, 8-channel chunk) at [img][y][x][Cop/8]
     const uint8_t* bits_in;     // act'-mask of a dgrad in the same form (instead of the bf16 `mask` view)
     long long bits_img_bytes;   // bytes of one image of bits_in (L2 prefetch per tile)
@@ -616,16 +689,27 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
             };
             auto issue_A = [&](int tile) {
                 const int sa = acnt % P.NA;
-                tc::mbar_wait(tc::smem_u32(&a_empty[sa]), ((acnt / P.NA) & 1) ^ 1);
+                mbar_wait_conv(tc::smem_u32(&a_empty[sa]), ((acnt / P.NA) & 1) ^ 1, lead, P.poll);
                 const uint32_t bar = tc::smem_u32(&a_full[sa]);
                 mbar_expect_tx_if(bar, (uint32_t)P.planes * (uint32_t)P.plane_bytes, lead);
                 const int ig = tile / P.n_bands, band = tile - ig * P.n_bands;
                 const uint32_t dst = smemA + (uint32_t)sa * (uint32_t)P.a_stage_bytes;
-                for (int q = 0; q < P.planes; ++q) {
-                    const CUtensorMap* m;
-                    int c0, c1, c2, c3;
-                    plane_coords(tile, q, m, c0, c1, c2, c3);
-                    tma_load_4d_if(dst + (uint32_t)q * (uint32_t)P.PS, m, c0, c1, c2, c3, bar, lead);
+                if (P.group) {          // one box per map: all of its chunk planes, [chunk][img][y][x]
+                    const uint32_t map_bytes = (uint32_t)P.ppm * (uint32_t)P.PS;
+                    const int cy = band * P.TH + P.y0, ci = ig * P.BI;
+                    tma_load_4d_if(dst, &mA0, 2 * P.x0, cy, ci, 0, bar, lead);
+                    if (P.planes > P.ppm) {
+                        tma_load_4d_if(dst + map_bytes, &mA1, 2 * P.x0, cy, ci, 0, bar, lead);
+                        tma_load_4d_if(dst + 2 * map_bytes, &mA2, 2 * P.x0, cy, ci, 0, bar, lead);
+                        tma_load_4d_if(dst + 3 * map_bytes, &mA3, 2 * P.x0, cy, ci, 0, bar, lead);
+                    }
+                } else {
+                    for (int q = 0; q < P.planes; ++q) {
+                        const CUtensorMap* m;
+                        int c0, c1, c2, c3;
+                        plane_coords(tile, q, m, c0, c1, c2, c3);
+                        tma_load_4d_if(dst + (uint32_t)q * (uint32_t)P.PS, m, c0, c1, c2, c3, bar, lead);
+                    }
                 }
                 if (band == 0) {
                     // what the epilogue of this tile reads straight from global memory (sign bytes, act'-mask, loss target): pull
@@ -640,6 +724,17 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
             // single-buffered activation stage: the load of the next tile can only start when this tile's MMAs are done, so its
             // planes are pulled into L2 meanwhile (the TMA load then hits L2 instead of HBM)
             auto prefetch_A = [&](int tile) {
+                if (P.group) {
+                    const int ig = tile / P.n_bands, band = tile - ig * P.n_bands;
+                    const int cy = band * P.TH + P.y0, ci = ig * P.BI;
+                    tma_prefetch_4d_if(&mA0, 2 * P.x0, cy, ci, 0, lead);
+                    if (P.planes > P.ppm) {
+                        tma_prefetch_4d_if(&mA1, 2 * P.x0, cy, ci, 0, lead);
+                        tma_prefetch_4d_if(&mA2, 2 * P.x0, cy, ci, 0, lead);
+                        tma_prefetch_4d_if(&mA3, 2 * P.x0, cy, ci, 0, lead);
+                    }
+                    return;
+                }
                 for (int q = 0; q < P.planes; ++q) {
                     const CUtensorMap* m;
                     int c0, c1, c2, c3;
@@ -668,7 +763,7 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                         const int nti = it / P.n_passes;
                         for (int kb = 0; kb < P.nkb; ++kb) {
                             const int sb = bcnt % P.NB;
-                            tc::mbar_wait(tc::smem_u32(&b_empty[sb]), ((bcnt / P.NB) & 1) ^ 1);
+                            mbar_wait_conv(tc::smem_u32(&b_empty[sb]), ((bcnt / P.NB) & 1) ^ 1, lead, P.poll);
                             const uint32_t bar = tc::smem_u32(&b_full[sb]);
                             mbar_expect_tx_if(bar, b_stage, lead);
                             tma_load_2d_if(smem0 + (uint32_t)sb * b_stage, &mB, kb * 64, nti * P.BN, bar, lead);
@@ -693,14 +788,14 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
             int lit = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lit) {
                 const int sa = acnt % P.NA;
-                tc::mbar_wait(tc::smem_u32(&a_full[sa]), (acnt / P.NA) & 1);
+                mbar_wait_conv(tc::smem_u32(&a_full[sa]), (acnt / P.NA) & 1, lead, P.poll);
                 tc::tc_fence_after();
                 PROF(2);
                 const uint32_t a_base = (((smemA + (uint32_t)sa * (uint32_t)P.a_stage_bytes) >> 4) & 0x3FFFu) | a_lbo;
                 for (int it = 0; it < P.n_ntiles * P.n_passes; ++it) {
                     const int pass = it % P.n_passes;
                     const int set = ccnt % P.n_sets;
-                    tc::mbar_wait(tc::smem_u32(&acc_empty[set]), ((ccnt / P.n_sets) & 1) ^ 1);
+                    mbar_wait_conv(tc::smem_u32(&acc_empty[set]), ((ccnt / P.n_sets) & 1) ^ 1, lead, P.poll);
                     tc::tc_fence_after();
                     if (it == 0) PROF(6);
                     const int mb0 = pass * P.MBs, nmb = min(P.MBs, P.MB_total - mb0);
@@ -709,7 +804,7 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                     if (P.b_res) {
                         // whole weight resident: one accumulator at a time, all of its K steps back to back
                         if (lit == 0 && it == 0) {
-                            for (int kb = 0; kb < P.nkb; ++kb) tc::mbar_wait(tc::smem_u32(&b_full[kb]), 0);
+                            for (int kb = 0; kb < P.nkb; ++kb) mbar_wait_conv(tc::smem_u32(&b_full[kb]), 0, lead, P.poll);
                             tc::tc_fence_after();
                         }
                         const uint32_t b_base = ((smem0 >> 4) & 0x3FFFu) | (1u << 16);
@@ -735,7 +830,7 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                     } else {
                         for (int kb = 0; kb < P.nkb; ++kb) {
                             const int sb = bcnt % P.NB;
-                            tc::mbar_wait(tc::smem_u32(&b_full[sb]), (bcnt / P.NB) & 1);
+                            mbar_wait_conv(tc::smem_u32(&b_full[sb]), (bcnt / P.NB) & 1, lead, P.poll);
                             tc::tc_fence_after();
                             const uint32_t b_lo = (((smem0 + (uint32_t)sb * b_stage) >> 4) & 0x3FFFu) | (1u << 16);
                             const uint4 ko = make_uint4(P.ks_off16[kb * 4], P.ks_off16[kb * 4 + 1], P.ks_off16[kb * 4 + 2], P.ks_off16[kb * 4 + 3]);
@@ -986,6 +1081,14 @@ int plan_fwd(const mrssm_pl_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
     P.n_sets = 2; P.set_cols = 256;
     P.MBs = std::max(1, 256 / P.BN);
     P.BX = P.Wv + nt - 1;
+    // grouped boxes (one TMA box per tensor map) put the chunk planes back to back: plane stride = the plane's own bytes.  The
+    // rows an MMA block reads past its plane's end (M round-up, tap shifts) then alias the next plane — they only feed rows
+    // whose outputs are discarded — and the last plane needs that much slack behind it.  Every map's first plane must start
+    // 128-byte aligned: the row pitch is widened until ppm * BX is a multiple of 8 pixels (whatever BI and BY turn out to be).
+    const mrssm_tv& src_view = (op == OP_DOWN) ? a->large : a->small;
+    const bool can_group = !g_dbg[4] && src_view.ptr && view_groupable(src_view, op == OP_DOWN && !P.s2d) && P.ppm <= 256;
+    if (can_group)
+        while ((P.ppm * P.BX) % 8 != 0) ++P.BX;
     const int maxshift = (nt - 1) * P.BX + nt - 1;
     const long long min_a = (long long)P.planes * ((128 + maxshift) * 16 + 128);    // one 128-row block of the smallest tile
     // the whole packed weight stays resident when it is small; otherwise it streams through a ring of 64-wide K blocks
@@ -1006,10 +1109,17 @@ int plan_fwd(const mrssm_pl_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
     }
     const long long bring = (long long)P.NB * P.BN * 128;
     const long long avail = SMEM_TOTAL - bring;
+    bool grouped = false;
     auto stage_bytes = [&](int BI, int BY, int TH, int& MB_total, int& PS) {
         long long Lout = ((long long)(BI - 1) * BY + (TH - 1)) * P.BX + P.Wv;
         MB_total = (int)((Lout + 127) / 128);
-        long long ps = std::max<long long>((long long)BI * BY * P.BX * 16, ((long long)MB_total * 128 + maxshift) * 16);
+        const long long dense = (long long)BI * BY * P.BX * 16, need = ((long long)MB_total * 128 + maxshift) * 16;
+        grouped = can_group && 2 * P.BX <= 256 && BI <= 256 && BY <= 256 && ((long long)P.ppm * dense) % 128 == 0 && dense < 262144;
+        if (grouped) {
+            PS = (int)dense;
+            return ((long long)P.planes * dense + std::max<long long>(0, need - dense) + 1023) / 1024 * 1024;
+        }
+        long long ps = std::max<long long>(dense, need);
         PS = (int)((ps + 127) / 128 * 128);
         return (long long)P.planes * PS;
     };
@@ -1065,6 +1175,7 @@ int plan_fwd(const mrssm_pl_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
         P.BI = 1; P.TH = TH; P.BY = TH + nt - 1;
     }
     P.a_stage_bytes = (int)stage_bytes(P.BI, P.BY, P.TH, P.MB_total, P.PS);
+    P.group = grouped ? 1 : 0;
     MRSSM_CHECK(P.PS / 16 < 16384, "plane conv: plane stride %d too large for the descriptor", P.PS);
     P.plane_bytes = P.BI * P.BY * P.BX * 16;
     P.n_groups = (a->n_img + P.BI - 1) / P.BI;
@@ -1087,6 +1198,7 @@ int plan_fwd(const mrssm_pl_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
     }
     P.bias = a->bias;
     P.prof = g_prof;
+    P.poll = g_dbg[0];
     P.scale_ptr = a->scale_ptr; P.scale_mul = a->scale_mul;
     P.mse_target = a->mse_target; P.mse_sum = a->mse_sum; P.mse_scale = a->mse_scale;
     if (P.mse_target) {
@@ -1150,14 +1262,14 @@ int launch_fwd(const mrssm_pl_conv_args* a, int op, cudaStream_t st) {
     if (op == OP_DOWN) {
         MRSSM_CHECK(a->large.ptr, "plane down: null source");
         if (P.s2d) {
-            if (int rc = make_view_maps(mA, &P.mergedA, a->large, (a->Hl + 1) / 2, (a->Wl + 1) / 2, a->Cl, a->n_img, false, P.BX, P.BY, P.BI))
+            if (int rc = make_view_maps(mA, &P.mergedA, a->large, (a->Hl + 1) / 2, (a->Wl + 1) / 2, a->Cl, a->n_img, false, P.BX, P.BY, P.BI, P.group ? P.ppm : 0))
                 return rc;
-        } else if (int rc = make_view_maps(mA, &P.mergedA, a->large, a->Hl, a->Wl, a->Cl, a->n_img, true, P.BX, P.BY, P.BI)) {
+        } else if (int rc = make_view_maps(mA, &P.mergedA, a->large, a->Hl, a->Wl, a->Cl, a->n_img, true, P.BX, P.BY, P.BI, P.group ? P.ppm : 0)) {
             return rc;
         }
     } else {
         MRSSM_CHECK(a->small.ptr, "plane up: null source");
-        if (int rc = make_view_maps(mA, &P.mergedA, a->small, a->Hs, a->Ws, a->Cs, a->n_img, false, P.BX, P.BY, P.BI)) return rc;
+        if (int rc = make_view_maps(mA, &P.mergedA, a->small, a->Hs, a->Ws, a->Cs, a->n_img, false, P.BX, P.BY, P.BI, P.group ? P.ppm : 0)) return rc;
     }
     const long long K_total = (long long)P.nkb * 64;
     const long long N_total = (long long)P.BN * P.n_ntiles;
@@ -1253,6 +1365,7 @@ struct WgP {
     int ksz, nt, Clp, Csp, N;
     int NG, gpp, n_cpass, n_mhalf;
     int NA, zero_bytes, mergedS, mergedL, s2d_cq;
+    int group;                  // one TMA box per tensor map (all chunk planes of the map, planes dense)
     int rep, Ntot;              // rep: the large tile is loaded once per COLUMN tap b with the box origin shifted by b pixels (plane
                                 // group = b), so one MMA of N = Ntot = nt * N covers the nt column taps of a row tap a; row taps stay
                                 // descriptor shifts of a * BX pixels (space-to-depth sources: N = 16 per tap otherwise)
@@ -1262,6 +1375,7 @@ struct WgP {
     float* dw;
     long long w_ss, w_sl;
     // bias gradient from the resident operand tile (warps 4..7 while the MMAs run): db_from 1 = small planes, 2 = large planes
+    int poll;
     float* db;
     int db_from, db_nch, db_npar;     // 8-channel chunks to sum, plane groups per chunk (large, parity split: 4)
     int db_valid, db_fold;            // real channels; fold > 0: channel c of the tile is channel c % fold for c < 4 * fold
@@ -1308,11 +1422,29 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
             uint32_t acnt = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int sa = acnt % P.NA;
-                tc::mbar_wait(tc::smem_u32(&a_empty[sa]), ((acnt / P.NA) & 1) ^ 1);
+                mbar_wait_conv(tc::smem_u32(&a_empty[sa]), ((acnt / P.NA) & 1) ^ 1, lead, P.poll);
                 const uint32_t bar = tc::smem_u32(&a_full[sa]);
                 mbar_expect_tx_if(bar, (uint32_t)P.nS * (uint32_t)P.small_bytes + (uint32_t)P.nL * (uint32_t)P.large_bytes, lead);
                 const int ig = tile / P.n_bands, band = tile - ig * P.n_bands;
                 const uint32_t dst = smem0 + (uint32_t)sa * (uint32_t)P.stage_bytes;
+                if (P.group) {
+                    // one box for the small planes of this Cs half, one per large tensor map (parity, or column tap when replicated)
+                    const int cy = band * P.TH, ci = ig * P.BI;
+                    const uint32_t dl = dst + (uint32_t)P.offL, map_bytes = (uint32_t)P.cpl * (uint32_t)P.PS_l;
+                    tma_load_4d_if(dst, &mS, 0, cy, ci, mhalf * 16, bar, lead);
+                    if (P.rep) {
+                        for (int mi = 0; mi < P.nt; ++mi) tma_load_4d_if(dl + (uint32_t)mi * map_bytes, &mL0, 2 * mi, cy, ci, 0, bar, lead);
+                    } else {
+                        tma_load_4d_if(dl, &mL0, 0, cy, ci, 0, bar, lead);
+                        if (P.nL > P.cpl) {
+                            tma_load_4d_if(dl + map_bytes, &mL1, 0, cy, ci, 0, bar, lead);
+                            tma_load_4d_if(dl + 2 * map_bytes, &mL2, 0, cy, ci, 0, bar, lead);
+                            tma_load_4d_if(dl + 3 * map_bytes, &mL3, 0, cy, ci, 0, bar, lead);
+                        }
+                    }
+                    ++acnt;
+                    continue;
+                }
                 for (int q = 0; q < P.nS; ++q) {
                     if (P.mergedS)
                         tma_load_4d_if(dst + (uint32_t)q * (uint32_t)P.PS_s, &mS, 0, band * P.TH, mhalf * 16 + q, ig * P.BI, bar, lead);
@@ -1350,7 +1482,7 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
             uint32_t accum = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int sa = acnt % P.NA;
-                tc::mbar_wait(tc::smem_u32(&a_full[sa]), (acnt / P.NA) & 1);
+                mbar_wait_conv(tc::smem_u32(&a_full[sa]), (acnt / P.NA) & 1, lead, P.poll);
                 tc::tc_fence_after();
                 const uint32_t sS = smem0 + (uint32_t)sa * (uint32_t)P.stage_bytes, sL = sS + (uint32_t)P.offL;
                 const uint32_t a0 = ((sS >> 4) & 0x3FFFu) | lbo;
@@ -1529,20 +1661,46 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
     P.gpp = std::min(P.NG, 512 / P.N);
     P.n_cpass = (P.NG + P.gpp - 1) / P.gpp;
     P.gpp = (P.NG + P.n_cpass - 1) / P.n_cpass;
-    P.BX = a->Ws + nt - 1;
-    const int maxshift = (nt - 1) * P.BX + nt - 1;
+    const int BXmin = a->Ws + nt - 1;
+    // grouped TMA boxes (one per tensor map: every chunk plane of the map, planes back to back): both operands must be
+    // x-contiguous planes.  The contraction runs over the pixels of a plane in steps of 16, so with nothing between the planes
+    // the pixel count of a small plane must itself be a multiple of 16: the row pitch BX is widened until it is (the extra
+    // columns are out-of-bounds zeros of the boxes).
+    const bool can_group = !g_dbg[4] && view_groupable(a->small, false) && view_groupable(a->large, !P.s2d_cq);
     auto plan = [&](int BI, int TH, bool banded, int NA) -> long long {
         const int BY = TH + nt - 1;
         const int SBY = banded ? TH : BY;
-        const long long L = banded ? (long long)TH * P.BX : (long long)BI * BY * P.BX;
+        int BX = BXmin;
+        bool grp = can_group && BI <= 256 && BY <= 256 && P.nS <= 256 && P.cpl <= 256;
+        if (grp) {
+            while (((long long)BI * SBY * BX) % 16 != 0 && BX < BXmin + 16) ++BX;
+            grp = ((long long)BI * SBY * BX) % 16 == 0 && 2 * BX <= 256;
+            if (!grp) BX = BXmin;
+        }
+        if (grp) {       // every box destination 128-byte aligned
+            const long long sb = (long long)BI * SBY * BX * 16, lb = (long long)BI * BY * BX * 16;
+            grp = ((long long)P.nS * sb) % 128 == 0 && ((long long)P.cpl * lb) % 128 == 0 && sb < 262144 && lb < 262144;
+            if (!grp) BX = BXmin;
+        }
+        P.BX = BX; P.group = grp ? 1 : 0;
+        const int maxshift = (nt - 1) * BX + nt - 1;
+        const long long L = banded ? (long long)TH * BX : (long long)BI * BY * BX;
         const long long L16 = (L + 15) / 16 * 16;
         P.BI = BI; P.TH = TH; P.BY = BY; P.SBY = SBY; P.NA = NA;
-        P.small_bytes = BI * SBY * P.BX * 16;
-        P.large_bytes = BI * BY * P.BX * 16;
-        P.PS_s = (int)((L16 * 16 + 127) / 128 * 128);
-        P.PS_l = (int)(((L16 + maxshift) * 16 + 127) / 128 * 128);
-        P.offL = P.nS * P.PS_s;
-        P.stage_bytes = P.offL + P.nL * P.PS_l;
+        P.small_bytes = BI * SBY * BX * 16;
+        P.large_bytes = BI * BY * BX * 16;
+        if (grp) {
+            P.PS_s = P.small_bytes;
+            P.PS_l = P.large_bytes;
+            P.offL = P.nS * P.PS_s;
+            // behind the last large plane: what the last K steps and the tap shifts read past it (stays zero: no box writes it)
+            P.stage_bytes = (int)(((long long)P.offL + (long long)P.nL * P.PS_l + (maxshift + 16) * 16 + 1023) / 1024 * 1024);
+        } else {
+            P.PS_s = (int)((L16 * 16 + 127) / 128 * 128);
+            P.PS_l = (int)(((L16 + maxshift) * 16 + 127) / 128 * 128);
+            P.offL = P.nS * P.PS_s;
+            P.stage_bytes = P.offL + P.nL * P.PS_l;
+        }
         P.nksteps = (int)(L16 / 16);
         const long long span = 16LL * P.PS_s + 0;    // an M=128 descriptor walks 16 chunk planes from the stage start
         const long long last = std::max<long long>(P.stage_bytes, span);
@@ -1555,7 +1713,7 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
     // whole images, double buffered, as many images per tile as fit (capped so a tile stays a few thousand pixels)
     if (plan(1, Hs, false, 2) <= avail) {
         int BI = 1;
-        while (BI < std::min(a->n_img, 256) && (long long)(BI + 1) * (Hs + nt - 1) * P.BX <= 4096 && plan(BI + 1, Hs, false, 2) <= avail) ++BI;
+        while (BI < std::min(a->n_img, 256) && (long long)(BI + 1) * (Hs + nt - 1) * BXmin <= 4096 && plan(BI + 1, Hs, false, 2) <= avail) ++BI;
         plan(BI, Hs, false, 2);
         P.n_bands = 1;
         done = true;
@@ -1577,6 +1735,7 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
     P.cs_valid = a->cs_valid; P.cl_valid = a->cl_valid;
     P.dw = a->dweight; P.w_ss = a->w_ss; P.w_sl = a->w_sl;
     P.scale_ptr = a->scale_ptr; P.scale_mul = a->scale_mul;
+    P.poll = g_dbg[0];
     P.db = a->dbias; P.db_from = a->dbias ? a->dbias_from : 0;
     if (P.db_from) {
         MRSSM_CHECK(P.db_from == 1 || P.db_from == 2, "plane wgrad: dbias_from %d (1 = small, 2 = large)", P.db_from);
@@ -1600,10 +1759,10 @@ int launch_wgrad(const mrssm_pl_conv_args* a, cudaStream_t st) {
     int splits;
     if (int rc = plan_wgrad(a, P, smem, splits)) return rc;
     CUtensorMap mS[4], mL[4];
-    if (int rc = make_view_maps(mS, &P.mergedS, a->small, a->Hs, a->Ws, a->Cs, a->n_img, false, P.BX, P.SBY, P.BI)) return rc;
+    if (int rc = make_view_maps(mS, &P.mergedS, a->small, a->Hs, a->Ws, a->Cs, a->n_img, false, P.BX, P.SBY, P.BI, P.group ? P.nS : 0)) return rc;
     if (P.s2d_cq) {
-        if (int rc = make_view_maps(mL, &P.mergedL, a->large, (a->Hl + 1) / 2, (a->Wl + 1) / 2, a->Cl, a->n_img, false, P.BX, P.BY, P.BI)) return rc;
-    } else if (int rc = make_view_maps(mL, &P.mergedL, a->large, a->Hl, a->Wl, a->Cl, a->n_img, true, P.BX, P.BY, P.BI)) {
+        if (int rc = make_view_maps(mL, &P.mergedL, a->large, (a->Hl + 1) / 2, (a->Wl + 1) / 2, a->Cl, a->n_img, false, P.BX, P.BY, P.BI, P.group ? P.cpl : 0)) return rc;
+    } else if (int rc = make_view_maps(mL, &P.mergedL, a->large, a->Hl, a->Wl, a->Cl, a->n_img, true, P.BX, P.BY, P.BI, P.group ? P.cpl : 0)) {
         return rc;
     }
     dim3 grid((unsigned)splits, (unsigned)(P.n_cpass * P.n_mhalf));
@@ -1908,7 +2067,7 @@ extern "C" int mrssm_pl_colsum(const mrssm_tv* x, int32_t n_img, int32_t H, int3
 }
 
 extern "C" int mrssm_pl_set_debug(int32_t key, int32_t value) {
-    MRSSM_CHECK(key >= 0 && key < 4, "pl_set_debug: bad key");
+    MRSSM_CHECK(key >= 0 && key < 8, "pl_set_debug: bad key");
     g_dbg[key] = value;
     return 0;
 }
@@ -1933,9 +2092,9 @@ extern "C" int mrssm_pl_describe(const mrssm_pl_conv_args* a, int32_t op, char* 
         if (int rc = plan_wgrad(a, P, smem, splits)) return rc;
         snprintf(buf, buflen,
                  "wgrad BI=%d bands=%d TH=%d BX=%d BY=%d nS=%d nL=%d PS_s=%d PS_l=%d stage=%d NA=%d ksteps/tile=%d N=%d groups=%d gpp=%d cpass=%d mhalf=%d "
-                 "splits=%d smem=%zu tiles=%d rep=%d",
+                 "splits=%d smem=%zu tiles=%d rep=%d group=%d",
                  P.BI, P.n_bands, P.TH, P.BX, P.BY, P.nS, P.nL, P.PS_s, P.PS_l, P.stage_bytes, P.NA, P.nksteps, P.N, P.NG, P.gpp, P.n_cpass,
-                 P.n_mhalf, splits, smem, P.n_groups * P.n_bands, P.rep);
+                 P.n_mhalf, splits, smem, P.n_groups * P.n_bands, P.rep, P.group);
     } else {
         FwdP P;
         size_t smem;
@@ -1943,9 +2102,9 @@ extern "C" int mrssm_pl_describe(const mrssm_pl_conv_args* a, int32_t op, char* 
         double eff = (double)P.BI * std::min(P.TH, P.Hv) * P.Wv / ((double)P.MB_total * 128);
         snprintf(buf, buflen,
                  "%s BI=%d bands=%d TH=%d BX=%d BY=%d planes=%d PS=%d stage=%d NA=%d NB=%d bres=%d BN=%d ntiles=%d ksteps=%d MB_total=%d MBs=%d passes=%d "
-                 "smem=%zu tiles=%d row_eff=%.2f",
+                 "smem=%zu tiles=%d group=%d row_eff=%.2f",
                  op == OP_DOWN ? "down" : "up", P.BI, P.n_bands, P.TH, P.BX, P.BY, P.planes, P.PS, P.a_stage_bytes, P.NA, P.NB, P.b_res, P.BN, P.n_ntiles,
-                 P.n_ksteps, P.MB_total, P.MBs, P.n_passes, smem, P.n_groups * P.n_bands, eff);
+                 P.n_ksteps, P.MB_total, P.MBs, P.n_passes, smem, P.n_groups * P.n_bands, P.group, eff);
     }
     return 0;
 }

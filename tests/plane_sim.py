@@ -132,18 +132,22 @@ def sim_fwd(L, op, src, w, Hl, Wl, Hs, Ws, n_out_pad, s2d_cq=0):
     ngroups = (n + BI - 1) // BI
     for ig in range(ngroups):
         for band in range(nb):
-            A = np.full((planes, PSpos, 8), np.nan, np.float32)
+            # the activation stage as one run of 16-byte positions: plane q starts at q * PS (grouped boxes put the planes back
+            # to back, so what an MMA block reads past its plane's end is the next plane; behind the last plane: never written)
+            MB = P["MB_total"]
+            rows = MB * 128
+            flat = np.full((P["stage"] // 16 + rows + 4 * BX + 8, 8), np.nan, np.float32)
             for q in range(planes):
                 if op == 0 and s2d_cq:
-                    A[q, :BI * BY * BX] = _box(src, q * 8, 0, band * TH, ig * BI, BX, BY, BI)
+                    box = _box(src, q * 8, 0, band * TH, ig * BI, BX, BY, BI)
                 elif op == 0:
                     ppm = Clp // 8
                     mi, c0 = q // ppm, (q % ppm) * 8
-                    A[q, :BI * BY * BX] = _box(src, c0, 0, band * TH, ig * BI, BX, BY, BI, 2, 2, mi & 1, mi >> 1)
+                    box = _box(src, c0, 0, band * TH, ig * BI, BX, BY, BI, 2, 2, mi & 1, mi >> 1)
                 else:
-                    A[q, :BI * BY * BX] = _box(src, q * 8, -(nt - 1), band * TH - (nt - 1), ig * BI, BX, BY, BI)
-            MB = P["MB_total"]
-            rows = MB * 128
+                    box = _box(src, q * 8, -(nt - 1), band * TH - (nt - 1), ig * BI, BX, BY, BI)
+                flat[q * PSpos:q * PSpos + BI * BY * BX] = box
+            A = [flat[q * PSpos:] for q in range(planes)]
             acc = np.zeros((rows, N_total), np.float32)
             for ks in range(n_ksteps):
                 j, t = ks % J, ks // J
@@ -154,7 +158,7 @@ def sim_fwd(L, op, src, w, Hl, Wl, Hs, Ws, n_out_pad, s2d_cq=0):
                     plane, shift = (r & 1) * 2 * J + 2 * j, (r >> 1) * BX + b
                 else:
                     plane, shift = 2 * j, (nt - 1 - r) * BX + (nt - 1 - b)
-                a16 = np.concatenate([A[plane, shift:shift + rows], A[plane + 1, shift:shift + rows]], axis=1)
+                a16 = np.concatenate([A[plane][shift:shift + rows], A[plane + 1][shift:shift + rows]], axis=1)
                 acc += a16 @ wp[:, ks * 16:ks * 16 + 16].T
             IP = BY * BX
             for p in range(rows):
@@ -171,6 +175,16 @@ def sim_fwd(L, op, src, w, Hl, Wl, Hs, Ws, n_out_pad, s2d_cq=0):
                         if yy < Ho and xx < Wo:
                             out[img, yy, xx, :] = acc[p, cls * Clp:(cls + 1) * Clp]
     return out, P
+
+
+class _Planes:
+    """Chunk planes inside a flat stage: take(p0, count, shift, K) -> [K, count, 8] rows shift.. of planes p0.."""
+
+    def __init__(self, flat, ps):
+        self.flat, self.ps = flat, ps
+
+    def take(self, p0, count, shift, K):
+        return np.stack([self.flat[(p0 + q) * self.ps + shift:(p0 + q) * self.ps + shift + K] for q in range(count)], 1)
 
 
 def sim_wgrad(L, small, large, k, s2d_cq=0, Hl=None):
@@ -195,23 +209,28 @@ def sim_wgrad(L, small, large, k, s2d_cq=0, Hl=None):
     nL = cpl if s2d_cq else 4 * cpl
     for ig in range(ngroups):
         for band in range(nb):
-            S = np.zeros((Csp // 8, PS_s, 8), np.float32)
-            Lg = np.zeros((nL, PS_l, 8), np.float32)
-            for q in range(Csp // 8):
-                S[q, :BI * SBY * BX] = _box(small, q * 8, 0, band * TH, ig * BI, BX, SBY, BI)
+            # the operand stage as runs of 16-byte positions: plane q at q * PS; what no box writes is zero (the kernel zeroes the
+            # stages once).  Grouped boxes put the planes back to back, so reads past a plane's end see the next plane.
+            K = nks * 16
+            nSp = Csp // 8
+            sflat = np.zeros((nSp * PS_s + K + 64, 8), np.float32)
+            lflat = np.zeros((nL * PS_l + K + 4 * BX + 64, 8), np.float32)
+            for q in range(nSp):
+                sflat[q * PS_s:q * PS_s + BI * SBY * BX] = _box(small, q * 8, 0, band * TH, ig * BI, BX, SBY, BI)
             for q in range(nL):
                 if s2d_cq:
-                    Lg[q, :BI * BY * BX] = _box(large, q * 8, 0, band * TH, ig * BI, BX, BY, BI)
+                    box = _box(large, q * 8, 0, band * TH, ig * BI, BX, BY, BI)
                 else:
                     mi, c0 = q // cpl, (q % cpl) * 8
-                    Lg[q, :BI * BY * BX] = _box(large, c0, 0, band * TH, ig * BI, BX, BY, BI, 2, 2, mi & 1, mi >> 1)
-            K = nks * 16
-            Sm = S[:, :K].transpose(1, 0, 2).reshape(K, Csp)            # [pixel][cs]
+                    box = _box(large, c0, 0, band * TH, ig * BI, BX, BY, BI, 2, 2, mi & 1, mi >> 1)
+                lflat[q * PS_l:q * PS_l + BI * BY * BX] = box
+            Sm = np.stack([sflat[q * PS_s:q * PS_s + K] for q in range(nSp)], 1).reshape(K, Csp)            # [pixel][cs]
+            Lg = _Planes(lflat, PS_l)
             if s2d_cq:
                 for g in range(nt * nt):
                     a, b = g // nt, g % nt
                     shift = a * BX + b
-                    Bm = Lg[:, shift:shift + K].transpose(1, 0, 2).reshape(K, Clp)                          # [pixel][(parity, c)]
+                    Bm = Lg.take(0, nL, shift, K).reshape(K, Clp)                          # [pixel][(parity, c)]
                     D = Sm.T @ Bm
                     for c in range(Clp):
                         par, cl = c // s2d_cq, c % s2d_cq
@@ -222,7 +241,7 @@ def sim_wgrad(L, small, large, k, s2d_cq=0, Hl=None):
             for g in range(k * nt):
                 kh, b = g // nt, g % nt
                 plane0, shift = (kh & 1) * 2 * cpl, (kh >> 1) * BX + b
-                Bm = Lg[plane0:plane0 + 2 * cpl, shift:shift + K].transpose(1, 0, 2).reshape(K, 2 * Clp)   # [pixel][(px, cl)]
+                Bm = Lg.take(plane0, 2 * cpl, shift, K).reshape(K, 2 * Clp)   # [pixel][(px, cl)]
                 D = Sm.T @ Bm
                 for px in range(2):
                     kw = 2 * b + px
