@@ -10,7 +10,7 @@ import torch
 from sweep_plans import DEV, L, ops, timed
 
 # name: (Hl, Cl, Hs, Cs, k, s2d, dbias_from)
-WG = {"E1": (64, 3, 31, 32, 4, 1, 1), "E2": (31, 32, 14, 64, 4, 0, 1), "E3": (14, 64, 6, 128, 4, 0, 1),
+WG = {"E4": (6, 128, 2, 256, 4, 0, 1), "E1": (64, 3, 31, 32, 4, 1, 1), "E2": (31, 32, 14, 64, 4, 0, 1), "E3": (14, 64, 6, 128, 4, 0, 1),
       "D2": (13, 64, 5, 128, 5, 0, 2), "D3": (30, 32, 13, 64, 6, 0, 2), "D4": (64, 3, 30, 32, 6, 1, 2)}
 
 
