@@ -1123,6 +1123,94 @@ def packed_pl(w, op, Cs_pad, Cl_pad, s2d_cq=0):
     return hit[1]
 
 
+class MlpTCFn(Function):
+    """MlpFn in bf16 tensor-core mode: every Linear is a tcgen05 GEMM (bf16 operands, fp32 accumulate; activation in the epilogue,
+    act' in the dgrad epilogue, bf16 intermediates), the result is fp32.  apply(act, final_act, n_parts, *parts, *params) like
+    MlpFn.  Replaces eleven per-layer fp32 CUDA-core launches of the SymbolicEncoder / DenseDecoder / RewardModel stacks
+    (reference encoder.py:282-305, observation_model.py:33-54, reward_model.py:20-35)."""
+
+    @staticmethod
+    def forward(ctx, act, final_act, n_parts, *args):
+        parts = [_f32c(t) for t in args[:n_parts]]
+        params = args[n_parts:]
+        M = parts[0].shape[0]
+        dev = parts[0].device
+        n_layers = len(params) // 2
+        if n_parts == 1:
+            x0, K0 = parts[0], parts[0].shape[1]
+        else:
+            assert n_parts == 2, "MlpTCFn concatenates at most two inputs"
+            K0 = parts[0].shape[1] + parts[1].shape[1]
+            x0 = torch.empty(M, K0, device=dev, dtype=torch.float32)
+            L.call("mrssm_concat2", L.ptr(parts[0]), parts[0].shape[1], L.ptr(parts[1]), parts[1].shape[1], M, L.ptr(x0))
+        cur = tc_to_bf16(L.nhwc(x0, 1, 1, K0), M, 1, 1, K0, dev)            # [M,1,1,pad8(K0)]
+        Kp = cur.shape[-1]
+        acts = [cur]
+        out = None
+        for i in range(n_layers):
+            W, b = params[2 * i], params[2 * i + 1]
+            N, K = W.shape
+            Np = pad16(N)
+            last = i == n_layers - 1
+            a = act if (not last or final_act) else 0
+            geom = (M, 1, 1, Kp, 1, 1, Np, 1)
+            if last:
+                out = torch.empty(M, N, device=dev, dtype=torch.float32)
+                tc_conv_down(geom, L.nhwc(cur, 1, 1, Kp), L.nhwc(out, 1, 1, N), packed(W, 0, Np, Kp), b, N, act=a, out_f32=1, valid=(N, K))
+            else:
+                y = _bf16(M, 1, 1, Np, device=dev)
+                tc_conv_down(geom, L.nhwc(cur, 1, 1, Kp), L.nhwc(y, 1, 1, Np), packed(W, 0, Np, Kp), b, N, act=a, valid=(N, K))
+                acts.append(y)
+                cur, Kp = y, Np
+        ctx.act, ctx.final_act, ctx.n_parts, ctx.params = act, final_act, n_parts, params
+        ctx.part_cols = [p.shape[1] for p in parts]
+        ctx.save_for_backward(out, *acts)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        act, params = ctx.act, ctx.params
+        out, *acts = ctx.saved_tensors
+        n_layers = len(params) // 2
+        M = out.shape[0]
+        dev = out.device
+        g = _f32c(g)
+        if ctx.final_act and act:
+            g = act_bwd(g, out, act)
+        N_last = out.shape[1]
+        dy = tc_to_bf16(L.nhwc(g, 1, 1, N_last), M, 1, 1, N_last, dev, Cpad=pad16(N_last))
+        gparts = [None] * ctx.n_parts
+        for i in reversed(range(n_layers)):
+            W, b = params[2 * i], params[2 * i + 1]
+            N, K = W.shape
+            x = acts[i]
+            Kp, Np = x.shape[-1], dy.shape[-1]
+            geom = (M, 1, 1, Kp, 1, 1, Np, 1)
+            tc_conv_wgrad(geom, L.nhwc(x, 1, 1, Kp), L.nhwc(dy, 1, 1, Np), L.ptr(grad_buf(W)), K, 1, N, K)
+            tc_colsum(dy.view(M, Np), N, grad_buf(b))
+            if i > 0:
+                dx = _bf16(M, 1, 1, Kp, device=dev)
+                tc_conv_up(geom, L.nhwc(dx, 1, 1, Kp), L.nhwc(dy, 1, 1, Np), packed(W, 1, Np, Kp), None, K,
+                           mask=L.nhwc(x, 1, 1, Kp) if act else None, mask_mode=act, valid=(N, K))
+                dy = dx
+            elif any(ctx.needs_input_grad[3:3 + ctx.n_parts]):
+                gx = torch.empty(M, K, device=dev, dtype=torch.float32)
+                tc_conv_up(geom, L.nhwc(gx, 1, 1, K), L.nhwc(dy, 1, 1, Np), packed(W, 1, Np, Kp), None, K, out_f32=1, valid=(N, K))
+                col = 0
+                for j, kp in enumerate(ctx.part_cols):
+                    if ctx.needs_input_grad[3 + j]:
+                        gparts[j] = gx[:, col:col + kp].contiguous() if ctx.n_parts > 1 else gx
+                    col += kp
+        return (None, None, None, *gparts, *([None] * len(params)))
+
+
+def mlp(act, final_act, n_parts, *args):
+    """MLP stack on the tensor cores in bf16 mode (large row counts), on the exact fp32 CUDA-core kernels otherwise."""
+    rows = args[0].shape[0]
+    fn = MlpTCFn if (bf16_mode() and rows >= 1024 and n_parts <= 2) else MlpFn
+    return fn.apply(act, final_act, n_parts, *args)
+
+
 class ConvEncoderTCFn(Function):
     """ConvEncoderFn on tensor cores: NCHW fp32 image -> bf16 parity-planar (8 ch) -> plane conv stack (parity-planar
     bf16 intermediates, each consumed with stride 2 by the next layer) -> fp32 [N, C*h*w] embedding in (C,H,W) order.

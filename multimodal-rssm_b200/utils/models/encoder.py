@@ -230,7 +230,7 @@ class SymbolicEncoder(_EncoderBase):
         self.modules = [self.fc1, self.fc2, self.fc3]
 
     def forward(self, observation):
-        return ops.MlpFn.apply(act_code(self.activation_function), True, 1, observation,
+        return ops.mlp(act_code(self.activation_function), True, 1, observation,
                                self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
                                self.fc3.weight, self.fc3.bias)
 
@@ -259,7 +259,7 @@ class _ConvEncoder(_EncoderBase):
         if hidden.shape[1] != 1024:
             raise ValueError(f"conv stack produced {hidden.shape[1]} features, the reference reshapes to 1024")
         if self.embedding_size != 1024:
-            hidden = ops.MlpFn.apply(act_code(self.activation_function), True, 1, hidden, self.fc.weight, self.fc.bias)
+            hidden = ops.mlp(act_code(self.activation_function), True, 1, hidden, self.fc.weight, self.fc.bias)
         return hidden
 
 

@@ -54,7 +54,7 @@ class DenseDecoder(ObservationModel_base):
 
     def forward(self, h_t, s_t):
         T, B = h_t.shape[:2]
-        y = ops.MlpFn.apply(act_code(self.activation_function), False, 2, h_t.reshape(T * B, -1), s_t.reshape(T * B, -1),
+        y = ops.mlp(act_code(self.activation_function), False, 2, h_t.reshape(T * B, -1), s_t.reshape(T * B, -1),
                             self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
                             self.fc3.weight, self.fc3.bias)
         return {"loc": y.reshape(T, B, -1), "scale": 1.0}

@@ -378,3 +378,30 @@ def _ref_masked_down(large, w, y):
     import torch.nn.functional as F
     d = F.conv2d(large.permute(0, 3, 1, 2), w, None, stride=2).permute(0, 2, 3, 1)
     return d * (y > 0)
+
+
+@pytest.mark.parametrize("shape", [((3,), (128, 128, 128), True, 2), ((200, 30), (128, 128, 3), False, 2), ((1024,), (512,), True, 1)])
+def test_mlp_tensor_core_matches_exact_kernels(shape):
+    """MlpTCFn (bf16 tcgen05 GEMMs per Linear) against MlpFn (exact fp32 CUDA-core kernels): SymbolicEncoder, DenseDecoder and
+    the fc branch of the conv encoder — forward, input gradients, every weight / bias gradient."""
+    from mrssm_b200 import ops
+    in_dims, widths, final_act, act = shape
+    M = 3000
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    parts = [torch.randn(M, k, device=DEV, generator=gen).requires_grad_(len(in_dims) > 1) for k in in_dims]
+    params, k = [], sum(in_dims)
+    for n in widths:
+        params += [torch.nn.Parameter(torch.randn(n, k, device=DEV, generator=gen) / k ** 0.5), torch.nn.Parameter(torch.randn(n, device=DEV, generator=gen) * 0.1)]
+        k = n
+    gout = torch.randn(M, widths[-1], device=DEV, generator=gen)
+    res = {}
+    for name, fn in (("exact", ops.MlpFn), ("tc", ops.MlpTCFn)):
+        for p in params + parts:
+            p.grad = None
+        y = fn.apply(act, final_act, len(parts), *parts, *params)
+        y.backward(gout)
+        res[name] = (y.detach().clone(), [p.grad.clone() for p in params], [p.grad.clone() for p in parts if p.requires_grad])
+    (y0, gw0, gx0), (y1, gw1, gx1) = res["exact"], res["tc"]
+    torch.testing.assert_close(y1, y0, rtol=2e-2, atol=2e-2)
+    for a, b in zip(gw1 + gx1, gw0 + gx0):        # (a ReLU whose pre-activation is ~0 may flip with bf16 operands: Frobenius, not max)
+        assert float((a - b).norm()) <= 2e-2 * float(b.norm()) + 1e-6, (float((a - b).norm()), float(b.norm()))
