@@ -54,10 +54,13 @@ def peaks():
 # ---------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port on the host cores
 # ---------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(T, fusion, sample_B=16, steps=3, warmup=1):
+def cpu_oracle_rate(T, fusion, sample_B=16, steps=3, warmup=1, model=None):
     from oracle import mrssm_oracle as O
     torch.set_num_threads(os.cpu_count())
-    oc = O.OracleConfig(fusion=fusion)
+    m = model or MODELS[3]
+    names = (m["image_name"], "pose_quat_v2")
+    oc = O.OracleConfig(fusion=fusion, belief_size=m["belief"], hidden_size=m["hidden"], state_size=m["state"], names_enc=names, names_rec=names,
+                        observation_shapes={m["image_name"]: [3, m["image"], m["image"]], "pose_quat_v2": [3]})
     P = O.make_params(oc, seed=0)
     opt = {}
     times = []
@@ -72,24 +75,26 @@ def cpu_oracle_rate(T, fusion, sample_B=16, steps=3, warmup=1):
     return sample_B * T / med, med, torch.get_num_threads()
 
 
-def reference_rate(T, fusion, sample_B=16, steps=3, warmup=1, in_process=False):
+def reference_rate(T, fusion, sample_B=16, steps=3, warmup=1, in_process=False, model=None):
     """The UNMODIFIED reference (oracle/_ref, staged by __graft_entry__.build) on the host cores: model.optimize(D) at
     B = sample_B.  Runs in its own process unless in_process (the product mirrors the names `algos` / `utils`).
     -> (rate, seconds per step, cores, kind); falls back to the oracle port when the reference is not staged."""
     from oracle import ref_arm
+    m = model or MODELS[3]
     if ref_arm.available():
         try:
             if in_process:
-                r = ref_arm.time_train(sample_B, T, fusion, steps, warmup, "cpu")
+                r = ref_arm.time_train(sample_B, T, fusion, steps, warmup, "cpu", m["image"], m["belief"], m["state"], m["hidden"])
             else:
                 out = subprocess.run([sys.executable, "-m", "oracle.ref_arm", "train", "--batch", str(sample_B), "--chunk", str(T),
-                                      "--steps", str(steps), "--warmup", str(warmup), "--fusion", fusion], cwd=ROOT,
+                                      "--steps", str(steps), "--warmup", str(warmup), "--fusion", fusion, "--image", str(m["image"]),
+                                      "--belief", str(m["belief"]), "--state", str(m["state"])], cwd=ROOT,
                                      capture_output=True, text=True, timeout=900)
                 r = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
             return r["seq_steps_per_s"], r["ms_per_step"] * 1e-3, r["cores"], "reference"
         except Exception as e:                                   # pragma: no cover
             print(f"bench: reference arm failed ({e!r}); timing the oracle port instead", file=sys.stderr)
-    rate, med, cores = cpu_oracle_rate(T, fusion, sample_B=sample_B, steps=steps, warmup=warmup)
+    rate, med, cores = cpu_oracle_rate(T, fusion, sample_B=sample_B, steps=steps, warmup=warmup, model=m)
     return rate, med, cores, "port"
 
 
@@ -110,10 +115,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rate, med, cores, kind = reference_rate(args.chunk, args.fusion, sample_B=16, steps=max(1, min(args.steps, 5)),
-                                            warmup=max(1, min(args.warmup, 1)), in_process=True)
+    sb = 16 if args.config == 3 else 4
+    rate, med, cores, kind = reference_rate(args.chunk, args.fusion, sample_B=sb, steps=max(1, min(args.steps, 5 if args.config == 3 else 2)),
+                                            warmup=max(1, min(args.warmup, 1)), in_process=True, model=model_of(args))
     what = "unmodified reference model.optimize(D)" if kind == "reference" else "fp32 oracle port of the reference step"
-    sample = f"B=16 of the B={args.batch} sequences, T={args.chunk}, full train step, {what}, fp32, {cores} threads"
+    sample = f"B={sb} of the B={args.batch} sequences, T={args.chunk}, full train step, {what}, fp32, {cores} threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
@@ -125,11 +131,33 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# BASELINE.json configs: 3 = the headline (full ELBO train step, D = H = 200, S = 30, 64x64 image + 3-d vector, B = 1024 x T = 50
+# per GPU); 5 = the scaled model (D = H = 1024, S = 64, 128x128 image; B = 2048 x T = 64 GLOBAL over 8 GPUs = 256 per GPU —
+# 129 024 frames of 128x128 activations do not fit one GPU's 180 GB)
+MODELS = {3: dict(belief=200, state=30, hidden=200, image=64, image_name="image_horizon", batch=1024, chunk=50),
+          5: dict(belief=1024, state=64, hidden=1024, image=128, image_name="image_horizon_128", batch=256, chunk=64)}
+
+
+def model_of(args):
+    return MODELS[args.config]
+
+
+def build_cfg(args, device, batch=None):
+    from mrssm_b200.config import hot_path_config
+    m = model_of(args)
+    cfg = hot_path_config(fusion=args.fusion, batch_size=batch or args.batch, chunk_size=args.chunk, device=device,
+                          belief_size=m["belief"], state_size=m["state"], hidden_size=m["hidden"], image_name=m["image_name"],
+                          image_size=m["image"])
+    cfg.train.use_amp = args.mode == "bf16"
+    return cfg
+
+
 def workload_config(args, world):
-    return {"workload": f"mrssm_{args.fusion.lower()}_train_step_B{args.batch}_T{args.chunk}_per_gpu",
-            "fusion": args.fusion, "per_gpu_batch": args.batch, "chunk_size": args.chunk,
-            "global_batch": args.batch * world, "belief": 200, "state": 30, "hidden": 200,
-            "modalities": "image_horizon[3,64,64]+pose_quat_v2[3]", "mode": args.mode,
+    m = model_of(args)
+    return {"workload": f"mrssm_{args.fusion.lower()}_train_step_B{args.batch}_T{args.chunk}_per_gpu" + ("" if args.config == 3 else f"_config{args.config}"),
+            "baseline_config": args.config, "fusion": args.fusion, "per_gpu_batch": args.batch, "chunk_size": args.chunk,
+            "global_batch": args.batch * world, "belief": m["belief"], "state": m["state"], "hidden": m["hidden"],
+            "modalities": f"{m['image_name']}[3,{m['image']},{m['image']}]+pose_quat_v2[3]", "mode": args.mode,
             "parallelism": f"dp{world}", "l2_policy": "inputs_exceed_l2"}
 
 
@@ -374,8 +402,7 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU path (use --impl reference)"
     torch.cuda.set_device(local)
     device = f"cuda:{local}"
-    cfg = hot_path_config(fusion=args.fusion, batch_size=args.batch, chunk_size=args.chunk, device=device)
-    cfg.train.use_amp = args.mode == "bf16"
+    cfg = build_cfg(args, device)
     torch.manual_seed(0)
     model = build_RSSM(cfg, torch.device(device))
     if world > 1:
@@ -407,8 +434,7 @@ def run_ours(args):
     strong = None
     if world > 1 and args.batch % world == 0:
         # secondary: strong scaling — the same GLOBAL batch (args.batch sequences) split over the ranks
-        cfg_s = hot_path_config(fusion=args.fusion, batch_size=args.batch // world, chunk_size=args.chunk, device=device)
-        cfg_s.train.use_amp = args.mode == "bf16"
+        cfg_s = build_cfg(args, device, batch=args.batch // world)
         torch.manual_seed(0)
         model_s = build_RSSM(cfg_s, torch.device(device))
         DataParallel(model_s)
@@ -439,12 +465,14 @@ def run_ours(args):
 
     cpu = same_box = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, med, cores, kind = reference_rate(args.chunk, args.fusion, sample_B=16, steps=3, warmup=1)
+        sb, st = (16, 3) if args.config == 3 else (4, 1)
+        rate, med, cores, kind = reference_rate(args.chunk, args.fusion, sample_B=sb, steps=st, warmup=1, model=model_of(args))
         what = "unmodified reference model.optimize(D)" if kind == "reference" else "fp32 oracle port"
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
-               "sample": f"B=16 sequences x T={args.chunk}, full train step, {what}, median of 3 steps",
+               "sample": f"B={sb} sequences x T={args.chunk}, full train step, {what}, median of {st} steps",
                "ms_per_step": med * 1e3}
-        same_box = rollout_configs(model, device)
+        if args.config == 3:
+            same_box = rollout_configs(model, device)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -470,12 +498,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="sequences per GPU")
-    ap.add_argument("--chunk", type=int, default=50)
+    ap.add_argument("--config", type=int, default=3, choices=sorted(MODELS), help="BASELINE.json config: 3 (headline) or 5 (scaled model)")
+    ap.add_argument("--batch", type=int, default=None, help="sequences per GPU (default: the config's)")
+    ap.add_argument("--chunk", type=int, default=None)
     ap.add_argument("--fusion", default="MoPoE", choices=["MoPoE", "PoE", "NN", "single"])
     ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.batch = args.batch or MODELS[args.config]["batch"]
+    args.chunk = args.chunk or MODELS[args.config]["chunk"]
     if args.impl == "reference":
         run_reference(args)
     else:
