@@ -1366,6 +1366,8 @@ struct WgP {
     int NG, gpp, n_cpass, n_mhalf;
     int NA, zero_bytes, mergedS, mergedL, s2d_cq;
     int group;                  // one TMA box per tensor map (all chunk planes of the map, planes dense)
+    int mrep;                   // Cs <= 64: the small tile is loaded twice, the copy one row lower, so the 128 MMA rows are
+                                // [cs | cs of the next row tap of the same parity]: one MMA accumulates row taps kh and kh + 2
     int rep, Ntot;              // rep: the large tile is loaded once per COLUMN tap b with the box origin shifted by b pixels (plane
                                 // group = b), so one MMA of N = Ntot = nt * N covers the nt column taps of a row tap a; row taps stay
                                 // descriptor shifts of a * BX pixels (space-to-depth sources: N = 16 per tap otherwise)
@@ -1424,7 +1426,7 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
                 const int sa = acnt % P.NA;
                 mbar_wait_conv(tc::smem_u32(&a_empty[sa]), ((acnt / P.NA) & 1) ^ 1, lead, P.poll);
                 const uint32_t bar = tc::smem_u32(&a_full[sa]);
-                mbar_expect_tx_if(bar, (uint32_t)P.nS * (uint32_t)P.small_bytes + (uint32_t)P.nL * (uint32_t)P.large_bytes, lead);
+                mbar_expect_tx_if(bar, (uint32_t)(P.mrep ? 2 : 1) * (uint32_t)P.nS * (uint32_t)P.small_bytes + (uint32_t)P.nL * (uint32_t)P.large_bytes, lead);
                 const int ig = tile / P.n_bands, band = tile - ig * P.n_bands;
                 const uint32_t dst = smem0 + (uint32_t)sa * (uint32_t)P.stage_bytes;
                 if (P.group) {
@@ -1432,6 +1434,7 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
                     const int cy = band * P.TH, ci = ig * P.BI;
                     const uint32_t dl = dst + (uint32_t)P.offL, map_bytes = (uint32_t)P.cpl * (uint32_t)P.PS_l;
                     tma_load_4d_if(dst, &mS, 0, cy, ci, mhalf * 16, bar, lead);
+                    if (P.mrep) tma_load_4d_if(dst + (uint32_t)P.nS * (uint32_t)P.PS_s, &mS, 0, cy - 1, ci, mhalf * 16, bar, lead);   // one row lower
                     if (P.rep) {
                         for (int mi = 0; mi < P.nt; ++mi) tma_load_4d_if(dl + (uint32_t)mi * map_bytes, &mL0, 2 * mi, cy, ci, 0, bar, lead);
                     } else {
@@ -1440,6 +1443,21 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
                             tma_load_4d_if(dl + map_bytes, &mL1, 0, cy, ci, 0, bar, lead);
                             tma_load_4d_if(dl + 2 * map_bytes, &mL2, 0, cy, ci, 0, bar, lead);
                             tma_load_4d_if(dl + 3 * map_bytes, &mL3, 0, cy, ci, 0, bar, lead);
+                        }
+                    }
+                    if (P.NA == 1 && tile + (int)gridDim.x < n_tiles) {
+                        // single stage: the next tile's boxes go to L2 now, its loads (after this tile's MMAs) then hit L2
+                        const int nx = tile + gridDim.x, nig = nx / P.n_bands, ny = (nx - nig * P.n_bands) * P.TH, ni = nig * P.BI;
+                        tma_prefetch_4d_if(&mS, 0, ny, ni, mhalf * 16, lead);
+                        if (P.rep) {
+                            for (int mi = 0; mi < P.nt; ++mi) tma_prefetch_4d_if(&mL0, 2 * mi, ny, ni, 0, lead);
+                        } else {
+                            tma_prefetch_4d_if(&mL0, 0, ny, ni, 0, lead);
+                            if (P.nL > P.cpl) {
+                                tma_prefetch_4d_if(&mL1, 0, ny, ni, 0, lead);
+                                tma_prefetch_4d_if(&mL2, 0, ny, ni, 0, lead);
+                                tma_prefetch_4d_if(&mL3, 0, ny, ni, 0, lead);
+                            }
                         }
                     }
                     ++acnt;
@@ -1504,7 +1522,8 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
                     continue;
                 }
                 for (int gi = 0; gi < ng; ++gi) {
-                    const int g = g0 + gi, kh = g / P.nt, b = g - kh * P.nt;      // space-to-depth source: kh is the row tap a
+                    const int g = g0 + gi, gk = g / P.nt, b = g - gk * P.nt;      // space-to-depth source: kh is the row tap a
+                    const int kh = P.mrep ? 4 * (gk >> 1) + (gk & 1) : gk;        // stacked: base taps 0, 1, 4, 5, ..
                     const uint32_t boff = P.s2d_cq ? (uint32_t)(kh * P.BX + b) * 16u
                                                    : (uint32_t)((kh & 1) * 2 * P.cpl) * (uint32_t)P.PS_l + (uint32_t)((kh >> 1) * P.BX + b) * 16u;
                     uint32_t a_lo = a0, b_lo = (((sL + boff) >> 4) & 0x3FFFu) | lbo;
@@ -1601,10 +1620,16 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
         }
         tc::mbar_wait(tc::smem_u32(&acc_full), 0);
         tc::tc_fence_after();
-        const int cs = mhalf * 128 + q * 32 + lane;
+        int cs = mhalf * 128 + q * 32 + lane;
+        int kh_add = 0;
+        if (P.mrep) {               // rows 64..127: the copy one row lower = the row tap two further on
+            kh_add = cs >= 64 ? 2 : 0;
+            cs &= 63;
+        }
         const float oscale = P.scale_ptr ? __ldg(P.scale_ptr) * P.scale_mul : 1.f;
         for (int gi = 0; gi < ng; ++gi) {
-            const int g = g0 + gi, kh = g / P.nt, b = g - kh * P.nt;
+            const int g = g0 + gi, gk = g / P.nt, b = g - gk * P.nt;
+            const int kh = (P.mrep ? 4 * (gk >> 1) + (gk & 1) : gk) + kh_add;
             for (int c0 = 0; c0 < P.N; c0 += 16) {
                 float v[16];
                 tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(gi * P.N + c0), v);
@@ -1625,7 +1650,7 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
                         cl = c - px * P.Clp;
                         kh2 = kh;
                         kw = 2 * b + px;
-                        ok = true;
+                        ok = kh < P.ksz;
                     }
                     if (ok && cl < P.cl_valid && kw < P.ksz) atomicAdd(P.dw + cs * P.w_ss + cl * P.w_sl + kh2 * P.ksz + kw, v[e] * oscale);
                 }
@@ -1654,19 +1679,19 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
     P.nL = P.s2d_cq ? P.cpl : 4 * P.cpl;
     P.n_mhalf = (P.Csp + 127) / 128;
     P.nS = std::min(16, P.Csp / 8);
-    P.NG = P.s2d_cq ? nt * nt : k * nt;
     P.rep = (P.s2d_cq && nt * P.N <= 256 && nt * nt * P.N <= 512 && !g_dbg[3]) ? 1 : 0;
     P.Ntot = nt * P.N;
     if (P.rep) P.nL = nt * P.cpl;
-    P.gpp = std::min(P.NG, 512 / P.N);
-    P.n_cpass = (P.NG + P.gpp - 1) / P.gpp;
-    P.gpp = (P.NG + P.n_cpass - 1) / P.n_cpass;
+    // row-tap stacking (mrep): with at most 64 small channels half of the 128 MMA rows would be empty; a second copy of the small
+    // tile, one row lower, fills them with the contributions of the row tap two further on (whole-image tiles, even kernels)
+    const bool can_mrep = !g_dbg[5] && !P.rep && !P.s2d_cq && P.nS == 8 && P.n_mhalf == 1 && k % 2 == 0;
     const int BXmin = a->Ws + nt - 1;
     // grouped TMA boxes (one per tensor map: every chunk plane of the map, planes back to back): both operands must be
     // x-contiguous planes.  The contraction runs over the pixels of a plane in steps of 16, so with nothing between the planes
     // the pixel count of a small plane must itself be a multiple of 16: the row pitch BX is widened until it is (the extra
     // columns are out-of-bounds zeros of the boxes).
     const bool can_group = !g_dbg[4] && view_groupable(a->small, false) && view_groupable(a->large, !P.s2d_cq);
+    bool want_mrep = can_mrep;
     auto plan = [&](int BI, int TH, bool banded, int NA) -> long long {
         const int BY = TH + nt - 1;
         const int SBY = banded ? TH : BY;
@@ -1683,6 +1708,8 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
             if (!grp) BX = BXmin;
         }
         P.BX = BX; P.group = grp ? 1 : 0;
+        P.mrep = (want_mrep && grp && !banded) ? 1 : 0;
+        const int scopies = P.mrep ? 2 : 1;
         const int maxshift = (nt - 1) * BX + nt - 1;
         const long long L = banded ? (long long)TH * BX : (long long)BI * BY * BX;
         const long long L16 = (L + 15) / 16 * 16;
@@ -1692,7 +1719,7 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
         if (grp) {
             P.PS_s = P.small_bytes;
             P.PS_l = P.large_bytes;
-            P.offL = P.nS * P.PS_s;
+            P.offL = scopies * P.nS * P.PS_s;
             // behind the last large plane: what the last K steps and the tap shifts read past it (stays zero: no box writes it)
             P.stage_bytes = (int)(((long long)P.offL + (long long)P.nL * P.PS_l + (maxshift + 16) * 16 + 1023) / 1024 * 1024);
         } else {
@@ -1710,8 +1737,22 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
     const long long avail = SMEM_TOTAL;
     const int Hs = a->Hs;
     bool done = false;
+    // row-tap stacking doubles the small tile: when that only fits single-buffered it is still the better plan (fewer MMAs and
+    // TMEM passes; the next tile is pulled into L2 while this one computes) — otherwise plan without it
+    if (can_mrep) {
+        if (plan(1, Hs, false, 2) <= avail && P.mrep) {
+            // fits double-buffered: the general search below keeps it
+        } else if (2 * ((k + 3) / 4) * nt * P.N <= 512 && plan(1, Hs, false, 1) <= avail && P.mrep) {
+            // (only when every tap group then fits one TMEM pass: measured E2 1.57 -> 1.30 ms, but D3 — still two passes,
+            // each with its tile load exposed — 3.53 -> 3.67 ms)
+            P.n_bands = 1;
+            done = true;
+        } else {
+            want_mrep = false;
+        }
+    }
     // whole images, double buffered, as many images per tile as fit (capped so a tile stays a few thousand pixels)
-    if (plan(1, Hs, false, 2) <= avail) {
+    if (!done && plan(1, Hs, false, 2) <= avail) {
         int BI = 1;
         while (BI < std::min(a->n_img, 256) && (long long)(BI + 1) * (Hs + nt - 1) * BXmin <= 4096 && plan(BI + 1, Hs, false, 2) <= avail) ++BI;
         plan(BI, Hs, false, 2);
@@ -1727,6 +1768,11 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
         plan(1, TH, true, 2);
     }
     MRSSM_CHECK(P.PS_s / 16 < 16384 && P.PS_l / 16 < 16384, "plane wgrad: plane stride too large");
+    // tap groups: (kh, kw / 2) — with row-tap stacking only the base taps kh = 4 j + parity (each MMA also carries kh + 2)
+    P.NG = P.s2d_cq ? nt * nt : (P.mrep ? 2 * ((k + 3) / 4) * nt : k * nt);
+    P.gpp = std::min(P.NG, 512 / P.N);
+    P.n_cpass = (P.NG + P.gpp - 1) / P.gpp;
+    P.gpp = (P.NG + P.n_cpass - 1) / P.n_cpass;
     P.n_groups = (a->n_img + P.BI - 1) / P.BI;
     smem_bytes = (size_t)P.zero_bytes + 1024;
     const int n_tiles = P.n_groups * P.n_bands;
@@ -2092,9 +2138,9 @@ extern "C" int mrssm_pl_describe(const mrssm_pl_conv_args* a, int32_t op, char* 
         if (int rc = plan_wgrad(a, P, smem, splits)) return rc;
         snprintf(buf, buflen,
                  "wgrad BI=%d bands=%d TH=%d BX=%d BY=%d nS=%d nL=%d PS_s=%d PS_l=%d stage=%d NA=%d ksteps/tile=%d N=%d groups=%d gpp=%d cpass=%d mhalf=%d "
-                 "splits=%d smem=%zu tiles=%d rep=%d group=%d",
+                 "splits=%d smem=%zu tiles=%d rep=%d group=%d mrep=%d",
                  P.BI, P.n_bands, P.TH, P.BX, P.BY, P.nS, P.nL, P.PS_s, P.PS_l, P.stage_bytes, P.NA, P.nksteps, P.N, P.NG, P.gpp, P.n_cpass,
-                 P.n_mhalf, splits, smem, P.n_groups * P.n_bands, P.rep, P.group);
+                 P.n_mhalf, splits, smem, P.n_groups * P.n_bands, P.rep, P.group, P.mrep);
     } else {
         FwdP P;
         size_t smem;

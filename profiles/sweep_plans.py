@@ -16,7 +16,7 @@ import torch
 from mrssm_b200 import _lib as L, ops
 
 DEV = "cuda:0"
-for _k in range(4):          # bring-up switches of csrc/conv_plane.cu from the environment: MRSSM_PL_DBG0=1 ...
+for _k in range(8):          # bring-up switches of csrc/conv_plane.cu from the environment: MRSSM_PL_DBG0=1 ...
     if os.environ.get(f"MRSSM_PL_DBG{_k}"):
         L.call_host("mrssm_pl_set_debug", _k, int(os.environ[f"MRSSM_PL_DBG{_k}"]))
 # name: (op, Hl, Cl, Hs, Cs, k, mode)   mode: fwd (bias + ReLU + sign bits out) | dgrad (sign bits in) | s2d variants

@@ -238,6 +238,28 @@ def sim_wgrad(L, small, large, k, s2d_cq=0, Hl=None):
                         if par < 4 and kh < k and kw < k:
                             dW[:, cl, kh, kw] += D[:, c]
                 continue
+            if P.get("mrep"):
+                # row-tap stacking: a second copy of the small tile one row lower (box origin y - 1) fills MMA rows 64..127;
+                # an MMA at base tap kh = 4 j + parity then also accumulates tap kh + 2 there
+                assert nSp == 8 and not banded
+                s1 = np.zeros_like(sflat)
+                for q in range(nSp):
+                    s1[q * PS_s:q * PS_s + BI * SBY * BX] = _box(small, q * 8, 0, band * TH - 1, ig * BI, BX, SBY, BI)
+                Sm1 = np.stack([s1[q * PS_s:q * PS_s + K] for q in range(nSp)], 1).reshape(K, Csp)
+                A = np.concatenate([Sm, Sm1], axis=1)                       # [pixel][128 MMA rows]
+                for g in range(2 * ((k + 3) // 4) * nt):
+                    gk, b = g // nt, g % nt
+                    kh = 4 * (gk >> 1) + (gk & 1)
+                    plane0, shift = (kh & 1) * 2 * cpl, (kh >> 1) * BX + b
+                    Bm = Lg.take(plane0, 2 * cpl, shift, K).reshape(K, 2 * Clp)
+                    D = A.T @ Bm
+                    for half in range(2):
+                        khh = kh + 2 * half
+                        for px in range(2):
+                            kw = 2 * b + px
+                            if khh < k and kw < k:
+                                dW[:, :, khh, kw] += D[half * Csp:(half + 1) * Csp, px * Clp:(px + 1) * Clp]
+                continue
             for g in range(k * nt):
                 kh, b = g // nt, g % nt
                 plane0, shift = (kh & 1) * 2 * cpl, (kh >> 1) * BX + b

@@ -10,7 +10,9 @@ from tests import plane_sim as S
 
 # (n_img, Hl, Cl, Hs, Cs, ksz): small-channel versions of every spatial geometry on the path
 DOWN = [(3, 64, 3, 31, 16, 4), (5, 31, 16, 14, 16, 4), (7, 14, 16, 6, 32, 4), (20, 6, 16, 2, 16, 4),
-        (2, 64, 3, 30, 16, 6), (3, 30, 16, 13, 16, 6), (5, 13, 16, 5, 32, 5), (1, 128, 3, 63, 16, 4)]
+        (2, 64, 3, 30, 16, 6), (3, 30, 16, 13, 16, 6), (5, 13, 16, 5, 32, 5), (1, 128, 3, 63, 16, 4),
+        # 64 small channels: the weight gradient stacks two row taps per MMA (mrep)
+        (3, 30, 16, 13, 64, 6), (5, 31, 16, 14, 64, 4), (7, 14, 8, 6, 64, 4)]
 UP = [(2, 64, 3, 30, 16, 6), (3, 30, 8, 13, 16, 6), (5, 13, 16, 5, 32, 5), (5, 31, 8, 14, 16, 4),
       (7, 14, 16, 6, 32, 4), (20, 6, 8, 2, 16, 4), (1, 128, 3, 62, 16, 6)]
 
