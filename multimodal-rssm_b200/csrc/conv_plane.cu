@@ -1366,6 +1366,9 @@ struct WgP {
     int NG, gpp, n_cpass, n_mhalf;
     int NA, zero_bytes, mergedS, mergedL, s2d_cq;
     int group;                  // one TMA box per tensor map (all chunk planes of the map, planes dense)
+    int psplit;                 // the tap groups of even / odd kh read disjoint large planes (row parity): grid.y passes are split
+                                // by row parity and each CTA loads only its parity's half of the large tile
+    int nL_cta;                 // large planes a CTA loads (nL, or half of it with psplit)
     int mrep;                   // Cs <= 64: the small tile is loaded twice, the copy one row lower, so the 128 MMA rows are
                                 // [cs | cs of the next row tap of the same parity]: one MMA accumulates row taps kh and kh + 2
     int rep, Ntot;              // rep: the large tile is loaded once per COLUMN tap b with the box origin shifted by b pixels (plane
@@ -1395,16 +1398,20 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_al = smem_raw + (smem0 - tc::smem_u32(smem_raw));
-    const int n_tiles = P.n_groups * P.n_bands;
     const int cpass = blockIdx.y % P.n_cpass, mhalf = blockIdx.y / P.n_cpass;
-    const int g0 = cpass * P.gpp, ng = min(P.gpp, P.NG - g0);
+    // tap groups of this CTA: [g0, g0 + ng) of all groups, or — row-parity split — of the groups of row parity `par`
+    const int par = P.psplit ? (cpass & 1) : 0, sub = P.psplit ? (cpass >> 1) : cpass;
+    const int n_kh_par = P.mrep ? (P.ksz - par + 3) / 4 : (P.ksz - par + 1) / 2;        // kh = par, par + 2 (or + 4), .. < ksz
+    const int NGc = P.psplit ? n_kh_par * P.nt : P.NG;
+    const int g0 = sub * P.gpp, ng = max(0, min(P.gpp, NGc - g0));
+    const int n_tiles = ng > 0 ? P.n_groups * P.n_bands : 0;       // (a pass without groups — odd kernels, odd parity — has no work)
 
     // zero the operand stages once: pixels the TMA boxes never write (row tails, M/K round-up) must read as 0
     for (int i = tid * 16; i < P.zero_bytes; i += NTHREADS * 16) *reinterpret_cast<uint4*>(smem_al + i) = make_uint4(0, 0, 0, 0);
     tc::fence_proxy_async();
     if (tid == 0) {
         // a stage is released by the MMA commit and, when this CTA also sums the bias gradient, by the summing warps
-        const bool do_sum = P.db_from != 0 && cpass == 0 && (P.db_from == 1 || mhalf == 0);
+        const bool do_sum = P.db_from != 0 && sub == 0 && (P.db_from == 1 ? par == 0 : mhalf == 0);
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(tc::smem_u32(&a_full[s]), 1);
             tc::mbar_init(tc::smem_u32(&a_empty[s]), do_sum ? 1 + WG_SUM_WARPS : 1);
@@ -1426,7 +1433,7 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
                 const int sa = acnt % P.NA;
                 mbar_wait_conv(tc::smem_u32(&a_empty[sa]), ((acnt / P.NA) & 1) ^ 1, lead, P.poll);
                 const uint32_t bar = tc::smem_u32(&a_full[sa]);
-                mbar_expect_tx_if(bar, (uint32_t)(P.mrep ? 2 : 1) * (uint32_t)P.nS * (uint32_t)P.small_bytes + (uint32_t)P.nL * (uint32_t)P.large_bytes, lead);
+                mbar_expect_tx_if(bar, (uint32_t)(P.mrep ? 2 : 1) * (uint32_t)P.nS * (uint32_t)P.small_bytes + (uint32_t)P.nL_cta * (uint32_t)P.large_bytes, lead);
                 const int ig = tile / P.n_bands, band = tile - ig * P.n_bands;
                 const uint32_t dst = smem0 + (uint32_t)sa * (uint32_t)P.stage_bytes;
                 if (P.group) {
@@ -1437,6 +1444,9 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
                     if (P.mrep) tma_load_4d_if(dst + (uint32_t)P.nS * (uint32_t)P.PS_s, &mS, 0, cy - 1, ci, mhalf * 16, bar, lead);   // one row lower
                     if (P.rep) {
                         for (int mi = 0; mi < P.nt; ++mi) tma_load_4d_if(dl + (uint32_t)mi * map_bytes, &mL0, 2 * mi, cy, ci, 0, bar, lead);
+                    } else if (P.psplit) {          // the two column-parity maps of this CTA's row parity
+                        tma_load_4d_if(dl, par ? &mL2 : &mL0, 0, cy, ci, 0, bar, lead);
+                        tma_load_4d_if(dl + map_bytes, par ? &mL3 : &mL1, 0, cy, ci, 0, bar, lead);
                     } else {
                         tma_load_4d_if(dl, &mL0, 0, cy, ci, 0, bar, lead);
                         if (P.nL > P.cpl) {
@@ -1451,6 +1461,9 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
                         tma_prefetch_4d_if(&mS, 0, ny, ni, mhalf * 16, lead);
                         if (P.rep) {
                             for (int mi = 0; mi < P.nt; ++mi) tma_prefetch_4d_if(&mL0, 2 * mi, ny, ni, 0, lead);
+                        } else if (P.psplit) {
+                            tma_prefetch_4d_if(par ? &mL2 : &mL0, 0, ny, ni, 0, lead);
+                            tma_prefetch_4d_if(par ? &mL3 : &mL1, 0, ny, ni, 0, lead);
                         } else {
                             tma_prefetch_4d_if(&mL0, 0, ny, ni, 0, lead);
                             if (P.nL > P.cpl) {
@@ -1523,9 +1536,12 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
                 }
                 for (int gi = 0; gi < ng; ++gi) {
                     const int g = g0 + gi, gk = g / P.nt, b = g - gk * P.nt;      // space-to-depth source: kh is the row tap a
-                    const int kh = P.mrep ? 4 * (gk >> 1) + (gk & 1) : gk;        // stacked: base taps 0, 1, 4, 5, ..
+                    int kh;
+                    if (P.psplit) kh = par + (P.mrep ? 4 : 2) * gk;               // the taps of this CTA's row parity
+                    else kh = P.mrep ? 4 * (gk >> 1) + (gk & 1) : gk;             // stacked: base taps 0, 1, 4, 5, ..
+                    const uint32_t prow = P.psplit ? 0u : (uint32_t)((kh & 1) * 2 * P.cpl);      // split: only this parity's planes are loaded
                     const uint32_t boff = P.s2d_cq ? (uint32_t)(kh * P.BX + b) * 16u
-                                                   : (uint32_t)((kh & 1) * 2 * P.cpl) * (uint32_t)P.PS_l + (uint32_t)((kh >> 1) * P.BX + b) * 16u;
+                                                   : prow * (uint32_t)P.PS_l + (uint32_t)((kh >> 1) * P.BX + b) * 16u;
                     uint32_t a_lo = a0, b_lo = (((sL + boff) >> 4) & 0x3FFFu) | lbo;
                     const uint32_t d = tmem_base + (uint32_t)(gi * P.N);
                     umma_bf16_lohi_if(d, a_lo, s_hi, b_lo, l_hi, idesc, accum, lead);
@@ -1544,7 +1560,7 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
         __syncwarp();
     } else if (warp >= 4) {
         const int q = warp - 4;
-        if (P.db_from != 0 && cpass == 0 && (P.db_from == 1 || mhalf == 0)) {      // `large` is shared by the Cs halves: one of them sums it
+        if (P.db_from != 0 && sub == 0 && (P.db_from == 1 ? par == 0 : mhalf == 0)) {      // `large` is shared by the Cs halves: one of them sums it
             // ---- bias gradient: per-channel sums over the pixels of the gradient operand, read from the tile the TMA already
             // put in shared memory for the MMAs (planes [chunk][pixel][8 ch]: a warp sweeps one plane with 16-byte loads).
             // Chunk c of this CTA is summed by warp (c % 4) [nch >= 4] or by warps {c, c + nch, ..} [nch < 4].
@@ -1629,7 +1645,7 @@ plane_wgrad_kernel(const __grid_constant__ CUtensorMap mS, const __grid_constant
         const float oscale = P.scale_ptr ? __ldg(P.scale_ptr) * P.scale_mul : 1.f;
         for (int gi = 0; gi < ng; ++gi) {
             const int g = g0 + gi, gk = g / P.nt, b = g - gk * P.nt;
-            const int kh = (P.mrep ? 4 * (gk >> 1) + (gk & 1) : gk) + kh_add;
+            const int kh = (P.psplit ? par + (P.mrep ? 4 : 2) * gk : (P.mrep ? 4 * (gk >> 1) + (gk & 1) : gk)) + kh_add;
             for (int c0 = 0; c0 < P.N; c0 += 16) {
                 float v[16];
                 tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(gi * P.N + c0), v);
@@ -1691,7 +1707,8 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
     // the pixel count of a small plane must itself be a multiple of 16: the row pitch BX is widened until it is (the extra
     // columns are out-of-bounds zeros of the boxes).
     const bool can_group = !g_dbg[4] && view_groupable(a->small, false) && view_groupable(a->large, !P.s2d_cq);
-    bool want_mrep = can_mrep;
+    bool want_mrep = can_mrep, want_psplit = false;
+    const bool can_psplit = !g_dbg[6] && !P.rep && !P.s2d_cq;
     auto plan = [&](int BI, int TH, bool banded, int NA) -> long long {
         const int BY = TH + nt - 1;
         const int SBY = banded ? TH : BY;
@@ -1709,6 +1726,8 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
         }
         P.BX = BX; P.group = grp ? 1 : 0;
         P.mrep = (want_mrep && grp && !banded) ? 1 : 0;
+        P.psplit = (want_psplit && grp) ? 1 : 0;
+        P.nL_cta = P.psplit ? P.nL / 2 : P.nL;
         const int scopies = P.mrep ? 2 : 1;
         const int maxshift = (nt - 1) * BX + nt - 1;
         const long long L = banded ? (long long)TH * BX : (long long)BI * BY * BX;
@@ -1721,7 +1740,7 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
             P.PS_l = P.large_bytes;
             P.offL = scopies * P.nS * P.PS_s;
             // behind the last large plane: what the last K steps and the tap shifts read past it (stays zero: no box writes it)
-            P.stage_bytes = (int)(((long long)P.offL + (long long)P.nL * P.PS_l + (maxshift + 16) * 16 + 1023) / 1024 * 1024);
+            P.stage_bytes = (int)(((long long)P.offL + (long long)P.nL_cta * P.PS_l + (maxshift + 16) * 16 + 1023) / 1024 * 1024);
         } else {
             P.PS_s = (int)((L16 * 16 + 127) / 128 * 128);
             P.PS_l = (int)(((L16 + maxshift) * 16 + 127) / 128 * 128);
@@ -1739,7 +1758,23 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
     bool done = false;
     // row-tap stacking doubles the small tile: when that only fits single-buffered it is still the better plan (fewer MMAs and
     // TMEM passes; the next tile is pulled into L2 while this one computes) — otherwise plan without it
-    if (can_mrep) {
+    const int NG_plain = P.s2d_cq ? nt * nt : k * nt, NG_stack = 2 * ((k + 3) / 4) * nt;
+    if (can_mrep && can_psplit && NG_stack * P.N > 512 && (NG_stack / 2) * P.N <= 512) {
+        // stacked row taps AND the passes split by row parity: each parity's groups fit one TMEM pass and its CTA loads the
+        // doubled small tile plus only half of the large tile — double-buffered (D3: 3 passes of 18 groups -> 2 of 6)
+        want_psplit = true;
+        if (plan(1, Hs, false, 2) <= avail && P.mrep && P.psplit) {
+            // keep; the whole-image search below refines the image count
+        } else {
+            want_psplit = false;
+        }
+    }
+    if (!want_psplit && can_psplit && !(can_mrep && NG_stack * P.N <= 512) && NG_plain * P.N > 512) {
+        want_mrep = false;              // several passes anyway: split them by row parity (each loads half of the large tile)
+        want_psplit = true;
+        if (!(plan(1, Hs, false, 2) <= avail && P.psplit)) want_psplit = false, want_mrep = can_mrep;
+    }
+    if (can_mrep && !want_psplit) {
         if (plan(1, Hs, false, 2) <= avail && P.mrep) {
             // fits double-buffered: the general search below keeps it
         } else if (2 * ((k + 3) / 4) * nt * P.N <= 512 && plan(1, Hs, false, 1) <= avail && P.mrep) {
@@ -1770,9 +1805,17 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
     MRSSM_CHECK(P.PS_s / 16 < 16384 && P.PS_l / 16 < 16384, "plane wgrad: plane stride too large");
     // tap groups: (kh, kw / 2) — with row-tap stacking only the base taps kh = 4 j + parity (each MMA also carries kh + 2)
     P.NG = P.s2d_cq ? nt * nt : (P.mrep ? 2 * ((k + 3) / 4) * nt : k * nt);
-    P.gpp = std::min(P.NG, 512 / P.N);
-    P.n_cpass = (P.NG + P.gpp - 1) / P.gpp;
-    P.gpp = (P.NG + P.n_cpass - 1) / P.n_cpass;
+    if (P.psplit) {             // per row parity: kh = par, par + 2 (+ 4 stacked), ..; the even parity has the most taps
+        const int ng_par = (P.mrep ? (k + 3) / 4 : (k + 1) / 2) * nt;
+        P.gpp = std::min(ng_par, 512 / P.N);
+        const int n_sub = (ng_par + P.gpp - 1) / P.gpp;
+        P.gpp = (ng_par + n_sub - 1) / n_sub;
+        P.n_cpass = 2 * n_sub;
+    } else {
+        P.gpp = std::min(P.NG, 512 / P.N);
+        P.n_cpass = (P.NG + P.gpp - 1) / P.gpp;
+        P.gpp = (P.NG + P.n_cpass - 1) / P.n_cpass;
+    }
     P.n_groups = (a->n_img + P.BI - 1) / P.BI;
     smem_bytes = (size_t)P.zero_bytes + 1024;
     const int n_tiles = P.n_groups * P.n_bands;
@@ -1788,7 +1831,7 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
         if (P.db_from == 1) {
             P.db_nch = P.nS; P.db_npar = 1; P.db_valid = a->cs_valid; P.db_fold = 0;
         } else {
-            P.db_nch = P.cpl; P.db_npar = (P.s2d_cq || P.rep) ? 1 : 4; P.db_valid = a->cl_valid; P.db_fold = P.s2d_cq;
+            P.db_nch = P.cpl; P.db_npar = (P.s2d_cq || P.rep) ? 1 : (P.psplit ? 2 : 4); P.db_valid = a->cl_valid; P.db_fold = P.s2d_cq;
         }
         MRSSM_CHECK(P.db_nch == 1 || P.db_nch == 2 || P.db_nch == 4 || P.db_nch == 8 || P.db_nch == 16,
                     "plane wgrad: bias-gradient sums need 1, 2, 4, 8 or 16 channel chunks (got %d)", P.db_nch);
@@ -2138,9 +2181,9 @@ extern "C" int mrssm_pl_describe(const mrssm_pl_conv_args* a, int32_t op, char* 
         if (int rc = plan_wgrad(a, P, smem, splits)) return rc;
         snprintf(buf, buflen,
                  "wgrad BI=%d bands=%d TH=%d BX=%d BY=%d nS=%d nL=%d PS_s=%d PS_l=%d stage=%d NA=%d ksteps/tile=%d N=%d groups=%d gpp=%d cpass=%d mhalf=%d "
-                 "splits=%d smem=%zu tiles=%d rep=%d group=%d mrep=%d",
+                 "splits=%d smem=%zu tiles=%d rep=%d group=%d mrep=%d psplit=%d",
                  P.BI, P.n_bands, P.TH, P.BX, P.BY, P.nS, P.nL, P.PS_s, P.PS_l, P.stage_bytes, P.NA, P.nksteps, P.N, P.NG, P.gpp, P.n_cpass,
-                 P.n_mhalf, splits, smem, P.n_groups * P.n_bands, P.rep, P.group, P.mrep);
+                 P.n_mhalf, splits, smem, P.n_groups * P.n_bands, P.rep, P.group, P.mrep, P.psplit);
     } else {
         FwdP P;
         size_t smem;

@@ -1272,16 +1272,10 @@ class ConvEncoderTCFn(Function):
             geom, Cs, Cl, cq = geoms[i]
             N, Hl, Wl, Clp, Hs, Ws, Csp, k = geom
             xv = L.tv(acts[i], L.PLANAR, (Hl + 1) // 2, (Wl + 1) // 2, Clp) if cq else L.tv(acts[i], L.PARITY, Hl, Wl, Clp)
-            if i == n_layers - 1 and Hs * Ws <= 4 and not cq:
-                # tiny maps: the plane kernel's TMA boxes are a few pixels wide (3.1 ms at cfg 3); the NHWC implicit-GEMM
-                # weight-gradient kernel gathers whole channel runs instead (1.2 ms + two small layout copies)
-                xn = pl_copy(xv, N, Hl, Wl, Clp, L.NHWC, dev)[0]
-                gn = pl_import(L.nchw(gm, Hs, Ws, Cs), N, Hs, Ws, Cs, Csp, L.NHWC, dev)[0]
-                tc_conv_wgrad(geom, L.nhwc(xn, Hl, Wl, Clp), L.nhwc(gn, Hs, Ws, Csp), L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl)
-                del xn, gn
-                pl_colsum(gb[1], N, Hs, Ws, Csp, Cs, grad_buf(b))
-            else:       # weight and bias gradient in one kernel (the bias sums read the gradient tile from shared memory)
-                pl_conv_wgrad(geom, xv, gb[1], L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl, s2d_cq=cq, dbias=grad_buf(b), dbias_from=1)
+            # weight and bias gradient in one kernel (the bias sums read the gradient tile from shared memory); with grouped TMA
+            # boxes and the passes split by row parity the 2x2-map layer (E4) runs here as well (0.9 ms; round 1 sent it to the NHWC
+            # implicit-GEMM kernel: 1.2 ms + two layout copies)
+            pl_conv_wgrad(geom, xv, gb[1], L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl, s2d_cq=cq, dbias=grad_buf(b), dbias_from=1)
             if i > 0:
                 gx = new_act(N, Hl, Wl, Clp, L.PLANAR, dev)
                 pl_conv_up(geom, gx[1], gb[1], packed_pl(Wt, UP, Csp, Clp), None, Cl, Clp, bits_in=bits[i - 1], valid=(Cs, Cl))
