@@ -24,7 +24,7 @@ LAYERS = {
     "E1_fwd": ("down_s2d", 64, 3, 31, 32, 4, "fwd"), "E2_fwd": ("down", 31, 32, 14, 64, 4, "fwd"), "E3_fwd": ("down", 14, 64, 6, 128, 4, "fwd"),
     "E4_dgrad": ("up", 6, 128, 2, 256, 4, "dgrad"), "E3_dgrad": ("up", 14, 64, 6, 128, 4, "dgrad"), "E2_dgrad": ("up", 31, 32, 14, 64, 4, "dgrad"),
     "D2_fwd": ("up", 13, 64, 5, 128, 5, "fwd"), "D3_fwd": ("up", 30, 32, 13, 64, 6, "fwd"),
-    "D4_dgrad": ("down_s2d", 64, 3, 30, 32, 6, "dgrad"), "D3_dgrad": ("down", 30, 32, 13, 64, 6, "dgrad"), "D2_dgrad": ("down", 13, 64, 5, 128, 5, "dgrad_bf16mask"),
+    "D4_fwd": ("up", 64, 3, 30, 32, 6, "mse"), "D4_dgrad": ("down_s2d", 64, 3, 30, 32, 6, "dgrad"), "D3_dgrad": ("down", 30, 32, 13, 64, 6, "dgrad"), "D2_dgrad": ("down", 13, 64, 5, 128, 5, "dgrad_bf16mask"),
 }
 
 
@@ -60,6 +60,11 @@ def build(name, n):
     bias = torch.zeros(Cl, device=DEV)
     bits = ops.new_relu_bits(n, Hl, Hl, Clp, DEV)
     bits.fill_(0x5A)
+    if mode == "mse":        # last ConvTranspose2d with the fused reconstruction loss (fp32 NCHW target, bf16 space-to-depth residual)
+        target = torch.rand(n, Cl, Hl, Hl, device=DEV) - 0.5
+        resid = ops.new_act(n, (Hl + 1) // 2, (Hl + 1) // 2, 16, L.PLANAR, DEV)
+        total = torch.zeros(1, device=DEV)
+        return lambda: ops.pl_conv_up_mse(gp, resid[1], src[1], wp, bias, Cl, Clp, target, L.nchw(target, Hl, Hl, Cl), total, 1.0 / n)
     out = ops.new_act(n, Hl, Hl, Clp, L.PLANAR, DEV)
     if mode == "fwd":
         return lambda: ops.pl_conv_up(gp, out[1], src[1], wp, bias, Cl, Clp, act=ops.RELU, bits_out=bits)
