@@ -172,6 +172,11 @@ typedef struct mrssm_pl_conv_args {
      * bf16 activation it stands for. */
     uint8_t* relu_bits_out;
     const uint8_t* relu_bits_in;
+    /* Fused reconstruction loss, target given as the bf16 SPACE-TO-DEPTH view of the image (the form mrssm_pl_import_s2d makes for
+     * the first encoder convolution — in training the decoder's target IS the encoder's input, base/algo.py:241,270-273) instead
+     * of mse_target: two 16-byte loads per position in the residual's own layout, 2 bytes per element instead of 4.  The target is
+     * then the image rounded to bf16. */
+    mrssm_tv mse_target_s2d;
 } mrssm_pl_conv_args;
 
 int mrssm_pl_conv_down(const mrssm_pl_conv_args* a, void* stream);

@@ -361,6 +361,8 @@ struct FwdP {
     float* mse_sum;
     float mse_scale;
     int mse_vec;                // target rows are x-contiguous and 8-byte aligned: float2 loads
+    int mse_on;                 // fused reconstruction loss (target: fp32 `mse_target` or the bf16 space-to-depth view `tgt`)
+    TV tgt;                     // bf16 space-to-depth target (the encoder's own imported image): two 16-byte loads per position
     // fast epilogue (bf16 output, act none / ReLU, every item inside one parity class): nc columns per item (16, 32 or 64)
     int fast, ncp, nc;
     int poll;                   // barrier polling of the converged warps (mbar_wait_conv)
@@ -455,9 +457,26 @@ __device__ __forceinline__ void epi_store8(const FwdP& P, const float* v, const 
 // NV is a template parameter so that every register-array index is static.
 template <int NV>
 __device__ __forceinline__ void mse_row(const FwdP& P, const float (&v)[32], const float* bias_s, int img, int y, int x, float& mse_acc) {
-    const float* tg = P.mse_target + img * P.out32.sI;
+    const float* tg = P.mse_target ? P.mse_target + img * P.out32.sI : nullptr;
     float* rc = P.out32.p ? (float*)P.out32.p + img * P.out32.sI : nullptr;
     float tv[4][NV];
+    if (P.tgt.p) {
+        // space-to-depth target: channel (parity class, c) of position (y, x) — the residual's own layout
+        const bf16* tp = (const bf16*)P.tgt.p + tv_pix(P.tgt, img, y, x);
+        const uint4 t0 = __ldg(reinterpret_cast<const uint4*>(tp)), t1 = __ldg(reinterpret_cast<const uint4*>(tp + P.tgt.sK));
+        float t16[16];
+        const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&t0);
+        const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&t1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 a = __bfloat1622float2(h0[e]), b = __bfloat1622float2(h1[e]);
+            t16[2 * e] = a.x; t16[2 * e + 1] = a.y; t16[8 + 2 * e] = b.x; t16[8 + 2 * e + 1] = b.y;
+        }
+#pragma unroll
+        for (int cls = 0; cls < 4; ++cls)
+#pragma unroll
+            for (int c = 0; c < NV; ++c) tv[cls][c] = t16[cls * NV + c];
+    } else
 #pragma unroll
     for (int py = 0; py < 2; ++py) {
         const int yy = 2 * y + py;
@@ -717,7 +736,7 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                     const int i0 = ig * P.BI, ni = min(P.BI, P.n_img - i0);
                     if (P.bits_img_bytes > 0) prefetch_range((const char*)P.bits_in, (long long)i0 * P.bits_img_bytes, (long long)(i0 + ni) * P.bits_img_bytes);
                     if (P.mask_img_bytes > 0) prefetch_range((const char*)P.mask.p, (long long)i0 * P.mask_img_bytes, (long long)(i0 + ni) * P.mask_img_bytes);
-                    if (P.tgt_img_bytes > 0) prefetch_range((const char*)P.mse_target, (long long)i0 * P.tgt_img_bytes, (long long)(i0 + ni) * P.tgt_img_bytes);
+                    if (P.tgt_img_bytes > 0) prefetch_range(P.tgt.p ? (const char*)P.tgt.p : (const char*)P.mse_target, (long long)i0 * P.tgt_img_bytes, (long long)(i0 + ni) * P.tgt_img_bytes);
                 }
                 ++acnt;
             };
@@ -869,7 +888,7 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         // Four warps share each TMEM lane quarter.  A pass is cut into items (128-row block, column part); the
         // warps of a quarter take items round-robin.
         const int e = warp - 4, q = e & 3, part = e >> 2;
-        const bool mse = NC == 0 && F32 && OP == OP_UP && P.mse_target != nullptr;       // fused reconstruction loss: whole rows per warp
+        const bool mse = NC == 0 && F32 && OP == OP_UP && P.mse_on;       // fused reconstruction loss: whole rows per warp
         // column parts per block: narrow outputs stay whole (the row decode is amortised over more columns)
         const int ncp = P.ncp;
         const int ncols = P.BN / ncp;
@@ -1201,20 +1220,26 @@ int plan_fwd(const mrssm_pl_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
     P.poll = g_dbg[0];
     P.scale_ptr = a->scale_ptr; P.scale_mul = a->scale_mul;
     P.mse_target = a->mse_target; P.mse_sum = a->mse_sum; P.mse_scale = a->mse_scale;
-    if (P.mse_target) {
+    P.tgt = cvt(a->mse_target_s2d);
+    if (P.tgt.p) P.mse_target = nullptr;
+    P.mse_on = (P.mse_target || P.tgt.p) ? 1 : 0;
+    if (P.mse_on) {
         MRSSM_CHECK(op == OP_UP && P.out_f32 && P.mse_sum && a->n_out_valid <= 4 && a->n_out_pad == 8 && a->large.ptr && !a->large.par,
                     "plane up: fused MSE needs out_f32, <= 4 channels (n_out_pad 8), a sum buffer and a linear space-to-depth residual view");
         P.out = cvt(a->large);
         P.mse_vec = a->out32.sW == 1 && (P.Wo & 1) == 0 && a->out32.sH % 2 == 0 && a->out32.sC % 2 == 0 && a->out32.sI % 2 == 0 &&
-                    ((uintptr_t)a->mse_target & 7) == 0;
-        const long long tb = 4 * a->out32.sI;
-        P.tgt_img_bytes = (!g_dbg[2] && tb > 0 && tb % 16 == 0 && ((uintptr_t)a->mse_target & 15) == 0 && tb <= (1 << 20)) ? tb : 0;
+                    a->mse_target && ((uintptr_t)a->mse_target & 7) == 0;
+        const long long tb = P.tgt.p ? 2 * P.tgt.sI : 4 * a->out32.sI;
+        const void* tbase = P.tgt.p ? P.tgt.p : (const void*)a->mse_target;
+        P.tgt_img_bytes = (!g_dbg[2] && tb > 0 && tb % 16 == 0 && ((uintptr_t)tbase & 15) == 0 && tb <= (1 << 20)) ? tb : 0;
+        MRSSM_CHECK(!P.tgt.p || (!P.tgt.par && P.tgt.sK % 8 == 0 && P.tgt.sW % 8 == 0 && P.tgt.sH % 8 == 0 && P.tgt.sI % 8 == 0 && ((uintptr_t)P.tgt.p & 15) == 0),
+                    "plane up: the space-to-depth loss target must be a linear view with 16-byte aligned chunks");
     }
     // epilogue shape: columns per item.  Fast path: bf16 output, act none / ReLU, ReLU (or no) act'-mask, and items that stay
     // inside one parity class; otherwise the generic epilogue (fp32 outputs, fused loss, ELU, odd widths).
     P.bits_out = a->relu_bits_out; P.bits_in = a->relu_bits_in;
     {
-        const bool mse_k = P.mse_target != nullptr;
+        const bool mse_k = P.mse_on != 0;
         int nc = 0;
         for (int c : {64, 32, 16}) {
             if (P.BN % c == 0 && (op == OP_DOWN || P.Cop % c == 0) && (c == 16 || P.BN / c <= 16)) {
@@ -1245,7 +1270,7 @@ int plan_fwd(const mrssm_pl_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
     auto vec_ok = [](const mrssm_tv& t) {
         return t.sW % 8 == 0 && t.sH % 8 == 0 && t.sI % 8 == 0 && t.sK % 8 == 0 && t.sP % 8 == 0 && ((uintptr_t)t.ptr & 15) == 0;
     };
-    MRSSM_CHECK(P.out_f32 ? (a->out32.ptr != nullptr || P.mse_target != nullptr) : vec_ok(out),
+    MRSSM_CHECK(P.out_f32 ? (a->out32.ptr != nullptr || P.mse_on) : vec_ok(out),
                 "plane conv: bf16 output view must keep 8-channel chunks 16-byte aligned");
     MRSSM_CHECK(!P.mask_mode || vec_ok(a->mask), "plane conv: mask view must keep 8-channel chunks 16-byte aligned");
     return 0;

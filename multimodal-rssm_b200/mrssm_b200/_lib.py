@@ -52,7 +52,7 @@ class PlConvArgs(C.Structure):
         ("large", TV), ("small", TV), ("mask", TV), ("out32", T4), ("wpacked", _vp), ("bias", _vp), ("dweight", _vp),
         ("w_ss", C.c_int64), ("w_sl", C.c_int64), ("scale_ptr", _vp), ("scale_mul", C.c_float),
         ("mse_target", _vp), ("mse_sum", _vp), ("mse_scale", C.c_float),
-        ("dbias", _vp), ("dbias_from", C.c_int32), ("relu_bits_out", _vp), ("relu_bits_in", _vp)]
+        ("dbias", _vp), ("dbias_from", C.c_int32), ("relu_bits_out", _vp), ("relu_bits_in", _vp), ("mse_target_s2d", TV)]
 
 
 class RolloutArgs(C.Structure):

@@ -952,12 +952,15 @@ def pl_conv_up(geom, out, small, wpacked, bias, n_out_valid, n_out_pad, act=0, m
 
 
 def pl_conv_up_mse(geom, resid, small, wpacked, bias, n_out_valid, n_out_pad, target, target_t4, sum_buf, factor, recon_t4=None,
-                   valid=None):
+                   valid=None, target_s2d=None):
     """Last ConvTranspose2d + reconstruction loss in one kernel: adds factor * sum((recon - target)^2) to sum_buf[0] and writes
-    the residual as bf16 in space-to-depth form into the view `resid`; recon_t4 (fp32, target's strides) is optional."""
+    the residual as bf16 in space-to-depth form into the view `resid`; recon_t4 (fp32, target's strides) is optional.
+    target_s2d: L.TV view of the target in bf16 space-to-depth form (pl_import_s2d) — read instead of the fp32 target."""
     out32 = L.T4(recon_t4.ptr if recon_t4 is not None else None, target_t4.sI, target_t4.sH, target_t4.sW, target_t4.sC)
     a = _pl_args(geom, large=resid, small=small, out32=out32, n_out_pad=n_out_pad, n_out_valid=n_out_valid, wpacked=L.ptr(wpacked),
                  bias=L.ptr(bias), mse=(target, sum_buf, factor))
+    if target_s2d is not None:
+        a.mse_target_s2d = target_s2d
     tag, work = _tc_work("mrssm_pl_conv_up", geom, valid or (geom[6], geom[3]))
     L.call("mrssm_pl_conv_up", C.byref(a), tag=tag, work=work)
 
@@ -1211,6 +1214,21 @@ def mlp(act, final_act, n_parts, *args):
     return fn.apply(act, final_act, n_parts, *args)
 
 
+# The bf16 space-to-depth form of the image the encoder just imported, keyed by the fp32 tensor it came from.  In a training step
+# the decoder's reconstruction target is the encoder's input (base/algo.py:241,270-273), so the fused loss kernel can read this
+# copy — half the bytes of the fp32 target, in the residual's own layout — instead.  One entry; a changed tensor never matches.
+_S2D = {}
+
+
+def remember_s2d(x, s2d):
+    _S2D.clear()
+    _S2D[(x.data_ptr(), tuple(x.shape), x._version)] = s2d
+
+
+def recall_s2d(target):
+    return _S2D.get((target.data_ptr(), tuple(target.shape), target._version))
+
+
 class ConvEncoderTCFn(Function):
     """ConvEncoderFn on tensor cores: NCHW fp32 image -> bf16 parity-planar (8 ch) -> plane conv stack (parity-planar
     bf16 intermediates, each consumed with stride 2 by the next layer) -> fp32 [N, C*h*w] embedding in (C,H,W) order.
@@ -1227,6 +1245,7 @@ class ConvEncoderTCFn(Function):
         cq0 = Cc if Cc <= 4 else 0
         if cq0:
             acts = [pl_import_s2d(L.nchw(x, H, W, Cc), N, H, W, Cc, dev)]
+            remember_s2d(x, acts[0][0])
             Clp = 16
         else:
             acts = [pl_import(L.nchw(x, H, W, Cc), N, H, W, Cc, pad8(Cc), L.PARITY, dev)]

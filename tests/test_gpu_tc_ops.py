@@ -319,6 +319,19 @@ def test_plane_up_fused_mse_matches_separate_ops(g):
         for par in range(4):
             sub = d[:, par >> 1::2, par & 1::2, :]
             torch.testing.assert_close(r[:, :sub.shape[1], :sub.shape[2], par * Cl:(par + 1) * Cl], sub, rtol=1e-2, atol=1e-2)
+    # target handed over as the bf16 space-to-depth import of the same image (what a training step does: the decoder's target
+    # is the encoder's input): the loss is taken against the image rounded to bf16
+    ts, tsv = ops.pl_import_s2d(L.nchw(target, Hl, Hl, Cl), n, Hl, Hl, Cl, DEV)
+    resid = ops.new_act(n, H2, H2, 16, "planar", DEV)
+    total = torch.zeros(1, device=DEV)
+    ops.pl_conv_up_mse(gp, resid[1], sb[1], wp, bias, Cl, Clp, target, L.nchw(target, Hl, Hl, Cl), total, 1.0 / n, target_s2d=tsv)
+    tb = _bf16_round(target)
+    torch.testing.assert_close(total[0], ((recon_ref - tb) ** 2).sum() / n, rtol=1e-4, atol=1e-4)
+    r = export_view(resid[0], "planar", n, H2, H2, 16)
+    d = (recon_ref - tb).permute(0, 2, 3, 1)
+    for par in range(4):
+        sub = d[:, par >> 1::2, par & 1::2, :]
+        torch.testing.assert_close(r[:, :sub.shape[1], :sub.shape[2], par * Cl:(par + 1) * Cl], sub, rtol=1e-2, atol=1e-2)
 
 
 def decode_relu_bits(bits, n, H, W, Cp):
