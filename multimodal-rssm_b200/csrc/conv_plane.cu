@@ -361,6 +361,7 @@ struct FwdP {
     float* mse_sum;
     float mse_scale;
     int mse_vec;                // target rows are x-contiguous and 8-byte aligned: float2 loads
+    int mse_lean;               // 3 channels, 32 accumulator columns: the lean fused-loss kernel (NC = -1)
     int mse_on;                 // fused reconstruction loss (target: fp32 `mse_target` or the bf16 space-to-depth view `tgt`)
     TV tgt;                     // bf16 space-to-depth target (the encoder's own imported image): two 16-byte loads per position
     // fast epilogue (bf16 output, act none / ReLU, every item inside one parity class): nc columns per item (16, 32 or 64)
@@ -455,11 +456,10 @@ __device__ __forceinline__ void epi_store8(const FwdP& P, const float* v, const 
 // Fused reconstruction loss for one output row of the last ConvTranspose2d (columns = 4 parity classes x 8, NV real
 // channels): residual vs target, sum of squares, optional reconstruction store, bf16 space-to-depth residual store.
 // NV is a template parameter so that every register-array index is static.
+// target values of the four parity classes of position (y, x): tv[class][channel] (issued before the accumulators are waited for)
 template <int NV>
-__device__ __forceinline__ void mse_row(const FwdP& P, const float (&v)[32], const float* bias_s, int img, int y, int x, float& mse_acc) {
+__device__ __forceinline__ void mse_load(const FwdP& P, int img, int y, int x, float (&tv)[4][NV]) {
     const float* tg = P.mse_target ? P.mse_target + img * P.out32.sI : nullptr;
-    float* rc = P.out32.p ? (float*)P.out32.p + img * P.out32.sI : nullptr;
-    float tv[4][NV];
     if (P.tgt.p) {
         // space-to-depth target: channel (parity class, c) of position (y, x) — the residual's own layout
         const bf16* tp = (const bf16*)P.tgt.p + tv_pix(P.tgt, img, y, x);
@@ -496,6 +496,12 @@ __device__ __forceinline__ void mse_row(const FwdP& P, const float (&v)[32], con
             }
         }
     }
+}
+
+template <int NV>
+__device__ __forceinline__ void mse_apply(const FwdP& P, const float (&v)[32], const float (&tv)[4][NV], const float* bias_s, int img, int y, int x,
+                                          float& mse_acc) {
+    float* rc = P.out32.p ? (float*)P.out32.p + img * P.out32.sI : nullptr;
     float r16[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) r16[e] = 0.f;
@@ -523,6 +529,13 @@ __device__ __forceinline__ void mse_row(const FwdP& P, const float (&v)[32], con
         for (int e = 0; e < 4; ++e) ph[e] = __floats2bfloat162_rn(r16[ch * 8 + 2 * e], r16[ch * 8 + 2 * e + 1]);
         *reinterpret_cast<uint4*>(dp + ch * P.out.sK) = pk;
     }
+}
+
+template <int NV>
+__device__ __forceinline__ void mse_row(const FwdP& P, const float (&v)[32], const float* bias_s, int img, int y, int x, float& mse_acc) {
+    float tv[4][NV];
+    mse_load<NV>(P, img, y, x, tv);
+    mse_apply<NV>(P, v, tv, bias_s, img, y, x, mse_acc);
 }
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
@@ -888,7 +901,7 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         // Four warps share each TMEM lane quarter.  A pass is cut into items (128-row block, column part); the
         // warps of a quarter take items round-robin.
         const int e = warp - 4, q = e & 3, part = e >> 2;
-        const bool mse = NC == 0 && F32 && OP == OP_UP && P.mse_on;       // fused reconstruction loss: whole rows per warp
+        const bool mse = (NC == 0 || NC == -1) && F32 && OP == OP_UP && P.mse_on;       // fused reconstruction loss: whole rows per warp
         // column parts per block: narrow outputs stay whole (the row decode is amortised over more columns)
         const int ncp = P.ncp;
         const int ncols = P.BN / ncp;
@@ -928,7 +941,17 @@ plane_fwd_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                     }
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * P.set_cols + mb * P.BN + col0);
                     if (NC > 0) {
-                        epi_fast_item<OP, NC == 0 ? 16 : NC>(P, bias_s, taddr, row_ok, img, y, x, n0, oscale);
+                        epi_fast_item<OP, NC <= 0 ? 16 : NC>(P, bias_s, taddr, row_ok, img, y, x, n0, oscale);
+                        continue;
+                    }
+                    if (NC == -1) {
+                        // fused reconstruction loss of a 3-channel image, its own kernel: target loads first, then the accumulators
+                        float tv3[4][3];
+                        if (row_ok) mse_load<3>(P, img, y, x, tv3);
+                        float v[32];
+                        tmem_ld32_nowait(taddr, v);
+                        tmem_wait_ld();
+                        if (row_ok) mse_apply<3>(P, v, tv3, bias_s, img, y, x, mse_acc);
                         continue;
                     }
                     if (mse) {
@@ -1240,6 +1263,7 @@ int plan_fwd(const mrssm_pl_conv_args* a, int op, FwdP& P, size_t& smem_bytes) {
     P.bits_out = a->relu_bits_out; P.bits_in = a->relu_bits_in;
     {
         const bool mse_k = P.mse_on != 0;
+        P.mse_lean = (mse_k && op == OP_UP && P.n_valid == 3 && P.BN == 32 && P.act == 0 && !g_dbg[1]) ? 1 : 0;
         int nc = 0;
         for (int c : {64, 32, 16}) {
             if (P.BN % c == 0 && (op == OP_DOWN || P.Cop % c == 0) && (c == 16 || P.BN / c <= 16)) {
@@ -1329,7 +1353,8 @@ int launch_fwd(const mrssm_pl_conv_args* a, int op, cudaStream_t st) {
     } while (0)
 #define PL_LAUNCH_OP(OPV)                                        \
     do {                                                         \
-        if (P.out_f32) PL_LAUNCH(OPV, true, 0);                  \
+        if (P.out_f32 && P.mse_lean) PL_LAUNCH(OP_UP, true, -1); \
+        else if (P.out_f32) PL_LAUNCH(OPV, true, 0);             \
         else if (!P.fast) PL_LAUNCH(OPV, false, 0);              \
         else if (P.nc == 64) PL_LAUNCH(OPV, false, 64);          \
         else if (P.nc == 32) PL_LAUNCH(OPV, false, 32);          \
