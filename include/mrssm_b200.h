@@ -97,6 +97,10 @@ typedef struct mrssm_tc_conv_args {
     const float* bias;      /* down/up, or NULL */
     float* dweight;         /* wgrad output (accumulated) */
     int64_t w_ss, w_sl;     /* wgrad: master weight strides */
+    /* dense layers only: fp32 [rows][addend_ld] added to the accumulator before the activation (the hoisted, time-parallel
+     * embedding half of an expert's fc1, encoder.py:172-176, when the belief half runs step by step) */
+    const float* addend;
+    int64_t addend_ld;
 } mrssm_tc_conv_args;
 
 int mrssm_tc_conv_down(const mrssm_tc_conv_args* a, void* stream);
@@ -306,6 +310,24 @@ int mrssm_rollout_tc_bwd_plan_bytes(int32_t D, int32_t S, int32_t H, int32_t A, 
                                     int64_t* packed_bytes);
 int mrssm_rollout_tc_bwd_plan(int32_t D, int32_t S, int32_t H, int32_t A, int32_t n_experts, void* host_buf, int64_t buflen);
 int mrssm_rollout_tc_bwd(const mrssm_rollout_bwd_args* g, const void* packed_dev, void* stream);
+
+/* ---- large-model rollout, one time step per call (BASELINE config 5: D = H = 1024 — beyond mrssm_rollout_tc_eligible) ---------
+ * The dense contractions of a step (transition_model.py:226-270: fc_embed_state_action, nn.GRUCell's two projections, every
+ * head's fc1 / fc2, and their dgrads) run as mrssm_tc_conv_down / up GEMMs over all B sequences; these entries do the work
+ * between them on the same [T,B,*] tensors and stash as mrssm_rollout_fwd / bwd (same structs), for time step t:
+ *   xin      : bf16 [B,KX] = [s_{t-1} * nonterminal_t, a_t, 0..]            (transition_model.py:228-232)
+ *   gate_fwd : gi, gh fp32 [B,3D] (biases included) -> h_t (beliefs[t], stash r z n W_hn h) and its bf16 copy   (nn.GRUCell)
+ *   heads_fwd: fc2 outputs of all heads fp32 [B,(1+E)*2S] -> prior / expert / posterior statistics and samples at t
+ *   heads_bwd / gate_bwd / xin_bwd: the matching backward pieces (cgs: state-gradient carry [B,S]; carry_a / carry_b: the two
+ *   parts of the belief-gradient carry [B,D]); d_o[hd]: bf16 [B,S2p] gradient of head hd's fc2 output. */
+int mrssm_rstep_xin(const mrssm_rollout_args* a, int32_t t, int32_t KX, void* xin_b, void* stream);
+int mrssm_rstep_gate_fwd(const mrssm_rollout_args* a, int32_t t, const float* gi, const float* gh, void* hb_out, void* stream);
+int mrssm_rstep_heads_fwd(const mrssm_rollout_args* a, int32_t t, const float* o, void* stream);
+int mrssm_rstep_heads_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float* cgs, void* const* d_o, int32_t S2p, void* stream);
+int mrssm_rstep_gate_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float* dh_heads, float* carry_a, const float* carry_b,
+                         void* dgi, void* dgh, void* stream);
+int mrssm_rstep_xin_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float* dxin, int32_t ld, float* cgs, void* stream);
+int mrssm_add2(const float* x, const float* y, int64_t n, float* out, void* stream);
 
 /* ---- latent part of the ELBO -------------------------------------------------------------------
  * Replaces _get_posterior_states (MRSSM_PoE/algo.py:63-68, MRSSM_MoPoE/algo.py:62-67, base/algo.py:

@@ -61,6 +61,7 @@ class RSSM_base(nn.Module):
         r = self.cfg.rssm
         lr0 = 0 if r.learning_rate_schedule != 0 else r.model_learning_rate
         self.model_optimizer = FusedClipAdam(self.param_list, lr=lr0, eps=r.adam_epsilon, max_grad_norm=r.grad_clip_norm)
+        ops.bump_weight_version()      # new or re-loaded parameters: no cached bf16 packing may match them by address
         if getattr(self, "dp", None) is not None:     # rebuilt after load_model under data parallelism: re-bind the exchange
             self.dp.attach(self.model_optimizer)
 

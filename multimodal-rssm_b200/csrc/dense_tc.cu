@@ -22,6 +22,8 @@ struct DenseP {
     void* out;
     const bf16* mask;
     const float* bias;
+    const float* addend;                  // fp32 [M][lda_add] added before the activation, or NULL
+    long long lda_add;
 };
 
 __device__ __forceinline__ void d_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -154,6 +156,12 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ 
                         const float4 b0 = *reinterpret_cast<const float4*>(bias_s + n), b1 = *reinterpret_cast<const float4*>(bias_s + n + 4);
                         float x[8] = {v[8 * h] + b0.x, v[8 * h + 1] + b0.y, v[8 * h + 2] + b0.z, v[8 * h + 3] + b0.w,
                                       v[8 * h + 4] + b1.x, v[8 * h + 5] + b1.y, v[8 * h + 6] + b1.z, v[8 * h + 7] + b1.w};
+                        if (P.addend) {
+                            const float* ap = P.addend + (long long)row * P.lda_add + n;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (n + i < P.n_valid) x[i] += __ldg(ap + i);
+                        }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) x[i] = act_apply(x[i], P.act);
                         if (P.mask_mode) {
@@ -200,7 +208,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ 
 // A: bf16 [M][K] with row stride lda (elements, multiple of 8); wpacked: bf16 [Npad][Kpad] (Kpad multiple of 64, zero padded)
 int dense_tc_launch(const void* A, long long lda, int M, int K, const void* wpacked, int Npad, int Kpad, int n_valid, const float* bias,
                     int bias_mod, int act, const void* mask, long long ldm, int mask_mode, void* out, long long ldc, long long cstride,
-                    int out_f32, cudaStream_t st) {
+                    int out_f32, cudaStream_t st, const float* addend, long long addend_ld) {
     MRSSM_CHECK(A && wpacked && out && M > 0 && K > 0 && Npad % 16 == 0 && Kpad % 64 == 0 && lda % 8 == 0 && K % 8 == 0,
                 "dense_tc: bad arguments (M %d K %d Npad %d Kpad %d lda %lld)", M, K, Npad, Kpad, lda);
     MRSSM_CHECK(Npad <= 4096, "dense_tc: %d output columns exceed the bias table", Npad);
@@ -217,6 +225,7 @@ int dense_tc_launch(const void* A, long long lda, int M, int K, const void* wpac
     P.act = act; P.mask_mode = mask ? mask_mode : 0; P.out_f32 = out_f32; P.bias_mod = bias_mod > 0 ? bias_mod : std::max(1, n_valid);
     P.ldc = ldc; P.cstride = cstride; P.ldm = ldm;
     P.out = out; P.mask = (const bf16*)mask; P.bias = bias;
+    P.addend = addend; P.lda_add = addend_ld;
     CUtensorMap mA, mW;
     if (int rc = mrssm_tma_map_2d_sw128(&mA, A, K, M, lda * 2, 64, 128)) return rc;
     if (int rc = mrssm_tma_map_2d_sw128(&mW, wpacked, Kpad, Npad, (long long)Kpad * 2, 64, P.BN)) return rc;

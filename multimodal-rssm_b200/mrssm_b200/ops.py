@@ -369,6 +369,183 @@ class RolloutSpec:
 N_FIXED_PARAMS = 6   # w_sa, b_sa, w_ih, w_hh, b_ih, b_hh  then per head (fc1.w, fc1.b, fc2.w, fc2.b)
 
 
+def rollout_step_enabled():
+    return _STATE["bf16"] and _STATE.get("rollout_step", True)
+
+
+def set_rollout_step(on):
+    """bf16 mode only: large models (beyond the fused tcgen05 rollout) run the rollout as per-step tcgen05 GEMMs."""
+    _STATE["rollout_step"] = bool(on)
+
+
+def _gemm_down(M, x_ptr, ldx, Kp, wp, bias, N, out_ptr, ldo, out_f32=0, act=0, addend=None, addend_ld=0, tag="step_gemm"):
+    """y[M, N] = act(x[M, Kp] W^T + bias (+ addend)); x bf16 rows (stride ldx), W packed mode 0, y bf16 or fp32 rows (stride ldo)."""
+    Np = wp.shape[1]
+    a = _tc_args((M, 1, 1, Kp, 1, 1, Np, 1), _row_t4(x_ptr, ldx), _row_t4(out_ptr, ldo), act, None, 0, out_f32, Np, N, 0,
+                 wpacked=L.ptr(wp), bias=L.ptr(bias))
+    if addend is not None:
+        a.addend, a.addend_ld = addend, addend_ld
+    L.call("mrssm_tc_conv_down", C.byref(a), tag=tag if L.profile is not None else None,
+           work=dict(flops=2.0 * M * Kp * N, bytes=2.0 * (M * Kp + N * Kp) + (4.0 if out_f32 else 2.0) * M * N) if L.profile is not None else None)
+
+
+def _gemm_up(M, dy_ptr, ldy, Np_dy, wp, K, out_ptr, ldo, out_f32=0, mask_ptr=None, ldm=0, mask_mode=0, tag="step_dgrad"):
+    """dx[M, K] = (dy[M, Np_dy] W) * act'(mask); dy bf16 rows, W packed mode 1, dx bf16 or fp32 rows."""
+    Kp_out = wp.shape[1]
+    mask = _row_t4(mask_ptr, ldm) if mask_ptr is not None else None
+    a = _tc_args((M, 1, 1, Kp_out, 1, 1, Np_dy, 1), _row_t4(out_ptr, ldo), _row_t4(dy_ptr, ldy), 0, mask, mask_mode, out_f32, Kp_out, K, 0,
+                 wpacked=L.ptr(wp), bias=None)
+    L.call("mrssm_tc_conv_up", C.byref(a), tag=tag if L.profile is not None else None,
+           work=dict(flops=2.0 * M * Np_dy * K, bytes=2.0 * (M * Np_dy + K * Np_dy) + (4.0 if out_f32 else 2.0) * M * K) if L.profile is not None else None)
+
+
+def _rollout_steps_fwd(a, spec, E, T, B, w_sa, b_sa, w_ih, w_hh, b_ih, b_hh, heads, emb_pre, stash, dev):
+    """The T steps of transition_model.py:226-270 as per-step tcgen05 GEMMs + the kernels of csrc/rollout_step.cu.  Fills the
+    output tensors and the stash named in `a`; returns the extra stash tensors [hb_all, xin_all]."""
+    D, S, H, A = spec.D, spec.S, spec.H, spec.A
+    NH = 1 + E
+    KX = pad8(S + A)
+    nb16 = lambda *sh: torch.empty(*sh, device=dev, dtype=torch.bfloat16)
+    xin_all = nb16(T, B, KX)
+    x_all = stash["x"] if stash is not None else nb16(1, B, D)
+    u_all = stash["u"] if stash is not None else [nb16(1, B, H) for _ in range(NH)]
+    hb_all = nb16(T + 1, B, D)
+    keep_all = stash is not None
+    L.call("mrssm_tc_to_bf16", C.byref(_row_t4(a.prev_belief, D)), B, 1, 1, D, D, 1.0, hb_all.data_ptr())
+    gi = torch.empty(B, 3 * D, device=dev, dtype=torch.float32)
+    gh = torch.empty(B, 3 * D, device=dev, dtype=torch.float32)
+    o_cat = torch.empty(B, NH * 2 * S, device=dev, dtype=torch.float32)
+    wp_sa = packed(w_sa, 0, pad16(D), KX)
+    wp_ih = packed(w_ih, 0, pad16(3 * D), D)
+    wp_hh = packed(w_hh, 0, pad16(3 * D), D)
+    wp_1 = [packed_cols(hd[0], 0, D, 0) for hd in heads]
+    wp_2 = [packed(hd[2], 0, pad16(2 * S), H) for hd in heads]
+    for t in range(T):
+        ts = t if keep_all else 0
+        L.call("mrssm_rstep_xin", C.byref(a), t, KX, xin_all[t].data_ptr())
+        _gemm_down(B, xin_all[t].data_ptr(), KX, KX, wp_sa, b_sa, D, x_all[ts].data_ptr(), D, act=spec.act, tag="step_fc_embed")
+        _gemm_down(B, x_all[ts].data_ptr(), D, D, wp_ih, b_ih, 3 * D, gi.data_ptr(), 3 * D, out_f32=1, tag="step_gru_ih")
+        _gemm_down(B, hb_all[t].data_ptr(), D, D, wp_hh, b_hh, 3 * D, gh.data_ptr(), 3 * D, out_f32=1, tag="step_gru_hh")
+        L.call("mrssm_rstep_gate_fwd", C.byref(a), t, gi.data_ptr(), gh.data_ptr(), hb_all[t + 1].data_ptr())
+        for hd in range(NH):
+            w1, b1, w2, b2 = heads[hd]
+            pre = emb_pre[hd]
+            _gemm_down(B, hb_all[t + 1].data_ptr(), D, D, wp_1[hd], None if pre is not None else b1, H, u_all[hd][ts].data_ptr(), H,
+                       act=spec.act, addend=None if pre is None else pre.data_ptr() + 4 * t * B * H, addend_ld=H, tag="step_fc1")
+            _gemm_down(B, u_all[hd][ts].data_ptr(), H, H, wp_2[hd], b2, 2 * S, o_cat.data_ptr() + 4 * hd * 2 * S, NH * 2 * S, out_f32=1,
+                       tag="step_fc2")
+        L.call("mrssm_rstep_heads_fwd", C.byref(a), t, o_cat.data_ptr())
+    return [hb_all, xin_all]
+
+
+def _rollout_steps_bwd(ctx, ins, embs, outs, st, gouts):
+    """BPTT of _rollout_steps_fwd: per step the dgrad GEMMs and the backward kernels of csrc/rollout_step.cu, then the deferred,
+    time-parallel weight-gradient GEMMs over the bf16 per-step gradients."""
+    spec, observe, E = ctx.spec, ctx.observe, ctx.E
+    prev_state, actions, prev_belief, nonterminals, eps_prior, eps_post = ins
+    params = ctx.params
+    D, S, H, A = spec.D, spec.S, spec.H, spec.A
+    T, B = actions.shape[0], actions.shape[1]
+    R, NH = T * B, 1 + E
+    dev = actions.device
+    w_sa, b_sa, w_ih, w_hh, b_ih, b_hh = params[:N_FIXED_PARAMS]
+    heads = [params[N_FIXED_PARAMS + 4 * i: N_FIXED_PARAMS + 4 * i + 4] for i in range(NH)]
+    x_all, r_, z_, n_, ghn_ = st[:5]
+    u_all = list(st[5:5 + NH])
+    hb_all, xin_all = st[5 + NH], st[6 + NH]
+    gouts = [None if g_ is None else _f32c(g_) for g_ in gouts]
+    KX, S2p = xin_all.shape[-1], pad16(2 * S)
+
+    g = L.RolloutBwdArgs()
+    a = g.f
+    a.T, a.B, a.D, a.S, a.H, a.A, a.n_experts = T, B, D, S, H, A, E
+    a.act, a.det, a.min_std = spec.act, int(bool(ctx.det)), spec.min_std
+    a.prev_state, a.prev_belief, a.actions = L.ptr(prev_state), L.ptr(prev_belief), L.ptr(actions)
+    a.nonterminals, a.eps_prior, a.eps_post = L.ptr(nonterminals), L.ptr(eps_prior), L.ptr(eps_post)
+    if observe:
+        spec.table.fill(a)
+    a.beliefs, a.prior_states, a.prior_means, a.prior_stds = [L.ptr(t_) for t_ in outs[:4]]
+    g.g_beliefs, g.g_prior_states, g.g_prior_means, g.g_prior_stds = [L.ptr(t_) for t_ in gouts[:4]]
+    if observe:
+        a.post_states, a.post_means, a.post_stds = [L.ptr(t_) for t_ in outs[4:7]]
+        g.g_post_states, g.g_post_means, g.g_post_stds = [L.ptr(t_) for t_ in gouts[4:7]]
+        for e in range(E):
+            a.exp_means[e + 1], a.exp_stds[e + 1] = L.ptr(outs[7 + e]), L.ptr(outs[7 + E + e])
+            g.g_exp_means[e + 1], g.g_exp_stds[e + 1] = L.ptr(gouts[7 + e]), L.ptr(gouts[7 + E + e])
+    a.st_r, a.st_z, a.st_n, a.st_ghn = L.ptr(r_), L.ptr(z_), L.ptr(n_), L.ptr(ghn_)
+    f32 = lambda *sh: torch.empty(*sh, device=dev, dtype=torch.float32)
+    nb16 = lambda *sh: torch.empty(*sh, device=dev, dtype=torch.bfloat16)
+    g_actions = f32(T, B, A)
+    g.g_actions = L.ptr(g_actions)
+    d_o = [nb16(T, B, S2p) for _ in range(NH)]
+    du_all = nb16(T, B, NH * H)
+    d_gi, d_gh, d_xpre = nb16(T, B, 3 * D), nb16(T, B, 3 * D), nb16(T, B, D)
+    dh_heads, carry_b, dxin = f32(B, D), torch.zeros(B, D, device=dev), f32(B, S + A)
+    carry_a, cgs = torch.zeros(B, D, device=dev), torch.zeros(B, S, device=dev)
+    # dgrad-type packings; the belief columns of every head's fc1 stacked along K: dh = [du_0 | du_1 | ..] [W1_0[:, :D]; W1_1[:, :D]; ..]
+    w1cat = f32(NH * H, D)
+    for hd in range(NH):
+        w1 = heads[hd][0]
+        L.call("mrssm_copy2d", L.ptr(w1), H, D, w1.shape[1], w1cat.data_ptr() + 4 * hd * H * D)
+    wp_1cat = tc_pack_weight(w1cat.reshape(NH * H, D, 1, 1), 1, NH * H, D)
+    del w1cat
+    wp_2 = [packed(hd[2], 1, S2p, H) for hd in heads]
+    wp_ih, wp_hh = packed(w_ih, 1, pad16(3 * D), D), packed(w_hh, 1, pad16(3 * D), D)
+    wp_sa = packed(w_sa, 1, pad16(D), KX)
+    d_o_ptrs = (C.c_void_p * L.MAX_HEADS)()
+    for t in reversed(range(T)):
+        for hd in range(NH):
+            d_o_ptrs[hd] = d_o[hd][t].data_ptr()
+        L.call("mrssm_rstep_heads_bwd", C.byref(g), t, cgs.data_ptr(), d_o_ptrs, S2p)
+        for hd in range(NH):
+            _gemm_up(B, d_o[hd][t].data_ptr(), S2p, S2p, wp_2[hd], H, du_all[t].data_ptr() + 2 * hd * H, NH * H,
+                     mask_ptr=u_all[hd][t].data_ptr(), ldm=H, mask_mode=spec.act, tag="step_fc2_dgrad")
+        _gemm_up(B, du_all[t].data_ptr(), NH * H, NH * H, wp_1cat, D, dh_heads.data_ptr(), D, out_f32=1, tag="step_fc1_dgrad")
+        L.call("mrssm_rstep_gate_bwd", C.byref(g), t, dh_heads.data_ptr(), carry_a.data_ptr(), carry_b.data_ptr(), d_gi[t].data_ptr(),
+               d_gh[t].data_ptr())
+        _gemm_up(B, d_gi[t].data_ptr(), 3 * D, 3 * D, wp_ih, D, d_xpre[t].data_ptr(), D, mask_ptr=x_all[t].data_ptr(), ldm=D, mask_mode=spec.act,
+                 tag="step_ih_dgrad")
+        _gemm_up(B, d_gh[t].data_ptr(), 3 * D, 3 * D, wp_hh, D, carry_b.data_ptr(), D, out_f32=1, tag="step_hh_dgrad")
+        _gemm_up(B, d_xpre[t].data_ptr(), D, D, wp_sa, S + A, dxin.data_ptr(), S + A, out_f32=1, tag="step_sa_dgrad")
+        L.call("mrssm_rstep_xin_bwd", C.byref(g), t, dxin.data_ptr(), S + A, cgs.data_ptr())
+    g_prev_belief = f32(B, D)
+    L.call("mrssm_add2", carry_a.data_ptr(), carry_b.data_ptr(), B * D, g_prev_belief.data_ptr())
+    g_prev_state = cgs
+
+    # deferred, time-parallel weight gradients: dW += dY^T X over all (t, b) rows, bf16 operands as they are
+    def wgrad(dy_ptr, ldy, N, x_ptr, ldx, K, rows, gw_ptr, ld, gb):
+        tc_conv_wgrad((rows, 1, 1, pad8(K), 1, 1, pad8(N), 1), L.T4(x_ptr, ldx, 0, 0, 1), L.T4(dy_ptr, ldy, 0, 0, 1), gw_ptr, ld, 1, N, K)
+        if gb is not None:
+            L.call("mrssm_tc_colsum", dy_ptr, rows, ldy, N, L.ptr(gb))
+
+    wgrad(d_xpre.data_ptr(), D, D, xin_all.data_ptr(), KX, S + A, R, L.ptr(grad_buf(w_sa)), S + A, grad_buf(b_sa))
+    wgrad(d_gi.data_ptr(), 3 * D, 3 * D, x_all.data_ptr(), D, D, R, L.ptr(grad_buf(w_ih)), D, grad_buf(b_ih))
+    wgrad(d_gh.data_ptr(), 3 * D, 3 * D, hb_all.data_ptr(), D, D, R, L.ptr(grad_buf(w_hh)), D, grad_buf(b_hh))
+    g_embs, ei = [], 0
+    for hd in range(NH):
+        w1, b1, w2, b2 = heads[hd]
+        ld = w1.shape[1]
+        wgrad(d_o[hd].data_ptr(), S2p, 2 * S, u_all[hd].data_ptr(), H, H, R, L.ptr(grad_buf(w2)), H, grad_buf(b2))
+        du_ptr = du_all.data_ptr() + 2 * hd * H
+        gw1 = grad_buf(w1)
+        wgrad(du_ptr, NH * H, H, hb_all[1].data_ptr(), D, D, R, L.ptr(gw1), ld, grad_buf(b1))
+        if hd > 0 and spec.expert_has_emb[hd - 1]:
+            emb = embs[ei]
+            Em = emb.shape[-1]
+            Emp = pad8(Em)
+            eb = pl_import(L.nhwc(emb, 1, 1, Em), R, 1, 1, Em, Emp, L.NHWC, dev)[0]
+            wgrad(du_ptr, NH * H, H, eb.data_ptr(), Emp, Em, R, _off(gw1, D), ld, None)
+            del eb
+            ge = None
+            if ctx.needs_input_grad[9 + ei]:
+                ge = torch.empty_like(emb)
+                tc_conv_up((R, 1, 1, Emp, 1, 1, pad8(H), 1), L.nhwc(ge, 1, 1, Em), L.T4(du_ptr, NH * H, 0, 0, 1),
+                           packed_cols(w1, D, Em, 1), None, Em, out_f32=1, valid=(H, Em))
+            g_embs.append(ge)
+            ei += 1
+    return (None, None, None, g_prev_state, g_actions, g_prev_belief, None, None, None, *g_embs, *([None] * len(params)))
+
+
 class RolloutFn(Function):
     """All T steps of transition_model.py:226-270 in one launch (+ hoisted expert-embedding GEMMs).
 
@@ -404,10 +581,15 @@ class RolloutFn(Function):
         a.nonterminals, a.eps_prior, a.eps_post = L.ptr(nonterminals), L.ptr(eps_prior), L.ptr(eps_post)
         keep = []
         use_tc = rollout_tc_enabled() and bool(L.load().mrssm_rollout_tc_eligible(D, S, H, A, E))
+        # models too large for the fused tcgen05 rollout (BASELINE config 5: D = H = 1024): one tcgen05 GEMM per contraction per
+        # time step over all B sequences, small kernels in between (csrc/rollout_step.cu)
+        use_step = (not use_tc) and rollout_step_enabled() and D % 16 == 0 and H % 16 == 0 and D >= 256
         if use_tc:
             # tcgen05 rollout: the kernel reads the packed bf16 weight stream, only the biases come through `a`
             a.b_sa, a.b_ih, a.b_hh = L.ptr(b_sa), L.ptr(b_ih), L.ptr(b_hh)
             tc_plan, tc_packed = rollout_tc_weights(spec, E, w_sa, w_ih, w_hh, heads, dev)
+        elif use_step:
+            a.b_sa, a.b_ih, a.b_hh = L.ptr(b_sa), L.ptr(b_ih), L.ptr(b_hh)
         else:
             wsaT = transpose(L.ptr(w_sa), D, S + A, S + A, dev)
             wihT = transpose(L.ptr(w_ih), 3 * D, D, D, dev)
@@ -420,7 +602,7 @@ class RolloutFn(Function):
         for hd in range(1 + E):
             w1, b1, w2, b2 = heads[hd]
             ld = w1.shape[1]
-            if not use_tc:
+            if not use_tc and not use_step:
                 w1T = transpose(L.ptr(w1), H, D, ld, dev)
                 w2T = transpose(L.ptr(w2), 2 * S, H, H, dev)
                 keep += [w1T, w2T]
@@ -461,7 +643,12 @@ class RolloutFn(Function):
                 a.exp_means[e + 1], a.exp_stds[e + 1] = L.ptr(em[e]), L.ptr(es[e])
             outs += post + em + es
         stash = None
-        if need_grad:
+        if need_grad and use_step:
+            # bf16 stash of the step path: x and u are the GEMM operands themselves; + the bf16 beliefs and [state, action] rows
+            nb16 = lambda *sh: torch.empty(*sh, device=dev, dtype=torch.bfloat16)
+            stash = dict(x=nb16(T, B, D), r=new(D), z=new(D), n=new(D), ghn=new(D), u=[nb16(T, B, H) for _ in range(1 + E)])
+            a.st_r, a.st_z, a.st_n, a.st_ghn = [L.ptr(stash[k]) for k in ("r", "z", "n", "ghn")]
+        elif need_grad:
             stash = dict(x=new(D), r=new(D), z=new(D), n=new(D), ghn=new(D), u=[new(H) for _ in range(1 + E)])
             a.st_x, a.st_r, a.st_z, a.st_n, a.st_ghn = [L.ptr(stash[k]) for k in ("x", "r", "z", "n", "ghn")]
             for hd in range(1 + E):
@@ -476,17 +663,21 @@ class RolloutFn(Function):
                 per = 4.0 * (A + S) + 4.0 * (D + 3 * S)
             macs = (S + A) * D + 6 * D * D + (1 + E) * (D * H + H * 2 * S) + sum(e.shape[-1] * H for e in embs)
             work = dict(bytes=per * T * B + 4.0 * n_w, flops=2.0 * macs * T * B)
+        extra = []
         if use_tc:
             L.call("mrssm_rollout_tc_fwd", C.byref(a), L.ptr_any(tc_plan), L.ptr_any(tc_packed),
                    tag="observe" if observe else "imagine", work=work)
+        elif use_step:
+            extra = _rollout_steps_fwd(a, spec, E, T, B, w_sa, b_sa, w_ih, w_hh, b_ih, b_hh, heads, emb_pre, stash, dev)
         else:
             L.call("mrssm_rollout_fwd", C.byref(a), tag="observe" if observe else "imagine", work=work)
         del keep
         ctx.spec, ctx.observe, ctx.det, ctx.E = spec, observe, det, E
         ctx.params = params
+        ctx.step_path = bool(use_step)
         ins = [prev_state, actions, prev_belief, nonterminals, eps_prior, eps_post]
         ctx.in_mask = [t is not None for t in ins]
-        st = [] if stash is None else [stash[k] for k in ("x", "r", "z", "n", "ghn")] + stash["u"]
+        st = [] if stash is None else [stash[k] for k in ("x", "r", "z", "n", "ghn")] + stash["u"] + extra
         ctx.counts = (len(embs), len(outs), len(st))
         ctx.save_for_backward(*[t for t in ins if t is not None], *embs, *outs, *st)
         ctx.set_materialize_grads(False)
@@ -501,6 +692,8 @@ class RolloutFn(Function):
         n_emb, n_out, n_st = ctx.counts
         embs, outs, st = saved[:n_emb], saved[n_emb:n_emb + n_out], saved[n_emb + n_out:]
         assert n_st, "rollout forward ran without grad"
+        if ctx.step_path:
+            return _rollout_steps_bwd(ctx, ins, embs, outs, st, gouts)
         stash = dict(zip(("x", "r", "z", "n", "ghn"), st[:5]), u=st[5:])
         params = ctx.params
         D, S, H, A = spec.D, spec.S, spec.H, spec.A

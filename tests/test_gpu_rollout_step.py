@@ -1,0 +1,94 @@
+"""-m gpu: the per-step tensor-core rollout for models beyond the fused tcgen05 rollout's D, H <= 208 (BASELINE config 5,
+deter = hidden = 1024; csrc/rollout_step.cu + the dense tcgen05 GEMMs of csrc/dense_tc.cu) against the exact fp32 CUDA-core
+rollout on the same inputs, noise and upstream gradients (transition_model.py:226-270 and its autograd).
+Every GEMM operand (weights, x, h, u, state and the per-step gradients) is rounded to bf16; the recurrent state, the gate /
+fusion arithmetic and all accumulation stay fp32.  Tolerances (stated): forward outputs max error <= 3e-2 (x the tensor's
+scale) and mean error <= 4e-3; gradients relative Frobenius error <= 8e-3 per tensor with the smooth (ELU) activation
+(measured 1.2e-3 .. 4.2e-3).  With ReLU the bf16 forward flips the mask of the ~0.2 % of units whose pre-activation is within
+rounding of zero, which alone moves a gradient tensor by sqrt(0.002) ~ 4-5 % in Frobenius norm against the fp32 run (measured
+<= 5.5e-2); that case is bounded at 8e-2 and is a statement about ReLU, not about the kernels."""
+import pytest
+import torch
+
+from tests.test_gpu_rollout_tc import _params
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+CASES = [
+    # (D, S, H, A, fusion, emb sizes per expert (0 = none), T, B, det)
+    (256, 32, 256, 3, "MoPoE", (0, 1024, 128), 5, 70, False),
+    (512, 64, 256, 3, "PoE", (0, 256, 128), 4, 130, False),        # config 5's stoch size; B not a multiple of the row tile
+    (256, 30, 272, 5, "single", (128,), 6, 33, False),             # 2S = 60 -> padded gradient operand, S + A = 35
+    (256, 30, 256, 3, None, (), 5, 64, False),                     # open-loop imagination
+    (1024, 64, 1024, 3, "MoPoE", (0, 1024, 128), 3, 16, False),    # config 5's model
+    (256, 32, 256, 3, "MoPoE", (0, 1024, 128), 3, 8, True),        # det=True
+]
+
+
+def _setup(case, seed, grads, act=None):
+    from mrssm_b200 import ops
+    D, S, H, A, fusion, emb_sizes, T, B, det = case
+    ops.bump_weight_version()       # fresh parameters may reuse the addresses of the previous case's: drop the packed copies
+    gen = torch.Generator(device=DEV).manual_seed(seed + D + B)
+    observe = fusion is not None
+    E = len(emb_sizes)
+    table = ops.FusionTable(E, S, fusion if observe else "single")
+    spec = ops.RolloutSpec(D, S, H, A, ops.RELU if act is None else act, 0.1, table, [e > 0 for e in emb_sizes])
+    params = [p.requires_grad_(grads) for p in _params(gen, D, S, H, A, emb_sizes)]
+    rn = lambda *s: torch.randn(*s, device=DEV, generator=gen)
+    nonterm = (torch.rand(T, B, device=DEV, generator=gen) > 0.15).float()
+    ins = [rn(B, S).requires_grad_(grads), rn(T, B, A).requires_grad_(grads), (rn(B, D) * 0.5).requires_grad_(grads), nonterm,
+           None if det else rn(T, B, S), None if (det or not observe) else rn(T, B, S)]
+    embs = [rn(T, B, e).requires_grad_(grads) for e in emb_sizes if e > 0]
+    return ops, spec, observe, det, ins, embs, params, rn, E
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_rollout_step_forward_matches_fp32(case):
+    from mrssm_b200 import _lib as L
+    ops, spec, observe, det, ins, embs, params, rn, E = _setup(case, 7, False)
+    assert L.load().mrssm_rollout_tc_eligible(spec.D, spec.S, spec.H, spec.A, E) == 0
+    with torch.no_grad():
+        ref = ops.RolloutFn.apply(spec, observe, det, *ins, *embs, *params)           # exact fp32 kernels
+        ops.set_bf16_mode(True)
+        try:
+            n0 = L.launches
+            out = ops.RolloutFn.apply(spec, observe, det, *ins, *embs, *params)
+            assert L.launches - n0 > 5 * case[6], "the per-step path did not run"
+        finally:
+            ops.set_bf16_mode(False)
+    names = ["beliefs", "prior_states", "prior_means", "prior_stds", "post_states", "post_means", "post_stds"] + \
+            [f"exp_mean{e}" for e in range(E)] + [f"exp_std{e}" for e in range(E)]
+    assert len(ref) == len(out)
+    for n, r, o in zip(names, ref, out):
+        assert torch.isfinite(o).all(), n
+        err = (o - r).abs()
+        assert float(err.max()) <= 3e-2 * max(1.0, float(r.abs().max())), (n, float(err.max()), float(r.abs().max()))
+        assert float(err.mean()) <= 4e-3 * max(1.0, float(r.abs().mean())), (n, float(err.mean()))
+
+
+@pytest.mark.parametrize("case,act,tol", [(c, "ELU", 8e-3) for c in CASES[:5]] + [(CASES[0], "RELU", 8e-2)])
+def test_rollout_step_bptt_matches_fp32(case, act, tol):
+    from mrssm_b200 import ops as _ops
+    ops, spec, observe, det, ins, embs, params, rn, E = _setup(case, 11, True, act=getattr(_ops, act))
+    leaves = ins[:3] + embs + params
+    gouts, results = None, []
+    for bf16 in (False, True):
+        for t in leaves:
+            t.grad = None
+        ops.set_bf16_mode(bf16)
+        try:
+            outs = ops.RolloutFn.apply(spec, observe, det, *ins, *embs, *params)
+            if gouts is None:
+                gouts = [rn(*o.shape) / o.shape[-1] ** 0.5 for o in outs]
+            torch.autograd.backward(outs, gouts)
+        finally:
+            ops.set_bf16_mode(False)
+        results.append([t.grad.clone() for t in leaves])
+    names = ["g_prev_state", "g_actions", "g_prev_belief"] + [f"g_emb{i}" for i in range(len(embs))] + \
+            [f"g_param{i}" for i in range(len(params))]
+    for n, r, o in zip(names, *results):
+        assert torch.isfinite(o).all(), n
+        rel = float((o - r).norm() / (r.norm() + 1e-12))
+        assert rel <= tol, (n, rel, float(r.norm()))
