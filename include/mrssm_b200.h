@@ -101,6 +101,11 @@ typedef struct mrssm_tc_conv_args {
      * embedding half of an expert's fc1, encoder.py:172-176, when the belief half runs step by step) */
     const float* addend;
     int64_t addend_ld;
+    /* dense layers only: block-diagonal ("grouped") GEMM — output columns [g*group_n, (g+1)*group_n) contract input columns
+       [g*group_k, (g+1)*group_k) only (all heads' fc2, or their dgrads, in one launch: encoder.py:126-190 runs one such Linear
+       per expert).  The packed weight then holds group_k (padded to 64) columns per output row.  0 = plain GEMM. */
+    int32_t group_n;
+    int32_t group_k;
 } mrssm_tc_conv_args;
 
 int mrssm_tc_conv_down(const mrssm_tc_conv_args* a, void* stream);
@@ -317,13 +322,16 @@ int mrssm_rollout_tc_bwd(const mrssm_rollout_bwd_args* g, const void* packed_dev
  * between them on the same [T,B,*] tensors and stash as mrssm_rollout_fwd / bwd (same structs), for time step t:
  *   xin      : bf16 [B,KX] = [s_{t-1} * nonterminal_t, a_t, 0..]            (transition_model.py:228-232)
  *   gate_fwd : gi, gh fp32 [B,3D] (biases included) -> h_t (beliefs[t], stash r z n W_hn h) and its bf16 copy   (nn.GRUCell)
- *   heads_fwd: fc2 outputs of all heads fp32 [B,(1+E)*2S] -> prior / expert / posterior statistics and samples at t
+ *   heads_fwd: fc2 outputs of all heads fp32 (row stride ldo, head hd at column hd * head_stride) -> prior / expert / posterior
+ *              statistics and samples at t
  *   heads_bwd / gate_bwd / xin_bwd: the matching backward pieces (cgs: state-gradient carry [B,S]; carry_a / carry_b: the two
- *   parts of the belief-gradient carry [B,D]); d_o[hd]: bf16 [B,S2p] gradient of head hd's fc2 output. */
+ *   parts of the belief-gradient carry [B,D]); d_o[hd]: bf16 rows of S2p columns (row stride ld), gradient of head hd's fc2
+ *   output, padding columns zeroed. */
 int mrssm_rstep_xin(const mrssm_rollout_args* a, int32_t t, int32_t KX, void* xin_b, void* stream);
 int mrssm_rstep_gate_fwd(const mrssm_rollout_args* a, int32_t t, const float* gi, const float* gh, void* hb_out, void* stream);
-int mrssm_rstep_heads_fwd(const mrssm_rollout_args* a, int32_t t, const float* o, void* stream);
-int mrssm_rstep_heads_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float* cgs, void* const* d_o, int32_t S2p, void* stream);
+int mrssm_rstep_heads_fwd(const mrssm_rollout_args* a, int32_t t, const float* o, int32_t ldo, int32_t head_stride, void* stream);
+int mrssm_rstep_heads_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float* cgs, void* const* d_o, int32_t ld, int32_t S2p,
+                          void* stream);
 int mrssm_rstep_gate_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float* dh_heads, float* carry_a, const float* carry_b,
                          void* dgi, void* dgh, void* stream);
 int mrssm_rstep_xin_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float* dxin, int32_t ld, float* cgs, void* stream);

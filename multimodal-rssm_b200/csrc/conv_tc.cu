@@ -534,7 +534,7 @@ extern "C" int mrssm_tc_colsum(const void* x, int64_t rows, int32_t Cpad, int32_
 
 int dense_tc_launch(const void* A, long long lda, int M, int K, const void* wpacked, int Npad, int Kpad, int n_valid, const float* bias,
                     int bias_mod, int act, const void* mask, long long ldm, int mask_mode, void* out, long long ldc, long long cstride,
-                    int out_f32, cudaStream_t st, const float* addend = nullptr, long long addend_ld = 0);
+                    int out_f32, cudaStream_t st, const float* addend = nullptr, long long addend_ld = 0, int group_n = 0, int group_k = 0);
 
 static int launch_fwd(const mrssm_tc_conv_args* a, int op, cudaStream_t st) {
     MRSSM_CHECK(a && a->large.ptr && a->small.ptr && a->wpacked, "tc_conv: null tensor");
@@ -548,12 +548,13 @@ static int launch_fwd(const mrssm_tc_conv_args* a, int op, cudaStream_t st) {
         if (full_window && in.sC == 1 && Cin % 8 == 0 && in.sI % 8 == 0 && a->n_out_pad % 16 == 0 && a->n_out_pad <= 4096 &&
             (a->out_f32 || (out.sC == 1 && out.sI % 8 == 0)) && (!a->mask.ptr || (a->mask.sC == 1 && a->mask.sI % 8 == 0))) {
             const int K = (op == OP_DOWN) ? a->ksz * a->ksz * Cin : Cin;
-            const int Kpad = (int)(ceil_div64(K, BK) * BK);
+            const int Kpad = (int)(ceil_div64(a->group_n > 0 ? a->group_k : K, BK) * BK);
             return dense_tc_launch(in.ptr, in.sI, a->n_img, K, a->wpacked, a->n_out_pad, Kpad, a->n_out_valid, a->bias, a->bias_mod, a->act,
-                                   a->mask.ptr, a->mask.sI, a->mask_mode, out.ptr, out.sI, out.sC, a->out_f32, st, a->addend, a->addend_ld);
+                                   a->mask.ptr, a->mask.sI, a->mask_mode, out.ptr, out.sI, out.sC, a->out_f32, st, a->addend, a->addend_ld,
+                                   a->group_n, a->group_k);
         }
     }
-    MRSSM_CHECK(!a->addend, "tc_conv: an addend is supported by the dense (1x1 / full-window) layers only");
+    MRSSM_CHECK(!a->addend && a->group_n == 0, "tc_conv: addend / grouping are supported by the dense (1x1 / full-window) layers only");
     FwdK k;
     k.n_img = a->n_img; k.Hl = a->Hl; k.Wl = a->Wl; k.Hs = a->Hs; k.Ws = a->Ws; k.ksz = a->ksz; k.nt = (a->ksz + 1) / 2;
     const mrssm_t4& in = (op == OP_DOWN) ? a->large : a->small;

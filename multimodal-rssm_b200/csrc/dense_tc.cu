@@ -24,6 +24,8 @@ struct DenseP {
     const float* bias;
     const float* addend;                  // fp32 [M][lda_add] added before the activation, or NULL
     long long lda_add;
+    int group_n, group_k;                 // block-diagonal GEMM: column tile -> first A column it contracts; 0 = plain
+    int vec4;                             // fp32 output rows allow 16-byte stores
 };
 
 __device__ __forceinline__ void d_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -69,7 +71,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ 
     const uint32_t a_bytes = 128u * 128u, b_bytes = (uint32_t)P.BN * 128u, stage = a_bytes + b_bytes;
     const int n_tiles = P.n_mtiles * P.n_ntiles;
 
-    for (int c = tid; c < 4096; c += DT) bias_s[c] = (P.bias && c < P.n_valid) ? P.bias[c % P.bias_mod] : 0.f;
+    for (int c = tid; c < P.Npad; c += DT) bias_s[c] = (P.bias && c < P.n_valid) ? P.bias[c % P.bias_mod] : 0.f;
     if (tid == 0) {
         for (int s = 0; s < 8; ++s) {
             tc::mbar_init(tc::smem_u32(&full[s]), 1);
@@ -92,12 +94,13 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ 
             uint32_t cnt = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int mt = tile / P.n_ntiles, nt = tile - mt * P.n_ntiles;
+                const int koff = P.group_n ? (nt * P.BN) / P.group_n * P.group_k : 0;
                 for (int kb = 0; kb < P.nkb; ++kb, ++cnt) {
                     const int s = cnt % P.NS;
                     tc::mbar_wait(tc::smem_u32(&empty[s]), ((cnt / P.NS) & 1) ^ 1);
                     const uint32_t bar = tc::smem_u32(&full[s]);
                     d_expect_tx(bar, stage);
-                    d_tma_2d(smem0 + (uint32_t)s * stage, &mA, kb * 64, mt * 128, bar);
+                    d_tma_2d(smem0 + (uint32_t)s * stage, &mA, koff + kb * 64, mt * 128, bar);
                     d_tma_2d(smem0 + (uint32_t)s * stage + a_bytes, &mW, kb * 64, nt * P.BN, bar);
                 }
             }
@@ -176,9 +179,14 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ 
                         }
                         if (P.out_f32) {
                             float* op = (float*)P.out + (long long)row * P.ldc;
+                            if (P.vec4 && n + 8 <= P.n_valid) {
+                                *reinterpret_cast<float4*>(op + n) = make_float4(x[0], x[1], x[2], x[3]);
+                                *reinterpret_cast<float4*>(op + n + 4) = make_float4(x[4], x[5], x[6], x[7]);
+                            } else {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (n + i < P.n_valid) op[(long long)(n + i) * P.cstride] = x[i];
+                                for (int i = 0; i < 8; ++i)
+                                    if (n + i < P.n_valid) op[(long long)(n + i) * P.cstride] = x[i];
+                            }
                         } else {
                             uint4 pk;
                             __nv_bfloat162* ph = reinterpret_cast<__nv_bfloat162*>(&pk);
@@ -208,17 +216,25 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ 
 // A: bf16 [M][K] with row stride lda (elements, multiple of 8); wpacked: bf16 [Npad][Kpad] (Kpad multiple of 64, zero padded)
 int dense_tc_launch(const void* A, long long lda, int M, int K, const void* wpacked, int Npad, int Kpad, int n_valid, const float* bias,
                     int bias_mod, int act, const void* mask, long long ldm, int mask_mode, void* out, long long ldc, long long cstride,
-                    int out_f32, cudaStream_t st, const float* addend, long long addend_ld) {
+                    int out_f32, cudaStream_t st, const float* addend, long long addend_ld, int group_n, int group_k) {
     MRSSM_CHECK(A && wpacked && out && M > 0 && K > 0 && Npad % 16 == 0 && Kpad % 64 == 0 && lda % 8 == 0 && K % 8 == 0,
                 "dense_tc: bad arguments (M %d K %d Npad %d Kpad %d lda %lld)", M, K, Npad, Kpad, lda);
     MRSSM_CHECK(Npad <= 4096, "dense_tc: %d output columns exceed the bias table", Npad);
     MRSSM_CHECK(out_f32 || (ldc % 8 == 0 && cstride == 1), "dense_tc: bf16 output rows must be 16-byte aligned");
     DenseP P;
     P.M = M; P.K = K; P.Npad = Npad; P.n_valid = n_valid;
+    P.n_mtiles = (M + 127) / 128;
     P.BN = Npad <= 256 ? Npad : (Npad % 256 == 0 ? 256 : (Npad % 128 == 0 ? 128 : 64));
+    // few row tiles (the per-step rollout GEMMs: M = batch): narrower column tiles put the K loop on more SMs
+    while (P.BN > 64 && P.BN % 2 == 0 && (P.BN / 2) % 16 == 0 && Npad % (P.BN / 2) == 0 && P.n_mtiles * ((Npad + P.BN - 1) / P.BN) < 74) P.BN /= 2;
+    P.group_n = group_n > 0 ? group_n : 0; P.group_k = group_k;
+    if (P.group_n) {
+        MRSSM_CHECK(group_k > 0 && group_n % 16 == 0 && Npad % group_n == 0, "dense_tc: bad grouping (%d columns over %d inputs)", group_n, group_k);
+        while (group_n % P.BN != 0 && P.BN > 16) P.BN = (P.BN % 32 == 0) ? P.BN / 2 : 16;
+        MRSSM_CHECK(group_n % P.BN == 0 && Npad % P.BN == 0, "dense_tc: group of %d columns not tileable", group_n);
+    }
     MRSSM_CHECK(Npad % P.BN == 0 || Npad > 256, "dense_tc: %d columns not tileable", Npad);
     P.n_ntiles = (Npad + P.BN - 1) / P.BN;
-    P.n_mtiles = (M + 127) / 128;
     P.nkb = Kpad / 64;
     const int stage = 128 * 128 + P.BN * 128;
     P.NS = std::max(2, std::min(8, (200 * 1024) / stage));
@@ -226,6 +242,7 @@ int dense_tc_launch(const void* A, long long lda, int M, int K, const void* wpac
     P.ldc = ldc; P.cstride = cstride; P.ldm = ldm;
     P.out = out; P.mask = (const bf16*)mask; P.bias = bias;
     P.addend = addend; P.lda_add = addend_ld;
+    P.vec4 = out_f32 && cstride == 1 && ldc % 4 == 0 && ((uintptr_t)out & 15) == 0;
     CUtensorMap mA, mW;
     if (int rc = mrssm_tma_map_2d_sw128(&mA, A, K, M, lda * 2, 64, 128)) return rc;
     if (int rc = mrssm_tma_map_2d_sw128(&mW, wpacked, Kpad, Npad, (long long)Kpad * 2, 64, P.BN)) return rc;

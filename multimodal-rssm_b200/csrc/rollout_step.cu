@@ -54,10 +54,10 @@ __global__ void rstep_gate_fwd_kernel(mrssm_rollout_args a, int t, const float* 
     }
 }
 
-// o[b][hd*2S + c]: fc2 outputs of every head (bias included).  -> prior / expert / posterior statistics, samples (step 5 of
+// o[b][hd*hs + c], c < 2S: fc2 outputs of every head (bias included), row stride ldo.  -> prior / expert / posterior statistics, samples (step 5 of
 // the fused kernels: softplus + min_std, 1/sigma-weighted PoE over the subset of each state dimension, rsample)
-__global__ void rstep_heads_fwd_kernel(mrssm_rollout_args a, int t, const float* __restrict__ o) {
-    const int S = a.S, B = a.B, E = a.n_experts, ldo = (1 + E) * 2 * S;
+__global__ void rstep_heads_fwd_kernel(mrssm_rollout_args a, int t, const float* __restrict__ o, int ldo, int hs) {
+    const int S = a.S, B = a.B, E = a.n_experts;
     const long long total = (long long)B * S;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int b = (int)(i / S), s = (int)(i - (long long)b * S);
@@ -73,7 +73,7 @@ __global__ void rstep_heads_fwd_kernel(mrssm_rollout_args a, int t, const float*
             float sumT = 0.f, sumMT = 0.f;
             const unsigned mask = a.n_subsets ? a.subset_mask[a.dim_subset[s]] : 1u;
             for (int e = 1; e <= E; ++e) {
-                const float em = ob[e * 2 * S + s], es = softplusf_(ob[e * 2 * S + S + s]) + a.min_std;
+                const float em = ob[e * hs + s], es = softplusf_(ob[e * hs + S + s]) + a.min_std;
                 a.exp_means[e][off] = em;
                 a.exp_stds[e][off] = es;
                 if (mask & (1u << (e - 1))) {
@@ -97,17 +97,17 @@ __global__ void rstep_heads_fwd_kernel(mrssm_rollout_args a, int t, const float*
 }
 
 // backward of rstep_heads_fwd: upstream grads of the statistics / samples at step t plus the state-gradient carry from step
-// t + 1 (cgs, [B,S]) -> grads of every head's fc2 output, written as the bf16 GEMM operand d_o[hd][b][0..S2p)
+// t + 1 (cgs, [B,S]) -> grads of every head's fc2 output, written as the bf16 GEMM operand d_o[hd][b * ld + 0..S2p)
 struct HeadsBwdOut {
     bf16* d_o[MRSSM_MAX_HEADS];
 };
-__global__ void rstep_heads_bwd_kernel(mrssm_rollout_bwd_args g, int t, const float* __restrict__ cgs, HeadsBwdOut out, int S2p) {
+__global__ void rstep_heads_bwd_kernel(mrssm_rollout_bwd_args g, int t, const float* __restrict__ cgs, HeadsBwdOut out, int ld, int S2p) {
     const mrssm_rollout_args& a = g.f;
     const int S = a.S, B = a.B, E = a.n_experts;
     const long long total = (long long)B * S;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int b = (int)(i / S), s = (int)(i - (long long)b * S);
-        const long long off = ((long long)t * B + b) * S + s, ro = (long long)b * S2p;
+        const long long off = ((long long)t * B + b) * S + s, ro = (long long)b * ld;
         const float carry = cgs[i];
         float gps = g.g_prior_states ? g.g_prior_states[off] : 0.f;
         if (E == 0) gps += carry;
@@ -215,24 +215,26 @@ extern "C" int mrssm_rstep_gate_fwd(const mrssm_rollout_args* a, int32_t t, cons
     MRSSM_LAUNCH_CHECK();
     return 0;
 }
-extern "C" int mrssm_rstep_heads_fwd(const mrssm_rollout_args* a, int32_t t, const float* o, void* stream) {
-    MRSSM_CHECK(a && o && t >= 0 && t < a->T && a->S <= MRSSM_MAX_STATE, "rstep_heads_fwd: bad arguments");
+extern "C" int mrssm_rstep_heads_fwd(const mrssm_rollout_args* a, int32_t t, const float* o, int32_t ldo, int32_t head_stride, void* stream) {
+    MRSSM_CHECK(a && o && t >= 0 && t < a->T && a->S <= MRSSM_MAX_STATE && head_stride >= 2 * a->S && ldo >= (1 + a->n_experts) * head_stride,
+                "rstep_heads_fwd: bad arguments");
     MRSSM_CHECK(a->prior_states && a->prior_means && a->prior_stds && (a->det || a->eps_prior), "rstep_heads_fwd: null prior output / noise");
     MRSSM_CHECK(a->n_experts >= 0 && a->n_experts < MRSSM_MAX_HEADS && a->n_subsets >= 0 && a->n_subsets <= MRSSM_MAX_SUBSETS,
                 "rstep_heads_fwd: n_experts=%d n_subsets=%d unsupported", a->n_experts, a->n_subsets);
     for (int h = 1; h <= a->n_experts; ++h) MRSSM_CHECK(a->exp_means[h] && a->exp_stds[h], "rstep_heads_fwd: expert %d outputs missing", h);
     if (a->n_experts > 0)
         MRSSM_CHECK(a->post_states && a->post_means && a->post_stds && (a->det || a->eps_post), "rstep_heads_fwd: null posterior output / noise");
-    rstep_heads_fwd_kernel<<<blocks_for((long long)a->B * a->S), NT, 0, (cudaStream_t)stream>>>(*a, t, o);
+    rstep_heads_fwd_kernel<<<blocks_for((long long)a->B * a->S), NT, 0, (cudaStream_t)stream>>>(*a, t, o, ldo, head_stride);
     MRSSM_LAUNCH_CHECK();
     return 0;
 }
-extern "C" int mrssm_rstep_heads_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float* cgs, void* const* d_o, int32_t S2p, void* stream) {
-    MRSSM_CHECK(g && cgs && d_o && t >= 0 && t < g->f.T && S2p >= 2 * g->f.S, "rstep_heads_bwd: bad arguments");
+extern "C" int mrssm_rstep_heads_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float* cgs, void* const* d_o, int32_t ld, int32_t S2p,
+                                     void* stream) {
+    MRSSM_CHECK(g && cgs && d_o && t >= 0 && t < g->f.T && S2p >= 2 * g->f.S && ld >= S2p, "rstep_heads_bwd: bad arguments");
     HeadsBwdOut out;
     for (int h = 0; h < MRSSM_MAX_HEADS; ++h) out.d_o[h] = h <= g->f.n_experts ? (bf16*)d_o[h] : nullptr;
     for (int h = 0; h <= g->f.n_experts; ++h) MRSSM_CHECK(out.d_o[h], "rstep_heads_bwd: head %d output missing", h);
-    rstep_heads_bwd_kernel<<<blocks_for((long long)g->f.B * g->f.S), NT, 0, (cudaStream_t)stream>>>(*g, t, cgs, out, S2p);
+    rstep_heads_bwd_kernel<<<blocks_for((long long)g->f.B * g->f.S), NT, 0, (cudaStream_t)stream>>>(*g, t, cgs, out, ld, S2p);
     MRSSM_LAUNCH_CHECK();
     return 0;
 }

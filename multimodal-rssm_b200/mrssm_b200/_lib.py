@@ -37,7 +37,7 @@ class TcConvArgs(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_img", "Hl", "Wl", "Cl", "Hs", "Ws", "Cs", "ksz", "act", "mask_mode",
                                          "out_f32", "n_out_pad", "n_out_valid", "bias_mod", "cs_valid", "cl_valid")] + [
         ("large", T4), ("small", T4), ("mask", T4), ("wpacked", _vp), ("bias", _vp), ("dweight", _vp),
-        ("w_ss", C.c_int64), ("w_sl", C.c_int64), ("addend", _vp), ("addend_ld", C.c_int64)]
+        ("w_ss", C.c_int64), ("w_sl", C.c_int64), ("addend", _vp), ("addend_ld", C.c_int64), ("group_n", C.c_int32), ("group_k", C.c_int32)]
 
 
 class TV(C.Structure):
@@ -153,8 +153,8 @@ SYMBOLS = {
     "mrssm_rollout_bwd": [C.POINTER(RolloutBwdArgs), _vp],
     "mrssm_rstep_xin": [C.POINTER(RolloutArgs), _i32, _i32, _vp, _vp],
     "mrssm_rstep_gate_fwd": [C.POINTER(RolloutArgs), _i32, _vp, _vp, _vp, _vp],
-    "mrssm_rstep_heads_fwd": [C.POINTER(RolloutArgs), _i32, _vp, _vp],
-    "mrssm_rstep_heads_bwd": [C.POINTER(RolloutBwdArgs), _i32, _vp, C.POINTER(_vp), _i32, _vp],
+    "mrssm_rstep_heads_fwd": [C.POINTER(RolloutArgs), _i32, _vp, _i32, _i32, _vp],
+    "mrssm_rstep_heads_bwd": [C.POINTER(RolloutBwdArgs), _i32, _vp, C.POINTER(_vp), _i32, _i32, _vp],
     "mrssm_rstep_gate_bwd": [C.POINTER(RolloutBwdArgs), _i32, _vp, _vp, _vp, _vp, _vp, _vp],
     "mrssm_rstep_xin_bwd": [C.POINTER(RolloutBwdArgs), _i32, _vp, _i32, _vp, _vp],
     "mrssm_add2": [_vp, _vp, _i64, _vp, _vp],

@@ -378,63 +378,98 @@ def set_rollout_step(on):
     _STATE["rollout_step"] = bool(on)
 
 
-def _gemm_down(M, x_ptr, ldx, Kp, wp, bias, N, out_ptr, ldo, out_f32=0, act=0, addend=None, addend_ld=0, tag="step_gemm"):
-    """y[M, N] = act(x[M, Kp] W^T + bias (+ addend)); x bf16 rows (stride ldx), W packed mode 0, y bf16 or fp32 rows (stride ldo)."""
-    Np = wp.shape[1]
+def _gemm_down(M, x_ptr, ldx, Kp, wp, Np, bias, N, out_ptr, ldo, out_f32=0, act=0, addend=None, addend_ld=0, group=None,
+               tag="step_gemm"):
+    """y[M, N] = act(x[M, Kp] W^T + bias (+ addend)); x bf16 rows (stride ldx), W packed mode 0 with Np rows, y bf16 or fp32 rows
+    (stride ldo).  group = (columns, inputs) per block of a block-diagonal W."""
     a = _tc_args((M, 1, 1, Kp, 1, 1, Np, 1), _row_t4(x_ptr, ldx), _row_t4(out_ptr, ldo), act, None, 0, out_f32, Np, N, 0,
                  wpacked=L.ptr(wp), bias=L.ptr(bias))
     if addend is not None:
         a.addend, a.addend_ld = addend, addend_ld
-    L.call("mrssm_tc_conv_down", C.byref(a), tag=tag if L.profile is not None else None,
-           work=dict(flops=2.0 * M * Kp * N, bytes=2.0 * (M * Kp + N * Kp) + (4.0 if out_f32 else 2.0) * M * N) if L.profile is not None else None)
+    if group is not None:
+        a.group_n, a.group_k = group
+    prof = L.profile is not None
+    kk = group[1] if group else Kp
+    L.call("mrssm_tc_conv_down", C.byref(a), tag=tag if prof else None,
+           work=dict(flops=2.0 * M * kk * N, bytes=2.0 * (M * Kp + N * kk) + (4.0 if out_f32 else 2.0) * M * N) if prof else None)
 
 
-def _gemm_up(M, dy_ptr, ldy, Np_dy, wp, K, out_ptr, ldo, out_f32=0, mask_ptr=None, ldm=0, mask_mode=0, tag="step_dgrad"):
-    """dx[M, K] = (dy[M, Np_dy] W) * act'(mask); dy bf16 rows, W packed mode 1, dx bf16 or fp32 rows."""
-    Kp_out = wp.shape[1]
+def _gemm_up(M, dy_ptr, ldy, Np_dy, wp, Kp_out, K, out_ptr, ldo, out_f32=0, mask_ptr=None, ldm=0, mask_mode=0, group=None,
+             tag="step_dgrad"):
+    """dx[M, K] = (dy[M, Np_dy] W) * act'(mask); dy bf16 rows, W packed mode 1 with Kp_out rows, dx bf16 or fp32 rows."""
     mask = _row_t4(mask_ptr, ldm) if mask_ptr is not None else None
     a = _tc_args((M, 1, 1, Kp_out, 1, 1, Np_dy, 1), _row_t4(out_ptr, ldo), _row_t4(dy_ptr, ldy), 0, mask, mask_mode, out_f32, Kp_out, K, 0,
                  wpacked=L.ptr(wp), bias=None)
-    L.call("mrssm_tc_conv_up", C.byref(a), tag=tag if L.profile is not None else None,
-           work=dict(flops=2.0 * M * Np_dy * K, bytes=2.0 * (M * Np_dy + K * Np_dy) + (4.0 if out_f32 else 2.0) * M * K) if L.profile is not None else None)
+    if group is not None:
+        a.group_n, a.group_k = group
+    prof = L.profile is not None
+    kk = group[1] if group else Np_dy
+    L.call("mrssm_tc_conv_up", C.byref(a), tag=tag if prof else None,
+           work=dict(flops=2.0 * M * kk * K, bytes=2.0 * (M * Np_dy + K * kk) + (4.0 if out_f32 else 2.0) * M * K) if prof else None)
 
 
-def _rollout_steps_fwd(a, spec, E, T, B, w_sa, b_sa, w_ih, w_hh, b_ih, b_hh, heads, emb_pre, stash, dev):
+def _step_head_weights(spec, heads, has_pre, dev):
+    """All heads' fc1 / fc2 weights stacked for merged launches (cached per weight version): fc1 over the belief columns as one
+    GEMM per chunk of heads (<= 4096 output columns), fc2 and its dgrad as block-diagonal GEMMs (one block per head)."""
+    D, S, H = spec.D, spec.S, spec.H
+    NH, S2p = len(heads), pad16(2 * S)
+    key = ("step_heads", heads[0][0].data_ptr(), NH)
+    ver = (_STATE["wversion"],) + tuple(p._version for h in heads for p in h) + tuple(has_pre)
+    hit = _wcache.get(key)
+    if hit is None or hit[0] != ver:
+        per = max(1, 4096 // H)
+        chunks = [(c0, min(NH, c0 + per)) for c0 in range(0, NH, per)]
+        z = lambda n: torch.zeros(n, device=dev, dtype=torch.float32)
+        w1f = [torch.cat([packed_cols(heads[h][0], 0, D, 0)[0] for h in range(c0, c1)]) for c0, c1 in chunks]
+        b1 = [torch.cat([z(H) if has_pre[h] else heads[h][1].detach() for h in range(c0, c1)]) for c0, c1 in chunks]
+        w2f = torch.cat([packed(heads[h][2], 0, S2p, H)[0] for h in range(NH)])
+        b2 = torch.cat([torch.cat([heads[h][3].detach(), z(S2p - 2 * S)]) for h in range(NH)])
+        w2b = [torch.cat([packed(heads[h][2], 1, S2p, H)[0] for h in range(c0, c1)]) for c0, c1 in chunks]
+        w1cat = torch.empty(NH * H, D, device=dev, dtype=torch.float32)
+        for hd in range(NH):
+            w1 = heads[hd][0]
+            L.call("mrssm_copy2d", L.ptr(w1), H, D, w1.shape[1], w1cat.data_ptr() + 4 * hd * H * D)
+        w1b = tc_pack_weight(w1cat.reshape(NH * H, D, 1, 1), 1, NH * H, D)           # dh = [du_0 | du_1 | ..] [W1_0[:, :D]; W1_1[:, :D]; ..]
+        hit = (ver, dict(chunks=chunks, w1f=w1f, b1=b1, w2f=w2f, b2=b2, w2b=w2b, w1b=w1b))
+        _wcache[key] = hit
+    return hit[1]
+
+
+def _rollout_steps_fwd(a, spec, E, T, B, w_sa, b_sa, w_ih, w_hh, b_ih, b_hh, heads, has_pre, pre_cat, stash, dev):
     """The T steps of transition_model.py:226-270 as per-step tcgen05 GEMMs + the kernels of csrc/rollout_step.cu.  Fills the
     output tensors and the stash named in `a`; returns the extra stash tensors [hb_all, xin_all]."""
     D, S, H, A = spec.D, spec.S, spec.H, spec.A
-    NH = 1 + E
+    NH, S2p = 1 + E, pad16(2 * S)
     KX = pad8(S + A)
     nb16 = lambda *sh: torch.empty(*sh, device=dev, dtype=torch.bfloat16)
     xin_all = nb16(T, B, KX)
     x_all = stash["x"] if stash is not None else nb16(1, B, D)
-    u_all = stash["u"] if stash is not None else [nb16(1, B, H) for _ in range(NH)]
+    u_cat = stash["u"][0] if stash is not None else nb16(1, B, NH * H)
     hb_all = nb16(T + 1, B, D)
     keep_all = stash is not None
     L.call("mrssm_tc_to_bf16", C.byref(_row_t4(a.prev_belief, D)), B, 1, 1, D, D, 1.0, hb_all.data_ptr())
     gi = torch.empty(B, 3 * D, device=dev, dtype=torch.float32)
     gh = torch.empty(B, 3 * D, device=dev, dtype=torch.float32)
-    o_cat = torch.empty(B, NH * 2 * S, device=dev, dtype=torch.float32)
+    o_cat = torch.empty(B, NH * S2p, device=dev, dtype=torch.float32)
     wp_sa = packed(w_sa, 0, pad16(D), KX)
     wp_ih = packed(w_ih, 0, pad16(3 * D), D)
     wp_hh = packed(w_hh, 0, pad16(3 * D), D)
-    wp_1 = [packed_cols(hd[0], 0, D, 0) for hd in heads]
-    wp_2 = [packed(hd[2], 0, pad16(2 * S), H) for hd in heads]
+    hw = _step_head_weights(spec, heads, has_pre, dev)
     for t in range(T):
         ts = t if keep_all else 0
         L.call("mrssm_rstep_xin", C.byref(a), t, KX, xin_all[t].data_ptr())
-        _gemm_down(B, xin_all[t].data_ptr(), KX, KX, wp_sa, b_sa, D, x_all[ts].data_ptr(), D, act=spec.act, tag="step_fc_embed")
-        _gemm_down(B, x_all[ts].data_ptr(), D, D, wp_ih, b_ih, 3 * D, gi.data_ptr(), 3 * D, out_f32=1, tag="step_gru_ih")
-        _gemm_down(B, hb_all[t].data_ptr(), D, D, wp_hh, b_hh, 3 * D, gh.data_ptr(), 3 * D, out_f32=1, tag="step_gru_hh")
+        _gemm_down(B, xin_all[t].data_ptr(), KX, KX, wp_sa, D, b_sa, D, x_all[ts].data_ptr(), D, act=spec.act, tag="step_fc_embed")
+        _gemm_down(B, x_all[ts].data_ptr(), D, D, wp_ih, 3 * D, b_ih, 3 * D, gi.data_ptr(), 3 * D, out_f32=1, tag="step_gru_ih")
+        _gemm_down(B, hb_all[t].data_ptr(), D, D, wp_hh, 3 * D, b_hh, 3 * D, gh.data_ptr(), 3 * D, out_f32=1, tag="step_gru_hh")
         L.call("mrssm_rstep_gate_fwd", C.byref(a), t, gi.data_ptr(), gh.data_ptr(), hb_all[t + 1].data_ptr())
-        for hd in range(NH):
-            w1, b1, w2, b2 = heads[hd]
-            pre = emb_pre[hd]
-            _gemm_down(B, hb_all[t + 1].data_ptr(), D, D, wp_1[hd], None if pre is not None else b1, H, u_all[hd][ts].data_ptr(), H,
-                       act=spec.act, addend=None if pre is None else pre.data_ptr() + 4 * t * B * H, addend_ld=H, tag="step_fc1")
-            _gemm_down(B, u_all[hd][ts].data_ptr(), H, H, wp_2[hd], b2, 2 * S, o_cat.data_ptr() + 4 * hd * 2 * S, NH * 2 * S, out_f32=1,
-                       tag="step_fc2")
-        L.call("mrssm_rstep_heads_fwd", C.byref(a), t, o_cat.data_ptr())
+        for ci, (c0, c1) in enumerate(hw["chunks"]):
+            n = (c1 - c0) * H
+            add = None if pre_cat is None else pre_cat.data_ptr() + 4 * (t * B * NH * H + c0 * H)
+            _gemm_down(B, hb_all[t + 1].data_ptr(), D, D, hw["w1f"][ci], n, hw["b1"][ci], n, u_cat[ts].data_ptr() + 2 * c0 * H, NH * H,
+                       act=spec.act, addend=add, addend_ld=NH * H, tag="step_fc1")
+        _gemm_down(B, u_cat[ts].data_ptr(), NH * H, NH * H, hw["w2f"], NH * S2p, hw["b2"], NH * S2p, o_cat.data_ptr(), NH * S2p, out_f32=1,
+                   group=(S2p, H), tag="step_fc2")
+        L.call("mrssm_rstep_heads_fwd", C.byref(a), t, o_cat.data_ptr(), NH * S2p, S2p)
     return [hb_all, xin_all]
 
 
@@ -450,9 +485,7 @@ def _rollout_steps_bwd(ctx, ins, embs, outs, st, gouts):
     dev = actions.device
     w_sa, b_sa, w_ih, w_hh, b_ih, b_hh = params[:N_FIXED_PARAMS]
     heads = [params[N_FIXED_PARAMS + 4 * i: N_FIXED_PARAMS + 4 * i + 4] for i in range(NH)]
-    x_all, r_, z_, n_, ghn_ = st[:5]
-    u_all = list(st[5:5 + NH])
-    hb_all, xin_all = st[5 + NH], st[6 + NH]
+    x_all, r_, z_, n_, ghn_, u_cat, hb_all, xin_all = st
     gouts = [None if g_ is None else _f32c(g_) for g_ in gouts]
     KX, S2p = xin_all.shape[-1], pad16(2 * S)
 
@@ -477,36 +510,31 @@ def _rollout_steps_bwd(ctx, ins, embs, outs, st, gouts):
     nb16 = lambda *sh: torch.empty(*sh, device=dev, dtype=torch.bfloat16)
     g_actions = f32(T, B, A)
     g.g_actions = L.ptr(g_actions)
-    d_o = [nb16(T, B, S2p) for _ in range(NH)]
+    d_o = nb16(T, B, NH * S2p)
     du_all = nb16(T, B, NH * H)
     d_gi, d_gh, d_xpre = nb16(T, B, 3 * D), nb16(T, B, 3 * D), nb16(T, B, D)
     dh_heads, carry_b, dxin = f32(B, D), torch.zeros(B, D, device=dev), f32(B, S + A)
     carry_a, cgs = torch.zeros(B, D, device=dev), torch.zeros(B, S, device=dev)
-    # dgrad-type packings; the belief columns of every head's fc1 stacked along K: dh = [du_0 | du_1 | ..] [W1_0[:, :D]; W1_1[:, :D]; ..]
-    w1cat = f32(NH * H, D)
-    for hd in range(NH):
-        w1 = heads[hd][0]
-        L.call("mrssm_copy2d", L.ptr(w1), H, D, w1.shape[1], w1cat.data_ptr() + 4 * hd * H * D)
-    wp_1cat = tc_pack_weight(w1cat.reshape(NH * H, D, 1, 1), 1, NH * H, D)
-    del w1cat
-    wp_2 = [packed(hd[2], 1, S2p, H) for hd in heads]
+    hw = _step_head_weights(spec, heads, [hd > 0 and spec.expert_has_emb[hd - 1] for hd in range(NH)], dev)
     wp_ih, wp_hh = packed(w_ih, 1, pad16(3 * D), D), packed(w_hh, 1, pad16(3 * D), D)
     wp_sa = packed(w_sa, 1, pad16(D), KX)
+    KXo = wp_sa.shape[1]
     d_o_ptrs = (C.c_void_p * L.MAX_HEADS)()
     for t in reversed(range(T)):
         for hd in range(NH):
-            d_o_ptrs[hd] = d_o[hd][t].data_ptr()
-        L.call("mrssm_rstep_heads_bwd", C.byref(g), t, cgs.data_ptr(), d_o_ptrs, S2p)
-        for hd in range(NH):
-            _gemm_up(B, d_o[hd][t].data_ptr(), S2p, S2p, wp_2[hd], H, du_all[t].data_ptr() + 2 * hd * H, NH * H,
-                     mask_ptr=u_all[hd][t].data_ptr(), ldm=H, mask_mode=spec.act, tag="step_fc2_dgrad")
-        _gemm_up(B, du_all[t].data_ptr(), NH * H, NH * H, wp_1cat, D, dh_heads.data_ptr(), D, out_f32=1, tag="step_fc1_dgrad")
+            d_o_ptrs[hd] = d_o[t].data_ptr() + 2 * hd * S2p
+        L.call("mrssm_rstep_heads_bwd", C.byref(g), t, cgs.data_ptr(), d_o_ptrs, NH * S2p, S2p)
+        for ci, (c0, c1) in enumerate(hw["chunks"]):
+            _gemm_up(B, d_o[t].data_ptr() + 2 * c0 * S2p, NH * S2p, (c1 - c0) * S2p, hw["w2b"][ci], (c1 - c0) * H, (c1 - c0) * H,
+                     du_all[t].data_ptr() + 2 * c0 * H, NH * H, mask_ptr=u_cat[t].data_ptr() + 2 * c0 * H, ldm=NH * H, mask_mode=spec.act,
+                     group=(H, S2p), tag="step_fc2_dgrad")
+        _gemm_up(B, du_all[t].data_ptr(), NH * H, NH * H, hw["w1b"], D, D, dh_heads.data_ptr(), D, out_f32=1, tag="step_fc1_dgrad")
         L.call("mrssm_rstep_gate_bwd", C.byref(g), t, dh_heads.data_ptr(), carry_a.data_ptr(), carry_b.data_ptr(), d_gi[t].data_ptr(),
                d_gh[t].data_ptr())
-        _gemm_up(B, d_gi[t].data_ptr(), 3 * D, 3 * D, wp_ih, D, d_xpre[t].data_ptr(), D, mask_ptr=x_all[t].data_ptr(), ldm=D, mask_mode=spec.act,
-                 tag="step_ih_dgrad")
-        _gemm_up(B, d_gh[t].data_ptr(), 3 * D, 3 * D, wp_hh, D, carry_b.data_ptr(), D, out_f32=1, tag="step_hh_dgrad")
-        _gemm_up(B, d_xpre[t].data_ptr(), D, D, wp_sa, S + A, dxin.data_ptr(), S + A, out_f32=1, tag="step_sa_dgrad")
+        _gemm_up(B, d_gi[t].data_ptr(), 3 * D, 3 * D, wp_ih, D, D, d_xpre[t].data_ptr(), D, mask_ptr=x_all[t].data_ptr(), ldm=D,
+                 mask_mode=spec.act, tag="step_ih_dgrad")
+        _gemm_up(B, d_gh[t].data_ptr(), 3 * D, 3 * D, wp_hh, D, D, carry_b.data_ptr(), D, out_f32=1, tag="step_hh_dgrad")
+        _gemm_up(B, d_xpre[t].data_ptr(), D, D, wp_sa, KXo, S + A, dxin.data_ptr(), S + A, out_f32=1, tag="step_sa_dgrad")
         L.call("mrssm_rstep_xin_bwd", C.byref(g), t, dxin.data_ptr(), S + A, cgs.data_ptr())
     g_prev_belief = f32(B, D)
     L.call("mrssm_add2", carry_a.data_ptr(), carry_b.data_ptr(), B * D, g_prev_belief.data_ptr())
@@ -525,7 +553,7 @@ def _rollout_steps_bwd(ctx, ins, embs, outs, st, gouts):
     for hd in range(NH):
         w1, b1, w2, b2 = heads[hd]
         ld = w1.shape[1]
-        wgrad(d_o[hd].data_ptr(), S2p, 2 * S, u_all[hd].data_ptr(), H, H, R, L.ptr(grad_buf(w2)), H, grad_buf(b2))
+        wgrad(d_o.data_ptr() + 2 * hd * S2p, NH * S2p, 2 * S, u_cat.data_ptr() + 2 * hd * H, NH * H, H, R, L.ptr(grad_buf(w2)), H, grad_buf(b2))
         du_ptr = du_all.data_ptr() + 2 * hd * H
         gw1 = grad_buf(w1)
         wgrad(du_ptr, NH * H, H, hb_all[1].data_ptr(), D, D, R, L.ptr(gw1), ld, grad_buf(b1))
@@ -598,6 +626,10 @@ class RolloutFn(Function):
             a.w_sa, a.b_sa, a.w_ih, a.b_ih, a.w_hh, a.b_hh = (L.ptr(wsaT), L.ptr(b_sa), L.ptr(wihT), L.ptr(b_ih),
                                                               L.ptr(whhT), L.ptr(b_hh))
         emb_pre = [None] * (1 + E)
+        has_pre = [hd > 0 and bool(spec.expert_has_emb[hd - 1]) for hd in range(1 + E)]
+        # step path: the hoisted embedding halves of all heads side by side (zero columns for heads without an embedding), the
+        # addend of the merged fc1 GEMM
+        pre_cat = torch.zeros(T, B, (1 + E) * H, device=dev, dtype=torch.float32) if (use_step and any(has_pre)) else None
         ei = 0
         for hd in range(1 + E):
             w1, b1, w2, b2 = heads[hd]
@@ -613,18 +645,22 @@ class RolloutFn(Function):
                 ei += 1
                 Em = emb.shape[-1]
                 assert ld == D + Em, (ld, D, Em)
-                pre = torch.empty(T, B, H, device=dev, dtype=torch.float32)
+                if pre_cat is not None:
+                    pre, pre_ptr, pre_ld = pre_cat, pre_cat.data_ptr() + 4 * hd * H, (1 + E) * H
+                else:
+                    pre = torch.empty(T, B, H, device=dev, dtype=torch.float32)
+                    pre_ptr, pre_ld = pre.data_ptr(), H
                 if bf16_mode() and Em >= 64:
                     # hoisted embedding half of fc1 as a tcgen05 GEMM: bf16 operands, fp32 accumulate and output
                     Emp, Hp = pad8(Em), pad16(H)
                     eb = pl_import(L.nhwc(emb, 1, 1, Em), T * B, 1, 1, Em, Emp, L.NHWC, dev)[0]
-                    tc_conv_down((T * B, 1, 1, Emp, 1, 1, Hp, 1), L.T4(eb.data_ptr(), Emp, 0, 0, 1), L.nhwc(pre, 1, 1, H),
+                    tc_conv_down((T * B, 1, 1, Emp, 1, 1, Hp, 1), L.T4(eb.data_ptr(), Emp, 0, 0, 1), L.T4(pre_ptr, pre_ld, 0, 0, 1),
                                  packed_cols(w1, D, Em, 0), b1, H, out_f32=1, valid=(H, Em))
                     del eb
                 else:
-                    dense_fwd(L.ptr(emb), Em, T * B, Em, _off(w1, D), ld, H, L.ptr(b1), 0, L.ptr(pre), H)
+                    dense_fwd(L.ptr(emb), Em, T * B, Em, _off(w1, D), ld, H, L.ptr(b1), 0, pre_ptr, pre_ld)
                 emb_pre[hd] = pre
-                a.emb_pre[hd] = L.ptr(pre)
+                a.emb_pre[hd] = pre_ptr
                 a.b1[hd] = None
             else:
                 assert ld == D
@@ -646,7 +682,7 @@ class RolloutFn(Function):
         if need_grad and use_step:
             # bf16 stash of the step path: x and u are the GEMM operands themselves; + the bf16 beliefs and [state, action] rows
             nb16 = lambda *sh: torch.empty(*sh, device=dev, dtype=torch.bfloat16)
-            stash = dict(x=nb16(T, B, D), r=new(D), z=new(D), n=new(D), ghn=new(D), u=[nb16(T, B, H) for _ in range(1 + E)])
+            stash = dict(x=nb16(T, B, D), r=new(D), z=new(D), n=new(D), ghn=new(D), u=[nb16(T, B, (1 + E) * H)])
             a.st_r, a.st_z, a.st_n, a.st_ghn = [L.ptr(stash[k]) for k in ("r", "z", "n", "ghn")]
         elif need_grad:
             stash = dict(x=new(D), r=new(D), z=new(D), n=new(D), ghn=new(D), u=[new(H) for _ in range(1 + E)])
@@ -668,7 +704,7 @@ class RolloutFn(Function):
             L.call("mrssm_rollout_tc_fwd", C.byref(a), L.ptr_any(tc_plan), L.ptr_any(tc_packed),
                    tag="observe" if observe else "imagine", work=work)
         elif use_step:
-            extra = _rollout_steps_fwd(a, spec, E, T, B, w_sa, b_sa, w_ih, w_hh, b_ih, b_hh, heads, emb_pre, stash, dev)
+            extra = _rollout_steps_fwd(a, spec, E, T, B, w_sa, b_sa, w_ih, w_hh, b_ih, b_hh, heads, has_pre, pre_cat, stash, dev)
         else:
             L.call("mrssm_rollout_fwd", C.byref(a), tag="observe" if observe else "imagine", work=work)
         del keep
