@@ -309,8 +309,8 @@ def profile_one_step(model, D):
 
 
 def measured_traffic(key):
-    """DRAM bytes per launch of a kernel from the committed `ncu --set full` capture (profiles/r01_traffic.json), or None."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """DRAM bytes per launch of a kernel from the committed `ncu --set full` capture (profiles/r02_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:
