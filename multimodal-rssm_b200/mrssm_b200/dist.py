@@ -24,8 +24,10 @@ class DataParallel:
     on the compute stream and runs it on its own stream, under the rest of backward).  ``all_reduce_grads`` launches what is
     left and makes the compute stream wait for all of it before the fused clip + Adam step."""
 
-    def __init__(self, model, overlap=True):
+    def __init__(self, model, overlap=None):
         assert dist.is_initialized()
+        if overlap is None:          # MRSSM_DP_OVERLAP=0: one all-reduce of the whole buffer after backward (A/B switch for measurements)
+            overlap = os.environ.get("MRSSM_DP_OVERLAP", "1") != "0"
         self.world = dist.get_world_size()
         self.model = model
         self.overlap = overlap
