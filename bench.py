@@ -461,6 +461,27 @@ def run_ours(args):
     dom_key = max(agg, key=lambda k: agg[k]["ms"])
     roof = roofline_of(dom_key, agg[dom_key], pk, total_ms)
     rollout_roof = {k: roofline_of(k, agg[k], pk, total_ms) for k in ("rollout_fwd:observe", "rollout_bwd:observe", "rollout_tc_fwd:observe", "rollout_tc_bwd:observe") if k in agg}
+    # The recurrence is serial: T-1 dependent steps, each a fixed chain of tcgen05.mma instructions issued by one thread.  The floor
+    # below is that chain at the tensor pipe's measured issue rate and nothing else (profiles/micro/umma_rate_tight.txt: 56 cycles
+    # per M=64, N=112 MMA; 263 MMAs per forward step, 175 per BPTT step for the 4-head model) - what the kernel would
+    # take if epilogues, shared-memory traffic and the weight stream were free.
+    sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
+    for k, n_mma in (("rollout_tc_fwd:observe", 263), ("rollout_tc_bwd:observe", 175)):
+        if k in rollout_roof and model_of(args)["belief"] == 200 and args.fusion == "MoPoE":
+            steps_t = args.chunk - 1
+            floor = n_mma * 56.0 / (sm_hz * 1e6) * steps_t * 1e3
+            rollout_roof[k]["serial"] = {"dependent_steps": steps_t, "us_per_step": rollout_roof[k]["launch_ms"] / steps_t * 1e3,
+                                         "mma_per_step": n_mma, "mma_issue_floor_ms": floor,
+                                         "frac_of_floor": floor / rollout_roof[k]["launch_ms"]}
+    step_keys = [k for k in agg if k.startswith(("rstep_", "tc_conv_down:step_", "tc_conv_up:step_")) or k == "add2"]
+    if step_keys:       # large-model rollout (config 5): per-step launches, launch-latency-bound by construction
+        ms_r = sum(agg[k]["ms"] for k in step_keys)
+        n_r = sum(agg[k]["n"] for k in step_keys)
+        rollout_roof["rollout_step(all launches)"] = {
+            "bound": "latency", "ms_per_train_step": ms_r, "launches": n_r, "us_per_launch": ms_r / n_r * 1e3,
+            "share_of_step": ms_r / total_ms, "dependent_steps": args.chunk - 1,
+            "algorithmic_flops": sum(agg[k]["flops"] for k in step_keys),
+            "achieved_tflops": sum(agg[k]["flops"] for k in step_keys) / (ms_r * 1e-3) / 1e12, "peak_tflops": pk["tf_sust"]}
     top = sorted(((k, d["ms"], d["n"]) for k, d in agg.items()), key=lambda x: -x[1])[:60]
 
     cpu = same_box = None
