@@ -337,6 +337,58 @@ int mrssm_rstep_gate_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float
 int mrssm_rstep_xin_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float* dxin, int32_t ld, float* cgs, void* stream);
 int mrssm_add2(const float* x, const float* y, int64_t n, float* out, void* stream);
 
+/* ---- the shipped YAML's remaining layers: exact fp32 kernels on NCHW tensors --------------------------------
+ * General 2-d convolution without bias — rectangular kernel, any stride / zero padding: nn.Conv2d of SoundEncoder_v2 /
+ * SoundDecoder_v2.out (encoder.py:661-721, observation_model.py:420-472), nn.Conv1d k1 (H = L, W = 1), and the bias-free
+ * Conv2d / ConvTranspose2d of the BatchNorm image stacks (encoder.py:324-337, observation_model.py:75-86).
+ *   x [N,Cin,H,W], w [Cout,Cin,KH,KW], y [N,Cout,Ho,Wo], Ho = (H + 2 PH - KH) / SH + 1.
+ *   fwd:   y  = conv(x, w)                     (reads x, w; writes y)
+ *   dgrad: dx = conv_transpose(y, w)           (reads y as the output gradient, w; writes dx)
+ *   wgrad: dw += correlation(x, y)             (reads x and y as the output gradient; ACCUMULATES into dw)
+ * nn.ConvTranspose2d(weight [Cin_T, Cout_T, KH, KW]) is the same geometry with the roles swapped: forward = dgrad with
+ * y := its input, dx := its output; its input gradient = fwd; its weight gradient = wgrad with x := the output gradient. */
+typedef struct mrssm_gconv_args {
+    int32_t N, Cin, H, W, Cout, KH, KW, SH, SW, PH, PW, Ho, Wo;
+    const float* x;
+    const float* w;
+    float* y;
+    float* dx;
+    float* dw;
+} mrssm_gconv_args;
+int mrssm_gconv_fwd(const mrssm_gconv_args* a, void* stream);
+int mrssm_gconv_dgrad(const mrssm_gconv_args* a, void* stream);
+int mrssm_gconv_wgrad(const mrssm_gconv_args* a, void* stream);
+
+/* nn.BatchNorm2d (instance = 0: one mean / biased variance per channel over (n, h, w)) and nn.InstanceNorm2d / 1d (instance = 1: per
+ * (n, c) plane) with affine parameters, x / y [N,C,HW] fp32, optional fused ReLU (the Conv - BatchNorm - ReLU triples).
+ *   batch_stats = 1 (train mode; InstanceNorm without tracked statistics always): statistics of this batch are written to
+ *     mean / var ([C] or [N*C]) and, when running_mean / running_var are given, those move by `momentum` towards the batch mean /
+ *     UNBIASED variance (InstanceNorm: averaged over the N planes) — torch.nn.functional.batch_norm / instance_norm semantics.
+ *   batch_stats = 0 (eval mode): normalise with running_mean / running_var.
+ * bwd: g = gradient of y -> dx; sum_g / sum_gx: scratch of one float per group; dgamma / dbeta ([C], may be NULL) are ACCUMULATED. */
+typedef struct mrssm_norm_args {
+    int32_t N, C, HW, instance, batch_stats, relu;
+    float eps, momentum;
+    const float* x;
+    float* y;
+    const float* gamma;
+    const float* beta;
+    float* mean;
+    float* var;
+    float* running_mean;
+    float* running_var;
+} mrssm_norm_args;
+int mrssm_norm_fwd(const mrssm_norm_args* a, void* stream);
+int mrssm_norm_bwd(const mrssm_norm_args* a, const float* g, float* sum_g, float* sum_gx, float* dgamma, float* dbeta, float* dx, void* stream);
+
+/* nn.GLU(dim=1): x [N,2C,L] -> y [N,C,L] = x[:, :C] * sigmoid(x[:, C:]) and its backward (encoder.py:672-700). */
+int mrssm_glu_fwd(const float* x, int64_t N, int32_t C, int32_t L, float* y, void* stream);
+int mrssm_glu_bwd(const float* x, const float* g, int64_t N, int32_t C, int32_t L, float* dx, void* stream);
+/* per-channel bias of an NCHW tensor (the last, biased ConvTranspose2d of the BatchNorm decoder, observation_model.py:85) and
+ * its gradient, ACCUMULATED into dbias [C]. */
+int mrssm_chan_bias_fwd(const float* x, int64_t N, int32_t C, int32_t HW, const float* bias, float* y, void* stream);
+int mrssm_chan_bias_bwd(const float* g, int64_t N, int32_t C, int32_t HW, float* dbias, void* stream);
+
 /* ---- latent part of the ELBO -------------------------------------------------------------------
  * Replaces _get_posterior_states (MRSSM_PoE/algo.py:63-68, MRSSM_MoPoE/algo.py:62-67, base/algo.py:
  * 157-163), _calc_kl (base/algo.py:75-94), _calc_mopoe_kl (MRSSM_MoPoE/algo.py:110-137) and the

@@ -1,0 +1,459 @@
+// Exact fp32 kernels for the layers of the reference's SHIPPED YAML that the tcgen05 conv stacks do not cover:
+//   * general 2-d convolution on NCHW tensors — rectangular kernels, any stride / padding, no bias — in its three roles
+//     (forward, input gradient, weight gradient).  nn.ConvTranspose2d is the same three kernels with the roles of input
+//     and output swapped.  Used by SoundEncoder_v2 / SoundDecoder_v2 (encoder.py:661-721, observation_model.py:420-472:
+//     kernels 3x9, 4x8, 3x4, 4x4, 7x7, Conv1d k1) and by the BatchNorm variants of ImageEncoder / ImageDecoder
+//     (encoder.py:324-337, observation_model.py:75-86: Conv / ConvT without bias followed by BatchNorm2d + ReLU);
+//   * nn.BatchNorm2d and nn.InstanceNorm2d / 1d (affine, running statistics) forward / backward, optional fused ReLU;
+//   * nn.GLU(dim=1) forward / backward.
+// The convolutions are tiled implicit GEMMs on the CUDA cores (64 x 64 x 16 tiles, 4 x 4 outputs per thread): exact fp32,
+// the first correct version of these layers; they are not on the benchmarked path (BASELINE configs carry no sound / BatchNorm).
+#include <algorithm>
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+
+struct GC {
+    int N, Cin, H, W, Cout, KH, KW, SH, SW, PH, PW, Ho, Wo;
+    const float* x;      // [N,Cin,H,W]
+    const float* w;      // [Cout,Cin,KH,KW]
+    const float* dy;     // [N,Cout,Ho,Wo]
+    float* out;
+    long long M, K, kchunk;
+    int Ncols;
+};
+
+// MODE 0: y = conv(x, w)          M = N*Ho*Wo, cols = Cout,          K = Cin*KH*KW
+// MODE 1: dx = conv^T(dy, w)      M = N*H*W,   cols = Cin,           K = Cout*KH*KW
+// MODE 2: dw += dy^T im2col(x)    M = Cout,    cols = Cin*KH*KW,     K = N*Ho*Wo (split over grid.z, atomics)
+template <int MODE>
+__global__ void __launch_bounds__(NT) gconv_kernel(const GC g) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x, kk = tid & 15, r0 = tid >> 4;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    long long kbeg = 0, kend = g.K;
+    if (MODE == 2) {
+        kbeg = (long long)blockIdx.z * g.kchunk;
+        kend = kbeg + g.kchunk < g.K ? kbeg + g.kchunk : g.K;
+    }
+    const int KHW = g.KH * g.KW, HoWo = g.Ho * g.Wo, HW = g.H * g.W;
+
+    // per-thread decode of its 4 A rows and 4 B columns (fixed over the K loop)
+    int a_n[4], a_a[4], a_b[4];
+    bool a_ok[4];
+    int b_c[4], b_kh[4], b_kw[4];
+    bool b_ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const long long m = m0 + r0 + 16 * j;
+        a_ok[j] = m < g.M;
+        a_n[j] = a_a[j] = a_b[j] = 0;
+        if (a_ok[j]) {
+            if (MODE == 0) {
+                const int n = (int)(m / HoWo), r = (int)(m - (long long)n * HoWo), ho = r / g.Wo, wo = r - ho * g.Wo;
+                a_n[j] = n; a_a[j] = ho * g.SH - g.PH; a_b[j] = wo * g.SW - g.PW;
+            } else if (MODE == 1) {
+                const int n = (int)(m / HW), r = (int)(m - (long long)n * HW), h = r / g.W, w = r - h * g.W;
+                a_n[j] = n; a_a[j] = h + g.PH; a_b[j] = w + g.PW;
+            } else {
+                a_n[j] = (int)m;
+            }
+        }
+        const int c = n0 + r0 + 16 * j;
+        b_ok[j] = c < g.Ncols;
+        b_c[j] = c; b_kh[j] = b_kw[j] = 0;
+        if (MODE == 2 && b_ok[j]) {
+            const int ci = c / KHW, r = c - ci * KHW;
+            b_c[j] = ci; b_kh[j] = r / g.KW; b_kw[j] = r - b_kh[j] * g.KW;
+        }
+    }
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int ty = tid >> 4, tx = tid & 15;
+
+    for (long long k0 = kbeg; k0 < kend; k0 += BK) {
+        const long long k = k0 + kk;
+        const bool kok = k < kend;
+        float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (kok) {
+            if (MODE == 0) {
+                const int ci = (int)(k / KHW), r = (int)(k - (long long)ci * KHW), kh = r / g.KW, kw = r - kh * g.KW;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int h = a_a[j] + kh, w = a_b[j] + kw;
+                    if (a_ok[j] && h >= 0 && h < g.H && w >= 0 && w < g.W)
+                        av[j] = __ldg(g.x + ((long long)a_n[j] * g.Cin + ci) * HW + (long long)h * g.W + w);
+                    if (b_ok[j]) bv[j] = __ldg(g.w + (long long)b_c[j] * g.K + k);
+                }
+            } else if (MODE == 1) {
+                const int co = (int)(k / KHW), r = (int)(k - (long long)co * KHW), kh = r / g.KW, kw = r - kh * g.KW;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int th = a_a[j] - kh, tw = a_b[j] - kw;
+                    if (a_ok[j] && th >= 0 && tw >= 0 && th % g.SH == 0 && tw % g.SW == 0) {
+                        const int ho = th / g.SH, wo = tw / g.SW;
+                        if (ho < g.Ho && wo < g.Wo) av[j] = __ldg(g.dy + ((long long)a_n[j] * g.Cout + co) * HoWo + (long long)ho * g.Wo + wo);
+                    }
+                    if (b_ok[j]) bv[j] = __ldg(g.w + ((long long)co * g.Cin + b_c[j]) * KHW + r);
+                }
+            } else {
+                const int n = (int)(k / HoWo), r = (int)(k - (long long)n * HoWo), ho = r / g.Wo, wo = r - ho * g.Wo;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (a_ok[j]) av[j] = __ldg(g.dy + ((long long)n * g.Cout + a_n[j]) * HoWo + r);
+                    const int h = ho * g.SH - g.PH + b_kh[j], w = wo * g.SW - g.PW + b_kw[j];
+                    if (b_ok[j] && h >= 0 && h < g.H && w >= 0 && w < g.W)
+                        bv[j] = __ldg(g.x + ((long long)n * g.Cin + b_c[j]) * HW + (long long)h * g.W + w);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            As[kk][r0 + 16 * j] = av[j];
+            Bs[kk][r0 + 16 * j] = bv[j];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < BK; ++p) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[p][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[p][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long m = m0 + ty * 4 + i;
+        if (m >= g.M) continue;
+        long long base = 0, cstride = 1;
+        if (MODE == 0) {
+            const int n = (int)(m / HoWo), r = (int)(m - (long long)n * HoWo);
+            base = (long long)n * g.Cout * HoWo + r; cstride = HoWo;
+        } else if (MODE == 1) {
+            const int n = (int)(m / HW), r = (int)(m - (long long)n * HW);
+            base = (long long)n * g.Cin * HW + r; cstride = HW;
+        } else {
+            base = m * g.Ncols;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = n0 + tx * 4 + j;
+            if (c >= g.Ncols) continue;
+            if (MODE == 2) atomicAdd(g.out + base + c, acc[i][j]);
+            else g.out[base + (long long)c * cstride] = acc[i][j];
+        }
+    }
+}
+
+int check_geom(const mrssm_gconv_args* a) {
+    MRSSM_CHECK(a && a->N > 0 && a->Cin > 0 && a->Cout > 0 && a->H > 0 && a->W > 0 && a->KH > 0 && a->KW > 0 && a->SH > 0 && a->SW > 0 &&
+                    a->PH >= 0 && a->PW >= 0, "gconv: bad geometry");
+    MRSSM_CHECK(a->Ho == (a->H + 2 * a->PH - a->KH) / a->SH + 1 && a->Wo == (a->W + 2 * a->PW - a->KW) / a->SW + 1 && a->Ho > 0 && a->Wo > 0,
+                "gconv: output %dx%d does not match input %dx%d, kernel %dx%d, stride %dx%d, padding %dx%d", a->Ho, a->Wo, a->H, a->W,
+                a->KH, a->KW, a->SH, a->SW, a->PH, a->PW);
+    return 0;
+}
+
+GC make(const mrssm_gconv_args* a) {
+    GC g;
+    g.N = a->N; g.Cin = a->Cin; g.H = a->H; g.W = a->W; g.Cout = a->Cout; g.KH = a->KH; g.KW = a->KW; g.SH = a->SH; g.SW = a->SW;
+    g.PH = a->PH; g.PW = a->PW; g.Ho = a->Ho; g.Wo = a->Wo;
+    g.x = a->x; g.w = a->w; g.dy = a->y; g.out = nullptr; g.M = 0; g.K = 0; g.kchunk = 0; g.Ncols = 0;
+    return g;
+}
+
+// ---- normalisation ------------------------------------------------------------------------------------------------------
+// A "group" is what one mean / variance is taken over: BatchNorm: channel c over (n, i); InstanceNorm: plane (n, c) over i.
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+    return t;
+}
+
+__global__ void norm_stats_kernel(const float* __restrict__ x, int N, int C, int HW, int instance, float* __restrict__ mean,
+                                  float* __restrict__ var) {
+    __shared__ double sh[32];
+    const int gidx = blockIdx.x;
+    double s = 0.0, q = 0.0;
+    if (instance) {
+        const float* p = x + (long long)gidx * HW;
+        for (int i = threadIdx.x; i < HW; i += blockDim.x) { const double v = p[i]; s += v; q += v * v; }
+    } else {
+        const long long total = (long long)N * HW;
+        for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+            const long long n = e / HW, i = e - n * HW;
+            const double v = x[(n * C + gidx) * HW + i];
+            s += v; q += v * v;
+        }
+    }
+    s = block_sum(s, sh);
+    q = block_sum(q, sh);
+    if (threadIdx.x == 0) {
+        const double cnt = instance ? (double)HW : (double)N * HW, m = s / cnt;
+        mean[gidx] = (float)m;
+        var[gidx] = (float)fmax(q / cnt - m * m, 0.0);
+    }
+}
+
+// running <- (1 - momentum) running + momentum * (batch mean, unbiased batch variance); InstanceNorm: averaged over the N planes
+__global__ void norm_running_kernel(const float* __restrict__ mean, const float* __restrict__ var, int N, int C, int HW, int instance,
+                                    float momentum, float* __restrict__ rmean, float* __restrict__ rvar) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float m, v;
+    if (instance) {
+        double sm = 0.0, sv = 0.0;
+        for (int n = 0; n < N; ++n) { sm += mean[n * C + c]; sv += var[n * C + c]; }
+        m = (float)(sm / N);
+        v = (float)(sv / N) * ((float)HW / (float)(HW - 1));
+    } else {
+        const float cnt = (float)N * (float)HW;
+        m = mean[c];
+        v = var[c] * (cnt / (cnt - 1.f));
+    }
+    rmean[c] = (1.f - momentum) * rmean[c] + momentum * m;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * v;
+}
+
+// y = [relu](gamma (x - mean_g) / sqrt(var_g + eps) + beta);  per_plane: statistics indexed by (n, c), else by c
+__global__ void norm_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ var,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, long long total, int C, int HW,
+                                  int per_plane, int relu, float eps, float* __restrict__ y) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long pl = e / HW;
+        const int c = (int)(pl % C);
+        const long long gi = per_plane ? pl : c;
+        float v = (x[e] - mean[gi]) * rsqrtf(var[gi] + eps) * gamma[c] + beta[c];
+        if (relu && v < 0.f) v = 0.f;
+        y[e] = v;
+    }
+}
+
+// per group: sum of g^ = g * [y > 0 if relu] and of g^ * x^;  dgamma[c] += sum g^ x^, dbeta[c] += sum g^
+__global__ void norm_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ x,
+                                       const float* __restrict__ mean, const float* __restrict__ var, int N, int C, int HW, int instance,
+                                       int per_plane_stats, int relu, float eps, float* __restrict__ sum_g, float* __restrict__ sum_gx,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ double sh[32];
+    const int gidx = blockIdx.x;
+    double s = 0.0, q = 0.0;
+    if (instance) {
+        const int c = gidx % C;
+        const long long si = per_plane_stats ? gidx : c;
+        const float mu = mean[si], rs = rsqrtf(var[si] + eps);
+        const long long o = (long long)gidx * HW;
+        for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+            float gg = g[o + i];
+            if (relu && !(y[o + i] > 0.f)) gg = 0.f;
+            s += gg; q += (double)gg * ((x[o + i] - mu) * rs);
+        }
+    } else {
+        const float mu = mean[gidx], rs = rsqrtf(var[gidx] + eps);
+        const long long total = (long long)N * HW;
+        for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+            const long long n = e / HW, i = e - n * HW, o = (n * C + gidx) * HW + i;
+            float gg = g[o];
+            if (relu && !(y[o] > 0.f)) gg = 0.f;
+            s += gg; q += (double)gg * ((x[o] - mu) * rs);
+        }
+    }
+    s = block_sum(s, sh);
+    q = block_sum(q, sh);
+    if (threadIdx.x == 0) {
+        sum_g[gidx] = (float)s;
+        sum_gx[gidx] = (float)q;
+        const int c = instance ? gidx % C : gidx;
+        if (dgamma) atomicAdd(dgamma + c, (float)q);
+        if (dbeta) atomicAdd(dbeta + c, (float)s);
+    }
+}
+
+// batch statistics: dx = gamma / sigma (g^ - mean(g^) - x^ mean(g^ x^));  fixed (running) statistics: dx = gamma / sigma g^
+__global__ void norm_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ x,
+                                      const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ gamma,
+                                      const float* __restrict__ sum_g, const float* __restrict__ sum_gx, long long total, int N, int C, int HW,
+                                      int instance, int per_plane_stats, int batch_stats, int relu, float eps, float* __restrict__ dx) {
+    const float inv_cnt = instance ? 1.f / (float)HW : 1.f / ((float)N * (float)HW);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long pl = e / HW;
+        const int c = (int)(pl % C);
+        const long long gi = instance ? pl : c, si = (instance && !per_plane_stats) ? c : gi;
+        const float rs = rsqrtf(var[si] + eps);
+        float gg = g[e];
+        if (relu && !(y[e] > 0.f)) gg = 0.f;
+        float v = gg;
+        if (batch_stats) v = gg - sum_g[gi] * inv_cnt - (x[e] - mean[si]) * rs * sum_gx[gi] * inv_cnt;
+        dx[e] = gamma[c] * rs * v;
+    }
+}
+
+// ---- GLU over dim 1: x [N, 2C, L] -> y [N, C, L] = a * sigmoid(b) ---------------------------------------------------------------
+__global__ void glu_fwd_kernel(const float* __restrict__ x, long long total, int C, int L, float* __restrict__ y) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long cl = (long long)C * L, n = e / cl, r = e - n * cl;
+        const float a = x[n * 2 * cl + r], b = x[n * 2 * cl + cl + r];
+        y[e] = a * sigmoidf_(b);
+    }
+}
+__global__ void glu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, long long total, int C, int L, float* __restrict__ dx) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long cl = (long long)C * L, n = e / cl, r = e - n * cl;
+        const float a = x[n * 2 * cl + r], s = sigmoidf_(x[n * 2 * cl + cl + r]), gg = g[e];
+        dx[n * 2 * cl + r] = gg * s;
+        dx[n * 2 * cl + cl + r] = gg * a * s * (1.f - s);
+    }
+}
+
+// y[n][c][i] = x[n][c][i] + bias[c] (the last ConvTranspose2d of the BatchNorm decoder keeps its bias) and the bias gradient
+__global__ void chan_bias_fwd_kernel(const float* __restrict__ x, long long total, int C, int HW, const float* __restrict__ bias,
+                                     float* __restrict__ y) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
+        y[e] = x[e] + bias[(int)((e / HW) % C)];
+}
+__global__ void chan_bias_bwd_kernel(const float* __restrict__ g, int N, int C, int HW, float* __restrict__ dbias) {
+    __shared__ double sh[32];
+    const int c = blockIdx.x;
+    double s = 0.0;
+    for (int n = blockIdx.y; n < N; n += gridDim.y) {
+        const float* p = g + ((long long)n * C + c) * HW;
+        for (int i = threadIdx.x; i < HW; i += blockDim.x) s += p[i];
+    }
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) atomicAdd(dbias + c, (float)s);
+}
+
+inline int ew_blocks(long long total) { return (int)std::max<long long>(1, std::min<long long>(148 * 16, (total + 255) / 256)); }
+
+}  // namespace
+
+extern "C" int mrssm_gconv_fwd(const mrssm_gconv_args* a, void* stream) {
+    if (int e = check_geom(a)) return e;
+    MRSSM_CHECK(a->x && a->w && a->y, "gconv_fwd: null tensor");
+    GC g = make(a);
+    g.out = a->y; g.M = (long long)a->N * a->Ho * a->Wo; g.Ncols = a->Cout; g.K = (long long)a->Cin * a->KH * a->KW;
+    dim3 grid((unsigned)ceil_div64(g.M, BM), (unsigned)ceil_div64(g.Ncols, BN));
+    gconv_kernel<0><<<grid, NT, 0, (cudaStream_t)stream>>>(g);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mrssm_gconv_dgrad(const mrssm_gconv_args* a, void* stream) {
+    if (int e = check_geom(a)) return e;
+    MRSSM_CHECK(a->dx && a->w && a->y, "gconv_dgrad: null tensor");
+    GC g = make(a);
+    g.out = a->dx; g.M = (long long)a->N * a->H * a->W; g.Ncols = a->Cin; g.K = (long long)a->Cout * a->KH * a->KW;
+    dim3 grid((unsigned)ceil_div64(g.M, BM), (unsigned)ceil_div64(g.Ncols, BN));
+    gconv_kernel<1><<<grid, NT, 0, (cudaStream_t)stream>>>(g);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mrssm_gconv_wgrad(const mrssm_gconv_args* a, void* stream) {
+    if (int e = check_geom(a)) return e;
+    MRSSM_CHECK(a->x && a->dw && a->y, "gconv_wgrad: null tensor");
+    GC g = make(a);
+    g.out = a->dw; g.M = a->Cout; g.Ncols = a->Cin * a->KH * a->KW; g.K = (long long)a->N * a->Ho * a->Wo;
+    const long long tiles = ceil_div64(g.M, BM) * ceil_div64(g.Ncols, BN);
+    long long splits = std::max<long long>(1, std::min<long long>(ceil_div64(4 * 148, tiles), g.K / (8 * BK)));
+    splits = std::min<long long>(splits, 65535);
+    g.kchunk = ceil_div64(ceil_div64(g.K, splits), BK) * BK;
+    splits = ceil_div64(g.K, g.kchunk);
+    dim3 grid((unsigned)ceil_div64(g.M, BM), (unsigned)ceil_div64(g.Ncols, BN), (unsigned)splits);
+    gconv_kernel<2><<<grid, NT, 0, (cudaStream_t)stream>>>(g);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mrssm_norm_fwd(const mrssm_norm_args* a, void* stream) {
+    MRSSM_CHECK(a && a->x && a->y && a->gamma && a->beta && a->mean && a->var && a->N > 0 && a->C > 0 && a->HW > 0, "norm_fwd: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int groups = a->instance ? a->N * a->C : a->C;
+    const long long total = (long long)a->N * a->C * a->HW;
+    if (a->batch_stats) {
+        MRSSM_CHECK(a->instance ? a->HW > 1 || !a->running_mean : (long long)a->N * a->HW > 1, "norm_fwd: a single value per group has no variance");
+        norm_stats_kernel<<<groups, 256, 0, st>>>(a->x, a->N, a->C, a->HW, a->instance, a->mean, a->var);
+        MRSSM_LAUNCH_CHECK();
+        if (a->running_mean && a->running_var) {
+            norm_running_kernel<<<(a->C + 127) / 128, 128, 0, st>>>(a->mean, a->var, a->N, a->C, a->HW, a->instance, a->momentum,
+                                                                   a->running_mean, a->running_var);
+            MRSSM_LAUNCH_CHECK();
+        }
+        norm_apply_kernel<<<ew_blocks(total), 256, 0, st>>>(a->x, a->mean, a->var, a->gamma, a->beta, total, a->C, a->HW, a->instance, a->relu,
+                                                           a->eps, a->y);
+    } else {
+        MRSSM_CHECK(a->running_mean && a->running_var, "norm_fwd: fixed statistics requested without running buffers");
+        norm_apply_kernel<<<ew_blocks(total), 256, 0, st>>>(a->x, a->running_mean, a->running_var, a->gamma, a->beta, total, a->C, a->HW, 0,
+                                                           a->relu, a->eps, a->y);
+    }
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mrssm_norm_bwd(const mrssm_norm_args* a, const float* g, float* sum_g, float* sum_gx, float* dgamma, float* dbeta, float* dx,
+                              void* stream) {
+    MRSSM_CHECK(a && a->x && a->y && a->gamma && g && sum_g && sum_gx && dx && a->N > 0 && a->C > 0 && a->HW > 0, "norm_bwd: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int groups = a->instance ? a->N * a->C : a->C;
+    const long long total = (long long)a->N * a->C * a->HW;
+    const float* mean = a->batch_stats ? a->mean : a->running_mean;
+    const float* var = a->batch_stats ? a->var : a->running_var;
+    MRSSM_CHECK(mean && var, "norm_bwd: statistics missing");
+    const int per_plane = a->instance && a->batch_stats;
+    norm_bwd_reduce_kernel<<<groups, 256, 0, st>>>(g, a->y, a->x, mean, var, a->N, a->C, a->HW, a->instance, per_plane, a->relu, a->eps, sum_g,
+                                                  sum_gx, dgamma, dbeta);
+    MRSSM_LAUNCH_CHECK();
+    norm_bwd_apply_kernel<<<ew_blocks(total), 256, 0, st>>>(g, a->y, a->x, mean, var, a->gamma, sum_g, sum_gx, total, a->N, a->C, a->HW, a->instance,
+                                                           per_plane, a->batch_stats, a->relu, a->eps, dx);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mrssm_glu_fwd(const float* x, int64_t N, int32_t C, int32_t L, float* y, void* stream) {
+    MRSSM_CHECK(x && y && N > 0 && C > 0 && L > 0, "glu_fwd: bad arguments");
+    const long long total = (long long)N * C * L;
+    glu_fwd_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, total, C, L, y);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mrssm_glu_bwd(const float* x, const float* g, int64_t N, int32_t C, int32_t L, float* dx, void* stream) {
+    MRSSM_CHECK(x && g && dx && N > 0 && C > 0 && L > 0, "glu_bwd: bad arguments");
+    const long long total = (long long)N * C * L;
+    glu_bwd_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, g, total, C, L, dx);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mrssm_chan_bias_fwd(const float* x, int64_t N, int32_t C, int32_t HW, const float* bias, float* y, void* stream) {
+    MRSSM_CHECK(x && y && bias && N > 0 && C > 0 && HW > 0, "chan_bias_fwd: bad arguments");
+    const long long total = (long long)N * C * HW;
+    chan_bias_fwd_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, total, C, HW, bias, y);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mrssm_chan_bias_bwd(const float* g, int64_t N, int32_t C, int32_t HW, float* dbias, void* stream) {
+    MRSSM_CHECK(g && dbias && N > 0 && C > 0 && HW > 0, "chan_bias_bwd: bad arguments");
+    dim3 grid((unsigned)C, (unsigned)std::min<long long>(N, 64));
+    chan_bias_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, (int)N, C, HW, dbias);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}

@@ -71,6 +71,16 @@ class RolloutArgs(C.Structure):
         ("st_u", _vp * MAX_HEADS)]
 
 
+class GConvArgs(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("N", "Cin", "H", "W", "Cout", "KH", "KW", "SH", "SW", "PH", "PW", "Ho", "Wo")] + [
+        ("x", _vp), ("w", _vp), ("y", _vp), ("dx", _vp), ("dw", _vp)]
+
+
+class NormArgs(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("N", "C", "HW", "instance", "batch_stats", "relu")] + [("eps", C.c_float), ("momentum", C.c_float)] + [
+        (n, _vp) for n in ("x", "y", "gamma", "beta", "mean", "var", "running_mean", "running_var")]
+
+
 class RolloutBwdArgs(C.Structure):
     _fields_ = [("f", RolloutArgs)] + [(n, _vp) for n in (
         "g_beliefs", "g_prior_states", "g_prior_means", "g_prior_stds", "g_post_states", "g_post_means",
@@ -158,6 +168,15 @@ SYMBOLS = {
     "mrssm_rstep_gate_bwd": [C.POINTER(RolloutBwdArgs), _i32, _vp, _vp, _vp, _vp, _vp, _vp],
     "mrssm_rstep_xin_bwd": [C.POINTER(RolloutBwdArgs), _i32, _vp, _i32, _vp, _vp],
     "mrssm_add2": [_vp, _vp, _i64, _vp, _vp],
+    "mrssm_gconv_fwd": [C.POINTER(GConvArgs), _vp],
+    "mrssm_gconv_dgrad": [C.POINTER(GConvArgs), _vp],
+    "mrssm_gconv_wgrad": [C.POINTER(GConvArgs), _vp],
+    "mrssm_norm_fwd": [C.POINTER(NormArgs), _vp],
+    "mrssm_norm_bwd": [C.POINTER(NormArgs), _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mrssm_glu_fwd": [_vp, _i64, _i32, _i32, _vp, _vp],
+    "mrssm_glu_bwd": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
+    "mrssm_chan_bias_fwd": [_vp, _i64, _i32, _i32, _vp, _vp, _vp],
+    "mrssm_chan_bias_bwd": [_vp, _i64, _i32, _i32, _vp, _vp],
     "mrssm_latent_fwd": [C.POINTER(LatentArgs), _vp],
     "mrssm_latent_bwd": [C.POINTER(LatentArgs), _vp],
     "mrssm_overshoot_gather": [C.POINTER(OvershootArgs), _vp],

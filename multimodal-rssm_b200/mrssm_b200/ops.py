@@ -1697,3 +1697,195 @@ class ConvDecoderMseTCFn(Function):
     @staticmethod
     def backward(ctx, g):
         return ConvDecoderTCFn._backward(ctx, g, 3)
+
+
+# ---- general NCHW fp32 layers: the sound modality and the BatchNorm image stacks of the shipped YAML (csrc/generic_nchw.cu) ----
+def _pair(v):
+    return (int(v), int(v)) if isinstance(v, int) else (int(v[0]), int(v[1]))
+
+
+def _gconv_call(fn, N, Cin, H, W, Cout, KH, KW, stride, padding, Ho, Wo, x=None, w=None, y=None, dx=None, dw=None):
+    a = L.GConvArgs(N, Cin, H, W, Cout, KH, KW, stride[0], stride[1], padding[0], padding[1], Ho, Wo, x, w, y, dx, dw)
+    tag = work = None
+    if L.profile is not None:
+        tag = "%s[%dx%dx%d->%dx%dx%d k%dx%d]" % (fn[6:], Cin, H, W, Cout, Ho, Wo, KH, KW)
+        work = dict(flops=2.0 * N * Ho * Wo * Cout * Cin * KH * KW, bytes=4.0 * N * (Cin * H * W + Cout * Ho * Wo) + 4.0 * Cout * Cin * KH * KW)
+    L.call(fn, C.byref(a), tag=tag, work=work)
+
+
+class GConvFn(Function):
+    """nn.Conv2d / nn.ConvTranspose2d without bias on fp32 NCHW tensors, any kernel / stride / zero padding (exact CUDA-core
+    kernels).  apply(x, weight, stride, padding, transposed); the weight gradient is accumulated into weight.grad."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, padding, transposed):
+        x = _f32c(x)
+        stride, padding = _pair(stride), _pair(padding)
+        KH, KW = w.shape[2], (w.shape[3] if w.dim() == 4 else 1)           # Conv1d weights [out, in, k] are k x 1 kernels
+        N = x.shape[0]
+        if not transposed:
+            Cin, H, W = x.shape[1:]
+            Cout = w.shape[0]
+            assert w.shape[1] == Cin, (w.shape, x.shape)
+            Ho, Wo = (H + 2 * padding[0] - KH) // stride[0] + 1, (W + 2 * padding[1] - KW) // stride[1] + 1
+            out = torch.empty(N, Cout, Ho, Wo, device=x.device, dtype=torch.float32)
+            geom = (N, Cin, H, W, Cout, KH, KW, stride, padding, Ho, Wo)
+            _gconv_call("mrssm_gconv_fwd", *geom, x=L.ptr(x), w=L.ptr(w), y=L.ptr(out))
+        else:
+            Cout, Ho, Wo = x.shape[1:]                     # conv geometry: the ConvT input is the conv's output side
+            Cin = w.shape[1]
+            assert w.shape[0] == Cout, (w.shape, x.shape)
+            H, W = (Ho - 1) * stride[0] - 2 * padding[0] + KH, (Wo - 1) * stride[1] - 2 * padding[1] + KW
+            out = torch.empty(N, Cin, H, W, device=x.device, dtype=torch.float32)
+            geom = (N, Cin, H, W, Cout, KH, KW, stride, padding, Ho, Wo)
+            _gconv_call("mrssm_gconv_dgrad", *geom, w=L.ptr(w), y=L.ptr(x), dx=L.ptr(out))
+        ctx.geom, ctx.transposed, ctx.w = geom, transposed, w
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = _f32c(g)
+        w, geom = ctx.w, ctx.geom
+        gx = None
+        if not ctx.transposed:
+            if w.requires_grad:
+                _gconv_call("mrssm_gconv_wgrad", *geom, x=L.ptr(x), y=L.ptr(g), dw=L.ptr(grad_buf(w)))
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty_like(x)
+                _gconv_call("mrssm_gconv_dgrad", *geom, w=L.ptr(w), y=L.ptr(g), dx=L.ptr(gx))
+        else:
+            if w.requires_grad:
+                _gconv_call("mrssm_gconv_wgrad", *geom, x=L.ptr(g), y=L.ptr(x), dw=L.ptr(grad_buf(w)))
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty_like(x)
+                _gconv_call("mrssm_gconv_fwd", *geom, x=L.ptr(g), w=L.ptr(w), y=L.ptr(gx))
+        return gx, None, None, None, None
+
+
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1          # nn.BatchNorm2d / nn.InstanceNorm2d defaults, as the reference constructs them
+
+
+class NormFn(Function):
+    """nn.BatchNorm2d (instance=False) / nn.InstanceNorm2d / 1d (instance=True), affine, with an optional fused ReLU.
+    apply(x [N,C,*], gamma, beta, running_mean | None, running_var | None, instance, train, relu).  train (or no running
+    buffers): statistics of this batch, running buffers moved by momentum 0.1; else the running statistics.  The gradients of
+    gamma / beta are accumulated into their .grad."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, rmean, rvar, instance, train, relu):
+        x = _f32c(x)
+        N, Cn = x.shape[0], x.shape[1]
+        HW = x.numel() // (N * Cn)
+        batch_stats = bool(train or rmean is None)
+        groups = N * Cn if instance else Cn
+        y = torch.empty_like(x)
+        mean = torch.empty(groups, device=x.device, dtype=torch.float32) if batch_stats else None
+        var = torch.empty(groups, device=x.device, dtype=torch.float32) if batch_stats else None
+        a = L.NormArgs(N, Cn, HW, int(instance), int(batch_stats), int(relu), BN_EPS, BN_MOMENTUM, L.ptr(x), L.ptr(y), L.ptr(gamma), L.ptr(beta),
+                       L.ptr(mean), L.ptr(var), L.ptr(rmean) if (rmean is not None and (train or not batch_stats)) else None,
+                       L.ptr(rvar) if (rvar is not None and (train or not batch_stats)) else None)
+        if not batch_stats:
+            a.mean, a.var = L.ptr(rmean), L.ptr(rvar)       # (unused by the kernel in this mode; keeps the checks uniform)
+        L.call("mrssm_norm_fwd", C.byref(a), tag="norm_fwd", work=dict(flops=0.0, bytes=8.0 * x.numel()) if L.profile is not None else None)
+        L.kernel_launches += 2 if batch_stats else 0
+        ctx.cfg = (N, Cn, HW, int(instance), int(batch_stats), int(relu))
+        ctx.params = (gamma, beta, rmean, rvar)
+        ctx.save_for_backward(x, y, mean, var)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y, mean, var = ctx.saved_tensors
+        gamma, beta, rmean, rvar = ctx.params
+        N, Cn, HW, instance, batch_stats, relu = ctx.cfg
+        g = _f32c(g)
+        groups = N * Cn if instance else Cn
+        scratch = torch.empty(2, groups, device=x.device, dtype=torch.float32)
+        dx = torch.empty_like(x)
+        a = L.NormArgs(N, Cn, HW, instance, batch_stats, relu, BN_EPS, BN_MOMENTUM, L.ptr(x), L.ptr(y), L.ptr(gamma), L.ptr(beta),
+                       L.ptr(mean), L.ptr(var), L.ptr(rmean), L.ptr(rvar))
+        L.call("mrssm_norm_bwd", C.byref(a), L.ptr(g), scratch[0].data_ptr(), scratch[1].data_ptr(),
+               L.ptr(grad_buf(gamma)) if gamma.requires_grad else None, L.ptr(grad_buf(beta)) if beta.requires_grad else None, L.ptr(dx),
+               tag="norm_bwd", work=dict(flops=0.0, bytes=16.0 * x.numel()) if L.profile is not None else None)
+        L.kernel_launches += 1
+        return dx, None, None, None, None, None, None, None
+
+
+class GluFn(Function):
+    """nn.GLU(dim=1) on [N, 2C, *] fp32."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32c(x)
+        N, C2 = x.shape[0], x.shape[1]
+        assert C2 % 2 == 0
+        Lr = x.numel() // (N * C2)
+        y = torch.empty(N, C2 // 2, *x.shape[2:], device=x.device, dtype=torch.float32)
+        L.call("mrssm_glu_fwd", L.ptr(x), N, C2 // 2, Lr, L.ptr(y))
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        N, C2 = x.shape[0], x.shape[1]
+        dx = torch.empty_like(x)
+        L.call("mrssm_glu_bwd", L.ptr(x), L.ptr(_f32c(g)), N, C2 // 2, x.numel() // (N * C2), L.ptr(dx))
+        return dx
+
+
+def conv2d_nobias(x, w, stride=1, padding=0):
+    return GConvFn.apply(x, w, stride, padding, False)
+
+
+def conv_transpose2d_nobias(x, w, stride=1, padding=0):
+    return GConvFn.apply(x, w, stride, padding, True)
+
+
+def batch_norm(x, bn, relu=False):
+    """bn: the nn.BatchNorm2d holding the parameters / running buffers (its .training flag selects the statistics)."""
+    y = NormFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, False, bn.training, relu)
+    if bn.training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return y
+
+
+def instance_norm(x, m):
+    """m: nn.InstanceNorm2d / 1d (affine).  Tracked layers normalise with the running statistics in eval mode; torch leaves their
+    num_batches_tracked untouched."""
+    tracked = m.running_mean is not None
+    return NormFn.apply(x, m.weight, m.bias, m.running_mean if tracked else None, m.running_var if tracked else None, True,
+                        m.training or not tracked, False)
+
+
+def conv1d_k1(x, w):
+    """nn.Conv1d(kernel_size=1, bias=False) on [N, C, L]: the general kernel with H = L, W = 1."""
+    assert w.dim() == 3 and w.shape[2] == 1
+    return GConvFn.apply(x.unsqueeze(-1), w, 1, 0, False).squeeze(-1)
+
+
+class ChannelBiasFn(Function):
+    """y[n,c,...] = x[n,c,...] + bias[c]; the bias gradient is accumulated into bias.grad."""
+
+    @staticmethod
+    def forward(ctx, x, bias):
+        x = _f32c(x)
+        N, Cn = x.shape[0], x.shape[1]
+        y = torch.empty_like(x)
+        L.call("mrssm_chan_bias_fwd", L.ptr(x), N, Cn, x.numel() // (N * Cn), L.ptr(bias), L.ptr(y))
+        ctx.bias = bias
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32c(g)
+        N, Cn = g.shape[0], g.shape[1]
+        if ctx.bias.requires_grad:
+            L.call("mrssm_chan_bias_bwd", L.ptr(g), N, Cn, g.numel() // (N * Cn), L.ptr(grad_buf(ctx.bias)))
+        return g, None
+
+
+def add_channel_bias(x, bias):
+    return ChannelBiasFn.apply(x, bias)

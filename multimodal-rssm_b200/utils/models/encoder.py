@@ -8,8 +8,8 @@ own ``forward`` is never called.
 
 Covered: bottle helpers a3, MultimodalEncoder a4, ImageEncoder 64/128 a5,
 SymbolicEncoder a6, StochasticStateModel a11, ObsEncoder a12, MultimodalObsEncoder a13, fusion a14.
-Not covered (raise NotImplementedError): 84x84 / 256x256 images, sound, the
-q(st|ot) expert family, normalization layers.
+Round 2 added the rest of the shipped YAML: `SoundEncoder_v2` and the BatchNorm variant of the 64x64 image encoder (exact fp32
+kernels).  Not covered (raise NotImplementedError): 84x84 / 256x256 images, the q(st|ot) expert family.
 """
 import itertools
 
@@ -240,22 +240,36 @@ class _ConvEncoder(_EncoderBase):
 
     def __init__(self, embedding_size, activation_function="relu", image_dim=3, normalization=None):
         super().__init__()
-        if normalization is not None:
-            raise NotImplementedError(f"normalization={normalization!r} is a 'next' row (SURVEY §8f#1)")
+        if normalization not in (None, "BatchNorm"):
+            raise NotImplementedError(f"normalization={normalization!r} (the reference implements None and BatchNorm only)")
+        if normalization == "BatchNorm" and len(self.CHANNELS) != 4:
+            raise NotImplementedError("BatchNorm: the reference has it for the 64x64 stack only (encoder.py:324-337)")
         self.embedding_size = embedding_size
         self.activation_function = activation_function
+        self.normalization = normalization
         layers, cin = [], image_dim
         for cout in self.CHANNELS:
-            layers += [nn.Conv2d(cin, cout, 4, stride=2), nn.ReLU()]
+            if normalization == "BatchNorm":             # keys conv.{0,3,..}.weight, conv.{1,4,..}.{weight,bias,running_*}
+                layers += [nn.Conv2d(cin, cout, 4, stride=2, bias=False), nn.BatchNorm2d(cout, affine=True, track_running_stats=True), nn.ReLU()]
+            else:
+                layers += [nn.Conv2d(cin, cout, 4, stride=2), nn.ReLU()]
             cin = cout
         self.conv = nn.Sequential(*layers)               # parameter container: keys conv.{0,2,..}.{weight,bias}
         self.fc = nn.Identity() if embedding_size == 1024 else nn.Linear(1024, embedding_size)
         self.modules = [self.conv, self.fc]
 
     def forward(self, observation):
-        params = [p for m in self.conv if isinstance(m, nn.Conv2d) for p in (m.weight, m.bias)]
-        fn = ops.ConvEncoderTCFn if ops.bf16_mode() else ops.ConvEncoderFn
-        hidden = fn.apply(observation, *params)
+        if self.normalization == "BatchNorm":
+            # Conv2d (no bias) -> BatchNorm2d -> ReLU triples on the exact fp32 NCHW kernels (csrc/generic_nchw.cu), both modes
+            hidden = observation
+            mods = list(self.conv)
+            for i in range(0, len(mods), 3):
+                hidden = ops.batch_norm(ops.conv2d_nobias(hidden, mods[i].weight, 2, 0), mods[i + 1], relu=True)
+            hidden = hidden.reshape(-1, 1024)
+        else:
+            params = [p for m in self.conv if isinstance(m, nn.Conv2d) for p in (m.weight, m.bias)]
+            fn = ops.ConvEncoderTCFn if ops.bf16_mode() else ops.ConvEncoderFn
+            hidden = fn.apply(observation, *params)
         if hidden.shape[1] != 1024:
             raise ValueError(f"conv stack produced {hidden.shape[1]} features, the reference reshapes to 1024")
         if self.embedding_size != 1024:
@@ -273,6 +287,40 @@ class ImageEncoder_128(_ConvEncoder):
     CHANNELS = (16, 32, 64, 128, 256)
 
 
+class SoundEncoder_v2(_EncoderBase):
+    """Spectrogram [N,128,20] -> embedding (reference encoder.py:661-721): four bias-free Conv2d (+ InstanceNorm2d with tracked
+    statistics) + GLU stages, a k = 1 Conv1d + InstanceNorm1d + GLU down-conversion.  Same constructor, `.modules`, state-dict
+    keys (`down_sample_k.{0,1}.*`, `down_conversion.{0,1}.*`).  Exact fp32 kernels (csrc/generic_nchw.cu)."""
+
+    def __init__(self, embbed_size=250, channels_base=128):
+        super().__init__()
+        cb = channels_base
+        self.embbed_size = embbed_size
+        self.conversion_channels = int(cb * 64)
+        inorm = lambda c: nn.InstanceNorm2d(num_features=c, affine=True, track_running_stats=True)
+        self.down_sample_1 = nn.Sequential(nn.Conv2d(1, cb, kernel_size=(3, 9), padding=(1, 4), bias=False), nn.GLU(dim=1))
+        self.down_sample_2 = nn.Sequential(nn.Conv2d(cb // 2, cb * 2, kernel_size=(4, 8), stride=(2, 2), padding=(1, 3), bias=False),
+                                           inorm(cb * 2), nn.GLU(dim=1))
+        self.down_sample_3 = nn.Sequential(nn.Conv2d(cb, cb * 4, kernel_size=(4, 8), stride=(2, 2), padding=(1, 3), bias=False),
+                                           inorm(cb * 4), nn.GLU(dim=1))
+        self.down_sample_4 = nn.Sequential(nn.Conv2d(cb * 2, cb * 4, kernel_size=(3, 4), stride=(1, 1), padding=(1, 1), bias=False),
+                                           inorm(cb * 4), nn.GLU(dim=1))
+        self.down_conversion = nn.Sequential(nn.Conv1d(self.conversion_channels, int(embbed_size / 2), kernel_size=1, bias=False),
+                                             nn.InstanceNorm1d(num_features=int(embbed_size / 2), affine=True), nn.GLU(dim=1))
+        self.modules = [self.down_sample_1, self.down_sample_2, self.down_sample_3, self.down_sample_4, self.down_conversion]
+
+    def forward(self, x):
+        x = x.unsqueeze(1)
+        c = self.down_sample_1[0]
+        x = ops.GluFn.apply(ops.conv2d_nobias(x, c.weight, c.stride, c.padding))
+        for stage in (self.down_sample_2, self.down_sample_3, self.down_sample_4):
+            c = stage[0]
+            x = ops.GluFn.apply(ops.instance_norm(ops.conv2d_nobias(x, c.weight, c.stride, c.padding), stage[1]))
+        x = x.contiguous().view(-1, self.conversion_channels, 4)
+        x = ops.GluFn.apply(ops.instance_norm(ops.conv1d_k1(x, self.down_conversion[0].weight), self.down_conversion[1]))
+        return x.contiguous().view(-1, self.embbed_size)
+
+
 def build_ImageEncoder(observation_shape, visual_embedding_size, cnn_activation_function, normalization=None):
     size = list(observation_shape[1:])
     cls = {(64, 64): ImageEncoder, (128, 128): ImageEncoder_128}.get(tuple(size))
@@ -286,7 +334,7 @@ def build_Encoder(name, observation_shapes, embedding_size, activation_function,
     if "image" in name:
         return build_ImageEncoder(shape, embedding_size["image"], activation_function["cnn"], normalization=normalization)
     if "sound" in name:
-        raise NotImplementedError("sound modality is a 'next' row (SURVEY §8f#1)")
+        return SoundEncoder_v2(embbed_size=embedding_size["sound"])
     return SymbolicEncoder(shape[0], embedding_size["other"], activation_function["dense"])
 
 

@@ -67,21 +67,42 @@ class _ConvDecoder(ObservationModel_base):
     def __init__(self, belief_size, state_size, embedding_size, activation_function="relu", image_dim=3,
                  normalization=None):
         super().__init__()
-        if normalization is not None:
-            raise NotImplementedError(f"normalization={normalization!r} is a 'next' row (SURVEY §8f#1)")
+        if normalization not in (None, "BatchNorm"):
+            raise NotImplementedError(f"normalization={normalization!r} (the reference implements None and BatchNorm only)")
+        if normalization == "BatchNorm" and len(self.LAYERS) != 4:
+            raise NotImplementedError("BatchNorm: the reference has it for the 64x64 stack only (observation_model.py:75-86)")
         self.embedding_size = embedding_size
+        self.normalization = normalization
         self.fc1 = nn.Linear(belief_size + state_size, embedding_size)
         layers, cin = [], embedding_size
         for i, (cout, k) in enumerate(self.LAYERS):
             cout = image_dim if cout is None else cout
-            layers.append(nn.ConvTranspose2d(cin, cout, k, stride=2))
-            if i < len(self.LAYERS) - 1:
-                layers.append(nn.ReLU())
+            last = i == len(self.LAYERS) - 1
+            if normalization == "BatchNorm" and not last:     # keys conv.{0,3,6}.weight, conv.{1,4,7}.*, conv.9.{weight,bias}
+                layers += [nn.ConvTranspose2d(cin, cout, k, stride=2, bias=False), nn.BatchNorm2d(cout, affine=True, track_running_stats=True),
+                           nn.ReLU()]
+            else:
+                layers.append(nn.ConvTranspose2d(cin, cout, k, stride=2))
+                if not last:
+                    layers.append(nn.ReLU())
             cin = cout
         self.conv = nn.Sequential(*layers)               # keys conv.{0,2,4,..}.{weight,bias}
         self.modules = [self.fc1, self.conv]
 
+    def _forward_batchnorm(self, h_t, s_t):
+        """fc1 -> (ConvT without bias -> BatchNorm2d -> ReLU) x 3 -> ConvT with bias, on the exact fp32 NCHW kernels."""
+        T, B = h_t.shape[:2]
+        x = ops.MlpFn.apply(0, False, 2, h_t.reshape(T * B, -1), s_t.reshape(T * B, -1), self.fc1.weight, self.fc1.bias)
+        x = x.reshape(-1, self.embedding_size, 1, 1)
+        mods = list(self.conv)
+        for i in range(0, len(mods) - 1, 3):
+            x = ops.batch_norm(ops.conv_transpose2d_nobias(x, mods[i].weight, 2, 0), mods[i + 1], relu=True)
+        x = ops.add_channel_bias(ops.conv_transpose2d_nobias(x, mods[-1].weight, 2, 0), mods[-1].bias)
+        return {"loc": x.reshape(T, B, *x.shape[1:]), "scale": 1.0}
+
     def forward(self, h_t, s_t):
+        if self.normalization == "BatchNorm":
+            return self._forward_batchnorm(h_t, s_t)
         T, B = h_t.shape[:2]
         params = [self.fc1.weight, self.fc1.bias]
         params += [p for m in self.conv if isinstance(m, nn.ConvTranspose2d) for p in (m.weight, m.bias)]
@@ -92,7 +113,7 @@ class _ConvDecoder(ObservationModel_base):
     def mse_loss(self, h_t, s_t, o_t):
         """sum_features mean_{t,b} (loc - o)^2.  bf16 mode, <= 4 image channels: decoder and loss are ONE autograd node — the
         last ConvTranspose2d's epilogue reduces the loss and keeps the bf16 residual, the reconstruction is never written."""
-        if not (ops.bf16_mode() and o_t.shape[2] <= 4):
+        if not (ops.bf16_mode() and o_t.shape[2] <= 4) or self.normalization == "BatchNorm":
             return super().mse_loss(h_t, s_t, o_t)
         T, B = h_t.shape[:2]
         params = [self.fc1.weight, self.fc1.bias]
@@ -111,6 +132,37 @@ class ImageDecoder_128(_ConvDecoder):
     LAYERS = ((256, 6), (128, 4), (64, 4), (32, 4), (None, 6))
 
 
+class SoundDecoder_v2(ObservationModel_base):
+    """(belief, state) -> spectrogram [T,B,128,20] (reference observation_model.py:420-472): k = 1 Conv1d up-conversion, three
+    bias-free ConvTranspose2d + InstanceNorm2d (tracked statistics) + GLU stages, a 7x7 Conv2d.  `forward(s_t, h_t)` keeps the
+    reference's argument names: every caller passes (beliefs, states) positionally, so the concatenation is [states, beliefs]
+    (SURVEY Q14).  Exact fp32 kernels (csrc/generic_nchw.cu)."""
+
+    def __init__(self, belief_size, state_size, channels_base=128):
+        super().__init__()
+        cb = channels_base
+        self.state_size, self.belief_size, self.channels_base = state_size, belief_size, cb
+        inorm = lambda c: nn.InstanceNorm2d(num_features=c, affine=True, track_running_stats=True)
+        self.up_conversion = nn.Conv1d(state_size + belief_size, int(cb * 2 * 32 * 4), kernel_size=1, bias=False)
+        self.up_sample_0 = nn.Sequential(nn.ConvTranspose2d(cb * 2, cb * 4, kernel_size=(3, 4), stride=(1, 1), padding=(1, 1), bias=False),
+                                         inorm(cb * 4), nn.GLU(dim=1))
+        self.up_sample_1 = nn.Sequential(nn.ConvTranspose2d(cb * 2, cb * 2, kernel_size=4, stride=2, padding=1, bias=False),
+                                         inorm(cb * 2), nn.GLU(dim=1))
+        self.up_sample_2 = nn.Sequential(nn.ConvTranspose2d(cb, cb, kernel_size=4, stride=2, padding=1, bias=False), inorm(cb), nn.GLU(dim=1))
+        self.out = nn.Conv2d(cb // 2, 1, kernel_size=7, stride=1, padding=3, bias=False)
+        self.modules = [self.up_conversion, self.up_sample_0, self.up_sample_1, self.up_sample_2, self.out]
+
+    def forward(self, s_t, h_t):
+        T, B = h_t.shape[:2]
+        x = torch.cat([h_t.reshape(T * B, -1, 1), s_t.reshape(T * B, -1, 1)], dim=1)
+        x = ops.conv1d_k1(x, self.up_conversion.weight).view(-1, int(self.channels_base * 2), 32, 4)
+        for stage in (self.up_sample_0, self.up_sample_1, self.up_sample_2):
+            c = stage[0]
+            x = ops.GluFn.apply(ops.instance_norm(ops.conv_transpose2d_nobias(x, c.weight, c.stride, c.padding), stage[1]))
+        x = ops.conv2d_nobias(x, self.out.weight, 1, 3).squeeze(1)
+        return {"loc": x.reshape(T, B, *x.shape[1:]), "scale": 1.0}
+
+
 def build_ObservationModel(name, observation_shapes, belief_size, state_size, hidden_size, embedding_size,
                            activation_function, normalization=None):
     shape = observation_shapes[name]
@@ -120,7 +172,9 @@ def build_ObservationModel(name, observation_shapes, belief_size, state_size, hi
             raise NotImplementedError(f"image size {list(shape[1:])}: only 64x64 and 128x128 are on the B200 hot path")
         return cls(belief_size, state_size, embedding_size["image"], activation_function["cnn"],
                    image_dim=shape[0], normalization=normalization)
-    if "sound" in name or name == "draw_target":
+    if "sound" in name:
+        return SoundDecoder_v2(belief_size=belief_size, state_size=state_size)
+    if name == "draw_target":
         raise NotImplementedError(f"decoder for '{name}' is outside the B200 hot path (SURVEY §2/§8f)")
     return DenseDecoder(shape[0], belief_size, state_size, embedding_size["other"], activation_function["dense"])
 

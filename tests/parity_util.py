@@ -44,7 +44,7 @@ def _hot_cfg(oc, B, T, device):
                            overshooting_distance=oc.overshooting_distance, overshooting_kl_beta=oc.overshooting_kl_beta,
                            overshooting_reward_scale=oc.overshooting_reward_scale,
                            worldmodel_LogProbLoss=oc.worldmodel_LogProbLoss, learning_rate_schedule=oc.learning_rate_schedule,
-                           embedding_size=dict(oc.embedding_size))
+                           embedding_size=dict(oc.embedding_size), normalization=oc.normalization)
 
 
 def unflatten(flat):
@@ -71,7 +71,7 @@ def named_params(model, oc):
         sd = model.get_state_dict()
         sd.pop("model_optimizer")
         by_ptr = {p.data_ptr(): p for p in model.param_list}
-        return {k: by_ptr[v.data_ptr()] for k, v in O.flatten_state(sd).items()}
+        return {k: by_ptr[v.data_ptr()] for k, v in O.flatten_state(sd).items() if not O.is_buffer(k)}
     return dict(model.named_parameters())
 
 
@@ -86,6 +86,15 @@ class FakeD:
         d = self.device
         return ({k: v.to(d) for k, v in self.b["obs"].items()}, self.b["actions"].to(d),
                 self.b["rewards"].to(d), self.b["nonterminals"].to(d))
+
+
+def named_buffers(model, oc):
+    """flat oracle key -> BatchNorm / InstanceNorm buffer of the product model."""
+    if oc.multimodal:
+        sd = model.get_state_dict()
+        sd.pop("model_optimizer", None)
+        return {k: v for k, v in O.flatten_state(sd).items() if O.is_buffer(k)}
+    return {k: v for k, v in torch.nn.Module.state_dict(model).items() if O.is_buffer(k)}
 
 
 def build_product(oc, B, T, device, seed=0, bf16=False):

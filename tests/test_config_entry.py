@@ -61,10 +61,19 @@ def test_main_prepares_the_experiment_like_the_reference(tmp_path):
     assert a.endswith("run_0") and b.endswith("run_1") and os.path.isdir(b)
 
 
-def test_shipped_default_modalities_raise_until_built():
-    """The unmodified YAML names BatchNorm + sound: the factory must say so, not fall back."""
+def test_shipped_default_yaml_builds_the_model():
+    """The unmodified YAML names BatchNorm + sound, deter = hidden = 1024, stoch = 128: the factory builds it,
+    with the reference's state-dict keys for the normalisation layers."""
     from algos.MRSSM.MRSSM.algo import build_RSSM
     import torch
     cfg = load_config(os.path.join(ENTRY, "config"), ["main.wandb=False"])
-    with pytest.raises(NotImplementedError):
-        build_RSSM(cfg, torch.device("cpu"))
+    model = build_RSSM(cfg, torch.device("cpu"))
+    sd = model.get_state_dict()
+    enc, dec = sd["encoder"], sd["observation_model"]
+    assert {"conv.0.weight", "conv.1.weight", "conv.1.bias", "conv.1.running_mean", "conv.1.running_var", "conv.1.num_batches_tracked",
+            "conv.9.weight", "conv.10.running_var"} <= set(enc["image_horizon"]) and "conv.0.bias" not in enc["image_horizon"]
+    assert {"down_sample_1.0.weight", "down_sample_2.1.running_mean", "down_sample_4.1.weight", "down_conversion.0.weight",
+            "down_conversion.1.bias"} <= set(enc["sound"]) and "down_conversion.1.running_mean" not in enc["sound"]
+    assert {"fc1.weight", "conv.0.weight", "conv.1.running_mean", "conv.7.bias", "conv.9.weight", "conv.9.bias"} <= set(dec["image_horizon"])
+    assert {"up_conversion.weight", "up_sample_0.0.weight", "up_sample_2.1.running_var", "out.weight"} <= set(dec["sound"])
+    assert tuple(dec["sound"]["up_conversion.weight"].shape) == (128 * 2 * 32 * 4, 1024 + 128, 1)

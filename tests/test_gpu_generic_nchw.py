@@ -1,0 +1,227 @@
+"""-m gpu: the exact fp32 NCHW kernels behind the shipped YAML's sound modality and BatchNorm image stacks (csrc/generic_nchw.cu,
+through the C ABI and the autograd Functions of mrssm_b200/ops.py) against torch.nn.functional on the same inputs — the layers of
+SoundEncoder_v2 / SoundDecoder_v2 (reference encoder.py:661-721, observation_model.py:420-472) and of the BatchNorm variants of
+ImageEncoder / ImageDecoder (encoder.py:324-337, observation_model.py:75-86).  Tolerance: rtol 1e-4 on values and gradients
+(fp32 accumulation-order differences only), atol scaled to the tensor."""
+import pytest
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32_reference():
+    """torch's CUDA convolutions default to TF32 (10-bit mantissa products): the reference side must be real fp32."""
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _close(a, b, rtol=1e-4):
+    scale = max(1.0, float(b.abs().max()))
+    torch.testing.assert_close(a, b, rtol=rtol, atol=2e-5 * scale)
+
+
+# (N, Cin, H, W, Cout, kernel, stride, padding): every Conv2d of the sound encoder / decoder + the BatchNorm image encoder's
+CONVS = [
+    (3, 1, 128, 20, 128, (3, 9), (1, 1), (1, 4)),       # down_sample_1
+    (2, 64, 128, 20, 256, (4, 8), (2, 2), (1, 3)),      # down_sample_2
+    (2, 128, 64, 10, 512, (4, 8), (2, 2), (1, 3)),      # down_sample_3
+    (2, 256, 32, 5, 512, (3, 4), (1, 1), (1, 1)),       # down_sample_4
+    (2, 64, 128, 20, 1, (7, 7), (1, 1), (3, 3)),        # SoundDecoder_v2.out
+    (5, 3, 64, 64, 32, (4, 4), (2, 2), (0, 0)),         # image encoder, BatchNorm variant: conv.0
+    (5, 128, 6, 6, 256, (4, 4), (2, 2), (0, 0)),        # conv.9
+    (3, 7, 9, 11, 5, (2, 3), (3, 2), (2, 0)),           # odd everything
+]
+
+
+@pytest.mark.parametrize("g", CONVS)
+def test_conv2d_matches_torch(g):
+    from mrssm_b200 import ops
+    N, Cin, H, W, Cout, k, s, p = g
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn(N, Cin, H, W, device=DEV, generator=gen, requires_grad=True)
+    w = (torch.randn(Cout, Cin, *k, device=DEV, generator=gen) / (Cin * k[0] * k[1]) ** 0.5).requires_grad_(True)
+    ref = F.conv2d(x, w, None, stride=s, padding=p)
+    go = torch.randn(ref.shape, device=DEV, generator=gen)
+    gx_ref, gw_ref = torch.autograd.grad(ref, (x, w), go)
+    w.grad = None
+    y = ops.conv2d_nobias(x, w, s, p)
+    _close(y, ref.detach())
+    (gx,) = torch.autograd.grad(y, (x,), go)
+    _close(gx, gx_ref)
+    _close(w.grad, gw_ref)
+    # the weight gradient ACCUMULATES (it lands in the optimiser's flat buffer): a second backward doubles it
+    y2 = ops.conv2d_nobias(x, w, s, p)
+    torch.autograd.grad(y2, (x,), go)
+    _close(w.grad, 2 * gw_ref)
+
+
+# (N, Cin, Hs, Ws, Cout, kernel, stride, padding): every ConvTranspose2d of the sound decoder + the BatchNorm image decoder's
+CONVTS = [
+    (2, 256, 32, 4, 512, (3, 4), (1, 1), (1, 1)),       # up_sample_0
+    (2, 256, 32, 5, 256, (4, 4), (2, 2), (1, 1)),       # up_sample_1
+    (2, 128, 64, 10, 128, (4, 4), (2, 2), (1, 1)),      # up_sample_2
+    (6, 1024, 1, 1, 128, (5, 5), (2, 2), (0, 0)),       # image decoder conv.0 on the 1x1 map
+    (3, 64, 13, 13, 32, (6, 6), (2, 2), (0, 0)),        # conv.6
+    (3, 32, 30, 30, 3, (6, 6), (2, 2), (0, 0)),         # conv.9 (with bias, added separately)
+]
+
+
+@pytest.mark.parametrize("g", CONVTS)
+def test_conv_transpose2d_matches_torch(g):
+    from mrssm_b200 import ops
+    N, Cin, Hs, Ws, Cout, k, s, p = g
+    gen = torch.Generator(device=DEV).manual_seed(2)
+    x = torch.randn(N, Cin, Hs, Ws, device=DEV, generator=gen, requires_grad=True)
+    w = (torch.randn(Cin, Cout, *k, device=DEV, generator=gen) / (Cin * k[0] * k[1]) ** 0.5).requires_grad_(True)
+    b = torch.randn(Cout, device=DEV, generator=gen).requires_grad_(True)
+    ref = F.conv_transpose2d(x, w, b, stride=s, padding=p)
+    go = torch.randn(ref.shape, device=DEV, generator=gen)
+    gx_ref, gw_ref, gb_ref = torch.autograd.grad(ref, (x, w, b), go)
+    w.grad = b.grad = None
+    y = ops.add_channel_bias(ops.conv_transpose2d_nobias(x, w, s, p), b)
+    _close(y, ref.detach())
+    (gx,) = torch.autograd.grad(y, (x,), go)
+    _close(gx, gx_ref)
+    _close(w.grad, gw_ref)
+    _close(b.grad, gb_ref)
+
+
+def test_conv1d_k1_matches_torch():
+    from mrssm_b200 import ops
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    for N, Cin, Lr, Cout in ((3, 8192, 4, 128), (5, 1152, 1, 4096)):       # down_conversion, a slice of up_conversion
+        x = torch.randn(N, Cin, Lr, device=DEV, generator=gen, requires_grad=True)
+        w = (torch.randn(Cout, Cin, 1, device=DEV, generator=gen) / Cin ** 0.5).requires_grad_(True)
+        ref = F.conv1d(x, w)
+        go = torch.randn(ref.shape, device=DEV, generator=gen)
+        gx_ref, gw_ref = torch.autograd.grad(ref, (x, w), go)
+        w.grad = None
+        y = ops.conv1d_k1(x, w)
+        _close(y, ref.detach())
+        (gx,) = torch.autograd.grad(y, (x,), go)
+        _close(gx, gx_ref)
+        _close(w.grad, gw_ref)
+
+
+@pytest.mark.parametrize("shape,relu", [((7, 32, 31, 31), True), ((4, 256, 2, 2), True), ((5, 64, 13, 13), False)])
+def test_batch_norm_matches_torch(shape, relu):
+    from mrssm_b200 import ops
+    gen = torch.Generator(device=DEV).manual_seed(4)
+    Cn = shape[1]
+    bn_ref, bn = nn.BatchNorm2d(Cn).to(DEV), nn.BatchNorm2d(Cn).to(DEV)
+    with torch.no_grad():
+        bn_ref.weight.copy_(torch.rand(Cn, device=DEV, generator=gen) + 0.5)
+        bn_ref.bias.copy_(torch.randn(Cn, device=DEV, generator=gen))
+    bn.load_state_dict(bn_ref.state_dict())
+    for step in range(2):                                             # two steps: the running statistics move twice
+        x = (torch.randn(shape, device=DEV, generator=gen) * 2 + 0.7).requires_grad_(True)
+        ref = bn_ref(x)
+        ref = F.relu(ref) if relu else ref
+        go = torch.randn(shape, device=DEV, generator=gen)
+        gx_ref, gg_ref, gb_ref = torch.autograd.grad(ref, (x, bn_ref.weight, bn_ref.bias), go)
+        bn.weight.grad = bn.bias.grad = None
+        y = ops.batch_norm(x, bn, relu=relu)
+        _close(y, ref.detach())
+        (gx,) = torch.autograd.grad(y, (x,), go)
+        _close(gx, gx_ref)
+        _close(bn.weight.grad, gg_ref)
+        _close(bn.bias.grad, gb_ref)
+        _close(bn.running_mean, bn_ref.running_mean)
+        _close(bn.running_var, bn_ref.running_var)
+        assert int(bn.num_batches_tracked) == int(bn_ref.num_batches_tracked) == step + 1
+    bn.eval(), bn_ref.eval()
+    x = torch.randn(shape, device=DEV, generator=gen).requires_grad_(True)
+    ref = F.relu(bn_ref(x)) if relu else bn_ref(x)
+    go = torch.randn(shape, device=DEV, generator=gen)
+    (gx_ref,) = torch.autograd.grad(ref, (x,), go)
+    y = ops.batch_norm(x, bn, relu=relu)
+    _close(y, ref.detach())
+    (gx,) = torch.autograd.grad(y, (x,), go)
+    _close(gx, gx_ref)
+
+
+@pytest.mark.parametrize("shape,tracked", [((3, 256, 64, 10), True), ((2, 512, 32, 4), True), ((4, 128, 4), False)])
+def test_instance_norm_matches_torch(shape, tracked):
+    from mrssm_b200 import ops
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    Cn = shape[1]
+    mk = (lambda: nn.InstanceNorm2d(Cn, affine=True, track_running_stats=True)) if tracked else (lambda: nn.InstanceNorm1d(Cn, affine=True))
+    m_ref, m = mk().to(DEV), mk().to(DEV)
+    with torch.no_grad():
+        m_ref.weight.copy_(torch.rand(Cn, device=DEV, generator=gen) + 0.5)
+        m_ref.bias.copy_(torch.randn(Cn, device=DEV, generator=gen))
+    m.load_state_dict(m_ref.state_dict())
+    for mode in (["train", "train", "eval"] if tracked else ["train", "eval"]):
+        (m.train(), m_ref.train()) if mode == "train" else (m.eval(), m_ref.eval())
+        x = (torch.randn(shape, device=DEV, generator=gen) * 1.5 - 0.3).requires_grad_(True)
+        ref = m_ref(x)
+        go = torch.randn(shape, device=DEV, generator=gen)
+        gx_ref, gg_ref, gb_ref = torch.autograd.grad(ref, (x, m_ref.weight, m_ref.bias), go)
+        m.weight.grad = m.bias.grad = None
+        y = ops.instance_norm(x, m)
+        _close(y, ref.detach())
+        (gx,) = torch.autograd.grad(y, (x,), go)
+        _close(gx, gx_ref)
+        _close(m.weight.grad, gg_ref)
+        _close(m.bias.grad, gb_ref)
+        if tracked:
+            _close(m.running_mean, m_ref.running_mean)
+            _close(m.running_var, m_ref.running_var)
+            assert int(m.num_batches_tracked) == int(m_ref.num_batches_tracked)
+
+
+def test_glu_matches_torch():
+    from mrssm_b200 import ops
+    gen = torch.Generator(device=DEV).manual_seed(6)
+    for shape in ((3, 128, 128, 20), (5, 128, 4), (2, 6, 3, 1)):
+        x = torch.randn(shape, device=DEV, generator=gen, requires_grad=True)
+        ref = F.glu(x, dim=1)
+        go = torch.randn(ref.shape, device=DEV, generator=gen)
+        (gx_ref,) = torch.autograd.grad(ref, (x,), go)
+        y = ops.GluFn.apply(x)
+        _close(y, ref.detach())
+        (gx,) = torch.autograd.grad(y, (x,), go)
+        _close(gx, gx_ref)
+
+
+def test_sound_modules_match_torch_modules_built_from_the_same_layers():
+    """SoundEncoder_v2 / SoundDecoder_v2 mirrors (their nn layers are parameter containers) against calling those very nn layers."""
+    from utils.models.encoder import SoundEncoder_v2
+    from utils.models.observation_model import SoundDecoder_v2
+    torch.manual_seed(0)
+    enc = SoundEncoder_v2(embbed_size=256).to(DEV)
+    dec = SoundDecoder_v2(belief_size=40, state_size=24).to(DEV)
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    x = torch.randn(3, 128, 20, device=DEV, generator=gen)
+    ref = x.unsqueeze(1)
+    for st in (enc.down_sample_1, enc.down_sample_2, enc.down_sample_3, enc.down_sample_4):
+        ref = st(ref)
+    ref = enc.down_conversion(ref.contiguous().view(-1, enc.conversion_channels, 4)).contiguous().view(-1, 256)
+    sd = {k: v.clone() for k, v in enc.state_dict().items()}
+    ref_stats = {k: v.clone() for k, v in enc.state_dict().items() if "running" in k}
+    enc.load_state_dict(sd)                                                          # (the torch pass above moved the statistics)
+    for k, v in enc.state_dict().items():
+        if "running_mean" in k:
+            v.zero_()
+        elif "running_var" in k:
+            v.fill_(1.0)
+    out = enc(x)
+    _close(out, ref.detach(), rtol=2e-4)
+    for k, v in enc.state_dict().items():
+        if "running" in k:
+            _close(v, ref_stats[k])
+    h, s = torch.randn(2, 3, 40, device=DEV, generator=gen), torch.randn(2, 3, 24, device=DEV, generator=gen)
+    y = dec(h, s)["loc"]                                                             # called as every caller does: (beliefs, states)
+    z = torch.cat([s.reshape(6, -1, 1), h.reshape(6, -1, 1)], dim=1)
+    z = dec.up_conversion(z).view(-1, 256, 32, 4)
+    for st in (dec.up_sample_0, dec.up_sample_1, dec.up_sample_2):
+        z = st(z)
+    z = dec.out(z).squeeze(1).reshape(2, 3, 128, 20)
+    assert y.shape == (2, 3, 128, 20)
+    _close(y, z.detach(), rtol=2e-4)

@@ -27,7 +27,11 @@ def test_train_step_matches_oracle(fusion, kw):
                                   "mopoe_over", "poe_over", "single_over",
                                   # LogProb loss (base/algo.py:164-167), LR ramp (:208-212), fc branch of the conv encoder
                                   # (encoder.py:261-262), 128x128 stacks (encoder.py:415-509, observation_model.py:162-229)
-                                  "mopoe_logprob", "single_logprob", "mopoe_lrramp", "mopoe_emb512", "mopoe_img128"])
+                                  "mopoe_logprob", "single_logprob", "mopoe_lrramp", "mopoe_emb512", "mopoe_img128",
+                                  # the shipped YAML's layers: BatchNorm image stacks (encoder.py:324-337, observation_model.py:75-86)
+                                  # and the sound modality (encoder.py:661-721, observation_model.py:420-472), running statistics
+                                  # after every step and an eval-mode pass included
+                                  "mopoe_bn", "single_bn", "mopoe_sound", "mopoe_sound_bn"])
 def test_train_step_matches_reference_fixture(name, golden_dir):
     """Directly against tests/golden/train_*.pt (outputs of the unmodified reference)."""
     rec = torch.load(os.path.join(golden_dir, f"train_{name}.pt"), weights_only=False)
@@ -53,6 +57,29 @@ def test_train_step_matches_reference_fixture(name, golden_dir):
         for k, s in step["params_after"].items():
             p = named[k].detach().cpu().reshape(-1)
             torch.testing.assert_close(p[s["idx"]], s["val"], rtol=RTOL, atol=1e-5)
+        bufs = U.named_buffers(model, oc) if "buffers_after" in step else {}
+        for k, b in step.get("buffers_after", {}).items():            # running statistics / batch counters of the norm layers
+            if b.dtype == torch.long:
+                assert int(bufs[k]) == int(b), k
+            else:
+                torch.testing.assert_close(bufs[k].detach().cpu(), b, rtol=RTOL, atol=1e-6, msg=lambda m: f"buffer {k}: {m}")
+    if "eval" in rec:                                                  # eval mode: the running statistics normalise
+        ev = rec["eval"]
+        batch, _ = O.synthetic_batch(oc, B, T, seed=ev["data_seed"])
+        dev = torch.device(DEV)
+        tgt = {n: batch["obs"][n][1:].to(dev) for n in oc.names_enc}
+        model.eval()
+        try:
+            with torch.no_grad():
+                st = model.estimate_state(tgt, batch["actions"][:-1].to(dev), None, batch["nonterminals"][:-1].to(dev), det=True)
+                out = model.observation_model(h_t=st["beliefs"], s_t=st["posterior_states"])
+        finally:
+            model.train()
+        U.assert_states_close(st, ev["states"], RTOL, 2e-5)
+        for n, s in ev["recon"].items():
+            r = (out[n] if oc.multimodal else out)["loc"].detach().cpu().reshape(-1)
+            torch.testing.assert_close(r[s["idx"]], s["val"], rtol=RTOL, atol=1e-5)
+            assert float(r.double().norm()) == pytest.approx(s["norm"], rel=RTOL), n
 
 
 @pytest.mark.parametrize("fusion", ["MoPoE", "single"])
