@@ -13,6 +13,8 @@ CONFIGS = {
     # everything on: 9 crop positions over 68x68 stored frames, Gaussian noise, PCA colour shift, a binary mask modality
     "augment": dict(side=72, names=[IMAGE, BIN, VEC], n_crop=9, dh_base=2, dw_base=2, noise_scales=[0.02, 0.05],
                     pca_scales=[0.1]),
+    # the modality set of the shipped rssm YAML: image + sound spectrogram [128, 20]
+    "shipped": dict(side=64, names=[IMAGE, "sound"], n_crop=1, dh_base=1, dw_base=1, noise_scales=[0.0], pca_scales=[0.0]),
 }
 SIZE, N, L = 40, 3, 4
 EPISODES = [9, 7, 11]
@@ -26,6 +28,8 @@ def shapes(cfg):
     out = {IMAGE: [3, 64, 64], VEC: [3]}
     if BIN in cfg["names"]:
         out[BIN] = [1, 64, 64]
+    if "sound" in cfg["names"]:
+        out["sound"] = [128, 20]
     return out
 
 
@@ -51,6 +55,8 @@ def write_dataset(root, cfg, seed=5):
                 "seed": np.arange(n + 3)}
         if BIN in cfg["names"]:
             data[BIN] = (rng.rand(n, 1, side, side) > 0.5).astype(np.uint8) * 255
+        if "sound" in cfg["names"]:
+            data["sound"] = rng.randn(n, 128, 20).astype(np.float32)
         path = os.path.join(root, "episode_%d.npy" % e)
         np.save(path, data, allow_pickle=True)
         files.append(path)

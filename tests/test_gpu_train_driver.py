@@ -150,3 +150,40 @@ def test_main_entry_point_trains_from_the_yaml_tree(tmp_path):
     fresh.load_model(ckpt)
     for a, b in zip(fresh.param_list, model.param_list):
         assert torch.equal(a, b)
+
+
+def test_main_entry_point_runs_the_unmodified_shipped_yaml(tmp_path):
+    """The shipped YAML as it is — image + sound, BatchNorm, MoPoE, deter = hidden = 1024, stoch = 128, use_amp
+    — with only the data paths, sizes and iteration counts overridden: trains, validates (eval-mode normalisation), checkpoints,
+    and the checkpoint (running statistics included) loads back."""
+    import importlib.util
+    import glob
+    from algos.MRSSM.MRSSM.algo import build_RSSM
+    from tests.test_config_entry import ENTRY
+    spec = importlib.util.spec_from_file_location("mrssm_main", os.path.join(ENTRY, "main.py"))
+    main = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(main)
+    R.write_dataset(str(tmp_path / "train"), R.CONFIGS["shipped"], seed=5)
+    R.write_dataset(str(tmp_path / "val"), R.CONFIGS["shipped"], seed=6)
+    ov = ["main.wandb=False", f"main.device={DEV}", "train.train_data_path=train", "train.validation_data_path=val",
+          f"train.experience_size={R.SIZE}", "train.batch_size=3", "train.chunk_size=4", "train.train_iteration=3",
+          "train.validation_interval=2", "train.checkpoint_interval=3"]
+    (model,) = main.main(["--cwd", str(tmp_path)] + ov)
+    c = model.cfg.rssm
+    assert list(c.observation_names_enc) == ["image_horizon", "sound"] and c.normalization == "BatchNorm"
+    assert (c.belief_size, c.hidden_size, c.state_size) == (1024, 1024, 128) and c.multimodal_params.fusion_method == "MoPoE"
+    assert model.itr_optim == 3 and torch.isfinite(model.model_loss).item()
+    bn = model.encoder.encoders["image_horizon"].conv[1]
+    assert int(bn.num_batches_tracked) == 3 and float(bn.running_var.sub(1).abs().max()) > 0
+    inorm = model.encoder.encoders["sound"].down_sample_2[1]
+    assert float(inorm.running_mean.abs().max()) > 0
+    runs = glob.glob(str(tmp_path / "results" / "*" / "*" / "run_0"))
+    ckpt = os.path.join(runs[0], "models_3.pth")
+    assert os.path.exists(ckpt)
+    fresh = build_RSSM(model.cfg, torch.device(DEV))
+    fresh.load_model(ckpt)
+    for a, b in zip(fresh.param_list, model.param_list):
+        assert torch.equal(a, b)
+    assert torch.equal(fresh.encoder.encoders["image_horizon"].conv[1].running_mean, bn.running_mean)
+    assert torch.equal(fresh.observation_model.observation_models["sound"].up_sample_1[1].running_var,
+                       model.observation_model.observation_models["sound"].up_sample_1[1].running_var)
