@@ -13,7 +13,7 @@
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+constexpr int BK = 16, NT = 256;      // tiles: (BM, BN) = (64, 64), or (256, 16) when there are at most 16 columns (BM * BN = 16 * NT)
 
 struct GC {
     int N, Cin, H, W, Cout, KH, KW, SH, SW, PH, PW, Ho, Wo;
@@ -26,10 +26,13 @@ struct GC {
 };
 
 // MODE 0: y = conv(x, w)          M = N*Ho*Wo, cols = Cout,          K = Cin*KH*KW
-// MODE 1: dx = conv^T(dy, w)      M = N*H*W,   cols = Cin,           K = Cout*KH*KW
+// MODE 1: dx = conv^T(dy, w)      cols = Cin; one grid.z slice per stride-parity class (rh, rw) of the input positions: only the
+//         taps kh = rh + i*SH, kw = rw + j*SW reach a position with (h + PH) % SH == rh, so a class is a dense GEMM with
+//         M = N*Hc*Wc rows and K = Cout*nkh*nkw (no wasted taps, the same weight tile for every row of a CTA)
 // MODE 2: dw += dy^T im2col(x)    M = Cout,    cols = Cin*KH*KW,     K = N*Ho*Wo (split over grid.z, atomics)
-template <int MODE>
+template <int MODE, int BM, int BN>
 __global__ void __launch_bounds__(NT) gconv_kernel(const GC g) {
+    constexpr int RA = BM / 16, RB = BN / 16;          // A rows / B columns each thread loads per K step
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
     const int tid = threadIdx.x, kk = tid & 15, r0 = tid >> 4;
@@ -41,28 +44,43 @@ __global__ void __launch_bounds__(NT) gconv_kernel(const GC g) {
         kend = kbeg + g.kchunk < g.K ? kbeg + g.kchunk : g.K;
     }
     const int KHW = g.KH * g.KW, HoWo = g.Ho * g.Wo, HW = g.H * g.W;
+    // MODE 1: this CTA's parity class
+    int rh = 0, rw = 0, h0 = 0, w0 = 0, Hc = 0, Wc = 0, nkh = 0, nkw = 0;
+    long long Mrows = g.M;
+    if (MODE == 1) {
+        rh = blockIdx.z / g.SW; rw = blockIdx.z - rh * g.SW;
+        h0 = ((rh - g.PH) % g.SH + g.SH) % g.SH; w0 = ((rw - g.PW) % g.SW + g.SW) % g.SW;
+        Hc = h0 < g.H ? (g.H - h0 + g.SH - 1) / g.SH : 0; Wc = w0 < g.W ? (g.W - w0 + g.SW - 1) / g.SW : 0;
+        nkh = rh < g.KH ? (g.KH - rh + g.SH - 1) / g.SH : 0; nkw = rw < g.KW ? (g.KW - rw + g.SW - 1) / g.SW : 0;
+        Mrows = (long long)g.N * Hc * Wc;
+        if (m0 >= Mrows) return;
+        kend = (long long)g.Cout * nkh * nkw;
+    }
 
     // per-thread decode of its 4 A rows and 4 B columns (fixed over the K loop)
-    int a_n[4], a_a[4], a_b[4];
-    bool a_ok[4];
-    int b_c[4], b_kh[4], b_kw[4];
-    bool b_ok[4];
+    int a_n[RA], a_a[RA], a_b[RA];
+    bool a_ok[RA];
+    int b_c[RB], b_kh[RB], b_kw[RB];
+    bool b_ok[RB];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < RA; ++j) {
         const long long m = m0 + r0 + 16 * j;
-        a_ok[j] = m < g.M;
+        a_ok[j] = m < Mrows;
         a_n[j] = a_a[j] = a_b[j] = 0;
         if (a_ok[j]) {
             if (MODE == 0) {
                 const int n = (int)(m / HoWo), r = (int)(m - (long long)n * HoWo), ho = r / g.Wo, wo = r - ho * g.Wo;
                 a_n[j] = n; a_a[j] = ho * g.SH - g.PH; a_b[j] = wo * g.SW - g.PW;
             } else if (MODE == 1) {
-                const int n = (int)(m / HW), r = (int)(m - (long long)n * HW), h = r / g.W, w = r - h * g.W;
-                a_n[j] = n; a_a[j] = h + g.PH; a_b[j] = w + g.PW;
+                const int HWc = Hc * Wc, n = (int)(m / HWc), r = (int)(m - (long long)n * HWc), hi = r / Wc, wi = r - hi * Wc;
+                a_n[j] = n; a_a[j] = (h0 + hi * g.SH + g.PH - rh) / g.SH; a_b[j] = (w0 + wi * g.SW + g.PW - rw) / g.SW;   // ho, wo of tap (rh, rw)
             } else {
                 a_n[j] = (int)m;
             }
         }
+    }
+#pragma unroll
+    for (int j = 0; j < RB; ++j) {
         const int c = n0 + r0 + 16 * j;
         b_ok[j] = c < g.Ncols;
         b_c[j] = c; b_kh[j] = b_kw[j] = 0;
@@ -77,38 +95,47 @@ __global__ void __launch_bounds__(NT) gconv_kernel(const GC g) {
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const int ty = tid >> 4, tx = tid & 15;
+    const int ty = tid / (BN / 4), tx = tid % (BN / 4);
 
     for (long long k0 = kbeg; k0 < kend; k0 += BK) {
         const long long k = k0 + kk;
         const bool kok = k < kend;
-        float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+        float av[RA], bv[RB];
+#pragma unroll
+        for (int j = 0; j < RA; ++j) av[j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < RB; ++j) bv[j] = 0.f;
         if (kok) {
             if (MODE == 0) {
                 const int ci = (int)(k / KHW), r = (int)(k - (long long)ci * KHW), kh = r / g.KW, kw = r - kh * g.KW;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < RA; ++j) {
                     const int h = a_a[j] + kh, w = a_b[j] + kw;
                     if (a_ok[j] && h >= 0 && h < g.H && w >= 0 && w < g.W)
                         av[j] = __ldg(g.x + ((long long)a_n[j] * g.Cin + ci) * HW + (long long)h * g.W + w);
-                    if (b_ok[j]) bv[j] = __ldg(g.w + (long long)b_c[j] * g.K + k);
                 }
-            } else if (MODE == 1) {
-                const int co = (int)(k / KHW), r = (int)(k - (long long)co * KHW), kh = r / g.KW, kw = r - kh * g.KW;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int th = a_a[j] - kh, tw = a_b[j] - kw;
-                    if (a_ok[j] && th >= 0 && tw >= 0 && th % g.SH == 0 && tw % g.SW == 0) {
-                        const int ho = th / g.SH, wo = tw / g.SW;
-                        if (ho < g.Ho && wo < g.Wo) av[j] = __ldg(g.dy + ((long long)a_n[j] * g.Cout + co) * HoWo + (long long)ho * g.Wo + wo);
-                    }
-                    if (b_ok[j]) bv[j] = __ldg(g.w + ((long long)co * g.Cin + b_c[j]) * KHW + r);
+                for (int j = 0; j < RB; ++j)
+                    if (b_ok[j]) bv[j] = __ldg(g.w + (long long)b_c[j] * g.K + k);
+            } else if (MODE == 1) {
+                const int nk = nkh * nkw, co = (int)(k / nk), r = (int)(k - (long long)co * nk), ti = r / nkw, tj = r - ti * nkw;
+                const int wofs = (rh + ti * g.SH) * g.KW + rw + tj * g.SW;
+#pragma unroll
+                for (int j = 0; j < RA; ++j) {
+                    const int ho = a_a[j] - ti, wo = a_b[j] - tj;
+                    if (a_ok[j] && ho >= 0 && ho < g.Ho && wo >= 0 && wo < g.Wo)
+                        av[j] = __ldg(g.dy + ((long long)a_n[j] * g.Cout + co) * HoWo + (long long)ho * g.Wo + wo);
                 }
+#pragma unroll
+                for (int j = 0; j < RB; ++j)
+                    if (b_ok[j]) bv[j] = __ldg(g.w + ((long long)co * g.Cin + b_c[j]) * KHW + wofs);
             } else {
                 const int n = (int)(k / HoWo), r = (int)(k - (long long)n * HoWo), ho = r / g.Wo, wo = r - ho * g.Wo;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < RA; ++j)
                     if (a_ok[j]) av[j] = __ldg(g.dy + ((long long)n * g.Cout + a_n[j]) * HoWo + r);
+#pragma unroll
+                for (int j = 0; j < RB; ++j) {
                     const int h = ho * g.SH - g.PH + b_kh[j], w = wo * g.SW - g.PW + b_kw[j];
                     if (b_ok[j] && h >= 0 && h < g.H && w >= 0 && w < g.W)
                         bv[j] = __ldg(g.x + ((long long)n * g.Cin + b_c[j]) * HW + (long long)h * g.W + w);
@@ -116,10 +143,9 @@ __global__ void __launch_bounds__(NT) gconv_kernel(const GC g) {
             }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            As[kk][r0 + 16 * j] = av[j];
-            Bs[kk][r0 + 16 * j] = bv[j];
-        }
+        for (int j = 0; j < RA; ++j) As[kk][r0 + 16 * j] = av[j];
+#pragma unroll
+        for (int j = 0; j < RB; ++j) Bs[kk][r0 + 16 * j] = bv[j];
         __syncthreads();
 #pragma unroll
         for (int p = 0; p < BK; ++p) {
@@ -137,14 +163,14 @@ __global__ void __launch_bounds__(NT) gconv_kernel(const GC g) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const long long m = m0 + ty * 4 + i;
-        if (m >= g.M) continue;
+        if (m >= Mrows) continue;
         long long base = 0, cstride = 1;
         if (MODE == 0) {
             const int n = (int)(m / HoWo), r = (int)(m - (long long)n * HoWo);
             base = (long long)n * g.Cout * HoWo + r; cstride = HoWo;
         } else if (MODE == 1) {
-            const int n = (int)(m / HW), r = (int)(m - (long long)n * HW);
-            base = (long long)n * g.Cin * HW + r; cstride = HW;
+            const int HWc = Hc * Wc, n = (int)(m / HWc), r = (int)(m - (long long)n * HWc), hi = r / Wc, wi = r - hi * Wc;
+            base = (long long)n * g.Cin * HW + (long long)(h0 + hi * g.SH) * g.W + (w0 + wi * g.SW); cstride = HW;
         } else {
             base = m * g.Ncols;
         }
@@ -349,8 +375,13 @@ extern "C" int mrssm_gconv_fwd(const mrssm_gconv_args* a, void* stream) {
     MRSSM_CHECK(a->x && a->w && a->y, "gconv_fwd: null tensor");
     GC g = make(a);
     g.out = a->y; g.M = (long long)a->N * a->Ho * a->Wo; g.Ncols = a->Cout; g.K = (long long)a->Cin * a->KH * a->KW;
-    dim3 grid((unsigned)ceil_div64(g.M, BM), (unsigned)ceil_div64(g.Ncols, BN));
-    gconv_kernel<0><<<grid, NT, 0, (cudaStream_t)stream>>>(g);
+    if (g.Ncols <= 16) {
+        dim3 grid((unsigned)ceil_div64(g.M, 256), 1);
+        gconv_kernel<0, 256, 16><<<grid, NT, 0, (cudaStream_t)stream>>>(g);
+    } else {
+        dim3 grid((unsigned)ceil_div64(g.M, 64), (unsigned)ceil_div64(g.Ncols, 64));
+        gconv_kernel<0, 64, 64><<<grid, NT, 0, (cudaStream_t)stream>>>(g);
+    }
     MRSSM_LAUNCH_CHECK();
     return 0;
 }
@@ -359,9 +390,15 @@ extern "C" int mrssm_gconv_dgrad(const mrssm_gconv_args* a, void* stream) {
     if (int e = check_geom(a)) return e;
     MRSSM_CHECK(a->dx && a->w && a->y, "gconv_dgrad: null tensor");
     GC g = make(a);
-    g.out = a->dx; g.M = (long long)a->N * a->H * a->W; g.Ncols = a->Cin; g.K = (long long)a->Cout * a->KH * a->KW;
-    dim3 grid((unsigned)ceil_div64(g.M, BM), (unsigned)ceil_div64(g.Ncols, BN));
-    gconv_kernel<1><<<grid, NT, 0, (cudaStream_t)stream>>>(g);
+    g.out = a->dx; g.Ncols = a->Cin; g.K = (long long)a->Cout * a->KH * a->KW;
+    g.M = (long long)a->N * ceil_div64(a->H, a->SH) * ceil_div64(a->W, a->SW);          // rows of the largest parity class
+    if (g.Ncols <= 16) {
+        dim3 grid((unsigned)ceil_div64(g.M, 256), 1, (unsigned)(a->SH * a->SW));
+        gconv_kernel<1, 256, 16><<<grid, NT, 0, (cudaStream_t)stream>>>(g);
+    } else {
+        dim3 grid((unsigned)ceil_div64(g.M, 64), (unsigned)ceil_div64(g.Ncols, 64), (unsigned)(a->SH * a->SW));
+        gconv_kernel<1, 64, 64><<<grid, NT, 0, (cudaStream_t)stream>>>(g);
+    }
     MRSSM_LAUNCH_CHECK();
     return 0;
 }
@@ -371,13 +408,17 @@ extern "C" int mrssm_gconv_wgrad(const mrssm_gconv_args* a, void* stream) {
     MRSSM_CHECK(a->x && a->dw && a->y, "gconv_wgrad: null tensor");
     GC g = make(a);
     g.out = a->dw; g.M = a->Cout; g.Ncols = a->Cin * a->KH * a->KW; g.K = (long long)a->N * a->Ho * a->Wo;
-    const long long tiles = ceil_div64(g.M, BM) * ceil_div64(g.Ncols, BN);
+    // few output channels (the 7x7 Conv2d to one channel): the transposed tile, 16 weight rows x 256 taps per CTA
+    const bool narrow = g.M <= 16;
+    const int BMw = narrow ? 16 : 64, BNw = narrow ? 256 : 64;
+    const long long tiles = ceil_div64(g.M, BMw) * ceil_div64(g.Ncols, BNw);
     long long splits = std::max<long long>(1, std::min<long long>(ceil_div64(4 * 148, tiles), g.K / (8 * BK)));
     splits = std::min<long long>(splits, 65535);
     g.kchunk = ceil_div64(ceil_div64(g.K, splits), BK) * BK;
     splits = ceil_div64(g.K, g.kchunk);
-    dim3 grid((unsigned)ceil_div64(g.M, BM), (unsigned)ceil_div64(g.Ncols, BN), (unsigned)splits);
-    gconv_kernel<2><<<grid, NT, 0, (cudaStream_t)stream>>>(g);
+    dim3 grid((unsigned)ceil_div64(g.M, BMw), (unsigned)ceil_div64(g.Ncols, BNw), (unsigned)splits);
+    if (narrow) gconv_kernel<2, 16, 256><<<grid, NT, 0, (cudaStream_t)stream>>>(g);
+    else gconv_kernel<2, 64, 64><<<grid, NT, 0, (cudaStream_t)stream>>>(g);
     MRSSM_LAUNCH_CHECK();
     return 0;
 }
