@@ -214,6 +214,9 @@ int mrssm_pl_set_debug(int32_t key, int32_t value);
 /* tuning aid: force the forward-type planner's tiling (images per tile, rows per band, activation stages, resident weights
  * 0/1, weight-ring slots); 0 / -1 = planner's choice.  Production plans come from the built-in measured table. */
 int mrssm_pl_set_plan_override(int32_t BI, int32_t TH, int32_t NA, int32_t bres, int32_t NB);
+/* Persistent plane kernels launch one CTA per SM; n_sm (default 148) caps their grids so that they can share the GPU with a kernel
+ * that occupies the other SMs (the weight gradients of the decoder beside the 32-CTA rollout BPTT). Host-side, sticky. */
+int mrssm_pl_set_sm_budget(int32_t n_sm);
 /* tuning aid: device buffer of 148*16*8 int64 receiving per-tile clock64 stamps of the fwd-type kernel (NULL = off) */
 int mrssm_pl_set_profile_buffer(void* dev_buf);
 

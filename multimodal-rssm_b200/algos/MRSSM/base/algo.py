@@ -229,7 +229,8 @@ class RSSM_base(nn.Module):
     def optimize_loss(self, observations_target, actions, rewards, nonterminals, states, itr_optim):
         self.model_optimizer.zero_grad()            # kernels accumulate straight into the flat grad buffer
         model_loss, info = self._get_model_loss(observations_target, actions, rewards, nonterminals, states)
-        model_loss.backward()
+        with ops.side_wgrad_scope():                # decoder weight gradients may run beside the rollout BPTT; joined on exit
+            model_loss.backward()
         if self.dp is not None:
             self.dp.all_reduce_grads(self.model_optimizer)
         self._ramp_lr()

@@ -34,6 +34,7 @@ long long* g_prof = nullptr;    // optional device buffer for in-kernel clock64 
 struct PlanOvr {
     int BI, TH, NA, bres, NB;
 };
+int g_sm_budget = 148;       // SMs a persistent plane kernel may occupy (mrssm_pl_set_sm_budget: kernels sharing the GPU with the rollout)
 PlanOvr g_ovr = {0, 0, 0, -1, 0};
 int g_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // bring-up switches: 0 barrier polling, 1 no fast epilogue, 2 no L2 prefetch, 3 no column-tap
                                             // replication (wgrad), 4 no grouped TMA boxes
@@ -1344,7 +1345,7 @@ int launch_fwd(const mrssm_pl_conv_args* a, int op, cudaStream_t st) {
         P.ks_off16[ks] = off;
     }
     const int n_tiles = P.n_groups * P.n_bands;
-    int grid = std::min(n_tiles, 148);
+    int grid = std::min(n_tiles, g_sm_budget);
     smem = std::max<size_t>(smem, 120 * 1024);       // > half an SM: one CTA per SM (each allocates all 512 TMEM columns)
 #define PL_LAUNCH(OPV, F32V, NCV)                                                                                                   \
     do {                                                                                                                             \
@@ -1870,7 +1871,7 @@ int plan_wgrad(const mrssm_pl_conv_args* a, WgP& P, size_t& smem_bytes, int& spl
     smem_bytes = (size_t)P.zero_bytes + 1024;
     const int n_tiles = P.n_groups * P.n_bands;
     const int ypass = P.n_cpass * P.n_mhalf;
-    splits = std::max(1, std::min(n_tiles, 148 / ypass));      // the whole grid is one wave (one CTA per SM)
+    splits = std::max(1, std::min(n_tiles, g_sm_budget / ypass));      // the whole grid is one wave (one CTA per SM)
     P.cs_valid = a->cs_valid; P.cl_valid = a->cl_valid;
     P.dw = a->dweight; P.w_ss = a->w_ss; P.w_sl = a->w_sl;
     P.scale_ptr = a->scale_ptr; P.scale_mul = a->scale_mul;
@@ -2208,6 +2209,12 @@ extern "C" int mrssm_pl_colsum(const mrssm_tv* x, int32_t n_img, int32_t H, int3
 extern "C" int mrssm_pl_set_debug(int32_t key, int32_t value) {
     MRSSM_CHECK(key >= 0 && key < 8, "pl_set_debug: bad key");
     g_dbg[key] = value;
+    return 0;
+}
+
+extern "C" int mrssm_pl_set_sm_budget(int32_t n_sm) {
+    MRSSM_CHECK(n_sm >= 8 && n_sm <= 148, "pl_set_sm_budget: %d SMs (8 .. 148)", n_sm);
+    g_sm_budget = n_sm;
     return 0;
 }
 

@@ -146,6 +146,7 @@ SYMBOLS = {
     "mrssm_pl_import_s2d": [C.POINTER(T4), _i32, _i32, _i32, _i32, _f, C.POINTER(TV), _vp],
     "mrssm_pl_describe": [C.POINTER(PlConvArgs), _i32, C.c_char_p, _i32],
     "mrssm_pl_set_plan_override": [_i32, _i32, _i32, _i32, _i32],
+    "mrssm_pl_set_sm_budget": [_i32],
     "mrssm_pl_set_debug": [_i32, _i32],
     "mrssm_pl_set_profile_buffer": [_vp],
     "mrssm_rollout_fwd": [C.POINTER(RolloutArgs), _vp],

@@ -83,9 +83,13 @@ class DataParallel:
                 t.register_hook(hook)
                 return
 
-    def _launch(self, name):
+    def _launch(self, name, final=False):
         if name in self._launched:
             return
+        if not final:
+            from . import ops
+            if name == "decoder" and ops.side_pending():
+                return      # its weight gradients are queued for / running on the side stream: exchanged from all_reduce_grads
         lo, hi = self._buckets[name]
         self._launched.append(name)
         self._pending.append(dist.all_reduce(self.model.model_optimizer.flat_g[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
@@ -100,7 +104,7 @@ class DataParallel:
             dist.all_reduce(opt.flat_g, op=dist.ReduceOp.SUM)
             return
         for name in self._buckets:
-            self._launch(name)
+            self._launch(name, final=True)       # (the backward scope has joined the side stream by now)
         # the gaps between the buckets (reward head, padding)
         pos = 0
         for lo, hi in sorted(self._buckets.values()) + [(opt.flat_g.numel(), opt.flat_g.numel())]:

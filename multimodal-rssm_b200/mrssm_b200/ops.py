@@ -10,6 +10,7 @@ clip+Adam launch consumes them.  Use ``loss.backward()``, not ``torch.autograd.g
 parameters.
 """
 import ctypes as C
+import os
 
 import torch
 from torch.autograd import Function
@@ -29,6 +30,87 @@ def grad_buf(p):
     if p.grad is None:
         p.grad = torch.zeros_like(p)
     return p.grad
+
+
+# ---- side stream: weight-gradient kernels that run beside the serial rollout BPTT ----------------------------------------------
+# The rollout BPTT occupies 32 of the 148 SMs for ~2 ms and everything after it depends on it; the decoder's weight gradients
+# depend on nothing that follows them.  The decoder's backward therefore only queues them (side_defer); the rollout's backward
+# launches them on a second stream right before its own kernel (side_flush: the first one with its grid capped to the SMs the
+# rollout leaves free), and whoever reads the gradient buffer next waits for that stream (side_join: optimiser step, DP exchange).
+_SIDE = {"stream": None, "jobs": [], "keep": [], "done": None, "active": False,
+         "enabled": os.environ.get("MRSSM_SIDE_WGRAD", "1") != "0"}        # (A/B switch for measurements)
+
+
+def set_side_wgrad(on):
+    _SIDE["enabled"] = bool(on)
+
+
+class side_wgrad_scope:
+    """`with side_wgrad_scope(): loss.backward()` — inside, weight gradients may be queued for the side stream; on exit the
+    current stream has seen all of them.  Outside such a scope every Function launches its weight gradients in place."""
+
+    def __enter__(self):
+        _SIDE["active"] = True
+        return self
+
+    def __exit__(self, *exc):
+        _SIDE["active"] = False
+        side_join()
+        return False
+
+
+def side_enabled():
+    return _SIDE["active"] and _SIDE["enabled"] and _STATE["bf16"] and L.profile is None
+
+
+def side_defer(job, tensors):
+    """Queue `job` (a closure launching kernels on torch's current stream) and keep `tensors` alive until it has run."""
+    _SIDE["jobs"].append(job)
+    _SIDE["keep"] += [t for t in tensors if t is not None]
+
+
+def side_pending():
+    return bool(_SIDE["jobs"]) or _SIDE["done"] is not None
+
+
+def side_flush(first_sm_budget=0):
+    """Launch the queued jobs on the side stream, after everything already on the current stream."""
+    jobs, keep = _SIDE["jobs"], _SIDE["keep"]
+    if not jobs:
+        return
+    if _SIDE["stream"] is None:
+        _SIDE["stream"] = torch.cuda.Stream()
+    st = _SIDE["stream"]
+    ready = torch.cuda.Event()
+    ready.record()
+    st.wait_event(ready)
+    with torch.cuda.stream(st):
+        for i, job in enumerate(jobs):
+            if i == 0 and first_sm_budget:
+                L.call_host("mrssm_pl_set_sm_budget", first_sm_budget)
+            try:
+                job()
+            finally:
+                if i == 0 and first_sm_budget:
+                    L.call_host("mrssm_pl_set_sm_budget", 148)
+        done = torch.cuda.Event()
+        done.record()
+    for t in keep:
+        t.record_stream(st)
+    _SIDE["done"] = done
+    _SIDE["jobs"], _SIDE["keep"] = [], []
+
+
+def side_join():
+    """Make the current stream see every queued / side-stream weight gradient (jobs nobody flushed run here, in order)."""
+    jobs = _SIDE["jobs"]
+    if jobs:
+        for job in jobs:
+            job()
+        _SIDE["jobs"], _SIDE["keep"] = [], []
+    if _SIDE["done"] is not None:
+        torch.cuda.current_stream().wait_event(_SIDE["done"])
+        _SIDE["done"] = None
 
 
 def _conv(fn, geom, large, small, weight_ptr, w_ss, w_sl, bias_ptr=None, act=0, mask_ptr=None, mask_mode=0,
@@ -796,6 +878,10 @@ class RolloutFn(Function):
             macs = (S + A) * D + 6 * D * D + 2 * NHh * (D * H + H * 2 * S) - NHh * D * H      # dgrad GEMVs of one step
             work = dict(bytes=4.0 * (rd + wr) * T * B + 4.0 * n_w, flops=2.0 * macs * T * B)
         if use_tc:
+            if side_pending():
+                # the decoder's queued weight gradients go to the side stream now: the first of them on the SMs this kernel leaves free
+                n_cta = -(-B // 32) if -(-B // 64) < 74 else -(-B // 64)
+                side_flush(148 - n_cta if n_cta <= 74 else 0)
             L.call("mrssm_rollout_tc_bwd", C.byref(g), L.ptr_any(tc_packed), tag="observe" if observe else "imagine", work=work)
         else:
             L.call("mrssm_rollout_bwd", C.byref(g), tag="observe" if observe else "imagine", work=work)
@@ -1663,8 +1749,14 @@ class ConvDecoderTCFn(Function):
                 nl = L.NHWC if (i > 0 and geoms[i - 1][0][4] == 1) or i == 0 else L.PARITY
                 gxt, gxv = new_act(R, Hs, Ws, Csp, nl, dev)
                 sc = scale if i == n_layers - 1 else None          # only the first consumer of the raw residual applies the scale
-                pl_conv_wgrad(gg, gv, xv, L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl, s2d_cq=cq if s2d else 0, scale=sc,
-                              dbias=grad_buf(b), dbias_from=2)
+                def wgrad_job(gg=gg, gv=gv, xv=xv, Wt=Wt, b=b, Cl=Cl, Cs=Cs, k=k, cq=cq, s2d=s2d, sc=sc):
+                    pl_conv_wgrad(gg, gv, xv, L.ptr(grad_buf(Wt)), Cl * k * k, k * k, Cs, Cl, s2d_cq=cq if s2d else 0, scale=sc,
+                                  dbias=grad_buf(b), dbias_from=2)
+                if side_enabled():
+                    grad_buf(Wt), grad_buf(b)                       # (allocated on this stream if this is the first step)
+                    side_defer(wgrad_job, [gb, xi, sc[0] if sc else None])
+                else:
+                    wgrad_job()
                 xbits = bits.get(i)                    # sign bits of this layer's input (written by the plane layer below)
                 pl_conv_down(gg, gv, gxv, packed_pl(Wt, DOWN_S2D if s2d else DOWN, Csp, gg[3], cq if s2d else 0), None, Cs, Csp,
                              mask=xv if (i > 0 and xbits is None) else None, mask_mode=RELU if i > 0 else 0, valid=(Cs, Cl),

@@ -160,7 +160,7 @@ def _bucket_worker(rank, world, port, q):
     local = opt.flat_g.clone()                          # this rank's gradient, no exchange
     order = []
     orig = dp._launch
-    dp._launch = lambda name: (order.append(name), orig(name))[1]
+    dp._launch = lambda name, final=False: (order.append(name), orig(name, final=final))[1]
     run(dp)
     launched_in_backward = list(order)
     dp.all_reduce_grads(opt)
