@@ -73,8 +73,9 @@ def side_pending():
     return bool(_SIDE["jobs"]) or _SIDE["done"] is not None
 
 
-def side_flush(first_sm_budget=0):
-    """Launch the queued jobs on the side stream, after everything already on the current stream."""
+def side_flush(first_sm_budget=0, all_jobs=False):
+    """Launch the queued jobs on the side stream, after everything already on the current stream.  first_sm_budget caps the grid of
+    the first job's persistent kernels (of every job when all_jobs)."""
     jobs, keep = _SIDE["jobs"], _SIDE["keep"]
     if not jobs:
         return
@@ -86,12 +87,13 @@ def side_flush(first_sm_budget=0):
     st.wait_event(ready)
     with torch.cuda.stream(st):
         for i, job in enumerate(jobs):
-            if i == 0 and first_sm_budget:
+            capped = bool(first_sm_budget) and (i == 0 or all_jobs)
+            if capped:
                 L.call_host("mrssm_pl_set_sm_budget", first_sm_budget)
             try:
                 job()
             finally:
-                if i == 0 and first_sm_budget:
+                if capped:
                     L.call_host("mrssm_pl_set_sm_budget", 148)
         done = torch.cuda.Event()
         done.record()
@@ -570,6 +572,9 @@ def _rollout_steps_bwd(ctx, ins, embs, outs, st, gouts):
     x_all, r_, z_, n_, ghn_, u_cat, hb_all, xin_all = st
     gouts = [None if g_ is None else _f32c(g_) for g_ in gouts]
     KX, S2p = xin_all.shape[-1], pad16(2 * S)
+    if side_pending():
+        # the decoder's queued weight gradients share the GPU with the (launch-latency-bound) per-step BPTT below
+        side_flush(int(os.environ.get("MRSSM_STEP_SIDE_SMS", "100")), all_jobs=True)
 
     g = L.RolloutBwdArgs()
     a = g.f
