@@ -473,10 +473,10 @@ def run_ours(args):
             rollout_roof[k]["serial"] = {"dependent_steps": steps_t, "us_per_step": rollout_roof[k]["launch_ms"] / steps_t * 1e3,
                                          "mma_per_step": n_mma, "mma_issue_floor_ms": floor,
                                          "frac_of_floor": floor / rollout_roof[k]["launch_ms"]}
-    step_keys = [k for k in agg if k.startswith(("rstep_", "tc_conv_down:step_", "tc_conv_up:step_")) or k == "add2"]
+    step_keys = [k for k in agg if k.startswith(("rstep_", "rollout_steps_", "tc_conv_down:step_", "tc_conv_up:step_")) or k == "add2"]
     if step_keys:       # large-model rollout (config 5): per-step launches, launch-latency-bound by construction
         ms_r = sum(agg[k]["ms"] for k in step_keys)
-        n_r = sum(agg[k]["n"] for k in step_keys)
+        n_r = 2 * (args.chunk - 1) * 8       # kernels of the two C-issued loops: 8 per time step and direction (one chunk of heads)
         rollout_roof["rollout_step(all launches)"] = {
             "bound": "latency", "ms_per_train_step": ms_r, "launches": n_r, "us_per_launch": ms_r / n_r * 1e3,
             "share_of_step": ms_r / total_ms, "dependent_steps": args.chunk - 1,

@@ -340,6 +340,32 @@ int mrssm_rstep_gate_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float
 int mrssm_rstep_xin_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float* dxin, int32_t ld, float* cgs, void* stream);
 int mrssm_add2(const float* x, const float* y, int64_t n, float* out, void* stream);
 
+/* All T steps of the large-model rollout in one call (the per-step entries above, issued from C so that a train step does not
+ * pay ~1000 Python-level launches; same kernels, same order).  Weights are the bf16 packings of mrssm_tc_pack_weight (forward:
+ * mode 0, backward: mode 1); heads are stacked: fc1 over the belief columns in n_chunks chunks of heads [chunk_c0, chunk_c1)
+ * (<= 4096 output columns each), fc2 / its dgrad as block-diagonal GEMMs.  Workspace tensors are caller-allocated:
+ *   xin_all bf16 [T,B,KX], x_all bf16 [T or 1,B,D], u_cat bf16 [T or 1,B,NH*H] (keep_all selects T), hb_all bf16 [T+1,B,D],
+ *   gi / gh fp32 [B,3D], o_cat fp32 [B,NH*S2p]; backward: d_o bf16 [T,B,NH*S2p], du_all bf16 [T,B,NH*H], d_gi / d_gh bf16 [T,B,3D],
+ *   d_xpre bf16 [T,B,D], dh_heads / carry_a / carry_b fp32 [B,D] (carries zeroed by the caller), dxin fp32 [B,S+A], cgs fp32 [B,S]
+ *   (zeroed by the caller; holds the gradient of prev_state on return), g_prev_belief fp32 [B,D]. */
+typedef struct mrssm_rstep_ws {
+    int32_t KX, S2p, NH, n_chunks, keep_all, KXo;
+    int32_t chunk_c0[MRSSM_MAX_HEADS], chunk_c1[MRSSM_MAX_HEADS];
+    const void* wp_sa; const void* wp_ih; const void* wp_hh; const void* w2f;
+    const void* w1f[MRSSM_MAX_HEADS];
+    const float* b1[MRSSM_MAX_HEADS];
+    const float* b2;
+    const float* pre_cat;
+    const void* wp_sa_b; const void* wp_ih_b; const void* wp_hh_b; const void* w1b;
+    const void* w2b[MRSSM_MAX_HEADS];
+    void* xin_all; void* x_all; void* u_cat; void* hb_all;
+    float* gi; float* gh; float* o_cat;
+    void* d_o; void* du_all; void* d_gi; void* d_gh; void* d_xpre;
+    float* dh_heads; float* carry_a; float* carry_b; float* dxin; float* cgs; float* g_prev_belief;
+} mrssm_rstep_ws;
+int mrssm_rollout_steps_fwd(const mrssm_rollout_args* a, const mrssm_rstep_ws* w, void* stream);
+int mrssm_rollout_steps_bwd(const mrssm_rollout_bwd_args* g, const mrssm_rstep_ws* w, void* stream);
+
 /* ---- the shipped YAML's remaining layers: exact fp32 kernels on NCHW tensors --------------------------------
  * General 2-d convolution without bias — rectangular kernel, any stride / zero padding: nn.Conv2d of SoundEncoder_v2 /
  * SoundDecoder_v2.out (encoder.py:661-721, observation_model.py:420-472), nn.Conv1d k1 (H = L, W = 1), and the bias-free

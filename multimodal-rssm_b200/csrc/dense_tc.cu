@@ -248,7 +248,14 @@ int dense_tc_launch(const void* A, long long lda, int M, int K, const void* wpac
     if (int rc = mrssm_tma_map_2d_sw128(&mW, wpacked, Kpad, Npad, (long long)Kpad * 2, 64, P.BN)) return rc;
     const size_t smem = (size_t)P.NS * stage + 1024;
     const int grid = std::min(P.n_mtiles * P.n_ntiles, 148);
-    MRSSM_CUDA(cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 120 * 1024)));
+    // (set once: the call takes a driver lock, and the per-step rollout launches this kernel ~1000 times per train step)
+    constexpr size_t kMaxSmem = 200 * 1024 + 1024;          // NS * stage <= 200 KB by construction of NS
+    static bool attr_set = false;
+    if (!attr_set) {
+        MRSSM_CUDA(cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        attr_set = true;
+    }
+    MRSSM_CHECK(smem <= kMaxSmem, "dense_tc: %zu bytes of shared memory", smem);
     dense_tc_kernel<<<grid, DT, std::max<size_t>(smem, 120 * 1024), st>>>(mA, mW, P);
     MRSSM_LAUNCH_CHECK();
     return 0;

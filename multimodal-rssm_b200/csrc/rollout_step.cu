@@ -258,3 +258,92 @@ extern "C" int mrssm_add2(const float* x, const float* y, int64_t n, float* out,
     MRSSM_LAUNCH_CHECK();
     return 0;
 }
+
+// ---- all T steps from C ------------------------------------------------------------------------------------------------------
+int dense_tc_launch(const void* A, long long lda, int M, int K, const void* wpacked, int Npad, int Kpad, int n_valid, const float* bias,
+                    int bias_mod, int act, const void* mask, long long ldm, int mask_mode, void* out, long long ldc, long long cstride,
+                    int out_f32, cudaStream_t st, const float* addend, long long addend_ld, int group_n, int group_k);
+
+namespace {
+// C[M][n_valid] = act(A[M][K] W^T + bias (+ addend)) (* act'(mask)); block-diagonal when gn > 0 (see dense_tc.cu)
+inline int gemm(cudaStream_t st, int M, const void* A, long long lda, int K, const void* wp, int Npad, int n_valid, const float* bias, int act,
+                const void* mask, long long ldm, int mask_mode, void* out, long long ldc, int out_f32, const float* addend = nullptr,
+                long long addend_ld = 0, int gn = 0, int gk = 0) {
+    const int Kpad = (int)(ceil_div64(gn > 0 ? gk : K, 64) * 64);
+    return dense_tc_launch(A, lda, M, K, wp, Npad, Kpad, n_valid, bias, 0, act, mask, ldm, mask_mode, out, ldc, 1, out_f32, st, addend, addend_ld,
+                           gn, gk);
+}
+inline bf16* b16(void* p, long long off) { return (bf16*)p + off; }
+}  // namespace
+
+#define RSTEP_TRY(expr)             \
+    do {                            \
+        if (int rc_ = (expr)) return rc_; \
+    } while (0)
+
+extern "C" int mrssm_rollout_steps_fwd(const mrssm_rollout_args* a, const mrssm_rstep_ws* w, void* stream) {
+    MRSSM_CHECK(a && w && w->xin_all && w->x_all && w->u_cat && w->hb_all && w->gi && w->gh && w->o_cat && w->wp_sa && w->wp_ih && w->wp_hh && w->w2f &&
+                    w->b2, "rollout_steps_fwd: null workspace / weights");
+    MRSSM_CHECK(a->D % 16 == 0 && a->H % 16 == 0 && w->NH == 1 + a->n_experts && w->n_chunks >= 1 && w->n_chunks <= MRSSM_MAX_HEADS &&
+                    w->KX >= a->S + a->A && w->S2p >= 2 * a->S, "rollout_steps_fwd: bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = a->T, B = a->B, D = a->D, H = a->H, NH = w->NH, KX = w->KX, S2p = w->S2p;
+    const long long BD = (long long)B * D, BU = (long long)B * NH * H;
+    for (int t = 0; t < T; ++t) {
+        const int ts = w->keep_all ? t : 0;
+        bf16* xin_t = b16(w->xin_all, (long long)t * B * KX);
+        bf16* x_t = b16(w->x_all, ts * BD);
+        bf16* u_t = b16(w->u_cat, ts * BU);
+        bf16* hb_t = b16(w->hb_all, t * BD);
+        bf16* hb_n = b16(w->hb_all, (t + 1) * BD);
+        RSTEP_TRY(mrssm_rstep_xin(a, t, KX, xin_t, stream));
+        RSTEP_TRY(gemm(st, B, xin_t, KX, KX, w->wp_sa, D, D, a->b_sa, a->act, nullptr, 0, 0, x_t, D, 0));
+        RSTEP_TRY(gemm(st, B, x_t, D, D, w->wp_ih, 3 * D, 3 * D, a->b_ih, 0, nullptr, 0, 0, w->gi, 3 * D, 1));
+        RSTEP_TRY(gemm(st, B, hb_t, D, D, w->wp_hh, 3 * D, 3 * D, a->b_hh, 0, nullptr, 0, 0, w->gh, 3 * D, 1));
+        RSTEP_TRY(mrssm_rstep_gate_fwd(a, t, w->gi, w->gh, hb_n, stream));
+        for (int ci = 0; ci < w->n_chunks; ++ci) {
+            const int c0 = w->chunk_c0[ci], n = (w->chunk_c1[ci] - c0) * H;
+            const float* add = w->pre_cat ? w->pre_cat + ((long long)t * B * NH * H + (long long)c0 * H) : nullptr;
+            RSTEP_TRY(gemm(st, B, hb_n, D, D, w->w1f[ci], n, n, w->b1[ci], a->act, nullptr, 0, 0, u_t + (long long)c0 * H, (long long)NH * H, 0, add,
+                           (long long)NH * H));
+        }
+        RSTEP_TRY(gemm(st, B, u_t, (long long)NH * H, NH * H, w->w2f, NH * S2p, NH * S2p, w->b2, 0, nullptr, 0, 0, w->o_cat, (long long)NH * S2p, 1,
+                       nullptr, 0, S2p, H));
+        RSTEP_TRY(mrssm_rstep_heads_fwd(a, t, w->o_cat, NH * S2p, S2p, stream));
+    }
+    return 0;
+}
+
+extern "C" int mrssm_rollout_steps_bwd(const mrssm_rollout_bwd_args* g, const mrssm_rstep_ws* w, void* stream) {
+    MRSSM_CHECK(g && w && w->x_all && w->u_cat && w->d_o && w->du_all && w->d_gi && w->d_gh && w->d_xpre && w->dh_heads && w->carry_a && w->carry_b &&
+                    w->dxin && w->cgs && w->g_prev_belief && w->wp_sa_b && w->wp_ih_b && w->wp_hh_b && w->w1b && w->keep_all,
+                "rollout_steps_bwd: null workspace / weights (the forward must have kept its stash)");
+    const mrssm_rollout_args* a = &g->f;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = a->T, B = a->B, D = a->D, H = a->H, S = a->S, A = a->A, NH = w->NH, S2p = w->S2p;
+    const long long BD = (long long)B * D, BU = (long long)B * NH * H, BO = (long long)B * NH * S2p;
+    void* d_o_ptrs[MRSSM_MAX_HEADS];
+    for (int t = T - 1; t >= 0; --t) {
+        bf16* d_o_t = b16(w->d_o, t * BO);
+        bf16* du_t = b16(w->du_all, t * BU);
+        bf16* u_t = b16(w->u_cat, t * BU);
+        bf16* x_t = b16(w->x_all, t * BD);
+        bf16* dgi_t = b16(w->d_gi, 3 * t * BD);
+        bf16* dgh_t = b16(w->d_gh, 3 * t * BD);
+        bf16* dxp_t = b16(w->d_xpre, t * BD);
+        for (int hd = 0; hd < MRSSM_MAX_HEADS; ++hd) d_o_ptrs[hd] = hd < NH ? (void*)(d_o_t + (long long)hd * S2p) : nullptr;
+        RSTEP_TRY(mrssm_rstep_heads_bwd(g, t, w->cgs, d_o_ptrs, NH * S2p, S2p, stream));
+        for (int ci = 0; ci < w->n_chunks; ++ci) {
+            const int c0 = w->chunk_c0[ci], nc = w->chunk_c1[ci] - c0;
+            RSTEP_TRY(gemm(st, B, d_o_t + (long long)c0 * S2p, (long long)NH * S2p, nc * S2p, w->w2b[ci], nc * H, nc * H, nullptr, 0,
+                           u_t + (long long)c0 * H, (long long)NH * H, a->act, du_t + (long long)c0 * H, (long long)NH * H, 0, nullptr, 0, H, S2p));
+        }
+        RSTEP_TRY(gemm(st, B, du_t, (long long)NH * H, NH * H, w->w1b, D, D, nullptr, 0, nullptr, 0, 0, w->dh_heads, D, 1));
+        RSTEP_TRY(mrssm_rstep_gate_bwd(g, t, w->dh_heads, w->carry_a, w->carry_b, dgi_t, dgh_t, stream));
+        RSTEP_TRY(gemm(st, B, dgi_t, 3 * D, 3 * D, w->wp_ih_b, D, D, nullptr, 0, x_t, D, a->act, dxp_t, D, 0));
+        RSTEP_TRY(gemm(st, B, dgh_t, 3 * D, 3 * D, w->wp_hh_b, D, D, nullptr, 0, nullptr, 0, 0, w->carry_b, D, 1));
+        RSTEP_TRY(gemm(st, B, dxp_t, D, D, w->wp_sa_b, w->KXo, S + A, nullptr, 0, nullptr, 0, 0, w->dxin, S + A, 1));
+        RSTEP_TRY(mrssm_rstep_xin_bwd(g, t, w->dxin, S + A, w->cgs, stream));
+    }
+    return mrssm_add2(w->carry_a, w->carry_b, BD, w->g_prev_belief, stream);
+}

@@ -71,6 +71,15 @@ class RolloutArgs(C.Structure):
         ("st_u", _vp * MAX_HEADS)]
 
 
+class RstepWs(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("KX", "S2p", "NH", "n_chunks", "keep_all", "KXo")] + [
+        ("chunk_c0", C.c_int32 * MAX_HEADS), ("chunk_c1", C.c_int32 * MAX_HEADS),
+        ("wp_sa", _vp), ("wp_ih", _vp), ("wp_hh", _vp), ("w2f", _vp), ("w1f", _vp * MAX_HEADS), ("b1", _vp * MAX_HEADS), ("b2", _vp),
+        ("pre_cat", _vp), ("wp_sa_b", _vp), ("wp_ih_b", _vp), ("wp_hh_b", _vp), ("w1b", _vp), ("w2b", _vp * MAX_HEADS)] + [
+        (n, _vp) for n in ("xin_all", "x_all", "u_cat", "hb_all", "gi", "gh", "o_cat", "d_o", "du_all", "d_gi", "d_gh", "d_xpre",
+                           "dh_heads", "carry_a", "carry_b", "dxin", "cgs", "g_prev_belief")]
+
+
 class GConvArgs(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("N", "Cin", "H", "W", "Cout", "KH", "KW", "SH", "SW", "PH", "PW", "Ho", "Wo")] + [
         ("x", _vp), ("w", _vp), ("y", _vp), ("dx", _vp), ("dw", _vp)]
@@ -169,6 +178,8 @@ SYMBOLS = {
     "mrssm_rstep_gate_bwd": [C.POINTER(RolloutBwdArgs), _i32, _vp, _vp, _vp, _vp, _vp, _vp],
     "mrssm_rstep_xin_bwd": [C.POINTER(RolloutBwdArgs), _i32, _vp, _i32, _vp, _vp],
     "mrssm_add2": [_vp, _vp, _i64, _vp, _vp],
+    "mrssm_rollout_steps_fwd": [C.POINTER(RolloutArgs), C.POINTER(RstepWs), _vp],
+    "mrssm_rollout_steps_bwd": [C.POINTER(RolloutBwdArgs), C.POINTER(RstepWs), _vp],
     "mrssm_gconv_fwd": [C.POINTER(GConvArgs), _vp],
     "mrssm_gconv_dgrad": [C.POINTER(GConvArgs), _vp],
     "mrssm_gconv_wgrad": [C.POINTER(GConvArgs), _vp],

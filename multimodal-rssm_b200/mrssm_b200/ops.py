@@ -462,36 +462,6 @@ def set_rollout_step(on):
     _STATE["rollout_step"] = bool(on)
 
 
-def _gemm_down(M, x_ptr, ldx, Kp, wp, Np, bias, N, out_ptr, ldo, out_f32=0, act=0, addend=None, addend_ld=0, group=None,
-               tag="step_gemm"):
-    """y[M, N] = act(x[M, Kp] W^T + bias (+ addend)); x bf16 rows (stride ldx), W packed mode 0 with Np rows, y bf16 or fp32 rows
-    (stride ldo).  group = (columns, inputs) per block of a block-diagonal W."""
-    a = _tc_args((M, 1, 1, Kp, 1, 1, Np, 1), _row_t4(x_ptr, ldx), _row_t4(out_ptr, ldo), act, None, 0, out_f32, Np, N, 0,
-                 wpacked=L.ptr(wp), bias=L.ptr(bias))
-    if addend is not None:
-        a.addend, a.addend_ld = addend, addend_ld
-    if group is not None:
-        a.group_n, a.group_k = group
-    prof = L.profile is not None
-    kk = group[1] if group else Kp
-    L.call("mrssm_tc_conv_down", C.byref(a), tag=tag if prof else None,
-           work=dict(flops=2.0 * M * kk * N, bytes=2.0 * (M * Kp + N * kk) + (4.0 if out_f32 else 2.0) * M * N) if prof else None)
-
-
-def _gemm_up(M, dy_ptr, ldy, Np_dy, wp, Kp_out, K, out_ptr, ldo, out_f32=0, mask_ptr=None, ldm=0, mask_mode=0, group=None,
-             tag="step_dgrad"):
-    """dx[M, K] = (dy[M, Np_dy] W) * act'(mask); dy bf16 rows, W packed mode 1 with Kp_out rows, dx bf16 or fp32 rows."""
-    mask = _row_t4(mask_ptr, ldm) if mask_ptr is not None else None
-    a = _tc_args((M, 1, 1, Kp_out, 1, 1, Np_dy, 1), _row_t4(out_ptr, ldo), _row_t4(dy_ptr, ldy), 0, mask, mask_mode, out_f32, Kp_out, K, 0,
-                 wpacked=L.ptr(wp), bias=None)
-    if group is not None:
-        a.group_n, a.group_k = group
-    prof = L.profile is not None
-    kk = group[1] if group else Np_dy
-    L.call("mrssm_tc_conv_up", C.byref(a), tag=tag if prof else None,
-           work=dict(flops=2.0 * M * kk * K, bytes=2.0 * (M * Np_dy + K * kk) + (4.0 if out_f32 else 2.0) * M * K) if prof else None)
-
-
 def _step_head_weights(spec, heads, has_pre, dev):
     """All heads' fc1 / fc2 weights stacked for merged launches (cached per weight version): fc1 over the belief columns as one
     GEMM per chunk of heads (<= 4096 output columns), fc2 and its dgrad as block-diagonal GEMMs (one block per head)."""
@@ -519,9 +489,21 @@ def _step_head_weights(spec, heads, has_pre, dev):
     return hit[1]
 
 
+def _step_ws(spec, E, hw, KX):
+    w = L.RstepWs()
+    NH = 1 + E
+    w.KX, w.S2p, w.NH, w.n_chunks = KX, pad16(2 * spec.S), NH, len(hw["chunks"])
+    for ci, (c0, c1) in enumerate(hw["chunks"]):
+        w.chunk_c0[ci], w.chunk_c1[ci] = c0, c1
+        w.w1f[ci], w.b1[ci], w.w2b[ci] = L.ptr(hw["w1f"][ci]), L.ptr(hw["b1"][ci]), L.ptr(hw["w2b"][ci])
+    w.w2f, w.b2, w.w1b = L.ptr(hw["w2f"]), L.ptr(hw["b2"]), L.ptr(hw["w1b"])
+    return w
+
+
 def _rollout_steps_fwd(a, spec, E, T, B, w_sa, b_sa, w_ih, w_hh, b_ih, b_hh, heads, has_pre, pre_cat, stash, dev):
-    """The T steps of transition_model.py:226-270 as per-step tcgen05 GEMMs + the kernels of csrc/rollout_step.cu.  Fills the
-    output tensors and the stash named in `a`; returns the extra stash tensors [hb_all, xin_all]."""
+    """The T steps of transition_model.py:226-270 as per-step tcgen05 GEMMs + the kernels of csrc/rollout_step.cu, issued by one C
+    call (mrssm_rollout_steps_fwd).  Fills the output tensors and the stash named in `a`; returns the extra stash tensors
+    [hb_all, xin_all]."""
     D, S, H, A = spec.D, spec.S, spec.H, spec.A
     NH, S2p = 1 + E, pad16(2 * S)
     KX = pad8(S + A)
@@ -530,30 +512,22 @@ def _rollout_steps_fwd(a, spec, E, T, B, w_sa, b_sa, w_ih, w_hh, b_ih, b_hh, hea
     x_all = stash["x"] if stash is not None else nb16(1, B, D)
     u_cat = stash["u"][0] if stash is not None else nb16(1, B, NH * H)
     hb_all = nb16(T + 1, B, D)
-    keep_all = stash is not None
     L.call("mrssm_tc_to_bf16", C.byref(_row_t4(a.prev_belief, D)), B, 1, 1, D, D, 1.0, hb_all.data_ptr())
     gi = torch.empty(B, 3 * D, device=dev, dtype=torch.float32)
     gh = torch.empty(B, 3 * D, device=dev, dtype=torch.float32)
     o_cat = torch.empty(B, NH * S2p, device=dev, dtype=torch.float32)
-    wp_sa = packed(w_sa, 0, pad16(D), KX)
-    wp_ih = packed(w_ih, 0, pad16(3 * D), D)
-    wp_hh = packed(w_hh, 0, pad16(3 * D), D)
-    hw = _step_head_weights(spec, heads, has_pre, dev)
-    for t in range(T):
-        ts = t if keep_all else 0
-        L.call("mrssm_rstep_xin", C.byref(a), t, KX, xin_all[t].data_ptr())
-        _gemm_down(B, xin_all[t].data_ptr(), KX, KX, wp_sa, D, b_sa, D, x_all[ts].data_ptr(), D, act=spec.act, tag="step_fc_embed")
-        _gemm_down(B, x_all[ts].data_ptr(), D, D, wp_ih, 3 * D, b_ih, 3 * D, gi.data_ptr(), 3 * D, out_f32=1, tag="step_gru_ih")
-        _gemm_down(B, hb_all[t].data_ptr(), D, D, wp_hh, 3 * D, b_hh, 3 * D, gh.data_ptr(), 3 * D, out_f32=1, tag="step_gru_hh")
-        L.call("mrssm_rstep_gate_fwd", C.byref(a), t, gi.data_ptr(), gh.data_ptr(), hb_all[t + 1].data_ptr())
-        for ci, (c0, c1) in enumerate(hw["chunks"]):
-            n = (c1 - c0) * H
-            add = None if pre_cat is None else pre_cat.data_ptr() + 4 * (t * B * NH * H + c0 * H)
-            _gemm_down(B, hb_all[t + 1].data_ptr(), D, D, hw["w1f"][ci], n, hw["b1"][ci], n, u_cat[ts].data_ptr() + 2 * c0 * H, NH * H,
-                       act=spec.act, addend=add, addend_ld=NH * H, tag="step_fc1")
-        _gemm_down(B, u_cat[ts].data_ptr(), NH * H, NH * H, hw["w2f"], NH * S2p, hw["b2"], NH * S2p, o_cat.data_ptr(), NH * S2p, out_f32=1,
-                   group=(S2p, H), tag="step_fc2")
-        L.call("mrssm_rstep_heads_fwd", C.byref(a), t, o_cat.data_ptr(), NH * S2p, S2p)
+    w = _step_ws(spec, E, _step_head_weights(spec, heads, has_pre, dev), KX)
+    w.keep_all = int(stash is not None)
+    w.wp_sa, w.wp_ih, w.wp_hh = L.ptr(packed(w_sa, 0, pad16(D), KX)), L.ptr(packed(w_ih, 0, pad16(3 * D), D)), L.ptr(packed(w_hh, 0, pad16(3 * D), D))
+    w.pre_cat = L.ptr(pre_cat)
+    w.xin_all, w.x_all, w.u_cat, w.hb_all = xin_all.data_ptr(), x_all.data_ptr(), u_cat.data_ptr(), hb_all.data_ptr()
+    w.gi, w.gh, w.o_cat = gi.data_ptr(), gh.data_ptr(), o_cat.data_ptr()
+    work = None
+    if L.profile is not None:
+        macs = (S + A) * D + 6 * D * D + NH * (D * H + H * 2 * S)
+        work = dict(flops=2.0 * macs * T * B, bytes=0.0)
+    L.call("mrssm_rollout_steps_fwd", C.byref(a), C.byref(w), tag="rollout_steps_fwd", work=work)
+    L.kernel_launches += T * (7 + w.n_chunks) - 1
     return [hb_all, xin_all]
 
 
@@ -602,29 +576,22 @@ def _rollout_steps_bwd(ctx, ins, embs, outs, st, gouts):
     d_gi, d_gh, d_xpre = nb16(T, B, 3 * D), nb16(T, B, 3 * D), nb16(T, B, D)
     dh_heads, carry_b, dxin = f32(B, D), torch.zeros(B, D, device=dev), f32(B, S + A)
     carry_a, cgs = torch.zeros(B, D, device=dev), torch.zeros(B, S, device=dev)
-    hw = _step_head_weights(spec, heads, [hd > 0 and spec.expert_has_emb[hd - 1] for hd in range(NH)], dev)
-    wp_ih, wp_hh = packed(w_ih, 1, pad16(3 * D), D), packed(w_hh, 1, pad16(3 * D), D)
+    w = _step_ws(spec, E, _step_head_weights(spec, heads, [hd > 0 and spec.expert_has_emb[hd - 1] for hd in range(NH)], dev), KX)
+    w.keep_all = 1
     wp_sa = packed(w_sa, 1, pad16(D), KX)
-    KXo = wp_sa.shape[1]
-    d_o_ptrs = (C.c_void_p * L.MAX_HEADS)()
-    for t in reversed(range(T)):
-        for hd in range(NH):
-            d_o_ptrs[hd] = d_o[t].data_ptr() + 2 * hd * S2p
-        L.call("mrssm_rstep_heads_bwd", C.byref(g), t, cgs.data_ptr(), d_o_ptrs, NH * S2p, S2p)
-        for ci, (c0, c1) in enumerate(hw["chunks"]):
-            _gemm_up(B, d_o[t].data_ptr() + 2 * c0 * S2p, NH * S2p, (c1 - c0) * S2p, hw["w2b"][ci], (c1 - c0) * H, (c1 - c0) * H,
-                     du_all[t].data_ptr() + 2 * c0 * H, NH * H, mask_ptr=u_cat[t].data_ptr() + 2 * c0 * H, ldm=NH * H, mask_mode=spec.act,
-                     group=(H, S2p), tag="step_fc2_dgrad")
-        _gemm_up(B, du_all[t].data_ptr(), NH * H, NH * H, hw["w1b"], D, D, dh_heads.data_ptr(), D, out_f32=1, tag="step_fc1_dgrad")
-        L.call("mrssm_rstep_gate_bwd", C.byref(g), t, dh_heads.data_ptr(), carry_a.data_ptr(), carry_b.data_ptr(), d_gi[t].data_ptr(),
-               d_gh[t].data_ptr())
-        _gemm_up(B, d_gi[t].data_ptr(), 3 * D, 3 * D, wp_ih, D, D, d_xpre[t].data_ptr(), D, mask_ptr=x_all[t].data_ptr(), ldm=D,
-                 mask_mode=spec.act, tag="step_ih_dgrad")
-        _gemm_up(B, d_gh[t].data_ptr(), 3 * D, 3 * D, wp_hh, D, D, carry_b.data_ptr(), D, out_f32=1, tag="step_hh_dgrad")
-        _gemm_up(B, d_xpre[t].data_ptr(), D, D, wp_sa, KXo, S + A, dxin.data_ptr(), S + A, out_f32=1, tag="step_sa_dgrad")
-        L.call("mrssm_rstep_xin_bwd", C.byref(g), t, dxin.data_ptr(), S + A, cgs.data_ptr())
+    w.wp_sa_b, w.wp_ih_b, w.wp_hh_b = L.ptr(wp_sa), L.ptr(packed(w_ih, 1, pad16(3 * D), D)), L.ptr(packed(w_hh, 1, pad16(3 * D), D))
+    w.KXo = wp_sa.shape[1]
     g_prev_belief = f32(B, D)
-    L.call("mrssm_add2", carry_a.data_ptr(), carry_b.data_ptr(), B * D, g_prev_belief.data_ptr())
+    w.x_all, w.u_cat = x_all.data_ptr(), u_cat.data_ptr()
+    w.d_o, w.du_all, w.d_gi, w.d_gh, w.d_xpre = d_o.data_ptr(), du_all.data_ptr(), d_gi.data_ptr(), d_gh.data_ptr(), d_xpre.data_ptr()
+    w.dh_heads, w.carry_a, w.carry_b, w.dxin, w.cgs = dh_heads.data_ptr(), carry_a.data_ptr(), carry_b.data_ptr(), dxin.data_ptr(), cgs.data_ptr()
+    w.g_prev_belief = g_prev_belief.data_ptr()
+    work = None
+    if L.profile is not None:
+        macs = (S + A) * D + 6 * D * D + NH * (D * H + H * 2 * S)
+        work = dict(flops=2.0 * macs * T * B, bytes=0.0)
+    L.call("mrssm_rollout_steps_bwd", C.byref(g), C.byref(w), tag="rollout_steps_bwd", work=work)
+    L.kernel_launches += T * (7 + w.n_chunks)
     g_prev_state = cgs
 
     # deferred, time-parallel weight gradients: dW += dY^T X over all (t, b) rows, bf16 operands as they are

@@ -63,7 +63,8 @@ def test_rollout_tc_plan_is_host_only():
 STRUCTS = {"mrssm_t4": "T4", "mrssm_conv_args": "ConvArgs", "mrssm_tc_conv_args": "TcConvArgs", "mrssm_tv": "TV",
            "mrssm_pl_conv_args": "PlConvArgs", "mrssm_rollout_args": "RolloutArgs", "mrssm_rollout_bwd_args": "RolloutBwdArgs",
            "mrssm_latent_args": "LatentArgs", "mrssm_overshoot_args": "OvershootArgs",
-           "mrssm_replay_gather_args": "ReplayGatherArgs", "mrssm_gconv_args": "GConvArgs", "mrssm_norm_args": "NormArgs"}
+           "mrssm_replay_gather_args": "ReplayGatherArgs", "mrssm_gconv_args": "GConvArgs", "mrssm_norm_args": "NormArgs",
+           "mrssm_rstep_ws": "RstepWs"}
 
 
 def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):

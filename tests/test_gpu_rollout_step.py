@@ -53,9 +53,9 @@ def test_rollout_step_forward_matches_fp32(case):
         ref = ops.RolloutFn.apply(spec, observe, det, *ins, *embs, *params)           # exact fp32 kernels
         ops.set_bf16_mode(True)
         try:
-            n0 = L.launches
+            n0 = L.kernel_launches
             out = ops.RolloutFn.apply(spec, observe, det, *ins, *embs, *params)
-            assert L.launches - n0 > 5 * case[6], "the per-step path did not run"
+            assert L.kernel_launches - n0 > 5 * case[6], "the per-step path did not run"
         finally:
             ops.set_bf16_mode(False)
     names = ["beliefs", "prior_states", "prior_means", "prior_stds", "post_states", "post_means", "post_stds"] + \
