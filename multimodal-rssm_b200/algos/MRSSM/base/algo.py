@@ -244,6 +244,7 @@ class RSSM_base(nn.Module):
     def optimize(self, D):
         self.itr_optim += 1
         ops.set_bf16_mode(bool(self.cfg.train.use_amp))      # use_amp selects the bf16 tensor-core kernels (Q11)
+        ops.forget_s2d()
         observations_target, actions, rewards, nonterminals = self._sample_data(D)
         # gradients are zeroed inside optimize_loss *before* any backward work; the forward below only
         # builds the graph
@@ -253,6 +254,7 @@ class RSSM_base(nn.Module):
     def validation(self, D):
         self.eval()
         ops.set_bf16_mode(bool(self.cfg.train.use_amp))
+        ops.forget_s2d()
         with torch.no_grad():
             observations_target, actions, rewards, nonterminals = self._sample_data(D)
             states = self.estimate_state(observations_target, actions[:-1], rewards, nonterminals[:-1])

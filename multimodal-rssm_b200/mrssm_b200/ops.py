@@ -468,7 +468,7 @@ def _step_head_weights(spec, heads, has_pre, dev):
     D, S, H = spec.D, spec.S, spec.H
     NH, S2p = len(heads), pad16(2 * S)
     key = ("step_heads", heads[0][0].data_ptr(), NH)
-    ver = (_STATE["wversion"],) + tuple(p._version for h in heads for p in h) + tuple(has_pre)
+    ver = (_STATE["wversion"],) + tuple(p._version for h in heads for p in h) + tuple(has_pre) + tuple(_tok(p) for h in heads for p in h)
     hit = _wcache.get(key)
     if hit is None or hit[0] != ver:
         per = max(1, 4096 // H)
@@ -1300,6 +1300,17 @@ def pl_import_s2d(src_t4, n, H, W, Cc, device, scale=1.0):
 # ---- bf16 tensor-core mode ------------------------------------------------------------------------------------
 _STATE = {"bf16": False, "wversion": 0}
 _wcache = {}
+_tok_counter = [0]
+
+
+def _tok(w):
+    """Identity token of a weight tensor OBJECT: cached packings are keyed by address + versions, and a new tensor that lands on a
+    freed tensor's address (a second model, a test's next parameter set) starts at the same versions — its token differs."""
+    t = getattr(w, "_mrssm_tok", None)
+    if t is None:
+        _tok_counter[0] += 1
+        t = w._mrssm_tok = _tok_counter[0]
+    return t
 
 
 def set_bf16_mode(on):
@@ -1347,7 +1358,7 @@ def rollout_tc_weights(spec, E, w_sa, w_ih, w_hh, heads, dev, bwd=False):
     plan, n_pack, packed_bytes = rollout_tc_plan(D, S, H, A, E, dev, bwd)
     ws = [w_sa, w_ih, w_hh] + [w for hd in heads for w in (hd[0], hd[2])]
     key = ("rollout_tc", E, bwd) + tuple(w.data_ptr() for w in ws)
-    ver = (_STATE["wversion"],) + tuple(w._version for w in ws)
+    ver = (_STATE["wversion"],) + tuple(w._version for w in ws) + tuple(_tok(w) for w in ws)
     hit = _wcache.get(key)
     if hit is None or hit[0] != ver:
         pa = L.RolloutArgs()
@@ -1369,7 +1380,7 @@ def bump_weight_version():
 
 def packed(w, mode, Cs_pad, Cl_pad):
     key = (w.data_ptr(), mode, Cs_pad, Cl_pad)
-    ver = (_STATE["wversion"], w._version)
+    ver = (_STATE["wversion"], w._version, _tok(w))
     hit = _wcache.get(key)
     if hit is None or hit[0] != ver:
         w4 = w if w.dim() == 4 else w.reshape(w.shape[0], w.shape[1], 1, 1)
@@ -1382,7 +1393,7 @@ def packed_cols(w, col0, ncols, mode):
     """Cached tcgen05 packing of the column block w[:, col0:col0+ncols] of a Linear weight [out, in] (mode 0: y = x W^T,
     mode 1: dx = dy W)."""
     key = (w.data_ptr(), "cols", col0, ncols, mode)
-    ver = (_STATE["wversion"], w._version)
+    ver = (_STATE["wversion"], w._version, _tok(w))
     hit = _wcache.get(key)
     if hit is None or hit[0] != ver:
         Cs, ld = w.shape
@@ -1405,7 +1416,7 @@ def _bf16(*shape, device):
 def packed_pl(w, op, Cs_pad, Cl_pad, s2d_cq=0):
     """Cached plane-kernel packing of a conv weight (re-packed when the master changes)."""
     key = (w.data_ptr(), "pl", op, Cs_pad, Cl_pad, s2d_cq)
-    ver = (_STATE["wversion"], w._version)
+    ver = (_STATE["wversion"], w._version, _tok(w))
     hit = _wcache.get(key)
     if hit is None or hit[0] != ver:
         hit = (ver, pl_pack_weight(w.detach(), op, Cs_pad, Cl_pad, s2d_cq))
@@ -1514,6 +1525,12 @@ def remember_s2d(x, s2d):
 
 def recall_s2d(target):
     return _S2D.get((target.data_ptr(), tuple(target.shape), target._version))
+
+
+def forget_s2d():
+    """Called at the start of every optimize / validation: an entry never outlives the iteration whose encoder made it (a later
+    tensor may land on the same address)."""
+    _S2D.clear()
 
 
 class ConvEncoderTCFn(Function):
