@@ -323,7 +323,7 @@ def roofline_of(key, d, pk, total_ms):
     ms = d["ms"] / d["n"]
     flops, byts = d["flops"] / d["n"], d["bytes"] / d["n"]
     ridge = pk["tf_sust"] * 1e12 / (pk["hbm"] * 1e9)
-    tensor_bound = byts > 0 and flops / byts > ridge
+    tensor_bound = flops > 0 and (byts <= 0 or flops / byts > ridge)      # (multi-launch calls report flops only)
     if tensor_bound:
         ach = flops / (ms * 1e-3) / 1e12
         out = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"]}
