@@ -388,6 +388,17 @@ int mrssm_gconv_fwd(const mrssm_gconv_args* a, void* stream);
 int mrssm_gconv_dgrad(const mrssm_gconv_args* a, void* stream);
 int mrssm_gconv_wgrad(const mrssm_gconv_args* a, void* stream);
 
+/* Staging kernels of the bf16 tensor-core route of the same convolutions (bf16 mode, channels in multiples of 8; ops.GConvTCFn):
+ * NCHW fp32 -> NHWC bf16, explicit im2col rows col[(n,ho,wo)][(kh,kw,ci)] (and the matching col2im gather, fp32 NHWC out), NHWC fp32 ->
+ * NCHW fp32, and the weight / weight-gradient permutation between [Cout][Cin][KH*KW] and the GEMM's tap-major [Cout][(tap, ci)].
+ * The GEMMs themselves are mrssm_tc_conv_down / up / wgrad on the rows. */
+int mrssm_nchw_to_nhwc_bf16(const float* x, int64_t N, int32_t C, int32_t HW, void* out, void* stream);
+int mrssm_nhwc_to_nchw_f32(const float* x, int64_t N, int32_t C, int32_t HW, float* out, void* stream);
+int mrssm_im2col_nhwc(const mrssm_gconv_args* a, const void* x_nhwc, void* col, void* stream);
+int mrssm_col2im_nhwc(const mrssm_gconv_args* a, const void* dcol, float* dx_nhwc, void* stream);
+int mrssm_gconv_weight_perm(const float* w, int64_t Cout, int32_t Cin, int32_t KHW, float* w2, void* stream);
+int mrssm_gconv_weight_perm_add(const float* dw2, int64_t Cout, int32_t Cin, int32_t KHW, float* grad, void* stream);
+
 /* nn.BatchNorm2d (instance = 0: one mean / biased variance per channel over (n, h, w)) and nn.InstanceNorm2d / 1d (instance = 1: per
  * (n, c) plane) with affine parameters, x / y [N,C,HW] fp32, optional fused ReLU (the Conv - BatchNorm - ReLU triples).
  *   batch_stats = 1 (train mode; InstanceNorm without tracked statistics always): statistics of this batch are written to

@@ -366,6 +366,94 @@ __global__ void chan_bias_bwd_kernel(const float* __restrict__ g, int N, int C, 
     if (threadIdx.x == 0) atomicAdd(dbias + c, (float)s);
 }
 
+// ---- bf16 tensor-core route of the general convolution (bf16 mode): NHWC staging, explicit im2col rows, dense tcgen05 GEMMs ----
+// batched transpose in[n][A][B] -> out[n][B][A] with conversion (NCHW fp32 -> NHWC bf16: A = C, B = HW; NHWC fp32 -> NCHW fp32: A = HW, B = C)
+template <typename Tin, typename Tout>
+__global__ void btranspose_kernel(const Tin* __restrict__ in, int A, int B, Tout* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const long long img = blockIdx.z;
+    const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+    const Tin* ip = in + img * (long long)A * B;
+    Tout* op = out + img * (long long)A * B;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int a = a0 + i, b = b0 + threadIdx.x;
+        tile[i][threadIdx.x] = (a < A && b < B) ? (float)ip[(long long)a * B + b] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int b = b0 + i, a = a0 + threadIdx.x;
+        if (a < A && b < B) op[(long long)b * A + a] = (Tout)tile[threadIdx.x][i];
+    }
+}
+
+// col[m][tap * Cin + ci] = x_nhwc[n][ho*SH - PH + kh][wo*SW - PW + kw][ci]  (bf16, 8 channels = 16 bytes per thread)
+__global__ void im2col_nhwc_kernel(const uint4* __restrict__ x, int N, int H, int W, int C8, int KH, int KW, int SH, int SW, int PH, int PW,
+                                   int Ho, int Wo, uint4* __restrict__ col) {
+    const long long total = (long long)N * Ho * Wo * KH * KW * C8;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % C8);
+        long long r = e / C8;
+        const int tap = (int)(r % (KH * KW));
+        r /= KH * KW;
+        const int wo = (int)(r % Wo);
+        r /= Wo;
+        const int ho = (int)(r % Ho), n = (int)(r / Ho);
+        const int kh = tap / KW, kw = tap - kh * KW, h = ho * SH - PH + kh, w = wo * SW - PW + kw;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(x + (((long long)n * H + h) * W + w) * C8 + c);
+        col[e] = v;
+    }
+}
+
+// dx_nhwc[n][h][w][ci] = sum over the taps that reach (h, w) of dcol[(n, ho, wo)][tap * Cin + ci]   (fp32 accumulate / output)
+__global__ void col2im_nhwc_kernel(const uint4* __restrict__ dcol, int N, int H, int W, int C8, int KH, int KW, int SH, int SW, int PH, int PW,
+                                   int Ho, int Wo, float4* __restrict__ dx) {
+    const long long total = (long long)N * H * W * C8;
+    const long long rowv = (long long)KH * KW * C8;          // uint4 per im2col row
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % C8);
+        long long r = e / C8;
+        const int w = (int)(r % W);
+        r /= W;
+        const int h = (int)(r % H), n = (int)(r / H);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int kh = (h + PH) % SH; kh < KH; kh += SH) {
+            const int ho = (h + PH - kh) / SH;
+            if (ho < 0 || ho >= Ho) continue;
+            for (int kw = (w + PW) % SW; kw < KW; kw += SW) {
+                const int wo = (w + PW - kw) / SW;
+                if (wo < 0 || wo >= Wo) continue;
+                const uint4 v = __ldg(dcol + (((long long)n * Ho + ho) * Wo + wo) * rowv + (long long)(kh * KW + kw) * C8 + c);
+                const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __bfloat1622float2(p[i]);
+                    acc[2 * i] += f.x; acc[2 * i + 1] += f.y;
+                }
+            }
+        }
+        dx[2 * e] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        dx[2 * e + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+}
+
+// grad[co][ci][tap] += dw2[co][tap * Cin + ci]   (the GEMM's tap-major weight gradient back into the parameter's layout)
+__global__ void wperm_add_kernel(const float* __restrict__ dw2, long long total, int Cin, int KHW, float* __restrict__ grad) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long K = (long long)Cin * KHW, co = e / K, k = e - co * K;
+        const int tap = (int)(k / Cin), ci = (int)(k - (long long)tap * Cin);
+        grad[co * K + (long long)ci * KHW + tap] += dw2[e];
+    }
+}
+// w2[co][tap * Cin + ci] = w[co][ci][tap]
+__global__ void wperm_kernel(const float* __restrict__ w, long long total, int Cin, int KHW, float* __restrict__ w2) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long K = (long long)Cin * KHW, co = e / K, k = e - co * K;
+        const int tap = (int)(k / Cin), ci = (int)(k - (long long)tap * Cin);
+        w2[e] = w[co * K + (long long)ci * KHW + tap];
+    }
+}
+
 inline int ew_blocks(long long total) { return (int)std::max<long long>(1, std::min<long long>(148 * 16, (total + 255) / 256)); }
 
 }  // namespace
@@ -495,6 +583,54 @@ extern "C" int mrssm_chan_bias_bwd(const float* g, int64_t N, int32_t C, int32_t
     MRSSM_CHECK(g && dbias && N > 0 && C > 0 && HW > 0, "chan_bias_bwd: bad arguments");
     dim3 grid((unsigned)C, (unsigned)std::min<long long>(N, 64));
     chan_bias_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, (int)N, C, HW, dbias);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- staging kernels of the tensor-core route (mrssm_b200/ops.py: GConvTCFn) -----------------------------------------------------
+extern "C" int mrssm_nchw_to_nhwc_bf16(const float* x, int64_t N, int32_t C, int32_t HW, void* out, void* stream) {
+    MRSSM_CHECK(x && out && N > 0 && N <= 65535 && C > 0 && HW > 0, "nchw_to_nhwc_bf16: bad arguments");
+    dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N), block(32, 8);
+    btranspose_kernel<float, __nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(x, C, HW, (__nv_bfloat16*)out);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int mrssm_nhwc_to_nchw_f32(const float* x, int64_t N, int32_t C, int32_t HW, float* out, void* stream) {
+    MRSSM_CHECK(x && out && N > 0 && N <= 65535 && C > 0 && HW > 0, "nhwc_to_nchw_f32: bad arguments");
+    dim3 grid((unsigned)((C + 31) / 32), (unsigned)((HW + 31) / 32), (unsigned)N), block(32, 8);
+    btranspose_kernel<float, float><<<grid, block, 0, (cudaStream_t)stream>>>(x, HW, C, out);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int mrssm_im2col_nhwc(const mrssm_gconv_args* a, const void* x_nhwc, void* col, void* stream) {
+    if (int e = check_geom(a)) return e;
+    MRSSM_CHECK(x_nhwc && col && a->Cin % 8 == 0, "im2col_nhwc: needs bf16 NHWC input with channels in multiples of 8");
+    const long long total = (long long)a->N * a->Ho * a->Wo * a->KH * a->KW * (a->Cin / 8);
+    im2col_nhwc_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)x_nhwc, a->N, a->H, a->W, a->Cin / 8, a->KH, a->KW, a->SH,
+                                                                          a->SW, a->PH, a->PW, a->Ho, a->Wo, (uint4*)col);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int mrssm_col2im_nhwc(const mrssm_gconv_args* a, const void* dcol, float* dx_nhwc, void* stream) {
+    if (int e = check_geom(a)) return e;
+    MRSSM_CHECK(dcol && dx_nhwc && a->Cin % 8 == 0, "col2im_nhwc: needs channels in multiples of 8");
+    const long long total = (long long)a->N * a->H * a->W * (a->Cin / 8);
+    col2im_nhwc_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)dcol, a->N, a->H, a->W, a->Cin / 8, a->KH, a->KW, a->SH,
+                                                                          a->SW, a->PH, a->PW, a->Ho, a->Wo, (float4*)dx_nhwc);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int mrssm_gconv_weight_perm(const float* w, int64_t Cout, int32_t Cin, int32_t KHW, float* w2, void* stream) {
+    MRSSM_CHECK(w && w2 && Cout > 0 && Cin > 0 && KHW > 0, "gconv_weight_perm: bad arguments");
+    const long long total = (long long)Cout * Cin * KHW;
+    wperm_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(w, total, Cin, KHW, w2);
+    MRSSM_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int mrssm_gconv_weight_perm_add(const float* dw2, int64_t Cout, int32_t Cin, int32_t KHW, float* grad, void* stream) {
+    MRSSM_CHECK(dw2 && grad && Cout > 0 && Cin > 0 && KHW > 0, "gconv_weight_perm_add: bad arguments");
+    const long long total = (long long)Cout * Cin * KHW;
+    wperm_add_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(dw2, total, Cin, KHW, grad);
     MRSSM_LAUNCH_CHECK();
     return 0;
 }

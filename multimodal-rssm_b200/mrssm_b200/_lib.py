@@ -183,6 +183,12 @@ SYMBOLS = {
     "mrssm_gconv_fwd": [C.POINTER(GConvArgs), _vp],
     "mrssm_gconv_dgrad": [C.POINTER(GConvArgs), _vp],
     "mrssm_gconv_wgrad": [C.POINTER(GConvArgs), _vp],
+    "mrssm_nchw_to_nhwc_bf16": [_vp, _i64, _i32, _i32, _vp, _vp],
+    "mrssm_nhwc_to_nchw_f32": [_vp, _i64, _i32, _i32, _vp, _vp],
+    "mrssm_im2col_nhwc": [C.POINTER(GConvArgs), _vp, _vp, _vp],
+    "mrssm_col2im_nhwc": [C.POINTER(GConvArgs), _vp, _vp, _vp],
+    "mrssm_gconv_weight_perm": [_vp, _i64, _i32, _i32, _vp, _vp],
+    "mrssm_gconv_weight_perm_add": [_vp, _i64, _i32, _i32, _vp, _vp],
     "mrssm_norm_fwd": [C.POINTER(NormArgs), _vp],
     "mrssm_norm_bwd": [C.POINTER(NormArgs), _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mrssm_glu_fwd": [_vp, _i64, _i32, _i32, _vp, _vp],

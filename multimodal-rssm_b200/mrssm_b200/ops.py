@@ -1918,11 +1918,18 @@ class GluFn(Function):
 
 
 def conv2d_nobias(x, w, stride=1, padding=0):
-    return GConvFn.apply(x, w, stride, padding, False)
+    s_, p_ = _pair(stride), _pair(padding)
+    KH, KW = w.shape[2], (w.shape[3] if w.dim() == 4 else 1)
+    rows = x.shape[0] * ((x.shape[2] + 2 * p_[0] - KH) // s_[0] + 1) * ((x.shape[3] + 2 * p_[1] - KW) // s_[1] + 1)
+    fn = GConvTCFn if gconv_tc_eligible(w.shape[1], w.shape[0], KH, KW, rows) else GConvFn
+    return fn.apply(x, w, stride, padding, False)
 
 
 def conv_transpose2d_nobias(x, w, stride=1, padding=0):
-    return GConvFn.apply(x, w, stride, padding, True)
+    KH, KW = w.shape[2], w.shape[3]
+    rows = x.shape[0] * x.shape[2] * x.shape[3]
+    fn = GConvTCFn if gconv_tc_eligible(w.shape[1], w.shape[0], KH, KW, rows) else GConvFn     # conv view: Cin = w.shape[1], Cout = w.shape[0]
+    return fn.apply(x, w, stride, padding, True)
 
 
 def batch_norm(x, bn, relu=False):
@@ -1970,3 +1977,171 @@ class ChannelBiasFn(Function):
 
 def add_channel_bias(x, bias):
     return ChannelBiasFn.apply(x, bias)
+
+
+# ---- the same convolutions on the tensor cores (bf16 mode): NHWC bf16 staging, explicit im2col rows, dense tcgen05 GEMMs ------------
+_GC_COL_BYTES = 2 << 30          # im2col rows materialised per chunk of images
+
+
+def set_gconv_tc(on):
+    _STATE["gconv_tc"] = bool(on)
+
+
+def gconv_tc_eligible(Cin, Cout, KH, KW, rows):
+    """bf16 mode, channels in tensor-core granules, enough work to fill the GEMM tiles (the 128 .. 512-channel sound layers, the
+    BatchNorm image stacks' inner layers); everything else stays on the exact fp32 kernels."""
+    return (_STATE["bf16"] and _STATE.get("gconv_tc", True) and Cin % 8 == 0 and Cout % 16 == 0 and Cout <= 4096 and Cin * KH * KW >= 256
+            and (Cin * KH * KW) % 16 == 0
+            and Cout >= 32 and rows >= 1024)
+
+
+class _GcTc:
+    """One convolution geometry (conv view: x [N,Cin,H,W], w [Cout,Cin,KH,KW], y [N,Cout,Ho,Wo]) in chunks of images."""
+
+    def __init__(self, geom, w, dev):
+        (self.N, self.Cin, self.H, self.W, self.Cout, self.KH, self.KW, self.stride, self.padding, self.Ho, self.Wo) = geom
+        self.K = self.Cin * self.KH * self.KW
+        self.dev = dev
+        self.nb = max(1, min(self.N, 65535, _GC_COL_BYTES // (self.Ho * self.Wo * self.K * 2)))
+        self.w = w
+        self._w2 = None
+
+    def w2(self):
+        """fp32 [Cout, (tap, ci)] copy of the weight: the K order of the NHWC im2col rows."""
+        if self._w2 is None:
+            self._w2 = torch.empty(self.Cout, self.K, device=self.dev, dtype=torch.float32)
+            L.call("mrssm_gconv_weight_perm", L.ptr(self.w), self.Cout, self.Cin, self.KH * self.KW, L.ptr(self._w2))
+        return self._w2
+
+    def args(self, n):
+        return L.GConvArgs(n, self.Cin, self.H, self.W, self.Cout, self.KH, self.KW, self.stride[0], self.stride[1], self.padding[0],
+                           self.padding[1], self.Ho, self.Wo, None, None, None, None, None)
+
+    def chunks(self):
+        for n0 in range(0, self.N, self.nb):
+            yield n0, min(self.nb, self.N - n0)
+
+    def nhwc_bf16(self, t, n0, n, Cc, HW):
+        """images n0 .. n0+n of an fp32 NCHW tensor -> bf16 [n*HW, Cc] rows"""
+        out = torch.empty(n * HW, Cc, device=self.dev, dtype=torch.bfloat16)
+        L.call("mrssm_nchw_to_nhwc_bf16", t.data_ptr() + 4 * n0 * Cc * HW, n, Cc, HW, L.ptr(out))
+        return out
+
+    def to_nchw(self, rows, t, n0, n, Cc, HW):
+        """fp32 [n*HW, Cc] rows -> images n0 .. n0+n of the fp32 NCHW tensor t"""
+        L.call("mrssm_nhwc_to_nchw_f32", L.ptr(rows), n, Cc, HW, t.data_ptr() + 4 * n0 * Cc * HW)
+
+    def im2col(self, xh, n):
+        col = torch.empty(n * self.Ho * self.Wo, self.K, device=self.dev, dtype=torch.bfloat16)
+        L.call("mrssm_im2col_nhwc", C.byref(self.args(n)), L.ptr(xh), L.ptr(col))
+        return col
+
+    def rows_times_wT(self, col, M):
+        """[M, K] bf16 rows x w2^T -> fp32 [M, Cout]"""
+        out = torch.empty(M, self.Cout, device=self.dev, dtype=torch.float32)
+        wp = tc_pack_weight(self.w2().reshape(self.Cout, self.K, 1, 1), 0, self.Cout, self.K) if not hasattr(self, "_wp0") else self._wp0
+        self._wp0 = wp
+        tc_conv_down((M, 1, 1, self.K, 1, 1, self.Cout, 1), _row_t4(col.data_ptr(), self.K), _row_t4(out.data_ptr(), self.Cout), wp, None,
+                     self.Cout, out_f32=1, valid=(self.Cout, self.K))
+        return out
+
+    def rows_times_w(self, yh, M):
+        """[M, Cout] bf16 rows x w2 -> bf16 [M, K] (the gradient of the im2col rows), <= 4096 columns per GEMM"""
+        dcol = torch.empty(M, self.K, device=self.dev, dtype=torch.bfloat16)
+        if not hasattr(self, "_wp1"):
+            self._wp1 = []
+            for c0 in range(0, self.K, 4096):
+                nc = min(4096, self.K - c0)
+                Npad, Kpad = pad16(nc), pad64(self.Cout)
+                wp = torch.empty(4, Npad, Kpad, device=self.dev, dtype=torch.bfloat16)
+                L.call("mrssm_tc_pack_weight", self.w2().data_ptr() + 4 * c0, self.K, 1, self.Cout, nc, self.Cout, pad8(nc), 1, 1, Npad, Kpad,
+                       L.ptr(wp))
+                self._wp1.append((c0, nc, wp))
+        for c0, nc, wp in self._wp1:
+            tc_conv_up((M, 1, 1, pad16(nc), 1, 1, self.Cout, 1), _row_t4(dcol.data_ptr() + 2 * c0, self.K), _row_t4(yh.data_ptr(), self.Cout),
+                       wp, None, nc, valid=(self.Cout, nc))
+        return dcol
+
+    def col2im(self, dcol, n):
+        out = torch.empty(n * self.H * self.W, self.Cin, device=self.dev, dtype=torch.float32)
+        L.call("mrssm_col2im_nhwc", C.byref(self.args(n)), L.ptr(dcol), L.ptr(out))
+        return out
+
+    def wgrad(self, col, yh, M, dw2):
+        """dw2[Cout, K] += yh^T col"""
+        tc_conv_wgrad((M, 1, 1, self.K, 1, 1, self.Cout, 1), _row_t4(col.data_ptr(), self.K), _row_t4(yh.data_ptr(), self.Cout), L.ptr(dw2),
+                      self.K, 1, self.Cout, self.K)
+
+    def add_wgrad(self, dw2):
+        L.call("mrssm_gconv_weight_perm_add", L.ptr(dw2), self.Cout, self.Cin, self.KH * self.KW, L.ptr(grad_buf(self.w)))
+
+
+class GConvTCFn(Function):
+    """GConvFn on the tensor cores: same arguments and results (fp32 NCHW in / out, weight gradient accumulated into weight.grad),
+    bf16 operands, fp32 accumulation.  The im2col rows of a chunk of images are materialised in bf16 (recomputed in backward
+    rather than kept)."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, padding, transposed):
+        x = _f32c(x)
+        stride, padding = _pair(stride), _pair(padding)
+        KH, KW = w.shape[2], (w.shape[3] if w.dim() == 4 else 1)
+        N = x.shape[0]
+        if not transposed:
+            Cin, H, W = x.shape[1:]
+            Cout = w.shape[0]
+            Ho, Wo = (H + 2 * padding[0] - KH) // stride[0] + 1, (W + 2 * padding[1] - KW) // stride[1] + 1
+        else:
+            Cout, Ho, Wo = x.shape[1:]
+            Cin = w.shape[1]
+            H, W = (Ho - 1) * stride[0] - 2 * padding[0] + KH, (Wo - 1) * stride[1] - 2 * padding[1] + KW
+        geom = (N, Cin, H, W, Cout, KH, KW, stride, padding, Ho, Wo)
+        g = _GcTc(geom, w, x.device)
+        if not transposed:
+            out = torch.empty(N, Cout, Ho, Wo, device=x.device, dtype=torch.float32)
+            for n0, n in g.chunks():
+                col = g.im2col(g.nhwc_bf16(x, n0, n, Cin, H * W), n)
+                g.to_nchw(g.rows_times_wT(col, n * Ho * Wo), out, n0, n, Cout, Ho * Wo)
+                del col
+        else:
+            out = torch.empty(N, Cin, H, W, device=x.device, dtype=torch.float32)
+            for n0, n in g.chunks():
+                dcol = g.rows_times_w(g.nhwc_bf16(x, n0, n, Cout, Ho * Wo), n * Ho * Wo)
+                g.to_nchw(g.col2im(dcol, n), out, n0, n, Cin, H * W)
+                del dcol
+        ctx.geom, ctx.transposed, ctx.w = geom, transposed, w
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        (x,) = ctx.saved_tensors
+        go = _f32c(go)
+        w, geom = ctx.w, ctx.geom
+        N, Cin, H, W, Cout, KH, KW, stride, padding, Ho, Wo = geom
+        g = _GcTc(geom, w, x.device)
+        need_x, need_w = ctx.needs_input_grad[0], w.requires_grad
+        gx = torch.empty_like(x) if need_x else None
+        dw2 = torch.zeros(Cout, g.K, device=x.device, dtype=torch.float32) if need_w else None
+        for n0, n in g.chunks():
+            M = n * Ho * Wo
+            if not ctx.transposed:
+                yh = g.nhwc_bf16(go, n0, n, Cout, Ho * Wo)                 # output gradient rows [M, Cout]
+                if need_w:
+                    col = g.im2col(g.nhwc_bf16(x, n0, n, Cin, H * W), n)
+                    g.wgrad(col, yh, M, dw2)
+                    del col
+                if need_x:
+                    dcol = g.rows_times_w(yh, M)
+                    g.to_nchw(g.col2im(dcol, n), gx, n0, n, Cin, H * W)
+                    del dcol
+            else:
+                col = g.im2col(g.nhwc_bf16(go, n0, n, Cin, H * W), n)      # im2col rows of the (large) output gradient
+                if need_w:
+                    g.wgrad(col, g.nhwc_bf16(x, n0, n, Cout, Ho * Wo), M, dw2)
+                if need_x:
+                    g.to_nchw(g.rows_times_wT(col, M), gx, n0, n, Cout, Ho * Wo)
+                del col
+        if need_w:
+            g.add_wgrad(dw2)
+        return gx, None, None, None, None

@@ -197,6 +197,7 @@ def run_train_parity_bf16(fusion, B, T, steps, device, **cfg_kw):
         den = sum(float((g ** 2).sum()) for g in ref["grads"].values())
         rep["grad_rel_fro"] = max(rep["grad_rel_fro"], (num / den) ** 0.5)
         # keep the oracle on the product's trajectory so step 2 compares like with like
+        bufs = named_buffers(model, oc) if any(O.is_buffer(k) for k in P) else {}
         for k in P:
-            P[k].copy_(named[k].detach().cpu())
+            P[k].copy_((bufs[k] if O.is_buffer(k) else named[k]).detach().cpu())
     return rep

@@ -225,3 +225,53 @@ def test_sound_modules_match_torch_modules_built_from_the_same_layers():
     z = dec.out(z).squeeze(1).reshape(2, 3, 128, 20)
     assert y.shape == (2, 3, 128, 20)
     _close(y, z.detach(), rtol=2e-4)
+
+
+def _fro(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+@pytest.mark.parametrize("g,transposed", [(c, False) for c in CONVS[1:4]] + [((4, 32, 31, 31, 64, (4, 4), (2, 2), (0, 0)), False),
+                                                                            ((70, 8192, 4, 1, 128, (1, 1), (1, 1), (0, 0)), False)]
+                         + [(c, True) for c in CONVTS[0:3]] + [((70, 1024, 1, 1, 128, (5, 5), (2, 2), (0, 0)), True)])
+def test_tensor_core_route_matches_exact_kernels(g, transposed):
+    """GConvTCFn (bf16 NHWC staging, explicit im2col rows, tcgen05 GEMMs; bf16 mode's route for the 128 .. 512-channel sound layers
+    and the inner layers of the BatchNorm image stacks) against GConvFn (exact fp32) on the same inputs: output, input gradient and
+    weight gradient within 1e-2 relative Frobenius error (bf16 operands, fp32 accumulation; measured 2e-3 .. 4e-3)."""
+    from mrssm_b200 import ops
+    N, C0, H0, W0, C1, k, s, p = g
+    gen = torch.Generator(device=DEV).manual_seed(8)
+    x = torch.randn(N, C0, H0, W0, device=DEV, generator=gen, requires_grad=True)
+    wshape = (C0, C1, *k) if transposed else (C1, C0, *k)
+    w = (torch.randn(wshape, device=DEV, generator=gen) / (C0 * k[0] * k[1]) ** 0.5).requires_grad_(True)
+    res = []
+    go = None
+    for fn in (ops.GConvFn, ops.GConvTCFn):
+        w.grad = None
+        y = fn.apply(x, w, s, p, transposed)
+        if go is None:
+            go = torch.randn(y.shape, device=DEV, generator=gen)
+        (gx,) = torch.autograd.grad(y, (x,), go)
+        res.append((y.detach(), gx, w.grad.clone()))
+    for name, a, b in zip(("y", "gx", "gw"), res[1], res[0]):
+        assert a.shape == b.shape and torch.isfinite(a).all(), name
+        assert _fro(a, b) <= 1e-2, (name, _fro(a, b))
+
+
+def test_tensor_core_route_chunks_over_images():
+    from mrssm_b200 import ops
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    x = torch.randn(9, 64, 32, 10, device=DEV, generator=gen, requires_grad=True)
+    w = (torch.randn(128, 64, 4, 8, device=DEV, generator=gen) / 45.0).requires_grad_(True)
+    outs = []
+    for col_bytes in (2 << 30, 3 * 16 * 5 * 2048 * 2):                 # everything in one chunk; 3 images per chunk (3 chunks)
+        old, ops._GC_COL_BYTES = ops._GC_COL_BYTES, col_bytes
+        try:
+            w.grad = None
+            y = ops.GConvTCFn.apply(x, w, (2, 2), (1, 3), False)
+            (gx,) = torch.autograd.grad(y, (x,), torch.ones_like(y))
+            outs.append((y.detach(), gx, w.grad.clone()))
+        finally:
+            ops._GC_COL_BYTES = old
+    for a, b in zip(*outs):
+        assert _fro(a, b) <= 1e-5                                        # (atomics order in the weight gradient only)

@@ -93,6 +93,15 @@ def test_bf16_tensor_core_mode_within_stated_tolerance(fusion):
     assert rep["grad_rel_fro"] < 5e-2, rep
 
 
+def test_bf16_mode_shipped_layers_within_stated_tolerance():
+    """The shipped YAML's layer set (image + sound, BatchNorm) in bf16 mode — the 128 .. 512-channel convolutions on the tensor-core
+    route (ops.GConvTCFn), normalisation / GLU in fp32 — against the fp32 oracle, same stated tolerances as the other bf16 cases."""
+    shapes = {"image_horizon": [3, 64, 64], "sound": [128, 20]}
+    rep = U.run_train_parity_bf16("MoPoE", B=2, T=5, steps=2, device=DEV, names_enc=("image_horizon", "sound"),
+                                  names_rec=("image_horizon", "sound"), observation_shapes=shapes, normalization="BatchNorm", lr=1e-5)
+    assert rep["state_err"] < 2e-2 and rep["loss_rel"] < 2e-2 and rep["gnorm_rel"] < 3e-2 and rep["grad_rel_fro"] < 5e-2, rep
+
+
 def test_normalize_image_u8_matches_reference_formula():
     """mrssm_normalize_image_u8 against image_processing.py:5-11 restated in torch, with the noise supplied."""
     from mrssm_b200 import _lib as L
