@@ -184,6 +184,89 @@ __global__ void __launch_bounds__(NT) gconv_kernel(const GC g) {
     }
 }
 
+// ---- convolutions to very few output channels (SoundDecoder_v2.out: 64 -> 1, 7x7): the GEMM tile would be 15/16 padding ------------
+// forward: one thread per output pixel, all (<= 4) output channels, weights [k][co] in shared memory
+template <int CO>
+__global__ void gconv_fwd_small_kernel(const GC g) {
+    extern __shared__ float wsm[];
+    const int KHW = g.KH * g.KW, K = g.Cin * KHW, HoWo = g.Ho * g.Wo, HW = g.H * g.W;
+    for (int i = threadIdx.x; i < K * CO; i += blockDim.x) {
+        const int k = i / CO, co = i - k * CO;
+        wsm[i] = co < g.Cout ? g.w[(long long)co * K + k] : 0.f;
+    }
+    __syncthreads();
+    for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < g.M; m += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(m / HoWo), r = (int)(m - (long long)n * HoWo), ho = r / g.Wo, wo = r - ho * g.Wo;
+        const int hb = ho * g.SH - g.PH, wb = wo * g.SW - g.PW;
+        float acc[CO];
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+        for (int ci = 0; ci < g.Cin; ++ci) {
+            const float* xp = g.x + ((long long)n * g.Cin + ci) * HW;
+            const float* wp = wsm + (long long)ci * KHW * CO;
+            for (int kh = 0; kh < g.KH; ++kh) {
+                const int h = hb + kh;
+                if (h < 0 || h >= g.H) continue;
+                for (int kw = 0; kw < g.KW; ++kw) {
+                    const int w = wb + kw;
+                    if (w < 0 || w >= g.W) continue;
+                    const float v = __ldg(xp + (long long)h * g.W + w);
+#pragma unroll
+                    for (int c = 0; c < CO; ++c) acc[c] = fmaf(v, wp[(kh * g.KW + kw) * CO + c], acc[c]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CO; ++c)
+            if (c < g.Cout) g.out[((long long)n * g.Cout + c) * HoWo + r] = acc[c];
+    }
+}
+
+// weight gradient: CTA = (input channel ci, output channel co, slice of the images); a thread walks output pixels with one register
+// accumulator per tap (kernel size is a template parameter so that the taps are unrolled with constant indices), then the block
+// reduces the taps and adds them to dw[co][ci][*]
+template <int KH, int KW>
+__global__ void __launch_bounds__(256) gconv_wgrad_small_kernel(const GC g, int n_slices) {
+    constexpr int KHW = KH * KW;
+    __shared__ float red[8][KHW];
+    const int HoWo = g.Ho * g.Wo, HW = g.H * g.W;
+    const int ci = blockIdx.x, co = blockIdx.y;
+    float acc[KHW];
+#pragma unroll
+    for (int t = 0; t < KHW; ++t) acc[t] = 0.f;
+    for (int n = blockIdx.z; n < g.N; n += n_slices) {
+        const float* xp = g.x + ((long long)n * g.Cin + ci) * HW;
+        const float* dp = g.dy + ((long long)n * g.Cout + co) * HoWo;
+        for (int r = threadIdx.x; r < HoWo; r += blockDim.x) {
+            const int ho = r / g.Wo, wo = r - ho * g.Wo, hb = ho * g.SH - g.PH, wb = wo * g.SW - g.PW;
+            const float d = __ldg(dp + r);
+#pragma unroll
+            for (int kh = 0; kh < KH; ++kh) {
+                const int h = hb + kh;
+                if (h < 0 || h >= g.H) continue;
+                const float* row = xp + (long long)h * g.W;
+#pragma unroll
+                for (int kw = 0; kw < KW; ++kw) {
+                    const int w = wb + kw;
+                    if (w >= 0 && w < g.W) acc[kh * KW + kw] = fmaf(d, __ldg(row + w), acc[kh * KW + kw]);
+                }
+            }
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int t = 0; t < KHW; ++t) {
+        const float v = warp_sum(acc[t]);
+        if (lane == 0) red[warp][t] = v;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < KHW; t += blockDim.x) {
+        float v = 0.f;
+        for (int wq = 0; wq < (int)(blockDim.x >> 5); ++wq) v += red[wq][t];
+        atomicAdd(g.out + ((long long)co * g.Cin + ci) * KHW + t, v);
+    }
+}
+
 int check_geom(const mrssm_gconv_args* a) {
     MRSSM_CHECK(a && a->N > 0 && a->Cin > 0 && a->Cout > 0 && a->H > 0 && a->W > 0 && a->KH > 0 && a->KW > 0 && a->SH > 0 && a->SW > 0 &&
                     a->PH >= 0 && a->PW >= 0, "gconv: bad geometry");
@@ -463,7 +546,11 @@ extern "C" int mrssm_gconv_fwd(const mrssm_gconv_args* a, void* stream) {
     MRSSM_CHECK(a->x && a->w && a->y, "gconv_fwd: null tensor");
     GC g = make(a);
     g.out = a->y; g.M = (long long)a->N * a->Ho * a->Wo; g.Ncols = a->Cout; g.K = (long long)a->Cin * a->KH * a->KW;
-    if (g.Ncols <= 16) {
+    const size_t wsm = (size_t)g.K * 4 * sizeof(float);
+    if (g.Ncols <= 4 && wsm <= 96 * 1024) {
+        MRSSM_CUDA(cudaFuncSetAttribute(gconv_fwd_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
+        gconv_fwd_small_kernel<4><<<(unsigned)std::min<long long>(148 * 16, ceil_div64(g.M, 256)), 256, wsm, (cudaStream_t)stream>>>(g);
+    } else if (g.Ncols <= 16) {
         dim3 grid((unsigned)ceil_div64(g.M, 256), 1);
         gconv_kernel<0, 256, 16><<<grid, NT, 0, (cudaStream_t)stream>>>(g);
     } else {
@@ -496,7 +583,14 @@ extern "C" int mrssm_gconv_wgrad(const mrssm_gconv_args* a, void* stream) {
     MRSSM_CHECK(a->x && a->dw && a->y, "gconv_wgrad: null tensor");
     GC g = make(a);
     g.out = a->dw; g.M = a->Cout; g.Ncols = a->Cin * a->KH * a->KW; g.K = (long long)a->N * a->Ho * a->Wo;
-    // few output channels (the 7x7 Conv2d to one channel): the transposed tile, 16 weight rows x 256 taps per CTA
+    if (a->Cout <= 4 && a->KH == 7 && a->KW == 7) {          // SoundDecoder_v2.out: the 7x7 Conv2d to one channel
+        const int n_slices = (int)std::max<long long>(1, std::min<long long>(a->N, ceil_div64(4 * 148, (long long)a->Cin * a->Cout)));
+        dim3 grid((unsigned)a->Cin, (unsigned)a->Cout, (unsigned)n_slices);
+        gconv_wgrad_small_kernel<7, 7><<<grid, 256, 0, (cudaStream_t)stream>>>(g, n_slices);
+        MRSSM_LAUNCH_CHECK();
+        return 0;
+    }
+    // few output channels: the transposed tile, 16 weight rows x 256 taps per CTA
     const bool narrow = g.M <= 16;
     const int BMw = narrow ? 16 : 64, BNw = narrow ? 256 : 64;
     const long long tiles = ceil_div64(g.M, BMw) * ceil_div64(g.Ncols, BNw);
