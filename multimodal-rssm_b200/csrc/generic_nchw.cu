@@ -306,11 +306,18 @@ __global__ void norm_stats_kernel(const float* __restrict__ x, int N, int C, int
         const float* p = x + (long long)gidx * HW;
         for (int i = threadIdx.x; i < HW; i += blockDim.x) { const double v = p[i]; s += v; q += v * v; }
     } else {
-        const long long total = (long long)N * HW;
-        for (long long e = threadIdx.x; e < total; e += blockDim.x) {
-            const long long n = e / HW, i = e - n * HW;
-            const double v = x[(n * C + gidx) * HW + i];
-            s += v; q += v * v;
+        if (HW >= (int)blockDim.x) {
+            for (int n = 0; n < N; ++n) {
+                const float* p = x + ((long long)n * C + gidx) * HW;
+                for (int i = threadIdx.x; i < HW; i += blockDim.x) { const double v = p[i]; s += v; q += v * v; }
+            }
+        } else {
+            const long long total = (long long)N * HW;
+            for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+                const long long n = e / HW, i = e - n * HW;
+                const double v = x[(n * C + gidx) * HW + i];
+                s += v; q += v * v;
+            }
         }
     }
     s = block_sum(s, sh);
@@ -356,6 +363,40 @@ __global__ void norm_apply_kernel(const float* __restrict__ x, const float* __re
     }
 }
 
+// the same with one CTA per (n, c) plane (HW >= 64): the per-plane scalars are read once, no index arithmetic per element
+__global__ void norm_apply_plane_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ var,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta, int C, int HW, int per_plane,
+                                        int relu, float eps, float* __restrict__ y) {
+    const long long pl = blockIdx.x;
+    const int c = (int)(pl % C);
+    const long long gi = per_plane ? pl : c;
+    const float mu = mean[gi], sc = rsqrtf(var[gi] + eps) * gamma[c], bt = beta[c];
+    const float* xp = x + pl * HW;
+    float* yp = y + pl * HW;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+        float v = (xp[i] - mu) * sc + bt;
+        if (relu && v < 0.f) v = 0.f;
+        yp[i] = v;
+    }
+}
+__global__ void norm_bwd_apply_plane_kernel(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ x,
+                                            const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ gamma,
+                                            const float* __restrict__ sum_g, const float* __restrict__ sum_gx, int N, int C, int HW, int instance,
+                                            int per_plane_stats, int batch_stats, int relu, float eps, float* __restrict__ dx) {
+    const long long pl = blockIdx.x;
+    const int c = (int)(pl % C);
+    const long long gi = instance ? pl : c, si = (instance && !per_plane_stats) ? c : gi;
+    const float inv_cnt = instance ? 1.f / (float)HW : 1.f / ((float)N * (float)HW);
+    const float mu = mean[si], rs = rsqrtf(var[si] + eps), gm = gamma[c] * rs;
+    const float mg = batch_stats ? sum_g[gi] * inv_cnt : 0.f, mgx = batch_stats ? sum_gx[gi] * inv_cnt : 0.f;
+    const long long o = pl * HW;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+        float gg = g[o + i];
+        if (relu && !(y[o + i] > 0.f)) gg = 0.f;
+        dx[o + i] = gm * (gg - mg - (x[o + i] - mu) * rs * mgx);
+    }
+}
+
 // per group: sum of g^ = g * [y > 0 if relu] and of g^ * x^;  dgamma[c] += sum g^ x^, dbeta[c] += sum g^
 __global__ void norm_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ x,
                                        const float* __restrict__ mean, const float* __restrict__ var, int N, int C, int HW, int instance,
@@ -376,12 +417,23 @@ __global__ void norm_bwd_reduce_kernel(const float* __restrict__ g, const float*
         }
     } else {
         const float mu = mean[gidx], rs = rsqrtf(var[gidx] + eps);
-        const long long total = (long long)N * HW;
-        for (long long e = threadIdx.x; e < total; e += blockDim.x) {
-            const long long n = e / HW, i = e - n * HW, o = (n * C + gidx) * HW + i;
-            float gg = g[o];
-            if (relu && !(y[o] > 0.f)) gg = 0.f;
-            s += gg; q += (double)gg * ((x[o] - mu) * rs);
+        if (HW >= (int)blockDim.x) {
+            for (int n = 0; n < N; ++n) {
+                const long long o0 = ((long long)n * C + gidx) * HW;
+                for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+                    float gg = g[o0 + i];
+                    if (relu && !(y[o0 + i] > 0.f)) gg = 0.f;
+                    s += gg; q += (double)gg * ((x[o0 + i] - mu) * rs);
+                }
+            }
+        } else {
+            const long long total = (long long)N * HW;
+            for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+                const long long n = e / HW, i = e - n * HW, o = (n * C + gidx) * HW + i;
+                float gg = g[o];
+                if (relu && !(y[o] > 0.f)) gg = 0.f;
+                s += gg; q += (double)gg * ((x[o] - mu) * rs);
+            }
         }
     }
     s = block_sum(s, sh);
@@ -619,12 +671,21 @@ extern "C" int mrssm_norm_fwd(const mrssm_norm_args* a, void* stream) {
                                                                    a->running_mean, a->running_var);
             MRSSM_LAUNCH_CHECK();
         }
-        norm_apply_kernel<<<ew_blocks(total), 256, 0, st>>>(a->x, a->mean, a->var, a->gamma, a->beta, total, a->C, a->HW, a->instance, a->relu,
-                                                           a->eps, a->y);
+        if (a->HW >= 64)
+            norm_apply_plane_kernel<<<(unsigned)((long long)a->N * a->C), a->HW >= 512 ? 256 : 64, 0, st>>>(a->x, a->mean, a->var, a->gamma, a->beta,
+                                                                                                        a->C, a->HW, a->instance, a->relu, a->eps, a->y);
+        else
+            norm_apply_kernel<<<ew_blocks(total), 256, 0, st>>>(a->x, a->mean, a->var, a->gamma, a->beta, total, a->C, a->HW, a->instance, a->relu,
+                                                               a->eps, a->y);
     } else {
         MRSSM_CHECK(a->running_mean && a->running_var, "norm_fwd: fixed statistics requested without running buffers");
-        norm_apply_kernel<<<ew_blocks(total), 256, 0, st>>>(a->x, a->running_mean, a->running_var, a->gamma, a->beta, total, a->C, a->HW, 0,
-                                                           a->relu, a->eps, a->y);
+        if (a->HW >= 64)
+            norm_apply_plane_kernel<<<(unsigned)((long long)a->N * a->C), a->HW >= 512 ? 256 : 64, 0, st>>>(a->x, a->running_mean, a->running_var,
+                                                                                                        a->gamma, a->beta, a->C, a->HW, 0, a->relu,
+                                                                                                        a->eps, a->y);
+        else
+            norm_apply_kernel<<<ew_blocks(total), 256, 0, st>>>(a->x, a->running_mean, a->running_var, a->gamma, a->beta, total, a->C, a->HW, 0,
+                                                               a->relu, a->eps, a->y);
     }
     MRSSM_LAUNCH_CHECK();
     return 0;
@@ -643,8 +704,13 @@ extern "C" int mrssm_norm_bwd(const mrssm_norm_args* a, const float* g, float* s
     norm_bwd_reduce_kernel<<<groups, 256, 0, st>>>(g, a->y, a->x, mean, var, a->N, a->C, a->HW, a->instance, per_plane, a->relu, a->eps, sum_g,
                                                   sum_gx, dgamma, dbeta);
     MRSSM_LAUNCH_CHECK();
-    norm_bwd_apply_kernel<<<ew_blocks(total), 256, 0, st>>>(g, a->y, a->x, mean, var, a->gamma, sum_g, sum_gx, total, a->N, a->C, a->HW, a->instance,
-                                                           per_plane, a->batch_stats, a->relu, a->eps, dx);
+    if (a->HW >= 64)
+        norm_bwd_apply_plane_kernel<<<(unsigned)((long long)a->N * a->C), a->HW >= 512 ? 256 : 64, 0, st>>>(g, a->y, a->x, mean, var, a->gamma, sum_g,
+                                                                                                        sum_gx, a->N, a->C, a->HW, a->instance,
+                                                                                                        per_plane, a->batch_stats, a->relu, a->eps, dx);
+    else
+        norm_bwd_apply_kernel<<<ew_blocks(total), 256, 0, st>>>(g, a->y, a->x, mean, var, a->gamma, sum_g, sum_gx, total, a->N, a->C, a->HW,
+                                                               a->instance, per_plane, a->batch_stats, a->relu, a->eps, dx);
     MRSSM_LAUNCH_CHECK();
     return 0;
 }
