@@ -424,9 +424,10 @@ int mrssm_norm_bwd(const mrssm_norm_args* a, const float* g, float* sum_g, float
 /* nn.GLU(dim=1): x [N,2C,L] -> y [N,C,L] = x[:, :C] * sigmoid(x[:, C:]) and its backward (encoder.py:672-700). */
 int mrssm_glu_fwd(const float* x, int64_t N, int32_t C, int32_t L, float* y, void* stream);
 int mrssm_glu_bwd(const float* x, const float* g, int64_t N, int32_t C, int32_t L, float* dx, void* stream);
-/* per-channel bias of an NCHW tensor (the last, biased ConvTranspose2d of the BatchNorm decoder, observation_model.py:85) and
- * its gradient, ACCUMULATED into dbias [C]. */
-int mrssm_chan_bias_fwd(const float* x, int64_t N, int32_t C, int32_t HW, const float* bias, float* y, void* stream);
+/* per-channel bias of an NCHW tensor with an optional ReLU (the biased Conv2d / ConvTranspose2d + ReLU pairs of the 84x84 and
+ * 256x256 image stacks, encoder.py:362-413,511-615; the last ConvTranspose2d of the BatchNorm decoders, observation_model.py:85) and
+ * the bias gradient, ACCUMULATED into dbias [C]. */
+int mrssm_chan_bias_fwd(const float* x, int64_t N, int32_t C, int32_t HW, const float* bias, int32_t relu, float* y, void* stream);
 int mrssm_chan_bias_bwd(const float* g, int64_t N, int32_t C, int32_t HW, float* dbias, void* stream);
 
 /* ---- latent part of the ELBO -------------------------------------------------------------------

@@ -484,10 +484,12 @@ __global__ void glu_bwd_kernel(const float* __restrict__ x, const float* __restr
 }
 
 // y[n][c][i] = x[n][c][i] + bias[c] (the last ConvTranspose2d of the BatchNorm decoder keeps its bias) and the bias gradient
-__global__ void chan_bias_fwd_kernel(const float* __restrict__ x, long long total, int C, int HW, const float* __restrict__ bias,
+__global__ void chan_bias_fwd_kernel(const float* __restrict__ x, long long total, int C, int HW, const float* __restrict__ bias, int relu,
                                      float* __restrict__ y) {
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
-        y[e] = x[e] + bias[(int)((e / HW) % C)];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const float v = x[e] + bias[(int)((e / HW) % C)];
+        y[e] = (relu && v < 0.f) ? 0.f : v;
+    }
 }
 __global__ void chan_bias_bwd_kernel(const float* __restrict__ g, int N, int C, int HW, float* __restrict__ dbias) {
     __shared__ double sh[32];
@@ -731,10 +733,10 @@ extern "C" int mrssm_glu_bwd(const float* x, const float* g, int64_t N, int32_t 
     return 0;
 }
 
-extern "C" int mrssm_chan_bias_fwd(const float* x, int64_t N, int32_t C, int32_t HW, const float* bias, float* y, void* stream) {
+extern "C" int mrssm_chan_bias_fwd(const float* x, int64_t N, int32_t C, int32_t HW, const float* bias, int32_t relu, float* y, void* stream) {
     MRSSM_CHECK(x && y && bias && N > 0 && C > 0 && HW > 0, "chan_bias_fwd: bad arguments");
     const long long total = (long long)N * C * HW;
-    chan_bias_fwd_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, total, C, HW, bias, y);
+    chan_bias_fwd_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, total, C, HW, bias, relu, y);
     MRSSM_LAUNCH_CHECK();
     return 0;
 }

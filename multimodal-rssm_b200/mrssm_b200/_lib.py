@@ -193,7 +193,7 @@ SYMBOLS = {
     "mrssm_norm_bwd": [C.POINTER(NormArgs), _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mrssm_glu_fwd": [_vp, _i64, _i32, _i32, _vp, _vp],
     "mrssm_glu_bwd": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
-    "mrssm_chan_bias_fwd": [_vp, _i64, _i32, _i32, _vp, _vp, _vp],
+    "mrssm_chan_bias_fwd": [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp],
     "mrssm_chan_bias_bwd": [_vp, _i64, _i32, _i32, _vp, _vp],
     "mrssm_latent_fwd": [C.POINTER(LatentArgs), _vp],
     "mrssm_latent_bwd": [C.POINTER(LatentArgs), _vp],

@@ -1955,28 +1955,33 @@ def conv1d_k1(x, w):
 
 
 class ChannelBiasFn(Function):
-    """y[n,c,...] = x[n,c,...] + bias[c]; the bias gradient is accumulated into bias.grad."""
+    """y[n,c,...] = [relu](x[n,c,...] + bias[c]); the bias gradient is accumulated into bias.grad."""
 
     @staticmethod
-    def forward(ctx, x, bias):
+    def forward(ctx, x, bias, relu):
         x = _f32c(x)
         N, Cn = x.shape[0], x.shape[1]
         y = torch.empty_like(x)
-        L.call("mrssm_chan_bias_fwd", L.ptr(x), N, Cn, x.numel() // (N * Cn), L.ptr(bias), L.ptr(y))
-        ctx.bias = bias
+        L.call("mrssm_chan_bias_fwd", L.ptr(x), N, Cn, x.numel() // (N * Cn), L.ptr(bias), int(relu), L.ptr(y))
+        ctx.bias, ctx.relu = bias, bool(relu)
+        if relu:
+            ctx.save_for_backward(y)
         return y
 
     @staticmethod
     def backward(ctx, g):
         g = _f32c(g)
         N, Cn = g.shape[0], g.shape[1]
+        if ctx.relu:
+            (y,) = ctx.saved_tensors
+            g = act_bwd(g, y, RELU)
         if ctx.bias.requires_grad:
             L.call("mrssm_chan_bias_bwd", L.ptr(g), N, Cn, g.numel() // (N * Cn), L.ptr(grad_buf(ctx.bias)))
-        return g, None
+        return g, None, None
 
 
-def add_channel_bias(x, bias):
-    return ChannelBiasFn.apply(x, bias)
+def add_channel_bias(x, bias, relu=False):
+    return ChannelBiasFn.apply(x, bias, relu)
 
 
 # ---- the same convolutions on the tensor cores (bf16 mode): NHWC bf16 staging, explicit im2col rows, dense tcgen05 GEMMs ------------

@@ -8,8 +8,8 @@ own ``forward`` is never called.
 
 Covered: bottle helpers a3, MultimodalEncoder a4, ImageEncoder 64/128 a5,
 SymbolicEncoder a6, StochasticStateModel a11, ObsEncoder a12, MultimodalObsEncoder a13, fusion a14.
-Round 2 added the rest of the shipped YAML: `SoundEncoder_v2` and the BatchNorm variant of the 64x64 image encoder (exact fp32
-kernels).  Not covered (raise NotImplementedError): 84x84 / 256x256 images, the q(st|ot) expert family.
+Round 2 added the rest of the shipped YAML (`SoundEncoder_v2`, BatchNorm image stacks) and the 84x84 / 256x256 stacks (general NCHW
+kernels).  Not covered (raise NotImplementedError): the q(st|ot) expert family, InstanceNorm / GroupNorm image variants.
 """
 import itertools
 
@@ -236,35 +236,44 @@ class SymbolicEncoder(_EncoderBase):
 
 
 class _ConvEncoder(_EncoderBase):
-    CHANNELS = ()
+    """Stride-2 Conv2d stacks of the reference's image encoders (encoder.py:307-615): LAYERS = (out channels, kernel) per layer.
+    normalization None: Conv2d + ReLU pairs (keys conv.{0,2,..}.{weight,bias}); "BatchNorm": Conv2d(bias=False) + BatchNorm2d + ReLU
+    triples (keys conv.{0,3,..}.weight, conv.{1,4,..}.*).  The 64x64 / 128x128 stacks without normalisation run on the plane tcgen05
+    kernels (bf16 mode) or the exact SIMT kernels; every other variant on the general NCHW kernels (csrc/generic_nchw.cu: exact
+    fp32, tensor-core route for the wide layers in bf16 mode)."""
+    LAYERS = ()
+    PLANE_PATH = False          # the validated fast path of ops.ConvEncoder(TC)Fn (k = 4 everywhere)
 
     def __init__(self, embedding_size, activation_function="relu", image_dim=3, normalization=None):
         super().__init__()
         if normalization not in (None, "BatchNorm"):
-            raise NotImplementedError(f"normalization={normalization!r} (the reference implements None and BatchNorm only)")
-        if normalization == "BatchNorm" and len(self.CHANNELS) != 4:
-            raise NotImplementedError("BatchNorm: the reference has it for the 64x64 stack only (encoder.py:324-337)")
+            raise NotImplementedError(f"normalization={normalization!r}: None and BatchNorm are implemented (InstanceNorm / GroupNorm "
+                                      "variants of the 128x128 / 256x256 stacks are not)")
         self.embedding_size = embedding_size
         self.activation_function = activation_function
         self.normalization = normalization
         layers, cin = [], image_dim
-        for cout in self.CHANNELS:
-            if normalization == "BatchNorm":             # keys conv.{0,3,..}.weight, conv.{1,4,..}.{weight,bias,running_*}
-                layers += [nn.Conv2d(cin, cout, 4, stride=2, bias=False), nn.BatchNorm2d(cout, affine=True, track_running_stats=True), nn.ReLU()]
+        for cout, k in self.LAYERS:
+            if normalization == "BatchNorm":
+                layers += [nn.Conv2d(cin, cout, k, stride=2, bias=False), nn.BatchNorm2d(cout, affine=True, track_running_stats=True), nn.ReLU()]
             else:
-                layers += [nn.Conv2d(cin, cout, 4, stride=2), nn.ReLU()]
+                layers += [nn.Conv2d(cin, cout, k, stride=2), nn.ReLU()]
             cin = cout
-        self.conv = nn.Sequential(*layers)               # parameter container: keys conv.{0,2,..}.{weight,bias}
+        self.conv = nn.Sequential(*layers)               # parameter / buffer container
         self.fc = nn.Identity() if embedding_size == 1024 else nn.Linear(1024, embedding_size)
         self.modules = [self.conv, self.fc]
 
     def forward(self, observation):
+        mods = list(self.conv)
         if self.normalization == "BatchNorm":
-            # Conv2d (no bias) -> BatchNorm2d -> ReLU triples on the exact fp32 NCHW kernels (csrc/generic_nchw.cu), both modes
             hidden = observation
-            mods = list(self.conv)
             for i in range(0, len(mods), 3):
                 hidden = ops.batch_norm(ops.conv2d_nobias(hidden, mods[i].weight, 2, 0), mods[i + 1], relu=True)
+            hidden = hidden.reshape(-1, 1024)
+        elif not self.PLANE_PATH:
+            hidden = observation
+            for i in range(0, len(mods), 2):
+                hidden = ops.add_channel_bias(ops.conv2d_nobias(hidden, mods[i].weight, 2, 0), mods[i].bias, relu=True)
             hidden = hidden.reshape(-1, 1024)
         else:
             params = [p for m in self.conv if isinstance(m, nn.Conv2d) for p in (m.weight, m.bias)]
@@ -279,12 +288,24 @@ class _ConvEncoder(_EncoderBase):
 
 class ImageEncoder(_ConvEncoder):
     """64x64: Conv 3->32->64->128->256, k4 s2, ReLU (reference encoder.py:307-360)."""
-    CHANNELS = (32, 64, 128, 256)
+    LAYERS = ((32, 4), (64, 4), (128, 4), (256, 4))
+    PLANE_PATH = True
+
+
+class ImageEncoder_84(_ConvEncoder):
+    """84x84: Conv 3->32 k4 ->64 k5 ->128 k5 ->256 k6, s2, ReLU (reference encoder.py:362-413)."""
+    LAYERS = ((32, 4), (64, 5), (128, 5), (256, 6))
 
 
 class ImageEncoder_128(_ConvEncoder):
     """128x128: Conv 3->16->32->64->128->256, k4 s2, ReLU (reference encoder.py:415-509)."""
-    CHANNELS = (16, 32, 64, 128, 256)
+    LAYERS = ((16, 4), (32, 4), (64, 4), (128, 4), (256, 4))
+    PLANE_PATH = True
+
+
+class ImageEncoder_256(_ConvEncoder):
+    """256x256: Conv 3->8->16->32->64->128->256, k4 s2, ReLU (reference encoder.py:511-615)."""
+    LAYERS = ((8, 4), (16, 4), (32, 4), (64, 4), (128, 4), (256, 4))
 
 
 class SoundEncoder_v2(_EncoderBase):
@@ -323,9 +344,9 @@ class SoundEncoder_v2(_EncoderBase):
 
 def build_ImageEncoder(observation_shape, visual_embedding_size, cnn_activation_function, normalization=None):
     size = list(observation_shape[1:])
-    cls = {(64, 64): ImageEncoder, (128, 128): ImageEncoder_128}.get(tuple(size))
+    cls = {(64, 64): ImageEncoder, (84, 84): ImageEncoder_84, (128, 128): ImageEncoder_128, (256, 256): ImageEncoder_256}.get(tuple(size))
     if cls is None:
-        raise NotImplementedError(f"image size {size}: only 64x64 and 128x128 are on the B200 hot path")
+        raise NotImplementedError(f"image size {size}: the reference defines 64, 84, 128 and 256")
     return cls(visual_embedding_size, cnn_activation_function, image_dim=observation_shape[0], normalization=normalization)
 
 

@@ -61,24 +61,29 @@ class DenseDecoder(ObservationModel_base):
 
 
 class _ConvDecoder(ObservationModel_base):
+    """fc([h, s]) -> stride-2 ConvTranspose2d stacks of the reference's image decoders (observation_model.py:56-345): LAYERS =
+    (out channels or None for the image's, kernel).  normalization None: ConvT + ReLU pairs, the last ConvT without ReLU;
+    "BatchNorm": ConvT(bias=False) + BatchNorm2d + ReLU triples, the last ConvT with bias.  64x64 / 128x128 without normalisation
+    run on the plane tcgen05 kernels (bf16 mode) / exact SIMT kernels, every other variant on the general NCHW kernels."""
     __constants__ = ["embedding_size"]
-    LAYERS = ()        # (out_channels or None for image_dim, kernel)
+    LAYERS = ()
+    FC_NAME = "fc1"
+    PLANE_PATH = False
 
     def __init__(self, belief_size, state_size, embedding_size, activation_function="relu", image_dim=3,
                  normalization=None):
         super().__init__()
         if normalization not in (None, "BatchNorm"):
-            raise NotImplementedError(f"normalization={normalization!r} (the reference implements None and BatchNorm only)")
-        if normalization == "BatchNorm" and len(self.LAYERS) != 4:
-            raise NotImplementedError("BatchNorm: the reference has it for the 64x64 stack only (observation_model.py:75-86)")
+            raise NotImplementedError(f"normalization={normalization!r}: None and BatchNorm are implemented (InstanceNorm / GroupNorm "
+                                      "variants of the 256x256 stack are not)")
         self.embedding_size = embedding_size
         self.normalization = normalization
-        self.fc1 = nn.Linear(belief_size + state_size, embedding_size)
+        setattr(self, self.FC_NAME, nn.Linear(belief_size + state_size, embedding_size))
         layers, cin = [], embedding_size
         for i, (cout, k) in enumerate(self.LAYERS):
             cout = image_dim if cout is None else cout
             last = i == len(self.LAYERS) - 1
-            if normalization == "BatchNorm" and not last:     # keys conv.{0,3,6}.weight, conv.{1,4,7}.*, conv.9.{weight,bias}
+            if normalization == "BatchNorm" and not last:
                 layers += [nn.ConvTranspose2d(cin, cout, k, stride=2, bias=False), nn.BatchNorm2d(cout, affine=True, track_running_stats=True),
                            nn.ReLU()]
             else:
@@ -86,25 +91,35 @@ class _ConvDecoder(ObservationModel_base):
                 if not last:
                     layers.append(nn.ReLU())
             cin = cout
-        self.conv = nn.Sequential(*layers)               # keys conv.{0,2,4,..}.{weight,bias}
-        self.modules = [self.fc1, self.conv]
+        self.conv = nn.Sequential(*layers)               # parameter / buffer container
+        self.modules = [self._fc, self.conv]
 
-    def _forward_batchnorm(self, h_t, s_t):
-        """fc1 -> (ConvT without bias -> BatchNorm2d -> ReLU) x 3 -> ConvT with bias, on the exact fp32 NCHW kernels."""
+    @property
+    def _fc(self):
+        return getattr(self, self.FC_NAME)
+
+    def _forward_generic(self, h_t, s_t):
         T, B = h_t.shape[:2]
-        x = ops.MlpFn.apply(0, False, 2, h_t.reshape(T * B, -1), s_t.reshape(T * B, -1), self.fc1.weight, self.fc1.bias)
+        x = ops.MlpFn.apply(0, False, 2, h_t.reshape(T * B, -1), s_t.reshape(T * B, -1), self._fc.weight, self._fc.bias)
         x = x.reshape(-1, self.embedding_size, 1, 1)
-        mods = list(self.conv)
-        for i in range(0, len(mods) - 1, 3):
-            x = ops.batch_norm(ops.conv_transpose2d_nobias(x, mods[i].weight, 2, 0), mods[i + 1], relu=True)
-        x = ops.add_channel_bias(ops.conv_transpose2d_nobias(x, mods[-1].weight, 2, 0), mods[-1].bias)
+        mods = [m for m in self.conv if not isinstance(m, nn.ReLU)]
+        i = 0
+        while i < len(mods):
+            ct = mods[i]
+            x = ops.conv_transpose2d_nobias(x, ct.weight, 2, 0)
+            if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm2d):
+                x = ops.batch_norm(x, mods[i + 1], relu=True)
+                i += 2
+            else:
+                x = ops.add_channel_bias(x, ct.bias, relu=i < len(mods) - 1)
+                i += 1
         return {"loc": x.reshape(T, B, *x.shape[1:]), "scale": 1.0}
 
     def forward(self, h_t, s_t):
-        if self.normalization == "BatchNorm":
-            return self._forward_batchnorm(h_t, s_t)
+        if self.normalization is not None or not self.PLANE_PATH:
+            return self._forward_generic(h_t, s_t)
         T, B = h_t.shape[:2]
-        params = [self.fc1.weight, self.fc1.bias]
+        params = [self._fc.weight, self._fc.bias]
         params += [p for m in self.conv if isinstance(m, nn.ConvTranspose2d) for p in (m.weight, m.bias)]
         fn = ops.ConvDecoderTCFn if ops.bf16_mode() else ops.ConvDecoderFn
         y = fn.apply(h_t.reshape(T * B, -1), s_t.reshape(T * B, -1), *params)
@@ -113,10 +128,10 @@ class _ConvDecoder(ObservationModel_base):
     def mse_loss(self, h_t, s_t, o_t):
         """sum_features mean_{t,b} (loc - o)^2.  bf16 mode, <= 4 image channels: decoder and loss are ONE autograd node — the
         last ConvTranspose2d's epilogue reduces the loss and keeps the bf16 residual, the reconstruction is never written."""
-        if not (ops.bf16_mode() and o_t.shape[2] <= 4) or self.normalization == "BatchNorm":
+        if not (ops.bf16_mode() and o_t.shape[2] <= 4) or self.normalization is not None or not self.PLANE_PATH:
             return super().mse_loss(h_t, s_t, o_t)
         T, B = h_t.shape[:2]
-        params = [self.fc1.weight, self.fc1.bias]
+        params = [self._fc.weight, self._fc.bias]
         params += [p for m in self.conv if isinstance(m, nn.ConvTranspose2d) for p in (m.weight, m.bias)]
         return ops.ConvDecoderMseTCFn.apply(h_t.reshape(T * B, -1), s_t.reshape(T * B, -1),
                                             o_t.reshape(T * B, *o_t.shape[2:]), *params)
@@ -125,11 +140,24 @@ class _ConvDecoder(ObservationModel_base):
 class ImageDecoder(_ConvDecoder):
     """64x64: fc -> ConvT 1024->128 k5 -> 64 k5 -> 32 k6 -> C k6, stride 2 (reference :58-105)."""
     LAYERS = ((128, 5), (64, 5), (32, 6), (None, 6))
+    PLANE_PATH = True
+
+
+class ImageDecoder_84(_ConvDecoder):
+    """84x84: fc -> ConvT 1024->128 k3 -> 64 k4 -> 32 k4 -> 16 k6 -> C k6 (reference :108-160; its Linear is named `fc`)."""
+    LAYERS = ((128, 3), (64, 4), (32, 4), (16, 6), (None, 6))
+    FC_NAME = "fc"
 
 
 class ImageDecoder_128(_ConvDecoder):
     """128x128: fc -> ConvT 1024->256 k6 -> 128 k4 -> 64 k4 -> 32 k4 -> C k6 (reference :162-229)."""
     LAYERS = ((256, 6), (128, 4), (64, 4), (32, 4), (None, 6))
+    PLANE_PATH = True
+
+
+class ImageDecoder_256(_ConvDecoder):
+    """256x256: fc -> ConvT 1024->256 k6 -> 128 k4 -> 64 k4 -> 32 k4 -> 16 k4 -> C k6 (reference :231-345)."""
+    LAYERS = ((256, 6), (128, 4), (64, 4), (32, 4), (16, 4), (None, 6))
 
 
 class SoundDecoder_v2(ObservationModel_base):
@@ -167,9 +195,9 @@ def build_ObservationModel(name, observation_shapes, belief_size, state_size, hi
                            activation_function, normalization=None):
     shape = observation_shapes[name]
     if "image" in name:
-        cls = {(64, 64): ImageDecoder, (128, 128): ImageDecoder_128}.get(tuple(shape[1:]))
+        cls = {(64, 64): ImageDecoder, (84, 84): ImageDecoder_84, (128, 128): ImageDecoder_128, (256, 256): ImageDecoder_256}.get(tuple(shape[1:]))
         if cls is None:
-            raise NotImplementedError(f"image size {list(shape[1:])}: only 64x64 and 128x128 are on the B200 hot path")
+            raise NotImplementedError(f"image size {list(shape[1:])}: the reference defines 64, 84, 128 and 256")
         return cls(belief_size, state_size, embedding_size["image"], activation_function["cnn"],
                    image_dim=shape[0], normalization=normalization)
     if "sound" in name:

@@ -59,7 +59,7 @@ class OracleConfig:
     predict_reward: bool = False     # base/algo.py:200-201: False zeroes the reward loss (shipped default)
     learning_rate_schedule: int = 0        # > 0: Adam starts at lr 0 and gains lr/schedule per loss evaluation up to lr (base/algo.py:40-41,195-198)
     worldmodel_LogProbLoss: bool = False   # -log N(o; loc, 1) instead of the squared error (base/algo.py:101-103, :375-378)
-    normalization: Optional[str] = None   # None | "BatchNorm" (64x64 image encoder / decoder, encoder.py:324-337, observation_model.py:75-86)
+    normalization: Optional[str] = None   # None | "BatchNorm" | "InstanceNorm" (image stacks: IMAGE_NORMS below; encoder.py:324-337, observation_model.py:75-86)
     overshooting_distance: int = 0   # latent overshooting (base/algo.py:111-148, MoPoE/algo.py:69-108); kl_beta 0 = off
     overshooting_kl_beta: float = 0.0
     overshooting_reward_scale: float = 0.0
@@ -102,6 +102,17 @@ def flatten_state(nested, prefix="") -> Dict[str, Tensor]:
     return out
 
 
+# (out channels, kernel) of the stride-2 Conv2d / ConvTranspose2d stacks per image side (encoder.py:307-615, observation_model.py:56-345;
+# None = the image's channel count) and the normalisation variants the reference defines for each (GroupNorm is not restated).
+IMAGE_ENCODER_LAYERS = {64: [(32, 4), (64, 4), (128, 4), (256, 4)], 84: [(32, 4), (64, 5), (128, 5), (256, 6)],
+                        128: [(16, 4), (32, 4), (64, 4), (128, 4), (256, 4)], 256: [(8, 4), (16, 4), (32, 4), (64, 4), (128, 4), (256, 4)]}
+IMAGE_DECODER_LAYERS = {64: [(128, 5), (64, 5), (32, 6), (None, 6)], 84: [(128, 3), (64, 4), (32, 4), (16, 6), (None, 6)],
+                        128: [(256, 6), (128, 4), (64, 4), (32, 4), (None, 6)], 256: [(256, 6), (128, 4), (64, 4), (32, 4), (16, 4), (None, 6)]}
+IMAGE_NORMS = {("enc", 64): (None, "BatchNorm"), ("enc", 84): (None, "BatchNorm"), ("enc", 128): (None, "BatchNorm", "InstanceNorm"),
+               ("enc", 256): (None, "BatchNorm", "InstanceNorm"), ("dec", 64): (None, "BatchNorm"), ("dec", 84): (None, "BatchNorm"),
+               ("dec", 128): (None, "BatchNorm"), ("dec", 256): (None, "BatchNorm", "InstanceNorm")}
+
+
 def param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
     """Shapes of every learnable tensor of the model, keyed like the flattened reference
     checkpoint (SURVEY §5 'Checkpoint / resume'; PyTorch layouts)."""
@@ -122,40 +133,41 @@ def param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
 
     def image_encoder(prefix, shape):
         c = shape[0]
-        chans = [c, 32, 64, 128, 256] if shape[1] == 64 else [c, 16, 32, 64, 128, 256]
-        if cfg.normalization == "BatchNorm":        # Conv2d(bias=False), BatchNorm2d, ReLU triples (encoder.py:324-337)
-            assert shape[1] == 64, "BatchNorm oracle: 64x64 images only"
-            for i in range(len(chans) - 1):
-                sh[f"{prefix}conv.{3 * i}.weight"] = (chans[i + 1], chans[i], 4, 4)
-                batch_norm(f"{prefix}conv.{3 * i + 1}", chans[i + 1])
-            if cfg.embedding_size["image"] != 1024:
-                lin(prefix + "fc", cfg.embedding_size["image"], 1024)
-            return
-        for i in range(len(chans) - 1):
-            sh[f"{prefix}conv.{2 * i}.weight"] = (chans[i + 1], chans[i], 4, 4)
-            sh[f"{prefix}conv.{2 * i}.bias"] = (chans[i + 1],)
+        layers = IMAGE_ENCODER_LAYERS[shape[1]]
+        norm = cfg.normalization
+        assert norm in IMAGE_NORMS[("enc", shape[1])], f"the reference has no {norm} variant of the {shape[1]}x{shape[1]} encoder"
+        cin = c
+        for i, (cout, k) in enumerate(layers):
+            if norm is None:                        # Conv2d + ReLU pairs
+                sh[f"{prefix}conv.{2 * i}.weight"] = (cout, cin, k, k)
+                sh[f"{prefix}conv.{2 * i}.bias"] = (cout,)
+            else:                                   # Conv2d(bias=False), BatchNorm2d / InstanceNorm2d, ReLU triples (encoder.py:324-337 ...)
+                sh[f"{prefix}conv.{3 * i}.weight"] = (cout, cin, k, k)
+                batch_norm(f"{prefix}conv.{3 * i + 1}", cout)
+            cin = cout
         if cfg.embedding_size["image"] != 1024:
             lin(prefix + "fc", cfg.embedding_size["image"], 1024)
 
     def image_decoder(prefix, shape):
         c, E = shape[0], cfg.embedding_size["image"]
-        lin(prefix + "fc1", E, D + S)
-        if shape[1] == 64:
-            spec = [(E, 128, 5), (128, 64, 5), (64, 32, 6), (32, c, 6)]
-        else:
-            spec = [(E, 256, 6), (256, 128, 4), (128, 64, 4), (64, 32, 4), (32, c, 6)]
-        if cfg.normalization == "BatchNorm":        # ConvT(bias=False), BatchNorm2d, ReLU triples, last ConvT with bias
-            assert shape[1] == 64, "BatchNorm oracle: 64x64 images only"
-            for i, (ci, co, k) in enumerate(spec):
-                sh[f"{prefix}conv.{3 * i}.weight"] = (ci, co, k, k)
-                if i < len(spec) - 1:
-                    batch_norm(f"{prefix}conv.{3 * i + 1}", co)
+        lin(prefix + ("fc" if shape[1] == 84 else "fc1"), E, D + S)          # ImageDecoder_84 names its Linear `fc` (observation_model.py:115)
+        layers = IMAGE_DECODER_LAYERS[shape[1]]
+        norm = cfg.normalization
+        assert norm in IMAGE_NORMS[("dec", shape[1])], f"the reference has no {norm} variant of the {shape[1]}x{shape[1]} decoder"
+        cin = E
+        for i, (cout, k) in enumerate(layers):
+            cout = c if cout is None else cout
+            last = i == len(layers) - 1
+            if norm is None:
+                sh[f"{prefix}conv.{2 * i}.weight"] = (cin, cout, k, k)
+                sh[f"{prefix}conv.{2 * i}.bias"] = (cout,)
+            else:                                   # ConvT(bias=False), norm, ReLU triples; the last ConvT keeps its bias
+                sh[f"{prefix}conv.{3 * i}.weight"] = (cin, cout, k, k)
+                if last:
+                    sh[f"{prefix}conv.{3 * i}.bias"] = (cout,)
                 else:
-                    sh[f"{prefix}conv.{3 * i}.bias"] = (co,)
-            return
-        for i, (ci, co, k) in enumerate(spec):
-            sh[f"{prefix}conv.{2 * i}.weight"] = (ci, co, k, k)
-            sh[f"{prefix}conv.{2 * i}.bias"] = (co,)
+                    batch_norm(f"{prefix}conv.{3 * i + 1}", cout)
+            cin = cout
 
     def instance_norm(prefix, c):                   # affine parameters (running statistics: make_buffers)
         sh[prefix + ".weight"] = (c,)
@@ -257,7 +269,7 @@ def make_params(cfg: OracleConfig, seed: int = 0, dtype=torch.float32) -> Dict[s
             fan_in = max(shp[0], 16)
         b = 1.0 / math.sqrt(fan_in)
         out[k] = ((torch.rand(shp, generator=g, dtype=torch.float64) * 2 - 1) * b).to(dtype)
-    if cfg.normalization == "BatchNorm" or any("sound" in n for n in (*cfg.names_enc, *cfg.names_rec)):
+    if cfg.normalization is not None or any("sound" in n for n in (*cfg.names_enc, *cfg.names_rec)):
         out.update(make_buffers(cfg, dtype))
     return out
 
@@ -334,14 +346,15 @@ def _groups(P: Dict[str, Tensor], cfg: OracleConfig):
 # --------------------------------------------------------------------------------------------
 # encoders  (utils/models/encoder.py)
 # --------------------------------------------------------------------------------------------
-def image_encoder(p: _P, x: Tensor, emb: int, act_cnn: str = "relu", train: bool = True) -> Tensor:
+def image_encoder(p: _P, x: Tensor, emb: int, act_cnn: str = "relu", train: bool = True, norm: str = "BatchNorm") -> Tensor:
     """ImageEncoder (64x64) encoder.py:307-351 / ImageEncoder_128 :415-500, normalization=None:
     n x (Conv2d k4 s2 + ReLU) then reshape(-1,1024) (flatten order C,H,W).
     normalization="BatchNorm" (encoder.py:324-337): n x (Conv2d k4 s2 without bias + BatchNorm2d + ReLU)."""
     i = 0
     if (p.prefix + "conv.1.running_mean") in p.p:
         while (p.prefix + f"conv.{3 * i}.weight") in p.p:
-            x = F.relu(batch_norm(p.sub(f"conv.{3 * i + 1}."), F.conv2d(x, p[f"conv.{3 * i}.weight"], None, stride=2), train))
+            nfn = instance_norm if norm == "InstanceNorm" else batch_norm
+            x = F.relu(nfn(p.sub(f"conv.{3 * i + 1}."), F.conv2d(x, p[f"conv.{3 * i}.weight"], None, stride=2), train))
             i += 1
         x = x.reshape(-1, 1024)
         if emb != 1024:
@@ -423,7 +436,7 @@ def encode(P, cfg: OracleConfig, obs: Dict[str, Tensor], train: bool = True) -> 
         Tn, B = x.shape[:2]
         flat = x.reshape(Tn * B, *x.shape[2:])
         if "image" in n:
-            e = image_encoder(g["enc"][n], flat, cfg.embedding_size["image"], train=train)
+            e = image_encoder(g["enc"][n], flat, cfg.embedding_size["image"], train=train, norm=cfg.normalization)
         elif "sound" in n:
             e = sound_encoder(g["enc"][n], flat, train)
         else:
@@ -569,12 +582,13 @@ def rollout(P, cfg: OracleConfig, prev_state: Tensor, actions: Tensor, prev_beli
 # --------------------------------------------------------------------------------------------
 # decoders  (utils/models/observation_model.py), reward model
 # --------------------------------------------------------------------------------------------
-def image_decoder(p: _P, h: Tensor, s: Tensor, train: bool = True) -> Tensor:
+def image_decoder(p: _P, h: Tensor, s: Tensor, train: bool = True, norm: str = "BatchNorm") -> Tensor:
     """ImageDecoder.forward observation_model.py:91-105 (64x64) / ImageDecoder_128 :215-229:
     fc1([h,s]) (no activation) -> [N,E,1,1] -> ConvTranspose2d stack with ReLU between."""
     Tn, B = h.shape[:2]
+    fc = "fc1" if (p.prefix + "fc1.weight") in p.p else "fc"            # ImageDecoder_84: `fc`
     x = F.linear(torch.cat([h.reshape(Tn * B, -1), s.reshape(Tn * B, -1)], 1),
-                 p["fc1.weight"], p["fc1.bias"])
+                 p[fc + ".weight"], p[fc + ".bias"])
     x = x.reshape(Tn * B, -1, 1, 1)
     if (p.prefix + "conv.1.running_mean") in p.p:           # observation_model.py:75-86
         n = 0
@@ -584,7 +598,8 @@ def image_decoder(p: _P, h: Tensor, s: Tensor, train: bool = True) -> Tensor:
             last = i == n - 1
             x = F.conv_transpose2d(x, p[f"conv.{3 * i}.weight"], p[f"conv.{3 * i}.bias"] if last else None, stride=2)
             if not last:
-                x = F.relu(batch_norm(p.sub(f"conv.{3 * i + 1}."), x, train))
+                nfn = instance_norm if norm == "InstanceNorm" else batch_norm
+                x = F.relu(nfn(p.sub(f"conv.{3 * i + 1}."), x, train))
         return x.reshape(Tn, B, *x.shape[1:])
     n = 0
     while (p.prefix + f"conv.{2 * n}.weight") in p.p:
@@ -616,7 +631,7 @@ def decode(P, cfg: OracleConfig, h: Tensor, s: Tensor, train: bool = True) -> Di
     out = {}
     for n in cfg.names_rec:
         if "image" in n:
-            out[n] = image_decoder(g["dec"][n], h, s, train)
+            out[n] = image_decoder(g["dec"][n], h, s, train, norm=cfg.normalization)
         elif "sound" in n:
             out[n] = sound_decoder(g["dec"][n], h, s, train)
         else:

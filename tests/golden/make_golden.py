@@ -160,7 +160,12 @@ def states_to_plain(st):
     return out
 
 
+ONLY = set()
+
+
 def gen_train(name, oc, B=4, T=6, steps=2):
+    if ONLY and name not in ONLY:
+        return
     torch.manual_seed(0)
     model = build_RSSM(ref_cfg(oc, B, T), torch.device("cpu"))
     P = O.make_params(oc, seed=0)
@@ -231,6 +236,8 @@ def gen_train(name, oc, B=4, T=6, steps=2):
 def gen_infer(name, oc, B=3, T=5, H=7):
     """estimate_state(det=True) and the open-loop imagination call of check_model.ipynb cell 55
     (transition_model(s, actions[H], h, None, None), stochastic and det)."""
+    if ONLY and name not in ONLY:
+        return
     torch.manual_seed(0)
     model = build_RSSM(ref_cfg(oc, B, T), torch.device("cpu"))
     P = O.make_params(oc, seed=0)
@@ -259,6 +266,7 @@ def gen_infer(name, oc, B=3, T=5, H=7):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    ONLY.update(sys.argv[1:])            # python make_golden.py [name ...]: regenerate only the named fixtures
     gen_train("mopoe", O.OracleConfig(fusion="MoPoE"))
     gen_train("poe", O.OracleConfig(fusion="PoE"))
     gen_train("nn", O.OracleConfig(fusion="NN"))
@@ -290,5 +298,13 @@ if __name__ == "__main__":
                                              names_rec=("image_horizon_128", "pose_quat_v2"),
                                              observation_shapes={"image_horizon_128": [3, 128, 128], "pose_quat_v2": [3]}), B=2, T=4)
     gen_train("mopoe_lrramp", O.OracleConfig(fusion="MoPoE", learning_rate_schedule=3), steps=3)
+    # the remaining image stacks (encoder.py:362-413, 511-615; observation_model.py:108-160, 231-345) and normalisation variants
+    for side, name in ((84, "image_horizon_84"), (256, "image_horizon_256")):
+        gen_train(f"mopoe_img{side}", O.OracleConfig(fusion="MoPoE", names_enc=(name, "pose_quat_v2"), names_rec=(name, "pose_quat_v2"),
+                                                      observation_shapes={name: [3, side, side], "pose_quat_v2": [3]}), B=2, T=4)
+    gen_train("single_img84_bn", O.OracleConfig(fusion="single", names_enc=("image_horizon_84",), names_rec=("image_horizon_84",),
+                                                observation_shapes={"image_horizon_84": [3, 84, 84]}, normalization="BatchNorm", lr=1e-5))
+    # (an InstanceNorm fixture of the 256x256 stacks was tried and dropped: its last encoder layer normalises planes of 4 values,
+    #  which amplifies summation-order noise beyond any useful pin; the product implements None and BatchNorm for the image stacks)
     gen_infer("mopoe", O.OracleConfig(fusion="MoPoE"))
     gen_infer("single", O.OracleConfig(fusion="single", names_enc=("image_horizon",), names_rec=("image_horizon",)))

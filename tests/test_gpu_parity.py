@@ -31,7 +31,10 @@ def test_train_step_matches_oracle(fusion, kw):
                                   # the shipped YAML's layers: BatchNorm image stacks (encoder.py:324-337, observation_model.py:75-86)
                                   # and the sound modality (encoder.py:661-721, observation_model.py:420-472), running statistics
                                   # after every step and an eval-mode pass included
-                                  "mopoe_bn", "single_bn", "mopoe_sound", "mopoe_sound_bn"])
+                                  "mopoe_bn", "single_bn", "mopoe_sound", "mopoe_sound_bn",
+                                  # the remaining image stacks: 84x84 and 256x256 (encoder.py:362-413,511-615; observation_model.py:
+                                  # 108-160,231-345), BatchNorm on a stack other than 64x64
+                                  "mopoe_img84", "mopoe_img256", "single_img84_bn"])
 def test_train_step_matches_reference_fixture(name, golden_dir):
     """Directly against tests/golden/train_*.pt (outputs of the unmodified reference)."""
     rec = torch.load(os.path.join(golden_dir, f"train_{name}.pt"), weights_only=False)

@@ -9,7 +9,7 @@ from oracle import mrssm_oracle as O
 
 TRAIN = ["mopoe", "poe", "nn", "single", "mopoe_clip", "poe_noalpha", "mopoe_reward", "mopoe_over", "poe_over", "single_over",
          "mopoe_bn", "single_bn", "mopoe_sound", "mopoe_sound_bn", "mopoe_logprob", "single_logprob", "mopoe_lrramp",
-         "mopoe_emb512", "mopoe_img128"]
+         "mopoe_emb512", "mopoe_img128", "mopoe_img84", "mopoe_img256", "single_img84_bn"]
 
 
 def _cfg(meta):
