@@ -105,6 +105,15 @@ def test_bf16_mode_shipped_layers_within_stated_tolerance():
     assert rep["state_err"] < 2e-2 and rep["loss_rel"] < 2e-2 and rep["gnorm_rel"] < 3e-2 and rep["grad_rel_fro"] < 5e-2, rep
 
 
+@pytest.mark.parametrize("side", [84, 256])
+def test_bf16_mode_other_image_sizes_within_stated_tolerance(side):
+    """84x84 / 256x256 stacks in bf16 mode (general NCHW kernels, tensor-core route for their wide layers) against the fp32 oracle."""
+    name = f"image_horizon_{side}"
+    rep = U.run_train_parity_bf16("MoPoE", B=3, T=5, steps=2, device=DEV, names_enc=(name, "pose_quat_v2"), names_rec=(name, "pose_quat_v2"),
+                                  observation_shapes={name: [3, side, side], "pose_quat_v2": [3]})
+    assert rep["state_err"] < 2e-2 and rep["loss_rel"] < 2e-2 and rep["gnorm_rel"] < 3e-2 and rep["grad_rel_fro"] < 5e-2, rep
+
+
 def test_normalize_image_u8_matches_reference_formula():
     """mrssm_normalize_image_u8 against image_processing.py:5-11 restated in torch, with the noise supplied."""
     from mrssm_b200 import _lib as L
