@@ -190,9 +190,25 @@ def write_checkpoint(path, B=2, T=4, steps=2, fusion="MoPoE"):
     return dict(file=os.path.join(path, "models_%d.pth" % steps), n_params=sum(p.numel() for p in model.param_list))
 
 
+def try_expert_dist(expert_dist):
+    """Does the unmodified reference construct a model with this `multimodal_params.expert_dist`?  (q(st|ot): its MoPoE / PoE
+    factories call MultimodalStochasticEncoder(observation_names_enc=...) while that class takes observation_names_rec
+    — MRSSM_MoPoE/algo.py:51-60 vs utils/models/encoder.py:885-895 — so construction raises TypeError.)"""
+    import torch
+    build_RSSM = _import_reference()
+    cfg = reference_cfg(2, 4, "cpu", "MoPoE")
+    cfg.rssm.multimodal_params.expert_dist = expert_dist
+    try:
+        build_RSSM(cfg, torch.device("cpu"))
+        return dict(expert_dist=expert_dist, constructed=True)
+    except Exception as e:                                   # noqa: BLE001  (the point is to report whatever the reference raises)
+        return dict(expert_dist=expert_dist, constructed=False, error=type(e).__name__, message=str(e))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["train", "samebox", "ckpt"])
+    ap.add_argument("what", choices=["train", "samebox", "ckpt", "expert_dist"])
+    ap.add_argument("--expert-dist", default="q(st|ot)")
     ap.add_argument("--out", default="/tmp/mrssm_ref_ckpt")
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--chunk", type=int, default=50)
@@ -204,7 +220,9 @@ def main():
     ap.add_argument("--belief", type=int, default=200)
     ap.add_argument("--state", type=int, default=30)
     a = ap.parse_args()
-    if a.what == "ckpt":
+    if a.what == "expert_dist":
+        res = try_expert_dist(a.expert_dist)
+    elif a.what == "ckpt":
         res = write_checkpoint(a.out, fusion=a.fusion)
     elif a.what == "train":
         res = time_train(a.batch, a.chunk, a.fusion, a.steps, a.warmup, a.device, a.image, a.belief, a.state, a.belief)

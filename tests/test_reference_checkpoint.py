@@ -72,3 +72,23 @@ def test_reference_written_checkpoint_loads(tmp_path, fusion):
     for p, q in zip(model.param_list, model2.param_list):
         assert torch.equal(p, q)
     assert model2.model_optimizer.step_count == 0 and float(model2.model_optimizer.flat_m.abs().max()) == 0.0
+
+
+@pytest.mark.skipif(not ref_arm.available(), reason="oracle/_ref not staged (run __graft_entry__.build() where /root/reference is mounted)")
+def test_expert_dist_q_st_ot_is_unreachable_in_the_reference_and_rejected_here():
+    """SURVEY §8f rank 4 lists expert_dist="q(st|ot)" as a variant.  The unmodified reference cannot construct it (its PoE / MoPoE
+    factories pass `observation_names_enc=` to MultimodalStochasticEncoder, whose parameter is `observation_names_rec`: TypeError), so
+    there is no behaviour to mirror; the product says so with NotImplementedError instead of inventing one."""
+    from algos.MRSSM.MRSSM.algo import build_RSSM
+    from mrssm_b200.config import hot_path_config
+    out = subprocess.run([sys.executable, "-m", "oracle.ref_arm", "expert_dist"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    info = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert info["constructed"] is False and info["error"] == "TypeError" and "observation_names_enc" in info["message"], info
+    ok = subprocess.run([sys.executable, "-m", "oracle.ref_arm", "expert_dist", "--expert-dist", "q(st|ht,ot)"], cwd=ROOT,
+                        capture_output=True, text=True, timeout=600)
+    assert json.loads([l for l in ok.stdout.splitlines() if l.startswith("{")][-1])["constructed"] is True
+    cfg = hot_path_config(fusion="MoPoE", batch_size=2, chunk_size=4, device="cpu")
+    cfg.rssm.multimodal_params.expert_dist = "q(st|ot)"
+    with pytest.raises(NotImplementedError):
+        build_RSSM(cfg, torch.device("cpu"))
