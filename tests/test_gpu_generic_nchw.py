@@ -275,3 +275,68 @@ def test_tensor_core_route_chunks_over_images():
             ops._GC_COL_BYTES = old
     for a, b in zip(*outs):
         assert _fro(a, b) <= 1e-5                                        # (atomics order in the weight gradient only)
+
+
+def _guarded(numel, dtype=torch.float32, pad=4096):
+    """A buffer of `numel` elements between two sentinel-filled guard zones: (whole, view, check())."""
+    whole = torch.full((numel + 2 * pad,), 12345.0, device=DEV, dtype=dtype)
+    view = whole[pad:pad + numel]
+
+    def check():
+        assert bool((whole[:pad] == 12345.0).all()) and bool((whole[pad + numel:] == 12345.0).all()), "write outside the output buffer"
+    return whole, view, check
+
+
+@pytest.mark.parametrize("g", [(3, 7, 9, 11, 5, (2, 3), (3, 2), (2, 0)), (2, 64, 20, 10, 1, (7, 7), (1, 1), (3, 3)),
+                               (5, 3, 30, 30, 32, (6, 6), (2, 2), (0, 0)), (2, 40, 13, 9, 70, (3, 4), (1, 2), (1, 1))])
+def test_general_convolution_kernels_stay_inside_their_outputs(g):
+    """Through the C ABI with guard zones around every output (compute-sanitizer is not available on the pool): the three roles of
+    the general convolution — 64x64, 256x16, 16x256 and direct small-channel tiles, ragged sizes — write only what they own."""
+    import ctypes as C
+    from mrssm_b200 import _lib as L
+    N, Cin, H, W, Cout, k, s, p = g
+    Ho, Wo = (H + 2 * p[0] - k[0]) // s[0] + 1, (W + 2 * p[1] - k[1]) // s[1] + 1
+    gen = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.randn(N, Cin, H, W, device=DEV, generator=gen)
+    w = torch.randn(Cout, Cin, *k, device=DEV, generator=gen)
+    dy = torch.randn(N, Cout, Ho, Wo, device=DEV, generator=gen)
+    _, y, chk_y = _guarded(N * Cout * Ho * Wo)
+    _, dx, chk_dx = _guarded(x.numel())
+    _, dw, chk_dw = _guarded(w.numel())
+    dw.zero_()
+
+    def args(**kw):
+        return L.GConvArgs(N, Cin, H, W, Cout, k[0], k[1], s[0], s[1], p[0], p[1], Ho, Wo, kw.get("x"), kw.get("w"), kw.get("y"), kw.get("dx"),
+                           kw.get("dw"))
+    L.call("mrssm_gconv_fwd", C.byref(args(x=L.ptr(x), w=L.ptr(w), y=y.data_ptr())))
+    L.call("mrssm_gconv_dgrad", C.byref(args(w=L.ptr(w), y=L.ptr(dy), dx=dx.data_ptr())))
+    L.call("mrssm_gconv_wgrad", C.byref(args(x=L.ptr(x), y=L.ptr(dy), dw=dw.data_ptr())))
+    torch.cuda.synchronize()
+    chk_y(), chk_dx(), chk_dw()
+    ref = F.conv2d(x, w, None, stride=s, padding=p)
+    _close(y.view_as(ref), ref)
+
+
+def test_tensor_core_staging_kernels_stay_inside_their_outputs():
+    import ctypes as C
+    from mrssm_b200 import _lib as L
+    N, Cin, H, W, Cout, k, s, p = 3, 24, 11, 7, 16, (3, 4), (2, 1), (1, 2)
+    Ho, Wo = (H + 2 * p[0] - k[0]) // s[0] + 1, (W + 2 * p[1] - k[1]) // s[1] + 1
+    K = Cin * k[0] * k[1]
+    gen = torch.Generator(device=DEV).manual_seed(12)
+    x = torch.randn(N, Cin, H, W, device=DEV, generator=gen)
+    a = L.GConvArgs(N, Cin, H, W, Cout, k[0], k[1], s[0], s[1], p[0], p[1], Ho, Wo, None, None, None, None, None)
+    _, xh, chk_xh = _guarded(N * H * W * Cin, torch.bfloat16)
+    L.call("mrssm_nchw_to_nhwc_bf16", L.ptr(x), N, Cin, H * W, xh.data_ptr())
+    _, col, chk_col = _guarded(N * Ho * Wo * K, torch.bfloat16)
+    L.call("mrssm_im2col_nhwc", C.byref(a), xh.data_ptr(), col.data_ptr())
+    _, dxh, chk_dxh = _guarded(N * H * W * Cin)
+    L.call("mrssm_col2im_nhwc", C.byref(a), col.data_ptr(), dxh.data_ptr())
+    _, back, chk_back = _guarded(N * Cin * H * W)
+    L.call("mrssm_nhwc_to_nchw_f32", dxh.data_ptr(), N, Cin, H * W, back.data_ptr())
+    torch.cuda.synchronize()
+    chk_xh(), chk_col(), chk_dxh(), chk_back()
+    # im2col followed by col2im multiplies every input pixel by the number of windows that cover it
+    cover = F.conv_transpose2d(torch.ones(1, 1, Ho, Wo, device=DEV), torch.ones(1, 1, *k, device=DEV), stride=s,
+                               padding=p, output_padding=(H - ((Ho - 1) * s[0] - 2 * p[0] + k[0]), W - ((Wo - 1) * s[1] - 2 * p[1] + k[1])))
+    _close(back.view(N, Cin, H, W), x.bfloat16().float() * cover, rtol=1e-5)
