@@ -9,6 +9,7 @@ ready-made chunks (bench.py's e2e leg); the full replay buffer — chunk samplin
 store — is ``utils/replay_buffer/memory.py``.
 """
 import contextlib
+import ctypes as C
 import os
 
 import torch
@@ -67,6 +68,7 @@ class PinnedChunkSource:
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in obs.values()) + 4 * (a.numel() + r.numel() + n.numel())
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.slots = [None, None]          # device staging, double buffered
+        self._s2d_ready = [False, False]
         self.i = 0
         self.pending = None                # (slot index, ready event) of the batch in flight
 
@@ -77,14 +79,23 @@ class PinnedChunkSource:
             raw = {name: torch.empty_like(v, device=dev) for name, v in obs.items()}
             f32 = {name: (torch.empty(v.shape, device=dev, dtype=torch.float32) if v.dtype == torch.uint8 else raw[name])
                    for name, v in obs.items()}
+            # bf16 mode: the space-to-depth bf16 form of frames 1.. of every <= 4-channel image (what the conv encoder's first layer
+            # and the fused reconstruction loss read; optimize() drops frame 0, base/algo.py:213-215), made on the copy stream too
+            s2d = {}
+            for name, v in obs.items():
+                if v.dtype == torch.uint8 and v.dim() == 5 and v.shape[2] <= 4 and v.shape[0] > 1 and v.shape[3] % 2 == 0 and v.shape[4] % 2 == 0:
+                    T, B, Cc, H, W = v.shape
+                    s2d[name] = torch.empty(L.view_numel(L.PLANAR, (T - 1) * B, H // 2, W // 2, 16), device=dev, dtype=torch.bfloat16)
             self.slots[k] = (raw, f32, torch.empty_like(a, device=dev), torch.empty_like(r, device=dev),
-                             torch.empty_like(n, device=dev))
+                             torch.empty_like(n, device=dev), s2d)
         return self.slots[k]
 
     def _launch(self, k, chunk_index):
         """Enqueue H2D + normalisation of one chunk into slot k on the copy stream."""
+        self._s2d_ready[k] = False
         obs, a, r, n = self.host[chunk_index % len(self.host)]
-        raw, f32, da, dr, dn = self._slot(k)
+        raw, f32, da, dr, dn, s2d = self._slot(k)
+        from . import ops
         main = torch.cuda.current_stream(self.device)
         self.copy_stream.wait_stream(main)                 # the slot's previous consumer has been enqueued before us
         with torch.cuda.stream(self.copy_stream):
@@ -93,6 +104,12 @@ class PinnedChunkSource:
                 if v.dtype == torch.uint8:
                     L.call("mrssm_normalize_image_u8", L.ptr_any(raw[name]), v.numel(), self.bit_depth, None,
                            self.seed + chunk_index, L.ptr(f32[name]))
+                    if name in s2d and ops.bf16_mode():
+                        T, B, Cc, H, W = v.shape
+                        x1 = f32[name][1:]
+                        L.call("mrssm_pl_import_s2d", C.byref(L.nchw(x1, H, W, Cc)), (T - 1) * B, H, W, Cc, 1.0,
+                               C.byref(L.tv(s2d[name], L.PLANAR, H // 2, W // 2, 16)))
+                        self._s2d_ready[k] = True
             da.copy_(a, non_blocking=True)
             dr.copy_(r, non_blocking=True)
             dn.copy_(n, non_blocking=True)
@@ -106,7 +123,12 @@ class PinnedChunkSource:
             self.pending = (k, self._launch(k, self.i))
         _, ev = self.pending
         torch.cuda.current_stream(self.device).wait_event(ev)
-        raw, f32, da, dr, dn = self.slots[k]
+        raw, f32, da, dr, dn, s2d = self.slots[k]
+        if self._s2d_ready[k]:
+            from . import ops
+            for name, t in s2d.items():    # keyed like the tensor the encoder will see: frames 1.. folded to [(T-1)*B, C, H, W]
+                x1 = f32[name][1:]
+                ops.remember_s2d(x1.reshape(-1, *x1.shape[2:]), t)
         self.i += 1
         self.pending = (k ^ 1, self._launch(k ^ 1, self.i)) if self.prefetch else None
         return [dict(f32), da, dr, dn]

@@ -156,3 +156,40 @@ def test_pinned_chunk_source_feeds_optimize():
         model.optimize(D2)
         losses.append(float(model.model_loss))
     assert all(l == l and abs(l) < 1e6 for l in losses), losses
+
+
+def test_pinned_chunk_source_prefetched_s2d_is_the_same_step():
+    """bf16 mode: the input pipeline converts frames 1.. to the bf16 space-to-depth form on its copy stream and the conv encoder /
+    fused reconstruction loss pick that copy up instead of converting on the critical path — same kernel, same fp32 source, so the
+    step is the same with and without it."""
+    from mrssm_b200 import ops
+    from mrssm_b200.data import PinnedChunkSource
+    oc = O.OracleConfig(fusion="MoPoE")
+    g = torch.Generator().manual_seed(0)
+    chunks = []
+    for _ in range(2):
+        obs = {"image_horizon": torch.randint(0, 256, (5, 3, 3, 64, 64), generator=g, dtype=torch.uint8),
+               "pose_quat_v2": torch.randn(5, 3, 3, generator=g)}
+        chunks.append((obs, torch.randn(5, 3, 3, generator=g), torch.zeros(5, 3), torch.ones(5, 3, 1)))
+    losses, hits = [], []
+    for prefetch_s2d in (True, False):
+        model, _ = U.build_product(oc, 3, 5, DEV, bf16=True)
+        D = PinnedChunkSource(chunks, DEV, bit_depth=5, seed=1)
+        if not prefetch_s2d:
+            D._slot(0)[5].clear(), D._slot(1)[5].clear()           # no s2d buffers -> nothing is made or registered
+        orig, seen = ops.recall_s2d, []
+        ops.recall_s2d = lambda t: (seen.append(orig(t) is not None), orig(t))[1]
+        try:
+            torch.manual_seed(3)
+            run = []
+            for _ in range(3):
+                model.optimize(D)
+                run.append(float(model.model_loss))
+        finally:
+            ops.recall_s2d = orig
+        losses.append(run)
+        hits.append(seen)
+    assert all(hits[0]) and len(hits[0]) >= 6                       # encoder and loss both found the prefetched copy, every step
+    assert hits[1][0] is False                                      # without it the encoder converts itself (and then the loss finds that)
+    for a, b in zip(*losses):                                       # (fp32 atomics in the loss reduction: equal up to summation order)
+        assert a == pytest.approx(b, rel=1e-5), losses
