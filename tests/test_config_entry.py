@@ -77,3 +77,19 @@ def test_shipped_default_yaml_builds_the_model():
     assert {"fc1.weight", "conv.0.weight", "conv.1.running_mean", "conv.7.bias", "conv.9.weight", "conv.9.bias"} <= set(dec["image_horizon"])
     assert {"up_conversion.weight", "up_sample_0.0.weight", "up_sample_2.1.running_var", "out.weight"} <= set(dec["sound"])
     assert tuple(dec["sound"]["up_conversion.weight"].shape) == (128 * 2 * 32 * 4, 1024 + 128, 1)
+
+
+REF_CONFIG = "/root/reference/train/COBOTTA/SingleHoleDrilling/MRSSM/MRSSM/config"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CONFIG), reason="the reference tree is only mounted in the build container")
+def test_yaml_tree_parses_to_the_reference_tree():
+    """The five YAML files are written in their own layout; what they parse to is, key for key and value for value, what the
+    reference's files parse to (so `python main.py` without overrides is the reference's shipped experiment)."""
+    import yaml
+    for rel in ("config.yaml", "main/main.yaml", "env/SingleHoleDrilling.yaml", "rssm/multimodal.yaml", "train/train.yaml"):
+        with open(os.path.join(ENTRY, "config", rel)) as f:
+            mine = yaml.safe_load(f)
+        with open(os.path.join(REF_CONFIG, rel)) as f:
+            ref = yaml.safe_load(f)
+        assert mine == ref, rel
