@@ -545,7 +545,8 @@ static int launch_fwd(const mrssm_tc_conv_args* a, int op, cudaStream_t st) {
         const bool full_window = op == OP_DOWN ? (a->Hs == 1 && a->Ws == 1 && a->Hl == a->ksz && a->Wl == a->ksz &&
                                                   (a->ksz == 1 || (in.sW == Cin && in.sH == (long long)a->Wl * Cin)))
                                                : (a->ksz == 1 && a->Hl == 1 && a->Wl == 1 && a->Hs == 1 && a->Ws == 1);
-        if (full_window && in.sC == 1 && Cin % 8 == 0 && in.sI % 8 == 0 && a->n_out_pad % 16 == 0 && a->n_out_pad <= 4096 &&
+        if (full_window && in.sC == 1 && Cin % 8 == 0 && in.sI % 8 == 0 && a->n_out_pad % 16 == 0 &&
+            (a->n_out_pad <= 4096 || !a->bias || (a->bias_mod > 0 && a->bias_mod % 8 == 0 && a->bias_mod <= 4096 && a->n_out_valid % a->bias_mod == 0)) &&
             (a->out_f32 || (out.sC == 1 && out.sI % 8 == 0)) && (!a->mask.ptr || (a->mask.sC == 1 && a->mask.sI % 8 == 0))) {
             const int K = (op == OP_DOWN) ? a->ksz * a->ksz * Cin : Cin;
             const int Kpad = (int)(ceil_div64(a->group_n > 0 ? a->group_k : K, BK) * BK);

@@ -18,6 +18,7 @@ constexpr int DT = 704, D_MMA_WARP = 21, D_EPI = 16;
 struct DenseP {
     int M, K, Npad, n_valid, BN, n_ntiles, n_mtiles, nkb, NS;
     int act, mask_mode, out_f32, bias_mod;
+    int bias_period;                      // entries of the shared-memory bias table: column n reads entry n % bias_period
     long long ldc, cstride, ldm;          // output row / column stride (elements), mask row stride
     void* out;
     const bf16* mask;
@@ -71,7 +72,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ 
     const uint32_t a_bytes = 128u * 128u, b_bytes = (uint32_t)P.BN * 128u, stage = a_bytes + b_bytes;
     const int n_tiles = P.n_mtiles * P.n_ntiles;
 
-    for (int c = tid; c < P.Npad; c += DT) bias_s[c] = (P.bias && c < P.n_valid) ? P.bias[c % P.bias_mod] : 0.f;
+    for (int c = tid; c < P.bias_period; c += DT) bias_s[c] = (P.bias && c < P.n_valid) ? P.bias[c % P.bias_mod] : 0.f;
     if (tid == 0) {
         for (int s = 0; s < 8; ++s) {
             tc::mbar_init(tc::smem_u32(&full[s]), 1);
@@ -156,7 +157,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ 
                     for (int h = 0; h < 2; ++h) {
                         const int n = nt * P.BN + col0 + c0 + 8 * h;
                         if (n >= P.Npad) continue;
-                        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + n), b1 = *reinterpret_cast<const float4*>(bias_s + n + 4);
+                        const int nb = n % P.bias_period;
+                        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + nb), b1 = *reinterpret_cast<const float4*>(bias_s + nb + 4);
                         float x[8] = {v[8 * h] + b0.x, v[8 * h + 1] + b0.y, v[8 * h + 2] + b0.z, v[8 * h + 3] + b0.w,
                                       v[8 * h + 4] + b1.x, v[8 * h + 5] + b1.y, v[8 * h + 6] + b1.z, v[8 * h + 7] + b1.w};
                         if (P.addend) {
@@ -219,7 +221,9 @@ int dense_tc_launch(const void* A, long long lda, int M, int K, const void* wpac
                     int out_f32, cudaStream_t st, const float* addend, long long addend_ld, int group_n, int group_k) {
     MRSSM_CHECK(A && wpacked && out && M > 0 && K > 0 && Npad % 16 == 0 && Kpad % 64 == 0 && lda % 8 == 0 && K % 8 == 0,
                 "dense_tc: bad arguments (M %d K %d Npad %d Kpad %d lda %lld)", M, K, Npad, Kpad, lda);
-    MRSSM_CHECK(Npad <= 4096, "dense_tc: %d output columns exceed the bias table", Npad);
+    // the bias table holds 4096 entries: all columns, or one period of a periodic bias (ConvTranspose2d on the 1x1 map: n = tap * C + c)
+    const bool periodic = bias_mod > 0 && bias_mod % 8 == 0 && bias_mod <= 4096 && n_valid % bias_mod == 0;
+    MRSSM_CHECK(Npad <= 4096 || !bias || periodic, "dense_tc: %d output columns exceed the bias table", Npad);
     MRSSM_CHECK(out_f32 || (ldc % 8 == 0 && cstride == 1), "dense_tc: bf16 output rows must be 16-byte aligned");
     DenseP P;
     P.M = M; P.K = K; P.Npad = Npad; P.n_valid = n_valid;
@@ -239,6 +243,7 @@ int dense_tc_launch(const void* A, long long lda, int M, int K, const void* wpac
     const int stage = 128 * 128 + P.BN * 128;
     P.NS = std::max(2, std::min(8, (200 * 1024) / stage));
     P.act = act; P.mask_mode = mask ? mask_mode : 0; P.out_f32 = out_f32; P.bias_mod = bias_mod > 0 ? bias_mod : std::max(1, n_valid);
+    P.bias_period = (Npad > 4096 && periodic) ? bias_mod : std::min(Npad, 4096);
     P.ldc = ldc; P.cstride = cstride; P.ldm = ldm;
     P.out = out; P.mask = (const bf16*)mask; P.bias = bias;
     P.addend = addend; P.lda_add = addend_ld;
