@@ -476,7 +476,7 @@ def run_ours(args):
     step_keys = [k for k in agg if k.startswith(("rstep_", "rollout_steps_", "tc_conv_down:step_", "tc_conv_up:step_")) or k == "add2"]
     if step_keys:       # large-model rollout (config 5): per-step launches, launch-latency-bound by construction
         ms_r = sum(agg[k]["ms"] for k in step_keys)
-        n_r = 2 * (args.chunk - 1) * 8       # kernels of the two C-issued loops: 8 per time step and direction (one chunk of heads)
+        n_r = 2 * (args.chunk - 1) * 7       # kernels of the two C-issued loops: 7 per time step and direction (one chunk of heads)
         rollout_roof["rollout_step(all launches)"] = {
             "bound": "latency", "ms_per_train_step": ms_r, "launches": n_r, "us_per_launch": ms_r / n_r * 1e3,
             "share_of_step": ms_r / total_ms, "dependent_steps": args.chunk - 1,

@@ -332,9 +332,12 @@ int mrssm_rollout_tc_bwd(const mrssm_rollout_bwd_args* g, const void* packed_dev
  *   output, padding columns zeroed. */
 int mrssm_rstep_xin(const mrssm_rollout_args* a, int32_t t, int32_t KX, void* xin_b, void* stream);
 int mrssm_rstep_gate_fwd(const mrssm_rollout_args* a, int32_t t, const float* gi, const float* gh, void* hb_out, void* stream);
-int mrssm_rstep_heads_fwd(const mrssm_rollout_args* a, int32_t t, const float* o, int32_t ldo, int32_t head_stride, void* stream);
-int mrssm_rstep_heads_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float* cgs, void* const* d_o, int32_t ld, int32_t S2p,
+/* xin_next (bf16 [B,KX], may be NULL): also write step t + 1's [s_t * nonterminal_{t+1}, a_{t+1}, 0..] operand (saves the xin launch) */
+int mrssm_rstep_heads_fwd(const mrssm_rollout_args* a, int32_t t, const float* o, int32_t ldo, int32_t head_stride, void* xin_next, int32_t KX,
                           void* stream);
+/* dxin_next (fp32 [B,S+A], may be NULL): step t + 1's dxin; replaces cgs as the carry and yields g_actions[t + 1] (xin_bwd folded in) */
+int mrssm_rstep_heads_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float* cgs, const float* dxin_next, void* const* d_o, int32_t ld,
+                          int32_t S2p, void* stream);
 int mrssm_rstep_gate_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float* dh_heads, float* carry_a, const float* carry_b,
                          void* dgi, void* dgh, void* stream);
 int mrssm_rstep_xin_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float* dxin, int32_t ld, float* cgs, void* stream);

@@ -56,7 +56,8 @@ __global__ void rstep_gate_fwd_kernel(mrssm_rollout_args a, int t, const float* 
 
 // o[b][hd*hs + c], c < 2S: fc2 outputs of every head (bias included), row stride ldo.  -> prior / expert / posterior statistics, samples (step 5 of
 // the fused kernels: softplus + min_std, 1/sigma-weighted PoE over the subset of each state dimension, rsample)
-__global__ void rstep_heads_fwd_kernel(mrssm_rollout_args a, int t, const float* __restrict__ o, int ldo, int hs) {
+__global__ void rstep_heads_fwd_kernel(mrssm_rollout_args a, int t, const float* __restrict__ o, int ldo, int hs, bf16* __restrict__ xin_next,
+                                       int KX) {
     const int S = a.S, B = a.B, E = a.n_experts;
     const long long total = (long long)B * S;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -91,7 +92,20 @@ __global__ void rstep_heads_fwd_kernel(mrssm_rollout_args a, int t, const float*
             }
             a.post_means[off] = qm;
             a.post_stds[off] = qs;
-            a.post_states[off] = a.det ? qm : fmaf(qs, a.eps_post[off], qm);
+            const float qst = a.det ? qm : fmaf(qs, a.eps_post[off], qm);
+            a.post_states[off] = qst;
+            if (xin_next) {
+                const float m = a.nonterminals ? a.nonterminals[(long long)(t + 1) * B + b] : 1.f;
+                xin_next[(long long)b * KX + s] = __float2bfloat16(qst * m);
+            }
+        } else if (xin_next) {
+            const float m = a.nonterminals ? a.nonterminals[(long long)(t + 1) * B + b] : 1.f;
+            xin_next[(long long)b * KX + s] = __float2bfloat16(pst * m);
+        }
+        if (xin_next && s == 0) {            // the row's action columns and zero padding (the [s * mask, a, 0..] operand of step t + 1)
+            for (int c = S; c < KX; ++c)
+                xin_next[(long long)b * KX + c] =
+                    __float2bfloat16(c < S + a.A ? a.actions[((long long)(t + 1) * B + b) * a.A + (c - S)] : 0.f);
         }
     }
 }
@@ -101,14 +115,25 @@ __global__ void rstep_heads_fwd_kernel(mrssm_rollout_args a, int t, const float*
 struct HeadsBwdOut {
     bf16* d_o[MRSSM_MAX_HEADS];
 };
-__global__ void rstep_heads_bwd_kernel(mrssm_rollout_bwd_args g, int t, const float* __restrict__ cgs, HeadsBwdOut out, int ld, int S2p) {
+// cgs: the state-gradient carry [B,S], or — dxin_next given — taken straight from step t + 1's dxin = dxpre W_sa (fp32 [B, S+A]): its state
+// columns times the mask are the carry, its action columns are g_actions[t + 1] (the xin_bwd of step t + 1 folded in)
+__global__ void rstep_heads_bwd_kernel(mrssm_rollout_bwd_args g, int t, const float* __restrict__ cgs, const float* __restrict__ dxin_next,
+                                       HeadsBwdOut out, int ld, int S2p) {
     const mrssm_rollout_args& a = g.f;
     const int S = a.S, B = a.B, E = a.n_experts;
     const long long total = (long long)B * S;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int b = (int)(i / S), s = (int)(i - (long long)b * S);
         const long long off = ((long long)t * B + b) * S + s, ro = (long long)b * ld;
-        const float carry = cgs[i];
+        float carry;
+        if (dxin_next) {
+            const float m = a.nonterminals ? a.nonterminals[(long long)(t + 1) * B + b] : 1.f;
+            carry = dxin_next[(long long)b * (S + a.A) + s] * m;
+            if (s == 0 && g.g_actions)
+                for (int c = 0; c < a.A; ++c) g.g_actions[((long long)(t + 1) * B + b) * a.A + c] = dxin_next[(long long)b * (S + a.A) + S + c];
+        } else {
+            carry = cgs[i];
+        }
         float gps = g.g_prior_states ? g.g_prior_states[off] : 0.f;
         if (E == 0) gps += carry;
         const float gpm = gps + (g.g_prior_means ? g.g_prior_means[off] : 0.f);
@@ -215,7 +240,8 @@ extern "C" int mrssm_rstep_gate_fwd(const mrssm_rollout_args* a, int32_t t, cons
     MRSSM_LAUNCH_CHECK();
     return 0;
 }
-extern "C" int mrssm_rstep_heads_fwd(const mrssm_rollout_args* a, int32_t t, const float* o, int32_t ldo, int32_t head_stride, void* stream) {
+extern "C" int mrssm_rstep_heads_fwd(const mrssm_rollout_args* a, int32_t t, const float* o, int32_t ldo, int32_t head_stride, void* xin_next,
+                                     int32_t KX, void* stream) {
     MRSSM_CHECK(a && o && t >= 0 && t < a->T && a->S <= MRSSM_MAX_STATE && head_stride >= 2 * a->S && ldo >= (1 + a->n_experts) * head_stride,
                 "rstep_heads_fwd: bad arguments");
     MRSSM_CHECK(a->prior_states && a->prior_means && a->prior_stds && (a->det || a->eps_prior), "rstep_heads_fwd: null prior output / noise");
@@ -224,17 +250,19 @@ extern "C" int mrssm_rstep_heads_fwd(const mrssm_rollout_args* a, int32_t t, con
     for (int h = 1; h <= a->n_experts; ++h) MRSSM_CHECK(a->exp_means[h] && a->exp_stds[h], "rstep_heads_fwd: expert %d outputs missing", h);
     if (a->n_experts > 0)
         MRSSM_CHECK(a->post_states && a->post_means && a->post_stds && (a->det || a->eps_post), "rstep_heads_fwd: null posterior output / noise");
-    rstep_heads_fwd_kernel<<<blocks_for((long long)a->B * a->S), NT, 0, (cudaStream_t)stream>>>(*a, t, o, ldo, head_stride);
+    MRSSM_CHECK(!xin_next || (t + 1 < a->T && KX >= a->S + a->A), "rstep_heads_fwd: xin_next needs a step t + 1 and KX >= S + A");
+    rstep_heads_fwd_kernel<<<blocks_for((long long)a->B * a->S), NT, 0, (cudaStream_t)stream>>>(*a, t, o, ldo, head_stride, (bf16*)xin_next, KX);
     MRSSM_LAUNCH_CHECK();
     return 0;
 }
-extern "C" int mrssm_rstep_heads_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float* cgs, void* const* d_o, int32_t ld, int32_t S2p,
-                                     void* stream) {
-    MRSSM_CHECK(g && cgs && d_o && t >= 0 && t < g->f.T && S2p >= 2 * g->f.S && ld >= S2p, "rstep_heads_bwd: bad arguments");
+extern "C" int mrssm_rstep_heads_bwd(const mrssm_rollout_bwd_args* g, int32_t t, const float* cgs, const float* dxin_next, void* const* d_o,
+                                     int32_t ld, int32_t S2p, void* stream) {
+    MRSSM_CHECK(g && (cgs || dxin_next) && d_o && t >= 0 && t < g->f.T && S2p >= 2 * g->f.S && ld >= S2p, "rstep_heads_bwd: bad arguments");
+    MRSSM_CHECK(!dxin_next || t + 1 < g->f.T, "rstep_heads_bwd: dxin_next needs a step t + 1");
     HeadsBwdOut out;
     for (int h = 0; h < MRSSM_MAX_HEADS; ++h) out.d_o[h] = h <= g->f.n_experts ? (bf16*)d_o[h] : nullptr;
     for (int h = 0; h <= g->f.n_experts; ++h) MRSSM_CHECK(out.d_o[h], "rstep_heads_bwd: head %d output missing", h);
-    rstep_heads_bwd_kernel<<<blocks_for((long long)g->f.B * g->f.S), NT, 0, (cudaStream_t)stream>>>(*g, t, cgs, out, ld, S2p);
+    rstep_heads_bwd_kernel<<<blocks_for((long long)g->f.B * g->f.S), NT, 0, (cudaStream_t)stream>>>(*g, t, cgs, dxin_next, out, ld, S2p);
     MRSSM_LAUNCH_CHECK();
     return 0;
 }
@@ -296,7 +324,7 @@ extern "C" int mrssm_rollout_steps_fwd(const mrssm_rollout_args* a, const mrssm_
         bf16* u_t = b16(w->u_cat, ts * BU);
         bf16* hb_t = b16(w->hb_all, t * BD);
         bf16* hb_n = b16(w->hb_all, (t + 1) * BD);
-        RSTEP_TRY(mrssm_rstep_xin(a, t, KX, xin_t, stream));
+        if (t == 0) RSTEP_TRY(mrssm_rstep_xin(a, t, KX, xin_t, stream));          // later steps: written by the previous step's heads kernel
         RSTEP_TRY(gemm(st, B, xin_t, KX, KX, w->wp_sa, D, D, a->b_sa, a->act, nullptr, 0, 0, x_t, D, 0));
         RSTEP_TRY(gemm(st, B, x_t, D, D, w->wp_ih, 3 * D, 3 * D, a->b_ih, 0, nullptr, 0, 0, w->gi, 3 * D, 1));
         RSTEP_TRY(gemm(st, B, hb_t, D, D, w->wp_hh, 3 * D, 3 * D, a->b_hh, 0, nullptr, 0, 0, w->gh, 3 * D, 1));
@@ -309,7 +337,8 @@ extern "C" int mrssm_rollout_steps_fwd(const mrssm_rollout_args* a, const mrssm_
         }
         RSTEP_TRY(gemm(st, B, u_t, (long long)NH * H, NH * H, w->w2f, NH * S2p, NH * S2p, w->b2, 0, nullptr, 0, 0, w->o_cat, (long long)NH * S2p, 1,
                        nullptr, 0, S2p, H));
-        RSTEP_TRY(mrssm_rstep_heads_fwd(a, t, w->o_cat, NH * S2p, S2p, stream));
+        RSTEP_TRY(mrssm_rstep_heads_fwd(a, t, w->o_cat, NH * S2p, S2p, t + 1 < T ? (void*)b16(w->xin_all, (long long)(t + 1) * B * KX) : nullptr, KX,
+                                        stream));
     }
     return 0;
 }
@@ -332,7 +361,8 @@ extern "C" int mrssm_rollout_steps_bwd(const mrssm_rollout_bwd_args* g, const mr
         bf16* dgh_t = b16(w->d_gh, 3 * t * BD);
         bf16* dxp_t = b16(w->d_xpre, t * BD);
         for (int hd = 0; hd < MRSSM_MAX_HEADS; ++hd) d_o_ptrs[hd] = hd < NH ? (void*)(d_o_t + (long long)hd * S2p) : nullptr;
-        RSTEP_TRY(mrssm_rstep_heads_bwd(g, t, w->cgs, d_o_ptrs, NH * S2p, S2p, stream));
+        // (the state-gradient carry and g_actions[t + 1] come straight from step t + 1's dxin; the last step has no successor: cgs = 0)
+        RSTEP_TRY(mrssm_rstep_heads_bwd(g, t, w->cgs, t + 1 < T ? w->dxin : nullptr, d_o_ptrs, NH * S2p, S2p, stream));
         for (int ci = 0; ci < w->n_chunks; ++ci) {
             const int c0 = w->chunk_c0[ci], nc = w->chunk_c1[ci] - c0;
             RSTEP_TRY(gemm(st, B, d_o_t + (long long)c0 * S2p, (long long)NH * S2p, nc * S2p, w->w2b[ci], nc * H, nc * H, nullptr, 0,
@@ -343,7 +373,7 @@ extern "C" int mrssm_rollout_steps_bwd(const mrssm_rollout_bwd_args* g, const mr
         RSTEP_TRY(gemm(st, B, dgi_t, 3 * D, 3 * D, w->wp_ih_b, D, D, nullptr, 0, x_t, D, a->act, dxp_t, D, 0));
         RSTEP_TRY(gemm(st, B, dgh_t, 3 * D, 3 * D, w->wp_hh_b, D, D, nullptr, 0, nullptr, 0, 0, w->carry_b, D, 1));
         RSTEP_TRY(gemm(st, B, dxp_t, D, D, w->wp_sa_b, w->KXo, S + A, nullptr, 0, nullptr, 0, 0, w->dxin, S + A, 1));
-        RSTEP_TRY(mrssm_rstep_xin_bwd(g, t, w->dxin, S + A, w->cgs, stream));
     }
+    RSTEP_TRY(mrssm_rstep_xin_bwd(g, 0, w->dxin, S + A, w->cgs, stream));      // step 0's dxin: gradient of prev_state, g_actions[0]
     return mrssm_add2(w->carry_a, w->carry_b, BD, w->g_prev_belief, stream);
 }

@@ -173,8 +173,8 @@ SYMBOLS = {
     "mrssm_rollout_bwd": [C.POINTER(RolloutBwdArgs), _vp],
     "mrssm_rstep_xin": [C.POINTER(RolloutArgs), _i32, _i32, _vp, _vp],
     "mrssm_rstep_gate_fwd": [C.POINTER(RolloutArgs), _i32, _vp, _vp, _vp, _vp],
-    "mrssm_rstep_heads_fwd": [C.POINTER(RolloutArgs), _i32, _vp, _i32, _i32, _vp],
-    "mrssm_rstep_heads_bwd": [C.POINTER(RolloutBwdArgs), _i32, _vp, C.POINTER(_vp), _i32, _i32, _vp],
+    "mrssm_rstep_heads_fwd": [C.POINTER(RolloutArgs), _i32, _vp, _i32, _i32, _vp, _i32, _vp],
+    "mrssm_rstep_heads_bwd": [C.POINTER(RolloutBwdArgs), _i32, _vp, _vp, C.POINTER(_vp), _i32, _i32, _vp],
     "mrssm_rstep_gate_bwd": [C.POINTER(RolloutBwdArgs), _i32, _vp, _vp, _vp, _vp, _vp, _vp],
     "mrssm_rstep_xin_bwd": [C.POINTER(RolloutBwdArgs), _i32, _vp, _i32, _vp, _vp],
     "mrssm_add2": [_vp, _vp, _i64, _vp, _vp],

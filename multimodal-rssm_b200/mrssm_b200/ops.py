@@ -527,7 +527,7 @@ def _rollout_steps_fwd(a, spec, E, T, B, w_sa, b_sa, w_ih, w_hh, b_ih, b_hh, hea
         macs = (S + A) * D + 6 * D * D + NH * (D * H + H * 2 * S)
         work = dict(flops=2.0 * macs * T * B, bytes=0.0)
     L.call("mrssm_rollout_steps_fwd", C.byref(a), C.byref(w), tag="rollout_steps_fwd", work=work)
-    L.kernel_launches += T * (7 + w.n_chunks) - 1
+    L.kernel_launches += T * (6 + w.n_chunks)            # (+ the one L.call counts: the t = 0 xin kernel)
     return [hb_all, xin_all]
 
 
@@ -591,7 +591,7 @@ def _rollout_steps_bwd(ctx, ins, embs, outs, st, gouts):
         macs = (S + A) * D + 6 * D * D + NH * (D * H + H * 2 * S)
         work = dict(flops=2.0 * macs * T * B, bytes=0.0)
     L.call("mrssm_rollout_steps_bwd", C.byref(g), C.byref(w), tag="rollout_steps_bwd", work=work)
-    L.kernel_launches += T * (7 + w.n_chunks)
+    L.kernel_launches += T * (6 + w.n_chunks) + 1        # (+ xin_bwd of step 0; the one L.call counts: add2)
     g_prev_state = cgs
 
     # deferred, time-parallel weight gradients: dW += dY^T X over all (t, b) rows, bf16 operands as they are
