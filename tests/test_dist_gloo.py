@@ -102,7 +102,7 @@ class _Mod:
         return self._p
 
 
-def _bucket_worker(rank, world, port, q):
+def _bucket_worker(rank, world, port, q, late_decoder=False):
     for p in (ROOT, os.path.join(ROOT, "multimodal-rssm_b200")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -140,8 +140,15 @@ def _bucket_worker(rank, world, port, q):
         @staticmethod
         def backward(ctx, g):
             (x,) = ctx.saved_tensors
-            ctx.p.grad += g.sum() * x
+            if late_decoder and ctx.p is params["decoder"]:
+                # like the product in bf16 mode: the decoder's weight gradient is only QUEUED here (ops.side_defer) and lands
+                # when the side stream is joined, after backward
+                deferred.append((ctx.p, g.sum() * x))
+            else:
+                ctx.p.grad += g.sum() * x
             return g.sum() * ctx.p.detach(), None, None
+
+    deferred = []
 
     def run(dp_):
         opt.flat_g.zero_()
@@ -157,12 +164,21 @@ def _bucket_worker(rank, world, port, q):
         params["reward"].grad += float(rank + 1)
 
     run(None)
+    for p_, g_ in deferred:
+        p_.grad += g_
+    deferred.clear()
     local = opt.flat_g.clone()                          # this rank's gradient, no exchange
     order = []
     orig = dp._launch
     dp._launch = lambda name, final=False: (order.append(name), orig(name, final=final))[1]
+    if late_decoder:
+        from mrssm_b200 import ops
+        ops.side_pending = lambda: bool(deferred)            # what ops reports while weight gradients are queued / in flight
     run(dp)
     launched_in_backward = list(order)
+    for p_, g_ in deferred:                                  # ops.side_wgrad_scope's exit: the queued gradients have landed
+        p_.grad += g_
+    deferred.clear()
     dp.all_reduce_grads(opt)
     q.put((rank, local, opt.flat_g.clone(), launched_in_backward, dp.last_order))
     dist.barrier()
@@ -238,3 +254,24 @@ def test_optimizer_rebuilt_after_attach_is_rebound_gloo():
     torch.testing.assert_close(s0, s1)
     torch.testing.assert_close(second[0][1], second[1][1])
     assert second[0][4] == second[1][4] == 0.5
+
+
+def test_decoder_bucket_waits_for_side_stream_weight_gradients_gloo():
+    """bf16 mode queues the decoder's weight gradients for a side stream (ops.side_defer) and joins it after backward: while they are
+    pending the decoder bucket must NOT go out from its autograd hook (it would exchange a buffer its kernels have not written); it is
+    exchanged from all_reduce_grads instead, and the result is still the SUM over ranks."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, l0, s0, in_bwd0, ord0), (_, l1, s1, in_bwd1, ord1) = out
+    assert in_bwd0 == in_bwd1 == ["decoder", "transition"]          # both hooks fired ...
+    assert ord0 == ord1 == ["transition", "decoder", "encoder"]     # ... but the decoder bucket was held back until the join
+    torch.testing.assert_close(s0, s1)
+    torch.testing.assert_close(s0, l0 + l1)
