@@ -366,6 +366,8 @@ typedef struct mrssm_rstep_ws {
     void* d_o; void* du_all; void* d_gi; void* d_gh; void* d_xpre;
     float* dh_heads; float* carry_a; float* carry_b; float* dxin; float* cgs; float* g_prev_belief;
 } mrssm_rstep_ws;
+/* (the W_hh GEMM of a step is off the step's dependency chain and runs on a second, internal stream; 0 switches that off) */
+int mrssm_rstep_set_aux_stream(int32_t on);
 int mrssm_rollout_steps_fwd(const mrssm_rollout_args* a, const mrssm_rstep_ws* w, void* stream);
 int mrssm_rollout_steps_bwd(const mrssm_rollout_bwd_args* g, const mrssm_rstep_ws* w, void* stream);
 

@@ -302,7 +302,31 @@ inline int gemm(cudaStream_t st, int M, const void* A, long long lda, int K, con
                            gn, gk);
 }
 inline bf16* b16(void* p, long long off) { return (bf16*)p + off; }
+
+// A second stream for the one GEMM of a step that does not sit on the step's dependency chain: W_hh h_{t-1} (forward; needed only by
+// the gate kernel) and d_gh W_hh (backward; needed only by the previous step's gate kernel).  One process drives one GPU.
+struct Aux {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool ok = false;
+};
+Aux& aux_stream() {
+    static Aux a = [] {
+        Aux x;
+        x.ok = cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) == cudaSuccess &&
+               cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) == cudaSuccess;
+        return x;
+    }();
+    return a;
+}
+bool g_step_aux = true;
 }  // namespace
+
+extern "C" int mrssm_rstep_set_aux_stream(int32_t on) {
+    g_step_aux = on != 0;
+    return 0;
+}
 
 #define RSTEP_TRY(expr)             \
     do {                            \
@@ -317,18 +341,35 @@ extern "C" int mrssm_rollout_steps_fwd(const mrssm_rollout_args* a, const mrssm_
     cudaStream_t st = (cudaStream_t)stream;
     const int T = a->T, B = a->B, D = a->D, H = a->H, NH = w->NH, KX = w->KX, S2p = w->S2p;
     const long long BD = (long long)B * D, BU = (long long)B * NH * H;
+    Aux& ax = aux_stream();
+    const bool use_aux = g_step_aux && ax.ok;
+    auto gh_gemm = [&](cudaStream_t s_, int t_) {
+        return gemm(s_, B, b16(w->hb_all, t_ * BD), D, D, w->wp_hh, 3 * D, 3 * D, a->b_hh, 0, nullptr, 0, 0, w->gh, 3 * D, 1);
+    };
+    if (use_aux) {          // W_hh h_{-1} for step 0, off the chain
+        MRSSM_CUDA(cudaEventRecord(ax.fork, st));
+        MRSSM_CUDA(cudaStreamWaitEvent(ax.s, ax.fork, 0));
+        RSTEP_TRY(gh_gemm(ax.s, 0));
+        MRSSM_CUDA(cudaEventRecord(ax.join, ax.s));
+    }
     for (int t = 0; t < T; ++t) {
         const int ts = w->keep_all ? t : 0;
         bf16* xin_t = b16(w->xin_all, (long long)t * B * KX);
         bf16* x_t = b16(w->x_all, ts * BD);
         bf16* u_t = b16(w->u_cat, ts * BU);
-        bf16* hb_t = b16(w->hb_all, t * BD);
         bf16* hb_n = b16(w->hb_all, (t + 1) * BD);
         if (t == 0) RSTEP_TRY(mrssm_rstep_xin(a, t, KX, xin_t, stream));          // later steps: written by the previous step's heads kernel
         RSTEP_TRY(gemm(st, B, xin_t, KX, KX, w->wp_sa, D, D, a->b_sa, a->act, nullptr, 0, 0, x_t, D, 0));
         RSTEP_TRY(gemm(st, B, x_t, D, D, w->wp_ih, 3 * D, 3 * D, a->b_ih, 0, nullptr, 0, 0, w->gi, 3 * D, 1));
-        RSTEP_TRY(gemm(st, B, hb_t, D, D, w->wp_hh, 3 * D, 3 * D, a->b_hh, 0, nullptr, 0, 0, w->gh, 3 * D, 1));
+        if (use_aux) MRSSM_CUDA(cudaStreamWaitEvent(st, ax.join, 0));          // W_hh h_{t-1} has run beside the kernels above
+        else RSTEP_TRY(gh_gemm(st, t));
         RSTEP_TRY(mrssm_rstep_gate_fwd(a, t, w->gi, w->gh, hb_n, stream));
+        if (use_aux && t + 1 < T) {          // the next step's W_hh h_t beside this step's heads and the next step's W_sa, W_ih GEMMs
+            MRSSM_CUDA(cudaEventRecord(ax.fork, st));
+            MRSSM_CUDA(cudaStreamWaitEvent(ax.s, ax.fork, 0));
+            RSTEP_TRY(gh_gemm(ax.s, t + 1));
+            MRSSM_CUDA(cudaEventRecord(ax.join, ax.s));
+        }
         for (int ci = 0; ci < w->n_chunks; ++ci) {
             const int c0 = w->chunk_c0[ci], n = (w->chunk_c1[ci] - c0) * H;
             const float* add = w->pre_cat ? w->pre_cat + ((long long)t * B * NH * H + (long long)c0 * H) : nullptr;
@@ -352,6 +393,9 @@ extern "C" int mrssm_rollout_steps_bwd(const mrssm_rollout_bwd_args* g, const mr
     const int T = a->T, B = a->B, D = a->D, H = a->H, S = a->S, A = a->A, NH = w->NH, S2p = w->S2p;
     const long long BD = (long long)B * D, BU = (long long)B * NH * H, BO = (long long)B * NH * S2p;
     void* d_o_ptrs[MRSSM_MAX_HEADS];
+    Aux& ax = aux_stream();
+    const bool use_aux = g_step_aux && ax.ok;
+    bool pending = false;                     // a d_gh W_hh GEMM is in flight on the second stream
     for (int t = T - 1; t >= 0; --t) {
         bf16* d_o_t = b16(w->d_o, t * BO);
         bf16* du_t = b16(w->du_all, t * BU);
@@ -369,11 +413,24 @@ extern "C" int mrssm_rollout_steps_bwd(const mrssm_rollout_bwd_args* g, const mr
                            u_t + (long long)c0 * H, (long long)NH * H, a->act, du_t + (long long)c0 * H, (long long)NH * H, 0, nullptr, 0, H, S2p));
         }
         RSTEP_TRY(gemm(st, B, du_t, (long long)NH * H, NH * H, w->w1b, D, D, nullptr, 0, nullptr, 0, 0, w->dh_heads, D, 1));
+        if (pending) {                           // carry_b = d_gh W_hh of step t + 1
+            MRSSM_CUDA(cudaStreamWaitEvent(st, ax.join, 0));
+            pending = false;
+        }
         RSTEP_TRY(mrssm_rstep_gate_bwd(g, t, w->dh_heads, w->carry_a, w->carry_b, dgi_t, dgh_t, stream));
+        if (use_aux) {                           // d_gh W_hh feeds only the previous step's gate kernel: beside the W_ih / W_sa dgrads and the heads of step t - 1
+            MRSSM_CUDA(cudaEventRecord(ax.fork, st));
+            MRSSM_CUDA(cudaStreamWaitEvent(ax.s, ax.fork, 0));
+            RSTEP_TRY(gemm(ax.s, B, dgh_t, 3 * D, 3 * D, w->wp_hh_b, D, D, nullptr, 0, nullptr, 0, 0, w->carry_b, D, 1));
+            MRSSM_CUDA(cudaEventRecord(ax.join, ax.s));
+            pending = true;
+        } else {
+            RSTEP_TRY(gemm(st, B, dgh_t, 3 * D, 3 * D, w->wp_hh_b, D, D, nullptr, 0, nullptr, 0, 0, w->carry_b, D, 1));
+        }
         RSTEP_TRY(gemm(st, B, dgi_t, 3 * D, 3 * D, w->wp_ih_b, D, D, nullptr, 0, x_t, D, a->act, dxp_t, D, 0));
-        RSTEP_TRY(gemm(st, B, dgh_t, 3 * D, 3 * D, w->wp_hh_b, D, D, nullptr, 0, nullptr, 0, 0, w->carry_b, D, 1));
         RSTEP_TRY(gemm(st, B, dxp_t, D, D, w->wp_sa_b, w->KXo, S + A, nullptr, 0, nullptr, 0, 0, w->dxin, S + A, 1));
     }
+    if (pending) MRSSM_CUDA(cudaStreamWaitEvent(st, ax.join, 0));
     RSTEP_TRY(mrssm_rstep_xin_bwd(g, 0, w->dxin, S + A, w->cgs, stream));      // step 0's dxin: gradient of prev_state, g_actions[0]
     return mrssm_add2(w->carry_a, w->carry_b, BD, w->g_prev_belief, stream);
 }

@@ -178,6 +178,7 @@ SYMBOLS = {
     "mrssm_rstep_gate_bwd": [C.POINTER(RolloutBwdArgs), _i32, _vp, _vp, _vp, _vp, _vp, _vp],
     "mrssm_rstep_xin_bwd": [C.POINTER(RolloutBwdArgs), _i32, _vp, _i32, _vp, _vp],
     "mrssm_add2": [_vp, _vp, _i64, _vp, _vp],
+    "mrssm_rstep_set_aux_stream": [_i32],
     "mrssm_rollout_steps_fwd": [C.POINTER(RolloutArgs), C.POINTER(RstepWs), _vp],
     "mrssm_rollout_steps_bwd": [C.POINTER(RolloutBwdArgs), C.POINTER(RstepWs), _vp],
     "mrssm_gconv_fwd": [C.POINTER(GConvArgs), _vp],
